@@ -1,0 +1,239 @@
+/*
+ * jl_b200.h — C ABI of libjl_b200.so: the B200 (sm_100a) kernels behind the
+ * Jiao-Liao ASR forward + adapter fine-tune hot path.
+ *
+ * The reference (mixxs/Jiao-Liao_Speech_Recognition) publishes no code and
+ * therefore no FFI of its own (/root/reference/README.md:3); its hot path runs
+ * inside the Python dependencies it pins (/root/reference/requirements.txt:75,78,81).
+ * Each entry point below names the dependency function it replaces
+ * (SP = site-packages of the build container).
+ *
+ * Conventions:
+ *  - plain C, POD parameter structs, raw DEVICE pointers, sizes and element strides;
+ *  - the caller owns every buffer including workspace; the library never allocates or
+ *    frees device memory and keeps no pointer after the call returns;
+ *  - every call enqueues its work on `stream` (a cudaStream_t passed as void*) and
+ *    returns without synchronising;
+ *  - return 0 (JL_OK) or a negative error code; text via jl_last_error() (thread-local);
+ *  - no CPU fallback: a device that is not sm_100 gives JL_EUNSUPPORTED.
+ */
+#ifndef JL_B200_H
+#define JL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JL_VERSION 1
+
+enum {
+  JL_OK = 0,
+  JL_EINVAL = -1,            /* bad argument (null pointer, negative size, misalignment) */
+  JL_EUNSUPPORTED_SHAPE = -2,/* shape outside what the kernel was built for */
+  JL_ECUDA = -3,             /* CUDA runtime / driver error at launch */
+  JL_EUNSUPPORTED = -4       /* not an sm_100 device */
+};
+
+enum { JL_DT_BF16 = 0, JL_DT_F32 = 1 };
+
+int jl_version(void);
+const char* jl_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t jl_launch_count(void);
+void jl_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1 + a2: 80-bin Kaldi log-mel filterbank + utterance CMVN.
+ * Replaces SP/torchaudio/compliance/kaldi.py:514-645 (fbank) as called from
+ * SP/transformers/models/speech_to_text/feature_extraction_speech_to_text.py:104-120, and
+ * utterance_cmvn / pad / attention-mask at :142-163, :275-303.
+ * ------------------------------------------------------------------------------------------ */
+#define JL_MEL_BINS 80
+#define JL_MEL_MAXW 32       /* widest triangular filter in FFT bins */
+#define JL_MEL_FRAMES_PER_CTA 32
+typedef struct {
+  const float* wave;          /* [batch, wave_stride] fp32 in [-1, 1], 16 kHz */
+  int64_t wave_stride;        /* elements between utterances */
+  const int32_t* num_samples; /* [batch] valid samples per utterance */
+  int32_t batch;
+  int32_t max_frames;         /* F of the output (>= frames of the longest utterance) */
+  const float* window;        /* [400] povey window (host-built, fp32) */
+  const float* twiddle;       /* [512, 2] (cos, -sin)(2*pi*k/512), k = 0..511 (host-built from float64) */
+  const int32_t* mel_lo;      /* [80] first FFT bin of each filter */
+  const int32_t* mel_cnt;     /* [80] number of FFT bins (<= JL_MEL_MAXW) */
+  const float* mel_w;         /* [80, JL_MEL_MAXW] weights, zero padded */
+  float* feats;               /* [batch, max_frames, 80] fp32 out (CMVN'd, padded frames = 0) */
+  void* feats_bf16;           /* optional bf16 copy of feats, same shape (may be NULL) */
+  int32_t* attention_mask;    /* [batch, max_frames] int32 out (may be NULL) */
+  int32_t* frame_lengths;     /* [batch] int32 out: valid frames per utterance */
+  int32_t apply_cmvn;         /* 1 = CMVN (default path); 0 = raw log-mel (tests) */
+} jl_mel_cmvn_params;
+int jl_mel_cmvn_workspace_bytes(const jl_mel_cmvn_params* p, size_t* out);
+int jl_mel_cmvn_fwd(const jl_mel_cmvn_params* p, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05 tensor cores:  C[M,N] = epilogue(alpha * A[M,K] · B[N,K]^T + bias)
+ * A and B are K-contiguous by default (nn.Linear layout); see a_layout / b_layout.  Replaces torch.nn.functional.linear as used by
+ * SP/transformers/models/wav2vec2/modeling_wav2vec2.py:495-498,524-528,547 (q/k/v/out),
+ * :557-573 (FFN), :1708 (lm_head), and (through im2col) the Conv1d at
+ * SP/transformers/models/speech_to_text/modeling_speech_to_text.py:82-99.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  JL_EPI_NONE = 0,
+  JL_EPI_GELU = 1,      /* erf GELU; if aux_out != NULL the pre-activation is stored there (bf16) */
+  JL_EPI_RELU = 2,
+  JL_EPI_GELU_BWD = 3,  /* C = acc * gelu'(aux)          (aux = saved pre-activation, bf16) */
+  JL_EPI_RELU_BWD = 4,  /* C = acc * (aux > 0)           (aux = saved post-activation, bf16) */
+  JL_EPI_GLU = 5        /* C[:, j] = v[2j] * sigmoid(v[2j+1]); C has N/2 columns (interleaved weight rows) */
+};
+enum {
+  JL_LAYOUT_K = 0,      /* operand stored with K contiguous:  A[M, K] / B[N, K]  (nn.Linear layout) */
+  JL_LAYOUT_MN = 1      /* operand stored with M (or N) contiguous:  A as [K, M] / B as [K, N]  */
+};
+typedef struct {
+  const void* a; int64_t lda;        /* bf16, row stride lda elements (multiple of 8); [M, K] or [K, M] per a_layout */
+  const void* b; int64_t ldb;        /* bf16, [N, K] or [K, N] per b_layout */
+  int32_t a_layout, b_layout;        /* JL_LAYOUT_K | JL_LAYOUT_MN — MN lets dgrad (dY·W) and wgrad (dYᵀ·X) run without transposed copies */
+  void* c; int64_t ldc;              /* [M, N] (N/2 columns for GLU), dtype out_dtype */
+  const float* bias;                 /* [N] fp32 or NULL */
+  const void* residual; int64_t ldr; /* bf16 [M, N] added after the epilogue op, or NULL */
+  const void* aux; int64_t ldaux;    /* bf16 [M, N] epilogue input (GELU_BWD / RELU_BWD) or NULL */
+  void* aux_out; int64_t ldaux_out;  /* bf16 [M, N] pre-activation out (GELU) or NULL */
+  const int32_t* row_lengths;        /* optional [M / rows_per_seq]: rows t >= length are written as 0 */
+  int32_t rows_per_seq;
+  int32_t m, n, k;
+  int32_t epilogue;
+  int32_t out_dtype;                 /* JL_DT_BF16 | JL_DT_F32 */
+  float alpha;
+} jl_gemm_params;
+int jl_gemm_bf16(const jl_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (eps 1e-5).  Replaces nn.LayerNorm at
+ * SP/transformers/models/wav2vec2/modeling_wav2vec2.py:623,625,639,645,792,941.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x; int64_t ldx;     /* bf16 [rows, d] */
+  const float* gamma; const float* beta;
+  void* y; int64_t ldy;           /* bf16 [rows, d] */
+  float* mean; float* rstd;       /* [rows] fp32 out (NULL in inference) */
+  int32_t rows, d;
+  float eps;
+} jl_layernorm_fwd_params;
+int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream);
+
+typedef struct {
+  const void* dy; int64_t lddy;   /* bf16 [rows, d] */
+  const void* x; int64_t ldx;     /* bf16 [rows, d] forward input */
+  const float* gamma;
+  const float* mean; const float* rstd;
+  const void* dres; int64_t lddres; /* optional bf16 [rows, d] added to dx (the residual branch grad) */
+  void* dx; int64_t lddx;         /* bf16 [rows, d] */
+  float* dgamma; float* dbeta;    /* optional fp32 [d] (trainable adapter norms); NULL for frozen */
+  float* partial;                 /* workspace fp32 [2, nblk, d] when dgamma != NULL */
+  int32_t rows, d;
+} jl_layernorm_bwd_params;
+int jl_layernorm_bwd_workspace_bytes(const jl_layernorm_bwd_params* p, size_t* out);
+int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-attention softmax(Q K^T * scale + keymask) V per (utterance, head), head_dim 64.
+ * Replaces the eager math at SP/transformers/models/wav2vec2/modeling_wav2vec2.py:438-463
+ * (never materialises the [B,H,T,T] scores); also the AttAdapter attention (heads = 1).
+ * q/k/v/o rows are (b*seq + t); head h occupies columns [h*64, h*64+64).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q; const void* k; const void* v; int64_t ld_qkv;  /* bf16, common row stride */
+  void* o; int64_t ld_o;                                         /* bf16 [B*seq, heads*64] */
+  float* lse;                     /* [B, heads, seq] fp32 (log-sum-exp of scaled scores) or NULL */
+  const int32_t* lengths;         /* [B] valid frames (keys >= length masked; query rows >= length output 0) */
+  int32_t batch, seq, heads;
+  float scale;
+} jl_attn_fwd_params;
+int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream);
+
+typedef struct {
+  const void* q; const void* k; const void* v; int64_t ld_qkv;
+  const void* o; const void* d_o; int64_t ld_o;
+  const float* lse;
+  void* dq; void* dk; void* dv; int64_t ld_dqkv;   /* bf16 */
+  float* delta;                   /* workspace [B, heads, seq] fp32 */
+  const int32_t* lengths;
+  int32_t batch, seq, heads;
+  float scale;
+} jl_attn_bwd_params;
+int jl_attn_bwd(const jl_attn_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9: fused log-softmax + CTC loss (+ gradient w.r.t. the logits).  Replaces
+ * SP/transformers/models/wav2vec2/modeling_wav2vec2.py:1711-1736 →
+ * SP/torch/nn/functional.py:3042-3115 (ctc_loss) incl. the log_softmax pass.
+ * ------------------------------------------------------------------------------------------ */
+enum { JL_CTC_SUM = 0, JL_CTC_MEAN = 1 };
+typedef struct {
+  const void* logits; int64_t ld_logits;  /* [B*seq, V] rows, dtype logits_dtype */
+  int32_t logits_dtype;
+  const int32_t* labels; int32_t max_label_len;   /* [B, max_label_len], negative = padding */
+  const int32_t* input_lengths;           /* [B] valid frames */
+  int32_t batch, seq, vocab, blank;
+  int32_t reduction, zero_infinity;
+  float* nll;                             /* [B] fp32 out: per-utterance −log p (0 if zero_infinity hit) */
+  float* loss;                            /* [1] fp32 out: reduced loss */
+  void* grad; int64_t ld_grad;            /* optional [B*seq, V] d loss / d logits, dtype grad_dtype */
+  int32_t grad_dtype;
+} jl_ctc_params;
+int jl_ctc_workspace_bytes(const jl_ctc_params* p, size_t* out);
+int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a10: greedy CTC decode — argmax over V (first max wins), drop frames >= length, collapse
+ * consecutive repeats, drop blank.  Replaces torch.argmax + the Python groupby at
+ * SP/transformers/models/wav2vec2/tokenization_wav2vec2.py:310-317.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* logits; int64_t ld_logits; int32_t logits_dtype;
+  const int32_t* input_lengths;
+  int32_t batch, seq, vocab, blank;
+  int32_t* frame_ids;     /* workspace/out [B, seq] per-frame argmax */
+  int32_t* out_ids;       /* [B, seq] compacted ids (tail = -1) */
+  int32_t* out_lengths;   /* [B] */
+} jl_ctc_greedy_params;
+int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-movement / elementwise helpers on the path.
+ * ------------------------------------------------------------------------------------------ */
+/* im2col for Conv1d(k=5, s=2, p=2) over [B, t_in, c] bf16 → [B*t_out, 5*c] bf16 (tap-major). */
+int jl_im2col_k5s2(const void* x, void* out, int32_t batch, int32_t t_in, int32_t c, int32_t t_out, void* stream);
+/* h[b,t,:] = h[b,t,:] * scale + pos[t+2,:] for t < len_b;  h[b,t,:] = 0 for t >= len_b
+ * (modeling_speech_to_text.py:542,568-579; pos_table is the host-built [seq + 2, d] fp32 sinusoid table, :123-139) */
+int jl_embed_positions(void* h, float scale, const float* pos_table, const int32_t* lengths, int32_t batch, int32_t seq,
+                       int32_t d, void* stream);
+int jl_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
+/* out[n] (+)= sum_m x[m, n]  (bias gradients) */
+int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, float* partial, void* stream);
+int jl_colsum_workspace_bytes(int32_t rows, int32_t cols, size_t* out);
+int jl_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+int jl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* Fused AdamW over one flat fp32 bucket (adapter + lm_head parameters); also refreshes the bf16
+ * shadow copy the kernels read.  grad is multiplied by grad_scale first (1/world after allreduce). */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; void* param_bf16;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  int32_t step;
+} jl_adamw_params;
+int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
+
+/* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
+ * sizes the CPU oracle cannot reach; never called by the product path. */
+int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JL_B200_H */

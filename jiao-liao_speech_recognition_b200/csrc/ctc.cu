@@ -1,0 +1,456 @@
+// a9 + a10: fused log-softmax + CTC loss/gradient, and the greedy collapse decoder.
+//
+// Replaces SP/transformers/models/wav2vec2/modeling_wav2vec2.py:1711-1736 (labels >= 0 selection, fp32 log_softmax,
+// ctc_loss with blank = pad_token_id, reduction, zero_infinity) → SP/torch/nn/functional.py:3042-3115, and the
+// argmax + groupby collapse + pad strip of SP/transformers/models/wav2vec2/tokenization_wav2vec2.py:310-317.
+//
+// HBM-bound design: the [B·T, V] logits are streamed once per pass with 16-byte loads, one warp per frame:
+//   ctc_prep        compact the labels (>= 0) per utterance, target lengths
+//   ctc_row_stats   online max / log-sum-exp over V by warp shuffle (+ first-max argmax for greedy), then gathers the
+//                   2S+1 extended-label log-probs of the frame while the row is still hot in L1/L2
+//   ctc_lattice     one CTA per utterance: alpha (threads 0-511) and beta (threads 512-1023) recursions run
+//                   concurrently over the gathered log-probs, one barrier per frame, rows double-buffered in smem
+//   ctc_grad        one CTA per frame: grad = softmax − Σ_{s: l'_s = v} exp(α+β−lp+nll); duplicate labels are combined in
+//                   fixed order in shared memory (deterministic — no float atomics), the row is written once
+//   ctc_reduce      reduction "sum" | "mean" and zero_infinity
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace jl {
+
+constexpr int CTC_LATTICE_HALF = 512;
+constexpr int CTC_GRAD_THREADS = 256;
+
+struct CtcWs {
+  int32_t* labels;   // [B, Smax] compacted
+  int32_t* tlen;     // [B]
+  float* lse;        // [B*T]
+  float* lpx;        // [B, T, L]
+  float* alpha;      // [B, T, L]
+  float* beta;       // [B, T, L]
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static CtcWs carve_ws(const jl_ctc_params* p, void* ws, size_t* total) {
+  const size_t B = p->batch, T = p->seq, S = p->max_label_len > 0 ? p->max_label_len : 1, L = 2 * S + 1;
+  size_t off = 0;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  CtcWs w;
+  w.labels = reinterpret_cast<int32_t*>(base + off); off += align256(B * S * 4);
+  w.tlen = reinterpret_cast<int32_t*>(base + off); off += align256(B * 4);
+  w.lse = reinterpret_cast<float*>(base + off); off += align256(B * T * 4);
+  w.lpx = reinterpret_cast<float*>(base + off); off += align256(B * T * L * 4);
+  w.alpha = reinterpret_cast<float*>(base + off); off += align256(B * T * L * 4);
+  w.beta = reinterpret_cast<float*>(base + off); off += align256(B * T * L * 4);
+  if (total) *total = off;
+  return w;
+}
+
+__global__ void ctc_prep_kernel(const int32_t* __restrict__ labels, int smax, int vocab, int32_t* __restrict__ out_labels,
+                                int32_t* __restrict__ tlen) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  int n = 0;
+  for (int j = 0; j < smax; ++j) {
+    const int v = labels[static_cast<int64_t>(b) * smax + j];
+    if (v >= 0) out_labels[static_cast<int64_t>(b) * smax + n++] = min(v, vocab - 1);   // range is validated on the host
+  }
+  tlen[b] = n;
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_logit(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float ld_logit<float>(const float* p, int64_t i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float ld_logit<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+
+__device__ __forceinline__ void online_update(float x, int idx, float& m, float& s, float& best, int& besti) {
+  if (x > best) { best = x; besti = idx; }
+  if (x > m) {
+    s = s * expf(m - x) + 1.0f;
+    m = x;
+  } else {
+    s += expf(x - m);
+  }
+}
+
+// One warp per frame row.  lse / frame_ids / lpx may each be null.
+template <typename T>
+__global__ void __launch_bounds__(256) ctc_row_stats_kernel(const T* __restrict__ logits, int64_t ld, int rows, int seq, int vocab,
+                                                            const int32_t* __restrict__ lengths, float* __restrict__ lse_out,
+                                                            int32_t* __restrict__ frame_ids, const int32_t* __restrict__ labels, int smax,
+                                                            const int32_t* __restrict__ tlen, int blank, float* __restrict__ lpx) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = row / seq, t = row - b * seq;
+  if (t >= lengths[b]) {
+    if (lane == 0) {
+      if (lse_out) lse_out[row] = 0.0f;
+      if (frame_ids) frame_ids[row] = -1;
+    }
+    return;
+  }
+  const T* x = logits + static_cast<int64_t>(row) * ld;
+  float m = -CUDART_INF_F, s = 0.0f, best = -CUDART_INF_F;
+  int besti = 0x7fffffff;
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = ((ld % VEC) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  if (vec_ok) {
+    const int nvec = vocab / VEC;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    for (int i = lane; i < nvec; i += 32) {
+      const uint4 v = __ldg(xv + i);
+      if constexpr (sizeof(T) == 4) {
+        online_update(__uint_as_float(v.x), i * 4 + 0, m, s, best, besti);
+        online_update(__uint_as_float(v.y), i * 4 + 1, m, s, best, besti);
+        online_update(__uint_as_float(v.z), i * 4 + 2, m, s, best, besti);
+        online_update(__uint_as_float(v.w), i * 4 + 3, m, s, best, besti);
+      } else {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w[q]);
+          online_update(f.x, i * 8 + 2 * q, m, s, best, besti);
+          online_update(f.y, i * 8 + 2 * q + 1, m, s, best, besti);
+        }
+      }
+    }
+    for (int i = nvec * VEC + lane; i < vocab; i += 32) online_update(ld_logit<T>(x, i), i, m, s, best, besti);
+  } else {
+    for (int i = lane; i < vocab; i += 32) online_update(ld_logit<T>(x, i), i, m, s, best, besti);
+  }
+  // warp combine: (m, s) by rescaling; argmax with "first max wins"
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
+    const float mm = fmaxf(m, m2);
+    const float sa = (m == -CUDART_INF_F) ? 0.0f : s * expf(m - mm);
+    const float sb = (m2 == -CUDART_INF_F) ? 0.0f : s2 * expf(m2 - mm);
+    s = sa + sb;
+    m = mm;
+    if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+  }
+  const float lse = m + logf(s);
+  if (lane == 0) {
+    if (lse_out) lse_out[row] = lse;
+    if (frame_ids) frame_ids[row] = besti;
+  }
+  if (lpx != nullptr) {
+    const int S = tlen[b];
+    const int L = 2 * S + 1;
+    const int Lmax = 2 * smax + 1;
+    float* dst = lpx + static_cast<int64_t>(row) * Lmax;
+    for (int sidx = lane; sidx < L; sidx += 32) {
+      const int c = (sidx & 1) ? labels[static_cast<int64_t>(b) * smax + (sidx >> 1)] : blank;
+      dst[sidx] = ld_logit<T>(x, c) - lse;
+    }
+  }
+}
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// One CTA per utterance; threads [0, 512) run alpha forward in time, threads [512, 1024) run beta backward.
+__global__ void __launch_bounds__(2 * CTC_LATTICE_HALF) ctc_lattice_kernel(const int32_t* __restrict__ labels, int smax,
+                                                                           const int32_t* __restrict__ tlen,
+                                                                           const int32_t* __restrict__ lengths, int seq, int blank,
+                                                                           const float* __restrict__ lpx, float* __restrict__ alpha,
+                                                                           float* __restrict__ beta, float* __restrict__ nll) {
+  extern __shared__ float lat_smem[];
+  const int b = blockIdx.x;
+  const int S = tlen[b];
+  const int L = 2 * S + 1;
+  const int Lmax = 2 * smax + 1;
+  const int T = min(lengths[b], seq);
+  float* a_buf = lat_smem;                 // [2][Lmax]
+  float* b_buf = lat_smem + 2 * Lmax;      // [2][Lmax]
+  int* ext = reinterpret_cast<int*>(lat_smem + 4 * Lmax);   // [Lmax]
+  const bool is_beta = threadIdx.x >= CTC_LATTICE_HALF;
+  const int gtid = threadIdx.x - (is_beta ? CTC_LATTICE_HALF : 0);
+  for (int s = threadIdx.x; s < L; s += blockDim.x) ext[s] = (s & 1) ? labels[static_cast<int64_t>(b) * smax + (s >> 1)] : blank;
+  __syncthreads();
+  if (T == 0) {
+    if (threadIdx.x == 0) nll[b] = (L > 1) ? CUDART_INF_F : 0.0f;
+    return;
+  }
+  const float* lp_b = lpx + static_cast<int64_t>(b) * seq * Lmax;
+  float* al_b = alpha + static_cast<int64_t>(b) * seq * Lmax;
+  float* be_b = beta + static_cast<int64_t>(b) * seq * Lmax;
+  float* buf = is_beta ? b_buf : a_buf;
+  float* out = is_beta ? be_b : al_b;
+
+  // t = 0 (alpha) / t = T-1 (beta)
+  {
+    const int t = is_beta ? T - 1 : 0;
+    for (int s = gtid; s < L; s += CTC_LATTICE_HALF) {
+      float v = -CUDART_INF_F;
+      if (!is_beta) {
+        if (s <= 1) v = lp_b[static_cast<int64_t>(t) * Lmax + s];
+      } else {
+        if (s >= L - 2) v = lp_b[static_cast<int64_t>(t) * Lmax + s];
+      }
+      buf[s] = v;
+      out[static_cast<int64_t>(t) * Lmax + s] = v;
+    }
+  }
+  __syncthreads();
+  for (int step = 1; step < T; ++step) {
+    const int t = is_beta ? T - 1 - step : step;
+    const float* prev = buf + ((step - 1) & 1) * Lmax;
+    float* cur = buf + (step & 1) * Lmax;
+    for (int s = gtid; s < L; s += CTC_LATTICE_HALF) {
+      const float lp = lp_b[static_cast<int64_t>(t) * Lmax + s];
+      float x0 = prev[s], x1 = -CUDART_INF_F, x2 = -CUDART_INF_F;
+      if (!is_beta) {
+        if (s >= 1) x1 = prev[s - 1];
+        if (s >= 2 && (s & 1) && ext[s] != ext[s - 2]) x2 = prev[s - 2];
+      } else {
+        if (s + 1 < L) x1 = prev[s + 1];
+        if (s + 2 < L && (s & 1) && ext[s] != ext[s + 2]) x2 = prev[s + 2];
+      }
+      const float v = lse3(x0, x1, x2) + lp;
+      cur[s] = v;
+      out[static_cast<int64_t>(t) * Lmax + s] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float* last = a_buf + ((T - 1) & 1) * Lmax;
+    const float l1 = last[L - 1];
+    const float l2 = (L > 1) ? last[L - 2] : -CUDART_INF_F;
+    nll[b] = -lse3(l1, l2, -CUDART_INF_F);
+  }
+}
+
+template <typename TG>
+__device__ __forceinline__ void st_grad(TG* p, int64_t i, float v);
+template <>
+__device__ __forceinline__ void st_grad<float>(float* p, int64_t i, float v) { p[i] = v; }
+template <>
+__device__ __forceinline__ void st_grad<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// One CTA per frame row.
+template <typename T, typename TG>
+__global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __restrict__ logits, int64_t ld, TG* __restrict__ grad, int64_t ldg,
+                                                                   int seq, int vocab, int batch, const int32_t* __restrict__ lengths,
+                                                                   const int32_t* __restrict__ labels, int smax,
+                                                                   const int32_t* __restrict__ tlen, int blank,
+                                                                   const float* __restrict__ lse_all, const float* __restrict__ lpx,
+                                                                   const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                                   const float* __restrict__ nll, int reduction, int zero_infinity) {
+  extern __shared__ float grad_smem[];
+  const int row = blockIdx.x;
+  const int b = row / seq, t = row - b * seq;
+  const int tid = threadIdx.x;
+  TG* g = grad + static_cast<int64_t>(row) * ldg;
+  const float nll_b = nll[b];
+  const bool infeasible = isinf(nll_b);
+  if (t >= lengths[b] || (infeasible && zero_infinity)) {
+    for (int v = tid; v < vocab; v += CTC_GRAD_THREADS) st_grad<TG>(g, v, 0.0f);
+    return;
+  }
+  if (infeasible) {
+    for (int v = tid; v < vocab; v += CTC_GRAD_THREADS) st_grad<TG>(g, v, CUDART_NAN_F);
+    return;
+  }
+  const int S = tlen[b];
+  const int L = 2 * S + 1;
+  const int Lmax = 2 * smax + 1;
+  float* occ = grad_smem;                               // [Lmax]
+  float* blank_part = grad_smem + Lmax;                 // [32]
+  const float scale = (reduction == JL_CTC_MEAN) ? 1.0f / (static_cast<float>(max(S, 1)) * static_cast<float>(batch)) : 1.0f;
+  const int64_t lat = static_cast<int64_t>(row) * Lmax;
+  for (int s = tid; s < L; s += CTC_GRAD_THREADS) {
+    const float e = alpha[lat + s] + beta[lat + s] - lpx[lat + s] + nll_b;
+    const float o = expf(e);
+    occ[s] = (isfinite(o)) ? o : 0.0f;
+  }
+  __syncthreads();
+  const T* x = logits + static_cast<int64_t>(row) * ld;
+  const float lse = lse_all[row];
+  // softmax part, written once
+  for (int v = tid; v < vocab; v += CTC_GRAD_THREADS) {
+    const float sm = expf(ld_logit<T>(x, v) - lse);
+    st_grad<TG>(g, v, sm * scale);
+  }
+  // blank: fixed-order sum over the even states (warp 0: strided partials in lane order, then a shuffle tree)
+  if (tid < 32) {
+    float part = 0.0f;
+    for (int s = 2 * tid; s < L; s += 64) part += occ[s];
+    part = warp_sum(part);
+    if (tid == 0) blank_part[0] = part;
+  }
+  __syncthreads();   // also orders the softmax row writes before the fix-ups below
+  // non-blank labels: the first occurrence of each label owns the (ordered) sum over its repeats
+  for (int s = 2 * tid + 1; s < L; s += 2 * CTC_GRAD_THREADS) {
+    const int c = labels[static_cast<int64_t>(b) * smax + (s >> 1)];
+    bool first = true;
+    for (int s2 = 1; s2 < s; s2 += 2)
+      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == c) { first = false; break; }
+    if (!first || c == blank) continue;
+    float tot = 0.0f;
+    for (int s2 = s; s2 < L; s2 += 2)
+      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == c) tot += occ[s2];
+    st_grad<TG>(g, c, (expf(ld_logit<T>(x, c) - lse) - tot) * scale);
+  }
+  if (tid == 0) {
+    // a label equal to the blank index folds into the blank column (degenerate but well defined)
+    float tot = blank_part[0];
+    for (int s2 = 1; s2 < L; s2 += 2)
+      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == blank) tot += occ[s2];
+    st_grad<TG>(g, blank, (expf(ld_logit<T>(x, blank) - lse) - tot) * scale);
+  }
+}
+
+__global__ void ctc_reduce_kernel(float* __restrict__ nll, const int32_t* __restrict__ tlen, int batch, int reduction, int zero_infinity,
+                                  float* __restrict__ loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float acc = 0.0f;
+  for (int b = 0; b < batch; ++b) {
+    float v = nll[b];
+    if (zero_infinity && isinf(v)) {
+      v = 0.0f;
+      nll[b] = 0.0f;
+    }
+    acc += (reduction == JL_CTC_MEAN) ? v / static_cast<float>(max(tlen[b], 1)) : v;
+  }
+  if (loss) *loss = (reduction == JL_CTC_MEAN) ? acc / static_cast<float>(batch) : acc;
+}
+
+// Greedy: collapse consecutive repeats of the per-frame argmax, drop blank, compact.  One warp per utterance.
+__global__ void ctc_collapse_kernel(const int32_t* __restrict__ frame_ids, const int32_t* __restrict__ lengths, int seq, int blank,
+                                    int32_t* __restrict__ out_ids, int32_t* __restrict__ out_lengths) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int T = min(lengths[b], seq);
+  const int32_t* ids = frame_ids + static_cast<int64_t>(b) * seq;
+  int32_t* out = out_ids + static_cast<int64_t>(b) * seq;
+  int base = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    int id = -1;
+    if (t < T) {
+      id = ids[t];
+      keep = (id != blank) && (t == 0 || ids[t - 1] != id);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[base + __popc(mask & ((1u << lane) - 1u))] = id;
+    base += __popc(mask);
+  }
+  for (int i = base + lane; i < seq; i += 32) out[i] = -1;
+  if (lane == 0) out_lengths[b] = base;
+}
+
+static int ctc_validate_common(const void* logits, const int32_t* lengths, int batch, int seq, int vocab, int blank, int dtype) {
+  JL_REQUIRE(logits && lengths, JL_EINVAL, "ctc: null logits / input_lengths");
+  JL_REQUIRE(batch > 0 && seq > 0 && vocab > 1, JL_EINVAL, "ctc: batch, seq must be positive and vocab > 1");
+  JL_REQUIRE(blank >= 0 && blank < vocab, JL_EINVAL, "ctc: blank %d outside [0, %d)", blank, vocab);
+  JL_REQUIRE(dtype == JL_DT_BF16 || dtype == JL_DT_F32, JL_EINVAL, "ctc: unknown logits dtype %d", dtype);
+  return JL_OK;
+}
+
+}  // namespace jl
+
+extern "C" {
+
+int jl_ctc_workspace_bytes(const jl_ctc_params* p, size_t* out) {
+  JL_REQUIRE(p && out, JL_EINVAL, "ctc_workspace_bytes: null argument");
+  JL_REQUIRE(p->batch > 0 && p->seq > 0 && p->max_label_len >= 0, JL_EINVAL, "ctc_workspace_bytes: bad shape");
+  jl::carve_ws(p, nullptr, out);
+  return JL_OK;
+}
+
+int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
+  JL_REQUIRE(p != nullptr, JL_EINVAL, "ctc: null params");
+  int rc = jl::ctc_validate_common(p->logits, p->input_lengths, p->batch, p->seq, p->vocab, p->blank, p->logits_dtype);
+  if (rc != JL_OK) return rc;
+  JL_REQUIRE(p->labels != nullptr || p->max_label_len == 0, JL_EINVAL, "ctc: null labels");
+  JL_REQUIRE(p->nll != nullptr && workspace != nullptr, JL_EINVAL, "ctc: nll and workspace are required");
+  JL_REQUIRE(p->reduction == JL_CTC_SUM || p->reduction == JL_CTC_MEAN, JL_EINVAL, "ctc: unknown reduction %d", p->reduction);
+  JL_REQUIRE(p->max_label_len >= 0 && 2 * p->max_label_len + 1 <= 8192, JL_EUNSUPPORTED_SHAPE, "ctc: max_label_len %d too large", p->max_label_len);
+  if (p->grad) JL_REQUIRE(p->grad_dtype == JL_DT_BF16 || p->grad_dtype == JL_DT_F32, JL_EINVAL, "ctc: unknown grad dtype");
+  rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const jl::CtcWs w = jl::carve_ws(p, workspace, nullptr);
+  const int smax = p->max_label_len > 0 ? p->max_label_len : 1;
+  const int Lmax = 2 * smax + 1;
+  const int rows = p->batch * p->seq;
+
+  if (p->max_label_len > 0) {
+    jl::ctc_prep_kernel<<<p->batch, 32, 0, s>>>(p->labels, smax, p->vocab, w.labels, w.tlen);
+    JL_CHECK_LAUNCH("ctc_prep");
+  } else {
+    cudaMemsetAsync(w.tlen, 0, sizeof(int32_t) * p->batch, s);
+  }
+  const int sblocks = jl::ceil_div(rows, 8);
+  if (p->logits_dtype == JL_DT_F32)
+    jl::ctc_row_stats_kernel<float><<<sblocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
+                                                           p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen, p->blank, w.lpx);
+  else
+    jl::ctc_row_stats_kernel<__nv_bfloat16><<<sblocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
+                                                                   p->vocab, p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen,
+                                                                   p->blank, w.lpx);
+  JL_CHECK_LAUNCH("ctc_row_stats");
+  const size_t lat_smem = static_cast<size_t>(5) * Lmax * sizeof(float);
+  if (lat_smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(jl::ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lat_smem));
+    JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "ctc: cannot reserve lattice shared memory: %s", cudaGetErrorString(e));
+  }
+  jl::ctc_lattice_kernel<<<p->batch, 2 * jl::CTC_LATTICE_HALF, lat_smem, s>>>(w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
+                                                                            w.alpha, w.beta, p->nll);
+  JL_CHECK_LAUNCH("ctc_lattice");
+  if (p->grad != nullptr) {
+    const size_t gsm = static_cast<size_t>(Lmax + 32) * sizeof(float);
+#define JL_CTC_GRAD(TL, TGR)                                                                                                           \
+  jl::ctc_grad_kernel<TL, TGR><<<rows, jl::CTC_GRAD_THREADS, gsm, s>>>(reinterpret_cast<const TL*>(p->logits), p->ld_logits,              \
+                                                                        reinterpret_cast<TGR*>(p->grad), p->ld_grad, p->seq, p->vocab,   \
+                                                                        p->batch, p->input_lengths, w.labels, smax, w.tlen, p->blank,    \
+                                                                        w.lse, w.lpx, w.alpha, w.beta, p->nll, p->reduction,             \
+                                                                        p->zero_infinity)
+    if (p->logits_dtype == JL_DT_F32 && p->grad_dtype == JL_DT_F32) JL_CTC_GRAD(float, float);
+    else if (p->logits_dtype == JL_DT_F32) JL_CTC_GRAD(float, __nv_bfloat16);
+    else if (p->grad_dtype == JL_DT_F32) JL_CTC_GRAD(__nv_bfloat16, float);
+    else JL_CTC_GRAD(__nv_bfloat16, __nv_bfloat16);
+#undef JL_CTC_GRAD
+    JL_CHECK_LAUNCH("ctc_grad");
+  }
+  jl::ctc_reduce_kernel<<<1, 32, 0, s>>>(p->nll, w.tlen, p->batch, p->reduction, p->zero_infinity, p->loss);
+  JL_CHECK_LAUNCH("ctc_reduce");
+  return JL_OK;
+}
+
+int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream) {
+  JL_REQUIRE(p != nullptr, JL_EINVAL, "ctc_greedy: null params");
+  int rc = jl::ctc_validate_common(p->logits, p->input_lengths, p->batch, p->seq, p->vocab, p->blank, p->logits_dtype);
+  if (rc != JL_OK) return rc;
+  JL_REQUIRE(p->frame_ids && p->out_ids && p->out_lengths, JL_EINVAL, "ctc_greedy: null output pointer");
+  rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = p->batch * p->seq;
+  const int sblocks = jl::ceil_div(rows, 8);
+  if (p->logits_dtype == JL_DT_F32)
+    jl::ctc_row_stats_kernel<float><<<sblocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
+                                                           p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr, p->blank, nullptr);
+  else
+    jl::ctc_row_stats_kernel<__nv_bfloat16><<<sblocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
+                                                                   p->vocab, p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr,
+                                                                   p->blank, nullptr);
+  JL_CHECK_LAUNCH("ctc_argmax");
+  jl::ctc_collapse_kernel<<<p->batch, 32, 0, s>>>(p->frame_ids, p->input_lengths, p->seq, p->blank, p->out_ids, p->out_lengths);
+  JL_CHECK_LAUNCH("ctc_collapse");
+  return JL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,572 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) fed by TMA.
+//
+//   C[M,N] = epilogue(alpha * A · Bᵀ + bias)          A: [M,K] (or [K,M]),  B: [N,K] (or [K,N]),  fp32 accumulate
+//
+// Replaces every dense contraction of the path: q/k/v/out projections, FFN, lm_head
+// (SP/transformers/models/wav2vec2/modeling_wav2vec2.py:495-498,524-528,547,557-573,1708), the two
+// Conv1d+GLU subsampling layers through im2col (SP/transformers/models/speech_to_text/
+// modeling_speech_to_text.py:82-99), the adapter projections, and — with the MN-major operand modes —
+// the dgrad (dY·W) and wgrad (dYᵀ·X) products of the adapter-only backward without transposed copies.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes → STAGES-deep smem ring (mbarrier full/empty)
+//   warp 1      MMA issuer: one elected lane issues 4 × tcgen05.mma (128 × BN × 16) per 64-wide k-block,
+//               tcgen05.commit releases the smem slot / publishes the accumulator
+//   warp 2      TMEM allocator (2 accumulator stages × BN fp32 columns) so the epilogue of tile i overlaps the
+//               mainloop of tile i+1
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes × 32 columns → registers → bias / GELU / ReLU / GLU / residual /
+//               activation-gradient / row masking → 16-byte global stores
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace jl {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
+
+struct GemmDev {
+  void* c;
+  int64_t ldc;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+  const __nv_bfloat16* aux;
+  int64_t ldaux;
+  __nv_bfloat16* aux_out;
+  int64_t ldaux_out;
+  const int32_t* row_lengths;
+  int32_t rows_per_seq;
+  int32_t m, n, k;
+  int32_t epilogue;
+  int32_t out_dtype;
+  float alpha;
+  int32_t num_m_tiles, num_n_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for one row × 32 consecutive accumulator columns (shared by the tcgen05 kernel and the
+// test-only SIMT reference so that both apply bit-identical post-processing).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_bf16_row32(const __nv_bfloat16* p, bool vec, int nvalid, float (&out)[32]) {
+  if (vec) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 v = __ldg(q + i);
+      float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+      out[8 * i + 0] = f0.x; out[8 * i + 1] = f0.y; out[8 * i + 2] = f1.x; out[8 * i + 3] = f1.y;
+      out[8 * i + 4] = f2.x; out[8 * i + 5] = f2.y; out[8 * i + 6] = f3.x; out[8 * i + 7] = f3.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = (j < nvalid) ? __bfloat162float(p[j]) : 0.0f;
+  }
+}
+
+template <int COUNT>
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* p, bool vec, int nvalid, const float (&v)[COUNT]) {
+  if (vec) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < COUNT / 8; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      q[i] = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < COUNT; ++j)
+      if (j < nvalid) p[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+template <int COUNT>
+__device__ __forceinline__ void store_f32_row(float* p, bool vec, int nvalid, const float (&v)[COUNT]) {
+  if (vec) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < COUNT / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < COUNT; ++j)
+      if (j < nvalid) p[j] = v[j];
+  }
+}
+
+__device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, int col0, float (&acc)[32]) {
+  if (row >= g.m || col0 >= g.n) return;
+  const int nvalid = min(32, g.n - col0);
+  const bool full = (nvalid == 32);
+
+  // alpha, bias
+  if (g.bias != nullptr) {
+    if (full) {
+      const float4* bq = reinterpret_cast<const float4*>(g.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(bq + i);
+        acc[4 * i + 0] = fmaf(acc[4 * i + 0], g.alpha, b.x);
+        acc[4 * i + 1] = fmaf(acc[4 * i + 1], g.alpha, b.y);
+        acc[4 * i + 2] = fmaf(acc[4 * i + 2], g.alpha, b.z);
+        acc[4 * i + 3] = fmaf(acc[4 * i + 3], g.alpha, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], g.alpha, (j < nvalid) ? __ldg(g.bias + col0 + j) : 0.0f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] *= g.alpha;
+  }
+
+  bool zero_row = false;
+  if (g.row_lengths != nullptr) {
+    const int b = row / g.rows_per_seq;
+    const int t = row - b * g.rows_per_seq;
+    zero_row = (t >= __ldg(g.row_lengths + b));
+  }
+
+  if (g.epilogue == JL_EPI_GLU) {
+    // interleaved (value, gate) column pairs → 16 outputs
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float val = acc[2 * j], gate = acc[2 * j + 1];
+      o[j] = zero_row ? 0.0f : val / (1.0f + expf(-gate));
+    }
+    const int ocol = col0 >> 1;
+    const int on = g.n >> 1;
+    const int ovalid = min(16, on - ocol);
+    if (g.out_dtype == JL_DT_BF16) {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + static_cast<int64_t>(row) * g.ldc + ocol;
+      const bool vec = (ovalid == 16) && ((g.ldc & 7) == 0);
+      store_bf16_row<16>(cp, vec, ovalid, o);
+    } else {
+      float* cp = reinterpret_cast<float*>(g.c) + static_cast<int64_t>(row) * g.ldc + ocol;
+      const bool vec = (ovalid == 16) && ((g.ldc & 3) == 0);
+      store_f32_row<16>(cp, vec, ovalid, o);
+    }
+    return;
+  }
+
+  if (g.epilogue == JL_EPI_GELU) {
+    if (g.aux_out != nullptr) {
+      __nv_bfloat16* ap = g.aux_out + static_cast<int64_t>(row) * g.ldaux_out + col0;
+      store_bf16_row<32>(ap, full && ((g.ldaux_out & 7) == 0), nvalid, acc);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+  } else if (g.epilogue == JL_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.0f);
+  } else if (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) {
+    float a[32];
+    load_bf16_row32(g.aux + static_cast<int64_t>(row) * g.ldaux + col0, full && ((g.ldaux & 7) == 0), nvalid, a);
+    if (g.epilogue == JL_EPI_GELU_BWD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(a[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = (a[j] > 0.0f) ? acc[j] : 0.0f;
+    }
+  }
+
+  if (g.residual != nullptr) {
+    float r[32];
+    load_bf16_row32(g.residual + static_cast<int64_t>(row) * g.ldr + col0, full && ((g.ldr & 7) == 0), nvalid, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += r[j];
+  }
+  if (zero_row) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+  }
+
+  if (g.out_dtype == JL_DT_BF16) {
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + static_cast<int64_t>(row) * g.ldc + col0;
+    store_bf16_row<32>(cp, full && ((g.ldc & 7) == 0), nvalid, acc);
+  } else {
+    float* cp = reinterpret_cast<float*>(g.c) + static_cast<int64_t>(row) * g.ldc + col0;
+    store_f32_row<32>(cp, full && ((g.ldc & 3) == 0), nvalid, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+  using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32, 256]");
+  static_assert(!B_MN || BN >= 64, "MN-major B needs 64-wide swizzle blocks");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + STAGES * GEMM_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int num_kb = (g.k + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tma_a);
+    ptx::prefetch_tensormap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar + s, 1);
+      ptx::mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar + s, 1);
+      ptx::mbar_init(tempty_bar + s, GEMM_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
+        const int n0 = (tile % g.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
+          uint8_t* a_dst = s_a + stage * GEMM_A_BYTES;
+          uint8_t* b_dst = s_b + stage * L::B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < GEMM_BM / 64; ++i) ptx::tma_load_2d(a_dst + i * 8192, &tma_a, full_bar + stage, m0 + 64 * i, k0);
+          } else {
+            ptx::tma_load_2d(a_dst, &tma_a, full_bar + stage, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) ptx::tma_load_2d(b_dst + i * 8192, &tma_b, full_bar + stage, n0 + 64 * i, k0);
+          } else {
+            ptx::tma_load_2d(b_dst, &tma_b, full_bar + stage, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar + as, aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(s_a + stage * GEMM_A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(s_b + stage * L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // K-major: 32 B along the 128 B swizzled row per 16-element k-step; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows (2 × 1024 B swizzle atoms) per k-step; 64-wide MN blocks 8192 B apart.
+            const uint64_t da = A_MN ? ptx::make_sw128_desc(a_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::make_sw128_desc(b_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar + stage);   // smem slot free once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar + as);         // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;             // which 32-column chunks (even / odd)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
+      const int n0 = (tile % g.num_n_tiles) * BN;
+      ptx::mbar_wait(tfull_bar + as, aphase);
+      ptx::tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32);
+        ptx::tmem_ld_32x32(taddr, v);
+        ptx::tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar + as);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Test-only SIMT reference (fp32 accumulate, same epilogue code).
+// ------------------------------------------------------------------------------------------------
+struct GemmRefOperands {
+  const __nv_bfloat16* a; int64_t lda; int a_mn;
+  const __nv_bfloat16* b; int64_t ldb; int b_mn;
+};
+
+__global__ void gemm_ref_kernel(const GemmRefOperands o, const GemmDev g) {
+  const int chunks = (g.n + 31) / 32;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(g.m) * chunks) return;
+  const int row = static_cast<int>(idx / chunks);
+  const int col0 = static_cast<int>(idx % chunks) * 32;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+  for (int kk = 0; kk < g.k; ++kk) {
+    const float av = __bfloat162float(o.a_mn ? o.a[static_cast<int64_t>(kk) * o.lda + row] : o.a[static_cast<int64_t>(row) * o.lda + kk]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < g.n) {
+        const float bv = __bfloat162float(o.b_mn ? o.b[static_cast<int64_t>(kk) * o.ldb + col] : o.b[static_cast<int64_t>(col) * o.ldb + kk]);
+        acc[j] = fmaf(av, bv, acc[j]);
+      }
+    }
+  }
+  gemm_epilogue_row32(g, row, col0, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements × `outer` rows (row stride ld elements), 128B swizzle, box 64 × box_rows.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  JL_REQUIRE(enc != nullptr, JL_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JL_REQUIRE(r == CUDA_SUCCESS, JL_ECUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld", (int)r, ptr,
+             (long long)inner, (long long)outer, (long long)ld);
+  return JL_OK;
+}
+
+static int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static int validate(const jl_gemm_params* p) {
+  JL_REQUIRE(p != nullptr, JL_EINVAL, "gemm: null params");
+  JL_REQUIRE(p->a && p->b && p->c, JL_EINVAL, "gemm: null operand pointer");
+  JL_REQUIRE(p->m > 0 && p->n > 0 && p->k > 0, JL_EINVAL, "gemm: m, n, k must be positive (got %d, %d, %d)", p->m, p->n, p->k);
+  JL_REQUIRE((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->b) & 15) == 0, JL_EINVAL,
+             "gemm: A and B must be 16-byte aligned");
+  JL_REQUIRE((p->lda & 7) == 0 && (p->ldb & 7) == 0, JL_EINVAL, "gemm: lda/ldb must be multiples of 8 elements (got %lld, %lld)",
+             (long long)p->lda, (long long)p->ldb);
+  JL_REQUIRE(p->a_layout == JL_LAYOUT_K || p->a_layout == JL_LAYOUT_MN, JL_EINVAL, "gemm: bad a_layout");
+  JL_REQUIRE(p->b_layout == JL_LAYOUT_K || p->b_layout == JL_LAYOUT_MN, JL_EINVAL, "gemm: bad b_layout");
+  JL_REQUIRE(p->lda >= (p->a_layout == JL_LAYOUT_K ? p->k : p->m), JL_EINVAL, "gemm: lda too small");
+  JL_REQUIRE(p->ldb >= (p->b_layout == JL_LAYOUT_K ? p->k : p->n), JL_EINVAL, "gemm: ldb too small");
+  JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_GLU, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
+  JL_REQUIRE(p->out_dtype == JL_DT_BF16 || p->out_dtype == JL_DT_F32, JL_EINVAL, "gemm: unknown out_dtype %d", p->out_dtype);
+  JL_REQUIRE((reinterpret_cast<uintptr_t>(p->c) & 15) == 0, JL_EINVAL, "gemm: C must be 16-byte aligned");
+  if (p->epilogue == JL_EPI_GLU) JL_REQUIRE((p->n & 1) == 0, JL_EINVAL, "gemm: GLU needs an even N");
+  if (p->epilogue == JL_EPI_GELU_BWD || p->epilogue == JL_EPI_RELU_BWD)
+    JL_REQUIRE(p->aux != nullptr, JL_EINVAL, "gemm: activation-gradient epilogue needs aux");
+  if (p->bias) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->bias) & 15) == 0, JL_EINVAL, "gemm: bias must be 16-byte aligned");
+  if (p->residual) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0, JL_EINVAL, "gemm: residual must be 16-byte aligned");
+  if (p->aux) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->aux) & 15) == 0, JL_EINVAL, "gemm: aux must be 16-byte aligned");
+  if (p->aux_out) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->aux_out) & 15) == 0, JL_EINVAL, "gemm: aux_out must be 16-byte aligned");
+  if (p->row_lengths) JL_REQUIRE(p->rows_per_seq > 0, JL_EINVAL, "gemm: row_lengths needs rows_per_seq > 0");
+  return JL_OK;
+}
+
+static GemmDev to_dev(const jl_gemm_params* p, int bn) {
+  GemmDev g;
+  g.c = p->c; g.ldc = p->ldc;
+  g.bias = p->bias;
+  g.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual); g.ldr = p->ldr;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(p->aux); g.ldaux = p->ldaux;
+  g.aux_out = reinterpret_cast<__nv_bfloat16*>(p->aux_out); g.ldaux_out = p->ldaux_out;
+  g.row_lengths = p->row_lengths; g.rows_per_seq = p->rows_per_seq;
+  g.m = p->m; g.n = p->n; g.k = p->k;
+  g.epilogue = p->epilogue; g.out_dtype = p->out_dtype; g.alpha = p->alpha;
+  g.num_m_tiles = ceil_div(p->m, GEMM_BM);
+  g.num_n_tiles = ceil_div(p->n, bn);
+  return g;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "gemm: cannot reserve %d B of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  CUtensorMap ma, mb;
+  int rc;
+  if (A_MN) rc = make_map(&ma, p->a, p->m, p->k, p->lda, 64);
+  else rc = make_map(&ma, p->a, p->k, p->m, p->lda, GEMM_BM);
+  if (rc != JL_OK) return rc;
+  if (B_MN) rc = make_map(&mb, p->b, p->n, p->k, p->ldb, 64);
+  else rc = make_map(&mb, p->b, p->k, p->n, p->ldb, BN);
+  if (rc != JL_OK) return rc;
+  const GemmDev g = to_dev(p, BN);
+  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
+  JL_CHECK_LAUNCH("gemm_tcgen05");
+  return JL_OK;
+}
+
+template <int BN, int STAGES>
+static int dispatch_layout(const jl_gemm_params* p, cudaStream_t s) {
+  const bool amn = p->a_layout == JL_LAYOUT_MN, bmn = p->b_layout == JL_LAYOUT_MN;
+  if constexpr (BN >= 64) {
+    if (amn && bmn) return launch_gemm<BN, STAGES, true, true>(p, s);
+    if (bmn) return launch_gemm<BN, STAGES, false, true>(p, s);
+  }
+  if (amn) return launch_gemm<BN, STAGES, true, false>(p, s);
+  return launch_gemm<BN, STAGES, false, false>(p, s);
+}
+
+// Pick the N tile: fewest (waves × per-tile cost) over the candidates; per-tile cost ∝ BN plus a fixed part.
+static int pick_bn(const jl_gemm_params* p) {
+  const bool bmn = p->b_layout == JL_LAYOUT_MN;
+  if (!bmn && p->n <= 32) return 32;
+  if (p->n <= 64) return 64;
+  const int sms = num_sms();
+  const int mt = ceil_div(p->m, GEMM_BM);
+  int best = 64;
+  long best_cost = -1;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && bn / 2 >= p->n) continue;
+    const long tiles = static_cast<long>(mt) * ceil_div(p->n, bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cost = waves * (bn + 24);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace jl
+
+extern "C" {
+
+int jl_gemm_bf16(const jl_gemm_params* p, void* stream) {
+  int rc = jl::validate(p);
+  if (rc != JL_OK) return rc;
+  rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (jl::pick_bn(p)) {
+    case 256: return jl::dispatch_layout<256, 4>(p, s);
+    case 128: return jl::dispatch_layout<128, 6>(p, s);
+    case 64: return jl::dispatch_layout<64, 8>(p, s);
+    default: return jl::dispatch_layout<32, 8>(p, s);
+  }
+}
+
+int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {
+  int rc = jl::validate(p);
+  if (rc != JL_OK) return rc;
+  rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::GemmRefOperands o;
+  o.a = reinterpret_cast<const __nv_bfloat16*>(p->a); o.lda = p->lda; o.a_mn = p->a_layout == JL_LAYOUT_MN;
+  o.b = reinterpret_cast<const __nv_bfloat16*>(p->b); o.ldb = p->ldb; o.b_mn = p->b_layout == JL_LAYOUT_MN;
+  const jl::GemmDev g = jl::to_dev(p, 32);
+  const int64_t total = static_cast<int64_t>(p->m) * ((p->n + 31) / 32);
+  const int threads = 128;
+  const int64_t blocks = (total + threads - 1) / threads;
+  jl::gemm_ref_kernel<<<static_cast<unsigned>(blocks), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(o, g);
+  JL_CHECK_LAUNCH("gemm_ref");
+  return JL_OK;
+}
+
+}  // extern "C"

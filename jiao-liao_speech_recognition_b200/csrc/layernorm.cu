@@ -1,0 +1,247 @@
+// LayerNorm over the last dim, bf16 in / bf16 out, fp32 statistics (eps 1e-5 on the path).
+// Replaces nn.LayerNorm at SP/transformers/models/wav2vec2/modeling_wav2vec2.py:623,625,639,645 (pre-LN layer),
+// :792 (final encoder norm) and :941 (adapter norm), forward and backward (dx; dgamma/dbeta only for the
+// trainable adapter norms — the backbone is frozen).
+//
+// HBM-bound: one warp per row, the whole row lives in registers (16-byte loads, two-pass variance in registers),
+// one read + one write of the activation.  Backward keeps per-lane dgamma/dbeta accumulators in registers across
+// the rows a CTA owns, reduces them through shared memory and leaves one partial row per CTA; a second small
+// kernel sums the partials in fixed order (deterministic, no atomics).
+#include "common.cuh"
+
+namespace jl {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_THREADS = LN_WARPS * 32;
+
+template <int NCH>
+__device__ __forceinline__ void ln_load_row(const __nv_bfloat16* row, int nchunks, int lane, float (&x)[NCH][8]) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = c * 32 + lane;
+    if (ch < nchunks) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + ch);
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+      x[c][0] = f0.x; x[c][1] = f0.y; x[c][2] = f1.x; x[c][3] = f1.y;
+      x[c][4] = f2.x; x[c][5] = f2.y; x[c][6] = f3.x; x[c][7] = f3.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[c][j] = 0.0f;
+    }
+  }
+}
+
+__device__ __forceinline__ void ln_load8_f32(const float* p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+__device__ __forceinline__ void ln_store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_layernorm_fwd_params p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nchunks = p.d >> 3;
+  const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<int64_t>(row) * p.ldx;
+  float x[NCH][8];
+  ln_load_row<NCH>(xr, nchunks, lane, x);
+  float sum = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += x[c][j];
+  const float inv_d = 1.0f / static_cast<float>(p.d);
+  const float mean = warp_sum(sum) * inv_d;
+  float sq = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    if (c * 32 + lane < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[c][j] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  const float var = warp_sum(sq) * inv_d;
+  const float rstd = 1.0f / sqrtf(var + p.eps);
+  if (lane == 0) {
+    if (p.mean != nullptr) p.mean[row] = mean;
+    if (p.rstd != nullptr) p.rstd[row] = rstd;
+  }
+  __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(row) * p.ldy;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = c * 32 + lane;
+    if (ch < nchunks) {
+      float g[8], b[8], o[8];
+      ln_load8_f32(p.gamma + ch * 8, g);
+      ln_load8_f32(p.beta + ch * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, g[j], b[j]);
+      ln_store8_bf16(yr + ch * 8, o);
+    }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_layernorm_bwd_params p) {
+  __shared__ float s_red[NCH * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nchunks = p.d >> 3;
+  const float inv_d = 1.0f / static_cast<float>(p.d);
+  const bool want_wgrad = (p.dgamma != nullptr);
+  float dg[NCH][8], db[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[c][j] = 0.0f; db[c][j] = 0.0f; }
+
+  for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
+    float x[NCH][8], dy[NCH][8];
+    ln_load_row<NCH>(reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<int64_t>(row) * p.ldx, nchunks, lane, x);
+    ln_load_row<NCH>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + static_cast<int64_t>(row) * p.lddy, nchunks, lane, dy);
+    const float mean = __ldg(p.mean + row), rstd = __ldg(p.rstd + row);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = c * 32 + lane;
+      if (ch < nchunks) {
+        float g[8];
+        ln_load8_f32(p.gamma + ch * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (x[c][j] - mean) * rstd;
+          if (want_wgrad) { dg[c][j] = fmaf(dy[c][j], xh, dg[c][j]); db[c][j] += dy[c][j]; }
+          const float gy = dy[c][j] * g[j];
+          x[c][j] = xh;
+          dy[c][j] = gy;
+          s1 += gy;
+          s2 = fmaf(gy, xh, s2);
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    __nv_bfloat16* dxr = reinterpret_cast<__nv_bfloat16*>(p.dx) + static_cast<int64_t>(row) * p.lddx;
+    const __nv_bfloat16* drr = p.dres ? reinterpret_cast<const __nv_bfloat16*>(p.dres) + static_cast<int64_t>(row) * p.lddres : nullptr;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = c * 32 + lane;
+      if (ch < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dy[c][j] - c1 - x[c][j] * c2);
+        if (drr != nullptr) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(drr) + ch);
+          const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+          o[0] += f0.x; o[1] += f0.y; o[2] += f1.x; o[3] += f1.y; o[4] += f2.x; o[5] += f2.y; o[6] += f3.x; o[7] += f3.y;
+        }
+        ln_store8_bf16(dxr + ch * 8, o);
+      }
+    }
+  }
+
+  if (want_wgrad) {
+    // CTA reduction of the per-warp accumulators (warps add in fixed order) → one partial row per CTA
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int w = 0; w < LN_WARPS; ++w) {
+        __syncthreads();
+        if (warp == w) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = pass == 0 ? dg[c][j] : db[c][j];
+              float* dst = &s_red[(c * 32 + lane) * 8 + j];
+              *dst = (w == 0) ? v : (*dst + v);
+            }
+        }
+      }
+      __syncthreads();
+      float* dst = p.partial + (static_cast<int64_t>(pass) * gridDim.x + blockIdx.x) * p.d;
+      for (int i = threadIdx.x; i < p.d; i += LN_THREADS) dst[i] = s_red[i];
+    }
+  }
+}
+
+__global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d) return;
+  float g = 0.0f, b = 0.0f;
+  for (int k = 0; k < nblk; ++k) {
+    g += partial[static_cast<int64_t>(k) * d + i];
+    b += partial[(static_cast<int64_t>(nblk) + k) * d + i];
+  }
+  dgamma[i] = g;
+  if (dbeta != nullptr) dbeta[i] = b;
+}
+
+static int ln_bwd_blocks(int rows) {
+  int blocks = ceil_div(rows, LN_WARPS);
+  return blocks < 296 ? blocks : 296;   // 2 CTAs per SM on 148 SMs
+}
+
+static int ln_pick(int d) { return d <= 768 ? 3 : (d <= 1024 ? 4 : 8); }
+
+}  // namespace jl
+
+extern "C" {
+
+int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
+  JL_REQUIRE(p && p->x && p->y && p->gamma && p->beta, JL_EINVAL, "layernorm_fwd: null pointer");
+  JL_REQUIRE(p->rows > 0 && p->d > 0, JL_EINVAL, "layernorm_fwd: rows and d must be positive");
+  JL_REQUIRE((p->d & 7) == 0 && p->d <= 2048, JL_EUNSUPPORTED_SHAPE, "layernorm_fwd: d must be a multiple of 8 and <= 2048 (got %d)", p->d);
+  JL_REQUIRE((p->ldx & 7) == 0 && (p->ldy & 7) == 0, JL_EINVAL, "layernorm_fwd: row strides must be multiples of 8");
+  JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->y) | reinterpret_cast<uintptr_t>(p->gamma) |
+               reinterpret_cast<uintptr_t>(p->beta)) & 15) == 0, JL_EINVAL, "layernorm_fwd: pointers must be 16-byte aligned");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = jl::ceil_div(p->rows, jl::LN_WARPS);
+  switch (jl::ln_pick(p->d)) {
+    case 3: jl::layernorm_fwd_kernel<3><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    case 4: jl::layernorm_fwd_kernel<4><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    default: jl::layernorm_fwd_kernel<8><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+  }
+  JL_CHECK_LAUNCH("layernorm_fwd");
+  return JL_OK;
+}
+
+int jl_layernorm_bwd_workspace_bytes(const jl_layernorm_bwd_params* p, size_t* out) {
+  JL_REQUIRE(p && out, JL_EINVAL, "layernorm_bwd_workspace_bytes: null argument");
+  *out = (p->dgamma != nullptr) ? static_cast<size_t>(2) * jl::ln_bwd_blocks(p->rows) * p->d * sizeof(float) : 0;
+  return JL_OK;
+}
+
+int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
+  JL_REQUIRE(p && p->dy && p->x && p->gamma && p->mean && p->rstd && p->dx, JL_EINVAL, "layernorm_bwd: null pointer");
+  JL_REQUIRE(p->rows > 0 && p->d > 0, JL_EINVAL, "layernorm_bwd: rows and d must be positive");
+  JL_REQUIRE((p->d & 7) == 0 && p->d <= 2048, JL_EUNSUPPORTED_SHAPE, "layernorm_bwd: d must be a multiple of 8 and <= 2048 (got %d)", p->d);
+  JL_REQUIRE((p->ldx & 7) == 0 && (p->lddy & 7) == 0 && (p->lddx & 7) == 0 && (p->dres == nullptr || (p->lddres & 7) == 0), JL_EINVAL,
+             "layernorm_bwd: row strides must be multiples of 8");
+  JL_REQUIRE(p->dgamma == nullptr || p->partial != nullptr, JL_EINVAL, "layernorm_bwd: dgamma needs the partial workspace");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, jl::LN_WARPS);
+  switch (jl::ln_pick(p->d)) {
+    case 3: jl::layernorm_bwd_kernel<3><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    case 4: jl::layernorm_bwd_kernel<4><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    default: jl::layernorm_bwd_kernel<8><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+  }
+  JL_CHECK_LAUNCH("layernorm_bwd");
+  if (p->dgamma != nullptr) {
+    jl::layernorm_bwd_reduce_kernel<<<jl::ceil_div(p->d, 256), 256, 0, s>>>(p->partial, blocks, p->d, p->dgamma, p->dbeta);
+    JL_CHECK_LAUNCH("layernorm_bwd_reduce");
+  }
+  return JL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,634 @@
+"""Drop-in PyTorch modules for the Jiao-Liao ASR path: ``JLEncoder`` (conv subsampler + pre-LN transformer with
+``WFAdapter`` / ``AttAdapter`` slots), ``JLForCTC`` (encoder + CTC head).
+
+The modules are ordinary ``nn.Module``s — parameters, ``state_dict``, ``.to()``, optimizers all work — but their
+``forward`` never runs a PyTorch op on activations: ``JLEngine`` walks the layers and calls the C ABI
+(``libjl_b200.so``: tcgen05 GEMMs, fused LayerNorm / attention / CTC kernels).  Training is adapter-only: the
+backbone is frozen (``freeze_base_model``), the backward pass propagates dX through the frozen layers with the same
+GEMM kernel in its MN-major operand modes and produces weight gradients only for the adapters and ``lm_head``.
+
+Interfaces mirrored (SP = site-packages of the build container):
+  * encoder forward           SP/transformers/models/speech_to_text/modeling_speech_to_text.py:561-608
+  * pre-LN layer + adapter    SP/transformers/models/wav2vec2/modeling_wav2vec2.py:612-655 (hook :627-630,647-648)
+  * CTC model forward / loss  SP/transformers/models/wav2vec2/modeling_wav2vec2.py:1675-1744
+  * adapter management        :1046-1060 (_get_adapters), :1062-1073 (init_adapter_layers), :1075-1248 (load_adapter),
+                              :1666-1672 (freeze_base_model)
+WFAdapter / AttAdapter definitions: SURVEY.md §8c (from /root/reference/README.md:1 + BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .configuration import JLConfig
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+def subsampled_length(n, num_convs: int = 2):
+    """(L - 1) // 2 + 1 per stride-2 conv (modeling_speech_to_text.py:489-496).  Works on ints and tensors."""
+    for _ in range(num_convs):
+        n = (n - 1) // 2 + 1
+    return n
+
+
+def sinusoid_table(num_rows: int, dim: int) -> torch.Tensor:
+    """modeling_speech_to_text.py:123-139: [sin | cos] halves, log(10000)/(half-1) spacing, padding row 1 zeroed.
+    Built once per device with the same fp32 operation sequence HF uses, so the table matches the reference's."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.int64).float() * -e)
+    e = torch.arange(num_rows, dtype=torch.int64).float().unsqueeze(1) * e.unsqueeze(0)
+    tab = torch.cat([torch.sin(e), torch.cos(e)], dim=1).view(num_rows, -1)
+    if dim % 2 == 1:
+        tab = torch.cat([tab, torch.zeros(num_rows, 1)], dim=1)
+    tab[1, :] = 0
+    return tab
+
+
+# =============================================================================================== modules
+class WFAdapter(nn.Module):
+    """Bottleneck adapter whose projections exist only as low-rank factors (weight factorisation):
+    z = LN(h); u = relu((z B_dᵀ) A_dᵀ + c_d); y = (u B_uᵀ) A_uᵀ + c_u; out = h + y.
+    Every factor carries a leading dialect dimension K; ``dialect`` selects the set used by a call."""
+
+    kind = "wf"
+
+    def __init__(self, hidden_size: int, bottleneck: int = 256, rank: int = 32, num_dialects: int = 1, eps: float = 1e-5):
+        super().__init__()
+        k, d, b, r = num_dialects, hidden_size, bottleneck, rank
+        self.hidden_size, self.bottleneck, self.rank, self.num_dialects = d, b, r, k
+        self.norm = nn.LayerNorm(d, eps=eps)
+        self.down_B = nn.Parameter(torch.empty(k, r, d))
+        self.down_A = nn.Parameter(torch.empty(k, b, r))
+        self.down_bias = nn.Parameter(torch.empty(k, b))
+        self.up_B = nn.Parameter(torch.empty(k, r, b))
+        self.up_A = nn.Parameter(torch.empty(k, d, r))
+        self.up_bias = nn.Parameter(torch.empty(k, d))
+        self.reset_parameters()
+
+    def reset_parameters(self, std: float = 0.02, generator: Optional[torch.Generator] = None):
+        with torch.no_grad():
+            for p in (self.down_B, self.down_A, self.up_B, self.up_A):
+                p.copy_(torch.randn(p.shape, generator=generator) * std)
+            self.down_bias.zero_()
+            self.up_bias.zero_()
+            self.norm.weight.fill_(1.0)
+            self.norm.bias.zero_()
+
+
+class AttAdapter(nn.Module):
+    """Adapter that attends over the utterance's own hidden states: z = LN(h); q,k,v = z W_{q,k,v}ᵀ + b ∈ R^64;
+    a = softmax(q kᵀ / 8 + keymask) v; out = h + a W_oᵀ + b_o.  One head of dim 64."""
+
+    kind = "att"
+
+    def __init__(self, hidden_size: int, att_dim: int = 64, eps: float = 1e-5):
+        super().__init__()
+        if att_dim != 64:
+            raise ValueError("AttAdapter: att_dim must be 64")
+        self.hidden_size, self.att_dim = hidden_size, att_dim
+        self.norm = nn.LayerNorm(hidden_size, eps=eps)
+        self.q_proj = nn.Linear(hidden_size, att_dim)
+        self.k_proj = nn.Linear(hidden_size, att_dim)
+        self.v_proj = nn.Linear(hidden_size, att_dim)
+        self.o_proj = nn.Linear(att_dim, hidden_size)
+        self.reset_parameters()
+
+    def reset_parameters(self, std: float = 0.02, generator: Optional[torch.Generator] = None):
+        with torch.no_grad():
+            for lin in (self.q_proj, self.k_proj, self.v_proj, self.o_proj):
+                lin.weight.copy_(torch.randn(lin.weight.shape, generator=generator) * std)
+                lin.bias.zero_()
+            self.norm.weight.fill_(1.0)
+            self.norm.bias.zero_()
+
+
+def _make_adapter(kind: Optional[str], cfg: JLConfig) -> Optional[nn.Module]:
+    if kind is None:
+        return None
+    if kind == "wf":
+        return WFAdapter(cfg.hidden_size, cfg.wf_bottleneck, cfg.wf_rank, cfg.num_dialects, cfg.layer_norm_eps)
+    if kind == "att":
+        return AttAdapter(cfg.hidden_size, cfg.att_dim, cfg.layer_norm_eps)
+    raise ValueError(kind)
+
+
+class JLAttention(nn.Module):
+    def __init__(self, d: int):
+        super().__init__()
+        self.q_proj, self.k_proj, self.v_proj, self.out_proj = (nn.Linear(d, d) for _ in range(4))
+
+
+class JLFeedForward(nn.Module):
+    def __init__(self, d: int, inner: int):
+        super().__init__()
+        self.intermediate_dense = nn.Linear(d, inner)
+        self.output_dense = nn.Linear(inner, d)
+
+
+class JLEncoderLayer(nn.Module):
+    def __init__(self, cfg: JLConfig):
+        super().__init__()
+        d = cfg.hidden_size
+        self.layer_norm = nn.LayerNorm(d, eps=cfg.layer_norm_eps)
+        self.attention = JLAttention(d)
+        self.adapter_attn = _make_adapter(cfg.adapter_attn, cfg)
+        self.final_layer_norm = nn.LayerNorm(d, eps=cfg.layer_norm_eps)
+        self.feed_forward = JLFeedForward(d, cfg.intermediate_size)
+        self.adapter_ffn = _make_adapter(cfg.adapter_ffn, cfg)
+
+
+class JLEncoder(nn.Module):
+    """Conv1d(k5,s2)+GLU ×2 → ×√d + sinusoid positions → N pre-LN layers with adapter slots → final LayerNorm."""
+
+    def __init__(self, cfg: JLConfig):
+        super().__init__()
+        self.config = cfg
+        d = cfg.hidden_size
+        self.conv = nn.ModuleList([
+            nn.Conv1d(cfg.input_feat_per_channel, cfg.conv_channels, 5, stride=2, padding=2),
+            nn.Conv1d(cfg.conv_channels // 2, 2 * d, 5, stride=2, padding=2),
+        ])
+        self.layers = nn.ModuleList([JLEncoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+        self.layer_norm = nn.LayerNorm(d, eps=cfg.layer_norm_eps)
+        self._engine: Optional["JLEngine"] = None
+
+    def engine(self, lm_head: Optional[nn.Linear] = None) -> "JLEngine":
+        if self._engine is None:
+            self._engine = JLEngine(self, lm_head)
+        if lm_head is not None:
+            self._engine.lm_head = lm_head
+        return self._engine
+
+    def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                frame_lengths: Optional[torch.Tensor] = None, dialect: int = 0):
+        """input_features [B, F, 80] (fp32 or bf16, CUDA) → last_hidden_state [B, T', d] bf16 (padded rows zeroed before the
+        final LayerNorm, as the reference).  Also returns nothing else: use ``output_lengths`` for T' lengths."""
+        eng = self.engine()
+        lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
+        st = eng.forward(input_features, lengths, training=False, dialect=dialect, want_logits=False)
+        b = input_features.shape[0]
+        return st.h_final.view(b, st.t, self.config.hidden_size)
+
+
+# =============================================================================================== engine
+class _State:
+    """Activations kept between forward and backward of one step."""
+    pass
+
+
+class JLEngine:
+    """Walks the module tree and issues the C-ABI calls.  Holds bf16 copies of the weights in the layouts the kernels
+    read (q/k/v concatenated; conv weights tap-major with GLU rows interleaved)."""
+
+    def __init__(self, encoder: JLEncoder, lm_head: Optional[nn.Linear] = None):
+        L.load()
+        self.enc = encoder
+        self.cfg = encoder.config
+        self.lm_head = lm_head
+        self._frozen = None
+        self._frozen_key = None
+        self._shadow: Dict[int, Tuple[int, int, torch.Tensor]] = {}
+        self._pos: Dict[Tuple[str, int], torch.Tensor] = {}
+        self.flat = None   # set by training.FlatAdapterParams
+
+    # ------------------------------------------------------------------ weights
+    def _backbone_params(self):
+        for n, p in self.enc.named_parameters():
+            if ".adapter_attn." not in n and ".adapter_ffn." not in n:
+                yield n, p
+
+    def _frozen_pack(self):
+        key = tuple((p.data_ptr(), p._version) for _, p in self._backbone_params())
+        if self._frozen is not None and key == self._frozen_key:
+            return self._frozen
+        fz = {}
+        with torch.no_grad():
+            for i, conv in enumerate(self.enc.conv):
+                cout, cin, k = conv.weight.shape
+                half = cout // 2
+                idx = torch.stack([torch.arange(half), torch.arange(half) + half], dim=1).reshape(-1).to(conv.weight.device)
+                w = conv.weight.permute(0, 2, 1).reshape(cout, k * cin)[idx]
+                fz[f"conv{i}.w"] = w.to(BF16).contiguous()
+                fz[f"conv{i}.b"] = conv.bias[idx].to(F32).contiguous()
+            for i, layer in enumerate(self.enc.layers):
+                a = layer.attention
+                fz[f"{i}.wqkv"] = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).to(BF16).contiguous()
+                fz[f"{i}.bqkv"] = torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0).to(F32).contiguous()
+                fz[f"{i}.wo"] = a.out_proj.weight.to(BF16).contiguous()
+                fz[f"{i}.bo"] = a.out_proj.bias.to(F32).contiguous()
+                fz[f"{i}.w1"] = layer.feed_forward.intermediate_dense.weight.to(BF16).contiguous()
+                fz[f"{i}.b1"] = layer.feed_forward.intermediate_dense.bias.to(F32).contiguous()
+                fz[f"{i}.w2"] = layer.feed_forward.output_dense.weight.to(BF16).contiguous()
+                fz[f"{i}.b2"] = layer.feed_forward.output_dense.bias.to(F32).contiguous()
+        self._frozen, self._frozen_key = fz, key
+        return fz
+
+    def _bf16(self, p: torch.Tensor) -> torch.Tensor:
+        """bf16 copy of a trainable fp32 parameter, refreshed (by the cast kernel) when the parameter changed."""
+        if self.flat is not None:
+            v = self.flat.bf16_view(p)
+            if v is not None:
+                return v
+        ent = self._shadow.get(id(p))
+        if ent is not None and ent[0] == p.data_ptr() and ent[1] == p._version:
+            return ent[2]
+        sh = ops.cast_bf16(p.detach().contiguous())
+        self._shadow[id(p)] = (p.data_ptr(), p._version, sh)
+        return sh
+
+    def _cat_bf16(self, params: List[torch.Tensor]) -> torch.Tensor:
+        if self.flat is not None:
+            v = self.flat.bf16_cat_view(params)
+            if v is not None:
+                return v
+        key = tuple(id(p) for p in params)
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        ent = self._shadow.get(key)
+        if ent is not None and ent[0] == ver:
+            return ent[2]
+        with torch.no_grad():
+            sh = ops.cast_bf16(torch.cat([p.detach() for p in params], 0).contiguous())
+        self._shadow[key] = (ver, None, sh)
+        return sh
+
+    def _cat_f32(self, params: List[torch.Tensor]) -> torch.Tensor:
+        if self.flat is not None:
+            v = self.flat.f32_cat_view(params)
+            if v is not None:
+                return v
+        with torch.no_grad():
+            return torch.cat([p.detach() for p in params], 0).contiguous()
+
+    def pos_table(self, device, rows: int) -> torch.Tensor:
+        key = (str(device), self.cfg.hidden_size)
+        tab = self._pos.get(key)
+        if tab is None or tab.shape[0] < rows:
+            tab = sinusoid_table(max(rows, 1024), self.cfg.hidden_size).to(device).contiguous()
+            self._pos[key] = tab
+        return tab
+
+    # ------------------------------------------------------------------ lengths
+    def output_lengths(self, input_features, attention_mask=None, frame_lengths=None) -> torch.Tensor:
+        """T' lengths (int32, device) after the two stride-2 convs."""
+        if frame_lengths is None:
+            if attention_mask is None:
+                frame_lengths = torch.full((input_features.shape[0],), input_features.shape[1], dtype=I32, device=input_features.device)
+            else:
+                frame_lengths = attention_mask.sum(-1)
+        return subsampled_length(frame_lengths.to(torch.int64)).to(I32)
+
+    # ------------------------------------------------------------------ adapters
+    def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect: int, zero_rows: bool):
+        """Returns (out, saved).  out = h + adapter(h); padded rows zeroed when ``zero_rows`` (end of a layer)."""
+        eps = ad.norm.eps
+        z, mean, rstd = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), eps, save_stats=training)
+        rl = dict(row_lengths=lengths, rows_per_seq=t) if zero_rows else {}
+        if ad.kind == "wf":
+            k = dialect
+            t1 = ops.gemm(z, self._bf16(ad.down_B)[k])
+            u = ops.gemm(t1, self._bf16(ad.down_A)[k], bias=ad.down_bias.detach()[k], epilogue=L.JL_EPI_RELU)
+            t2 = ops.gemm(u, self._bf16(ad.up_B)[k])
+            out = ops.gemm(t2, self._bf16(ad.up_A)[k], bias=ad.up_bias.detach()[k], residual=h, **rl)
+            saved = (h, mean, rstd, z, t1, u, t2, k) if training else None
+        else:
+            wqkv = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
+            bqkv = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
+            qkv = ops.gemm(z, wqkv, bias=bqkv)
+            a, lse = ops.attn_fwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], lengths, b, t, 1, 1.0 / 8.0, want_lse=training)
+            out = ops.gemm(a, self._bf16(ad.o_proj.weight), bias=ad.o_proj.bias.detach(), residual=h, **rl)
+            saved = (h, mean, rstd, z, qkv, a, lse) if training else None
+        return out, saved
+
+    def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink") -> torch.Tensor:
+        """dy = grad of the adapter output → returns grad of the adapter input; weight grads go to ``g``."""
+        MN = L.JL_LAYOUT_MN
+        if ad.kind == "wf":
+            h, mean, rstd, z, t1, u, t2, k = saved
+            ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)                 # dyᵀ · t2
+            ops.colsum(dy, out=g.out(ad.up_bias, k))
+            dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
+            ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32)                  # dt2ᵀ · u
+            dpre = ops.gemm(dt2, self._bf16(ad.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=u)      # (dt2 · B_u) ∘ relu'
+            ops.colsum(dpre, out=g.out(ad.down_bias, k))
+            ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)              # dpreᵀ · t1
+            dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
+            ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32)                # dt1ᵀ · z
+            dz = ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN)                                         # dt1 · B_d
+        else:
+            h, mean, rstd, z, qkv, a, lse = saved
+            ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)             # dyᵀ · a
+            ops.colsum(dy, out=g.out(ad.o_proj.bias))
+            da = ops.gemm(dy, self._bf16(ad.o_proj.weight), b_layout=MN)                                      # dy · W_o
+            dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0)
+            ws = [ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight]
+            bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
+            gw, gb = g.out_cat(ws), g.out_cat(bs)
+            ops.gemm(dqkv, z, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                                # dqkvᵀ · z
+            ops.colsum(dqkv, out=gb)
+            g.scatter_cat(ws, gw)
+            g.scatter_cat(bs, gb)
+            dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
+        dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True,
+                                     dgamma=g.out(ad.norm.weight), dbeta=g.out(ad.norm.bias))
+        return dh
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_features: torch.Tensor, lengths: torch.Tensor, training: bool = False, dialect: int = 0,
+                want_logits: bool = True) -> _State:
+        cfg = self.cfg
+        d, heads = cfg.hidden_size, cfg.num_attention_heads
+        fz = self._frozen_pack()
+        if not input_features.is_cuda:
+            raise RuntimeError("JLEngine.forward: input_features must be a CUDA tensor (no CPU fallback)")
+        b, f, nmel = input_features.shape
+        if nmel != cfg.input_feat_per_channel:
+            raise ValueError(f"expected {cfg.input_feat_per_channel} mel bins, got {nmel}")
+        x16 = input_features if input_features.dtype == BF16 else ops.cast_bf16(input_features.contiguous())
+        x16 = x16.contiguous()
+        st = _State()
+        st.b, st.training, st.dialect = b, training, dialect
+        st.lengths = lengths
+        # conv subsampler as two im2col GEMMs with fused bias + GLU
+        a1, t1 = ops.im2col_k5s2(x16)
+        c1 = ops.gemm(a1, fz["conv0.w"], bias=fz["conv0.b"], epilogue=L.JL_EPI_GLU)
+        a2, t = ops.im2col_k5s2(c1.view(b, t1, cfg.conv_channels // 2))
+        h = ops.gemm(a2, fz["conv1.w"], bias=fz["conv1.b"], epilogue=L.JL_EPI_GLU)
+        st.t = t
+        ops.embed_positions_(h, math.sqrt(d), self.pos_table(h.device, t + 2), lengths, b, t)
+        scale = 1.0 / 8.0   # head_dim 64
+        st.layers = []
+        for i, layer in enumerate(self.enc.layers):
+            sv = _State()
+            sv.h_in = h
+            x1, sv.mean1, sv.rstd1 = ops.layernorm_fwd(h, layer.layer_norm.weight.detach(), layer.layer_norm.bias.detach(),
+                                                       layer.layer_norm.eps, save_stats=training)
+            qkv = ops.gemm(x1, fz[f"{i}.wqkv"], bias=fz[f"{i}.bqkv"])
+            o, lse = ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], lengths, b, t, heads, scale, want_lse=training)
+            h1 = ops.gemm(o, fz[f"{i}.wo"], bias=fz[f"{i}.bo"], residual=h)
+            sv.qkv, sv.o, sv.lse = qkv, o, lse
+            sv.ad_attn = None
+            if layer.adapter_attn is not None:
+                h1, sv.ad_attn = self._adapter_fwd(layer.adapter_attn, h1, lengths, b, t, training, dialect, zero_rows=False)
+            sv.h1 = h1
+            x2, sv.mean2, sv.rstd2 = ops.layernorm_fwd(h1, layer.final_layer_norm.weight.detach(), layer.final_layer_norm.bias.detach(),
+                                                       layer.final_layer_norm.eps, save_stats=training)
+            pre = torch.empty((b * t, cfg.intermediate_size), dtype=BF16, device=h.device) if training else None
+            act = ops.gemm(x2, fz[f"{i}.w1"], bias=fz[f"{i}.b1"], epilogue=L.JL_EPI_GELU, aux_out=pre)
+            sv.pre = pre
+            last_is_ffn = layer.adapter_ffn is None
+            rl = dict(row_lengths=lengths, rows_per_seq=t) if last_is_ffn else {}
+            h2 = ops.gemm(act, fz[f"{i}.w2"], bias=fz[f"{i}.b2"], residual=h1, **rl)
+            sv.ad_ffn = None
+            if layer.adapter_ffn is not None:
+                h2, sv.ad_ffn = self._adapter_fwd(layer.adapter_ffn, h2, lengths, b, t, training, dialect, zero_rows=True)
+            h = h2
+            if training:
+                st.layers.append(sv)
+        st.h_last = h
+        ln = self.enc.layer_norm
+        st.h_final, st.mean_f, st.rstd_f = ops.layernorm_fwd(h, ln.weight.detach(), ln.bias.detach(), ln.eps, save_stats=training)
+        st.logits = None
+        if want_logits:
+            if self.lm_head is None:
+                raise RuntimeError("JLEngine.forward: no lm_head attached")
+            out_dtype = F32 if cfg.logits_dtype == "float32" else BF16
+            st.logits = ops.gemm(st.h_final, self._bf16(self.lm_head.weight), bias=self.lm_head.bias.detach(), out_dtype=out_dtype)
+        return st
+
+    # ------------------------------------------------------------------ backward (adapter-only)
+    def lowest_adapter_layer(self) -> int:
+        for i, layer in enumerate(self.enc.layers):
+            if layer.adapter_attn is not None or layer.adapter_ffn is not None:
+                return i
+        return len(self.enc.layers)
+
+    def backward(self, st: _State, dlogits: torch.Tensor, g: "GradSink") -> None:
+        """dlogits [B*T', V] bf16 (d loss / d logits, zero on padded rows) → adapter + lm_head gradients into ``g``."""
+        for n, p in self._backbone_params():
+            if p.requires_grad:
+                raise NotImplementedError(
+                    f"backbone parameter {n} requires grad: this path implements the adapter-only backward of the reference "
+                    "(call freeze_base_model())")
+        MN = L.JL_LAYOUT_MN
+        cfg = self.cfg
+        d, heads = cfg.hidden_size, cfg.num_attention_heads
+        b, t = st.b, st.t
+        fz = self._frozen_pack()
+        lengths = st.lengths
+        # head: logits = h_final · Wᵀ + b
+        ops.gemm(dlogits, st.h_final, a_layout=MN, b_layout=MN, out=g.out(self.lm_head.weight), out_dtype=F32)   # dlogitsᵀ · h_final
+        ops.colsum(dlogits, out=g.out(self.lm_head.bias))
+        l0 = self.lowest_adapter_layer()
+        if l0 >= len(self.enc.layers):
+            return
+        dhf = ops.gemm(dlogits, self._bf16(self.lm_head.weight), b_layout=MN)                                   # dlogits · W
+        ln = self.enc.layer_norm
+        dh, _, _ = ops.layernorm_bwd(dhf, st.h_last, ln.weight.detach(), st.mean_f, st.rstd_f)
+        for i in range(len(self.enc.layers) - 1, l0 - 1, -1):
+            layer, sv = self.enc.layers[i], st.layers[i]
+            if layer.adapter_ffn is not None:
+                dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g)
+                if i == l0 and layer.adapter_attn is None:
+                    break
+            # FFN: h2 = h1 + W2 · gelu(W1 · LN2(h1) + b1) + b2
+            dpre = ops.gemm(dh, fz[f"{i}.w2"], b_layout=MN, epilogue=L.JL_EPI_GELU_BWD, aux=sv.pre)
+            dx2 = ops.gemm(dpre, fz[f"{i}.w1"], b_layout=MN)
+            fl = layer.final_layer_norm
+            dh1, _, _ = ops.layernorm_bwd(dx2, sv.h1, fl.weight.detach(), sv.mean2, sv.rstd2, dres=dh)
+            if layer.adapter_attn is not None:
+                dh1 = self._adapter_bwd(layer.adapter_attn, sv.ad_attn, dh1, lengths, b, t, g)
+                if i == l0:
+                    break
+            # attention: h1 = h + Wo · attn(LN1(h) Wqkvᵀ) + bo
+            d_o = ops.gemm(dh1, fz[f"{i}.wo"], b_layout=MN)
+            qkv = sv.qkv
+            dqkv = ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], sv.o, d_o, sv.lse, lengths, b, t, heads, 1.0 / 8.0)
+            dx1 = ops.gemm(dqkv, fz[f"{i}.wqkv"], b_layout=MN)
+            l1 = layer.layer_norm
+            dh, _, _ = ops.layernorm_bwd(dx1, sv.h_in, l1.weight.detach(), sv.mean1, sv.rstd1, dres=dh1)
+
+
+class GradSink:
+    """Where the backward pass writes weight gradients: fp32 tensors keyed by parameter.  The default sink allocates a
+    tensor per parameter; ``training.FlatAdapterParams`` hands out views of one contiguous bucket instead."""
+
+    def __init__(self):
+        self.grads: Dict[int, torch.Tensor] = {}
+        self.params: Dict[int, torch.Tensor] = {}
+
+    def _full(self, p: torch.Tensor) -> torch.Tensor:
+        gt = self.grads.get(id(p))
+        if gt is None:
+            gt = torch.zeros(p.shape, dtype=F32, device=p.device)
+            self.grads[id(p)] = gt
+            self.params[id(p)] = p
+        return gt
+
+    def out(self, p: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
+        gt = self._full(p)
+        return gt if k is None else gt[k]
+
+    def out_cat(self, ps: List[torch.Tensor]) -> torch.Tensor:
+        rows = sum(p.shape[0] for p in ps)
+        return torch.empty((rows,) + tuple(ps[0].shape[1:]), dtype=F32, device=ps[0].device)
+
+    def scatter_cat(self, ps: List[torch.Tensor], cat: torch.Tensor) -> None:
+        off = 0
+        for p in ps:
+            self._full(p).copy_(cat[off: off + p.shape[0]])
+            off += p.shape[0]
+
+
+# =============================================================================================== CTC model
+class _CTCStep(torch.autograd.Function):
+    """Autograd bridge: forward ran in the engine; backward runs the engine's adapter-only backward and returns the
+    adapter / lm_head gradients so that ``loss.backward()`` + any torch optimizer work unchanged."""
+
+    @staticmethod
+    def forward(ctx, model, st, dlogits, loss, *params):
+        ctx.model, ctx.st, ctx.dlogits, ctx.n = model, st, dlogits, len(params)
+        ctx.params = params
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        sink = GradSink()
+        eng = ctx.model.encoder.engine(ctx.model.lm_head)
+        b, t = ctx.st.b, ctx.st.t
+        eng.backward(ctx.st, ctx.dlogits.view(b * t, -1), sink)
+        grads = []
+        for p in ctx.params:
+            gt = sink.grads.get(id(p))
+            grads.append(None if gt is None else gt * gloss)
+        return (None, None, None, None, *grads)
+
+
+class JLForCTC(nn.Module):
+    """Encoder + ``lm_head`` + CTC loss, HF ``Wav2Vec2ForCTC``-style interface."""
+
+    def __init__(self, config: JLConfig):
+        super().__init__()
+        self.config = config
+        self.encoder = JLEncoder(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size)
+        self.init_weights(seed=0)
+
+    # ---- init (modeling_wav2vec2.py:990-1003: Linear N(0, 0.02) / bias 0, LayerNorm 1 / 0, Conv1d kaiming-normal)
+    def init_weights(self, seed: int = 0) -> None:
+        gen = torch.Generator().manual_seed(seed)
+        std = self.config.initializer_range
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * std)
+                    m.bias.zero_()
+                elif isinstance(m, nn.LayerNorm):
+                    m.weight.fill_(1.0)
+                    m.bias.zero_()
+                elif isinstance(m, nn.Conv1d):
+                    fan_in = m.in_channels * m.kernel_size[0]
+                    m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * math.sqrt(2.0 / fan_in))
+                    bound = math.sqrt(1.0 / fan_in)
+                    m.bias.copy_((torch.rand(m.bias.shape, generator=gen) * 2 - 1) * bound)
+                elif isinstance(m, (WFAdapter, AttAdapter)):
+                    m.reset_parameters(std, gen)
+
+    # ---- adapter management
+    def freeze_base_model(self) -> None:
+        """Frozen backbone, trainable adapters + lm_head (modeling_wav2vec2.py:1666-1672)."""
+        for p in self.parameters():
+            p.requires_grad = False
+        for p in self._get_adapters().values():
+            p.requires_grad = True
+
+    def _get_adapters(self) -> Dict[str, nn.Parameter]:
+        """name → Parameter for every adapter layer plus lm_head (modeling_wav2vec2.py:1046-1060)."""
+        out = {}
+        for n, p in self.named_parameters():
+            if ".adapter_attn." in n or ".adapter_ffn." in n or n.startswith("lm_head."):
+                out[n] = p
+        return out
+
+    def init_adapter_layers(self, seed: Optional[int] = None) -> None:
+        """Re-initialise adapters and lm_head (modeling_wav2vec2.py:1062-1073)."""
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        std = self.config.initializer_range
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, (WFAdapter, AttAdapter)):
+                    m.reset_parameters(std, gen)
+            self.lm_head.weight.copy_((torch.randn(self.lm_head.weight.shape, generator=gen) * std).to(self.lm_head.weight.device))
+            self.lm_head.bias.zero_()
+
+    def save_adapter(self, path: str) -> None:
+        torch.save({n: p.detach().cpu() for n, p in self._get_adapters().items()}, path)
+
+    def load_adapter(self, path: str, strict: bool = True) -> None:
+        """Swap a per-dialect adapter state dict in place (local file only); lm_head is resized to the file's
+        vocabulary like modeling_wav2vec2.py:1230-1244."""
+        if not os.path.isfile(path):
+            raise EnvironmentError(f"adapter file {path} not found (local files only)")
+        sd = torch.load(path, map_location="cpu")
+        mine = self._get_adapters()
+        unexpected = set(sd) - set(mine)
+        missing = set(mine) - set(sd)
+        if strict and (unexpected or missing):
+            raise ValueError(f"adapter weights do not match: unexpected {sorted(unexpected)}, missing {sorted(missing)}")
+        new_vocab = sd["lm_head.weight"].shape[0] if "lm_head.weight" in sd else self.config.vocab_size
+        if new_vocab != self.config.vocab_size:
+            dev = self.lm_head.weight.device
+            self.lm_head = nn.Linear(self.config.hidden_size, new_vocab).to(dev)
+            self.config.vocab_size = new_vocab
+            mine = self._get_adapters()
+        with torch.no_grad():
+            for n, v in sd.items():
+                if n in mine:
+                    mine[n].copy_(v.to(mine[n].device, mine[n].dtype))
+
+    # ---- forward
+    def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, frame_lengths: Optional[torch.Tensor] = None, dialect: int = 0):
+        """→ (loss | None, logits [B, T', V]).  ``labels`` [B, S] padded with -100 (any negative value)."""
+        cfg = self.config
+        eng = self.encoder.engine(self.lm_head)
+        lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
+        train = labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self._get_adapters().values())
+        st = eng.forward(input_features, lengths, training=train, dialect=dialect, want_logits=True)
+        b, t = st.b, st.t
+        logits = st.logits.view(b, t, cfg.vocab_size)
+        if labels is None:
+            return None, logits
+        if int(labels.max()) >= cfg.vocab_size:
+            raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
+        lab = labels.to(device=logits.device, dtype=I32)
+        loss, nll, grad = ops.ctc_loss(logits, lab, lengths, blank=cfg.pad_token_id, reduction=cfg.ctc_loss_reduction,
+                                       zero_infinity=cfg.ctc_zero_infinity, want_grad=train, grad_dtype=BF16)
+        loss = loss.view(())
+        if train:
+            params = [p for p in self._get_adapters().values() if p.requires_grad]
+            loss = _CTCStep.apply(self, st, grad, loss, *params)
+        return loss, logits
+
+    def output_lengths(self, input_features, attention_mask=None, frame_lengths=None) -> torch.Tensor:
+        return self.encoder.engine(self.lm_head).output_lengths(input_features, attention_mask, frame_lengths)
+
+    @torch.no_grad()
+    def greedy_decode(self, logits: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+        """argmax → collapse repeats → strip blank (tokenization_wav2vec2.py:310-317) on the GPU; only the compacted
+        ids cross to the host."""
+        ids, n, _ = ops.ctc_greedy(logits, lengths.to(I32), blank=self.config.pad_token_id)
+        ids, n = ids.cpu(), n.cpu()
+        return [ids[i, : int(n[i])].tolist() for i in range(ids.shape[0])]
+
+    @torch.no_grad()
+    def transcribe(self, input_features, attention_mask=None, frame_lengths=None) -> List[List[int]]:
+        _, logits = self.forward(input_features, attention_mask, None, frame_lengths)
+        return self.greedy_decode(logits, self.output_lengths(input_features, attention_mask, frame_lengths))

@@ -1,0 +1,324 @@
+"""Tensor-level wrappers over the C ABI (``include/jl_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every computation below is a call into
+``libjl_b200.so``.  All wrappers enqueue on ``torch.cuda.current_stream()`` and never synchronise.  There is no
+fallback path: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libjl_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
+
+
+def _rows2d(t: torch.Tensor, name: str) -> None:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+
+
+# ----------------------------------------------------------------------------------------------- mel + CMVN
+def mel_cmvn(wave: torch.Tensor, num_samples: torch.Tensor, tables: dict, max_frames: int, apply_cmvn: bool = True,
+             want_bf16: bool = False):
+    """wave [B, N] fp32, num_samples [B] int32 → (feats fp32 [B, F, 80], feats bf16 | None, mask int32 [B, F], frame_lengths int32 [B])."""
+    _need(wave, F32, "wave", 2)
+    _need(num_samples, I32, "num_samples", 1)
+    if wave.stride(1) != 1:
+        raise ValueError("wave: inner stride must be 1")
+    b = wave.shape[0]
+    dev = wave.device
+    feats = torch.empty((b, max_frames, L.JL_MEL_BINS), dtype=F32, device=dev)
+    feats16 = torch.empty((b, max_frames, L.JL_MEL_BINS), dtype=BF16, device=dev) if want_bf16 else None
+    mask = torch.empty((b, max_frames), dtype=I32, device=dev)
+    flen = torch.empty((b,), dtype=I32, device=dev)
+    p = L.MelCmvnParams(wave=wave.data_ptr(), wave_stride=wave.stride(0), num_samples=num_samples.data_ptr(), batch=b,
+                        max_frames=max_frames, window=tables["window"].data_ptr(), twiddle=tables["twiddle"].data_ptr(),
+                        mel_lo=tables["mel_lo"].data_ptr(), mel_cnt=tables["mel_cnt"].data_ptr(), mel_w=tables["mel_w"].data_ptr(),
+                        feats=feats.data_ptr(), feats_bf16=_ptr(feats16), attention_mask=mask.data_ptr(),
+                        frame_lengths=flen.data_ptr(), apply_cmvn=1 if apply_cmvn else 0)
+    lib = L.load()
+    nbytes = C.c_size_t(0)
+    L.check(lib.jl_mel_cmvn_workspace_bytes(C.byref(p), C.byref(nbytes)))
+    ws = torch.empty((max(nbytes.value, 16),), dtype=torch.uint8, device=dev)
+    L.check(lib.jl_mel_cmvn_fwd(C.byref(p), ws.data_ptr(), _stream()))
+    return feats, feats16, mask, flen
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, epilogue: int = L.JL_EPI_NONE,
+         residual: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
+         row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0, out: Optional[torch.Tensor] = None,
+         out_dtype=BF16, alpha: float = 1.0, a_layout: int = L.JL_LAYOUT_K, b_layout: int = L.JL_LAYOUT_K,
+         reference: bool = False) -> torch.Tensor:
+    """C[M, N] = epilogue(alpha · A · Bᵀ + bias).  A is [M, K] (layout K) or [K, M] (layout MN); B is [N, K] or [K, N]."""
+    _need(a, BF16, "a")
+    _need(b, BF16, "b")
+    _rows2d(a, "a")
+    _rows2d(b, "b")
+    m, k = (a.shape[0], a.shape[1]) if a_layout == L.JL_LAYOUT_K else (a.shape[1], a.shape[0])
+    n, kb = (b.shape[0], b.shape[1]) if b_layout == L.JL_LAYOUT_K else (b.shape[1], b.shape[0])
+    if k != kb:
+        raise ValueError(f"gemm: K mismatch ({k} vs {kb})")
+    n_out = n // 2 if epilogue == L.JL_EPI_GLU else n
+    if out is None:
+        out = torch.empty((m, n_out), dtype=out_dtype, device=a.device)
+    else:
+        _rows2d(out, "out")
+        if tuple(out.shape) != (m, n_out):
+            raise ValueError(f"gemm: out has shape {tuple(out.shape)}, expected {(m, n_out)}")
+    if bias is not None:
+        _need(bias, F32, "bias", 1)
+    for t, nm in ((residual, "residual"), (aux, "aux"), (aux_out, "aux_out")):
+        if t is not None:
+            _need(t, BF16, nm)
+            _rows2d(t, nm)
+    if row_lengths is not None:
+        _need(row_lengths, I32, "row_lengths", 1)
+    p = L.GemmParams(a=a.data_ptr(), lda=a.stride(0), b=b.data_ptr(), ldb=b.stride(0), a_layout=a_layout, b_layout=b_layout,
+                     c=out.data_ptr(), ldc=out.stride(0), bias=_ptr(bias),
+                     residual=_ptr(residual), ldr=0 if residual is None else residual.stride(0),
+                     aux=_ptr(aux), ldaux=0 if aux is None else aux.stride(0),
+                     aux_out=_ptr(aux_out), ldaux_out=0 if aux_out is None else aux_out.stride(0),
+                     row_lengths=_ptr(row_lengths), rows_per_seq=rows_per_seq, m=m, n=n, k=k, epilogue=epilogue,
+                     out_dtype=L.JL_DT_BF16 if out.dtype == BF16 else L.JL_DT_F32, alpha=alpha)
+    if out.dtype not in (BF16, F32):
+        raise TypeError("gemm: out must be bf16 or fp32")
+    lib = L.load()
+    fn = lib.jl_debug_gemm_ref if reference else lib.jl_gemm_bf16
+    L.check(fn(C.byref(p), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, save_stats: bool = False,
+                  out: Optional[torch.Tensor] = None):
+    _need(x, BF16, "x")
+    _rows2d(x, "x")
+    _need(gamma, F32, "gamma", 1)
+    _need(beta, F32, "beta", 1)
+    rows, d = x.shape
+    y = torch.empty((rows, d), dtype=BF16, device=x.device) if out is None else out
+    mean = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
+    rstd = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
+    p = L.LayerNormFwdParams(x=x.data_ptr(), ldx=x.stride(0), gamma=gamma.data_ptr(), beta=beta.data_ptr(), y=y.data_ptr(),
+                             ldy=y.stride(0), mean=_ptr(mean), rstd=_ptr(rstd), rows=rows, d=d, eps=eps)
+    L.check(L.load().jl_layernorm_fwd(C.byref(p), _stream()))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                  dres: Optional[torch.Tensor] = None, want_wgrad: bool = False, dgamma: Optional[torch.Tensor] = None,
+                  dbeta: Optional[torch.Tensor] = None):
+    for t, nm in ((dy, "dy"), (x, "x")):
+        _need(t, BF16, nm)
+        _rows2d(t, nm)
+    rows, d = x.shape
+    dx = torch.empty((rows, d), dtype=BF16, device=x.device)
+    if want_wgrad:
+        dgamma = torch.empty((d,), dtype=F32, device=x.device) if dgamma is None else dgamma
+        dbeta = torch.empty((d,), dtype=F32, device=x.device) if dbeta is None else dbeta
+    p = L.LayerNormBwdParams(dy=dy.data_ptr(), lddy=dy.stride(0), x=x.data_ptr(), ldx=x.stride(0), gamma=gamma.data_ptr(),
+                             mean=mean.data_ptr(), rstd=rstd.data_ptr(), dres=_ptr(dres),
+                             lddres=0 if dres is None else dres.stride(0), dx=dx.data_ptr(), lddx=dx.stride(0),
+                             dgamma=_ptr(dgamma) if want_wgrad else None, dbeta=_ptr(dbeta) if want_wgrad else None,
+                             partial=None, rows=rows, d=d)
+    lib = L.load()
+    partial = None
+    if want_wgrad:
+        nbytes = C.c_size_t(0)
+        L.check(lib.jl_layernorm_bwd_workspace_bytes(C.byref(p), C.byref(nbytes)))
+        partial = torch.empty((max(nbytes.value // 4, 4),), dtype=F32, device=x.device)
+        p.partial = partial.data_ptr()
+    L.check(lib.jl_layernorm_bwd(C.byref(p), _stream()))
+    return dx, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int, heads: int,
+             scale: float, want_lse: bool = False):
+    """q/k/v: [B*seq, heads*64] views (unit inner stride, common row stride).  Returns (o [B*seq, heads*64] bf16, lse | None)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, BF16, nm)
+        _rows2d(t, nm)
+    if not (q.stride(0) == k.stride(0) == v.stride(0)):
+        raise ValueError("attn: q, k, v must share one row stride")
+    if q.shape[0] != batch * seq or q.shape[1] != heads * 64:
+        raise ValueError(f"attn: q has shape {tuple(q.shape)}, expected {(batch * seq, heads * 64)} (head_dim is 64)")
+    o = torch.empty((batch * seq, heads * 64), dtype=BF16, device=q.device)
+    lse = torch.empty((batch, heads, seq), dtype=F32, device=q.device) if want_lse else None
+    p = L.AttnFwdParams(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), ld_qkv=q.stride(0), o=o.data_ptr(), ld_o=o.stride(0),
+                        lse=_ptr(lse), lengths=_ptr(lengths), batch=batch, seq=seq, heads=heads, scale=scale)
+    L.check(L.load().jl_attn_fwd(C.byref(p), _stream()))
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, lengths, batch: int, seq: int, heads: int, scale: float):
+    """Returns dqkv [B*seq, 3*heads*64] bf16 (dq | dk | dv column blocks)."""
+    hd = heads * 64
+    dqkv = torch.empty((batch * seq, 3 * hd), dtype=BF16, device=q.device)
+    delta = torch.empty((batch, heads, seq), dtype=F32, device=q.device)
+    for t, nm in ((o, "o"), (d_o, "d_o")):
+        _need(t, BF16, nm)
+        _rows2d(t, nm)
+    if o.stride(0) != d_o.stride(0):
+        raise ValueError("attn_bwd: o and d_o must share one row stride")
+    p = L.AttnBwdParams(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), ld_qkv=q.stride(0), o=o.data_ptr(), d_o=d_o.data_ptr(),
+                        ld_o=o.stride(0), lse=lse.data_ptr(), dq=dqkv.data_ptr(), dk=dqkv[:, hd:].data_ptr(),
+                        dv=dqkv[:, 2 * hd:].data_ptr(), ld_dqkv=dqkv.stride(0), delta=delta.data_ptr(), lengths=_ptr(lengths),
+                        batch=batch, seq=seq, heads=heads, scale=scale)
+    L.check(L.load().jl_attn_bwd(C.byref(p), _stream()))
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------- CTC
+def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, input_lengths: torch.Tensor, blank: int = 0, reduction: str = "sum",
+             zero_infinity: bool = False, want_grad: bool = False, grad_dtype=BF16):
+    """logits [B, T, V] (fp32 | bf16, unit inner stride), labels [B, S] int32 (negative = pad), input_lengths [B] int32.
+    Returns (loss [1] fp32, nll [B] fp32, grad [B, T, V] | None)."""
+    if logits.dtype not in (F32, BF16):
+        raise TypeError("ctc_loss: logits must be fp32 or bf16")
+    _need(logits, logits.dtype, "logits", 3)
+    _need(labels, I32, "labels", 2)
+    _need(input_lengths, I32, "input_lengths", 1)
+    if reduction not in ("sum", "mean"):
+        raise ValueError(f"ctc_loss: unsupported reduction {reduction!r}")
+    b, t, v = logits.shape
+    if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
+        raise ValueError("ctc_loss: logits must be row-contiguous [B*T, V]")
+    labels = labels.contiguous()
+    dev = logits.device
+    nll = torch.empty((b,), dtype=F32, device=dev)
+    loss = torch.empty((1,), dtype=F32, device=dev)
+    grad = torch.empty((b, t, v), dtype=grad_dtype, device=dev) if want_grad else None
+    p = L.CtcParams(logits=logits.data_ptr(), ld_logits=logits.stride(1), logits_dtype=L.JL_DT_F32 if logits.dtype == F32 else L.JL_DT_BF16,
+                    labels=labels.data_ptr(), max_label_len=labels.shape[1], input_lengths=input_lengths.data_ptr(), batch=b, seq=t,
+                    vocab=v, blank=blank, reduction=L.JL_CTC_SUM if reduction == "sum" else L.JL_CTC_MEAN,
+                    zero_infinity=1 if zero_infinity else 0, nll=nll.data_ptr(), loss=loss.data_ptr(), grad=_ptr(grad),
+                    ld_grad=v, grad_dtype=L.JL_DT_F32 if grad_dtype == F32 else L.JL_DT_BF16)
+    lib = L.load()
+    nbytes = C.c_size_t(0)
+    L.check(lib.jl_ctc_workspace_bytes(C.byref(p), C.byref(nbytes)))
+    ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+    L.check(lib.jl_ctc_fwd(C.byref(p), ws.data_ptr(), _stream()))
+    return loss, nll, grad
+
+
+def ctc_greedy(logits: torch.Tensor, input_lengths: torch.Tensor, blank: int = 0):
+    """→ (out_ids [B, T] int32 with -1 tail, out_lengths [B] int32, frame_ids [B, T] int32)."""
+    if logits.dtype not in (F32, BF16):
+        raise TypeError("ctc_greedy: logits must be fp32 or bf16")
+    _need(logits, logits.dtype, "logits", 3)
+    _need(input_lengths, I32, "input_lengths", 1)
+    b, t, v = logits.shape
+    if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
+        raise ValueError("ctc_greedy: logits must be row-contiguous [B*T, V]")
+    dev = logits.device
+    frame_ids = torch.empty((b, t), dtype=I32, device=dev)
+    out_ids = torch.empty((b, t), dtype=I32, device=dev)
+    out_len = torch.empty((b,), dtype=I32, device=dev)
+    p = L.CtcGreedyParams(logits=logits.data_ptr(), ld_logits=logits.stride(1),
+                          logits_dtype=L.JL_DT_F32 if logits.dtype == F32 else L.JL_DT_BF16, input_lengths=input_lengths.data_ptr(),
+                          batch=b, seq=t, vocab=v, blank=blank, frame_ids=frame_ids.data_ptr(), out_ids=out_ids.data_ptr(),
+                          out_lengths=out_len.data_ptr())
+    L.check(L.load().jl_ctc_greedy(C.byref(p), _stream()))
+    return out_ids, out_len, frame_ids
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def im2col_k5s2(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """[B, T, C] bf16 contiguous → ([B*T_out, 5*C] bf16, T_out) for Conv1d(k=5, s=2, p=2)."""
+    _need(x, BF16, "x", 3)
+    if not x.is_contiguous():
+        raise ValueError("im2col: x must be contiguous")
+    b, t, c = x.shape
+    t_out = (t - 1) // 2 + 1
+    out = torch.empty((b * t_out, 5 * c), dtype=BF16, device=x.device)
+    L.check(L.load().jl_im2col_k5s2(x.data_ptr(), out.data_ptr(), b, t, c, t_out, _stream()))
+    return out, t_out
+
+
+def embed_positions_(h: torch.Tensor, scale: float, pos_table: torch.Tensor, lengths: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
+    _need(h, BF16, "h", 2)
+    _need(pos_table, F32, "pos_table", 2)
+    _need(lengths, I32, "lengths", 1)
+    if not h.is_contiguous() or pos_table.shape[0] < seq + 2 or pos_table.shape[1] != h.shape[1] or not pos_table.is_contiguous():
+        raise ValueError("embed_positions: bad shapes")
+    L.check(L.load().jl_embed_positions(h.data_ptr(), scale, pos_table.data_ptr(), lengths.data_ptr(), batch, seq, h.shape[1], _stream()))
+    return h
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    _need(x, BF16, "x")
+    _rows2d(x, "x")
+    rows, cols = x.shape
+    ld_out = (rows + 7) // 8 * 8
+    out = torch.zeros((cols, ld_out), dtype=BF16, device=x.device) if ld_out != rows else torch.empty((cols, rows), dtype=BF16, device=x.device)
+    L.check(L.load().jl_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _stream()))
+    return out[:, :rows]
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, BF16, "x")
+    _rows2d(x, "x")
+    rows, cols = x.shape
+    out = torch.empty((cols,), dtype=F32, device=x.device) if out is None else out
+    lib = L.load()
+    nbytes = C.c_size_t(0)
+    L.check(lib.jl_colsum_workspace_bytes(rows, cols, C.byref(nbytes)))
+    partial = torch.empty((nbytes.value // 4,), dtype=F32, device=x.device)
+    L.check(lib.jl_colsum_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, partial.data_ptr(), _stream()))
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, F32, "x")
+    if not x.is_contiguous():
+        raise ValueError("cast_bf16: x must be contiguous")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device) if out is None else out
+    if x.numel():
+        L.check(L.load().jl_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()))
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(a, BF16, "a")
+    _need(b, BF16, "b")
+    if not (a.is_contiguous() and b.is_contiguous()) or a.shape != b.shape:
+        raise ValueError("add: operands must be contiguous and of equal shape")
+    out = torch.empty_like(a) if out is None else out
+    L.check(L.load().jl_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()))
+    return out
+
+
+def adamw_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, lr: float,
+           beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01, grad_scale: float = 1.0,
+           param_bf16: Optional[torch.Tensor] = None) -> None:
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _need(t, F32, nm, 1)
+        if not t.is_contiguous():
+            raise ValueError(f"adamw: {nm} must be contiguous")
+    p = L.AdamWParams(param=param.data_ptr(), grad=grad.data_ptr(), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(),
+                      param_bf16=_ptr(param_bf16), n=param.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                      weight_decay=weight_decay, grad_scale=grad_scale, step=step)
+    L.check(L.load().jl_adamw_bucket(C.byref(p), _stream()))

@@ -1,0 +1,292 @@
+"""Adapter fine-tuning plumbing around the kernels: one flat fp32 bucket for the trainable parameters (adapters +
+lm_head), their gradients and AdamW state; one NCCL all-reduce of that bucket per step (the only collective on the
+path — the backbone is frozen); a fused AdamW kernel that also refreshes the bf16 shadow the GEMMs read;
+and CUDA-graph capture of the whole step (waveform → mel → encoder → CTC → adapter-only backward) so that the
+≈ 500 kernel launches of a step cost one graph launch.
+
+Replaces, for this path, DDP's bucketed reducer + ``torch.optim.AdamW`` as a SpeechBrain/HF recipe would use them
+(/root/reference/requirements.txt:1,71,75).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import ops
+from .feature_extraction import JLFeatureExtractor, device_tables, num_frames
+from .modeling import AttAdapter, GradSink, JLForCTC, subsampled_length
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+_ALIGN = 64   # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 buffer
+
+
+def _ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
+    """Trainable parameters, with each AttAdapter's q/k/v weights (and biases) adjacent so that the concatenated
+    [192, d] projection the kernels use is a plain view of the bucket."""
+    seen, out = set(), []
+
+    def add(p):
+        if id(p) not in seen and p.requires_grad:
+            seen.add(id(p))
+            out.append(p)
+
+    for m in model.modules():
+        if isinstance(m, AttAdapter):
+            for p in (m.q_proj.weight, m.k_proj.weight, m.v_proj.weight, m.q_proj.bias, m.k_proj.bias, m.v_proj.bias):
+                add(p)
+    for p in model._get_adapters().values():
+        add(p)
+    return out
+
+
+class FlatAdapterParams(GradSink):
+    """Flat storage for the trainable set.  After construction every trainable ``nn.Parameter``'s ``.data`` is a view
+    of ``self.param``; gradients are written by the backward kernels straight into ``self.grad``."""
+
+    def __init__(self, model: JLForCTC):
+        super().__init__()
+        self.model = model
+        self.plist = _ordered_trainables(model)
+        if not self.plist:
+            raise ValueError("no trainable parameters: call model.freeze_base_model() first")
+        dev = self.plist[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdapterParams needs the model on a CUDA device")
+        self.offset: Dict[int, int] = {}
+        off = 0
+        for p in self.plist:
+            self.offset[id(p)] = off
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.num_params = sum(p.numel() for p in self.plist)
+        self.param = torch.zeros(off, dtype=F32, device=dev)
+        self.grad = torch.zeros(off, dtype=F32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=F32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=F32, device=dev)
+        self.bf16 = torch.zeros(off, dtype=BF16, device=dev)
+        with torch.no_grad():
+            for p in self.plist:
+                v = self._view(self.param, p)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = self._view(self.grad, p)
+        ops.cast_bf16(self.param, out=self.bf16)
+        self.step_count = 0
+        model.encoder.engine(model.lm_head).flat = self
+
+    def _view(self, buf: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+        o = self.offset[id(p)]
+        return buf[o: o + p.numel()].view(p.shape)
+
+    def _adjacent(self, ps: Sequence[torch.Tensor]) -> bool:
+        for a, b in zip(ps[:-1], ps[1:]):
+            if id(a) not in self.offset or id(b) not in self.offset or a.numel() % _ALIGN:
+                return False
+            if self.offset[id(b)] != self.offset[id(a)] + a.numel() or a.shape[1:] != b.shape[1:]:
+                return False
+        return id(ps[-1]) in self.offset
+
+    def _cat(self, buf: torch.Tensor, ps: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+        if not self._adjacent(ps):
+            return None
+        o = self.offset[id(ps[0])]
+        n = sum(p.numel() for p in ps)
+        rows = sum(p.shape[0] for p in ps)
+        return buf[o: o + n].view((rows,) + tuple(ps[0].shape[1:]))
+
+    # ---- views the engine asks for
+    def bf16_view(self, p):
+        return self._view(self.bf16, p) if id(p) in self.offset else None
+
+    def bf16_cat_view(self, ps):
+        return self._cat(self.bf16, ps)
+
+    def f32_cat_view(self, ps):
+        return self._cat(self.param, ps)
+
+    # ---- GradSink interface
+    def out(self, p, k=None):
+        gt = self._view(self.grad, p)
+        return gt if k is None else gt[k]
+
+    def out_cat(self, ps):
+        v = self._cat(self.grad, ps)
+        return v if v is not None else super().out_cat(ps)
+
+    def scatter_cat(self, ps, cat):
+        if self._cat(self.grad, ps) is None:
+            off = 0
+            for p in ps:
+                self._view(self.grad, p).copy_(cat[off: off + p.shape[0]])
+                off += p.shape[0]
+
+    # ---- collective + optimizer
+    def allreduce(self) -> None:
+        """Sum of the gradient bucket over ranks — the single collective of the fine-tune step (NCCL over NVLink)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    def adamw_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01) -> None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.step_count += 1
+        ops.adamw_(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, beta1, beta2, eps, weight_decay,
+                   grad_scale=1.0 / world, param_bf16=self.bf16)
+
+
+def shard_utterances(num_frames_per_utt: Sequence[int], world: int) -> List[List[int]]:
+    """Length-sorted round-robin assignment of utterance indices to ranks so every rank gets ≈ equal total frames
+    (mixed-length config 4).  Deterministic; returns one index list per rank."""
+    order = sorted(range(len(num_frames_per_utt)), key=lambda i: (-num_frames_per_utt[i], i))
+    shards: List[List[int]] = [[] for _ in range(world)]
+    loads = [0] * world
+    for i in order:
+        r = min(range(world), key=lambda j: (loads[j], j))
+        shards[r].append(i)
+        loads[r] += num_frames_per_utt[i]
+    return shards
+
+
+class AdapterTrainer:
+    """One fine-tune step = H2D(waveforms, labels) → [mel+CMVN → encoder → lm_head → CTC loss+grad → adapter-only
+    backward] → all-reduce(adapter grads) → fused AdamW → D2H(loss).  The bracketed part is captured in a CUDA graph
+    per (batch, samples, label length) shape."""
+
+    def __init__(self, model: JLForCTC, lr: float = 1e-4, weight_decay: float = 0.01, use_cuda_graph: bool = True):
+        self.model = model
+        self.cfg = model.config
+        self.flat = FlatAdapterParams(model)
+        self.eng = model.encoder.engine(model.lm_head)
+        self.fe = JLFeatureExtractor(device=self.flat.param.device)
+        self.lr, self.weight_decay = lr, weight_decay
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[tuple, dict] = {}
+        self.launches_per_step = 0
+
+    def _body(self, wave, nsamp, lengths, labels, max_frames):
+        feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
+        st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, want_logits=True)
+        b, t = st.b, st.t
+        logits = st.logits.view(b, t, self.cfg.vocab_size)
+        loss, nll, grad = ops.ctc_loss(logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
+                                       zero_infinity=self.cfg.ctc_zero_infinity, want_grad=True, grad_dtype=BF16)
+        self.eng.backward(st, grad.view(b * t, -1), self.flat)
+        return loss
+
+    def _static(self, b: int, n: int, s: int) -> dict:
+        key = (b, n, s)
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
+        dev = self.flat.param.device
+        ent = {
+            "wave": torch.zeros((b, n), dtype=F32, device=dev),
+            "nsamp": torch.full((b,), n, dtype=I32, device=dev),
+            "lengths": torch.ones((b,), dtype=I32, device=dev),
+            "labels": torch.full((b, s), -100, dtype=I32, device=dev),
+            "max_frames": max(num_frames(n), 1),
+            "graph": None,
+            "loss": None,
+        }
+        self._graphs[key] = ent
+        return ent
+
+    def step(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad).
+        Returns the loss as a 1-element device tensor (call ``.item()`` for the D2H read)."""
+        b, n = wave.shape
+        s = labels.shape[1]
+        ent = self._static(b, n, s)
+        ent["wave"].copy_(wave, non_blocking=True)
+        ent["nsamp"].copy_(num_samples, non_blocking=True)
+        frames = torch.clamp((num_samples.to(torch.int64) - 400) // 160 + 1, min=0)
+        frames = torch.where(num_samples.to(torch.int64) < 400, torch.zeros_like(frames), frames)
+        ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
+        ent["labels"].copy_(labels, non_blocking=True)
+        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"])
+        if not self.use_cuda_graph:
+            L.launch_count_reset()
+            loss = self._body(*args)
+            self.launches_per_step = L.launch_count()
+        else:
+            if ent["graph"] is None:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):                      # warm-up: lazy packs, cudaFuncSetAttribute, allocator
+                        L.launch_count_reset()
+                        self._body(*args)
+                        self.launches_per_step = L.launch_count()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ent["loss"] = self._body(*args)
+                ent["graph"] = graph
+            ent["graph"].replay()
+            loss = ent["loss"]
+        self.flat.allreduce()
+        self.flat.adamw_step(self.lr, weight_decay=self.weight_decay)
+        return loss
+
+
+class Transcriber:
+    """Inference: H2D(waveforms) → [mel+CMVN → encoder → lm_head → greedy collapse] → D2H(token ids), graph-captured
+    per (batch, samples) shape."""
+
+    def __init__(self, model: JLForCTC, use_cuda_graph: bool = True):
+        self.model = model
+        self.cfg = model.config
+        self.eng = model.encoder.engine(model.lm_head)
+        self.dev = next(model.parameters()).device
+        self.fe = JLFeatureExtractor(device=self.dev)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[tuple, dict] = {}
+        self.launches_per_step = 0
+
+    def _body(self, wave, nsamp, lengths, max_frames):
+        feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
+        st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, want_logits=True)
+        logits = st.logits.view(st.b, st.t, self.cfg.vocab_size)
+        ids, n, _ = ops.ctc_greedy(logits, lengths, blank=self.cfg.pad_token_id)
+        return ids, n
+
+    @torch.no_grad()
+    def __call__(self, wave: torch.Tensor, num_samples: torch.Tensor):
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 host → (ids [B, T'] int32 device, lengths [B])."""
+        b, n = wave.shape
+        key = (b, n)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = {"wave": torch.zeros((b, n), dtype=F32, device=self.dev), "nsamp": torch.full((b,), n, dtype=I32, device=self.dev),
+                   "lengths": torch.ones((b,), dtype=I32, device=self.dev), "max_frames": max(num_frames(n), 1), "graph": None, "out": None}
+            self._graphs[key] = ent
+        ent["wave"].copy_(wave, non_blocking=True)
+        ent["nsamp"].copy_(num_samples, non_blocking=True)
+        ns = num_samples.to(torch.int64)
+        frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
+        ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
+        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"])
+        if not self.use_cuda_graph:
+            L.launch_count_reset()
+            out = self._body(*args)
+            self.launches_per_step = L.launch_count()
+            return out
+        if ent["graph"] is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    L.launch_count_reset()
+                    self._body(*args)
+                    self.launches_per_step = L.launch_count()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ent["out"] = self._body(*args)
+            ent["graph"] = graph
+        ent["graph"].replay()
+        return ent["out"]

@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 GEMM (through the C ABI) against fp32 matmul of the same bf16 operands: every tile width,
+ragged M/N/K, both operand layouts, every epilogue."""
+import math
+
+import pytest
+import torch
+
+from helpers import pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _ops():
+    return pkg().ops, pkg()._lib
+
+
+def _mk(m, n, k, seed=0, a_mn=False, b_mn=False):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(m, k, device="cuda", generator=g) * 0.5).to(BF16)
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.5).to(BF16)
+    a_store = a.t().contiguous() if a_mn else a
+    b_store = b.t().contiguous() if b_mn else b
+    return a, b, a_store, b_store
+
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (128, 256, 768), (200, 136, 72), (1000, 768, 768), (777, 2304, 768),
+          (300, 32, 768), (130, 256, 32), (64, 64, 8), (500, 5000, 768), (8000, 768, 3072), (250, 40, 128)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_gemm_plain(m, n, k):
+    ops, L = _ops()
+    a, b, _, _ = _mk(m, n, k)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b, out_dtype=F32)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-3, (m, n, k)
+    out16 = ops.gemm(a, b)
+    assert rel_err(out16.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("m,n,k", [(256, 256, 128), (200, 136, 72), (768, 32, 1000), (1000, 768, 5000), (5000, 768, 1000),
+                                   (32, 256, 777), (777, 8, 128)])
+def test_gemm_mn_major_operands(m, n, k, a_mn, b_mn):
+    ops, L = _ops()
+    if (a_mn and m % 8) or (b_mn and n % 8) or ((not a_mn or not b_mn) and k % 8):
+        pytest.skip("row stride must be a multiple of 8 elements")
+    a, b, a_s, b_s = _mk(m, n, k, seed=1, a_mn=a_mn, b_mn=b_mn)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a_s, b_s, out_dtype=F32, a_layout=int(a_mn), b_layout=int(b_mn))
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-3, (m, n, k, a_mn, b_mn)
+
+
+def test_gemm_matches_simt_reference_bitwise_epilogue():
+    """Same epilogue code on a SIMT fp32-accumulate kernel: only the accumulation order differs."""
+    ops, L = _ops()
+    a, b, _, _ = _mk(300, 200, 136, seed=3)
+    bias = torch.randn(200, device="cuda")
+    x = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU, out_dtype=F32)
+    y = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU, out_dtype=F32, reference=True)
+    torch.cuda.synchronize()
+    assert rel_err(x, y) < 1e-5
+
+
+def test_gemm_epilogues():
+    ops, L = _ops()
+    m, n, k = 520, 264, 200
+    a, b, _, _ = _mk(m, n, k, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    bias = torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(m, n, device="cuda", generator=g).to(BF16)
+    aux = torch.randn(m, n, device="cuda", generator=g).to(BF16)
+    acc = a.float() @ b.float().t()
+    # bias + alpha
+    out = ops.gemm(a, b, bias=bias, alpha=0.5, out_dtype=F32)
+    assert rel_err(out, 0.5 * acc + bias) < 2e-3
+    # GELU (erf) with saved pre-activation
+    pre = torch.empty(m, n, dtype=BF16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU, aux_out=pre, out_dtype=F32)
+    assert rel_err(out, torch.nn.functional.gelu(acc + bias)) < 2e-3
+    assert rel_err(pre.float(), acc + bias) < 1e-2
+    # ReLU + residual
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_RELU, residual=res, out_dtype=F32)
+    assert rel_err(out, torch.relu(acc + bias) + res.float()) < 2e-3
+    # GELU backward: acc * gelu'(aux)
+    x = aux.float()
+    gp = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    out = ops.gemm(a, b, epilogue=L.JL_EPI_GELU_BWD, aux=aux, out_dtype=F32)
+    assert rel_err(out, acc * gp) < 2e-3
+    # ReLU backward
+    out = ops.gemm(a, b, epilogue=L.JL_EPI_RELU_BWD, aux=aux, out_dtype=F32)
+    assert rel_err(out, acc * (x > 0)) < 2e-3
+    # GLU over interleaved (value, gate) columns
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GLU, out_dtype=F32)
+    v = acc + bias
+    assert out.shape == (m, n // 2)
+    assert rel_err(out, v[:, 0::2] * torch.sigmoid(v[:, 1::2])) < 2e-3
+    # row masking by utterance length
+    rows_per_seq = 130
+    lens = torch.tensor([130, 7, 0, 99], dtype=torch.int32, device="cuda")
+    out = ops.gemm(a, b, bias=bias, residual=res, row_lengths=lens, rows_per_seq=rows_per_seq, out_dtype=F32)
+    ref = acc + bias + res.float()
+    t = torch.arange(m, device="cuda") % rows_per_seq
+    valid = t < lens[torch.arange(m, device="cuda") // rows_per_seq]
+    assert rel_err(out, ref * valid[:, None]) < 2e-3
+    torch.cuda.synchronize()
+
+
+def test_gemm_rejects_bad_arguments():
+    ops, L = _ops()
+    a = torch.zeros(16, 12, dtype=BF16, device="cuda")     # lda = 12, not a multiple of 8
+    b = torch.zeros(16, 12, dtype=BF16, device="cuda")
+    with pytest.raises(L.JLError):
+        ops.gemm(a, b)
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(16, 16, dtype=BF16, device="cuda"), torch.zeros(16, 8, dtype=BF16, device="cuda"))

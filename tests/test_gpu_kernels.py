@@ -1,0 +1,227 @@
+"""GPU parity of LayerNorm, attention, CTC, greedy decode and the elementwise helpers (through the C ABI) against the
+oracle / plain fp32 math on the same seeded inputs."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import ROOT, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+# --------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,d", [(1000, 768), (333, 1024), (64, 128), (17, 2048)])
+def test_layernorm_fwd_bwd(rows, d):
+    ops = pkg().ops
+    g = _g(1)
+    x = (torch.randn(rows, d, device="cuda", generator=g) * 2 + 0.3).to(BF16)
+    gamma = torch.randn(d, device="cuda", generator=g) * 0.2 + 1.0
+    beta = torch.randn(d, device="cuda", generator=g) * 0.1
+    dy = torch.randn(rows, d, device="cuda", generator=g).to(BF16)
+    dres = torch.randn(rows, d, device="cuda", generator=g).to(BF16)
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5, save_stats=True)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (d,), gr, br, 1e-5)
+    assert rel_err(y.float(), yr) < 6e-3
+    assert rel_err(mean, xr.mean(-1)) < 1e-5
+    yr.backward(dy.float())
+    dx, dgamma, dbeta = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dres=dres, want_wgrad=True)
+    assert rel_err(dx.float(), xr.grad + dres.float()) < 8e-3
+    assert rel_err(dgamma, gr.grad) < 2e-3
+    assert rel_err(dbeta, br.grad) < 2e-3
+    dx2, _, _ = ops.layernorm_bwd(dy, x, gamma, mean, rstd)          # frozen norm: dx only
+    assert rel_err(dx2.float(), xr.grad) < 8e-3
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, lengths, b, t, h, scale):
+    q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in (q, k, v))
+    valid = torch.arange(t, device=q.device)[None, :] < lengths[:, None]
+    s = q @ k.transpose(2, 3) * scale
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    p = torch.nan_to_num(p)
+    o = (p @ v).transpose(1, 2).reshape(b * t, h * 64)
+    return o * valid.reshape(b * t, 1)
+
+
+@pytest.mark.parametrize("b,t,h,lens", [(3, 250, 12, [250, 131, 64]), (2, 70, 1, [70, 1]), (2, 750, 2, [750, 300]), (1, 33, 3, [20])])
+def test_attention_fwd_bwd(b, t, h, lens):
+    ops = pkg().ops
+    g = _g(2)
+    d = h * 64
+    qkv = (torch.randn(b * t, 3 * d, device="cuda", generator=g)).to(BF16)
+    lengths = torch.tensor(lens, dtype=I32, device="cuda")
+    scale = 0.125
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    o, lse = ops.attn_fwd(q, k, v, lengths, b, t, h, scale, want_lse=True)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr[:, :d], qr[:, d:2 * d], qr[:, 2 * d:], lengths, b, t, h, scale)
+    assert rel_err(o.float(), ref) < 1e-2
+    valid = (torch.arange(t, device="cuda")[None, :] < lengths[:, None]).reshape(b * t, 1)
+    assert float((o.float() * (~valid)).abs().max()) == 0.0
+    d_o = (torch.randn(b * t, d, device="cuda", generator=g) * valid).to(BF16)
+    ref.backward(d_o.float())
+    dqkv = ops.attn_bwd(q, k, v, o, d_o, lse, lengths, b, t, h, scale)
+    torch.cuda.synchronize()
+    gref = qr.grad * valid            # padded rows carry no gradient
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        assert rel_err(dqkv[:, sl].float(), gref[:, sl]) < 2e-2, name
+
+
+# --------------------------------------------------------------------------------------------- CTC
+def _ctc_case(b, t, v, smax, seed, feasible=True):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(b, t, v, generator=g) * 2.0
+    ilens = torch.randint(max(1, t // 2), t + 1, (b,), generator=g)
+    ilens[0] = t
+    labels = torch.full((b, smax), -100, dtype=torch.int64)
+    for i in range(b):
+        s = int(torch.randint(0, min(smax, int(ilens[i]) // 2) + 1, (1,), generator=g))
+        lab = torch.randint(1, v, (s,), generator=g)
+        if s >= 2:
+            lab[1] = lab[0]                                  # a repeated label (needs a blank between)
+        labels[i, :s] = lab
+    return logits, labels, ilens
+
+
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+@pytest.mark.parametrize("b,t,v,smax", [(4, 50, 37, 12), (3, 250, 5000, 100), (2, 9, 8, 4)])
+def test_ctc_loss_and_grad_match_oracle(b, t, v, smax, reduction):
+    from oracle import ctc as oc
+    ops = pkg().ops
+    logits, labels, ilens = _ctc_case(b, t, v, smax, seed=b * 100 + t)
+    oloss, onll, ograd = oc.ctc_loss_and_grad(logits, labels, ilens, 0, reduction, False)
+    loss, nll, grad = ops.ctc_loss(logits.cuda(), labels.to(I32).cuda(), ilens.to(I32).cuda(), 0, reduction, False, want_grad=True,
+                                   grad_dtype=F32)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - oloss) <= 1e-4 * max(1.0, abs(oloss))          # north_star: 1e-3 relative
+    assert rel_err(nll, onll) < 1e-5
+    assert float((grad.cpu() - ograd).abs().max()) < 5e-5
+    # bf16 logits / bf16 grad variant (what the training path uses)
+    loss16, _, grad16 = ops.ctc_loss(logits.cuda().to(BF16), labels.to(I32).cuda(), ilens.to(I32).cuda(), 0, reduction, False,
+                                     want_grad=True, grad_dtype=BF16)
+    o2, _, g2 = oc.ctc_loss_and_grad(logits.to(BF16).float(), labels, ilens, 0, reduction, False)
+    assert abs(float(loss16) - o2) <= 1e-4 * max(1.0, abs(o2))
+    assert float((grad16.float().cpu() - g2).abs().max()) < 5e-3
+
+
+def test_ctc_golden_cases_infeasible_and_zero_infinity():
+    ops = pkg().ops
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+    for ci in range(3):
+        logits = torch.from_numpy(gold[f"ctc{ci}_logits"]).cuda()
+        labels = torch.from_numpy(gold[f"ctc{ci}_labels"]).cuda()
+        ilens = torch.from_numpy(gold[f"ctc{ci}_input_lengths"]).cuda()
+        for red in ("sum", "mean"):
+            for zi in (0, 1):
+                loss, nll, grad = ops.ctc_loss(logits, labels, ilens, 0, red, bool(zi), want_grad=True, grad_dtype=F32)
+                ref_loss = float(gold[f"ctc{ci}_{red}_{zi}_loss"])
+                ref_grad = gold[f"ctc{ci}_{red}_{zi}_grad"]
+                if np.isinf(ref_loss):
+                    assert math.isinf(float(loss))
+                    continue
+                assert abs(float(loss) - ref_loss) <= 1e-4 * max(1.0, abs(ref_loss)), (ci, red, zi)
+                finite = np.isfinite(ref_grad)
+                assert np.allclose(grad.cpu().numpy()[finite], ref_grad[finite], atol=5e-5), (ci, red, zi)
+
+
+# --------------------------------------------------------------------------------------------- greedy
+def test_greedy_bit_exact():
+    from oracle import ctc as oc
+    ops = pkg().ops
+    g = torch.Generator().manual_seed(3)
+    b, t, v = 6, 250, 5000
+    logits = torch.randn(b, t, v, generator=g)
+    # make long runs and blanks likely, plus exact ties (first max must win)
+    ids = torch.randint(0, 6, (b, t), generator=g)
+    logits[torch.arange(b)[:, None], torch.arange(t)[None, :], ids] += 20.0
+    logits[0, 5, 17] = logits[0, 5].max()
+    logits[0, 5, 9] = logits[0, 5, 17]
+    lens = torch.tensor([250, 249, 100, 1, 0, 33])
+    ref = oc.greedy_decode(logits, lens, 0)
+    out_ids, out_len, frame_ids = ops.ctc_greedy(logits.cuda(), lens.to(I32).cuda(), 0)
+    torch.cuda.synchronize()
+    out_ids, out_len = out_ids.cpu(), out_len.cpu()
+    for i in range(b):
+        assert out_ids[i, : int(out_len[i])].tolist() == ref[i], i
+        assert (out_ids[i, int(out_len[i]):] == -1).all()
+    am = torch.argmax(logits, -1)
+    for i in range(b):
+        assert torch.equal(frame_ids[i, : int(lens[i])].cpu().long(), am[i, : int(lens[i])])
+    # golden strings
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+    for i in range(5):
+        fr = torch.from_numpy(gold[f"greedy{i}_frames"].astype(np.int64))
+        lg = torch.full((1, len(fr), 16), -3.0)
+        lg[0, torch.arange(len(fr)), fr] = 3.0
+        oi, ol, _ = ops.ctc_greedy(lg.cuda().to(BF16), torch.tensor([len(fr)], dtype=I32).cuda(), 0)
+        assert oi[0, : int(ol[0])].cpu().tolist() == gold[f"greedy{i}_ids"].tolist()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def test_im2col_embed_transpose_colsum_cast_add_adamw():
+    ops = pkg().ops
+    md = pkg().modeling
+    g = _g(5)
+    # im2col == unfold of the zero-padded input
+    b, t, c = 3, 37, 16
+    x = torch.randn(b, t, c, device="cuda", generator=g).to(BF16)
+    col, t_out = ops.im2col_k5s2(x)
+    xp = F.pad(x.float().transpose(1, 2), (2, 2))                       # [b, c, t+4]
+    ref = xp.unfold(2, 5, 2)                                            # [b, c, t_out, 5]
+    ref = ref.permute(0, 2, 3, 1).reshape(b * t_out, 5 * c)
+    assert t_out == (t - 1) // 2 + 1 and torch.equal(col.float(), ref)
+    # conv1d + GLU through im2col + GEMM == F.conv1d + F.glu
+    conv = torch.nn.Conv1d(c, 24, 5, stride=2, padding=2).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(BF16).float())
+    half = 12
+    idx = torch.stack([torch.arange(half), torch.arange(half) + half], 1).reshape(-1).cuda()
+    wg = conv.weight.detach().permute(0, 2, 1).reshape(24, 5 * c)[idx].to(BF16).contiguous()
+    out = ops.gemm(col, wg, bias=conv.bias.detach()[idx].contiguous(), epilogue=pkg()._lib.JL_EPI_GLU, out_dtype=F32)
+    refc = F.glu(conv(x.float().transpose(1, 2)), dim=1).transpose(1, 2).reshape(b * t_out, half)
+    assert rel_err(out, refc) < 2e-3
+    # embed positions
+    d, seq = 64, 19
+    h = torch.randn(2 * seq, d, device="cuda", generator=g).to(BF16)
+    lens = torch.tensor([19, 7], dtype=I32, device="cuda")
+    tab = md.sinusoid_table(seq + 2, d).cuda()
+    ref = h.float().view(2, seq, d) * 8.0 + tab[2: seq + 2][None]
+    ref = ref * (torch.arange(seq, device="cuda")[None, :, None] < lens[:, None, None])
+    got = ops.embed_positions_(h.clone(), 8.0, tab, lens, 2, seq)
+    assert rel_err(got.float().view(2, seq, d), ref) < 5e-3
+    # transpose / colsum / cast / add
+    m = torch.randn(70, 45, device="cuda", generator=g).to(BF16)
+    assert torch.equal(ops.transpose(m), m.t())
+    big = torch.randn(5000, 333, device="cuda", generator=g).to(BF16)
+    assert rel_err(ops.colsum(big), big.float().sum(0)) < 1e-4
+    f = torch.randn(1001, device="cuda", generator=g)
+    assert torch.equal(ops.cast_bf16(f), f.to(BF16))
+    a1, a2 = big[:100].contiguous(), big[100:200].contiguous()
+    assert torch.equal(ops.add(a1, a2), (a1.float() + a2.float()).to(BF16))
+    # AdamW == torch.optim.AdamW
+    p = torch.randn(4099, device="cuda", generator=g)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, weight_decay=0.05)
+    m1, m2 = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(4099, dtype=BF16, device="cuda")
+    for step in range(1, 4):
+        gr = torch.randn(4099, device="cuda", generator=g)
+        ref_p.grad = gr.clone() * 0.5
+        opt.step()
+        ops.adamw_(p, gr, m1, m2, step, 1e-2, weight_decay=0.05, grad_scale=0.5, param_bf16=shadow)
+    torch.cuda.synchronize()
+    assert rel_err(p, ref_p.detach()) < 1e-5
+    assert torch.equal(shadow, p.to(BF16))

@@ -1,0 +1,141 @@
+"""End-to-end GPU parity: waveform → features → encoder (+ adapters) → logits → CTC loss → adapter-only gradients,
+product modules (through the C ABI) vs the fp32 CPU oracle on bf16-rounded weights."""
+import pytest
+import torch
+
+from helpers import pkg, rel_err, round_bf16_, synth_wave
+
+pytestmark = pytest.mark.gpu
+I32 = torch.int32
+
+
+def _oracle_setup(model, cfg):
+    from oracle import model as om
+    w = om.from_product_state_dict(model.state_dict())
+    ocfg = om.OracleConfig(**{k: v for k, v in cfg.to_dict().items() if k in om.OracleConfig.__dataclass_fields__})
+    return om, w, ocfg
+
+
+def _labels(lengths, vocab, smax, seed):
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.full((len(lengths), smax), -100, dtype=torch.int64)
+    for i, t in enumerate(lengths):
+        s = min(smax, int(0.4 * int(t)))
+        lab[i, :s] = torch.randint(1, vocab, (s,), generator=g)
+    return lab
+
+
+def _small_cfg(P, **kw):
+    base = dict(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, conv_channels=64, vocab_size=48,
+                wf_bottleneck=32, wf_rank=8)
+    base.update(kw)
+    return P.JLConfig(**base)
+
+
+@pytest.mark.parametrize("slots", [(None, None), (None, "wf"), (None, "att"), ("att", "wf"), ("wf", "att")])
+def test_small_model_logits_loss_and_adapter_grads(slots):
+    P = pkg()
+    cfg = _small_cfg(P, adapter_attn=slots[0], adapter_ffn=slots[1])
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    waves = [synth_wave(24000, 1), synth_wave(17321, 2), synth_wave(9000, 3)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, 10, seed=4)
+    loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    om, w, ocfg = _oracle_setup(model, cfg)
+    for k, v in w.items():
+        v.requires_grad_(om.is_trainable(k))
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, waves, labels)
+    oloss.backward()
+    assert olens.tolist() == lens
+    for i, t in enumerate(lens):
+        assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
+    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    for name, p in model._get_adapters().items():
+        ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
+        assert p.grad is not None, name
+        assert rel_err(p.grad.float(), ref) < 5e-2, f"grad {name}: {rel_err(p.grad.float(), ref)}"
+
+
+def test_base_config_forward_logits_and_greedy_ids():
+    """BASELINE.json config 1: 12-layer d=768 encoder with WFAdapter, batch 4 × 10 s, greedy decode."""
+    P = pkg()
+    cfg = P.JLConfig.base(adapter_ffn="wf")
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda().eval()
+    waves = [synth_wave(160000, 1234 + i) for i in range(4)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    with torch.no_grad():
+        _, logits = model(feats["input_features"], attention_mask=feats["attention_mask"])
+    lens = model.output_lengths(feats["input_features"], feats["attention_mask"])
+    torch.cuda.synchronize()
+    assert logits.shape == (4, 250, 5000)
+    om, w, ocfg = _oracle_setup(model, cfg)
+    with torch.no_grad():
+        _, ologits, olens = om.forward_from_waveforms(w, ocfg, waves)
+    fro = rel_err(logits.float(), ologits)
+    assert fro < 2e-2, f"relative Frobenius error {fro}"                       # stated bf16 tolerance, 12 layers
+    assert float((logits.float().cpu() - ologits).abs().max()) <= 5e-2 * float(ologits.abs().max())
+    agree = (logits.float().cpu().argmax(-1) == ologits.argmax(-1)).float().mean()
+    assert float(agree) >= 0.99
+    # greedy ids are bit-exact when decoded from the same logits
+    from oracle import ctc as oc
+    assert model.greedy_decode(logits, lens) == oc.greedy_decode(logits.float().cpu(), lens.cpu(), 0)
+
+
+def test_label_out_of_vocab_raises_and_inference_returns_no_loss():
+    P = pkg()
+    cfg = _small_cfg(P, adapter_ffn="wf")
+    model = P.JLForCTC(cfg).cuda()
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([synth_wave(8000, 1).numpy()], sampling_rate=16000)
+    loss, logits = model(feats["input_features"], feats["attention_mask"])
+    assert loss is None and logits.shape[-1] == cfg.vocab_size
+    with pytest.raises(ValueError):
+        model(feats["input_features"], feats["attention_mask"], labels=torch.tensor([[cfg.vocab_size]]).cuda())
+
+
+def test_trainer_step_matches_autograd_path_and_updates_adapters():
+    """Flat-bucket fast path (CUDA graph) == autograd path: same loss, same gradients; AdamW moves only adapters + lm_head."""
+    P = pkg()
+    cfg = _small_cfg(P, adapter_attn="att", adapter_ffn="wf")
+    torch.manual_seed(0)
+    m1 = P.JLForCTC(cfg)
+    round_bf16_(m1)
+    m2 = P.JLForCTC(cfg)
+    m2.load_state_dict(m1.state_dict())
+    m1, m2 = m1.cuda(), m2.cuda()
+    m1.freeze_base_model()
+    m2.freeze_base_model()
+    n = 16000
+    wave = torch.stack([synth_wave(n, 1), synth_wave(n, 2)])
+    ns = torch.tensor([n, 12000], dtype=I32)
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([wave[0].numpy(), wave[1, :12000].numpy()], sampling_rate=16000)
+    lens = m1.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, 8, seed=9)
+    loss_a, _ = m1(feats["input_features"], labels=labels.cuda(), frame_lengths=feats["frame_lengths"])
+    loss_a.backward()
+    ref_grads = {k: p.grad.clone() for k, p in m1._get_adapters().items()}
+    backbone_before = m2.encoder.layers[0].attention.q_proj.weight.clone()
+    tr = P.AdapterTrainer(m2, lr=1e-3, use_cuda_graph=True)
+    before = tr.flat.param.clone()
+    loss_b = tr.step(wave.pin_memory(), ns, labels.to(I32))
+    torch.cuda.synchronize()
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_a))
+    for k, p in m2._get_adapters().items():
+        assert rel_err(p.grad, ref_grads[k]) < 1e-5, k
+    assert not torch.equal(before, tr.flat.param)
+    assert torch.equal(backbone_before, m2.encoder.layers[0].attention.q_proj.weight)
+    loss_c = tr.step(wave.pin_memory(), ns, labels.to(I32))            # graph replay with refreshed bf16 shadows
+    torch.cuda.synchronize()
+    assert float(loss_c) < float(loss_b)
+    assert tr.launches_per_step > 50
