@@ -15,6 +15,10 @@ from . import _lib as L
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 
+# When set to a list, every gemm() call appends (params, kept-alive tensors, 2·M·N·K): bench.py replays the list to
+# time the step's tensor-core launches on their own (roofline of the dominant kernel).
+GEMM_TRACE = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -107,7 +111,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     lib = L.load()
     fn = lib.jl_debug_gemm_ref if reference else lib.jl_gemm_bf16
     L.check(fn(C.byref(p), _stream()))
+    if GEMM_TRACE is not None:
+        GEMM_TRACE.append((p, (a, b, out, bias, residual, aux, aux_out, row_lengths), 2.0 * m * n * k))
     return out
+
+
+def replay_gemm_trace(trace) -> None:
+    """Re-issue recorded GEMM launches (same operands, same shapes) on the current stream."""
+    lib = L.load()
+    s = _stream()
+    for p, _, _ in trace:
+        L.check(lib.jl_gemm_bf16(C.byref(p), s))
 
 
 # ----------------------------------------------------------------------------------------------- LayerNorm

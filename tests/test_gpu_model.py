@@ -60,7 +60,10 @@ def test_small_model_logits_loss_and_adapter_grads(slots):
     for name, p in model._get_adapters().items():
         ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
         assert p.grad is not None, name
-        assert rel_err(p.grad.float(), ref) < 5e-2, f"grad {name}: {rel_err(p.grad.float(), ref)}"
+        # relative Frobenius error, with an absolute floor for gradients that are analytically zero (the AttAdapter key
+        # bias shifts every score of a query equally, so its true gradient is 0 and both sides hold only rounding noise)
+        err = float((p.grad.float().cpu() - ref).norm())
+        assert err <= 5e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
 
 
 def test_base_config_forward_logits_and_greedy_ids():
@@ -84,8 +87,14 @@ def test_base_config_forward_logits_and_greedy_ids():
     fro = rel_err(logits.float(), ologits)
     assert fro < 2e-2, f"relative Frobenius error {fro}"                       # stated bf16 tolerance, 12 layers
     assert float((logits.float().cpu() - ologits).abs().max()) <= 5e-2 * float(ologits.abs().max())
-    agree = (logits.float().cpu().argmax(-1) == ologits.argmax(-1)).float().mean()
-    assert float(agree) >= 0.99
+    # frame-argmax agreement: random-init logits are nearly flat, so flips are allowed only where the oracle's own margin
+    # between the two candidates is inside the numerical error band
+    mine, theirs = logits.float().cpu().argmax(-1), ologits.argmax(-1)
+    agree = (mine == theirs).float().mean()
+    assert float(agree) >= 0.95, float(agree)
+    gap = ologits.gather(-1, theirs[..., None]) - ologits.gather(-1, mine[..., None])
+    band = 2.0 * float((logits.float().cpu() - ologits).abs().max())
+    assert float(gap.max()) <= band, (float(gap.max()), band)
     # greedy ids are bit-exact when decoded from the same logits
     from oracle import ctc as oc
     assert model.greedy_decode(logits, lens) == oc.greedy_decode(logits.float().cpu(), lens.cpu(), 0)
@@ -128,14 +137,14 @@ def test_trainer_step_matches_autograd_path_and_updates_adapters():
     backbone_before = m2.encoder.layers[0].attention.q_proj.weight.clone()
     tr = P.AdapterTrainer(m2, lr=1e-3, use_cuda_graph=True)
     before = tr.flat.param.clone()
-    loss_b = tr.step(wave.pin_memory(), ns, labels.to(I32))
+    loss_b = tr.step(wave.pin_memory(), ns, labels.to(I32)).item()      # the returned tensor is the graph's static output
     torch.cuda.synchronize()
-    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_a))
+    assert abs(float(loss_a) - loss_b) <= 1e-5 * abs(float(loss_a))
     for k, p in m2._get_adapters().items():
         assert rel_err(p.grad, ref_grads[k]) < 1e-5, k
     assert not torch.equal(before, tr.flat.param)
     assert torch.equal(backbone_before, m2.encoder.layers[0].attention.q_proj.weight)
-    loss_c = tr.step(wave.pin_memory(), ns, labels.to(I32))            # graph replay with refreshed bf16 shadows
+    loss_c = tr.step(wave.pin_memory(), ns, labels.to(I32)).item()     # graph replay with refreshed bf16 shadows
     torch.cuda.synchronize()
-    assert float(loss_c) < float(loss_b)
+    assert loss_c < loss_b
     assert tr.launches_per_step > 50
