@@ -17,6 +17,6 @@ from . import _lib, ops  # noqa: F401
 from .configuration import JLConfig  # noqa: F401
 from .feature_extraction import JLFeatureExtractor  # noqa: F401
 from .modeling import AttAdapter, GradSink, JLEncoder, JLEngine, JLForCTC, WFAdapter  # noqa: F401
-from .training import AdapterTrainer, FlatAdapterParams, Transcriber, shard_utterances  # noqa: F401
+from .training import AdapterTrainer, BucketLayout, FlatAdapterParams, Transcriber, ordered_trainables, shard_utterances  # noqa: F401
 
 __version__ = "0.1.0"

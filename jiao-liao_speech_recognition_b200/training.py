@@ -23,7 +23,7 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 _ALIGN = 64   # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 buffer
 
 
-def _ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
+def ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
     """Trainable parameters, with each AttAdapter's q/k/v weights (and biases) adjacent so that the concatenated
     [192, d] projection the kernels use is a plain view of the bucket."""
     seen, out = set(), []
@@ -42,6 +42,42 @@ def _ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
     return out
 
 
+class BucketLayout:
+    """Offsets of the trainable parameters inside one flat buffer (each padded to 64 elements so that every view is
+    16-byte aligned in fp32 and in bf16).  Device-agnostic: the same layout addresses the fp32 master copy, the gradient
+    bucket that is all-reduced, the AdamW moments and the bf16 shadow."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        self.offset: Dict[int, int] = {}
+        off = 0
+        for p in params:
+            self.offset[id(p)] = off
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.num_params = sum(p.numel() for p in params)
+
+    def view(self, buf: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+        o = self.offset[id(p)]
+        return buf[o: o + p.numel()].view(p.shape)
+
+    def adjacent(self, ps: Sequence[torch.Tensor]) -> bool:
+        for a, b in zip(ps[:-1], ps[1:]):
+            if id(a) not in self.offset or id(b) not in self.offset or a.numel() % _ALIGN:
+                return False
+            if self.offset[id(b)] != self.offset[id(a)] + a.numel() or a.shape[1:] != b.shape[1:]:
+                return False
+        return id(ps[-1]) in self.offset
+
+    def cat(self, buf: torch.Tensor, ps: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+        """[Σ rows, ...] view over consecutive parameters (e.g. q/k/v projections), or None if they are not adjacent."""
+        if not self.adjacent(ps):
+            return None
+        o = self.offset[id(ps[0])]
+        n = sum(p.numel() for p in ps)
+        rows = sum(p.shape[0] for p in ps)
+        return buf[o: o + n].view((rows,) + tuple(ps[0].shape[1:]))
+
+
 class FlatAdapterParams(GradSink):
     """Flat storage for the trainable set.  After construction every trainable ``nn.Parameter``'s ``.data`` is a view
     of ``self.param``; gradients are written by the backward kernels straight into ``self.grad``."""
@@ -49,19 +85,16 @@ class FlatAdapterParams(GradSink):
     def __init__(self, model: JLForCTC):
         super().__init__()
         self.model = model
-        self.plist = _ordered_trainables(model)
+        self.plist = ordered_trainables(model)
         if not self.plist:
             raise ValueError("no trainable parameters: call model.freeze_base_model() first")
         dev = self.plist[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdapterParams needs the model on a CUDA device")
-        self.offset: Dict[int, int] = {}
-        off = 0
-        for p in self.plist:
-            self.offset[id(p)] = off
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
-        self.total = off
-        self.num_params = sum(p.numel() for p in self.plist)
+        self.layout = BucketLayout(self.plist)
+        self.offset = self.layout.offset
+        self.total, self.num_params = self.layout.total, self.layout.num_params
+        off = self.total
         self.param = torch.zeros(off, dtype=F32, device=dev)
         self.grad = torch.zeros(off, dtype=F32, device=dev)
         self.exp_avg = torch.zeros(off, dtype=F32, device=dev)
@@ -78,24 +111,10 @@ class FlatAdapterParams(GradSink):
         model.encoder.engine(model.lm_head).flat = self
 
     def _view(self, buf: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
-        o = self.offset[id(p)]
-        return buf[o: o + p.numel()].view(p.shape)
-
-    def _adjacent(self, ps: Sequence[torch.Tensor]) -> bool:
-        for a, b in zip(ps[:-1], ps[1:]):
-            if id(a) not in self.offset or id(b) not in self.offset or a.numel() % _ALIGN:
-                return False
-            if self.offset[id(b)] != self.offset[id(a)] + a.numel() or a.shape[1:] != b.shape[1:]:
-                return False
-        return id(ps[-1]) in self.offset
+        return self.layout.view(buf, p)
 
     def _cat(self, buf: torch.Tensor, ps: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
-        if not self._adjacent(ps):
-            return None
-        o = self.offset[id(ps[0])]
-        n = sum(p.numel() for p in ps)
-        rows = sum(p.shape[0] for p in ps)
-        return buf[o: o + n].view((rows,) + tuple(ps[0].shape[1:]))
+        return self.layout.cat(buf, ps)
 
     # ---- views the engine asks for
     def bf16_view(self, p):
