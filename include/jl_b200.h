@@ -108,8 +108,13 @@ typedef struct {
   int32_t epilogue;
   int32_t out_dtype;                 /* JL_DT_BF16 | JL_DT_F32 */
   float alpha;
+  void* workspace;                   /* optional split-K scratch (jl_gemm_workspace_bytes); NULL = no split-K */
+  int64_t workspace_bytes;
 } jl_gemm_params;
 int jl_gemm_bf16(const jl_gemm_params* p, void* stream);
+/* bytes of split-K scratch this product would use (0 when it runs unsplit): plain products (no bias / activation /
+ * residual) whose output tiles cannot fill the SMs and whose K is long — the weight-gradient shapes dYᵀ·X */
+int jl_gemm_workspace_bytes(const jl_gemm_params* p, size_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (eps 1e-5).  Replaces nn.LayerNorm at

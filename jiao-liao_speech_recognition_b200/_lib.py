@@ -32,7 +32,8 @@ class GemmParams(C.Structure):
     _fields_ = [("a", vp), ("lda", i64), ("b", vp), ("ldb", i64), ("a_layout", i32), ("b_layout", i32),
                 ("c", vp), ("ldc", i64), ("bias", vp), ("residual", vp), ("ldr", i64), ("aux", vp), ("ldaux", i64),
                 ("aux_out", vp), ("ldaux_out", i64), ("row_lengths", vp), ("rows_per_seq", i32),
-                ("m", i32), ("n", i32), ("k", i32), ("epilogue", i32), ("out_dtype", i32), ("alpha", f32)]
+                ("m", i32), ("n", i32), ("k", i32), ("epilogue", i32), ("out_dtype", i32), ("alpha", f32),
+                ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class LayerNormFwdParams(C.Structure):
@@ -85,6 +86,7 @@ SYMBOLS = {
     "jl_mel_cmvn_fwd": (C.c_int, [C.POINTER(MelCmvnParams), vp, vp]),
     "jl_gemm_bf16": (C.c_int, [C.POINTER(GemmParams), vp]),
     "jl_debug_gemm_ref": (C.c_int, [C.POINTER(GemmParams), vp]),
+    "jl_gemm_workspace_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), vp]),
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),

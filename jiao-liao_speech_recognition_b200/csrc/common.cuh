@@ -51,11 +51,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-form GELU (SP/transformers/activations.py "gelu") and its derivative.  erf via Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 — far below the bf16 rounding of the stored result): one MUFU.RCP, one MUFU.EX2 and six FMAs, so the
+// GEMM epilogue stays under the ≈ 24 issue slots per output element that a K = 768 mainloop leaves it.
+//   q(v) = 0.5 · (1 − erf(|v|/√2)) = 0.5 · poly(t) · exp(−v²/2),  t = 1 / (1 + p·|v|/√2)
+//   Φ(v) = v >= 0 ? 1 − q : q;   gelu(v) = v · Φ(v);   gelu'(v) = Φ(v) + v · exp(−v²/2) / √(2π)
+__device__ __forceinline__ void gelu_parts(float v, float& cdf, float& e) {
+  const float ax = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  e = exp2f(-ax * ax * 1.4426950408889634f);       // exp(−v²/2)
+  const float q = 0.5f * poly * e;
+  cdf = (v >= 0.0f) ? 1.0f - q : q;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -65,38 +65,46 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
   }
 }
 
-// Column sums, stage 1: grid (ceil(cols / 64), nsplit); 256 threads = 8 row groups × 32 lanes × 2 columns.
+// Column sums, stage 1: grid (ceil(cols / 256), nsplit); 256 threads = 8 row groups × 32 lanes × 8 columns (16-byte loads).
 constexpr int COLSUM_SPLITS = 64;
-__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ partial) {
-  __shared__ float2 s_acc[8][32];
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                             float* __restrict__ partial) {
+  __shared__ float s_acc[8][32][9];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 64 + lane * 2;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r_begin = blockIdx.y * rows_per;
   const int r_end = min(rows, r_begin + rows_per);
-  float2 acc = make_float2(0.0f, 0.0f);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
   if (col < cols) {
-    const bool pair = (col + 1 < cols) && ((ldx & 1) == 0);
+    const bool vec = (col + 8 <= cols) && ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int r = r_begin + grp; r < r_end; r += 8) {
       const __nv_bfloat16* p = x + static_cast<int64_t>(r) * ldx + col;
-      if (pair) {
-        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
-        acc.x += f.x;
-        acc.y += f.y;
+      if (vec) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+        acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
       } else {
-        acc.x += __bfloat162float(p[0]);
-        if (col + 1 < cols) acc.y += __bfloat162float(p[1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col + j < cols) acc[j] += __bfloat162float(p[j]);
       }
     }
   }
-  s_acc[grp][lane] = acc;
-  __syncthreads();
-  if (grp == 0 && col < cols) {
-    float2 t = s_acc[0][lane];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) { t.x += s_acc[g][lane].x; t.y += s_acc[g][lane].y; }
-    partial[static_cast<int64_t>(blockIdx.y) * cols + col] = t.x;
-    if (col + 1 < cols) partial[static_cast<int64_t>(blockIdx.y) * cols + col + 1] = t.y;
+  for (int j = 0; j < 8; ++j) s_acc[grp][lane][j] = acc[j];
+  __syncthreads();
+  // thread t sums column (blockIdx.x * 256 + t) over the 8 row groups in fixed order
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += s_acc[g][l][j];
+    partial[static_cast<int64_t>(blockIdx.y) * cols + c] = t;
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nsplit, int cols, float* __restrict__ out) {
@@ -231,13 +239,12 @@ int jl_colsum_workspace_bytes(int32_t rows, int32_t cols, size_t* out) {
 int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, float* partial, void* stream) {
   JL_REQUIRE(x && out && partial, JL_EINVAL, "colsum: null pointer");
   JL_REQUIRE(rows > 0 && cols > 0 && ldx >= cols, JL_EINVAL, "colsum: bad dims");
-  JL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0, JL_EINVAL, "colsum: x must be 4-byte aligned");
-  int rc = jl::check_device();
+    int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int nsplit = jl::ceil_div(rows, 64);
   if (nsplit > jl::COLSUM_SPLITS) nsplit = jl::COLSUM_SPLITS;
-  dim3 grid(jl::ceil_div(cols, 64), nsplit);
+  dim3 grid(jl::ceil_div(cols, 256), nsplit);
   jl::colsum_partial_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, cols, partial);
   JL_CHECK_LAUNCH("colsum_partial");
   jl::colsum_final_kernel<<<jl::ceil_div(cols, 256), 256, 0, s>>>(partial, nsplit, cols, out);

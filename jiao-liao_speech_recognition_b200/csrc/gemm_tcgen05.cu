@@ -49,6 +49,10 @@ struct GemmDev {
   int32_t out_dtype;
   float alpha;
   int32_t num_m_tiles, num_n_tiles;
+  // split-K (weight-gradient shapes: few output tiles, very long K): unit = (tile, split); raw fp32 partials go to ws
+  int32_t split_k, kb_per_split;
+  float* ws;
+  int64_t ldw;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -233,8 +237,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
-  const int num_kb = (g.k + GEMM_BK - 1) / GEMM_BK;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles * g.split_k;      // work units: (output tile, K split)
+  const int num_kb_total = (g.k + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
@@ -265,10 +269,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x) {
+        const int tile = unit / g.split_k, split = unit - tile * g.split_k;
         const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
         const int n0 = (tile % g.num_n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = split * g.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + g.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
           ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
           uint8_t* a_dst = s_a + stage * GEMM_A_BYTES;
@@ -297,9 +304,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int split = unit % g.split_k;
+        const int num_kb = min(num_kb_total, (split + 1) * g.kb_per_split) - split * g.kb_per_split;
         ptx::mbar_wait(tempty_bar + as, aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -327,9 +336,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const int half = (warp - 4) >> 2;             // which 32-column chunks (even / odd)
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int tile = unit / g.split_k, split = unit - tile * g.split_k;
       const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
       const int n0 = (tile % g.num_n_tiles) * BN;
       ptx::mbar_wait(tfull_bar + as, aphase);
@@ -344,7 +354,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+        if (g.split_k > 1) {
+          const int col0 = n0 + c * 32;
+          if (row < g.m && col0 < g.n)
+            store_f32_row<32>(g.ws + (static_cast<int64_t>(split) * g.m + row) * g.ldw + col0, col0 + 32 <= g.ldw, g.n - col0, acc);
+        } else {
+          gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -357,6 +373,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// C = alpha * Σ_s ws[s]  (fixed order → deterministic), fp32 or bf16 out.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int64_t ldw, int splits, int m, int n, float alpha, void* __restrict__ c,
+                                     int64_t ldc, int out_dtype) {
+  const int64_t total = static_cast<int64_t>(m) * n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n), col = static_cast<int>(i - static_cast<int64_t>(r) * n);
+    float a = 0.0f;
+    for (int sidx = 0; sidx < splits; ++sidx) a += ws[(static_cast<int64_t>(sidx) * m + r) * ldw + col];
+    a *= alpha;
+    if (out_dtype == JL_DT_BF16) reinterpret_cast<__nv_bfloat16*>(c)[static_cast<int64_t>(r) * ldc + col] = __float2bfloat16_rn(a);
+    else reinterpret_cast<float*>(c)[static_cast<int64_t>(r) * ldc + col] = a;
   }
 }
 
@@ -459,8 +489,35 @@ static int validate(const jl_gemm_params* p) {
   return JL_OK;
 }
 
+static int pick_bn(const jl_gemm_params* p);
+
+// K splits for a plain product (no bias / activation / residual) whose output tiles cannot fill the SMs.
+static int pick_split(const jl_gemm_params* p, int bn, int* kb_per_split) {
+  const int num_kb = ceil_div(p->k, GEMM_BK);
+  *kb_per_split = num_kb;
+  if (p->epilogue != JL_EPI_NONE || p->bias || p->residual || p->row_lengths) return 1;
+  const int tiles = ceil_div(p->m, GEMM_BM) * ceil_div(p->n, bn);
+  const int sms = num_sms();
+  if (tiles * 2 > sms || num_kb < 16) return 1;
+  int want = sms / tiles;
+  if (want > num_kb / 4) want = num_kb / 4;
+  if (want < 2) return 1;
+  const int per = ceil_div(num_kb, want);
+  *kb_per_split = per;
+  return ceil_div(num_kb, per);
+}
+
+static size_t splitk_ws_bytes(const jl_gemm_params* p) {
+  int per = 0;
+  const int s = pick_split(p, pick_bn(p), &per);
+  if (s <= 1) return 0;
+  const size_t ldw = (static_cast<size_t>(p->n) + 3) & ~static_cast<size_t>(3);
+  return static_cast<size_t>(s) * p->m * ldw * sizeof(float);
+}
+
 static GemmDev to_dev(const jl_gemm_params* p, int bn) {
   GemmDev g;
+  g.split_k = 1; g.kb_per_split = ceil_div(p->k, GEMM_BK); g.ws = nullptr; g.ldw = 0;
   g.c = p->c; g.ldc = p->ldc;
   g.bias = p->bias;
   g.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual); g.ldr = p->ldr;
@@ -494,11 +551,29 @@ static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
   if (B_MN) rc = make_map(&mb, p->b, p->n, p->k, p->ldb, 64);
   else rc = make_map(&mb, p->b, p->k, p->n, p->ldb, BN);
   if (rc != JL_OK) return rc;
-  const GemmDev g = to_dev(p, BN);
-  const int tiles = g.num_m_tiles * g.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  GemmDev g = to_dev(p, BN);
+  if (p->workspace != nullptr) {
+    int per = 0;
+    const int s = pick_split(p, BN, &per);
+    const size_t need = splitk_ws_bytes(p);
+    if (s > 1 && static_cast<size_t>(p->workspace_bytes) >= need && (reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0) {
+      g.split_k = s;
+      g.kb_per_split = per;
+      g.ws = reinterpret_cast<float*>(p->workspace);
+      g.ldw = (static_cast<int64_t>(p->n) + 3) & ~static_cast<int64_t>(3);
+    }
+  }
+  const int units = g.num_m_tiles * g.num_n_tiles * g.split_k;
+  const int grid = units < num_sms() ? units : num_sms();
   kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
   JL_CHECK_LAUNCH("gemm_tcgen05");
+  if (g.split_k > 1) {
+    const int64_t total = static_cast<int64_t>(p->m) * p->n;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g.ws, g.ldw, g.split_k, p->m, p->n, p->alpha, p->c, p->ldc, p->out_dtype);
+    JL_CHECK_LAUNCH("gemm_splitk_reduce");
+  }
   return JL_OK;
 }
 
@@ -528,7 +603,7 @@ static int pick_bn(const jl_gemm_params* p) {
     if (bn > 64 && bn / 2 >= p->n) continue;
     const long tiles = static_cast<long>(mt) * ceil_div(p->n, bn);
     const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * (bn + 24);
+    const long cost = waves * (bn + 32);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -550,6 +625,14 @@ int jl_gemm_bf16(const jl_gemm_params* p, void* stream) {
     case 64: return jl::dispatch_layout<64, 8>(p, s);
     default: return jl::dispatch_layout<32, 8>(p, s);
   }
+}
+
+int jl_gemm_workspace_bytes(const jl_gemm_params* p, size_t* out) {
+  JL_REQUIRE(out != nullptr, JL_EINVAL, "gemm_workspace_bytes: null out");
+  int rc = jl::validate(p);
+  if (rc != JL_OK) return rc;
+  *out = jl::splitk_ws_bytes(p);
+  return JL_OK;
 }
 
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {

@@ -170,17 +170,29 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
   }
 }
 
-__global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d) return;
+// partial = [2][nblk][d] (dgamma partials, then dbeta partials).  CTA = 32 columns × 8 row groups; each group sums a
+// strided subset of the partial rows (coalesced 128 B reads), then the 8 groups are combined in fixed order.
+__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_g[8][33], s_b[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float g = 0.0f, b = 0.0f;
-  for (int k = 0; k < nblk; ++k) {
-    g += partial[static_cast<int64_t>(k) * d + i];
-    b += partial[(static_cast<int64_t>(nblk) + k) * d + i];
+  if (i < d) {
+    for (int k = grp; k < nblk; k += 8) {
+      g += partial[static_cast<int64_t>(k) * d + i];
+      b += partial[(static_cast<int64_t>(nblk) + k) * d + i];
+    }
   }
-  dgamma[i] = g;
-  if (dbeta != nullptr) dbeta[i] = b;
+  s_g[grp][lane] = g;
+  s_b[grp][lane] = b;
+  __syncthreads();
+  if (grp == 0 && i < d) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { g += s_g[w][lane]; b += s_b[w][lane]; }
+    dgamma[i] = g;
+    if (dbeta != nullptr) dbeta[i] = b;
+  }
 }
 
 static int ln_bwd_blocks(int rows) {
@@ -238,7 +250,7 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
   }
   JL_CHECK_LAUNCH("layernorm_bwd");
   if (p->dgamma != nullptr) {
-    jl::layernorm_bwd_reduce_kernel<<<jl::ceil_div(p->d, 256), 256, 0, s>>>(p->partial, blocks, p->d, p->dgamma, p->dbeta);
+    jl::layernorm_bwd_reduce_kernel<<<jl::ceil_div(p->d, 32), 256, 0, s>>>(p->partial, blocks, p->d, p->dgamma, p->dbeta);
     JL_CHECK_LAUNCH("layernorm_bwd_reduce");
   }
   return JL_OK;

@@ -109,10 +109,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if out.dtype not in (BF16, F32):
         raise TypeError("gemm: out must be bf16 or fp32")
     lib = L.load()
+    ws = None
+    if not reference and epilogue == L.JL_EPI_NONE and bias is None and residual is None and row_lengths is None:
+        nbytes = C.c_size_t(0)
+        L.check(lib.jl_gemm_workspace_bytes(C.byref(p), C.byref(nbytes)))
+        if nbytes.value:
+            ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=a.device)
+            p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes.value
     fn = lib.jl_debug_gemm_ref if reference else lib.jl_gemm_bf16
     L.check(fn(C.byref(p), _stream()))
     if GEMM_TRACE is not None:
-        GEMM_TRACE.append((p, (a, b, out, bias, residual, aux, aux_out, row_lengths), 2.0 * m * n * k))
+        GEMM_TRACE.append((p, (a, b, out, bias, residual, aux, aux_out, row_lengths, ws), 2.0 * m * n * k))
     return out
 
 

@@ -55,6 +55,19 @@ def test_gemm_mn_major_operands(m, n, k, a_mn, b_mn):
     assert rel_err(out, ref) < 2e-3, (m, n, k, a_mn, b_mn)
 
 
+@pytest.mark.parametrize("m,n,k,out_dtype", [(768, 64, 8000, F32), (192, 768, 8000, F32), (256, 32, 8000, BF16), (64, 192, 4104, F32)])
+def test_gemm_split_k_weight_gradient_shapes(m, n, k, out_dtype):
+    """dYᵀ·X shapes: few output tiles, long K → split-K with a fixed-order reduction (deterministic)."""
+    ops, L = _ops()
+    a, b, a_s, b_s = _mk(m, n, k, seed=11, a_mn=True, b_mn=True)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a_s, b_s, out_dtype=out_dtype, a_layout=1, b_layout=1)
+    out2 = ops.gemm(a_s, b_s, out_dtype=out_dtype, a_layout=1, b_layout=1)
+    torch.cuda.synchronize()
+    assert rel_err(out.float(), ref) < (2e-3 if out_dtype == F32 else 1e-2)
+    assert torch.equal(out, out2)
+
+
 def test_gemm_matches_simt_reference_bitwise_epilogue():
     """Same epilogue code on a SIMT fp32-accumulate kernel: only the accumulation order differs."""
     ops, L = _ops()
