@@ -254,6 +254,33 @@ def run_ours(args):
                 "launches_per_step": len(trace), "algorithmic_tflop_per_step": flops / 1e12, "gemm_ms_per_step": 1e3 * t_gemm,
                 "share_of_step": t_gemm / (t_res / args.steps)}
 
+    if args.gemm_breakdown and rank == 0:
+        # per-shape timing of the step's GEMM launches (tuning aid; written to a side file, not part of the JSON line)
+        import ctypes as C
+        lib = P._lib.load()
+        groups = {}
+        for prm, keep, fl in trace:
+            key = (prm.m, prm.n, prm.k, prm.a_layout, prm.b_layout, prm.epilogue, prm.out_dtype)
+            groups.setdefault(key, [prm, 0, fl])[1] += 1
+        rows = []
+        s_ = torch.cuda.current_stream().cuda_stream
+        for key, (prm, cnt, fl) in groups.items():
+            for _ in range(3):
+                lib.jl_gemm_bf16(C.byref(prm), s_)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                lib.jl_gemm_bf16(C.byref(prm), s_)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / 20
+            rows.append((us * cnt, key, cnt, us, fl / us / 1e6))
+        rows.sort(reverse=True)
+        with open(args.gemm_breakdown, "w") as f:
+            f.write("| m | n | k | A | B | epi | out | launches/step | us/launch (warm, back-to-back) | TFLOP/s | us/step |\n|---|---|---|---|---|---|---|---:|---:|---:|---:|\n")
+            for tot, key, cnt, us, tf in rows:
+                f.write(f"| {key[0]} | {key[1]} | {key[2]} | {'MN' if key[3] else 'K'} | {'MN' if key[4] else 'K'} | {key[5]} | "
+                        f"{'f32' if key[6] else 'bf16'} | {cnt} | {us:.1f} | {tf:.0f} | {tot:.0f} |\n")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -287,6 +314,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-breakdown", default=None, help="write a per-shape GEMM timing table to this file")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (profiling runs: one kernel launch per API call)")
     args = ap.parse_args()
     if args.impl == "reference":

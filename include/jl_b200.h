@@ -234,6 +234,11 @@ typedef struct {
 } jl_adamw_params;
 int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
 
+/* test / tuning hook: 0 = automatic kernel choice (default), 1 = single-CTA tcgen05 kernel only, 2 = CTA-pair
+ * (cta_group::2) kernel wherever it is legal.  Both are the product's own kernels; results are identical up to fp32
+ * accumulation order. */
+void jl_debug_set_gemm_mode(int mode);
+
 /* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
  * sizes the CPU oracle cannot reach; never called by the product path. */
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream);

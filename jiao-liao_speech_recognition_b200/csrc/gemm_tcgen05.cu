@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -376,6 +377,176 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel (tcgen05 cta_group::2): one 256 × BN output tile per cluster of two CTAs.  Each CTA stages its own
+// 128 rows of A and half (BN/2 rows) of B per k-block, the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads B from both CTAs' shared memory, and each CTA drains its own 128
+// accumulator lanes.  Per k-block a pair moves (256 + BN) · 128 B for 256 · BN · 64 MACs — 128 FLOP/B at BN = 256
+// against 85 for the single-CTA 128 × 256 tile — which is what lifts the L2 → SM operand traffic (≈ 6.3 kB/clk chip-wide)
+// out of the way of the tensor pipe.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem2 {
+  static constexpr int BNH = BN / 2;
+  static constexpr int B_BYTES = BNH * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+  using L = GemmSmem2<BN, STAGES>;
+  constexpr int BNH = BN / 2;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN == 128 || BN == 192 || BN == 256, "pair tile N must be 128, 192 or 256");
+  static_assert(!B_MN || (BNH % 64) == 0, "MN-major B needs 64-wide swizzle blocks per CTA");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + STAGES * GEMM_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;          // 256 × BN tiles
+  const int num_kb = (g.k + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tma_a);
+    ptx::prefetch_tensormap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar + s, 1);       // leader's: one arrive.expect_tx covering both CTAs' bytes
+      ptx::mbar_init(empty_bar + s, 1);      // each CTA's own: multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar + s, 1);                       // each CTA's own: multicast commit
+      ptx::mbar_init(tempty_bar + s, 2 * GEMM_EPI_WARPS);     // leader's: epilogue warps of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / g.num_n_tiles) * 256 + static_cast<int>(rank) * GEMM_BM;
+        const int n0 = (tile % g.num_n_tiles) * BN + static_cast<int>(rank) * BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
+          if (leader) ptx::mbar_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);
+          const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(full_bar + stage), 0);
+          uint8_t* a_dst = s_a + stage * GEMM_A_BYTES;
+          uint8_t* b_dst = s_b + stage * L::B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < GEMM_BM / 64; ++i) ptx::tma_load_2d_2sm(a_dst + i * 8192, &tma_a, bar, m0 + 64 * i, k0);
+          } else {
+            ptx::tma_load_2d_2sm(a_dst, &tma_a, bar, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BNH / 64; ++i) ptx::tma_load_2d_2sm(b_dst + i * 8192, &tma_b, bar, n0 + 64 * i, k0);
+          } else {
+            ptx::tma_load_2d_2sm(b_dst, &tma_b, bar, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar + as, aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(s_a + stage * GEMM_A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(s_b + stage * L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = A_MN ? ptx::make_sw128_desc(a_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::make_sw128_desc(b_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
+            ptx::umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit_2sm(empty_bar + stage, 0x3);    // both CTAs' smem slots are free once these MMAs have read them
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit_2sm(tfull_bar + as, 0x3);          // accumulators complete in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 accumulator lanes) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t leader_tempty = ptx::mapa_shared(ptx::smem_u32(tempty_bar), 0);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / g.num_n_tiles) * 256 + static_cast<int>(rank) * GEMM_BM;
+      const int n0 = (tile % g.num_n_tiles) * BN;
+      ptx::mbar_wait(tfull_bar + as, aphase);
+      ptx::tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32);
+        ptx::tmem_ld_32x32(taddr, v);
+        ptx::tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty + static_cast<uint32_t>(as * 8));
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();        // the peer may still be arriving on / reading from this CTA's shared memory
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // C = alpha * Σ_s ws[s]  (fixed order → deterministic), fp32 or bf16 out.
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int64_t ldw, int splits, int m, int n, float alpha, void* __restrict__ c,
                                      int64_t ldc, int out_dtype) {
@@ -609,6 +780,76 @@ static int pick_bn(const jl_gemm_params* p) {
   return best;
 }
 
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
+  using L = GemmSmem2<BN, STAGES>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "gemm(2cta): cannot reserve %d B of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  CUtensorMap ma, mb;
+  int rc;
+  if (A_MN) rc = make_map(&ma, p->a, p->m, p->k, p->lda, 64);
+  else rc = make_map(&ma, p->a, p->k, p->m, p->lda, GEMM_BM);
+  if (rc != JL_OK) return rc;
+  if (B_MN) rc = make_map(&mb, p->b, p->n, p->k, p->ldb, 64);
+  else rc = make_map(&mb, p->b, p->k, p->n, p->ldb, BN / 2);
+  if (rc != JL_OK) return rc;
+  GemmDev g = to_dev(p, BN);
+  g.num_m_tiles = ceil_div(p->m, 256);
+  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  const int pairs_max = num_sms() / 2;
+  const int pairs = tiles < pairs_max ? tiles : pairs_max;
+  kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
+  JL_CHECK_LAUNCH("gemm_tcgen05_2cta");
+  return JL_OK;
+}
+
+template <int BN, int STAGES>
+static int dispatch_layout_2cta(const jl_gemm_params* p, cudaStream_t s) {
+  const bool amn = p->a_layout == JL_LAYOUT_MN, bmn = p->b_layout == JL_LAYOUT_MN;
+  if constexpr ((BN / 2) % 64 == 0) {
+    if (amn && bmn) return launch_gemm_2cta<BN, STAGES, true, true>(p, s);
+    if (bmn) return launch_gemm_2cta<BN, STAGES, false, true>(p, s);
+  }
+  if (amn) return launch_gemm_2cta<BN, STAGES, true, false>(p, s);
+  return launch_gemm_2cta<BN, STAGES, false, false>(p, s);
+}
+
+static std::atomic<int> g_gemm_mode{0};   // 0 = auto, 1 = single-CTA kernel only, 2 = CTA-pair kernel wherever it is legal
+
+// N tile of the CTA-pair kernel, or 0 when the product should run on the single-CTA kernel.
+static int pick_bn_2cta(const jl_gemm_params* p) {
+  const int mode = g_gemm_mode.load();
+  if (mode == 1) return 0;
+  if (p->n < 128) return 0;
+  if (mode == 0 && (p->m < 1024 || static_cast<int64_t>(p->m) * p->n < 512 * 1024)) return 0;
+  int per = 0;
+  if (p->workspace != nullptr && pick_split(p, pick_bn(p), &per) > 1) return 0;
+  const bool bmn = p->b_layout == JL_LAYOUT_MN;
+  const int pairs = num_sms() / 2;
+  const int mt = ceil_div(p->m, 256);
+  int best = 0;
+  long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn == 192 && bmn) continue;
+    if (bn > 128 && bn / 2 >= p->n) continue;
+    const long tiles = static_cast<long>(mt) * ceil_div(p->n, bn);
+    const long waves = (tiles + pairs - 1) / pairs;
+    const long cost = waves * (bn + 32);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 }  // namespace jl
 
 extern "C" {
@@ -619,6 +860,12 @@ int jl_gemm_bf16(const jl_gemm_params* p, void* stream) {
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (jl::pick_bn_2cta(p)) {
+    case 256: return jl::dispatch_layout_2cta<256, 6>(p, s);
+    case 192: return jl::dispatch_layout_2cta<192, 6>(p, s);
+    case 128: return jl::dispatch_layout_2cta<128, 8>(p, s);
+    default: break;
+  }
   switch (jl::pick_bn(p)) {
     case 256: return jl::dispatch_layout<256, 4>(p, s);
     case 128: return jl::dispatch_layout<128, 6>(p, s);
@@ -626,6 +873,8 @@ int jl_gemm_bf16(const jl_gemm_params* p, void* stream) {
     default: return jl::dispatch_layout<32, 8>(p, s);
   }
 }
+
+void jl_debug_set_gemm_mode(int mode) { jl::g_gemm_mode.store(mode); }
 
 int jl_gemm_workspace_bytes(const jl_gemm_params* p, size_t* out) {
   JL_REQUIRE(out != nullptr, JL_EINVAL, "gemm_workspace_bytes: null out");

@@ -131,3 +131,56 @@ def test_gemm_rejects_bad_arguments():
         ops.gemm(a, b)
     with pytest.raises(ValueError):
         ops.gemm(torch.zeros(16, 16, dtype=BF16, device="cuda"), torch.zeros(16, 8, dtype=BF16, device="cuda"))
+
+
+@pytest.fixture
+def pair_mode():
+    L = pkg()._lib
+    L.load().jl_debug_set_gemm_mode(2)          # CTA-pair (cta_group::2) kernel wherever it is legal
+    yield
+    L.load().jl_debug_set_gemm_mode(0)
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 256, 128), (512, 128, 64), (8000, 768, 768), (8000, 2304, 768), (1000, 5000, 768),
+                                   (777, 200, 136), (8000, 3072, 768), (300, 192, 3072)])
+def test_gemm_cta_pair_kernel_plain(pair_mode, m, n, k):
+    ops, L = _ops()
+    a, b, _, _ = _mk(m, n, k, seed=21)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b, out_dtype=F32)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-3, (m, n, k)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("m,n,k", [(512, 256, 128), (8000, 768, 3072), (5000, 768, 8000), (1000, 136, 200)])
+def test_gemm_cta_pair_kernel_mn_major(pair_mode, m, n, k, a_mn, b_mn):
+    ops, L = _ops()
+    a, b, a_s, b_s = _mk(m, n, k, seed=22, a_mn=a_mn, b_mn=b_mn)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a_s, b_s, out_dtype=F32, a_layout=int(a_mn), b_layout=int(b_mn))
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-3, (m, n, k, a_mn, b_mn)
+
+
+def test_gemm_cta_pair_kernel_epilogues(pair_mode):
+    ops, L = _ops()
+    m, n, k = 1100, 392, 200
+    a, b, _, _ = _mk(m, n, k, seed=23)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    bias = torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(m, n, device="cuda", generator=g).to(BF16)
+    acc = a.float() @ b.float().t()
+    pre = torch.empty(m, n, dtype=BF16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU, aux_out=pre, residual=res, out_dtype=F32)
+    assert rel_err(out, torch.nn.functional.gelu(acc + bias) + res.float()) < 2e-3
+    assert rel_err(pre.float(), acc + bias) < 1e-2
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GLU)
+    v = acc + bias
+    assert rel_err(out.float(), v[:, 0::2] * torch.sigmoid(v[:, 1::2])) < 1e-2
+    lens = torch.tensor([275, 100, 0, 275], dtype=torch.int32, device="cuda")
+    out = ops.gemm(a, b, row_lengths=lens, rows_per_seq=275, out_dtype=F32)
+    t = torch.arange(m, device="cuda") % 275
+    valid = t < lens[torch.arange(m, device="cuda") // 275]
+    assert rel_err(out, acc * valid[:, None]) < 2e-3
+    torch.cuda.synchronize()
