@@ -234,6 +234,10 @@ typedef struct {
 } jl_adamw_params;
 int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
 
+/* test / tuning hook: attention implementation — 0 = tcgen05 kernels (TMEM scores, TMA operands), 1 = mma.sync
+ * flash kernels.  Both are the product's own kernels. */
+void jl_debug_set_attn_impl(int impl);
+
 /* test / tuning hook: 0 = automatic kernel choice (default), 1 = single-CTA tcgen05 kernel only, 2 = CTA-pair
  * (cta_group::2) kernel wherever it is legal.  Both are the product's own kernels; results are identical up to fp32
  * accumulation order. */

@@ -18,6 +18,7 @@ JL_EPI_NONE, JL_EPI_GELU, JL_EPI_RELU, JL_EPI_GELU_BWD, JL_EPI_RELU_BWD, JL_EPI_
 JL_LAYOUT_K, JL_LAYOUT_MN = 0, 1
 JL_CTC_SUM, JL_CTC_MEAN = 0, 1
 JL_MEL_BINS, JL_MEL_MAXW, JL_MEL_FRAMES_PER_CTA = 80, 32, 32
+DEFAULT_ATTN_IMPL = 1     # what the library starts with (0 = tcgen05 kernels, 1 = mma.sync kernels)
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -87,6 +88,7 @@ SYMBOLS = {
     "jl_gemm_bf16": (C.c_int, [C.POINTER(GemmParams), vp]),
     "jl_debug_gemm_ref": (C.c_int, [C.POINTER(GemmParams), vp]),
     "jl_debug_set_gemm_mode": (None, [C.c_int]),
+    "jl_debug_set_attn_impl": (None, [C.c_int]),
     "jl_gemm_workspace_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), vp]),
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),

@@ -10,6 +10,8 @@
 // atomics.  Key-padding mask from `lengths`; query rows >= length produce zeros and receive no gradient.
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace jl {
@@ -408,9 +410,15 @@ static int attn_check(const void* q, const void* k, const void* v, int64_t ld_qk
   return JL_OK;
 }
 
+int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream);   // attention_tc.cu
+int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream);
+static std::atomic<int> g_attn_impl{1};   // 0 = tcgen05 kernels, 1 = mma.sync kernels
+
 }  // namespace jl
 
 extern "C" {
+
+void jl_debug_set_attn_impl(int impl) { jl::g_attn_impl.store(impl); }
 
 int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream) {
   JL_REQUIRE(p != nullptr, JL_EINVAL, "attn_fwd: null params");
@@ -419,6 +427,7 @@ int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream) {
   JL_REQUIRE(p->o && (p->ld_o & 7) == 0 && (reinterpret_cast<uintptr_t>(p->o) & 15) == 0, JL_EINVAL, "attn_fwd: bad output pointer / stride");
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
+  if (jl::g_attn_impl.load() == 0) return jl::attn_fwd_tc(p, reinterpret_cast<cudaStream_t>(stream));
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
   jl::attn_fwd_kernel<<<grid, jl::ATT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   JL_CHECK_LAUNCH("attn_fwd");
@@ -437,6 +446,7 @@ int jl_attn_bwd(const jl_attn_bwd_params* p, void* stream) {
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (jl::g_attn_impl.load() == 0) return jl::attn_bwd_tc(p, s);
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
   jl::attn_bwd_dq_kernel<<<grid, jl::ATT_THREADS, 0, s>>>(*p);
   JL_CHECK_LAUNCH("attn_bwd_dq");

@@ -1,0 +1,536 @@
+// Attention on the 5th-generation tensor cores: softmax(Q Kᵀ·scale + keymask) V per (utterance, head), head_dim 64,
+// forward and backward, scores never leave the SM.
+// Replaces the eager attention math of SP/transformers/models/wav2vec2/modeling_wav2vec2.py:438-463 (+ its autograd
+// backward) and serves the AttAdapter's one-head attention.
+//
+// Common structure (256 threads, up to 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs):
+//   warp 0      TMA producer — 128B-swizzled [rows × 64] bf16 boxes straight out of the [B·T, ld] q|k|v / dO matrices
+//   warp 1      one thread issues tcgen05.mma (M = 128 rows = the CTA's "outer" tile, N = 64, K = 64), accumulators in TMEM
+//   warp 2      TMEM allocator (256 columns)
+//   warps 4-7   128 threads = 128 TMEM lanes = 128 outer rows: tcgen05.ld the score row, exp2 / mask / scale in
+//               registers, write the bf16 operand tile (P, dS, Pᵀ, dSᵀ) back to shared memory in the K-major
+//               128B-swizzle layout the next MMA reads, tcgen05.st for the online-softmax rescale of O
+// The same 64-row TMA tile is used as a K-major B operand (scores) and as an MN-major B operand (value / gradient
+// products) — no transposed copies.
+//   forward   outer = 128 queries, inner = 64 keys:  S = Q·Kᵀ → P → O += P·V            (online softmax, O rescaled in TMEM)
+//   bwd dQ    outer = 128 queries, inner = 64 keys:  S = Q·Kᵀ, dP = dO·Vᵀ → dS → dQ += dS·K   (also writes delta = rowsum(dO∘O))
+//   bwd dKV   outer = 128 keys,    inner = 64 queries: Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ → Pᵀ, dSᵀ → dV += Pᵀ·dO, dK += dSᵀ·Q
+// Every gradient element has exactly one writer (deterministic, no atomics).
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace jl {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_OUTER = 128;
+constexpr int TC_INNER = 64;
+constexpr uint32_t TC_T128 = 128 * 128;   // bytes of a [128 × 64] bf16 tile
+constexpr uint32_t TC_T64 = 64 * 128;     // bytes of a [ 64 × 64] bf16 tile
+constexpr float TC_LOG2E = 1.4426950408889634f;
+constexpr uint32_t TC_IDESC_KK = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // M128 N64, A,B K-major
+constexpr uint32_t TC_IDESC_KMN = TC_IDESC_KK | (1u << 16);                                                        // B MN-major
+
+// D[128 × 64] (+)= A[128 × 64] · B, A K-major at a_addr; B = 64-row tile at b_addr read K-major (Bᵀ: rows are N) or
+// MN-major (rows are K).  4 MMAs of K = 16.
+__device__ __forceinline__ void tc_mma_64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool b_mn, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t da = ptx::make_sw128_desc(a_addr + k * 32, 16, 1024);
+    const uint64_t db = b_mn ? ptx::make_sw128_desc(b_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
+    ptx::umma_bf16(d_tmem, da, db, b_mn ? TC_IDESC_KMN : TC_IDESC_KK, (accumulate || k > 0) ? 1u : 0u);
+  }
+}
+
+// Row r of a [128 × 64] bf16 K-major 128B-swizzled tile: 8 chunks of 16 B, physical chunk = c ^ (r & 7).
+__device__ __forceinline__ void tc_store_row(uint8_t* tile, int r, const uint32_t (&packed)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 v = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+}
+
+// 16 consecutive columns (two 16-byte chunks, first chunk index c0) of row r
+__device__ __forceinline__ void tc_store_cols16(uint8_t* tile, int r, int c0, const uint32_t (&pk)[8]) {
+  *reinterpret_cast<uint4*>(tile + r * 128 + (((c0) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(tile + r * 128 + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+__device__ __forceinline__ void tc_store_global_row32(__nv_bfloat16* dst, const float (&v)[32], float s) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 o;
+    o.x = pack_bf16x2(v[8 * i + 0] * s, v[8 * i + 1] * s);
+    o.y = pack_bf16x2(v[8 * i + 2] * s, v[8 * i + 3] * s);
+    o.z = pack_bf16x2(v[8 * i + 4] * s, v[8 * i + 5] * s);
+    o.w = pack_bf16x2(v[8 * i + 6] * s, v[8 * i + 7] * s);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+
+__device__ __forceinline__ void tc_zero_rows(__nv_bfloat16* base, int64_t ld, int row0, int seq) {
+  for (int idx = threadIdx.x; idx < TC_OUTER * 8; idx += TC_THREADS) {
+    const int r = idx >> 3, c = idx & 7;
+    if (row0 + r < seq) *reinterpret_cast<uint4*>(base + static_cast<int64_t>(row0 + r) * ld + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+struct TcBars {
+  uint64_t x_full;         // outer tile(s) landed
+  uint64_t y_full[2];      // inner tile stage landed
+  uint64_t y_empty[2];     // inner tile stage consumed by the accumulate MMAs
+  uint64_t s_full[2];      // score MMAs complete (fwd: two score buffers; bwd uses [0])
+  uint64_t s_empty[2];     // score rows read into registers by the 4 softmax warps
+  uint64_t p_full;         // operand tile(s) written to shared memory by the 4 softmax warps
+  uint64_t acc_done;       // accumulate MMAs of the current inner tile complete
+  uint32_t tmem_slot;
+};
+
+// ================================================================================================ forward
+struct __align__(1024) AttnFwdSmem {
+  uint8_t q[TC_T128];
+  uint8_t k[2][TC_T64];
+  uint8_t v[2][TC_T64];
+  uint8_t p[TC_T128];
+  TcBars bars;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                   const jl_attn_fwd_params p) {
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_OUTER;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
+  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
+  if (q0 >= len) {   // the whole query tile is padding
+    tc_zero_rows(o, p.ld_o, q0, p.seq);
+    if (lse && threadIdx.x < TC_OUTER && q0 + threadIdx.x < p.seq) lse[q0 + threadIdx.x] = 0.0f;
+    return;
+  }
+  extern __shared__ uint8_t tc_smem_raw[];
+  AttnFwdSmem& s = *reinterpret_cast<AttnFwdSmem*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
+  TcBars& B = s.bars;
+  const int nkb = (len + TC_INNER - 1) / TC_INNER;
+
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(&B.x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&B.y_full[i], 1);
+      ptx::mbar_init(&B.y_empty[i], 2);     // K slot freed by the score MMA commit, V slot by the PV commit
+      ptx::mbar_init(&B.s_full[i], 1);
+      ptx::mbar_init(&B.s_empty[i], 4);
+    }
+    ptx::mbar_init(&B.p_full, 4);
+    ptx::mbar_init(&B.acc_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&B.tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = B.tmem_slot;
+  const uint32_t t_s[2] = {tmem, tmem + 64};
+  const uint32_t t_o = tmem + 128;
+  const int grow = static_cast<int>(row_base);        // row of the utterance's first frame in the [B·T, ld] matrices
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&B.x_full, TC_T128);
+      ptx::tma_load_2d(s.q, &tq, &B.x_full, h * 64, grow + q0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&B.y_empty[st], ((j >> 1) & 1) ^ 1u);
+        ptx::mbar_expect_tx(&B.y_full[st], 2 * TC_T64);
+        ptx::tma_load_2d(s.k[st], &tk, &B.y_full[st], h * 64, grow + j * TC_INNER);
+        ptx::tma_load_2d(s.v[st], &tv, &B.y_full[st], h * 64, grow + j * TC_INNER);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t q_addr = ptx::smem_u32(s.q), p_addr = ptx::smem_u32(s.p);
+      ptx::mbar_wait(&B.x_full, 0);
+      auto issue_scores = [&](int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&B.y_full[st], (j >> 1) & 1);
+        ptx::mbar_wait(&B.s_empty[st], ((j >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        tc_mma_64(t_s[st], q_addr, ptx::smem_u32(s.k[st]), false, false);          // S_j = Q · K_jᵀ
+        ptx::umma_commit(&B.y_empty[st]);
+        ptx::umma_commit(&B.s_full[st]);
+      };
+      issue_scores(0);
+      for (int j = 0; j < nkb; ++j) {
+        if (j + 1 < nkb) issue_scores(j + 1);
+        ptx::mbar_wait(&B.p_full, j & 1);
+        ptx::tc_fence_after();
+        tc_mma_64(t_o, p_addr, ptx::smem_u32(s.v[j & 1]), true, j > 0);              // O += P_j · V_j
+        ptx::umma_commit(&B.y_empty[j & 1]);
+        ptx::umma_commit(&B.acc_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int r = (warp & 3) * 32 + lane;                  // TMEM lane = query row of the tile
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const float sl2 = p.scale * TC_LOG2E;
+    float m = -CUDART_INF_F, l = 0.0f;
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j & 1;
+      ptx::mbar_wait(&B.s_full[st], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      const int kbase = j * TC_INNER;
+      // pass 1: running row max over the 64 scores (16 columns per TMEM load keeps the register footprint small)
+      float mx = m;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(t_s[st] + lane_off + q * 16, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (kbase + q * 16 + i < len) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float corr = exp2f((m - mx) * sl2);             // mx finite: every key tile holds >= 1 valid key
+      const float mxs = mx * sl2;
+      if (j > 0) {
+        ptx::mbar_wait(&B.acc_done, (j - 1) & 1);          // PV_{j-1} complete: O may be rescaled, P may be overwritten
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, corr != 1.0f)) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t ov[32];
+            ptx::tmem_ld_32x32(t_o + lane_off + hh * 32, ov);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+            ptx::tmem_st_32x32(t_o + lane_off + hh * 32, ov);
+          }
+          ptx::tmem_st_wait();
+        }
+      }
+      // pass 2: P = exp2(S·scale·log2e − max) → bf16 operand tile, row sum
+      float sum = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[16], pk[8];
+        ptx::tmem_ld_32x16(t_s[st] + lane_off + q * 16, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = kbase + q * 16 + 2 * i;
+          const float a = (c < len) ? exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -mxs)) : 0.0f;
+          const float e = (c + 1 < len) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -mxs)) : 0.0f;
+          sum += a + e;
+          pk[i] = pack_bf16x2(a, e);
+        }
+        tc_store_cols16(s.p, r, 2 * q, pk);
+      }
+      l = l * corr + sum;
+      m = mx;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.s_empty[st]);      // score buffer may be overwritten by block j + 2
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.p_full);
+    }
+    ptx::mbar_wait(&B.acc_done, (nkb - 1) & 1);
+    ptx::tc_fence_after();
+    const int row = q0 + r;
+    const float inv = (row < len) ? 1.0f / l : 0.0f;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t ov[32];
+      ptx::tmem_ld_32x32(t_o + lane_off + hh * 32, ov);
+      ptx::tmem_ld_wait();
+      float of[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
+      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + hh * 32, of, inv);
+    }
+    if (lse && row < p.seq) lse[row] = (row < len) ? m * p.scale + logf(l) : 0.0f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// ================================================================================================ backward
+// MODE 0: dQ   (outer rows = queries; X1 = Q, X2 = dO; inner: Y1 = K_j, Y2 = V_j;  acc0 = dQ += dS · K_j)
+// MODE 1: dKV  (outer rows = keys;    X1 = K, X2 = V;  inner: Y1 = Q_i, Y2 = dO_i; acc0 = dV += Pᵀ · dO_i, acc1 = dK += dSᵀ · Q_i)
+template <int MODE>
+struct __align__(1024) AttnBwdSmem {
+  uint8_t x1[TC_T128];
+  uint8_t x2[TC_T128];
+  uint8_t y1[2][TC_T64];
+  uint8_t y2[2][TC_T64];
+  uint8_t op0[TC_T128];                       // dS (MODE 0) / Pᵀ (MODE 1)
+  uint8_t op1[MODE == 1 ? TC_T128 : 16];      // dSᵀ (MODE 1)
+  float col_lse[2][TC_INNER];                 // MODE 1: per-query log-sum-exp (×log2e) and delta of the inner tile
+  float col_delta[2][TC_INNER];
+  TcBars bars;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constant__ CUtensorMap tx2, const __grid_constant__ CUtensorMap ty1,
+                   const __grid_constant__ CUtensorMap ty2, const jl_attn_bwd_params p) {
+  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * TC_OUTER;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(MODE == 0 ? p.dq : p.dv) + row_base * p.ld_dqkv + h * 64;
+  __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
+  if (r0 >= len) {
+    tc_zero_rows(out0, p.ld_dqkv, r0, p.seq);
+    if (MODE == 1) tc_zero_rows(out1, p.ld_dqkv, r0, p.seq);
+    if (MODE == 0 && threadIdx.x < TC_OUTER && r0 + threadIdx.x < p.seq) delta[r0 + threadIdx.x] = 0.0f;
+    return;
+  }
+  extern __shared__ uint8_t tc_smem_raw[];
+  AttnBwdSmem<MODE>& s = *reinterpret_cast<AttnBwdSmem<MODE>*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
+  TcBars& B = s.bars;
+  const int nib = (len + TC_INNER - 1) / TC_INNER;
+
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(&B.x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&B.y_full[i], 1);
+      ptx::mbar_init(&B.y_empty[i], 1);
+      ptx::mbar_init(&B.s_full[i], 1);
+      ptx::mbar_init(&B.s_empty[i], 4);
+    }
+    ptx::mbar_init(&B.p_full, 4);
+    ptx::mbar_init(&B.acc_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&B.tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = B.tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 64, t_acc0 = tmem + 128, t_acc1 = tmem + 192;
+  const int grow = static_cast<int>(row_base);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&B.x_full, 2 * TC_T128);
+      ptx::tma_load_2d(s.x1, &tx1, &B.x_full, h * 64, grow + r0);
+      ptx::tma_load_2d(s.x2, &tx2, &B.x_full, h * 64, grow + r0);
+      for (int j = 0; j < nib; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&B.y_empty[st], ((j >> 1) & 1) ^ 1u);
+        ptx::mbar_expect_tx(&B.y_full[st], 2 * TC_T64);
+        ptx::tma_load_2d(s.y1[st], &ty1, &B.y_full[st], h * 64, grow + j * TC_INNER);
+        ptx::tma_load_2d(s.y2[st], &ty2, &B.y_full[st], h * 64, grow + j * TC_INNER);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t x1 = ptx::smem_u32(s.x1), x2 = ptx::smem_u32(s.x2);
+      const uint32_t op0 = ptx::smem_u32(s.op0), op1 = ptx::smem_u32(s.op1);
+      ptx::mbar_wait(&B.x_full, 0);
+      auto issue_scores = [&](int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&B.y_full[st], (j >> 1) & 1);
+        ptx::mbar_wait(&B.s_empty[0], (j & 1) ^ 1u);                     // score rows of block j-1 are in registers
+        ptx::tc_fence_after();
+        tc_mma_64(t_s, x1, ptx::smem_u32(s.y1[st]), false, false);         // S  = X1 · Y1ᵀ
+        tc_mma_64(t_dp, x2, ptx::smem_u32(s.y2[st]), false, false);        // dP = X2 · Y2ᵀ
+        ptx::umma_commit(&B.s_full[0]);
+      };
+      issue_scores(0);
+      for (int j = 0; j < nib; ++j) {
+        if (j + 1 < nib) issue_scores(j + 1);
+        const int st = j & 1;
+        ptx::mbar_wait(&B.p_full, j & 1);
+        ptx::tc_fence_after();
+        if (MODE == 0) {
+          tc_mma_64(t_acc0, op0, ptx::smem_u32(s.y1[st]), true, j > 0);    // dQ += dS · K_j
+        } else {
+          tc_mma_64(t_acc0, op0, ptx::smem_u32(s.y2[st]), true, j > 0);    // dV += Pᵀ · dO_i
+          tc_mma_64(t_acc1, op1, ptx::smem_u32(s.y1[st]), true, j > 0);    // dK += dSᵀ · Q_i
+        }
+        ptx::umma_commit(&B.y_empty[st]);
+        ptx::umma_commit(&B.acc_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int tid = threadIdx.x - 128;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int row = r0 + r;                                  // query (MODE 0) / key (MODE 1) index
+    const bool row_ok = row < len;
+    const float sl2 = p.scale * TC_LOG2E;
+    float row_lse = 0.0f, row_delta = 0.0f;
+    if (MODE == 0) {
+      // delta[q] = Σ_d dO[q, d] · O[q, d]
+      if (row_ok) {
+        const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o) + (row_base + row) * p.ld_o + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (row_base + row) * p.ld_o + h * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 a = __ldg(po + i), c = __ldg(pd + i);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = unpack_bf16x2(aw[q]), fc = unpack_bf16x2(cw[q]);
+            row_delta = fmaf(fa.x, fc.x, row_delta);
+            row_delta = fmaf(fa.y, fc.y, row_delta);
+          }
+        }
+        row_lse = lse[row] * TC_LOG2E;
+      }
+      if (row < p.seq) delta[row] = row_delta;
+    }
+    for (int j = 0; j < nib; ++j) {
+      const int st = j & 1;
+      const int cbase = j * TC_INNER;                        // first key (MODE 0) / query (MODE 1) of the inner tile
+      if (MODE == 1) {
+        if (tid < TC_INNER) {
+          const int q = cbase + tid;
+          s.col_lse[st][tid] = (q < len) ? lse[q] * TC_LOG2E : 0.0f;
+        } else {
+          const int q = cbase + tid - TC_INNER;
+          s.col_delta[st][tid - TC_INNER] = (q < len) ? delta[q] : 0.0f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      ptx::mbar_wait(&B.s_full[0], j & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t sv[16], dv[16], pk0[8], pk1[8];
+        ptx::tmem_ld_32x16(t_s + lane_off + q * 16, sv);
+        ptx::tmem_ld_32x16(t_dp + lane_off + q * 16, dv);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float pr[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = q * 16 + 2 * i + e;
+            const bool ok = row_ok && (cbase + c < len);
+            const float lse_c = (MODE == 0) ? row_lse : s.col_lse[st][c];
+            const float dl_c = (MODE == 0) ? row_delta : s.col_delta[st][c];
+            const float pe = ok ? exp2f(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -lse_c)) : 0.0f;
+            pr[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[2 * i + e]) - dl_c) * p.scale;
+          }
+          pk0[i] = (MODE == 0) ? pack_bf16x2(ds[0], ds[1]) : pack_bf16x2(pr[0], pr[1]);
+          pk1[i] = pack_bf16x2(ds[0], ds[1]);
+        }
+        if (q == 0 && j > 0) ptx::mbar_wait(&B.acc_done, (j - 1) & 1);   // accumulate MMAs of block j-1 have read the operand tiles
+        tc_store_cols16(s.op0, r, 2 * q, pk0);
+        if (MODE == 1) tc_store_cols16(s.op1, r, 2 * q, pk1);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);       // S / dP may be overwritten by block j + 1
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.p_full);
+    }
+    ptx::mbar_wait(&B.acc_done, (nib - 1) & 1);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int a = 0; a < (MODE == 1 ? 2 : 1); ++a) {
+      __nv_bfloat16* dst = (a == 0) ? out0 : out1;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t ov[32];
+        ptx::tmem_ld_32x32((a == 0 ? t_acc0 : t_acc1) + lane_off + hh * 32, ov);
+        ptx::tmem_ld_wait();
+        float of[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
+        if (row < p.seq) tc_store_global_row32(dst + static_cast<int64_t>(row) * p.ld_dqkv + hh * 32, of, 1.0f);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <typename K>
+static int tc_set_smem(K kern, size_t bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "%s: cannot reserve %zu B of shared memory: %s", name, bytes, cudaGetErrorString(e));
+  return JL_OK;
+}
+
+int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
+  const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
+  const int64_t inner = static_cast<int64_t>(p->heads) * 64;
+  CUtensorMap tq, tk, tv;
+  int rc = make_tma_map_2d_bf16(&tq, p->q, inner, rows, p->ld_qkv, TC_OUTER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&tk, p->k, inner, rows, p->ld_qkv, TC_INNER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&tv, p->v, inner, rows, p->ld_qkv, TC_INNER);
+  if (rc != JL_OK) return rc;
+  const size_t smem = sizeof(AttnFwdSmem) + 1024;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    rc = tc_set_smem(attn_fwd_tc_kernel, smem, "attn_fwd_tc");
+    if (rc != JL_OK) return rc;
+    configured_dev = dev;
+  }
+  dim3 grid(ceil_div(p->seq, TC_OUTER), p->heads, p->batch);
+  attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
+  JL_CHECK_LAUNCH("attn_fwd_tc");
+  return JL_OK;
+}
+
+int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream) {
+  const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
+  const int64_t inner = static_cast<int64_t>(p->heads) * 64;
+  CUtensorMap q128, do128, k64, v64, k128, v128, q64, do64;
+  int rc = make_tma_map_2d_bf16(&q128, p->q, inner, rows, p->ld_qkv, TC_OUTER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&do128, p->d_o, inner, rows, p->ld_o, TC_OUTER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&k64, p->k, inner, rows, p->ld_qkv, TC_INNER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&v64, p->v, inner, rows, p->ld_qkv, TC_INNER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&k128, p->k, inner, rows, p->ld_qkv, TC_OUTER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&v128, p->v, inner, rows, p->ld_qkv, TC_OUTER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&q64, p->q, inner, rows, p->ld_qkv, TC_INNER);
+  if (rc == JL_OK) rc = make_tma_map_2d_bf16(&do64, p->d_o, inner, rows, p->ld_o, TC_INNER);
+  if (rc != JL_OK) return rc;
+  const size_t smem0 = sizeof(AttnBwdSmem<0>) + 1024, smem1 = sizeof(AttnBwdSmem<1>) + 1024;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    rc = tc_set_smem(attn_bwd_tc_kernel<0>, smem0, "attn_bwd_tc<dq>");
+    if (rc == JL_OK) rc = tc_set_smem(attn_bwd_tc_kernel<1>, smem1, "attn_bwd_tc<dkv>");
+    if (rc != JL_OK) return rc;
+    configured_dev = dev;
+  }
+  dim3 grid(ceil_div(p->seq, TC_OUTER), p->heads, p->batch);
+  attn_bwd_tc_kernel<0><<<grid, TC_THREADS, smem0, stream>>>(q128, do128, k64, v64, *p);
+  JL_CHECK_LAUNCH("attn_bwd_tc_dq");
+  attn_bwd_tc_kernel<1><<<grid, TC_THREADS, smem1, stream>>>(k128, v128, q64, do64, *p);
+  JL_CHECK_LAUNCH("attn_bwd_tc_dkv");
+  return JL_OK;
+}
+
+}  // namespace jl

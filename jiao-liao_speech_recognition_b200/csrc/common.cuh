@@ -1,5 +1,6 @@
 // Shared host/device helpers for libjl_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,6 +13,9 @@ namespace jl {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_device();   // JL_OK when the current device is sm_100
+int num_sms();
+// 2-D bf16 tensor map: `inner` contiguous elements × `outer` rows (row stride ld elements), 128-byte swizzle, box = 64 × box_rows.
+int make_tma_map_2d_bf16(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_rows);
 
 #define JL_REQUIRE(cond, code, ...)       \
   do {                                    \

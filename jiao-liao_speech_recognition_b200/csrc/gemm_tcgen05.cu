@@ -17,7 +17,6 @@
 //   warps 4-11  epilogue: tcgen05.ld 32 lanes × 32 columns → registers → bias / GELU / ReLU / GLU / residual /
 //               activation-gradient / row masking → 16-byte global stores
 #include <cuda.h>
-#include <cudaTypedefs.h>
 
 #include <atomic>
 #include <mutex>
@@ -595,43 +594,8 @@ __global__ void gemm_ref_kernel(const GemmRefOperands o, const GemmDev g) {
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-  });
-  return fn;
-}
-
-// 2-D bf16 tensor map: `inner` contiguous elements × `outer` rows (row stride ld elements), 128B swizzle, box 64 × box_rows.
 static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
-  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
-  JL_REQUIRE(enc != nullptr, JL_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  JL_REQUIRE(r == CUDA_SUCCESS, JL_ECUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld", (int)r, ptr,
-             (long long)inner, (long long)outer, (long long)ld);
-  return JL_OK;
-}
-
-static int num_sms() {
-  static thread_local int cached_dev = -1, cached = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev != cached_dev) {
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    cached_dev = dev;
-  }
-  return cached;
+  return make_tma_map_2d_bf16(map, ptr, inner, outer, ld, box_rows);
 }
 
 static int validate(const jl_gemm_params* p) {

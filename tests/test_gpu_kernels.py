@@ -56,8 +56,17 @@ def _attn_ref(q, k, v, lengths, b, t, h, scale):
     return o * valid.reshape(b * t, 1)
 
 
-@pytest.mark.parametrize("b,t,h,lens", [(3, 250, 12, [250, 131, 64]), (2, 70, 1, [70, 1]), (2, 750, 2, [750, 300]), (1, 33, 3, [20])])
-def test_attention_fwd_bwd(b, t, h, lens):
+@pytest.fixture(params=[0, 1], ids=["tcgen05", "mma_sync"])
+def attn_impl(request):
+    lib = pkg()._lib.load()
+    lib.jl_debug_set_attn_impl(request.param)
+    yield request.param
+    lib.jl_debug_set_attn_impl(pkg()._lib.DEFAULT_ATTN_IMPL)
+
+
+@pytest.mark.parametrize("b,t,h,lens", [(3, 250, 12, [250, 131, 64]), (2, 70, 1, [70, 1]), (2, 750, 2, [750, 300]), (1, 33, 3, [20]),
+                                        (4, 128, 2, [128, 65, 64, 0])])
+def test_attention_fwd_bwd(attn_impl, b, t, h, lens):
     ops = pkg().ops
     g = _g(2)
     d = h * 64
