@@ -18,7 +18,7 @@ JL_EPI_NONE, JL_EPI_GELU, JL_EPI_RELU, JL_EPI_GELU_BWD, JL_EPI_RELU_BWD, JL_EPI_
 JL_LAYOUT_K, JL_LAYOUT_MN = 0, 1
 JL_CTC_SUM, JL_CTC_MEAN = 0, 1
 JL_MEL_BINS, JL_MEL_MAXW, JL_MEL_FRAMES_PER_CTA = 80, 32, 32
-DEFAULT_ATTN_IMPL = 1     # what the library starts with (0 = tcgen05 kernels, 1 = mma.sync kernels)
+DEFAULT_ATTN_IMPL = 0     # what the library starts with (0 = tcgen05 kernels, 1 = mma.sync kernels)
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

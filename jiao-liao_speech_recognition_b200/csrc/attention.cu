@@ -412,7 +412,7 @@ static int attn_check(const void* q, const void* k, const void* v, int64_t ld_qk
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream);   // attention_tc.cu
 int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream);
-static std::atomic<int> g_attn_impl{1};   // 0 = tcgen05 kernels, 1 = mma.sync kernels
+static std::atomic<int> g_attn_impl{0};   // 0 = tcgen05 kernels, 1 = mma.sync kernels
 
 }  // namespace jl
 
