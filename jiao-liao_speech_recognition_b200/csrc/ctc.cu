@@ -204,12 +204,18 @@ __global__ void __launch_bounds__(2 * CTC_LATTICE_HALF) ctc_lattice_kernel(const
     }
   }
   __syncthreads();
+  // The log-prob of the next frame is fetched before the barrier of the current one, so the global-load latency of
+  // the (serial) recursion is hidden behind the previous step.
+  float lp_pref = 0.0f;
+  if (T > 1 && gtid < L) lp_pref = lp_b[static_cast<int64_t>(is_beta ? T - 2 : 1) * Lmax + gtid];
   for (int step = 1; step < T; ++step) {
     const int t = is_beta ? T - 1 - step : step;
     const float* prev = buf + ((step - 1) & 1) * Lmax;
     float* cur = buf + (step & 1) * Lmax;
+    const float lp_first = lp_pref;
+    if (step + 1 < T && gtid < L) lp_pref = lp_b[static_cast<int64_t>(is_beta ? t - 1 : t + 1) * Lmax + gtid];
     for (int s = gtid; s < L; s += CTC_LATTICE_HALF) {
-      const float lp = lp_b[static_cast<int64_t>(t) * Lmax + s];
+      const float lp = (s == gtid) ? lp_first : lp_b[static_cast<int64_t>(t) * Lmax + s];
       float x0 = prev[s], x1 = -CUDART_INF_F, x2 = -CUDART_INF_F;
       if (!is_beta) {
         if (s >= 1) x1 = prev[s - 1];
@@ -278,10 +284,33 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
   __syncthreads();
   const T* x = logits + static_cast<int64_t>(row) * ld;
   const float lse = lse_all[row];
-  // softmax part, written once
-  for (int v = tid; v < vocab; v += CTC_GRAD_THREADS) {
-    const float sm = expf(ld_logit<T>(x, v) - lse);
-    st_grad<TG>(g, v, sm * scale);
+  // softmax part, written once (4 elements per thread per step when the rows are 16-byte aligned)
+  if ((ld & 3) == 0 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0) {
+    const int nv = vocab >> 2;
+    for (int i = tid; i < nv; i += CTC_GRAD_THREADS) {
+      float a[4];
+      if constexpr (sizeof(T) == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(x) + i);
+        a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(x) + i);
+        const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y);
+        a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = expf(a[e] - lse) * scale;
+      if constexpr (sizeof(TG) == 4) {
+        reinterpret_cast<float4*>(g)[i] = make_float4(a[0], a[1], a[2], a[3]);
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(a[0], a[1]);
+        o.y = pack_bf16x2(a[2], a[3]);
+        reinterpret_cast<uint2*>(g)[i] = o;
+      }
+    }
+    for (int v = nv * 4 + tid; v < vocab; v += CTC_GRAD_THREADS) st_grad<TG>(g, v, expf(ld_logit<T>(x, v) - lse) * scale);
+  } else {
+    for (int v = tid; v < vocab; v += CTC_GRAD_THREADS) st_grad<TG>(g, v, expf(ld_logit<T>(x, v) - lse) * scale);
   }
   // blank: fixed-order sum over the even states (warp 0: strided partials in lane order, then a shuffle tree)
   if (tid < 32) {

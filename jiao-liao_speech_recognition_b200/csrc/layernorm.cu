@@ -90,16 +90,19 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_laye
   }
 }
 
-template <int NCH>
+// WGRAD = false (frozen norms of the backbone: dx only) keeps the dγ/dβ accumulators out of the register file, which
+// doubles the resident warps of this HBM-bound kernel.
+template <int NCH, bool WGRAD>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_layernorm_bwd_params p) {
-  __shared__ float s_red[NCH * 256];
+  __shared__ float s_red[WGRAD ? NCH * 256 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = p.d >> 3;
   const float inv_d = 1.0f / static_cast<float>(p.d);
-  const bool want_wgrad = (p.dgamma != nullptr);
-  float dg[NCH][8], db[NCH][8];
+  constexpr bool want_wgrad = WGRAD;
+  constexpr int NW = WGRAD ? NCH : 1;
+  float dg[NW][8], db[NW][8];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NW; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[c][j] = 0.0f; db[c][j] = 0.0f; }
 
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (x[c][j] - mean) * rstd;
-          if (want_wgrad) { dg[c][j] = fmaf(dy[c][j], xh, dg[c][j]); db[c][j] += dy[c][j]; }
+          if constexpr (WGRAD) { dg[c][j] = fmaf(dy[c][j], xh, dg[c][j]); db[c][j] += dy[c][j]; }
           const float gy = dy[c][j] * g[j];
           x[c][j] = xh;
           dy[c][j] = gy;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
     }
   }
 
-  if (want_wgrad) {
+  if constexpr (WGRAD) {
     // CTA reduction of the per-warp accumulators (warps add in fixed order) → one partial row per CTA
     for (int pass = 0; pass < 2; ++pass) {
       for (int w = 0; w < LN_WARPS; ++w) {
@@ -243,10 +246,20 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, jl::LN_WARPS);
+  const bool wg = p->dgamma != nullptr;
   switch (jl::ln_pick(p->d)) {
-    case 3: jl::layernorm_bwd_kernel<3><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
-    case 4: jl::layernorm_bwd_kernel<4><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
-    default: jl::layernorm_bwd_kernel<8><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    case 3:
+      if (wg) jl::layernorm_bwd_kernel<3, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      else jl::layernorm_bwd_kernel<3, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      break;
+    case 4:
+      if (wg) jl::layernorm_bwd_kernel<4, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      else jl::layernorm_bwd_kernel<4, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      break;
+    default:
+      if (wg) jl::layernorm_bwd_kernel<8, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      else jl::layernorm_bwd_kernel<8, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      break;
   }
   JL_CHECK_LAUNCH("layernorm_bwd");
   if (p->dgamma != nullptr) {
