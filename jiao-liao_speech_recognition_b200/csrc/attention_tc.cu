@@ -186,23 +186,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       ptx::mbar_wait(&B.s_full[st], (j >> 1) & 1);
       ptx::tc_fence_after();
       const int kbase = j * TC_INNER;
-      // pass 1: running row max over the 64 scores (16 columns per TMEM load keeps the register footprint small)
+      // the 64 scores of this row: two 32-column TMEM loads, one wait; the score buffer is released right away
+      uint32_t sv[64];
+      ptx::tmem_ld_32x32(t_s[st] + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      ptx::tmem_ld_32x32(t_s[st] + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.s_empty[st]);      // score buffer may be overwritten by block j + 2
+      const bool partial = kbase + TC_INNER > len;          // only the last key tile needs the padding mask
       float mx = m;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(t_s[st] + lane_off + q * 16, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (kbase + q * 16 + i < len) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int i = 0; i < 64; ++i) {
+        if (partial && kbase + i >= len) sv[i] = 0xff800000u;     // -inf
+        mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
-      const float corr = exp2f((m - mx) * sl2);             // mx finite: every key tile holds >= 1 valid key
-      const float mxs = mx * sl2;
+      // Lazy rescale: keep the old reference max unless the row max grew by more than 2^8 (exp2 arguments stay <= 8, far
+      // from overflow); O and l are only rescaled then, which removes most TMEM round trips of the online softmax.
+      const bool grow = (mx - m) * sl2 > 8.0f;              // true on the first tile (m = -inf)
+      const float m_new = grow ? mx : m;
+      const float corr = grow ? exp2f((m - m_new) * sl2) : 1.0f;
+      const float mxs = m_new * sl2;
+      float sum = 0.0f;
+      uint32_t packed[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float a = exp2f(fmaf(__uint_as_float(sv[2 * i]), sl2, -mxs));
+        const float e = exp2f(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mxs));
+        sum += a + e;
+        packed[i] = pack_bf16x2(a, e);
+      }
+      l = l * corr + sum;
+      m = m_new;
       if (j > 0) {
         ptx::mbar_wait(&B.acc_done, (j - 1) & 1);          // PV_{j-1} complete: O may be rescaled, P may be overwritten
         ptx::tc_fence_after();
-        if (__any_sync(0xffffffffu, corr != 1.0f)) {
+        if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t ov[32];
@@ -213,30 +232,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             ptx::tmem_st_32x32(t_o + lane_off + hh * 32, ov);
           }
           ptx::tmem_st_wait();
+          ptx::tc_fence_before();
         }
       }
-      // pass 2: P = exp2(S·scale·log2e − max) → bf16 operand tile, row sum
-      float sum = 0.0f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t v[16], pk[8];
-        ptx::tmem_ld_32x16(t_s[st] + lane_off + q * 16, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = kbase + q * 16 + 2 * i;
-          const float a = (c < len) ? exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -mxs)) : 0.0f;
-          const float e = (c + 1 < len) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -mxs)) : 0.0f;
-          sum += a + e;
-          pk[i] = pack_bf16x2(a, e);
-        }
-        tc_store_cols16(s.p, r, 2 * q, pk);
-      }
-      l = l * corr + sum;
-      m = mx;
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&B.s_empty[st]);      // score buffer may be overwritten by block j + 2
+      tc_store_row(s.p, r, packed);
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&B.p_full);
@@ -414,17 +413,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
       ptx::mbar_wait(&B.s_full[0], j & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t sv[16], dv[16], pk0[8], pk1[8];
-        ptx::tmem_ld_32x16(t_s + lane_off + q * 16, sv);
-        ptx::tmem_ld_32x16(t_dp + lane_off + q * 16, dv);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t sv[32], dv[32], pk0[16], pk1[16];
+        ptx::tmem_ld_32x32(t_s + lane_off + hh * 32, sv);
+        ptx::tmem_ld_32x32(t_dp + lane_off + hh * 32, dv);
         ptx::tmem_ld_wait();
+        if (hh == 1) {                                       // both halves are in registers: release the score buffers
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           float pr[2], ds[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int c = q * 16 + 2 * i + e;
+            const int c = hh * 32 + 2 * i + e;
             const bool ok = row_ok && (cbase + c < len);
             const float lse_c = (MODE == 0) ? row_lse : s.col_lse[st][c];
             const float dl_c = (MODE == 0) ? row_delta : s.col_delta[st][c];
@@ -435,13 +439,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
           pk0[i] = (MODE == 0) ? pack_bf16x2(ds[0], ds[1]) : pack_bf16x2(pr[0], pr[1]);
           pk1[i] = pack_bf16x2(ds[0], ds[1]);
         }
-        if (q == 0 && j > 0) ptx::mbar_wait(&B.acc_done, (j - 1) & 1);   // accumulate MMAs of block j-1 have read the operand tiles
-        tc_store_cols16(s.op0, r, 2 * q, pk0);
-        if (MODE == 1) tc_store_cols16(s.op1, r, 2 * q, pk1);
+        if (hh == 0 && j > 0) ptx::mbar_wait(&B.acc_done, (j - 1) & 1);   // accumulate MMAs of block j-1 have read the operand tiles
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t t0[8], t1[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { t0[i] = pk0[8 * c2 + i]; t1[i] = pk1[8 * c2 + i]; }
+          tc_store_cols16(s.op0, r, 4 * hh + 2 * c2, t0);
+          if (MODE == 1) tc_store_cols16(s.op1, r, 4 * hh + 2 * c2, t1);
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);       // S / dP may be overwritten by block j + 1
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&B.p_full);

@@ -65,54 +65,53 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
   }
 }
 
-// Column sums, stage 1: grid (ceil(cols / 256), nsplit); 256 threads = 8 row groups × 32 lanes × 8 columns (16-byte loads).
-constexpr int COLSUM_SPLITS = 64;
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols,
-                                                             float* __restrict__ partial) {
-  __shared__ float s_acc[8][32][9];
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 256 + lane * 8;
-  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
-  const int r_begin = blockIdx.y * rows_per;
-  const int r_end = min(rows, r_begin + rows_per);
+// Column sums (bias gradients) in ONE launch: a CTA owns 8 adjacent columns, its 256 threads walk the rows with 16-byte
+// loads (thread t takes rows t, t + 256, …), then the 256 partials are combined by a fixed-order shared-memory tree —
+// deterministic, no atomics, no second kernel.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+  __shared__ float s_acc[256][9];
+  const int col = blockIdx.x * 8;
+  const int tid = threadIdx.x;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-  if (col < cols) {
-    const bool vec = (col + 8 <= cols) && ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    for (int r = r_begin + grp; r < r_end; r += 8) {
-      const __nv_bfloat16* p = x + static_cast<int64_t>(r) * ldx + col;
-      if (vec) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+  const bool vec = (col + 8 <= cols) && ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    int r = tid;
+    for (; r + 768 < rows; r += 1024) {            // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r + 256 * u) * ldx + col));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
         acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
         acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (col + j < cols) acc[j] += __bfloat162float(p[j]);
       }
     }
+    for (; r < rows; r += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
+      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+      acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+    }
+  } else {
+    for (int r = tid; r < rows; r += 256)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (col + j < cols) acc[j] += __bfloat162float(x[static_cast<int64_t>(r) * ldx + col + j]);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s_acc[grp][lane][j] = acc[j];
+  for (int j = 0; j < 8; ++j) s_acc[tid][j] = acc[j];
   __syncthreads();
-  // thread t sums column (blockIdx.x * 256 + t) over the 8 row groups in fixed order
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < cols) {
-    const int l = threadIdx.x >> 3, j = threadIdx.x & 7;
-    float t = 0.0f;
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    if (tid < stride) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += s_acc[g][l][j];
-    partial[static_cast<int64_t>(blockIdx.y) * cols + c] = t;
+      for (int j = 0; j < 8; ++j) s_acc[tid][j] += s_acc[tid + stride][j];
+    }
+    __syncthreads();
   }
-}
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nsplit, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float a = 0.0f;
-  for (int k = 0; k < nsplit; ++k) a += partial[static_cast<int64_t>(k) * cols + c];
-  out[c] = a;
+  if (tid < 8 && col + tid < cols) out[col + tid] = s_acc[0][tid];
 }
 
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
@@ -232,23 +231,19 @@ int jl_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, 
 
 int jl_colsum_workspace_bytes(int32_t rows, int32_t cols, size_t* out) {
   JL_REQUIRE(out != nullptr && rows > 0 && cols > 0, JL_EINVAL, "colsum_workspace_bytes: bad argument");
-  *out = static_cast<size_t>(jl::COLSUM_SPLITS) * cols * sizeof(float);
+  *out = 0;   // single-pass kernel: no scratch needed (the argument is kept for ABI stability)
   return JL_OK;
 }
 
 int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, float* partial, void* stream) {
-  JL_REQUIRE(x && out && partial, JL_EINVAL, "colsum: null pointer");
+  (void)partial;
+  JL_REQUIRE(x && out, JL_EINVAL, "colsum: null pointer");
   JL_REQUIRE(rows > 0 && cols > 0 && ldx >= cols, JL_EINVAL, "colsum: bad dims");
-    int rc = jl::check_device();
+  int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int nsplit = jl::ceil_div(rows, 64);
-  if (nsplit > jl::COLSUM_SPLITS) nsplit = jl::COLSUM_SPLITS;
-  dim3 grid(jl::ceil_div(cols, 256), nsplit);
-  jl::colsum_partial_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, cols, partial);
-  JL_CHECK_LAUNCH("colsum_partial");
-  jl::colsum_final_kernel<<<jl::ceil_div(cols, 256), 256, 0, s>>>(partial, nsplit, cols, out);
-  JL_CHECK_LAUNCH("colsum_final");
+  jl::colsum_kernel<<<jl::ceil_div(cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows,
+                                                                                             cols, out);
+  JL_CHECK_LAUNCH("colsum");
   return JL_OK;
 }
 

@@ -8,13 +8,13 @@
 // modeling_speech_to_text.py:82-99), the adapter projections, and — with the MN-major operand modes —
 // the dgrad (dY·W) and wgrad (dYᵀ·X) products of the adapter-only backward without transposed copies.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 512 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes → STAGES-deep smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer: one elected lane issues 4 × tcgen05.mma (128 × BN × 16) per 64-wide k-block,
 //               tcgen05.commit releases the smem slot / publishes the accumulator
 //   warp 2      TMEM allocator (2 accumulator stages × BN fp32 columns) so the epilogue of tile i overlaps the
 //               mainloop of tile i+1
-//   warps 4-11  epilogue: tcgen05.ld 32 lanes × 32 columns → registers → bias / GELU / ReLU / GLU / residual /
+//   warps 4-15  epilogue: tcgen05.ld 32 lanes × 32 columns → registers → bias / GELU / ReLU / GLU / residual /
 //               activation-gradient / row masking → 16-byte global stores
 #include <cuda.h>
 
@@ -28,7 +28,7 @@ namespace jl {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 12;
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
@@ -108,7 +108,40 @@ __device__ __forceinline__ void store_f32_row(float* p, bool vec, int nvalid, co
   }
 }
 
-__device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, int col0, float (&acc)[32]) {
+// Epilogue inputs that do not depend on the accumulator (residual row, activation-gradient input) are requested before
+// the epilogue waits on its TMEM load, so their L2 / HBM latency overlaps the TMEM read instead of following it.
+struct EpiPrefetch {
+  uint4 res[4];
+  uint4 aux[4];
+};
+__device__ __forceinline__ bool epi_res_vec(const GemmDev& g, int row, int col0) {
+  return g.residual != nullptr && row < g.m && col0 + 32 <= g.n && (g.ldr & 7) == 0 && g.epilogue != JL_EPI_GLU;
+}
+__device__ __forceinline__ bool epi_aux_vec(const GemmDev& g, int row, int col0) {
+  return (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) && row < g.m && col0 + 32 <= g.n && (g.ldaux & 7) == 0;
+}
+__device__ __forceinline__ void epi_prefetch(const GemmDev& g, int row, int col0, EpiPrefetch& pf) {
+  if (epi_res_vec(g, row, col0)) {
+    const uint4* q = reinterpret_cast<const uint4*>(g.residual + static_cast<int64_t>(row) * g.ldr + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pf.res[i] = __ldg(q + i);
+  }
+  if (epi_aux_vec(g, row, col0)) {
+    const uint4* q = reinterpret_cast<const uint4*>(g.aux + static_cast<int64_t>(row) * g.ldaux + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pf.aux[i] = __ldg(q + i);
+  }
+}
+__device__ __forceinline__ void unpack_row32(const uint4 (&q)[4], float (&out)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f0 = unpack_bf16x2(q[i].x), f1 = unpack_bf16x2(q[i].y), f2 = unpack_bf16x2(q[i].z), f3 = unpack_bf16x2(q[i].w);
+    out[8 * i + 0] = f0.x; out[8 * i + 1] = f0.y; out[8 * i + 2] = f1.x; out[8 * i + 3] = f1.y;
+    out[8 * i + 4] = f2.x; out[8 * i + 5] = f2.y; out[8 * i + 6] = f3.x; out[8 * i + 7] = f3.y;
+  }
+}
+
+__device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, int col0, float (&acc)[32], const EpiPrefetch& pf) {
   if (row >= g.m || col0 >= g.n) return;
   const int nvalid = min(32, g.n - col0);
   const bool full = (nvalid == 32);
@@ -176,7 +209,8 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, i
     for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.0f);
   } else if (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) {
     float a[32];
-    load_bf16_row32(g.aux + static_cast<int64_t>(row) * g.ldaux + col0, full && ((g.ldaux & 7) == 0), nvalid, a);
+    if (epi_aux_vec(g, row, col0)) unpack_row32(pf.aux, a);
+    else load_bf16_row32(g.aux + static_cast<int64_t>(row) * g.ldaux + col0, false, nvalid, a);
     if (g.epilogue == JL_EPI_GELU_BWD) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(a[j]);
@@ -188,7 +222,8 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, i
 
   if (g.residual != nullptr) {
     float r[32];
-    load_bf16_row32(g.residual + static_cast<int64_t>(row) * g.ldr + col0, full && ((g.ldr & 7) == 0), nvalid, r);
+    if (epi_res_vec(g, row, col0)) unpack_row32(pf.res, r);
+    else load_bf16_row32(g.residual + static_cast<int64_t>(row) * g.ldr + col0, false, nvalid, r);
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] += r[j];
   }
@@ -334,7 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-    const int half = (warp - 4) >> 2;             // which 32-column chunks (even / odd)
+    const int half = (warp - 4) >> 2;             // which 32-column chunks: c ≡ half (mod 3)
     int it = 0;
     for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
       const int as = it & 1;
@@ -346,10 +381,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32);
         ptx::tmem_ld_32x32(taddr, v);
+        EpiPrefetch pf;
+        if (g.split_k == 1) epi_prefetch(g, row, n0 + c * 32, pf);
         ptx::tmem_ld_wait();
         float acc[32];
 #pragma unroll
@@ -359,7 +396,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (row < g.m && col0 < g.n)
             store_f32_row<32>(g.ws + (static_cast<int64_t>(split) * g.m + row) * g.ldw + col0, col0 + 32 <= g.ldw, g.n - col0, acc);
         } else {
-          gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+          gemm_epilogue_row32(g, row, n0 + c * 32, acc, pf);
         }
       }
       ptx::tc_fence_before();
@@ -522,15 +559,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32);
         ptx::tmem_ld_32x32(taddr, v);
+        EpiPrefetch pf;
+        epi_prefetch(g, row, n0 + c * 32, pf);
         ptx::tmem_ld_wait();
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        gemm_epilogue_row32(g, row, n0 + c * 32, acc);
+        gemm_epilogue_row32(g, row, n0 + c * 32, acc, pf);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -588,7 +627,9 @@ __global__ void gemm_ref_kernel(const GemmRefOperands o, const GemmDev g) {
       }
     }
   }
-  gemm_epilogue_row32(g, row, col0, acc);
+  EpiPrefetch pf;
+  epi_prefetch(g, row, col0, pf);
+  gemm_epilogue_row32(g, row, col0, acc, pf);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -304,11 +304,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _rows2d(x, "x")
     rows, cols = x.shape
     out = torch.empty((cols,), dtype=F32, device=x.device) if out is None else out
-    lib = L.load()
-    nbytes = C.c_size_t(0)
-    L.check(lib.jl_colsum_workspace_bytes(rows, cols, C.byref(nbytes)))
-    partial = torch.empty((nbytes.value // 4,), dtype=F32, device=x.device)
-    L.check(lib.jl_colsum_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, partial.data_ptr(), _stream()))
+    L.check(L.load().jl_colsum_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, None, _stream()))
     return out
 
 
