@@ -60,6 +60,16 @@ __device__ __forceinline__ void tc_store_cols16(uint8_t* tile, int r, int c0, co
 }
 
 __device__ __forceinline__ void tc_store_global_row32(__nv_bfloat16* dst, const float (&v)[32], float s) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[16 * i + 2 * j] * s, v[16 * i + 2 * j + 1] * s);
+      st_global_v8(dst + 16 * i, w);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint4 o;

@@ -77,7 +77,15 @@ __device__ __forceinline__ void load_bf16_row32(const __nv_bfloat16* p, bool vec
 
 template <int COUNT>
 __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* p, bool vec, int nvalid, const float (&v)[COUNT]) {
-  if (vec) {
+  if (vec && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {      // 32-byte sectors written by single requests
+#pragma unroll
+    for (int i = 0; i < COUNT / 16; ++i) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[16 * i + 2 * j], v[16 * i + 2 * j + 1]);
+      st_global_v8(p + 16 * i, w);
+    }
+  } else if (vec) {
     uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
     for (int i = 0; i < COUNT / 8; ++i) {
@@ -97,7 +105,15 @@ __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* p, bool vec, int n
 
 template <int COUNT>
 __device__ __forceinline__ void store_f32_row(float* p, bool vec, int nvalid, const float (&v)[COUNT]) {
-  if (vec) {
+  if (vec && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < COUNT / 8; ++i) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[8 * i + j]);
+      st_global_v8(p + 8 * i, w);
+    }
+  } else if (vec) {
     float4* q = reinterpret_cast<float4*>(p);
 #pragma unroll
     for (int i = 0; i < COUNT / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -114,6 +130,21 @@ struct EpiPrefetch {
   uint4 res[4];
   uint4 aux[4];
 };
+__device__ __forceinline__ void epi_load_row(const __nv_bfloat16* p, uint4 (&dst)[4]) {      // 32 bf16 = 64 B
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    uint32_t w0[8], w1[8];
+    ld_global_nc_v8(p, w0);
+    ld_global_nc_v8(p + 16, w1);
+    dst[0] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    dst[1] = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+    dst[2] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    dst[3] = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(q + i);
+  }
+}
 __device__ __forceinline__ bool epi_res_vec(const GemmDev& g, int row, int col0) {
   return g.residual != nullptr && row < g.m && col0 + 32 <= g.n && (g.ldr & 7) == 0 && g.epilogue != JL_EPI_GLU;
 }
@@ -121,16 +152,8 @@ __device__ __forceinline__ bool epi_aux_vec(const GemmDev& g, int row, int col0)
   return (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) && row < g.m && col0 + 32 <= g.n && (g.ldaux & 7) == 0;
 }
 __device__ __forceinline__ void epi_prefetch(const GemmDev& g, int row, int col0, EpiPrefetch& pf) {
-  if (epi_res_vec(g, row, col0)) {
-    const uint4* q = reinterpret_cast<const uint4*>(g.residual + static_cast<int64_t>(row) * g.ldr + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pf.res[i] = __ldg(q + i);
-  }
-  if (epi_aux_vec(g, row, col0)) {
-    const uint4* q = reinterpret_cast<const uint4*>(g.aux + static_cast<int64_t>(row) * g.ldaux + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pf.aux[i] = __ldg(q + i);
-  }
+  if (epi_res_vec(g, row, col0)) epi_load_row(g.residual + static_cast<int64_t>(row) * g.ldr + col0, pf.res);
+  if (epi_aux_vec(g, row, col0)) epi_load_row(g.aux + static_cast<int64_t>(row) * g.ldaux + col0, pf.aux);
 }
 __device__ __forceinline__ void unpack_row32(const uint4 (&q)[4], float (&out)[32]) {
 #pragma unroll

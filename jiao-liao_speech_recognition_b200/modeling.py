@@ -184,6 +184,31 @@ class _State:
     pass
 
 
+class _SideBranch:
+    """Weight-gradient products do not feed the dX chain, so the backward pass issues them on a second stream: inside
+    the captured CUDA graph they become parallel branches that fill the SMs the (latency-bound) main chain leaves idle.
+    Tensors a branch reads are kept alive until ``join`` so the caching allocator cannot recycle them early."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+        self.side = torch.cuda.Stream() if enabled else None
+        self.keep = []
+
+    def run(self, fn, *tensors) -> None:
+        if not self.enabled:
+            fn()
+            return
+        self.keep.extend(tensors)
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            fn()
+
+    def join(self) -> None:
+        if self.enabled:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.keep.clear()
+
+
 class JLEngine:
     """Walks the module tree and issues the C-ABI calls.  Holds bf16 copies of the weights in the layouts the kernels
     read (q/k/v concatenated; conv weights tap-major with GLU rows interleaved)."""
@@ -198,6 +223,7 @@ class JLEngine:
         self._shadow: Dict[int, Tuple[int, int, torch.Tensor]] = {}
         self._pos: Dict[Tuple[str, int], torch.Tensor] = {}
         self.flat = None   # set by training.FlatAdapterParams
+        self.side_branch = True   # issue weight-gradient products on a second stream (parallel graph branches)
 
     # ------------------------------------------------------------------ weights
     def _backbone_params(self):
@@ -307,34 +333,47 @@ class JLEngine:
             saved = (h, mean, rstd, z, qkv, a, lse) if training else None
         return out, saved
 
-    def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink") -> torch.Tensor:
-        """dy = grad of the adapter output → returns grad of the adapter input; weight grads go to ``g``."""
+    def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink", sb: "_SideBranch") -> torch.Tensor:
+        """dy = grad of the adapter output → returns grad of the adapter input; weight grads go to ``g`` (issued on the
+        side branch ``sb``)."""
         MN = L.JL_LAYOUT_MN
         if ad.kind == "wf":
             h, mean, rstd, z, t1, u, t2, k = saved
-            ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)                 # dyᵀ · t2
-            ops.colsum(dy, out=g.out(ad.up_bias, k))
+
+            def w_up():
+                ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)             # dyᵀ · t2
+                ops.colsum(dy, out=g.out(ad.up_bias, k))
+            sb.run(w_up, dy, t2)
             dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
-            ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32)                  # dt2ᵀ · u
+            sb.run(lambda: ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32), dt2, u)   # dt2ᵀ · u
             dpre = ops.gemm(dt2, self._bf16(ad.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=u)      # (dt2 · B_u) ∘ relu'
-            ops.colsum(dpre, out=g.out(ad.down_bias, k))
-            ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)              # dpreᵀ · t1
+
+            def w_down():
+                ops.colsum(dpre, out=g.out(ad.down_bias, k))
+                ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)          # dpreᵀ · t1
+            sb.run(w_down, dpre, t1)
             dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
-            ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32)                # dt1ᵀ · z
+            sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
             dz = ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN)                                         # dt1 · B_d
         else:
             h, mean, rstd, z, qkv, a, lse = saved
-            ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)             # dyᵀ · a
-            ops.colsum(dy, out=g.out(ad.o_proj.bias))
+
+            def w_o():
+                ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)         # dyᵀ · a
+                ops.colsum(dy, out=g.out(ad.o_proj.bias))
+            sb.run(w_o, dy, a)
             da = ops.gemm(dy, self._bf16(ad.o_proj.weight), b_layout=MN)                                      # dy · W_o
             dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0)
             ws = [ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight]
             bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
-            gw, gb = g.out_cat(ws), g.out_cat(bs)
-            ops.gemm(dqkv, z, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                                # dqkvᵀ · z
-            ops.colsum(dqkv, out=gb)
-            g.scatter_cat(ws, gw)
-            g.scatter_cat(bs, gb)
+
+            def w_qkv():
+                gw, gb = g.out_cat(ws), g.out_cat(bs)
+                ops.gemm(dqkv, z, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                            # dqkvᵀ · z
+                ops.colsum(dqkv, out=gb)
+                g.scatter_cat(ws, gw)
+                g.scatter_cat(bs, gb)
+            sb.run(w_qkv, dqkv, z)
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
         dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True,
                                      dgamma=g.out(ad.norm.weight), dbeta=g.out(ad.norm.bias))
@@ -423,11 +462,16 @@ class JLEngine:
         b, t = st.b, st.t
         fz = self._frozen_pack()
         lengths = st.lengths
+        sb = _SideBranch(enabled=self.side_branch)
+
         # head: logits = h_final · Wᵀ + b
-        ops.gemm(dlogits, st.h_final, a_layout=MN, b_layout=MN, out=g.out(self.lm_head.weight), out_dtype=F32)   # dlogitsᵀ · h_final
-        ops.colsum(dlogits, out=g.out(self.lm_head.bias))
+        def w_head():
+            ops.gemm(dlogits, st.h_final, a_layout=MN, b_layout=MN, out=g.out(self.lm_head.weight), out_dtype=F32)   # dlogitsᵀ · h_final
+            ops.colsum(dlogits, out=g.out(self.lm_head.bias))
+        sb.run(w_head, dlogits, st.h_final)
         l0 = self.lowest_adapter_layer()
         if l0 >= len(self.enc.layers):
+            sb.join()
             return
         dhf = ops.gemm(dlogits, self._bf16(self.lm_head.weight), b_layout=MN)                                   # dlogits · W
         ln = self.enc.layer_norm
@@ -435,7 +479,7 @@ class JLEngine:
         for i in range(len(self.enc.layers) - 1, l0 - 1, -1):
             layer, sv = self.enc.layers[i], st.layers[i]
             if layer.adapter_ffn is not None:
-                dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g)
+                dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g, sb)
                 if i == l0 and layer.adapter_attn is None:
                     break
             # FFN: h2 = h1 + W2 · gelu(W1 · LN2(h1) + b1) + b2
@@ -444,7 +488,7 @@ class JLEngine:
             fl = layer.final_layer_norm
             dh1, _, _ = ops.layernorm_bwd(dx2, sv.h1, fl.weight.detach(), sv.mean2, sv.rstd2, dres=dh)
             if layer.adapter_attn is not None:
-                dh1 = self._adapter_bwd(layer.adapter_attn, sv.ad_attn, dh1, lengths, b, t, g)
+                dh1 = self._adapter_bwd(layer.adapter_attn, sv.ad_attn, dh1, lengths, b, t, g, sb)
                 if i == l0:
                     break
             # attention: h1 = h + Wo · attn(LN1(h) Wqkvᵀ) + bo
@@ -454,6 +498,7 @@ class JLEngine:
             dx1 = ops.gemm(dqkv, fz[f"{i}.wqkv"], b_layout=MN)
             l1 = layer.layer_norm
             dh, _, _ = ops.layernorm_bwd(dx1, sv.h_in, l1.weight.detach(), sv.mean1, sv.rstd1, dres=dh1)
+        sb.join()
 
 
 class GradSink:
