@@ -454,14 +454,20 @@ struct GemmSmem2 {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// PAIRS = 2: a cluster of four CTAs = two MMA pairs that share the same N tile (rows m0 … m0+511).  Each CTA fetches only a
+// quarter of the B tile and TMA-multicasts it to the CTA at the same position of the other pair, so a k-block moves
+// 4·16 KB of A + BN·128 B of B for 512 × BN × 64 MACs (175 FLOP/B at BN = 256 instead of 128).
+template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS>
+__global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
   using L = GemmSmem2<BN, STAGES>;
   constexpr int BNH = BN / 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static_assert(BN == 128 || BN == 192 || BN == 256, "pair tile N must be 128, 192 or 256");
-  static_assert(!B_MN || (BNH % 64) == 0, "MN-major B needs 64-wide swizzle blocks per CTA");
+  constexpr int BQ = BNH / PAIRS;               // B rows (K-major) / columns (MN-major) this CTA fetches itself
+  static_assert(!B_MN || (BQ % 64) == 0, "MN-major B needs 64-wide swizzle blocks per fetched slice");
+  static_assert(PAIRS == 1 || PAIRS == 2, "one or two MMA pairs per cluster");
+  static_assert((BQ * 128) % 1024 == 0, "fetched B slice must keep the 1024-byte swizzle atom alignment");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -475,11 +481,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t crank = ptx::cluster_ctarank();                // rank in the cluster
+  const uint32_t rank = crank & 1u;                             // position in the MMA pair
+  const uint32_t pic = crank >> 1;                              // pair index in the cluster
+  const uint32_t leader_rank = crank & ~1u;
   const bool leader = (rank == 0);
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
-  const int num_tiles = g.num_m_tiles * g.num_n_tiles;          // 256 × BN tiles
+  const int pair = blockIdx.x / (2 * PAIRS);                    // cluster index
+  const int num_pairs = gridDim.x / (2 * PAIRS);
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;          // (256·PAIRS) × BN tiles
   const int num_kb = (g.k + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
@@ -489,7 +498,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar + s, 1);       // leader's: one arrive.expect_tx covering both CTAs' bytes
-      ptx::mbar_init(empty_bar + s, 1);      // each CTA's own: multicast commit from the leader's MMA thread
+      ptx::mbar_init(empty_bar + s, PAIRS);  // each CTA's own: multicast commits from every pair's MMA thread
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar + s, 1);                       // each CTA's own: multicast commit
@@ -512,14 +521,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile / g.num_n_tiles) * 256 + static_cast<int>(rank) * GEMM_BM;
-        const int n0 = (tile % g.num_n_tiles) * BN + static_cast<int>(rank) * BNH;
+        const int m0 = (tile / g.num_n_tiles) * (256 * PAIRS) + static_cast<int>(pic) * 256 + static_cast<int>(rank) * GEMM_BM;
+        const int n0 = (tile % g.num_n_tiles) * BN + static_cast<int>(rank) * BNH + static_cast<int>(pic) * BQ * (PAIRS - 1);
+        const uint16_t bmask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));   // same pair position in both pairs
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
           if (leader) ptx::mbar_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);
-          const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(full_bar + stage), 0);
+          const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(full_bar + stage), leader_rank);
           uint8_t* a_dst = s_a + stage * GEMM_A_BYTES;
-          uint8_t* b_dst = s_b + stage * L::B_BYTES;
+          uint8_t* b_dst = s_b + stage * L::B_BYTES + (PAIRS - 1) * static_cast<int>(pic) * BQ * 128;
           const int k0 = kb * GEMM_BK;
           if (A_MN) {
 #pragma unroll
@@ -527,11 +537,20 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           } else {
             ptx::tma_load_2d_2sm(a_dst, &tma_a, bar, k0, m0);
           }
-          if (B_MN) {
+          if (PAIRS == 1) {
+            if (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BNH / 64; ++i) ptx::tma_load_2d_2sm(b_dst + i * 8192, &tma_b, bar, n0 + 64 * i, k0);
+              for (int i = 0; i < BQ / 64; ++i) ptx::tma_load_2d_2sm(b_dst + i * 8192, &tma_b, bar, n0 + 64 * i, k0);
+            } else {
+              ptx::tma_load_2d_2sm(b_dst, &tma_b, bar, k0, n0);
+            }
           } else {
-            ptx::tma_load_2d_2sm(b_dst, &tma_b, bar, k0, n0);
+            if (B_MN) {
+#pragma unroll
+              for (int i = 0; i < BQ / 64; ++i) ptx::tma_load_2d_2sm_mcast(b_dst + i * 8192, &tma_b, bar, n0 + 64 * i, k0, bmask);
+            } else {
+              ptx::tma_load_2d_2sm_mcast(b_dst, &tma_b, bar, k0, n0, bmask);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -561,22 +580,22 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             const uint64_t db = B_MN ? ptx::make_sw128_desc(b_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
             ptx::umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit_2sm(empty_bar + stage, 0x3);    // both CTAs' smem slots are free once these MMAs have read them
+          ptx::umma_commit_2sm(empty_bar + stage, PAIRS == 1 ? 0x3 : 0xF);   // every CTA that writes into these slots
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit_2sm(tfull_bar + as, 0x3);          // accumulators complete in both CTAs
+        ptx::umma_commit_2sm(tfull_bar + as, static_cast<uint16_t>(0x3u << (2 * pic)));   // accumulators complete in both CTAs of the pair
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 accumulator lanes) =====================
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
-    const uint32_t leader_tempty = ptx::mapa_shared(ptx::smem_u32(tempty_bar), 0);
+    const uint32_t leader_tempty = ptx::mapa_shared(ptx::smem_u32(tempty_bar), leader_rank);
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / g.num_n_tiles) * 256 + static_cast<int>(rank) * GEMM_BM;
+      const int m0 = (tile / g.num_n_tiles) * (256 * PAIRS) + static_cast<int>(pic) * 256 + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (tile % g.num_n_tiles) * BN;
       ptx::mbar_wait(tfull_bar + as, aphase);
       ptx::tc_fence_after();
@@ -809,10 +828,10 @@ static int pick_bn(const jl_gemm_params* p) {
 }
 
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS>
 static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
   using L = GemmSmem2<BN, STAGES>;
-  auto kern = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN, PAIRS>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -827,37 +846,37 @@ static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
   else rc = make_map(&ma, p->a, p->k, p->m, p->lda, GEMM_BM);
   if (rc != JL_OK) return rc;
   if (B_MN) rc = make_map(&mb, p->b, p->n, p->k, p->ldb, 64);
-  else rc = make_map(&mb, p->b, p->k, p->n, p->ldb, BN / 2);
+  else rc = make_map(&mb, p->b, p->k, p->n, p->ldb, BN / 2 / PAIRS);
   if (rc != JL_OK) return rc;
   GemmDev g = to_dev(p, BN);
-  g.num_m_tiles = ceil_div(p->m, 256);
+  g.num_m_tiles = ceil_div(p->m, 256 * PAIRS);
   const int tiles = g.num_m_tiles * g.num_n_tiles;
-  const int pairs_max = num_sms() / 2;
+  const int pairs_max = num_sms() / (2 * PAIRS);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
+  kern<<<2 * PAIRS * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
   JL_CHECK_LAUNCH("gemm_tcgen05_2cta");
   return JL_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int PAIRS>
 static int dispatch_layout_2cta(const jl_gemm_params* p, cudaStream_t s) {
   const bool amn = p->a_layout == JL_LAYOUT_MN, bmn = p->b_layout == JL_LAYOUT_MN;
-  if constexpr ((BN / 2) % 64 == 0) {
-    if (amn && bmn) return launch_gemm_2cta<BN, STAGES, true, true>(p, s);
-    if (bmn) return launch_gemm_2cta<BN, STAGES, false, true>(p, s);
+  if constexpr ((BN / 2 / PAIRS) % 64 == 0) {
+    if (amn && bmn) return launch_gemm_2cta<BN, STAGES, true, true, PAIRS>(p, s);
+    if (bmn) return launch_gemm_2cta<BN, STAGES, false, true, PAIRS>(p, s);
   }
-  if (amn) return launch_gemm_2cta<BN, STAGES, true, false>(p, s);
-  return launch_gemm_2cta<BN, STAGES, false, false>(p, s);
+  if (amn) return launch_gemm_2cta<BN, STAGES, true, false, PAIRS>(p, s);
+  return launch_gemm_2cta<BN, STAGES, false, false, PAIRS>(p, s);
 }
 
-static std::atomic<int> g_gemm_mode{0};   // 0 = auto, 1 = single-CTA kernel only, 2 = CTA-pair kernel wherever it is legal
+static std::atomic<int> g_gemm_mode{0};   // 0 = auto, 1 = single-CTA kernel only, 2 = CTA-pair kernel wherever legal, 3 = + B multicast across two pairs
 
 // N tile of the CTA-pair kernel, or 0 when the product should run on the single-CTA kernel.
 static int pick_bn_2cta(const jl_gemm_params* p) {
   const int mode = g_gemm_mode.load();
   if (mode == 1) return 0;
   if (p->n < 128) return 0;
-  if (mode == 0 && (p->m < 1024 || static_cast<int64_t>(p->m) * p->n < 512 * 1024)) return 0;
+  if ((mode == 0) && (p->m < 1024 || static_cast<int64_t>(p->m) * p->n < 512 * 1024)) return 0;
   int per = 0;
   if (p->workspace != nullptr && pick_split(p, pick_bn(p), &per) > 1) return 0;
   const bool bmn = p->b_layout == JL_LAYOUT_MN;
@@ -878,6 +897,12 @@ static int pick_bn_2cta(const jl_gemm_params* p) {
   return best;
 }
 
+// B multicast across two pairs (clusters of four CTAs): only when requested (mode 3) until validated on hardware.
+static bool use_multicast(const jl_gemm_params* p, int bn) {
+  (void)bn;
+  return g_gemm_mode.load() == 3 && p->m >= 512;
+}
+
 }  // namespace jl
 
 extern "C" {
@@ -888,10 +913,17 @@ int jl_gemm_bf16(const jl_gemm_params* p, void* stream) {
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (jl::pick_bn_2cta(p)) {
-    case 256: return jl::dispatch_layout_2cta<256, 6>(p, s);
-    case 192: return jl::dispatch_layout_2cta<192, 6>(p, s);
-    case 128: return jl::dispatch_layout_2cta<128, 8>(p, s);
+  const int bn2 = jl::pick_bn_2cta(p);
+  if (bn2 != 0 && jl::use_multicast(p, bn2)) {
+    const bool bmn = p->b_layout == JL_LAYOUT_MN;
+    if (bn2 == 256) return jl::dispatch_layout_2cta<256, 6, 2>(p, s);
+    if (bn2 == 192 && !bmn) return jl::dispatch_layout_2cta<192, 6, 2>(p, s);
+    if (bn2 == 128 && !bmn) return jl::dispatch_layout_2cta<128, 8, 2>(p, s);
+  }
+  switch (bn2) {
+    case 256: return jl::dispatch_layout_2cta<256, 6, 1>(p, s);
+    case 192: return jl::dispatch_layout_2cta<192, 6, 1>(p, s);
+    case 128: return jl::dispatch_layout_2cta<128, 8, 1>(p, s);
     default: break;
   }
   switch (jl::pick_bn(p)) {
