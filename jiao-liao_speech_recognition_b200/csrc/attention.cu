@@ -412,13 +412,18 @@ static int attn_check(const void* q, const void* k, const void* v, int64_t ld_qk
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream);   // attention_tc.cu
 int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream);
+extern int g_attn_fwd_ctas;
 static std::atomic<int> g_attn_impl{0};   // 0 = tcgen05 kernels, 1 = mma.sync kernels
 
 }  // namespace jl
 
 extern "C" {
 
-void jl_debug_set_attn_impl(int impl) { jl::g_attn_impl.store(impl); }
+void jl_debug_set_attn_impl(int impl) {
+  // 0 = tcgen05 kernels (forward compiled for 3 CTAs/SM), 1 = mma.sync kernels, 2 = tcgen05 with the 2-CTAs/SM forward
+  jl::g_attn_fwd_ctas = (impl == 2) ? 2 : 3;
+  jl::g_attn_impl.store(impl == 1 ? 1 : 0);
+}
 
 int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream) {
   JL_REQUIRE(p != nullptr, JL_EINVAL, "attn_fwd: null params");

@@ -108,7 +108,8 @@ struct __align__(1024) AttnFwdSmem {
   TcBars bars;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(TC_THREADS, MIN_CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                    const jl_attn_fwd_params p) {
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_OUTER;
@@ -139,16 +140,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     ptx::mbar_init(&B.acc_done, 1);
     ptx::fence_barrier_init();
   }
+  // 128 TMEM columns (64 scores + 64 output) and 65 KB of shared memory per CTA → three CTAs per SM: the score rows are
+  // pulled into registers with a single wait and the buffer is released at once, so S_{j+1} still overlaps softmax_j.
   if (warp == 2) {
-    ptx::tmem_alloc(&B.tmem_slot, 256);
+    ptx::tmem_alloc(&B.tmem_slot, 128);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = B.tmem_slot;
-  const uint32_t t_s[2] = {tmem, tmem + 64};
-  const uint32_t t_o = tmem + 128;
+  const uint32_t t_s[2] = {tmem, tmem};
+  const uint32_t t_o = tmem + 64;
   const int grow = static_cast<int>(row_base);        // row of the utterance's first frame in the [B·T, ld] matrices
 
   if (warp == 0) {
@@ -170,11 +173,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       auto issue_scores = [&](int j) {
         const int st = j & 1;
         ptx::mbar_wait(&B.y_full[st], (j >> 1) & 1);
-        ptx::mbar_wait(&B.s_empty[st], ((j >> 1) & 1) ^ 1u);
+        ptx::mbar_wait(&B.s_empty[0], (j & 1) ^ 1u);                               // scores of block j-1 are in registers
         ptx::tc_fence_after();
         tc_mma_64(t_s[st], q_addr, ptx::smem_u32(s.k[st]), false, false);          // S_j = Q · K_jᵀ
         ptx::umma_commit(&B.y_empty[st]);
-        ptx::umma_commit(&B.s_full[st]);
+        ptx::umma_commit(&B.s_full[0]);
       };
       issue_scores(0);
       for (int j = 0; j < nkb; ++j) {
@@ -193,7 +196,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     float m = -CUDART_INF_F, l = 0.0f;
     for (int j = 0; j < nkb; ++j) {
       const int st = j & 1;
-      ptx::mbar_wait(&B.s_full[st], (j >> 1) & 1);
+      ptx::mbar_wait(&B.s_full[0], j & 1);
       ptx::tc_fence_after();
       const int kbase = j * TC_INNER;
       // the 64 scores of this row: two 32-column TMEM loads, one wait; the score buffer is released right away
@@ -203,7 +206,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&B.s_empty[st]);      // score buffer may be overwritten by block j + 2
+      if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);       // score buffer may be overwritten by block j + 1
       const bool partial = kbase + TC_INNER > len;          // only the last key tile needs the padding mask
       float mx = m;
 #pragma unroll
@@ -270,7 +273,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 256);
+    ptx::tmem_dealloc(tmem, 128);
   }
 }
 
@@ -496,6 +499,8 @@ static int tc_set_smem(K kern, size_t bytes, const char* name) {
   return JL_OK;
 }
 
+int g_attn_fwd_ctas = 3;   // resident CTAs per SM the forward kernel is compiled for (3: 80 registers, 2: 128 registers)
+
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
   const int64_t inner = static_cast<int64_t>(p->heads) * 64;
@@ -509,12 +514,14 @@ int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    rc = tc_set_smem(attn_fwd_tc_kernel, smem, "attn_fwd_tc");
+    rc = tc_set_smem(attn_fwd_tc_kernel<3>, smem, "attn_fwd_tc");
+    if (rc == JL_OK) rc = tc_set_smem(attn_fwd_tc_kernel<2>, smem, "attn_fwd_tc");
     if (rc != JL_OK) return rc;
     configured_dev = dev;
   }
   dim3 grid(ceil_div(p->seq, TC_OUTER), p->heads, p->batch);
-  attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
+  if (g_attn_fwd_ctas == 3) attn_fwd_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
+  else attn_fwd_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
   JL_CHECK_LAUNCH("attn_fwd_tc");
   return JL_OK;
 }
