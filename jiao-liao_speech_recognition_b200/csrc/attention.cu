@@ -420,8 +420,8 @@ static std::atomic<int> g_attn_impl{0};   // 0 = tcgen05 kernels, 1 = mma.sync k
 extern "C" {
 
 void jl_debug_set_attn_impl(int impl) {
-  // 0 = tcgen05 kernels (forward compiled for 3 CTAs/SM), 1 = mma.sync kernels, 2 = tcgen05 with the 2-CTAs/SM forward
-  jl::g_attn_fwd_ctas = (impl == 2) ? 2 : 3;
+  // 0 = tcgen05 kernels (forward compiled for 2 CTAs/SM), 1 = mma.sync kernels, 2 = tcgen05 with the 3-CTAs/SM forward build
+  jl::g_attn_fwd_ctas = (impl == 2) ? 3 : 2;
   jl::g_attn_impl.store(impl == 1 ? 1 : 0);
 }
 

@@ -7,9 +7,11 @@
 //   warp 0      TMA producer — 128B-swizzled [rows × 64] bf16 boxes straight out of the [B·T, ld] q|k|v / dO matrices
 //   warp 1      one thread issues tcgen05.mma (M = 128 rows = the CTA's "outer" tile, N = 64, K = 64), accumulators in TMEM
 //   warp 2      TMEM allocator (256 columns)
-//   warps 4-7   128 threads = 128 TMEM lanes = 128 outer rows: tcgen05.ld the score row, exp2 / mask / scale in
-//               registers, write the bf16 operand tile (P, dS, Pᵀ, dSᵀ) back to shared memory in the K-major
-//               128B-swizzle layout the next MMA reads, tcgen05.st for the online-softmax rescale of O
+//   warps 4-11  two warpgroups × 128 threads: thread (quadrant, lane) of warpgroup g owns columns [32g, 32g+32) of TMEM
+//               lane = outer row: tcgen05.ld its half of the score row, ex2.approx / mask / scale in registers, write
+//               the bf16 operand tile (P, dS, Pᵀ, dSᵀ) back to shared memory in the K-major 128B-swizzle layout the next
+//               MMA reads, tcgen05.st for the online-softmax rescale of O; the two halves of a row exchange their
+//               running max through shared memory (one named barrier per key tile)
 // The same 64-row TMA tile is used as a K-major B operand (scores) and as an MN-major B operand (value / gradient
 // products) — no transposed copies.
 //   forward   outer = 128 queries, inner = 64 keys:  S = Q·Kᵀ → P → O += P·V            (online softmax, O rescaled in TMEM)
@@ -24,7 +26,7 @@
 
 namespace jl {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // 4 service warps (TMA, MMA, TMEM alloc, spare) + 8 softmax warps
 constexpr int TC_OUTER = 128;
 constexpr int TC_INNER = 64;
 constexpr uint32_t TC_T128 = 128 * 128;   // bytes of a [128 × 64] bf16 tile
@@ -32,6 +34,12 @@ constexpr uint32_t TC_T64 = 64 * 128;     // bytes of a [ 64 × 64] bf16 tile
 constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr uint32_t TC_IDESC_KK = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // M128 N64, A,B K-major
 constexpr uint32_t TC_IDESC_KMN = TC_IDESC_KK | (1u << 16);                                                        // B MN-major
+
+__device__ __forceinline__ float tc_exp2(float x) {      // single MUFU.EX2 (flush-to-zero); arguments here are <= 8
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // D[128 × 64] (+)= A[128 × 64] · B, A K-major at a_addr; B = 64-row tile at b_addr read K-major (Bᵀ: rows are N) or
 // MN-major (rows are K).  4 MMAs of K = 16.
@@ -105,6 +113,8 @@ struct __align__(1024) AttnFwdSmem {
   uint8_t k[2][TC_T64];
   uint8_t v[2][TC_T64];
   uint8_t p[TC_T128];
+  float red_max[2][2][TC_OUTER];   // [key tile parity][column half][row]
+  float red_sum[2][TC_OUTER];
   TcBars bars;
 };
 
@@ -134,9 +144,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       ptx::mbar_init(&B.y_full[i], 1);
       ptx::mbar_init(&B.y_empty[i], 2);     // K slot freed by the score MMA commit, V slot by the PV commit
       ptx::mbar_init(&B.s_full[i], 1);
-      ptx::mbar_init(&B.s_empty[i], 4);
+      ptx::mbar_init(&B.s_empty[i], 8);
     }
-    ptx::mbar_init(&B.p_full, 4);
+    ptx::mbar_init(&B.p_full, 8);
     ptx::mbar_init(&B.acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -191,83 +201,91 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
   } else if (warp >= 4) {
     const int r = (warp & 3) * 32 + lane;                  // TMEM lane = query row of the tile
+    const int half = (warp - 4) >> 2;                      // which 32 of the 64 key columns this thread owns
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = p.scale * TC_LOG2E;
-    float m = -CUDART_INF_F, l = 0.0f;
+    float m = -CUDART_INF_F, l = 0.0f;                     // m: reference max of the row (same in both halves), l: partial sum
     for (int j = 0; j < nkb; ++j) {
       const int st = j & 1;
       ptx::mbar_wait(&B.s_full[0], j & 1);
       ptx::tc_fence_after();
-      const int kbase = j * TC_INNER;
-      // the 64 scores of this row: two 32-column TMEM loads, one wait; the score buffer is released right away
-      uint32_t sv[64];
-      ptx::tmem_ld_32x32(t_s[st] + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      ptx::tmem_ld_32x32(t_s[st] + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      const int kbase = j * TC_INNER + half * 32;
+      uint32_t sv[32];
+      ptx::tmem_ld_32x32(t_s[st] + lane_off + half * 32, sv);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);       // score buffer may be overwritten by block j + 1
-      const bool partial = kbase + TC_INNER > len;          // only the last key tile needs the padding mask
-      float mx = m;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        if (partial && kbase + i >= len) sv[i] = 0xff800000u;     // -inf
-        mx = fmaxf(mx, __uint_as_float(sv[i]));
-      }
-      // Lazy rescale: keep the old reference max unless the row max grew by more than 2^8 (exp2 arguments stay <= 8, far
-      // from overflow); O and l are only rescaled then, which removes most TMEM round trips of the online softmax.
-      const bool grow = (mx - m) * sl2 > 8.0f;              // true on the first tile (m = -inf)
-      const float m_new = grow ? mx : m;
-      const float corr = grow ? exp2f((m - m_new) * sl2) : 1.0f;
-      const float mxs = m_new * sl2;
-      float sum = 0.0f;
-      uint32_t packed[32];
+      const bool partial = j * TC_INNER + TC_INNER > len;   // only the last key tile needs the padding mask
+      float mloc = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float a = exp2f(fmaf(__uint_as_float(sv[2 * i]), sl2, -mxs));
-        const float e = exp2f(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mxs));
-        sum += a + e;
+        if (partial && kbase + i >= len) sv[i] = 0xff800000u;     // -inf
+        mloc = fmaxf(mloc, __uint_as_float(sv[i]));
+      }
+      s.red_max[st][half][r] = mloc;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mx = fmaxf(m, fmaxf(mloc, s.red_max[st][half ^ 1][r]));
+      // Lazy rescale: keep the old reference max unless the row max grew by more than 2^8 (exp2 arguments stay <= 8);
+      // O and l are only rescaled then, which removes most TMEM round trips of the online softmax.
+      const bool grow = (mx - m) * sl2 > 8.0f;              // true on the first tile (m = -inf); identical in both halves
+      const float m_new = grow ? mx : m;
+      const float corr = grow ? tc_exp2((m - m_new) * sl2) : 1.0f;
+      const float mxs = m_new * sl2;
+      float sum0 = 0.0f, sum1 = 0.0f;
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = tc_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -mxs));
+        const float e = tc_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mxs));
+        sum0 += a;
+        sum1 += e;
         packed[i] = pack_bf16x2(a, e);
       }
-      l = l * corr + sum;
+      l = l * corr + (sum0 + sum1);
       m = m_new;
       if (j > 0) {
         ptx::mbar_wait(&B.acc_done, (j - 1) & 1);          // PV_{j-1} complete: O may be rescaled, P may be overwritten
         ptx::tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
+          uint32_t ov[32];
+          ptx::tmem_ld_32x32(t_o + lane_off + half * 32, ov);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t ov[32];
-            ptx::tmem_ld_32x32(t_o + lane_off + hh * 32, ov);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-            ptx::tmem_st_32x32(t_o + lane_off + hh * 32, ov);
-          }
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+          ptx::tmem_st_32x32(t_o + lane_off + half * 32, ov);
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
         }
       }
-      tc_store_row(s.p, r, packed);
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t t0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t0[i] = packed[8 * c2 + i];
+        tc_store_cols16(s.p, r, 4 * half + 2 * c2, t0);
+      }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&B.p_full);
     }
     ptx::mbar_wait(&B.acc_done, (nkb - 1) & 1);
     ptx::tc_fence_after();
+    s.red_sum[half][r] = l;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float l_tot = l + s.red_sum[half ^ 1][r];
     const int row = q0 + r;
-    const float inv = (row < len) ? 1.0f / l : 0.0f;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+    const float inv = (row < len) ? 1.0f / l_tot : 0.0f;
+    {
       uint32_t ov[32];
-      ptx::tmem_ld_32x32(t_o + lane_off + hh * 32, ov);
+      ptx::tmem_ld_32x32(t_o + lane_off + half * 32, ov);
       ptx::tmem_ld_wait();
       float of[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
-      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + hh * 32, of, inv);
+      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
     }
-    if (lse && row < p.seq) lse[row] = (row < len) ? m * p.scale + logf(l) : 0.0f;
+    if (lse && half == 0 && row < p.seq) lse[row] = (row < len) ? m * p.scale + logf(l_tot) : 0.0f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -322,9 +340,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
       ptx::mbar_init(&B.y_full[i], 1);
       ptx::mbar_init(&B.y_empty[i], 1);
       ptx::mbar_init(&B.s_full[i], 1);
-      ptx::mbar_init(&B.s_empty[i], 4);
+      ptx::mbar_init(&B.s_empty[i], 8);
     }
-    ptx::mbar_init(&B.p_full, 4);
+    ptx::mbar_init(&B.p_full, 8);
     ptx::mbar_init(&B.acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -385,6 +403,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
   } else if (warp >= 4) {
     const int tid = threadIdx.x - 128;
     const int r = (warp & 3) * 32 + lane;
+    const int hh = (warp - 4) >> 2;                          // which 32 of the 64 inner columns this thread owns
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row = r0 + r;                                  // query (MODE 0) / key (MODE 1) index
     const bool row_ok = row < len;
@@ -408,7 +427,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
         }
         row_lse = lse[row] * TC_LOG2E;
       }
-      if (row < p.seq) delta[row] = row_delta;
+      if (hh == 0 && row < p.seq) delta[row] = row_delta;
     }
     for (int j = 0; j < nib; ++j) {
       const int st = j & 1;
@@ -417,25 +436,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
         if (tid < TC_INNER) {
           const int q = cbase + tid;
           s.col_lse[st][tid] = (q < len) ? lse[q] * TC_LOG2E : 0.0f;
-        } else {
+        } else if (tid < 2 * TC_INNER) {
           const int q = cbase + tid - TC_INNER;
           s.col_delta[st][tid - TC_INNER] = (q < len) ? delta[q] : 0.0f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       ptx::mbar_wait(&B.s_full[0], j & 1);
       ptx::tc_fence_after();
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      {
         uint32_t sv[32], dv[32], pk0[16], pk1[16];
         ptx::tmem_ld_32x32(t_s + lane_off + hh * 32, sv);
         ptx::tmem_ld_32x32(t_dp + lane_off + hh * 32, dv);
         ptx::tmem_ld_wait();
-        if (hh == 1) {                                       // both halves are in registers: release the score buffers
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);
-        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&B.s_empty[0]);     // this warp's share of S / dP is in registers
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float pr[2], ds[2];
@@ -445,14 +461,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
             const bool ok = row_ok && (cbase + c < len);
             const float lse_c = (MODE == 0) ? row_lse : s.col_lse[st][c];
             const float dl_c = (MODE == 0) ? row_delta : s.col_delta[st][c];
-            const float pe = ok ? exp2f(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -lse_c)) : 0.0f;
+            const float pe = ok ? tc_exp2(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -lse_c)) : 0.0f;
             pr[e] = pe;
             ds[e] = pe * (__uint_as_float(dv[2 * i + e]) - dl_c) * p.scale;
           }
           pk0[i] = (MODE == 0) ? pack_bf16x2(ds[0], ds[1]) : pack_bf16x2(pr[0], pr[1]);
           pk1[i] = pack_bf16x2(ds[0], ds[1]);
         }
-        if (hh == 0 && j > 0) ptx::mbar_wait(&B.acc_done, (j - 1) & 1);   // accumulate MMAs of block j-1 have read the operand tiles
+        if (j > 0) ptx::mbar_wait(&B.acc_done, (j - 1) & 1);   // accumulate MMAs of block j-1 have read the operand tiles
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t t0[8], t1[8];
@@ -471,16 +487,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
 #pragma unroll
     for (int a = 0; a < (MODE == 1 ? 2 : 1); ++a) {
       __nv_bfloat16* dst = (a == 0) ? out0 : out1;
+      uint32_t ov[32];
+      ptx::tmem_ld_32x32((a == 0 ? t_acc0 : t_acc1) + lane_off + hh * 32, ov);
+      ptx::tmem_ld_wait();
+      float of[32];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t ov[32];
-        ptx::tmem_ld_32x32((a == 0 ? t_acc0 : t_acc1) + lane_off + hh * 32, ov);
-        ptx::tmem_ld_wait();
-        float of[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
-        if (row < p.seq) tc_store_global_row32(dst + static_cast<int64_t>(row) * p.ld_dqkv + hh * 32, of, 1.0f);
-      }
+      for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
+      if (row < p.seq) tc_store_global_row32(dst + static_cast<int64_t>(row) * p.ld_dqkv + hh * 32, of, 1.0f);
     }
   }
   ptx::tc_fence_before();
@@ -499,7 +512,7 @@ static int tc_set_smem(K kern, size_t bytes, const char* name) {
   return JL_OK;
 }
 
-int g_attn_fwd_ctas = 3;   // resident CTAs per SM the forward kernel is compiled for (3: 80 registers, 2: 128 registers)
+int g_attn_fwd_ctas = 2;   // resident CTAs per SM the forward kernel is compiled for
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;

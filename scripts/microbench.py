@@ -53,7 +53,7 @@ q1 = qkv[:, :64];
 timeit("attn_fwd 1 head", lambda: ops.attn_fwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], lens, 32, 250, 1, 0.125))
 timeit("attn_fwd 12 heads", lambda: ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125))
 L.load().jl_debug_set_attn_impl(2)
-timeit("attn_fwd 12 heads (tc, 2 CTAs/SM build)", lambda: ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125))
+timeit("attn_fwd 12 heads (tc, 3 CTAs/SM build)", lambda: ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125))
 L.load().jl_debug_set_attn_impl(0)
 o12, lse12 = ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125, want_lse=True)
 do12 = torch.randn_like(o12)
