@@ -148,3 +148,62 @@ def test_trainer_step_matches_autograd_path_and_updates_adapters():
     torch.cuda.synchronize()
     assert loss_c < loss_b
     assert tr.launches_per_step > 50
+
+
+def test_large_config_both_adapters_mixed_lengths():
+    """BASELINE.json configs 3 + 4 in miniature: d=1024 / 16 heads / 4096 FFN transformer stack (4 of the 24 layers to keep
+    the CPU oracle quick) with AttAdapter after attention and WFAdapter after the FFN, mixed-length utterances (padded and
+    masked), CTC 'mean' reduction: logits, loss and adapter gradients vs the oracle."""
+    P = pkg()
+    cfg = P.JLConfig.large(num_hidden_layers=4, adapter_attn="att", adapter_ffn="wf", vocab_size=600, ctc_loss_reduction="mean")
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    waves = [synth_wave(16000 * 3 + 123, 21), synth_wave(16000 * 2, 22), synth_wave(9000, 23), synth_wave(16000 * 3 + 123, 24)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens = model.output_lengths(feats["input_features"], feats["attention_mask"]).cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, 24, seed=5)
+    loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    om, w, ocfg = _oracle_setup(model, cfg)
+    for k, v in w.items():
+        v.requires_grad_(om.is_trainable(k))
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, waves, labels)
+    oloss.backward()
+    assert olens.tolist() == lens
+    for i, t in enumerate(lens):
+        assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
+    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    for name, p in model._get_adapters().items():
+        ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
+        err = float((p.grad.float().cpu() - ref).norm())
+        assert err <= 5e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
+
+
+def test_transcriber_matches_module_path_and_oracle_ids():
+    """Inference fast path (CUDA graph: waveform → mel → encoder → greedy ids) == module path; ids bit-exact vs the oracle's
+    greedy decode of the same logits."""
+    from oracle import ctc as oc
+    P = pkg()
+    cfg = _small_cfg(P, adapter_ffn="wf")
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda().eval()
+    n = 20000
+    wave = torch.stack([synth_wave(n, 31), synth_wave(n, 32), synth_wave(n, 33)])
+    ns = torch.tensor([n, 15000, 8000], dtype=I32)
+    tr = P.Transcriber(model, use_cuda_graph=True)
+    for _ in range(2):                                       # second call replays the graph
+        ids, nid = tr(wave.pin_memory(), ns)
+        torch.cuda.synchronize()
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([wave[i, : int(ns[i])].numpy() for i in range(3)], sampling_rate=16000)
+    with torch.no_grad():
+        _, logits = model(feats["input_features"], attention_mask=feats["attention_mask"])
+    lens = model.output_lengths(feats["input_features"], feats["attention_mask"])
+    ref = oc.greedy_decode(logits.float().cpu(), lens.cpu(), cfg.pad_token_id)
+    got = [ids[i, : int(nid[i])].cpu().tolist() for i in range(3)]
+    assert got == ref
