@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus: int, trainable: int = 6234248):
@@ -188,6 +188,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P = importlib.import_module(PKG)
+    if os.environ.get("JL_PDL") == "0":            # tuning aid: plain stream-ordered launches
+        P._lib.load().jl_debug_set_pdl(0)
     cfg = P.JLConfig.base(adapter_ffn="att")
     model = P.JLForCTC(cfg).cuda()
     model.freeze_base_model()
@@ -302,12 +304,31 @@ def run_ours(args):
         "rtf": (t_res / args.steps) / audio_s_per_step, "loss": loss_val, "cuda_graph": not args.eager,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, …) write to fd 1; the contract is ONE JSON line on stdout, so everything else is
+    sent to stderr and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -124,6 +124,7 @@ __device__ __forceinline__ void store_c_tile(__nv_bfloat16* dst, int64_t ld, int
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const jl_attn_fwd_params p) {
+  jl::pdl_prologue();
   __shared__ __align__(128) __nv_bfloat16 s_q[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_k[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_v[ATT_B * ATT_D];
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const jl_attn_fwd
 
 // ------------------------------------------------------------------------------------------------ backward: dQ (+ delta)
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const jl_attn_bwd_params p) {
+  jl::pdl_prologue();
   __shared__ __align__(128) __nv_bfloat16 s_q[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_do[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_k[ATT_B * ATT_D];
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const jl_attn_
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const jl_attn_bwd_params p) {
+  jl::pdl_prologue();
   __shared__ __align__(128) __nv_bfloat16 s_k[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_v[ATT_B * ATT_D];
   __shared__ __align__(128) __nv_bfloat16 s_q[ATT_B * ATT_D];
@@ -434,7 +437,7 @@ int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream) {
   if (rc != JL_OK) return rc;
   if (jl::g_attn_impl.load() == 0) return jl::attn_fwd_tc(p, reinterpret_cast<cudaStream_t>(stream));
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
-  jl::attn_fwd_kernel<<<grid, jl::ATT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  jl::launch(jl::attn_fwd_kernel, grid, jl::ATT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream), *p);
   JL_CHECK_LAUNCH("attn_fwd");
   return JL_OK;
 }
@@ -453,9 +456,9 @@ int jl_attn_bwd(const jl_attn_bwd_params* p, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (jl::g_attn_impl.load() == 0) return jl::attn_bwd_tc(p, s);
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
-  jl::attn_bwd_dq_kernel<<<grid, jl::ATT_THREADS, 0, s>>>(*p);
+  jl::launch(jl::attn_bwd_dq_kernel, grid, jl::ATT_THREADS, 0, s, *p);
   JL_CHECK_LAUNCH("attn_bwd_dq");
-  jl::attn_bwd_dkv_kernel<<<grid, jl::ATT_THREADS, 0, s>>>(*p);
+  jl::launch(jl::attn_bwd_dkv_kernel, grid, jl::ATT_THREADS, 0, s, *p);
   JL_CHECK_LAUNCH("attn_bwd_dkv");
   return JL_OK;
 }

@@ -122,6 +122,7 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                    const jl_attn_fwd_params p) {
+  jl::pdl_prologue();   // `lengths` may be produced by the preceding kernel: wait before the first global read
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_OUTER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
@@ -315,6 +316,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constant__ CUtensorMap tx2, const __grid_constant__ CUtensorMap ty1,
                    const __grid_constant__ CUtensorMap ty2, const jl_attn_bwd_params p) {
+  jl::pdl_prologue();   // `lengths` may be produced by the preceding kernel: wait before the first global read
   const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * TC_OUTER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
@@ -533,8 +535,8 @@ int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
     configured_dev = dev;
   }
   dim3 grid(ceil_div(p->seq, TC_OUTER), p->heads, p->batch);
-  if (g_attn_fwd_ctas == 3) attn_fwd_tc_kernel<3><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
-  else attn_fwd_tc_kernel<2><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, *p);
+  if (g_attn_fwd_ctas == 3) jl::launch(attn_fwd_tc_kernel<3>, grid, TC_THREADS, smem, stream, tq, tk, tv, *p);
+  else jl::launch(attn_fwd_tc_kernel<2>, grid, TC_THREADS, smem, stream, tq, tk, tv, *p);
   JL_CHECK_LAUNCH("attn_fwd_tc");
   return JL_OK;
 }
@@ -563,9 +565,9 @@ int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream) {
     configured_dev = dev;
   }
   dim3 grid(ceil_div(p->seq, TC_OUTER), p->heads, p->batch);
-  attn_bwd_tc_kernel<0><<<grid, TC_THREADS, smem0, stream>>>(q128, do128, k64, v64, *p);
+  jl::launch(attn_bwd_tc_kernel<0>, grid, TC_THREADS, smem0, stream, q128, do128, k64, v64, *p);
   JL_CHECK_LAUNCH("attn_bwd_tc_dq");
-  attn_bwd_tc_kernel<1><<<grid, TC_THREADS, smem1, stream>>>(k128, v128, q64, do64, *p);
+  jl::launch(attn_bwd_tc_kernel<1>, grid, TC_THREADS, smem1, stream, k128, v128, q64, do64, *p);
   JL_CHECK_LAUNCH("attn_bwd_tc_dkv");
   return JL_OK;
 }

@@ -41,6 +41,8 @@ int check_device() {
   return JL_OK;
 }
 
+int g_use_pdl = 1;
+
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -86,4 +88,5 @@ int jl_version(void) { return JL_VERSION; }
 const char* jl_last_error(void) { return jl::g_err; }
 int64_t jl_launch_count(void) { return jl::g_launches.load(); }
 void jl_launch_count_reset(void) { jl::g_launches.store(0); }
+void jl_debug_set_pdl(int on) { jl::g_use_pdl = on ? 1 : 0; }
 }

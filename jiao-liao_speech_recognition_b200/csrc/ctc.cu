@@ -50,6 +50,7 @@ static CtcWs carve_ws(const jl_ctc_params* p, void* ws, size_t* total) {
 
 __global__ void ctc_prep_kernel(const int32_t* __restrict__ labels, int smax, int vocab, int32_t* __restrict__ out_labels,
                                 int32_t* __restrict__ tlen) {
+  jl::pdl_prologue();
   const int b = blockIdx.x;
   if (threadIdx.x != 0) return;
   int n = 0;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) ctc_row_stats_kernel(const T* __restrict_
                                                             const int32_t* __restrict__ lengths, float* __restrict__ lse_out,
                                                             int32_t* __restrict__ frame_ids, const int32_t* __restrict__ labels, int smax,
                                                             const int32_t* __restrict__ tlen, int blank, float* __restrict__ lpx) {
+  jl::pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(2 * CTC_LATTICE_HALF) ctc_lattice_kernel(const
                                                                            const int32_t* __restrict__ lengths, int seq, int blank,
                                                                            const float* __restrict__ lpx, float* __restrict__ alpha,
                                                                            float* __restrict__ beta, float* __restrict__ nll) {
+  jl::pdl_prologue();
   extern __shared__ float lat_smem[];
   const int b = blockIdx.x;
   const int S = tlen[b];
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
                                                                    const float* __restrict__ lse_all, const float* __restrict__ lpx,
                                                                    const float* __restrict__ alpha, const float* __restrict__ beta,
                                                                    const float* __restrict__ nll, int reduction, int zero_infinity) {
+  jl::pdl_prologue();
   extern __shared__ float grad_smem[];
   const int row = blockIdx.x;
   const int b = row / seq, t = row - b * seq;
@@ -343,6 +347,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
 
 __global__ void ctc_reduce_kernel(float* __restrict__ nll, const int32_t* __restrict__ tlen, int batch, int reduction, int zero_infinity,
                                   float* __restrict__ loss) {
+  jl::pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float acc = 0.0f;
   for (int b = 0; b < batch; ++b) {
@@ -359,6 +364,7 @@ __global__ void ctc_reduce_kernel(float* __restrict__ nll, const int32_t* __rest
 // Greedy: collapse consecutive repeats of the per-frame argmax, drop blank, compact.  One warp per utterance.
 __global__ void ctc_collapse_kernel(const int32_t* __restrict__ frame_ids, const int32_t* __restrict__ lengths, int seq, int blank,
                                     int32_t* __restrict__ out_ids, int32_t* __restrict__ out_lengths) {
+  jl::pdl_prologue();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int T = min(lengths[b], seq);
   const int32_t* ids = frame_ids + static_cast<int64_t>(b) * seq;
@@ -417,17 +423,17 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
   const int rows = p->batch * p->seq;
 
   if (p->max_label_len > 0) {
-    jl::ctc_prep_kernel<<<p->batch, 32, 0, s>>>(p->labels, smax, p->vocab, w.labels, w.tlen);
+    jl::launch(jl::ctc_prep_kernel, p->batch, 32, 0, s, p->labels, smax, p->vocab, w.labels, w.tlen);
     JL_CHECK_LAUNCH("ctc_prep");
   } else {
     cudaMemsetAsync(w.tlen, 0, sizeof(int32_t) * p->batch, s);
   }
   const int sblocks = jl::ceil_div(rows, 8);
   if (p->logits_dtype == JL_DT_F32)
-    jl::ctc_row_stats_kernel<float><<<sblocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
+    jl::launch(jl::ctc_row_stats_kernel<float>, sblocks, 256, 0, s, reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
                                                            p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen, p->blank, w.lpx);
   else
-    jl::ctc_row_stats_kernel<__nv_bfloat16><<<sblocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
+    jl::launch(jl::ctc_row_stats_kernel<__nv_bfloat16>, sblocks, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
                                                                    p->vocab, p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen,
                                                                    p->blank, w.lpx);
   JL_CHECK_LAUNCH("ctc_row_stats");
@@ -436,13 +442,13 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
     cudaError_t e = cudaFuncSetAttribute(jl::ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lat_smem));
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "ctc: cannot reserve lattice shared memory: %s", cudaGetErrorString(e));
   }
-  jl::ctc_lattice_kernel<<<p->batch, 2 * jl::CTC_LATTICE_HALF, lat_smem, s>>>(w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
+  jl::launch(jl::ctc_lattice_kernel, p->batch, 2 * jl::CTC_LATTICE_HALF, lat_smem, s, w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
                                                                             w.alpha, w.beta, p->nll);
   JL_CHECK_LAUNCH("ctc_lattice");
   if (p->grad != nullptr) {
     const size_t gsm = static_cast<size_t>(Lmax + 32) * sizeof(float);
 #define JL_CTC_GRAD(TL, TGR)                                                                                                           \
-  jl::ctc_grad_kernel<TL, TGR><<<rows, jl::CTC_GRAD_THREADS, gsm, s>>>(reinterpret_cast<const TL*>(p->logits), p->ld_logits,              \
+  jl::launch(jl::ctc_grad_kernel<TL, TGR>, rows, jl::CTC_GRAD_THREADS, gsm, s, reinterpret_cast<const TL*>(p->logits), p->ld_logits,              \
                                                                         reinterpret_cast<TGR*>(p->grad), p->ld_grad, p->seq, p->vocab,   \
                                                                         p->batch, p->input_lengths, w.labels, smax, w.tlen, p->blank,    \
                                                                         w.lse, w.lpx, w.alpha, w.beta, p->nll, p->reduction,             \
@@ -454,7 +460,7 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
 #undef JL_CTC_GRAD
     JL_CHECK_LAUNCH("ctc_grad");
   }
-  jl::ctc_reduce_kernel<<<1, 32, 0, s>>>(p->nll, w.tlen, p->batch, p->reduction, p->zero_infinity, p->loss);
+  jl::launch(jl::ctc_reduce_kernel, 1, 32, 0, s, p->nll, w.tlen, p->batch, p->reduction, p->zero_infinity, p->loss);
   JL_CHECK_LAUNCH("ctc_reduce");
   return JL_OK;
 }
@@ -470,14 +476,14 @@ int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream) {
   const int rows = p->batch * p->seq;
   const int sblocks = jl::ceil_div(rows, 8);
   if (p->logits_dtype == JL_DT_F32)
-    jl::ctc_row_stats_kernel<float><<<sblocks, 256, 0, s>>>(reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
+    jl::launch(jl::ctc_row_stats_kernel<float>, sblocks, 256, 0, s, reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
                                                            p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr, p->blank, nullptr);
   else
-    jl::ctc_row_stats_kernel<__nv_bfloat16><<<sblocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
+    jl::launch(jl::ctc_row_stats_kernel<__nv_bfloat16>, sblocks, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
                                                                    p->vocab, p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr,
                                                                    p->blank, nullptr);
   JL_CHECK_LAUNCH("ctc_argmax");
-  jl::ctc_collapse_kernel<<<p->batch, 32, 0, s>>>(p->frame_ids, p->input_lengths, p->seq, p->blank, p->out_ids, p->out_lengths);
+  jl::launch(jl::ctc_collapse_kernel, p->batch, 32, 0, s, p->frame_ids, p->input_lengths, p->seq, p->blank, p->out_ids, p->out_lengths);
   JL_CHECK_LAUNCH("ctc_collapse");
   return JL_OK;
 }

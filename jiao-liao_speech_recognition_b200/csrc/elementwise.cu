@@ -9,6 +9,7 @@ namespace jl {
 
 // out[(b, t), tap * c + ch] = x[b, 2 t - 2 + tap, ch]   (zero outside [0, t_in))
 __global__ void im2col_k5s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int batch, int t_in, int c8, int t_out) {
+  jl::pdl_prologue();
   const int64_t total = static_cast<int64_t>(batch) * t_out * 5 * c8;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % c8);
@@ -27,6 +28,7 @@ __global__ void im2col_k5s2_kernel(const uint4* __restrict__ x, uint4* __restric
 // h[b,t,:] = h[b,t,:] * scale + pos[t + 2, :]  for t < len_b;  0 for t >= len_b
 __global__ void embed_positions_kernel(__nv_bfloat16* __restrict__ h, float scale, const float* __restrict__ pos,
                                        const int32_t* __restrict__ lengths, int batch, int seq, int d) {
+  jl::pdl_prologue();
   const int d8 = d >> 3;
   const int64_t total = static_cast<int64_t>(batch) * seq * d8;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -52,6 +54,7 @@ __global__ void embed_positions_kernel(__nv_bfloat16* __restrict__ h, float scal
 
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out, int64_t ld_out,
                                       int rows, int cols) {
+  jl::pdl_prologue();
   __shared__ __nv_bfloat16 tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -69,6 +72,7 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
 // loads (thread t takes rows t, t + 256, …), then the 256 partials are combined by a fixed-order shared-memory tree —
 // deterministic, no atomics, no second kernel.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+  jl::pdl_prologue();
   __shared__ float s_acc[256][9];
   const int col = blockIdx.x * 8;
   const int tid = threadIdx.x;
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 }
 
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  jl::pdl_prologue();
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -133,6 +138,7 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloa
 }
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, int64_t n) {
+  jl::pdl_prologue();
   const int64_t n8 = n >> 3;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -158,6 +164,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 
 // torch.optim.AdamW single-tensor update order: decay, moments, bias corrections, addcdiv.
 __global__ void adamw_kernel(const jl_adamw_params p, float bc1, float bc2_sqrt) {
+  jl::pdl_prologue();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const float step_size = p.lr / bc1;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
@@ -196,7 +203,7 @@ int jl_im2col_k5s2(const void* x, void* out, int32_t batch, int32_t t_in, int32_
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   const int64_t total = static_cast<int64_t>(batch) * t_out * 5 * (c / 8);
-  jl::im2col_k5s2_kernel<<<jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  jl::launch(jl::im2col_k5s2_kernel, jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), batch, t_in, c / 8, t_out);
   JL_CHECK_LAUNCH("im2col_k5s2");
   return JL_OK;
@@ -211,7 +218,7 @@ int jl_embed_positions(void* h, float scale, const float* pos_table, const int32
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   const int64_t total = static_cast<int64_t>(batch) * seq * (d / 8);
-  jl::embed_positions_kernel<<<jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  jl::launch(jl::embed_positions_kernel, jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<__nv_bfloat16*>(h), scale, pos_table, lengths, batch, seq, d);
   JL_CHECK_LAUNCH("embed_positions");
   return JL_OK;
@@ -223,7 +230,7 @@ int jl_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, 
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   dim3 grid(jl::ceil_div(cols, 32), jl::ceil_div(rows, 32));
-  jl::transpose_bf16_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  jl::launch(jl::transpose_bf16_kernel, grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(in), ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
   JL_CHECK_LAUNCH("transpose_bf16");
   return JL_OK;
@@ -241,7 +248,7 @@ int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t
   JL_REQUIRE(rows > 0 && cols > 0 && ldx >= cols, JL_EINVAL, "colsum: bad dims");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::colsum_kernel<<<jl::ceil_div(cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows,
+  jl::launch(jl::colsum_kernel, jl::ceil_div(cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows,
                                                                                              cols, out);
   JL_CHECK_LAUNCH("colsum");
   return JL_OK;
@@ -251,7 +258,7 @@ int jl_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   JL_REQUIRE(in && out && n > 0, JL_EINVAL, "cast: bad argument");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::cast_f32_to_bf16_kernel<<<jl::grid_for(n / 4 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  jl::launch(jl::cast_f32_to_bf16_kernel, jl::grid_for(n / 4 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       in, reinterpret_cast<__nv_bfloat16*>(out), n);
   JL_CHECK_LAUNCH("cast_f32_to_bf16");
   return JL_OK;
@@ -261,7 +268,7 @@ int jl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream
   JL_REQUIRE(a && b && out && n > 0, JL_EINVAL, "add: bad argument");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::add_bf16_kernel<<<jl::grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  jl::launch(jl::add_bf16_kernel, jl::grid_for(n / 8 + 1, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<__nv_bfloat16*>(out), n);
   JL_CHECK_LAUNCH("add_bf16");
   return JL_OK;
@@ -274,7 +281,7 @@ int jl_adamw_bucket(const jl_adamw_params* p, void* stream) {
   if (rc != JL_OK) return rc;
   const float bc1 = 1.0f - powf(p->beta1, static_cast<float>(p->step));
   const float bc2_sqrt = sqrtf(1.0f - powf(p->beta2, static_cast<float>(p->step)));
-  jl::adamw_kernel<<<jl::grid_for(p->n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, bc1, bc2_sqrt);
+  jl::launch(jl::adamw_kernel, jl::grid_for(p->n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), *p, bc1, bc2_sqrt);
   JL_CHECK_LAUNCH("adamw_bucket");
   return JL_OK;
 }

@@ -278,6 +278,7 @@ struct GemmSmem {
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+  jl::pdl_launch_dependents();
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32, 256]");
@@ -321,6 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  jl::pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -460,6 +462,7 @@ struct GemmSmem2 {
 template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS>
 __global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+  jl::pdl_launch_dependents();
   using L = GemmSmem2<BN, STAGES>;
   constexpr int BNH = BN / 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -514,6 +517,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  jl::pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -630,6 +634,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 // C = alpha * Σ_s ws[s]  (fixed order → deterministic), fp32 or bf16 out.
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int64_t ldw, int splits, int m, int n, float alpha, void* __restrict__ c,
                                      int64_t ldc, int out_dtype) {
+  jl::pdl_prologue();
   const int64_t total = static_cast<int64_t>(m) * n;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / n), col = static_cast<int>(i - static_cast<int64_t>(r) * n);
@@ -650,6 +655,7 @@ struct GemmRefOperands {
 };
 
 __global__ void gemm_ref_kernel(const GemmRefOperands o, const GemmDev g) {
+  jl::pdl_prologue();
   const int chunks = (g.n + 31) / 32;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(g.m) * chunks) return;
@@ -783,13 +789,13 @@ static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
   }
   const int units = g.num_m_tiles * g.num_n_tiles * g.split_k;
   const int grid = units < num_sms() ? units : num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
+  jl::launch(kern, grid, GEMM_THREADS, L::TOTAL, stream, ma, mb, g);
   JL_CHECK_LAUNCH("gemm_tcgen05");
   if (g.split_k > 1) {
     const int64_t total = static_cast<int64_t>(p->m) * p->n;
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g.ws, g.ldw, g.split_k, p->m, p->n, p->alpha, p->c, p->ldc, p->out_dtype);
+    jl::launch(splitk_reduce_kernel, blocks, 256, 0, stream, g.ws, g.ldw, g.split_k, p->m, p->n, p->alpha, p->c, p->ldc, p->out_dtype);
     JL_CHECK_LAUNCH("gemm_splitk_reduce");
   }
   return JL_OK;
@@ -853,7 +859,7 @@ static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
   const int tiles = g.num_m_tiles * g.num_n_tiles;
   const int pairs_max = num_sms() / (2 * PAIRS);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  kern<<<2 * PAIRS * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ma, mb, g);
+  jl::launch(kern, 2 * PAIRS * pairs, GEMM_THREADS, L::TOTAL, stream, ma, mb, g);
   JL_CHECK_LAUNCH("gemm_tcgen05_2cta");
   return JL_OK;
 }
@@ -956,7 +962,7 @@ int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {
   const int64_t total = static_cast<int64_t>(p->m) * ((p->n + 31) / 32);
   const int threads = 128;
   const int64_t blocks = (total + threads - 1) / threads;
-  jl::gemm_ref_kernel<<<static_cast<unsigned>(blocks), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(o, g);
+  jl::launch(jl::gemm_ref_kernel, static_cast<unsigned>(blocks), threads, 0, reinterpret_cast<cudaStream_t>(stream), o, g);
   JL_CHECK_LAUNCH("gemm_ref");
   return JL_OK;
 }

@@ -45,6 +45,7 @@ __device__ __forceinline__ void ln_store8_bf16(__nv_bfloat16* p, const float (&v
 
 template <int NCH>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_layernorm_fwd_params p) {
+  jl::pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_laye
 // doubles the resident warps of this HBM-bound kernel.
 template <int NCH, bool WGRAD>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_layernorm_bwd_params p) {
+  jl::pdl_prologue();
   __shared__ float s_red[WGRAD ? NCH * 256 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = p.d >> 3;
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
 // strided subset of the partial rows (coalesced 128 B reads), then the 8 groups are combined in fixed order.
 __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  jl::pdl_prologue();
   __shared__ float s_g[8][33], s_b[8][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -221,9 +224,9 @@ int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = jl::ceil_div(p->rows, jl::LN_WARPS);
   switch (jl::ln_pick(p->d)) {
-    case 3: jl::layernorm_fwd_kernel<3><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
-    case 4: jl::layernorm_fwd_kernel<4><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
-    default: jl::layernorm_fwd_kernel<8><<<blocks, jl::LN_THREADS, 0, s>>>(*p); break;
+    case 3: jl::launch(jl::layernorm_fwd_kernel<3>, blocks, jl::LN_THREADS, 0, s, *p); break;
+    case 4: jl::launch(jl::layernorm_fwd_kernel<4>, blocks, jl::LN_THREADS, 0, s, *p); break;
+    default: jl::launch(jl::layernorm_fwd_kernel<8>, blocks, jl::LN_THREADS, 0, s, *p); break;
   }
   JL_CHECK_LAUNCH("layernorm_fwd");
   return JL_OK;
@@ -249,21 +252,21 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
   const bool wg = p->dgamma != nullptr;
   switch (jl::ln_pick(p->d)) {
     case 3:
-      if (wg) jl::layernorm_bwd_kernel<3, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
-      else jl::layernorm_bwd_kernel<3, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      if (wg) jl::launch(jl::layernorm_bwd_kernel<3, true>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<3, false>, blocks, jl::LN_THREADS, 0, s, *p);
       break;
     case 4:
-      if (wg) jl::layernorm_bwd_kernel<4, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
-      else jl::layernorm_bwd_kernel<4, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      if (wg) jl::launch(jl::layernorm_bwd_kernel<4, true>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<4, false>, blocks, jl::LN_THREADS, 0, s, *p);
       break;
     default:
-      if (wg) jl::layernorm_bwd_kernel<8, true><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
-      else jl::layernorm_bwd_kernel<8, false><<<blocks, jl::LN_THREADS, 0, s>>>(*p);
+      if (wg) jl::launch(jl::layernorm_bwd_kernel<8, true>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<8, false>, blocks, jl::LN_THREADS, 0, s, *p);
       break;
   }
   JL_CHECK_LAUNCH("layernorm_bwd");
   if (p->dgamma != nullptr) {
-    jl::layernorm_bwd_reduce_kernel<<<jl::ceil_div(p->d, 32), 256, 0, s>>>(p->partial, blocks, p->d, p->dgamma, p->dbeta);
+    jl::launch(jl::layernorm_bwd_reduce_kernel, jl::ceil_div(p->d, 32), 256, 0, s, p->partial, blocks, p->d, p->dgamma, p->dbeta);
     JL_CHECK_LAUNCH("layernorm_bwd_reduce");
   }
   return JL_OK;

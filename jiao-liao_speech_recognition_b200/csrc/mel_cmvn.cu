@@ -72,6 +72,7 @@ __device__ __forceinline__ void fft256_pass(const float2* __restrict__ src, floa
 }
 
 __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmvn_params p, float* __restrict__ partials, int nblk) {
+  jl::pdl_prologue();
   extern __shared__ __align__(16) uint8_t mel_smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(mel_smem_raw);
 
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
 }
 
 __global__ void __launch_bounds__(MEL_THREADS) cmvn_kernel(const jl_mel_cmvn_params p, const float* __restrict__ partials, int nblk) {
+  jl::pdl_prologue();
   __shared__ float s_mean[JL_MEL_BINS];
   __shared__ float s_std[JL_MEL_BINS];
   const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
@@ -278,10 +280,10 @@ int jl_mel_cmvn_fwd(const jl_mel_cmvn_params* p, void* workspace, void* stream) 
     configured_dev = dev;
   }
   dim3 grid(nblk, p->batch);
-  jl::mel_fbank_kernel<<<grid, jl::MEL_THREADS, sizeof(jl::MelSmem), s>>>(*p, p->apply_cmvn ? reinterpret_cast<float*>(workspace) : nullptr, nblk);
+  jl::launch(jl::mel_fbank_kernel, grid, jl::MEL_THREADS, sizeof(jl::MelSmem), s, *p, p->apply_cmvn ? reinterpret_cast<float*>(workspace) : nullptr, nblk);
   JL_CHECK_LAUNCH("mel_fbank");
   if (p->apply_cmvn) {
-    jl::cmvn_kernel<<<grid, jl::MEL_THREADS, 0, s>>>(*p, reinterpret_cast<const float*>(workspace), nblk);
+    jl::launch(jl::cmvn_kernel, grid, jl::MEL_THREADS, 0, s, *p, reinterpret_cast<const float*>(workspace), nblk);
     JL_CHECK_LAUNCH("cmvn");
   }
   return JL_OK;
