@@ -234,7 +234,7 @@ typedef struct {
 } jl_adamw_params;
 int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
 
-/* test / tuning hook: 1 (default) = launch every kernel with programmatic dependent launch, 0 = plain stream order */
+/* test / tuning hook: 1 = launch every kernel with programmatic dependent launch, 0 (default) = plain stream order */
 void jl_debug_set_pdl(int on);
 
 /* test / tuning hook: attention implementation — 0 = tcgen05 kernels (TMEM scores, TMA operands), 1 = mma.sync

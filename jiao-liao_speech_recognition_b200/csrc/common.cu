@@ -41,7 +41,7 @@ int check_device() {
   return JL_OK;
 }
 
-int g_use_pdl = 1;
+int g_use_pdl = 0;   // measured on B200 (profiles/): PDL edges made the 383-kernel step 4.8 % slower (7.89 vs 7.53 ms) — early CTAs of kernel N+1 sit on SM resources kernel N still needs — so plain stream order is the default
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
