@@ -143,6 +143,9 @@ typedef struct {
 } jl_layernorm_bwd_params;
 int jl_layernorm_bwd_workspace_bytes(const jl_layernorm_bwd_params* p, size_t* out);
 int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream);
+/* only dγ / dβ (uses dy, x, mean, rstd, dgamma, dbeta, rows, d of the struct): one launch, deterministic; lets the caller run
+ * the dx part (jl_layernorm_bwd with dgamma = NULL) on the critical path and the weight gradients on a side stream */
+int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Self-attention softmax(Q K^T * scale + keymask) V per (utterance, head), head_dim 64.

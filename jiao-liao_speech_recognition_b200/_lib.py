@@ -94,6 +94,7 @@ SYMBOLS = {
     "jl_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), vp]),
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
+    "jl_layernorm_wgrad": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),
     "jl_attn_bwd": (C.c_int, [C.POINTER(AttnBwdParams), vp]),
     "jl_ctc_workspace_bytes": (C.c_int, [C.POINTER(CtcParams), C.POINTER(C.c_size_t)]),

@@ -139,6 +139,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   TcBars& B = s.bars;
   const int nkb = (len + TC_INNER - 1) / TC_INNER;
 
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tq);
+    ptx::prefetch_tensormap(&tk);
+    ptx::prefetch_tensormap(&tv);
+  }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(&B.x_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -336,6 +341,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
   TcBars& B = s.bars;
   const int nib = (len + TC_INNER - 1) / TC_INNER;
 
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tx1);
+    ptx::prefetch_tensormap(&tx2);
+    ptx::prefetch_tensormap(&ty1);
+    ptx::prefetch_tensormap(&ty2);
+  }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(&B.x_full, 1);
     for (int i = 0; i < 2; ++i) {

@@ -201,6 +201,48 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(const float* 
   }
 }
 
+// dγ = Σ_rows dy ∘ x̂, dβ = Σ_rows dy in ONE launch (CTA = 8 adjacent columns, 256 threads walk the rows with 16-byte loads,
+// fixed-order shared-memory tree): lets the dX part of an adapter norm's backward use the lean kernel on the critical path
+// while this runs on the weight-gradient branch.
+__global__ void __launch_bounds__(256) layernorm_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x,
+                                                              int64_t ldx, const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
+                                                              int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  jl::pdl_prologue();
+  __shared__ float s_g[256][9], s_b[256][9];
+  const int col = blockIdx.x * 8, tid = threadIdx.x;
+  float g[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { g[j] = 0.0f; b[j] = 0.0f; }
+  for (int r = tid; r < rows; r += 256) {
+    const uint4 vy = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + col));
+    const uint4 vx = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wx[4] = {vx.x, vx.y, vx.z, vx.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
+      g[2 * q] = fmaf(fy.x, (fx.x - mu) * rs, g[2 * q]);
+      g[2 * q + 1] = fmaf(fy.y, (fx.y - mu) * rs, g[2 * q + 1]);
+      b[2 * q] += fy.x;
+      b[2 * q + 1] += fy.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_g[tid][j] = g[j]; s_b[tid][j] = b[j]; }
+  __syncthreads();
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    if (tid < stride) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s_g[tid][j] += s_g[tid + stride][j]; s_b[tid][j] += s_b[tid + stride][j]; }
+    }
+    __syncthreads();
+  }
+  if (tid < 8 && col + tid < d) {
+    dgamma[col + tid] = s_g[0][tid];
+    if (dbeta != nullptr) dbeta[col + tid] = s_b[0][tid];
+  }
+}
+
 static int ln_bwd_blocks(int rows) {
   int blocks = ceil_div(rows, LN_WARPS);
   return blocks < 296 ? blocks : 296;   // 2 CTAs per SM on 148 SMs
@@ -229,6 +271,19 @@ int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
     default: jl::launch(jl::layernorm_fwd_kernel<8>, blocks, jl::LN_THREADS, 0, s, *p); break;
   }
   JL_CHECK_LAUNCH("layernorm_fwd");
+  return JL_OK;
+}
+
+int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream) {
+  JL_REQUIRE(p && p->dy && p->x && p->mean && p->rstd && p->dgamma, JL_EINVAL, "layernorm_wgrad: null pointer");
+  JL_REQUIRE(p->rows > 0 && p->d > 0 && (p->d & 7) == 0, JL_EINVAL, "layernorm_wgrad: d must be a positive multiple of 8");
+  JL_REQUIRE((p->ldx & 7) == 0 && (p->lddy & 7) == 0, JL_EINVAL, "layernorm_wgrad: row strides must be multiples of 8");
+  JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->dy)) & 15) == 0, JL_EINVAL, "layernorm_wgrad: pointers must be 16-byte aligned");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::layernorm_wgrad_kernel, p->d / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(p->dy),
+             p->lddy, reinterpret_cast<const __nv_bfloat16*>(p->x), p->ldx, p->mean, p->rstd, p->rows, p->d, p->dgamma, p->dbeta);
+  JL_CHECK_LAUNCH("layernorm_wgrad");
   return JL_OK;
 }
 

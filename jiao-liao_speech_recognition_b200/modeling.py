@@ -390,8 +390,8 @@ class JLEngine:
                 g.scatter_cat(bs, gb)
             sb.run(w_qkv, dqkv, z)
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
-        dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True,
-                                     dgamma=g.out(ad.norm.weight), dbeta=g.out(ad.norm.bias))
+        sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
+        dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy)
         return dh
 
     # ------------------------------------------------------------------ forward

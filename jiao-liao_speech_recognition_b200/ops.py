@@ -175,6 +175,19 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
     return dx, dgamma, dbeta
 
 
+def layernorm_wgrad(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, dgamma: torch.Tensor,
+                    dbeta: Optional[torch.Tensor] = None) -> None:
+    """dγ = Σ dy ∘ x̂ and dβ = Σ dy (one launch)."""
+    for t, nm in ((dy, "dy"), (x, "x")):
+        _need(t, BF16, nm)
+        _rows2d(t, nm)
+    rows, d = x.shape
+    p = L.LayerNormBwdParams(dy=dy.data_ptr(), lddy=dy.stride(0), x=x.data_ptr(), ldx=x.stride(0), gamma=None, mean=mean.data_ptr(),
+                             rstd=rstd.data_ptr(), dres=None, lddres=0, dx=None, lddx=0, dgamma=dgamma.data_ptr(), dbeta=_ptr(dbeta),
+                             partial=None, rows=rows, d=d)
+    L.check(L.load().jl_layernorm_wgrad(C.byref(p), _stream()))
+
+
 # ----------------------------------------------------------------------------------------------- attention
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int, heads: int,
              scale: float, want_lse: bool = False):

@@ -39,6 +39,9 @@ def test_layernorm_fwd_bwd(rows, d):
     assert rel_err(dx.float(), xr.grad + dres.float()) < 8e-3
     assert rel_err(dgamma, gr.grad) < 2e-3
     assert rel_err(dbeta, br.grad) < 2e-3
+    dg2, db2 = torch.empty_like(dgamma), torch.empty_like(dbeta)
+    ops.layernorm_wgrad(dy, x, mean, rstd, dg2, db2)                 # stand-alone dγ / dβ kernel (side-branch path)
+    assert rel_err(dg2, gr.grad) < 2e-3 and rel_err(db2, br.grad) < 2e-3
     dx2, _, _ = ops.layernorm_bwd(dy, x, gamma, mean, rstd)          # frozen norm: dx only
     assert rel_err(dx2.float(), xr.grad) < 8e-3
     torch.cuda.synchronize()
