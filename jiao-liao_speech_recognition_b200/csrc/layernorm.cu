@@ -43,50 +43,73 @@ __device__ __forceinline__ void ln_store8_bf16(__nv_bfloat16* p, const float (&v
   *reinterpret_cast<uint4*>(p) = o;
 }
 
+__device__ __forceinline__ void ln_unpack8(const uint4& v, float (&o)[8]) {
+  const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+  o[0] = f0.x; o[1] = f0.y; o[2] = f1.x; o[3] = f1.y; o[4] = f2.x; o[5] = f2.y; o[6] = f3.x; o[7] = f3.y;
+}
+
+// A warp owns LN_ROWS consecutive rows and requests all of them before it reduces the first one, so 12 (d = 768) 16-byte
+// loads per lane are in flight instead of 3 — the kernel is a pure stream and lives on memory-level parallelism.
+constexpr int LN_ROWS = 4;
 template <int NCH>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_layernorm_fwd_params p) {
   jl::pdl_prologue();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int row0 = (blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_ROWS;
+  if (row0 >= p.rows) return;
   const int nchunks = p.d >> 3;
-  const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<int64_t>(row) * p.ldx;
-  float x[NCH][8];
-  ln_load_row<NCH>(xr, nchunks, lane, x);
-  float sum = 0.0f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sum += x[c][j];
   const float inv_d = 1.0f / static_cast<float>(p.d);
-  const float mean = warp_sum(sum) * inv_d;
-  float sq = 0.0f;
+  uint4 raw[LN_ROWS][NCH];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
-    if (c * 32 + lane < nchunks) {
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const __nv_bfloat16* xr = reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<int64_t>(min(row0 + r, p.rows - 1)) * p.ldx;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = x[c][j] - mean;
-        sq = fmaf(d, d, sq);
-      }
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = c * 32 + lane;
+      raw[r][c] = (ch < nchunks) ? __ldg(reinterpret_cast<const uint4*>(xr) + ch) : make_uint4(0u, 0u, 0u, 0u);
     }
-  const float var = warp_sum(sq) * inv_d;
-  const float rstd = 1.0f / sqrtf(var + p.eps);
-  if (lane == 0) {
-    if (p.mean != nullptr) p.mean[row] = mean;
-    if (p.rstd != nullptr) p.rstd[row] = rstd;
   }
-  __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(row) * p.ldy;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int ch = c * 32 + lane;
-    if (ch < nchunks) {
-      float g[8], b[8], o[8];
-      ln_load8_f32(p.gamma + ch * 8, g);
-      ln_load8_f32(p.beta + ch * 8, b);
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const int row = row0 + r;
+    if (row >= p.rows) break;
+    float x[NCH][8];
+    float sum = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, g[j], b[j]);
-      ln_store8_bf16(yr + ch * 8, o);
+    for (int c = 0; c < NCH; ++c) {
+      ln_unpack8(raw[r][c], x[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += x[c][j];
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (c * 32 + lane < nchunks) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = x[c][j] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    const float var = warp_sum(sq) * inv_d;
+    const float rstd = 1.0f / sqrtf(var + p.eps);
+    if (lane == 0) {
+      if (p.mean != nullptr) p.mean[row] = mean;
+      if (p.rstd != nullptr) p.rstd[row] = rstd;
+    }
+    __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + static_cast<int64_t>(row) * p.ldy;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = c * 32 + lane;
+      if (ch < nchunks) {
+        float g[8], b[8], o[8];
+        ln_load8_f32(p.gamma + ch * 8, g);
+        ln_load8_f32(p.beta + ch * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, g[j], b[j]);
+        ln_store8_bf16(yr + ch * 8, o);
+      }
     }
   }
 }
@@ -108,46 +131,64 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[c][j] = 0.0f; db[c][j] = 0.0f; }
 
-  for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
-    float x[NCH][8], dy[NCH][8];
-    ln_load_row<NCH>(reinterpret_cast<const __nv_bfloat16*>(p.x) + static_cast<int64_t>(row) * p.ldx, nchunks, lane, x);
-    ln_load_row<NCH>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + static_cast<int64_t>(row) * p.lddy, nchunks, lane, dy);
-    const float mean = __ldg(p.mean + row), rstd = __ldg(p.rstd + row);
-    float s1 = 0.0f, s2 = 0.0f;
+  constexpr int RB = WGRAD ? 1 : 2;       // rows per warp-iteration (the lean dx-only variant keeps two rows in flight)
+  for (int row0 = (blockIdx.x * LN_WARPS + warp) * RB; row0 < p.rows; row0 += gridDim.x * LN_WARPS * RB) {
+    uint4 rx[RB][NCH], rdy[RB][NCH], rdr[RB][NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ch = c * 32 + lane;
-      if (ch < nchunks) {
-        float g[8];
-        ln_load8_f32(p.gamma + ch * 8, g);
+    for (int r = 0; r < RB; ++r) {
+      const int64_t rr = min(row0 + r, p.rows - 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (x[c][j] - mean) * rstd;
-          if constexpr (WGRAD) { dg[c][j] = fmaf(dy[c][j], xh, dg[c][j]); db[c][j] += dy[c][j]; }
-          const float gy = dy[c][j] * g[j];
-          x[c][j] = xh;
-          dy[c][j] = gy;
-          s1 += gy;
-          s2 = fmaf(gy, xh, s2);
-        }
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = c * 32 + lane;
+        const bool ok = ch < nchunks;
+        rx[r][c] = ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + rr * p.ldx) + ch) : make_uint4(0u, 0u, 0u, 0u);
+        rdy[r][c] = ok ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + rr * p.lddy) + ch) : make_uint4(0u, 0u, 0u, 0u);
+        rdr[r][c] = (ok && p.dres != nullptr) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dres) + rr * p.lddres) + ch)
+                                             : make_uint4(0u, 0u, 0u, 0u);
       }
     }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
-    __nv_bfloat16* dxr = reinterpret_cast<__nv_bfloat16*>(p.dx) + static_cast<int64_t>(row) * p.lddx;
-    const __nv_bfloat16* drr = p.dres ? reinterpret_cast<const __nv_bfloat16*>(p.dres) + static_cast<int64_t>(row) * p.lddres : nullptr;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ch = c * 32 + lane;
-      if (ch < nchunks) {
-        float o[8];
+    for (int r = 0; r < RB; ++r) {
+      const int row = row0 + r;
+      if (row >= p.rows) break;
+      float x[NCH][8], dy[NCH][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dy[c][j] - c1 - x[c][j] * c2);
-        if (drr != nullptr) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(drr) + ch);
-          const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
-          o[0] += f0.x; o[1] += f0.y; o[2] += f1.x; o[3] += f1.y; o[4] += f2.x; o[5] += f2.y; o[6] += f3.x; o[7] += f3.y;
+      for (int c = 0; c < NCH; ++c) {
+        ln_unpack8(rx[r][c], x[c]);
+        ln_unpack8(rdy[r][c], dy[c]);
+      }
+      const float mean = __ldg(p.mean + row), rstd = __ldg(p.rstd + row);
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = c * 32 + lane;
+        if (ch < nchunks) {
+          float g[8];
+          ln_load8_f32(p.gamma + ch * 8, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (x[c][j] - mean) * rstd;
+            if constexpr (WGRAD) { dg[c][j] = fmaf(dy[c][j], xh, dg[c][j]); db[c][j] += dy[c][j]; }
+            const float gy = dy[c][j] * g[j];
+            x[c][j] = xh;
+            dy[c][j] = gy;
+            s1 += gy;
+            s2 = fmaf(gy, xh, s2);
+          }
         }
-        ln_store8_bf16(dxr + ch * 8, o);
+      }
+      const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+      __nv_bfloat16* dxr = reinterpret_cast<__nv_bfloat16*>(p.dx) + static_cast<int64_t>(row) * p.lddx;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = c * 32 + lane;
+        if (ch < nchunks) {
+          float o[8], dr[8];
+          ln_unpack8(rdr[r][c], dr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rstd * (dy[c][j] - c1 - x[c][j] * c2) + dr[j];
+          ln_store8_bf16(dxr + ch * 8, o);
+        }
       }
     }
   }
@@ -213,18 +254,29 @@ __global__ void __launch_bounds__(256) layernorm_wgrad_kernel(const __nv_bfloat1
   float g[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { g[j] = 0.0f; b[j] = 0.0f; }
-  for (int r = tid; r < rows; r += 256) {
-    const uint4 vy = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + col));
-    const uint4 vx = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
-    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    const uint32_t wy[4] = {vy.x, vy.y, vy.z, vy.w}, wx[4] = {vx.x, vx.y, vx.z, vx.w};
+  for (int r0 = tid; r0 < rows; r0 += 1024) {
+    uint4 vy[4], vx[4];
+    float mu[4], rs[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
-      g[2 * q] = fmaf(fy.x, (fx.x - mu) * rs, g[2 * q]);
-      g[2 * q + 1] = fmaf(fy.y, (fx.y - mu) * rs, g[2 * q + 1]);
-      b[2 * q] += fy.x;
-      b[2 * q + 1] += fy.y;
+    for (int u = 0; u < 4; ++u) {                 // four independent rows in flight per thread
+      const int r = min(r0 + 256 * u, rows - 1);
+      vy[u] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + col));
+      vx[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
+      mu[u] = __ldg(mean + r);
+      rs[u] = __ldg(rstd + r);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + 256 * u >= rows) break;
+      const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w}, wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
+        g[2 * q] = fmaf(fy.x, (fx.x - mu[u]) * rs[u], g[2 * q]);
+        g[2 * q + 1] = fmaf(fy.y, (fx.y - mu[u]) * rs[u], g[2 * q + 1]);
+        b[2 * q] += fy.x;
+        b[2 * q + 1] += fy.y;
+      }
     }
   }
 #pragma unroll
@@ -264,7 +316,7 @@ int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int blocks = jl::ceil_div(p->rows, jl::LN_WARPS);
+  const int blocks = jl::ceil_div(p->rows, jl::LN_WARPS * jl::LN_ROWS);
   switch (jl::ln_pick(p->d)) {
     case 3: jl::launch(jl::layernorm_fwd_kernel<3>, blocks, jl::LN_THREADS, 0, s, *p); break;
     case 4: jl::launch(jl::layernorm_fwd_kernel<4>, blocks, jl::LN_THREADS, 0, s, *p); break;
@@ -303,7 +355,7 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, jl::LN_WARPS);
+  const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, jl::LN_WARPS * 2);
   const bool wg = p->dgamma != nullptr;
   switch (jl::ln_pick(p->d)) {
     case 3:
