@@ -250,8 +250,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_gemm = g0.elapsed_time(g1) / 1e3 / reps
     achieved = flops / t_gemm / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1f_gemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes"]
+        traffic_note = (f"ncu dram read+write of one launch of the shape with the largest share of the step {tj['shape_mnk']}: "
+                        f"{tj['dram_bytes'] / 1e6:.1f} MB vs {tj['algorithmic_bytes'] / 1e6:.1f} MB algorithmic ({tj['source']})")
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel / gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (the {len(trace)} GEMM launches of one step are timed back to back)",
                 "launches_per_step": len(trace), "algorithmic_tflop_per_step": flops / 1e12, "gemm_ms_per_step": 1e3 * t_gemm,
                 "share_of_step": t_gemm / (t_res / args.steps)}
