@@ -148,6 +148,31 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream);
 int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a6: WFAdapter forward in one kernel — LayerNorm + factorised down / up projections + bias / ReLU + residual.
+ *   out = h + (relu((LN(h) B_d^T) A_d^T + c_d) B_u^T) A_u^T + c_u            (/root/reference/README.md:1;
+ * bottleneck-adapter analogue SP/transformers/models/wav2vec2/modeling_wav2vec2.py:931-953, hook :647-648).
+ * The LayerNorm is folded into the first projection, so the caller passes  bd_scaled = bf16(B_d * gamma)  [r, d],
+ * s[j] = sum_k bd_scaled[j, k]  and  t[j] = sum_k B_d[j, k] * beta[k];  the rank dimension of A_d and A_u is zero-padded to 64.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* h; int64_t ldh;       /* bf16 [rows, d] */
+  void* out; int64_t ldo;           /* bf16 [rows, d] */
+  const void* bd_scaled;            /* bf16 [r, d] */
+  const float* s; const float* t;   /* fp32 [r] */
+  const void* ad_pad;               /* bf16 [b, 64]   (A_d [b, r], zero padded) */
+  const float* c_d;                 /* fp32 [b] */
+  const void* bu;                   /* bf16 [r, b] */
+  const void* au_pad;               /* bf16 [d, 64]   (A_u [d, r], zero padded) */
+  const float* c_u;                 /* fp32 [d] */
+  const int32_t* row_lengths;       /* optional: rows t >= length of their utterance are written as 0 */
+  int32_t rows_per_seq;
+  float* mean; float* rstd;         /* optional fp32 [rows] LayerNorm statistics out */
+  int32_t rows, d, r, b;
+  float eps;
+} jl_wfadapter_fwd_params;
+int jl_wfadapter_fwd(const jl_wfadapter_fwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-attention softmax(Q K^T * scale + keymask) V per (utterance, head), head_dim 64.
  * Replaces the eager math at SP/transformers/models/wav2vec2/modeling_wav2vec2.py:438-463
  * (never materialises the [B,H,T,T] scores); also the AttAdapter attention (heads = 1).

@@ -48,6 +48,12 @@ class LayerNormBwdParams(C.Structure):
                 ("partial", vp), ("rows", i32), ("d", i32)]
 
 
+class WFAdapterFwdParams(C.Structure):
+    _fields_ = [("h", vp), ("ldh", i64), ("out", vp), ("ldo", i64), ("bd_scaled", vp), ("s", vp), ("t", vp), ("ad_pad", vp),
+                ("c_d", vp), ("bu", vp), ("au_pad", vp), ("c_u", vp), ("row_lengths", vp), ("rows_per_seq", i32),
+                ("mean", vp), ("rstd", vp), ("rows", i32), ("d", i32), ("r", i32), ("b", i32), ("eps", f32)]
+
+
 class AttnFwdParams(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("ld_qkv", i64), ("o", vp), ("ld_o", i64), ("lse", vp),
                 ("lengths", vp), ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32)]
@@ -95,6 +101,7 @@ SYMBOLS = {
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_layernorm_wgrad": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
+    "jl_wfadapter_fwd": (C.c_int, [C.POINTER(WFAdapterFwdParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),
     "jl_attn_bwd": (C.c_int, [C.POINTER(AttnBwdParams), vp]),
     "jl_ctc_workspace_bytes": (C.c_int, [C.POINTER(CtcParams), C.POINTER(C.c_size_t)]),

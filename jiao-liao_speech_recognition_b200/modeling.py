@@ -224,6 +224,7 @@ class JLEngine:
         self._pos: Dict[Tuple[str, int], torch.Tensor] = {}
         self.flat = None   # set by training.FlatAdapterParams
         self.side_branch = True   # issue weight-gradient products on a second stream (parallel graph branches)
+        self.fused_wf = True      # inference: WFAdapter as one kernel (jl_wfadapter_fwd)
 
     # ------------------------------------------------------------------ weights
     def _backbone_params(self):
@@ -308,6 +309,33 @@ class JLEngine:
         with torch.no_grad():
             return torch.cat([p.detach() for p in params], 0).contiguous()
 
+    def _wf_fusable(self, ad) -> bool:
+        return (ad.hidden_size % 128 == 0 and ad.rank % 16 == 0 and 16 <= ad.rank <= 64 and ad.bottleneck % 64 == 0
+                and 64 <= ad.bottleneck <= 256)
+
+    def _wf_pack(self, ad, k: int) -> dict:
+        """Factors of dialect ``k`` in the layouts the fused kernel reads: B_d ⊙ γ (LayerNorm folded into the first
+        projection) with its row sums s and the β term t, rank dimension of A_d / A_u zero-padded to 64."""
+        ps = [ad.norm.weight, ad.norm.bias, ad.down_B, ad.down_A, ad.down_bias, ad.up_B, ad.up_A, ad.up_bias]
+        ver = tuple((q.data_ptr(), q._version) for q in ps) + (k,)
+        key = ("wf", id(ad), k)
+        ent = self._shadow.get(key)
+        if ent is not None and ent[0] == ver:
+            return ent[2]
+        with torch.no_grad():
+            gamma, beta = ad.norm.weight.detach().float(), ad.norm.bias.detach().float()
+            bd = (ad.down_B.detach()[k].float() * gamma[None, :]).to(BF16).contiguous()
+            r, b, d = ad.rank, ad.bottleneck, ad.hidden_size
+            adp = torch.zeros((b, 64), dtype=BF16, device=bd.device)
+            adp[:, :r] = ad.down_A.detach()[k].to(BF16)
+            aup = torch.zeros((d, 64), dtype=BF16, device=bd.device)
+            aup[:, :r] = ad.up_A.detach()[k].to(BF16)
+            pack = {"bd": bd, "s": bd.float().sum(1).contiguous(), "t": (ad.down_B.detach()[k].float() @ beta).contiguous(),
+                    "ad": adp, "c_d": ad.down_bias.detach()[k].float().contiguous(), "bu": ad.up_B.detach()[k].to(BF16).contiguous(),
+                    "au": aup, "c_u": ad.up_bias.detach()[k].float().contiguous(), "r": r, "b": b}
+        self._shadow[key] = (ver, None, pack)
+        return pack
+
     def pos_table(self, device, rows: int) -> torch.Tensor:
         key = (str(device), self.cfg.hidden_size)
         tab = self._pos.get(key)
@@ -330,6 +358,12 @@ class JLEngine:
     def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect: int, zero_rows: bool):
         """Returns (out, saved).  out = h + adapter(h); padded rows zeroed when ``zero_rows`` (end of a layer)."""
         eps = ad.norm.eps
+        if ad.kind == "wf" and not training and self.fused_wf and self._wf_fusable(ad):
+            # inference: the whole adapter is one kernel (LN folded into the first projection); training keeps the composed
+            # path because the backward needs every intermediate
+            out, _, _ = ops.wfadapter_fwd(h, self._wf_pack(ad, dialect), eps, row_lengths=lengths if zero_rows else None,
+                                          rows_per_seq=t if zero_rows else 0)
+            return out, None
         z, mean, rstd = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), eps, save_stats=training)
         rl = dict(row_lengths=lengths, rows_per_seq=t) if zero_rows else {}
         if ad.kind == "wf":

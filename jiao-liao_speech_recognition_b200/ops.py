@@ -188,6 +188,25 @@ def layernorm_wgrad(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd:
     L.check(L.load().jl_layernorm_wgrad(C.byref(p), _stream()))
 
 
+# ----------------------------------------------------------------------------------------------- fused WFAdapter
+def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0,
+                  save_stats: bool = False):
+    """out = h + WFAdapter(h) in one kernel.  ``pack`` holds the kernel-layout factors (see modeling.JLEngine._wf_pack)."""
+    _need(h, BF16, "h")
+    _rows2d(h, "h")
+    rows, d = h.shape
+    out = torch.empty((rows, d), dtype=BF16, device=h.device)
+    mean = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
+    rstd = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
+    p = L.WFAdapterFwdParams(h=h.data_ptr(), ldh=h.stride(0), out=out.data_ptr(), ldo=out.stride(0), bd_scaled=pack["bd"].data_ptr(),
+                             s=pack["s"].data_ptr(), t=pack["t"].data_ptr(), ad_pad=pack["ad"].data_ptr(), c_d=pack["c_d"].data_ptr(),
+                             bu=pack["bu"].data_ptr(), au_pad=pack["au"].data_ptr(), c_u=pack["c_u"].data_ptr(),
+                             row_lengths=_ptr(row_lengths), rows_per_seq=rows_per_seq, mean=_ptr(mean), rstd=_ptr(rstd), rows=rows, d=d,
+                             r=pack["r"], b=pack["b"], eps=eps)
+    L.check(L.load().jl_wfadapter_fwd(C.byref(p), _stream()))
+    return out, mean, rstd
+
+
 # ----------------------------------------------------------------------------------------------- attention
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int, heads: int,
              scale: float, want_lse: bool = False):

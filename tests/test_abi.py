@@ -31,6 +31,7 @@ STRUCTS = {
     "jl_layernorm_fwd_params": "LayerNormFwdParams",
     "jl_layernorm_bwd_params": "LayerNormBwdParams",
     "jl_attn_fwd_params": "AttnFwdParams",
+    "jl_wfadapter_fwd_params": "WFAdapterFwdParams",
     "jl_attn_bwd_params": "AttnBwdParams",
     "jl_ctc_params": "CtcParams",
     "jl_ctc_greedy_params": "CtcGreedyParams",

@@ -239,3 +239,47 @@ def test_im2col_embed_transpose_colsum_cast_add_adamw():
     torch.cuda.synchronize()
     assert rel_err(p, ref_p.detach()) < 1e-5
     assert torch.equal(shadow, p.to(BF16))
+
+
+# --------------------------------------------------------------------------------------------- fused WFAdapter
+@pytest.mark.parametrize("d,b,r,rows,seq,lens", [(768, 256, 32, 1000, 250, [250, 100, 250, 7]), (1024, 256, 32, 300, 150, [150, 149]),
+                                                   (128, 64, 16, 77, 77, [50]), (256, 128, 64, 520, 130, [130, 0, 1, 99])])
+def test_wfadapter_fused_forward_matches_oracle(d, b, r, rows, seq, lens):
+    """One-kernel WFAdapter (LN folded into the first projection) vs the oracle's wf_adapter on the same bf16 factors."""
+    from oracle import encoder as oe
+    P = pkg()
+    ops, md = P.ops, P.modeling
+    torch.manual_seed(0)
+    ad = md.WFAdapter(d, b, r, num_dialects=2)
+    with torch.no_grad():
+        ad.norm.weight.copy_(1.0 + 0.1 * torch.randn(d))
+        ad.norm.bias.copy_(0.1 * torch.randn(d))
+        ad.down_bias.copy_(0.05 * torch.randn(2, b))
+        ad.up_bias.copy_(0.05 * torch.randn(2, d))
+        for q in ad.parameters():
+            q.copy_(q.to(BF16).float())
+    ad = ad.cuda()
+
+    class _Enc:                       # minimal stand-in so that JLEngine can be used for its packing helper
+        pass
+    eng = md.JLEngine.__new__(md.JLEngine)
+    eng._shadow = {}
+    g = _g(9)
+    h = (torch.randn(rows, d, device="cuda", generator=g) * 1.5 + 0.2).to(BF16)
+    lengths = torch.tensor(lens, dtype=I32, device="cuda")
+    for k in (0, 1):
+        pack = eng._wf_pack(ad, k)
+        out, mean, rstd = ops.wfadapter_fwd(h, pack, ad.norm.eps, row_lengths=lengths, rows_per_seq=seq, save_stats=True)
+        torch.cuda.synchronize()
+        w = {"a.norm.weight": ad.norm.weight.detach().cpu(), "a.norm.bias": ad.norm.bias.detach().cpu()}
+        for nm in ("down_B", "down_A", "down_bias", "up_B", "up_A", "up_bias"):
+            w["a." + nm] = getattr(ad, nm).detach().cpu()
+        ref = oe.wf_adapter(w, "a", h.float().cpu(), dialect=k)
+        t = torch.arange(rows) % seq
+        valid = t < torch.tensor(lens)[torch.arange(rows) // seq]
+        ref = ref * valid[:, None]
+        assert rel_err(out.float(), ref) < 1e-2, (k, rel_err(out.float(), ref))
+        assert float(out.float().cpu()[~valid].abs().max() if (~valid).any() else 0.0) == 0.0
+        hm = h.float().cpu()
+        assert rel_err(mean, hm.mean(-1)) < 1e-3
+        assert rel_err(rstd, 1.0 / torch.sqrt(hm.var(-1, unbiased=False) + ad.norm.eps)) < 1e-3
