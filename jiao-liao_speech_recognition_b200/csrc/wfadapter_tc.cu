@@ -11,8 +11,9 @@
 //
 // One CTA = 128 rows (TMEM lanes).  warp 0: TMA producer; warp 1: tcgen05.mma issuer; warp 2: TMEM allocator;
 // warps 4-7: row statistics, the epilogue of every stage (TMEM → registers → bf16 operand tile of the next MMA in the
-// K-major 128B-swizzle layout), and the final + bias + residual store (256-bit accesses).
-//   G1  acc1[128, r]   = h[128, d] · B_d'ᵀ            12 × 64-wide k-chunks, 2-stage TMA ring
+// K-major 128B-swizzle layout); warps 4-11: the final + bias + residual store (256-bit accesses, the residual segment of
+// the next column group is prefetched while the current one is written).
+//   G1  acc1[128, r]   = h[128, d] · B_d'ᵀ            12 × 64-wide k-chunks, 4-stage TMA ring
 //   G2  acc2[128, b]   = t1[128, 64] · A_dᵀ            rank padded to 64 with zeros (host-side packing)
 //   G3  acc3[128, r]   = u[128, b] · B_uᵀ
 //   G4  acc4[128, 128] = t2[128, 64] · A_u,chunkᵀ      d / 128 chunks, accumulators double-buffered against the store
@@ -24,17 +25,18 @@
 
 namespace jl {
 
-constexpr int WF_THREADS = 256;
+constexpr int WF_THREADS = 384;   // 4 service warps + 4 row warps (statistics, stage epilogues) + 4 more for the output stage
+constexpr int WF_STAGES = 4;
 constexpr uint32_t WF_T128 = 128 * 128;   // bytes of a [128 × 64] bf16 tile
 
 struct __align__(1024) WfSmem {
-  uint8_t hs[2][WF_T128];        // h k-chunks (G1), later the A_u chunks (G4)
-  uint8_t bds[2][64 * 128];      // B_d' k-chunks [r ≤ 64 rows × 64]
-  uint8_t t[WF_T128];            // t1 / t2 operand tile [128 × 64], columns ≥ r are zero
-  uint8_t ad[256 * 128];         // A_d padded [b ≤ 256 rows × 64]
-  uint8_t u[4][WF_T128];         // u operand tiles [128 × 64] × b/64
-  uint8_t bu[4][64 * 128];       // B_u k-chunks [r rows × 64] × b/64
-  uint64_t full[2], empty[2];    // G1 ring
+  uint8_t hs[WF_STAGES][WF_T128];   // h k-chunks (G1 ring); the same 64 KB hold the u operand tiles [128 × 64] × b/64 afterwards
+  uint8_t bds[WF_STAGES][64 * 128]; // B_d' k-chunks [r ≤ 64 rows × 64]
+  uint8_t t[WF_T128];               // t1 / t2 operand tile [128 × 64], columns ≥ r are zero
+  uint8_t ad[256 * 128];            // A_d padded [b ≤ 256 rows × 64]; after G2 the two A_u chunk stages [128 × 64]
+  uint8_t bu[4][64 * 128];          // B_u k-chunks [r rows × 64] × b/64
+  uint64_t full[WF_STAGES], empty[WF_STAGES];    // G1 ring
+  uint64_t ad_free;              // G2 has consumed A_d: its shared memory may take A_u chunks
   uint64_t w_full;               // A_d, B_u resident
   uint64_t acc_full;             // G1 / G2 / G3 accumulators complete (one completion each)
   uint64_t op_full;              // operand tile written by the 4 row warps (one completion per stage)
@@ -79,13 +81,16 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
     ptx::prefetch_tensormap(&t_au);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < WF_STAGES; ++i) {
       ptx::mbar_init(&s.full[i], 1);
       ptx::mbar_init(&s.empty[i], 5);          // MMA commit + the 4 row warps (statistics pass)
+    }
+    ptx::mbar_init(&s.ad_free, 1);
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s.au_full[i], 1);
       ptx::mbar_init(&s.au_empty[i], 1);
       ptx::mbar_init(&s.acc4_full[i], 1);
-      ptx::mbar_init(&s.acc4_empty[i], 4);
+      ptx::mbar_init(&s.acc4_empty[i], 8);
     }
     ptx::mbar_init(&s.w_full, 1);
     ptx::mbar_init(&s.acc_full, 1);
@@ -113,23 +118,19 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
       for (int c = 0; c < nu; ++c) ptx::tma_load_2d(s.bu[c], &t_bu, &s.w_full, c * 64, 0);
       // G1 ring
       for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc & 1;
-        ptx::mbar_wait(&s.empty[st], ((kc >> 1) & 1) ^ 1u);
+        const int st = kc % WF_STAGES;
+        ptx::mbar_wait(&s.empty[st], ((kc / WF_STAGES) & 1) ^ 1u);
         ptx::mbar_expect_tx(&s.full[st], static_cast<uint32_t>(WF_T128 + p.r * 128));
         ptx::tma_load_2d(s.hs[st], &t_h, &s.full[st], kc * 64, m0);
         ptx::tma_load_2d(s.bds[st], &t_bd, &s.full[st], kc * 64, 0);
       }
-      // G4: A_u chunks reuse the h stages once the last two h chunks have been consumed
+      // G4: A_u chunks stream through the A_d region once G2 has read it
+      ptx::mbar_wait(&s.ad_free, 0);
       for (int c = 0; c < nc4; ++c) {
         const int st = c & 1;
-        if (c < 2) {
-          const int last = (nk - 1 - ((nk - 1 - st) & 1));          // last k-chunk that used stage st
-          ptx::mbar_wait(&s.empty[st], (last >> 1) & 1);
-        } else {
-          ptx::mbar_wait(&s.au_empty[st], ((c >> 1) & 1) ^ 1u);
-        }
+        ptx::mbar_wait(&s.au_empty[st], ((c >> 1) & 1) ^ 1u);
         ptx::mbar_expect_tx(&s.au_full[st], WF_T128);
-        ptx::tma_load_2d(s.hs[st], &t_au, &s.au_full[st], 0, c * 128);
+        ptx::tma_load_2d(s.ad + st * WF_T128, &t_au, &s.au_full[st], 0, c * 128);
       }
     }
   } else if (warp == 1) {
@@ -137,8 +138,8 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
       const uint32_t t_addr = ptx::smem_u32(s.t);
       // G1: acc1 = h · B_d'ᵀ
       for (int kc = 0; kc < nk; ++kc) {
-        const int st = kc & 1;
-        ptx::mbar_wait(&s.full[st], (kc >> 1) & 1);
+        const int st = kc % WF_STAGES;
+        ptx::mbar_wait(&s.full[st], (kc / WF_STAGES) & 1);
         ptx::tc_fence_after();
         wf_mma_k64(t_acc13, ptx::smem_u32(s.hs[st]), ptx::smem_u32(s.bds[st]), p.r, kc > 0);
         ptx::umma_commit(&s.empty[st]);
@@ -149,11 +150,12 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
       ptx::mbar_wait(&s.w_full, 0);
       ptx::tc_fence_after();
       wf_mma_k64(t_acc2, t_addr, ptx::smem_u32(s.ad), p.b, false);
+      ptx::umma_commit(&s.ad_free);
       ptx::umma_commit(&s.acc_full);                                   // completion 1
       // G3: acc3 = u · B_uᵀ
       ptx::mbar_wait(&s.op_full, 1);
       ptx::tc_fence_after();
-      for (int c = 0; c < nu; ++c) wf_mma_k64(t_acc13, ptx::smem_u32(s.u[c]), ptx::smem_u32(s.bu[c]), p.r, c > 0);
+      for (int c = 0; c < nu; ++c) wf_mma_k64(t_acc13, ptx::smem_u32(s.hs[c]), ptx::smem_u32(s.bu[c]), p.r, c > 0);
       ptx::umma_commit(&s.acc_full);                                   // completion 2
       // G4: acc4[c & 1] = t2 · A_u,cᵀ
       ptx::mbar_wait(&s.op_full, 0);                                   // completion 2 of op_full (parity 0 again)
@@ -163,7 +165,7 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
         ptx::mbar_wait(&s.au_full[st], (c >> 1) & 1);
         ptx::mbar_wait(&s.acc4_empty[st], ((c >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        wf_mma_k64(t_acc4[st], t_addr, ptx::smem_u32(s.hs[st]), 128, false);
+        wf_mma_k64(t_acc4[st], t_addr, ptx::smem_u32(s.ad + st * WF_T128), 128, false);
         ptx::umma_commit(&s.au_empty[st]);
         ptx::umma_commit(&s.acc4_full[st]);
       }
@@ -172,16 +174,18 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row = m0 + r;
+    const int half = (warp - 4) >> 2;        // output stage: which two of the four 32-column groups of a chunk
     bool valid = row < p.rows;
     if (valid && p.row_lengths != nullptr) {
       const int bb = row / p.rows_per_seq;
       valid = (row - bb * p.rows_per_seq) < __ldg(p.row_lengths + bb);
     }
+    if (half == 0) {
     // ---- row statistics from the staged h tiles
     float sx = 0.0f, sxx = 0.0f;
     for (int kc = 0; kc < nk; ++kc) {
-      const int st = kc & 1;
-      ptx::mbar_wait(&s.full[st], (kc >> 1) & 1);
+      const int st = kc % WF_STAGES;
+      ptx::mbar_wait(&s.full[st], (kc / WF_STAGES) & 1);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint4 v = *reinterpret_cast<const uint4*>(s.hs[st] + r * 128 + ((c ^ (r & 7)) << 4));
@@ -253,7 +257,7 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t q4[4] = {pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]};
-        wf_store_chunk(s.u[cc >> 1], r, (cc & 1) * 4 + c, q4);
+        wf_store_chunk(s.hs[cc >> 1], r, (cc & 1) * 4 + c, q4);
       }
     }
     ptx::tc_fence_before();
@@ -289,43 +293,56 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&s.op_full);                        // completion 2
-    // ---- stage 4: out = h + acc4 + c_u, padded rows := 0, 256-bit accesses
+    }   // half == 0
+    // ---- stage 4 (8 warps): out = h + acc4 + c_u, padded rows := 0, 256-bit accesses; the residual row segment of the next
+    //      column group is requested before the current one is finished
     const __nv_bfloat16* hrow = reinterpret_cast<const __nv_bfloat16*>(p.h) + static_cast<int64_t>(row) * p.ldh;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo;
-    for (int c = 0; c < nc4; ++c) {
+    const bool in_range = row < p.rows;
+    uint32_t hres[2][2][8];
+    if (in_range) {
+      ld_global_nc_v8(hrow + half * 64, hres[0][0]);
+      ld_global_nc_v8(hrow + half * 64 + 16, hres[0][1]);
+    }
+    const int iters = nc4 * 2;
+#pragma unroll 2
+    for (int it = 0; it < iters; ++it) {
+      const int c = it >> 1, q = half * 2 + (it & 1);
       const int st = c & 1;
-      ptx::mbar_wait(&s.acc4_full[st], (c >> 1) & 1);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        const int col = c * 128 + q * 32;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_acc4[st] + lane_off + q * 32, v);
-        uint32_t hres[2][8];
-        if (row < p.rows) {
-          ld_global_nc_v8(hrow + col, hres[0]);
-          ld_global_nc_v8(hrow + col + 16, hres[1]);
-        }
-        ptx::tmem_ld_wait();
-        if (row < p.rows) {
+      const int col = c * 128 + q * 32;
+      const int cur = it & 1;
+      if ((it & 1) == 0) {
+        ptx::mbar_wait(&s.acc4_full[st], (c >> 1) & 1);
+        ptx::tc_fence_after();
+      }
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(t_acc4[st] + lane_off + q * 32, v);
+      if (in_range && it + 1 < iters) {
+        const int c2 = (it + 1) >> 1, q2 = half * 2 + ((it + 1) & 1);
+        ld_global_nc_v8(hrow + c2 * 128 + q2 * 32, hres[cur ^ 1][0]);
+        ld_global_nc_v8(hrow + c2 * 128 + q2 * 32 + 16, hres[cur ^ 1][1]);
+      }
+      ptx::tmem_ld_wait();
+      if (in_range) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t w[8];
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = hh * 16 + 2 * i;
-              const float2 hr = unpack_bf16x2(hres[hh][i]);
-              const float a = valid ? __uint_as_float(v[j]) + __ldg(p.c_u + col + j) + hr.x : 0.0f;
-              const float b = valid ? __uint_as_float(v[j + 1]) + __ldg(p.c_u + col + j + 1) + hr.y : 0.0f;
-              w[i] = pack_bf16x2(a, b);
-            }
-            st_global_v8(orow + col + hh * 16, w);
+          for (int i = 0; i < 8; ++i) {
+            const int j = hh * 16 + 2 * i;
+            const float2 hr = unpack_bf16x2(hres[cur][hh][i]);
+            const float a = valid ? __uint_as_float(v[j]) + __ldg(p.c_u + col + j) + hr.x : 0.0f;
+            const float b = valid ? __uint_as_float(v[j + 1]) + __ldg(p.c_u + col + j + 1) + hr.y : 0.0f;
+            w[i] = pack_bf16x2(a, b);
           }
+          st_global_v8(orow + col + hh * 16, w);
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s.acc4_empty[st]);
+      if (it & 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s.acc4_empty[st]);
+      }
     }
   }
   ptx::tc_fence_before();
