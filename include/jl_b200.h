@@ -262,6 +262,26 @@ typedef struct {
 } jl_adamw_params;
 int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a11: the one collective of the fine-tune step — sum of the flat fp32 adapter + lm_head gradient
+ * bucket over the data-parallel ranks (what DDP's reducer does for the reference's trainable set,
+ * /root/reference/requirements.txt:1,75).  One process per GPU; NCCL over NVLink 5 / NVSwitch.
+ * libnccl.so.2 is resolved with dlopen at the first call (the copy the host process already has
+ * loaded wins), so the library carries no link-time dependency on NCCL; without it every
+ * jl_comm_* call returns JL_EUNSUPPORTED.
+ *   rank 0: jl_comm_unique_id(id) → ship the JL_COMM_ID_BYTES bytes to every rank out of band →
+ *   every rank: jl_comm_init(id, rank, world, &comm) on its own current device →
+ *   per step: jl_comm_allreduce(comm, bucket, n, stream) (in place, enqueue only; graph-capturable) →
+ *   jl_comm_destroy(comm).
+ * ------------------------------------------------------------------------------------------ */
+#define JL_COMM_ID_BYTES 128
+typedef struct jl_comm jl_comm;
+int jl_comm_unique_id(void* id_out);
+int jl_comm_init(const void* id, int32_t rank, int32_t world, jl_comm** out);
+int jl_comm_allreduce(jl_comm* comm, float* buf, size_t n_f32, void* stream);
+int jl_comm_rank(const jl_comm* comm, int32_t* rank, int32_t* world);
+int jl_comm_destroy(jl_comm* comm);
+
 /* test / tuning hook: 1 = launch every kernel with programmatic dependent launch, 0 (default) = plain stream order */
 void jl_debug_set_pdl(int on);
 

@@ -8,12 +8,14 @@ transfer.  Public surface (HF-style, drop-in for the reference's pinned stack on
     JLForCTC             encoder + CTC head: forward(input_features, attention_mask, labels) → (loss, logits)
     AdapterTrainer       flat-bucket adapter fine-tuning step (CUDA graph + one NCCL all-reduce + fused AdamW)
     Transcriber          waveform → token ids inference step (CUDA graph)
+    JLComm               C-ABI NCCL communicator for the one gradient all-reduce of the data-parallel step
 
 All computation goes through ``libjl_b200.so`` (C ABI in ``include/jl_b200.h``); there is no CPU fallback.
 The directory name contains a hyphen: import it with ``importlib.import_module("jiao-liao_speech_recognition_b200")``
 or through the ``jl_b200`` alias module at the repository root.
 """
 from . import _lib, ops  # noqa: F401
+from .comm import JLComm  # noqa: F401
 from .configuration import JLConfig  # noqa: F401
 from .feature_extraction import JLFeatureExtractor  # noqa: F401
 from .modeling import AttAdapter, GradSink, JLEncoder, JLEngine, JLForCTC, WFAdapter  # noqa: F401

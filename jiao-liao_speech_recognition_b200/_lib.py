@@ -115,7 +115,13 @@ SYMBOLS = {
     "jl_cast_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "jl_add_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
     "jl_adamw_bucket": (C.c_int, [C.POINTER(AdamWParams), vp]),
+    "jl_comm_unique_id": (C.c_int, [vp]),
+    "jl_comm_init": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
+    "jl_comm_allreduce": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "jl_comm_rank": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)]),
+    "jl_comm_destroy": (C.c_int, [vp]),
 }
+COMM_ID_BYTES = 128
 
 
 class JLError(RuntimeError):

@@ -8,18 +8,21 @@
 //   ctc_prep        compact the labels (>= 0) per utterance, target lengths
 //   ctc_row_stats   online max / log-sum-exp over V by warp shuffle (+ first-max argmax for greedy), then gathers the
 //                   2S+1 extended-label log-probs of the frame while the row is still hot in L1/L2
-//   ctc_lattice     one CTA per utterance: alpha (threads 0-511) and beta (threads 512-1023) recursions run
-//                   concurrently over the gathered log-probs, one barrier per frame, rows double-buffered in smem
+//   ctc_lattice     one CTA per (utterance, direction): the alpha and the beta recursion of an utterance run
+//                   on different SMs over the gathered log-probs, one barrier per frame, rows double-buffered in smem
 //   ctc_grad        one CTA per frame: grad = softmax − Σ_{s: l'_s = v} exp(α+β−lp+nll); duplicate labels are combined in
 //                   fixed order in shared memory (deterministic — no float atomics), the row is written once
 //   ctc_reduce      reduction "sum" | "mean" and zero_infinity
 #include <math_constants.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace jl {
 
 constexpr int CTC_LATTICE_HALF = 512;
+constexpr int CTC_LAT_AHEAD = 4;          // frames of log-probs kept in flight by the lattice recursion
 constexpr int CTC_GRAD_THREADS = 256;
 
 struct CtcWs {
@@ -162,79 +165,83 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
-// One CTA per utterance; threads [0, 512) run alpha forward in time, threads [512, 1024) run beta backward.
-__global__ void __launch_bounds__(2 * CTC_LATTICE_HALF) ctc_lattice_kernel(const int32_t* __restrict__ labels, int smax,
-                                                                           const int32_t* __restrict__ tlen,
-                                                                           const int32_t* __restrict__ lengths, int seq, int blank,
-                                                                           const float* __restrict__ lpx, float* __restrict__ alpha,
-                                                                           float* __restrict__ beta, float* __restrict__ nll) {
+// One CTA per (utterance, direction): blockIdx.y = 0 runs the alpha recursion forward in time, blockIdx.y = 1 the beta
+// recursion backward.  The recursion is serial in t and issue-bound on its SM (≈ 200 instructions per state and frame),
+// so the two directions of an utterance run on different SMs.
+__global__ void __launch_bounds__(CTC_LATTICE_HALF) ctc_lattice_kernel(const int32_t* __restrict__ labels, int smax,
+                                                                       const int32_t* __restrict__ tlen,
+                                                                       const int32_t* __restrict__ lengths, int seq, int blank,
+                                                                       const float* __restrict__ lpx, float* __restrict__ alpha,
+                                                                       float* __restrict__ beta, float* __restrict__ nll) {
   jl::pdl_prologue();
   extern __shared__ float lat_smem[];
   const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y != 0;
   const int S = tlen[b];
   const int L = 2 * S + 1;
   const int Lmax = 2 * smax + 1;
   const int T = min(lengths[b], seq);
-  float* a_buf = lat_smem;                 // [2][Lmax]
-  float* b_buf = lat_smem + 2 * Lmax;      // [2][Lmax]
-  int* ext = reinterpret_cast<int*>(lat_smem + 4 * Lmax);   // [Lmax]
-  const bool is_beta = threadIdx.x >= CTC_LATTICE_HALF;
-  const int gtid = threadIdx.x - (is_beta ? CTC_LATTICE_HALF : 0);
-  for (int s = threadIdx.x; s < L; s += blockDim.x) ext[s] = (s & 1) ? labels[static_cast<int64_t>(b) * smax + (s >> 1)] : blank;
+  float* buf = lat_smem;                                      // [2][Lmax]
+  int* ext = reinterpret_cast<int*>(lat_smem + 2 * Lmax);     // [Lmax]
+  const int nthr = blockDim.x;                                // the host sizes the CTA to the longest extended label sequence
+  const int gtid = threadIdx.x;
+  for (int s = gtid; s < L; s += nthr) ext[s] = (s & 1) ? labels[static_cast<int64_t>(b) * smax + (s >> 1)] : blank;
   __syncthreads();
   if (T == 0) {
-    if (threadIdx.x == 0) nll[b] = (L > 1) ? CUDART_INF_F : 0.0f;
+    if (!is_beta && gtid == 0) nll[b] = (L > 1) ? CUDART_INF_F : 0.0f;
     return;
   }
-  const float* lp_b = lpx + static_cast<int64_t>(b) * seq * Lmax;
-  float* al_b = alpha + static_cast<int64_t>(b) * seq * Lmax;
-  float* be_b = beta + static_cast<int64_t>(b) * seq * Lmax;
-  float* buf = is_beta ? b_buf : a_buf;
-  float* out = is_beta ? be_b : al_b;
+  const int64_t base = static_cast<int64_t>(b) * seq * Lmax;
+  const int64_t dir = is_beta ? -static_cast<int64_t>(Lmax) : static_cast<int64_t>(Lmax);    // one frame along the recursion
+  const int t_first = is_beta ? T - 1 : 0;
+  const float* lp_row = lpx + base + static_cast<int64_t>(t_first) * Lmax;      // row of the current frame
+  float* out_row = (is_beta ? beta : alpha) + base + static_cast<int64_t>(t_first) * Lmax;
 
   // t = 0 (alpha) / t = T-1 (beta)
-  {
-    const int t = is_beta ? T - 1 : 0;
-    for (int s = gtid; s < L; s += CTC_LATTICE_HALF) {
-      float v = -CUDART_INF_F;
-      if (!is_beta) {
-        if (s <= 1) v = lp_b[static_cast<int64_t>(t) * Lmax + s];
-      } else {
-        if (s >= L - 2) v = lp_b[static_cast<int64_t>(t) * Lmax + s];
-      }
-      buf[s] = v;
-      out[static_cast<int64_t>(t) * Lmax + s] = v;
+  for (int s = gtid; s < L; s += nthr) {
+    float v = -CUDART_INF_F;
+    if (!is_beta) {
+      if (s <= 1) v = lp_row[s];
+    } else {
+      if (s >= L - 2) v = lp_row[s];
     }
+    buf[s] = v;
+    out_row[s] = v;
   }
   __syncthreads();
-  // The log-prob of the next frame is fetched before the barrier of the current one, so the global-load latency of
-  // the (serial) recursion is hidden behind the previous step.
-  float lp_pref = 0.0f;
-  if (T > 1 && gtid < L) lp_pref = lp_b[static_cast<int64_t>(is_beta ? T - 2 : 1) * Lmax + gtid];
-  for (int step = 1; step < T; ++step) {
-    const int t = is_beta ? T - 1 - step : step;
-    const float* prev = buf + ((step - 1) & 1) * Lmax;
-    float* cur = buf + (step & 1) * Lmax;
-    const float lp_first = lp_pref;
-    if (step + 1 < T && gtid < L) lp_pref = lp_b[static_cast<int64_t>(is_beta ? t - 1 : t + 1) * Lmax + gtid];
-    for (int s = gtid; s < L; s += CTC_LATTICE_HALF) {
-      const float lp = (s == gtid) ? lp_first : lp_b[static_cast<int64_t>(t) * Lmax + s];
-      float x0 = prev[s], x1 = -CUDART_INF_F, x2 = -CUDART_INF_F;
-      if (!is_beta) {
-        if (s >= 1) x1 = prev[s - 1];
-        if (s >= 2 && (s & 1) && ext[s] != ext[s - 2]) x2 = prev[s - 2];
-      } else {
-        if (s + 1 < L) x1 = prev[s + 1];
-        if (s + 2 < L && (s & 1) && ext[s] != ext[s + 2]) x2 = prev[s + 2];
+  // A global load issued one step ahead would still expose most of its latency, so the log-probs of the next
+  // CTC_LAT_AHEAD frames are kept in flight in registers.
+  float ring[CTC_LAT_AHEAD];
+#pragma unroll
+  for (int u = 0; u < CTC_LAT_AHEAD; ++u) ring[u] = (1 + u < T && gtid < L) ? __ldg(lp_row + (1 + u) * dir + gtid) : 0.0f;
+  // neighbour offsets and the skip-transition predicate of this thread's first state do not depend on t
+  const int nb = is_beta ? 1 : -1;
+  for (int step0 = 1; step0 < T; step0 += CTC_LAT_AHEAD) {
+#pragma unroll
+    for (int u = 0; u < CTC_LAT_AHEAD; ++u) {
+      const int step = step0 + u;
+      if (step >= T) break;                                   // uniform over the CTA
+      lp_row += dir;
+      out_row += dir;
+      const float* prev = buf + ((step - 1) & 1) * Lmax;
+      float* cur = buf + (step & 1) * Lmax;
+      const float lp_first = ring[u];
+      if (step + CTC_LAT_AHEAD < T && gtid < L) ring[u] = __ldg(lp_row + CTC_LAT_AHEAD * dir + gtid);
+      for (int s = gtid; s < L; s += nthr) {
+        const float lp = (s == gtid) ? lp_first : lp_row[s];
+        const int s1 = s + nb, s2 = s + 2 * nb;
+        float x0 = prev[s], x1 = -CUDART_INF_F, x2 = -CUDART_INF_F;
+        if (s1 >= 0 && s1 < L) x1 = prev[s1];
+        if (s2 >= 0 && s2 < L && (s & 1) && ext[s] != ext[s2]) x2 = prev[s2];
+        const float v = lse3(x0, x1, x2) + lp;
+        cur[s] = v;
+        out_row[s] = v;
       }
-      const float v = lse3(x0, x1, x2) + lp;
-      cur[s] = v;
-      out[static_cast<int64_t>(t) * Lmax + s] = v;
+      __syncthreads();
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const float* last = a_buf + ((T - 1) & 1) * Lmax;
+  if (!is_beta && gtid == 0) {
+    const float* last = buf + ((T - 1) & 1) * Lmax;
     const float l1 = last[L - 1];
     const float l2 = (L > 1) ? last[L - 2] : -CUDART_INF_F;
     nll[b] = -lse3(l1, l2, -CUDART_INF_F);
@@ -437,12 +444,13 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
                                                                    p->vocab, p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen,
                                                                    p->blank, w.lpx);
   JL_CHECK_LAUNCH("ctc_row_stats");
-  const size_t lat_smem = static_cast<size_t>(5) * Lmax * sizeof(float);
+  const size_t lat_smem = static_cast<size_t>(3) * Lmax * sizeof(float);
   if (lat_smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(jl::ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lat_smem));
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "ctc: cannot reserve lattice shared memory: %s", cudaGetErrorString(e));
   }
-  jl::launch(jl::ctc_lattice_kernel, p->batch, 2 * jl::CTC_LATTICE_HALF, lat_smem, s, w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
+  const int lat_half = std::min(jl::CTC_LATTICE_HALF, ((2 * smax + 1 + 31) / 32) * 32);
+  jl::launch(jl::ctc_lattice_kernel, dim3(p->batch, 2), lat_half, lat_smem, s, w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
                                                                             w.alpha, w.beta, p->nll);
   JL_CHECK_LAUNCH("ctc_lattice");
   if (p->grad != nullptr) {

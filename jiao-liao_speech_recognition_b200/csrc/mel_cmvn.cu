@@ -28,12 +28,20 @@ constexpr int MEL_THREADS = MEL_WARPS * 32;
 constexpr float MEL_PREEMPH = 0.97f;
 constexpr float MEL_FLT_EPS = 1.1920928955078125e-07f;
 
+// Shared-memory layouts are chosen for the LSU, which bounds this kernel (ncu: 73 % of peak shared wavefronts, half of
+// them bank conflicts in the first version): the FFT buffers are padded (one float2 after every four), the per-pass
+// twiddles are stored contiguously in the butterfly index, and the mel weights are transposed so that the 32 lanes of a
+// tap load hit 32 different banks.
+constexpr int MEL_FFT_PAD = 256 + 64;
+__device__ __forceinline__ int fft_phys(int idx) { return idx + (idx >> 2); }
+
 struct MelSmem {
   float wave[MEL_SAMPLES_PER_CTA];
-  float2 fft[MEL_WARPS][2][256];
+  float2 fft[MEL_WARPS][2][MEL_FFT_PAD];
   float window[MEL_FRAME_LEN];
-  float2 tw512[512];
-  float mel_w[JL_MEL_BINS * JL_MEL_MAXW];
+  float2 tw512[257];                              // exp(-2πi k / 512), k = 0..256 (real-FFT untangling)
+  float2 tw_pass[3 * (4 + 16 + 64)];              // per radix-4 pass p ∈ {4, 16, 64}: [r-1][k] = exp(-2πi k r / (4p))
+  float mel_wt[JL_MEL_MAXW][JL_MEL_BINS + 1];     // transposed: [tap][bin]
   int mel_lo[JL_MEL_BINS];
   int mel_cnt[JL_MEL_BINS];
   float out[MEL_FPC][JL_MEL_BINS];
@@ -44,29 +52,28 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ int utt_frames(int n) { return n < MEL_FRAME_LEN ? 0 : 1 + (n - MEL_FRAME_LEN) / MEL_FRAME_SHIFT; }
 
 // One radix-4 Stockham pass over 256 complex points held in shared memory; a warp does the 64 butterflies.
-// p = size of the sub-transforms already computed (1, 4, 16, 64).  tw512[2n] = exp(-2πi n / 256).
-__device__ __forceinline__ void fft256_pass(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw512,
-                                            int p, int lane) {
+// p = size of the sub-transforms already computed (1, 4, 16, 64); tw = this pass's twiddles [3][p].
+__device__ __forceinline__ void fft256_pass(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw, int p,
+                                            int lane) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = lane + 32 * h;
     const int k = i & (p - 1);
     const int j = ((i - k) << 2) + k;
-    float2 u0 = src[i], u1 = src[i + 64], u2 = src[i + 128], u3 = src[i + 192];
+    float2 u0 = src[fft_phys(i)], u1 = src[fft_phys(i + 64)], u2 = src[fft_phys(i + 128)], u3 = src[fft_phys(i + 192)];
     if (p > 1) {
-      const int step = 64 / p;                 // exp(-2πi k r / (4p)) = W256[k r step]
-      u1 = cmul(u1, tw512[2 * (k * step)]);
-      u2 = cmul(u2, tw512[2 * (2 * k * step)]);
-      u3 = cmul(u3, tw512[2 * (3 * k * step)]);
+      u1 = cmul(u1, tw[k]);
+      u2 = cmul(u2, tw[p + k]);
+      u3 = cmul(u3, tw[2 * p + k]);
     }
     const float2 a = make_float2(u0.x + u2.x, u0.y + u2.y);
     const float2 b = make_float2(u0.x - u2.x, u0.y - u2.y);
     const float2 c = make_float2(u1.x + u3.x, u1.y + u3.y);
     const float2 d = make_float2(u1.x - u3.x, u1.y - u3.y);   // (u1 - u3); multiplied by -i → (d.y, -d.x)
-    dst[j] = make_float2(a.x + c.x, a.y + c.y);
-    dst[j + p] = make_float2(b.x + d.y, b.y - d.x);
-    dst[j + 2 * p] = make_float2(a.x - c.x, a.y - c.y);
-    dst[j + 3 * p] = make_float2(b.x - d.y, b.y + d.x);
+    dst[fft_phys(j)] = make_float2(a.x + c.x, a.y + c.y);
+    dst[fft_phys(j + p)] = make_float2(b.x + d.y, b.y - d.x);
+    dst[fft_phys(j + 2 * p)] = make_float2(a.x - c.x, a.y - c.y);
+    dst[fft_phys(j + 3 * p)] = make_float2(b.x - d.y, b.y + d.x);
   }
   __syncwarp();
 }
@@ -92,8 +99,15 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
   if (nv > 0) {
     // ---- stage constants and the shared span of samples
     for (int i = tid; i < MEL_FRAME_LEN; i += MEL_THREADS) s.window[i] = __ldg(p.window + i);
-    for (int i = tid; i < 512; i += MEL_THREADS) s.tw512[i] = __ldg(reinterpret_cast<const float2*>(p.twiddle) + i);
-    for (int i = tid; i < JL_MEL_BINS * JL_MEL_MAXW; i += MEL_THREADS) s.mel_w[i] = __ldg(p.mel_w + i);
+    for (int i = tid; i < 257; i += MEL_THREADS) s.tw512[i] = __ldg(reinterpret_cast<const float2*>(p.twiddle) + i);
+    for (int i = tid; i < 3 * (4 + 16 + 64); i += MEL_THREADS) {
+      // pass tables: offsets 0 (p = 4), 12 (p = 16), 60 (p = 64); entry [r-1][k] = W256^(k r 64/p) = tw512[2 k r 64/p]
+      const int pp = (i < 12) ? 4 : (i < 60 ? 16 : 64);
+      const int base = (i < 12) ? 0 : (i < 60 ? 12 : 60);
+      const int rr = (i - base) / pp + 1, kk = (i - base) % pp;
+      s.tw_pass[i] = __ldg(reinterpret_cast<const float2*>(p.twiddle) + ((2 * kk * rr * (64 / pp)) & 511));
+    }
+    for (int i = tid; i < JL_MEL_BINS * JL_MEL_MAXW; i += MEL_THREADS) s.mel_wt[i % JL_MEL_MAXW][i / JL_MEL_MAXW] = __ldg(p.mel_w + i);
     if (tid < JL_MEL_BINS) {
       s.mel_lo[tid] = __ldg(p.mel_lo + tid);
       s.mel_cnt[tid] = __ldg(p.mel_cnt + tid);
@@ -133,13 +147,13 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
           const float prev = x[i > 0 ? i - 1 : 0] - mean;
           y = (cur - MEL_PREEMPH * prev) * s.window[i];
         }
-        bufA_f[i] = y;                                                // z[j] = (y[2j], y[2j+1])
+        bufA_f[2 * fft_phys(i >> 1) + (i & 1)] = y;                   // z[j] = (y[2j], y[2j+1])
       }
       __syncwarp();
-      fft256_pass(bufA, bufB, s.tw512, 1, lane);
-      fft256_pass(bufB, bufA, s.tw512, 4, lane);
-      fft256_pass(bufA, bufB, s.tw512, 16, lane);
-      fft256_pass(bufB, bufA, s.tw512, 64, lane);
+      fft256_pass(bufA, bufB, s.tw_pass, 1, lane);
+      fft256_pass(bufB, bufA, s.tw_pass, 4, lane);
+      fft256_pass(bufA, bufB, s.tw_pass + 12, 16, lane);
+      fft256_pass(bufB, bufA, s.tw_pass + 60, 64, lane);
       // untangle the real transform: X[k] = E[k] + W512^k O[k], k = 0..256; power = |X|²
       float pk[9];
 #pragma unroll
@@ -147,8 +161,8 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
         const int k = lane + 32 * j;
         pk[j] = 0.0f;
         if (k <= 256) {
-          const float2 zk = bufA[k & 255];
-          const float2 zn = bufA[(256 - k) & 255];
+          const float2 zk = bufA[fft_phys(k & 255)];
+          const float2 zn = bufA[fft_phys((256 - k) & 255)];
           const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
           const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
           const float2 wo = cmul(s.tw512[k], o);
@@ -166,9 +180,8 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
       // sparse mel projection + log (kaldi.py:630-633)
       for (int m = lane; m < JL_MEL_BINS; m += 32) {
         const int lo = s.mel_lo[m], cnt = s.mel_cnt[m];
-        const float* w = s.mel_w + m * JL_MEL_MAXW;
         float acc = 0.0f;
-        for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], pw[lo + j], acc);
+        for (int j = 0; j < cnt; ++j) acc = fmaf(s.mel_wt[j][m], pw[lo + j], acc);
         s.out[fl][m] = logf(fmaxf(acc, MEL_FLT_EPS));
       }
       __syncwarp();

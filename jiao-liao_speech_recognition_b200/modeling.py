@@ -355,24 +355,60 @@ class JLEngine:
         return subsampled_length(frame_lengths.to(torch.int64)).to(I32)
 
     # ------------------------------------------------------------------ adapters
-    def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect: int, zero_rows: bool):
+    @staticmethod
+    def dialect_segments(dialect, b: int, num_dialects: int):
+        """``dialect`` = one id for the whole batch or one id per utterance (SURVEY §8c ``dialect_ids [B]``) → runs
+        ``[(k, b0, b1), …]`` of adjacent utterances that share a factor set.  Utterances of one dialect must be adjacent
+        (sort the batch by dialect): every run is one slice of the [B·T', d] activation matrix, and every factor set
+        has exactly one gradient writer."""
+        if isinstance(dialect, int):
+            ids = [dialect] * b
+        else:
+            ids = [int(k) for k in (dialect.tolist() if torch.is_tensor(dialect) else dialect)]
+            if len(ids) != b:
+                raise ValueError(f"dialect ids: expected {b} entries (one per utterance), got {len(ids)}")
+        segs = []
+        for i, k in enumerate(ids):
+            if not 0 <= k < num_dialects:
+                raise ValueError(f"dialect id {k} out of range for {num_dialects} factor set(s)")
+            if segs and segs[-1][0] == k:
+                segs[-1][2] = i + 1
+            else:
+                segs.append([k, i, i + 1])
+        seen = [k for k, _, _ in segs]
+        if len(set(seen)) != len(seen):
+            raise ValueError("utterances of one dialect must be adjacent in the batch (sort the batch by dialect id)")
+        return [tuple(x) for x in segs]
+
+    def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect, zero_rows: bool):
         """Returns (out, saved).  out = h + adapter(h); padded rows zeroed when ``zero_rows`` (end of a layer)."""
         eps = ad.norm.eps
+        segs = self.dialect_segments(dialect, b, ad.num_dialects) if ad.kind == "wf" else None
         if ad.kind == "wf" and not training and self.fused_wf and self._wf_fusable(ad):
-            # inference: the whole adapter is one kernel (LN folded into the first projection); training keeps the composed
-            # path because the backward needs every intermediate
-            out, _, _ = ops.wfadapter_fwd(h, self._wf_pack(ad, dialect), eps, row_lengths=lengths if zero_rows else None,
-                                          rows_per_seq=t if zero_rows else 0)
+            # inference: the whole adapter is one kernel per dialect run (LN folded into the first projection); training
+            # keeps the composed path because the backward needs every intermediate
+            out = torch.empty_like(h)
+            for k, b0, b1 in segs:
+                rows = slice(b0 * t, b1 * t)
+                ops.wfadapter_fwd(h[rows], self._wf_pack(ad, k), eps, row_lengths=lengths[b0:b1] if zero_rows else None,
+                                  rows_per_seq=t if zero_rows else 0, out=out[rows])
             return out, None
         z, mean, rstd = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), eps, save_stats=training)
         rl = dict(row_lengths=lengths, rows_per_seq=t) if zero_rows else {}
         if ad.kind == "wf":
-            k = dialect
-            t1 = ops.gemm(z, self._bf16(ad.down_B)[k])
-            u = ops.gemm(t1, self._bf16(ad.down_A)[k], bias=ad.down_bias.detach()[k], epilogue=L.JL_EPI_RELU)
-            t2 = ops.gemm(u, self._bf16(ad.up_B)[k])
-            out = ops.gemm(t2, self._bf16(ad.up_A)[k], bias=ad.up_bias.detach()[k], residual=h, **rl)
-            saved = (h, mean, rstd, z, t1, u, t2, k) if training else None
+            m, dev = h.shape[0], h.device
+            t1 = torch.empty((m, ad.rank), dtype=BF16, device=dev)
+            u = torch.empty((m, ad.bottleneck), dtype=BF16, device=dev)
+            t2 = torch.empty((m, ad.rank), dtype=BF16, device=dev)
+            out = torch.empty_like(h)
+            for k, b0, b1 in segs:
+                rows = slice(b0 * t, b1 * t)
+                rls = dict(row_lengths=lengths[b0:b1], rows_per_seq=t) if zero_rows else {}
+                ops.gemm(z[rows], self._bf16(ad.down_B)[k], out=t1[rows])
+                ops.gemm(t1[rows], self._bf16(ad.down_A)[k], bias=ad.down_bias.detach()[k], epilogue=L.JL_EPI_RELU, out=u[rows])
+                ops.gemm(u[rows], self._bf16(ad.up_B)[k], out=t2[rows])
+                ops.gemm(t2[rows], self._bf16(ad.up_A)[k], bias=ad.up_bias.detach()[k], residual=h[rows], out=out[rows], **rls)
+            saved = (h, mean, rstd, z, t1, u, t2, segs) if training else None
         else:
             wqkv = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
             bqkv = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
@@ -382,28 +418,42 @@ class JLEngine:
             saved = (h, mean, rstd, z, qkv, a, lse) if training else None
         return out, saved
 
+    def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch") -> None:
+        """Backward of the WFAdapter projections for the utterances of dialect ``k`` (a row slice): weight gradients of
+        factor set k on the side branch, dz[rows] = gradient at the adapter's LayerNorm output."""
+        MN = L.JL_LAYOUT_MN
+        dy, z, t1, u, t2 = dy[rows], z[rows], t1[rows], u[rows], t2[rows]
+
+        def w_up():
+            ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)             # dyᵀ · t2
+            ops.colsum(dy, out=g.out(ad.up_bias, k))
+        sb.run(w_up, dy, t2)
+        dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
+        sb.run(lambda: ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32), dt2, u)   # dt2ᵀ · u
+        dpre = ops.gemm(dt2, self._bf16(ad.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=u)      # (dt2 · B_u) ∘ relu'
+
+        def w_down():
+            ops.colsum(dpre, out=g.out(ad.down_bias, k))
+            ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)          # dpreᵀ · t1
+        sb.run(w_down, dpre, t1)
+        dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
+        sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
+        ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                                # dt1 · B_d
+
     def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink", sb: "_SideBranch") -> torch.Tensor:
         """dy = grad of the adapter output → returns grad of the adapter input; weight grads go to ``g`` (issued on the
         side branch ``sb``)."""
         MN = L.JL_LAYOUT_MN
         if ad.kind == "wf":
-            h, mean, rstd, z, t1, u, t2, k = saved
-
-            def w_up():
-                ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)             # dyᵀ · t2
-                ops.colsum(dy, out=g.out(ad.up_bias, k))
-            sb.run(w_up, dy, t2)
-            dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
-            sb.run(lambda: ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32), dt2, u)   # dt2ᵀ · u
-            dpre = ops.gemm(dt2, self._bf16(ad.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=u)      # (dt2 · B_u) ∘ relu'
-
-            def w_down():
-                ops.colsum(dpre, out=g.out(ad.down_bias, k))
-                ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)          # dpreᵀ · t1
-            sb.run(w_down, dpre, t1)
-            dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
-            sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
-            dz = ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN)                                         # dt1 · B_d
+            h, mean, rstd, z, t1, u, t2, segs = saved
+            dz = torch.empty_like(h)
+            for k, b0, b1 in segs:
+                self._wf_bwd_rows(ad, k, slice(b0 * t, b1 * t), dy, z, t1, u, t2, dz, g, sb)
+            present = {k for k, _, _ in segs}
+            for k in range(ad.num_dialects):           # factor sets without utterances in this batch: zero gradient
+                if k not in present:
+                    for prm in (ad.up_A, ad.up_bias, ad.up_B, ad.down_A, ad.down_bias, ad.down_B):
+                        g.out(prm, k).zero_()
         else:
             h, mean, rstd, z, qkv, a, lse = saved
 

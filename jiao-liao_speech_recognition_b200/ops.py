@@ -190,12 +190,18 @@ def layernorm_wgrad(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd:
 
 # ----------------------------------------------------------------------------------------------- fused WFAdapter
 def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0,
-                  save_stats: bool = False):
+                  save_stats: bool = False, out: Optional[torch.Tensor] = None):
     """out = h + WFAdapter(h) in one kernel.  ``pack`` holds the kernel-layout factors (see modeling.JLEngine._wf_pack)."""
     _need(h, BF16, "h")
     _rows2d(h, "h")
     rows, d = h.shape
-    out = torch.empty((rows, d), dtype=BF16, device=h.device)
+    if out is None:
+        out = torch.empty((rows, d), dtype=BF16, device=h.device)
+    else:
+        _need(out, BF16, "out")
+        _rows2d(out, "out")
+        if tuple(out.shape) != (rows, d):
+            raise ValueError(f"wfadapter_fwd: out has shape {tuple(out.shape)}, expected {(rows, d)}")
     mean = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
     rstd = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
     p = L.WFAdapterFwdParams(h=h.data_ptr(), ldh=h.stride(0), out=out.data_ptr(), ldo=out.stride(0), bd_scaled=pack["bd"].data_ptr(),

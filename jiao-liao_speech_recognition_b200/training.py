@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from . import ops
+from .comm import JLComm
 from .feature_extraction import JLFeatureExtractor, device_tables, num_frames
 from .modeling import AttAdapter, GradSink, JLForCTC, subsampled_length
 
@@ -108,6 +109,7 @@ class FlatAdapterParams(GradSink):
                 p.grad = self._view(self.grad, p)
         ops.cast_bf16(self.param, out=self.bf16)
         self.step_count = 0
+        self.comm = None          # optional JLComm (C-ABI NCCL communicator); None → torch.distributed, if initialised
         model.encoder.engine(model.lm_head).flat = self
 
     def _view(self, buf: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
@@ -143,16 +145,32 @@ class FlatAdapterParams(GradSink):
                 off += p.shape[0]
 
     # ---- collective + optimizer
+    def world_size(self) -> int:
+        if self.comm is not None:
+            return self.comm.world
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
     def allreduce(self) -> None:
-        """Sum of the gradient bucket over ranks — the single collective of the fine-tune step (NCCL over NVLink)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        """Sum of the gradient bucket over ranks — the single collective of the fine-tune step (NCCL over NVLink):
+        ``jl_comm_allreduce`` when a ``JLComm`` is attached, else ``torch.distributed.all_reduce`` (also the gloo path
+        of the CPU tests)."""
+        if self.comm is not None:
+            self.comm.allreduce_(self.grad)
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
 
     def adamw_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01) -> None:
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        world = self.world_size()
         self.step_count += 1
         ops.adamw_(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, beta1, beta2, eps, weight_decay,
                    grad_scale=1.0 / world, param_bf16=self.bf16)
+
+
+def _dialect_key(dialect):
+    """Hashable form of a dialect argument: an int, or a tuple of per-utterance ids."""
+    if isinstance(dialect, int):
+        return dialect
+    return tuple(int(k) for k in (dialect.tolist() if torch.is_tensor(dialect) else dialect))
 
 
 def shard_utterances(num_frames_per_utt: Sequence[int], world: int) -> List[List[int]]:
@@ -173,10 +191,18 @@ class AdapterTrainer:
     backward] → all-reduce(adapter grads) → fused AdamW → D2H(loss).  The bracketed part is captured in a CUDA graph
     per (batch, samples, label length) shape."""
 
-    def __init__(self, model: JLForCTC, lr: float = 1e-4, weight_decay: float = 0.01, use_cuda_graph: bool = True):
+    def __init__(self, model: JLForCTC, lr: float = 1e-4, weight_decay: float = 0.01, use_cuda_graph: bool = True, comm="auto"):
+        """``comm``: a ``JLComm``; ``"auto"`` (default) builds one from the initialised torch.distributed group when the
+        world has more than one rank; ``"torch"`` leaves the all-reduce to ``torch.distributed``; ``None`` = single rank."""
         self.model = model
         self.cfg = model.config
         self.flat = FlatAdapterParams(model)
+        if comm == "auto":
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            comm = JLComm.from_torch_distributed() if multi else None
+        elif comm == "torch":
+            comm = None
+        self.flat.comm = comm
         self.eng = model.encoder.engine(model.lm_head)
         self.fe = JLFeatureExtractor(device=self.flat.param.device)
         self.lr, self.weight_decay = lr, weight_decay
@@ -184,9 +210,9 @@ class AdapterTrainer:
         self._graphs: Dict[tuple, dict] = {}
         self.launches_per_step = 0
 
-    def _body(self, wave, nsamp, lengths, labels, max_frames):
+    def _body(self, wave, nsamp, lengths, labels, max_frames, dialect=0):
         feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-        st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, want_logits=True)
+        st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, dialect=dialect, want_logits=True)
         b, t = st.b, st.t
         logits = st.logits.view(b, t, self.cfg.vocab_size)
         loss, nll, grad = ops.ctc_loss(logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
@@ -194,8 +220,8 @@ class AdapterTrainer:
         self.eng.backward(st, grad.view(b * t, -1), self.flat)
         return loss
 
-    def _static(self, b: int, n: int, s: int) -> dict:
-        key = (b, n, s)
+    def _static(self, b: int, n: int, s: int, dialect=0) -> dict:
+        key = (b, n, s, dialect)                 # the dialect runs are host-side structure baked into the captured graph
         ent = self._graphs.get(key)
         if ent is not None:
             return ent
@@ -206,25 +232,28 @@ class AdapterTrainer:
             "lengths": torch.ones((b,), dtype=I32, device=dev),
             "labels": torch.full((b, s), -100, dtype=I32, device=dev),
             "max_frames": max(num_frames(n), 1),
+            "dialect": dialect,
             "graph": None,
             "loss": None,
         }
         self._graphs[key] = ent
         return ent
 
-    def step(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad).
+    def step(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor, dialect=0) -> torch.Tensor:
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad),
+        ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent).
         Returns the loss as a 1-element device tensor (call ``.item()`` for the D2H read)."""
         b, n = wave.shape
         s = labels.shape[1]
-        ent = self._static(b, n, s)
+        dialect = _dialect_key(dialect)
+        ent = self._static(b, n, s, dialect)
         ent["wave"].copy_(wave, non_blocking=True)
         ent["nsamp"].copy_(num_samples, non_blocking=True)
         frames = torch.clamp((num_samples.to(torch.int64) - 400) // 160 + 1, min=0)
         frames = torch.where(num_samples.to(torch.int64) < 400, torch.zeros_like(frames), frames)
         ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
         ent["labels"].copy_(labels, non_blocking=True)
-        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"])
+        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
         if not self.use_cuda_graph:
             L.launch_count_reset()
             loss = self._body(*args)
@@ -259,7 +288,7 @@ class AdapterTrainer:
             ent["graph"].replay()
             loss = ent["loss"]
         else:
-            loss = self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"])
+            loss = self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
         self.flat.allreduce()
         self.flat.adamw_step(self.lr, weight_decay=self.weight_decay)
         return loss
@@ -269,7 +298,7 @@ class AdapterTrainer:
         ent = self._last
         ops.GEMM_TRACE = []
         try:
-            self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"])
+            self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
             trace = ops.GEMM_TRACE
         finally:
             ops.GEMM_TRACE = None
@@ -290,21 +319,23 @@ class Transcriber:
         self._graphs: Dict[tuple, dict] = {}
         self.launches_per_step = 0
 
-    def _body(self, wave, nsamp, lengths, max_frames):
+    def _body(self, wave, nsamp, lengths, max_frames, dialect=0):
         feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-        st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, want_logits=True)
+        st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True)
         logits = st.logits.view(st.b, st.t, self.cfg.vocab_size)
         ids, n, _ = ops.ctc_greedy(logits, lengths, blank=self.cfg.pad_token_id)
         return ids, n
 
     @torch.no_grad()
-    def __call__(self, wave: torch.Tensor, num_samples: torch.Tensor):
-        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 host → (ids [B, T'] int32 device, lengths [B])."""
+    def __call__(self, wave: torch.Tensor, num_samples: torch.Tensor, dialect=0):
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 host → (ids [B, T'] int32 device, lengths [B]).
+        ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent)."""
         b, n = wave.shape
-        key = (b, n)
+        dialect = _dialect_key(dialect)
+        key = (b, n, dialect)
         ent = self._graphs.get(key)
         if ent is None:
-            ent = {"wave": torch.zeros((b, n), dtype=F32, device=self.dev), "nsamp": torch.full((b,), n, dtype=I32, device=self.dev),
+            ent = {"dialect": dialect, "wave": torch.zeros((b, n), dtype=F32, device=self.dev), "nsamp": torch.full((b,), n, dtype=I32, device=self.dev),
                    "lengths": torch.ones((b,), dtype=I32, device=self.dev), "max_frames": max(num_frames(n), 1), "graph": None, "out": None}
             self._graphs[key] = ent
         ent["wave"].copy_(wave, non_blocking=True)
@@ -312,7 +343,7 @@ class Transcriber:
         ns = num_samples.to(torch.int64)
         frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
         ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
-        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"])
+        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"])
         if not self.use_cuda_graph:
             L.launch_count_reset()
             out = self._body(*args)
@@ -342,4 +373,4 @@ class Transcriber:
         if ent["graph"] is not None:
             ent["graph"].replay()
             return ent["out"]
-        return self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"])
+        return self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"])

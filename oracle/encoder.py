@@ -100,10 +100,16 @@ def feed_forward(w: W, p: str, x: torch.Tensor) -> torch.Tensor:
     return F.linear(h, w[p + ".output_dense.weight"], w[p + ".output_dense.bias"])
 
 
-def wf_adapter(w: W, p: str, h: torch.Tensor, dialect: int = 0) -> torch.Tensor:
+def wf_adapter(w: W, p: str, h: torch.Tensor, dialect=0) -> torch.Tensor:
     """WFAdapter: bottleneck adapter whose projections exist only as
     low-rank factors.  z = LN(h); u = relu((z B_dᵀ) A_dᵀ + c_d);
-    y = (u B_uᵀ) A_uᵀ + c_u; out = h + y.  Leading dim of every factor = dialect."""
+    y = (u B_uᵀ) A_uᵀ + c_u; out = h + y.  Leading dim of every factor = dialect;
+    ``dialect`` is one id for the batch or one id per utterance (dialect_ids [B])."""
+    if not isinstance(dialect, int):
+        ids = [int(k) for k in dialect]
+        if len(ids) != h.shape[0]:
+            raise ValueError(f"dialect ids: expected {h.shape[0]} entries, got {len(ids)}")
+        return torch.cat([wf_adapter(w, p, h[i:i + 1], ids[i]) for i in range(len(ids))], 0)
     z = layer_norm(h, w, p + ".norm")
     u = torch.relu(F.linear(F.linear(z, w[p + ".down_B"][dialect]), w[p + ".down_A"][dialect], w[p + ".down_bias"][dialect]))
     y = F.linear(F.linear(u, w[p + ".up_B"][dialect]), w[p + ".up_A"][dialect], w[p + ".up_bias"][dialect])
@@ -125,11 +131,11 @@ def att_adapter(w: W, p: str, h: torch.Tensor, lengths: torch.Tensor) -> torch.T
     return h + F.linear(a, w[p + ".o_proj.weight"], w[p + ".o_proj.bias"])
 
 
-def apply_adapter(w: W, p: str, kind: Optional[str], h: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+def apply_adapter(w: W, p: str, kind: Optional[str], h: torch.Tensor, lengths: torch.Tensor, dialect=0) -> torch.Tensor:
     if kind is None:
         return h
     if kind == "wf":
-        return wf_adapter(w, p, h)
+        return wf_adapter(w, p, h, dialect)
     if kind == "att":
         return att_adapter(w, p, h, lengths)
     raise ValueError(kind)
@@ -141,24 +147,24 @@ def zero_padded_rows(h: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
 
 
 def encoder_layer(w: W, i: int, h: torch.Tensor, lengths: torch.Tensor, heads: int,
-                  adapter_attn: Optional[str], adapter_ffn: Optional[str]) -> torch.Tensor:
+                  adapter_attn: Optional[str], adapter_ffn: Optional[str], dialect=0) -> torch.Tensor:
     """h += Attn(LN h); [adapter_attn]; h += FFN(LN h); [adapter_ffn]; padded rows := 0."""
     p = f"layers.{i}"
     h = h + self_attention(w, p + ".attention", layer_norm(h, w, p + ".layer_norm"), lengths, heads)
-    h = apply_adapter(w, p + ".adapter_attn", adapter_attn, h, lengths)
+    h = apply_adapter(w, p + ".adapter_attn", adapter_attn, h, lengths, dialect)
     h = h + feed_forward(w, p + ".feed_forward", layer_norm(h, w, p + ".final_layer_norm"))
-    h = apply_adapter(w, p + ".adapter_ffn", adapter_ffn, h, lengths)
+    h = apply_adapter(w, p + ".adapter_ffn", adapter_ffn, h, lengths, dialect)
     return zero_padded_rows(h, lengths)
 
 
-def encode(w: W, cfg, feats: torch.Tensor, frame_lengths: torch.Tensor):
+def encode(w: W, cfg, feats: torch.Tensor, frame_lengths: torch.Tensor, dialect=0):
     """[B, F, 80] CMVN features + valid frame counts → (last_hidden_state [B, T', d], T' lengths)."""
     h = conv_subsample(w, feats)
     lengths = subsampled_length(frame_lengths)
     h = embed(h, lengths)
     h = zero_padded_rows(h, lengths)
     for i in range(cfg.num_hidden_layers):
-        h = encoder_layer(w, i, h, lengths, cfg.num_attention_heads, cfg.adapter_attn, cfg.adapter_ffn)
+        h = encoder_layer(w, i, h, lengths, cfg.num_attention_heads, cfg.adapter_attn, cfg.adapter_ffn, dialect)
     h = layer_norm(h, w, "layer_norm")
     return h, lengths
 

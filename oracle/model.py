@@ -135,8 +135,8 @@ def ctc_loss(logits, labels, input_lengths, blank=0, reduction="sum", zero_infin
 
 
 def forward_from_features(w, cfg: OracleConfig, feats: torch.Tensor, frame_lengths: torch.Tensor,
-                          labels: Optional[torch.Tensor] = None):
-    h, lengths = oenc.encode(w, cfg, feats, frame_lengths)
+                          labels: Optional[torch.Tensor] = None, dialect=0):
+    h, lengths = oenc.encode(w, cfg, feats, frame_lengths, dialect)
     logits = oenc.lm_head(w, h)
     loss = None
     if labels is not None:
@@ -147,9 +147,9 @@ def forward_from_features(w, cfg: OracleConfig, feats: torch.Tensor, frame_lengt
 
 
 def forward_from_waveforms(w, cfg: OracleConfig, waveforms: Sequence[torch.Tensor],
-                           labels: Optional[torch.Tensor] = None):
+                           labels: Optional[torch.Tensor] = None, dialect=0):
     feats, mask, flens = ofeat.extract(waveforms)
-    return forward_from_features(w, cfg, feats, torch.tensor(flens), labels)
+    return forward_from_features(w, cfg, feats, torch.tensor(flens), labels, dialect)
 
 
 def transcribe(w, cfg: OracleConfig, waveforms: Sequence[torch.Tensor]) -> List[List[int]]:

@@ -48,7 +48,7 @@ def main():
     # reference: one process, whole batch, no collective (world "1": run with the process group hidden)
     ok = True
     if rank == 0:
-        ref = P.AdapterTrainer(make(), lr=1e-3, use_cuda_graph=False)
+        ref = P.AdapterTrainer(make(), lr=1e-3, use_cuda_graph=False, comm=None)
         ref.flat.allreduce = lambda: None
         import types
         def adamw_no_dist(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
@@ -61,6 +61,7 @@ def main():
         gerr = float((bucket - ref.flat.grad).norm() / ref.flat.grad.norm())
         perr = float((params - ref.flat.param).abs().max())
         lerr = abs(float(lt) - rloss) / abs(rloss)
+        print(f"collective: {'jl_comm_allreduce (C ABI)' if tr.flat.comm is not None else 'torch.distributed'}")
         print(f"world {world}: loss sum {float(lt):.4f} vs single {rloss:.4f} (rel {lerr:.2e}); bucket rel err {gerr:.2e}; param max diff {perr:.2e}")
         ok = lerr < 1e-3 and gerr < 2e-2 and perr < 1e-3
     # every rank must hold the same parameters after the step

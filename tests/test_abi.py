@@ -77,3 +77,17 @@ def test_cpu_tensors_are_rejected():
     ops = pkg().ops
     with pytest.raises(RuntimeError):
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_comm_entry_points_reject_bad_arguments_without_a_gpu():
+    """jl_comm_* argument checks (no device work): null handles / buffers give JL_EINVAL with a message; destroy(NULL) is OK."""
+    P = pkg()
+    L = P._lib
+    lib = L.load()
+    assert lib.jl_comm_destroy(None) == 0
+    assert lib.jl_comm_allreduce(None, None, 16, None) == L.JL_EINVAL
+    assert b"communicator" in lib.jl_last_error()
+    assert lib.jl_comm_unique_id(None) == L.JL_EINVAL
+    assert lib.jl_comm_rank(None, None, None) == L.JL_EINVAL
+    with pytest.raises(ValueError):
+        P.JLComm(b"short", 0, 1)

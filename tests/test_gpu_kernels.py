@@ -283,3 +283,19 @@ def test_wfadapter_fused_forward_matches_oracle(d, b, r, rows, seq, lens):
         hm = h.float().cpu()
         assert rel_err(mean, hm.mean(-1)) < 1e-3
         assert rel_err(rstd, 1.0 / torch.sqrt(hm.var(-1, unbiased=False) + ad.norm.eps)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_comm_single_rank_roundtrip():
+    """jl_comm_unique_id → jl_comm_init(world 1) → allreduce (identity on one rank) → destroy, all through the C ABI."""
+    P = pkg()
+    comm = P.JLComm(P.JLComm.unique_id(), 0, 1)
+    x = torch.arange(1000, dtype=torch.float32, device="cuda")
+    y = comm.allreduce_(x.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        comm.allreduce_(x.to(torch.bfloat16))
+    comm.destroy()
+    with pytest.raises(RuntimeError):
+        comm.allreduce_(x)

@@ -207,3 +207,67 @@ def test_transcriber_matches_module_path_and_oracle_ids():
     ref = oc.greedy_decode(logits.float().cpu(), lens.cpu(), cfg.pad_token_id)
     got = [ids[i, : int(nid[i])].cpu().tolist() for i in range(3)]
     assert got == ref
+
+
+def test_per_utterance_dialect_ids_select_wfadapter_factor_sets():
+    """K = 3 WFAdapter factor sets, ``dialect_ids`` per utterance (runs [2, 2, 0, 0]); logits, loss and
+    per-dialect adapter gradients vs the oracle; the factor set with no utterance in the batch gets exactly zero gradient;
+    the inference path (fused one-kernel adapter per run) agrees with the training path; the trainer's graph agrees too."""
+    P = pkg()
+    cfg = _small_cfg(P, adapter_attn="att", adapter_ffn="wf", num_dialects=3, wf_bottleneck=64, wf_rank=16)
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    dialects = [2, 2, 0, 0]
+    waves = [synth_wave(24000, 11), synth_wave(21000, 12), synth_wave(24000, 13), synth_wave(9000, 14)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, 10, seed=5)
+    loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda(), dialect=dialects)
+    loss.backward()
+    torch.cuda.synchronize()
+    om, w, ocfg = _oracle_setup(model, cfg)
+    for k, v in w.items():
+        v.requires_grad_(om.is_trainable(k))
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, waves, labels, dialect=dialects)
+    oloss.backward()
+    for i, t in enumerate(lens):
+        assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
+    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    for name, p in model._get_adapters().items():
+        ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
+        err = float((p.grad.float().cpu() - ref).norm())
+        assert err <= 5e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
+        if ".adapter_ffn." in name and p.dim() >= 2 and p.shape[0] == 3 and "norm" not in name:
+            assert float(p.grad[1].abs().max()) == 0.0, f"{name}: unused dialect 1 must have zero gradient"
+            assert float(p.grad[0].abs().max()) > 0.0 and float(p.grad[2].abs().max()) > 0.0
+    # a different assignment gives different logits (the ids are really used) …
+    with torch.no_grad():
+        _, logits_inf = model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=dialects)
+        _, logits_other = model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=[0, 0, 2, 2])
+    for i, t in enumerate(lens):
+        # … and the inference path (one fused kernel per run) matches the composed training path
+        assert rel_err(logits_inf[i, :t].float(), logits[i, :t].float()) < 1e-2
+        assert rel_err(logits_other[i, :t].float(), logits[i, :t].float()) > 1e-2
+    # utterances of one dialect must be adjacent
+    with pytest.raises(ValueError):
+        model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=[0, 2, 0, 2])
+    with pytest.raises(ValueError):
+        model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=[0, 0, 3, 3])
+    # trainer (flat bucket + CUDA graph keyed by the dialect runs): same gradients as the autograd path
+    ref_grads = {n: p.grad.detach().clone() for n, p in model._get_adapters().items()}
+    n = 24000
+    wave = torch.zeros((4, n))
+    ns = torch.tensor([w_.shape[0] for w_ in waves], dtype=I32)
+    for i, w_ in enumerate(waves):
+        wave[i, : w_.shape[0]] = w_
+    lab32 = labels.to(I32)
+    tr = P.AdapterTrainer(model, lr=0.0, weight_decay=0.0, use_cuda_graph=True, comm=None)
+    tl = tr.step(wave.pin_memory(), ns, lab32, dialect=dialects).item()
+    torch.cuda.synchronize()
+    assert abs(tl - float(loss)) <= 1e-3 * abs(float(loss))
+    for name, p in model._get_adapters().items():
+        got = tr.flat.out(p)
+        assert rel_err(got, ref_grads[name]) < 1e-2 or float((got - ref_grads[name]).abs().max()) < 1e-5, name
