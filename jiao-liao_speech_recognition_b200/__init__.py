@@ -14,7 +14,7 @@ All computation goes through ``libjl_b200.so`` (C ABI in ``include/jl_b200.h``);
 The directory name contains a hyphen: import it with ``importlib.import_module("jiao-liao_speech_recognition_b200")``
 or through the ``jl_b200`` alias module at the repository root.
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, hf_compat, ops, scoring  # noqa: F401
 from .comm import JLComm  # noqa: F401
 from .configuration import JLConfig  # noqa: F401
 from .feature_extraction import JLFeatureExtractor  # noqa: F401

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from . import ops
+from . import hf_compat, ops
 from .configuration import JLConfig
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
@@ -713,29 +713,46 @@ class JLForCTC(nn.Module):
             self.lm_head.bias.zero_()
 
     def save_adapter(self, path: str) -> None:
-        torch.save({n: p.detach().cpu() for n, p in self._get_adapters().items()}, path)
+        """Write the adapter + lm_head tensors: ``*.safetensors`` (HF's ``adapter.<lang>.safetensors`` format,
+        modeling_wav2vec2.py:1152-1168) or a ``torch.save`` file for any other suffix."""
+        hf_compat.write_tensor_file({n: p for n, p in self._get_adapters().items()}, path)
 
-    def load_adapter(self, path: str, strict: bool = True) -> None:
-        """Swap a per-dialect adapter state dict in place (local file only); lm_head is resized to the file's
-        vocabulary like modeling_wav2vec2.py:1230-1244."""
+    def load_adapter(self, path: str, strict: bool = True, model_dir: Optional[str] = None, dialect: int = 0) -> None:
+        """Swap a per-dialect adapter in place (local files only).  ``path`` is a file, or — with ``model_dir`` — a
+        language/dialect name resolved to ``adapter.<name>.safetensors`` / ``adapter.<name>.bin`` in that directory
+        (modeling_wav2vec2.py:1152-1225).  Files with HF's bottleneck-adapter names (``…adapter_layer.{norm,linear_1,
+        linear_2}``) load into the WFAdapter of the ``adapter_ffn`` slot (factor set ``dialect``).  lm_head is resized to
+        the file's vocabulary like modeling_wav2vec2.py:1230-1244."""
+        if model_dir is not None:
+            path = hf_compat.adapter_file(model_dir, path)
         if not os.path.isfile(path):
             raise EnvironmentError(f"adapter file {path} not found (local files only)")
-        sd = torch.load(path, map_location="cpu")
-        mine = self._get_adapters()
-        unexpected = set(sd) - set(mine)
-        missing = set(mine) - set(sd)
-        if strict and (unexpected or missing):
-            raise ValueError(f"adapter weights do not match: unexpected {sorted(unexpected)}, missing {sorted(missing)}")
+        sd = hf_compat.read_tensor_file(path)
+        hf_named = any(".adapter_layer." in k for k in sd)
         new_vocab = sd["lm_head.weight"].shape[0] if "lm_head.weight" in sd else self.config.vocab_size
         if new_vocab != self.config.vocab_size:
             dev = self.lm_head.weight.device
             self.lm_head = nn.Linear(self.config.hidden_size, new_vocab).to(dev)
             self.config.vocab_size = new_vocab
-            mine = self._get_adapters()
+        if hf_named:
+            missing, skipped = hf_compat.load_hf_state_dict(self, sd, strict=False, dialect=dialect)
+            if strict and skipped:
+                raise ValueError(f"adapter weights do not match: unexpected {sorted(skipped)}")
+            return
+        mine = self._get_adapters()
+        unexpected = set(sd) - set(mine)
+        missing = set(mine) - set(sd)
+        if strict and (unexpected or missing):
+            raise ValueError(f"adapter weights do not match: unexpected {sorted(unexpected)}, missing {sorted(missing)}")
         with torch.no_grad():
             for n, v in sd.items():
                 if n in mine:
                     mine[n].copy_(v.to(mine[n].device, mine[n].dtype))
+
+    def load_hf_state_dict(self, sd, strict: bool = False, dialect: int = 0):
+        """Load a ``Wav2Vec2ForCTC`` / ``Speech2Text`` encoder state dict by its HF names (see ``hf_compat``).
+        Returns (missing model keys, skipped checkpoint keys)."""
+        return hf_compat.load_hf_state_dict(self, sd, strict=strict, dialect=dialect)
 
     # ---- forward
     def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,

@@ -216,6 +216,11 @@ def test_per_utterance_dialect_ids_select_wfadapter_factor_sets():
     P = pkg()
     cfg = _small_cfg(P, adapter_attn="att", adapter_ffn="wf", num_dialects=3, wf_bottleneck=64, wf_rank=16)
     model = P.JLForCTC(cfg)
+    with torch.no_grad():                       # make the adapters matter: the N(0, 0.02) init leaves them near-identity
+        for layer in model.encoder.layers:
+            layer.adapter_ffn.up_A.mul_(24.0)
+            layer.adapter_ffn.down_A.mul_(8.0)
+            layer.adapter_ffn.down_B.mul_(4.0)
     round_bf16_(model)
     model = model.cuda()
     model.freeze_base_model()
@@ -249,8 +254,9 @@ def test_per_utterance_dialect_ids_select_wfadapter_factor_sets():
         _, logits_other = model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=[0, 0, 2, 2])
     for i, t in enumerate(lens):
         # … and the inference path (one fused kernel per run) matches the composed training path
-        assert rel_err(logits_inf[i, :t].float(), logits[i, :t].float()) < 1e-2
-        assert rel_err(logits_other[i, :t].float(), logits[i, :t].float()) > 1e-2
+        same = rel_err(logits_inf[i, :t].float(), logits[i, :t].float())
+        other = rel_err(logits_other[i, :t].float(), logits[i, :t].float())
+        assert same < 1e-2 and other > 3e-2 and other > 5 * same, (same, other)
     # utterances of one dialect must be adjacent
     with pytest.raises(ValueError):
         model(feats["input_features"], attention_mask=feats["attention_mask"], dialect=[0, 2, 0, 2])
