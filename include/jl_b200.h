@@ -293,6 +293,8 @@ void jl_debug_set_attn_impl(int impl);
  * (cta_group::2) kernel wherever it is legal.  Both are the product's own kernels; results are identical up to fp32
  * accumulation order. */
 void jl_debug_set_gemm_mode(int mode);
+/* test / tuning hook: force the N tile (32/64/128/256 single-CTA kernel, 128/192/256 pair kernel with mode 2); 0 = automatic */
+void jl_debug_set_gemm_bn(int bn);
 
 /* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
  * sizes the CPU oracle cannot reach; never called by the product path. */

@@ -22,11 +22,26 @@
 namespace jl {
 
 constexpr int CTC_LATTICE_HALF = 512;
-constexpr int CTC_LAT_AHEAD = 4;          // frames of log-probs kept in flight by the lattice recursion
+constexpr float TC_LOG2E_F = 1.4426950408889634f;
+constexpr float TC_LN2_F = 0.6931471805599453f;
+constexpr int CTC_LAT_AHEAD = 8;          // frames of log-probs kept in flight by the lattice recursion
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 constexpr int CTC_GRAD_THREADS = 256;
 
 struct CtcWs {
   int32_t* labels;   // [B, Smax] compacted
+  int32_t* nxt;      // [B, Smax] next position holding the same label, -1 at the end of the chain
+  int32_t* fst;      // [B, Smax] 1 where the position is the first occurrence of its label
+  int32_t* nblank;   // [B] number of labels equal to the blank index (degenerate targets)
   int32_t* tlen;     // [B]
   float* lse;        // [B*T]
   float* lpx;        // [B, T, L]
@@ -42,6 +57,9 @@ static CtcWs carve_ws(const jl_ctc_params* p, void* ws, size_t* total) {
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   CtcWs w;
   w.labels = reinterpret_cast<int32_t*>(base + off); off += align256(B * S * 4);
+  w.nxt = reinterpret_cast<int32_t*>(base + off); off += align256(B * S * 4);
+  w.fst = reinterpret_cast<int32_t*>(base + off); off += align256(B * S * 4);
+  w.nblank = reinterpret_cast<int32_t*>(base + off); off += align256(B * 4);
   w.tlen = reinterpret_cast<int32_t*>(base + off); off += align256(B * 4);
   w.lse = reinterpret_cast<float*>(base + off); off += align256(B * T * 4);
   w.lpx = reinterpret_cast<float*>(base + off); off += align256(B * T * L * 4);
@@ -51,17 +69,43 @@ static CtcWs carve_ws(const jl_ctc_params* p, void* ws, size_t* total) {
   return w;
 }
 
-__global__ void ctc_prep_kernel(const int32_t* __restrict__ labels, int smax, int vocab, int32_t* __restrict__ out_labels,
-                                int32_t* __restrict__ tlen) {
+// One CTA per utterance: compact the labels, then link repeated labels (first-occurrence flag + next-occurrence index) so
+// that the gradient kernel combines duplicates in position order with O(S) work per frame instead of O(S²).
+constexpr int CTC_PREP_THREADS = 128;
+__global__ void __launch_bounds__(CTC_PREP_THREADS) ctc_prep_kernel(const int32_t* __restrict__ labels, int smax, int vocab, int blank,
+                                                                    int32_t* __restrict__ out_labels, int32_t* __restrict__ nxt,
+                                                                    int32_t* __restrict__ fst, int32_t* __restrict__ nblank,
+                                                                    int32_t* __restrict__ tlen) {
   jl::pdl_prologue();
+  __shared__ int s_n;
   const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  int n = 0;
-  for (int j = 0; j < smax; ++j) {
-    const int v = labels[static_cast<int64_t>(b) * smax + j];
-    if (v >= 0) out_labels[static_cast<int64_t>(b) * smax + n++] = min(v, vocab - 1);   // range is validated on the host
+  int32_t* lab = out_labels + static_cast<int64_t>(b) * smax;
+  if (threadIdx.x == 0) {
+    int n = 0, nb = 0;
+    for (int j = 0; j < smax; ++j) {
+      const int v = labels[static_cast<int64_t>(b) * smax + j];
+      if (v >= 0) {
+        const int c = min(v, vocab - 1);   // range is validated on the host
+        lab[n++] = c;
+        nb += (c == blank);
+      }
+    }
+    tlen[b] = n;
+    nblank[b] = nb;
+    s_n = n;
   }
-  tlen[b] = n;
+  __syncthreads();
+  const int n = s_n;
+  for (int j = threadIdx.x; j < n; j += CTC_PREP_THREADS) {
+    const int c = lab[j];
+    int first = 1, next = -1;
+    for (int i = 0; i < j; ++i)
+      if (lab[i] == c) { first = 0; break; }
+    for (int i = j + 1; i < n; ++i)
+      if (lab[i] == c) { next = i; break; }
+    fst[static_cast<int64_t>(b) * smax + j] = first;
+    nxt[static_cast<int64_t>(b) * smax + j] = next;
+  }
 }
 
 template <typename T>
@@ -165,9 +209,27 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
+// log(e^a + e^b + e^c) for the lattice recursion with one MUFU per exp / log (ex2.approx, lg2.approx).  The values are
+// log-probabilities of magnitude 10²–10³ whose fp32 spacing (≈ 6e-5) is far coarser than the 2⁻²² error of the
+// approximations, so the recursion's accuracy is unchanged; the recursion is serial, and its step time is the length of
+// this dependent instruction chain.
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float ms = (m == -CUDART_INF_F) ? 0.0f : m;          // differences first: (x - m) is exact or nearly so, x·log2e - m·log2e is not
+  float ea, eb, ec, lg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"((a - ms) * TC_LOG2E_F));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"((b - ms) * TC_LOG2E_F));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ec) : "f"((c - ms) * TC_LOG2E_F));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ea + eb + ec));
+  return (m == -CUDART_INF_F) ? -CUDART_INF_F : fmaf(lg, TC_LN2_F, m);
+}
+
 // One CTA per (utterance, direction): blockIdx.y = 0 runs the alpha recursion forward in time, blockIdx.y = 1 the beta
-// recursion backward.  The recursion is serial in t and issue-bound on its SM (≈ 200 instructions per state and frame),
-// so the two directions of an utterance run on different SMs.
+// recursion backward, so the two directions of an utterance run on different SMs.  The recursion is serial in t and its
+// step time is the dependent instruction chain of one state update (few warps per SM: nothing hides ALU latency), so
+// the common case — every thread owns one state (SINGLE) — keeps its neighbour indices, the skip-transition predicate and
+// all pointers in registers and does no per-step index arithmetic.
+template <bool SINGLE>
 __global__ void __launch_bounds__(CTC_LATTICE_HALF) ctc_lattice_kernel(const int32_t* __restrict__ labels, int smax,
                                                                        const int32_t* __restrict__ tlen,
                                                                        const int32_t* __restrict__ lengths, int seq, int blank,
@@ -183,6 +245,7 @@ __global__ void __launch_bounds__(CTC_LATTICE_HALF) ctc_lattice_kernel(const int
   const int T = min(lengths[b], seq);
   float* buf = lat_smem;                                      // [2][Lmax]
   int* ext = reinterpret_cast<int*>(lat_smem + 2 * Lmax);     // [Lmax]
+  float* lpring = lat_smem + 3 * Lmax;                        // [CTC_LAT_AHEAD][Lmax]
   const int nthr = blockDim.x;                                // the host sizes the CTA to the longest extended label sequence
   const int gtid = threadIdx.x;
   for (int s = gtid; s < L; s += nthr) ext[s] = (s & 1) ? labels[static_cast<int64_t>(b) * smax + (s >> 1)] : blank;
@@ -192,7 +255,7 @@ __global__ void __launch_bounds__(CTC_LATTICE_HALF) ctc_lattice_kernel(const int
     return;
   }
   const int64_t base = static_cast<int64_t>(b) * seq * Lmax;
-  const int64_t dir = is_beta ? -static_cast<int64_t>(Lmax) : static_cast<int64_t>(Lmax);    // one frame along the recursion
+  const int dir = is_beta ? -Lmax : Lmax;                     // one frame along the recursion (elements)
   const int t_first = is_beta ? T - 1 : 0;
   const float* lp_row = lpx + base + static_cast<int64_t>(t_first) * Lmax;      // row of the current frame
   float* out_row = (is_beta ? beta : alpha) + base + static_cast<int64_t>(t_first) * Lmax;
@@ -209,34 +272,72 @@ __global__ void __launch_bounds__(CTC_LATTICE_HALF) ctc_lattice_kernel(const int
     out_row[s] = v;
   }
   __syncthreads();
-  // A global load issued one step ahead would still expose most of its latency, so the log-probs of the next
-  // CTC_LAT_AHEAD frames are kept in flight in registers.
-  float ring[CTC_LAT_AHEAD];
-#pragma unroll
-  for (int u = 0; u < CTC_LAT_AHEAD; ++u) ring[u] = (1 + u < T && gtid < L) ? __ldg(lp_row + (1 + u) * dir + gtid) : 0.0f;
-  // neighbour offsets and the skip-transition predicate of this thread's first state do not depend on t
-  const int nb = is_beta ? 1 : -1;
-  for (int step0 = 1; step0 < T; step0 += CTC_LAT_AHEAD) {
-#pragma unroll
-    for (int u = 0; u < CTC_LAT_AHEAD; ++u) {
-      const int step = step0 + u;
-      if (step >= T) break;                                   // uniform over the CTA
+  // A frame's log-probs must already be on the SM when its step starts: they are streamed into a shared-memory ring
+  // CTC_LAT_AHEAD frames ahead with cp.async (each thread copies exactly the elements it will read itself, so its own
+  // wait_group is the only synchronisation the ring needs).
+#pragma unroll 1
+  for (int u = 0; u < CTC_LAT_AHEAD; ++u) {
+    if (1 + u < T)
+      for (int s = gtid; s < L; s += nthr) cp_async_f32(lpring + u * Lmax + s, lp_row + (1 + u) * dir + s);
+    cp_async_commit();
+  }
+  const int nb = is_beta ? 1 : -1;                            // neighbour offset along the recursion
+
+  if constexpr (SINGLE) {
+    const int s = gtid;
+    const bool active = s < L;
+    const int s1 = s + nb, s2 = s + 2 * nb;
+    const bool has1 = active && s1 >= 0 && s1 < L;
+    const bool has2 = active && s2 >= 0 && s2 < L && (s & 1) && ext[s] != ext[s2];
+    // shared-memory byte addresses of this thread's cells in the two row buffers and in the ring
+    const float* p0 = buf + s;
+    const float* p1 = buf + (has1 ? s1 : s);
+    const float* p2 = buf + (has2 ? s2 : s);
+    const float* lp_src = lp_row + CTC_LAT_AHEAD * dir + s;   // + dir per step → row (step + AHEAD)
+    float* out_ptr = out_row + s;
+    int slot = 0, par = 0;                                     // par: buffer holding the previous row
+    for (int step = 1; step < T; ++step) {
+      lp_src += dir;
+      out_ptr += dir;
+      cp_async_wait<CTC_LAT_AHEAD - 1>();
+      if (active) {
+        const int po = par * Lmax;
+        const float x0 = p0[po];
+        const float x1 = has1 ? p1[po] : -CUDART_INF_F;
+        const float x2 = has2 ? p2[po] : -CUDART_INF_F;
+        float* lps = lpring + slot * Lmax + s;
+        const float v = lse3_fast(x0, x1, x2) + *lps;
+        buf[(par ^ 1) * Lmax + s] = v;
+        *out_ptr = v;
+        if (step + CTC_LAT_AHEAD < T) cp_async_f32(lps, lp_src);
+      }
+      cp_async_commit();
+      slot = (slot + 1 == CTC_LAT_AHEAD) ? 0 : slot + 1;
+      par ^= 1;
+      __syncthreads();
+    }
+  } else {
+    int slot = 0;
+    for (int step = 1; step < T; ++step) {
       lp_row += dir;
       out_row += dir;
       const float* prev = buf + ((step - 1) & 1) * Lmax;
       float* cur = buf + (step & 1) * Lmax;
-      const float lp_first = ring[u];
-      if (step + CTC_LAT_AHEAD < T && gtid < L) ring[u] = __ldg(lp_row + CTC_LAT_AHEAD * dir + gtid);
+      float* lps = lpring + slot * Lmax;
+      cp_async_wait<CTC_LAT_AHEAD - 1>();                     // this step's frame has landed (groups complete in order)
       for (int s = gtid; s < L; s += nthr) {
-        const float lp = (s == gtid) ? lp_first : lp_row[s];
         const int s1 = s + nb, s2 = s + 2 * nb;
         float x0 = prev[s], x1 = -CUDART_INF_F, x2 = -CUDART_INF_F;
         if (s1 >= 0 && s1 < L) x1 = prev[s1];
         if (s2 >= 0 && s2 < L && (s & 1) && ext[s] != ext[s2]) x2 = prev[s2];
-        const float v = lse3(x0, x1, x2) + lp;
+        const float v = lse3_fast(x0, x1, x2) + lps[s];
         cur[s] = v;
         out_row[s] = v;
       }
+      if (step + CTC_LAT_AHEAD < T)                           // refill the slot just consumed (same thread, same elements)
+        for (int s = gtid; s < L; s += nthr) cp_async_f32(lps + s, lp_row + CTC_LAT_AHEAD * dir + s);
+      cp_async_commit();
+      slot = (slot + 1 == CTC_LAT_AHEAD) ? 0 : slot + 1;
       __syncthreads();
     }
   }
@@ -259,8 +360,9 @@ __device__ __forceinline__ void st_grad<__nv_bfloat16>(__nv_bfloat16* p, int64_t
 template <typename T, typename TG>
 __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __restrict__ logits, int64_t ld, TG* __restrict__ grad, int64_t ldg,
                                                                    int seq, int vocab, int batch, const int32_t* __restrict__ lengths,
-                                                                   const int32_t* __restrict__ labels, int smax,
-                                                                   const int32_t* __restrict__ tlen, int blank,
+                                                                   const int32_t* __restrict__ labels, const int32_t* __restrict__ nxt,
+                                                                   const int32_t* __restrict__ fst, const int32_t* __restrict__ nblank,
+                                                                   int smax, const int32_t* __restrict__ tlen, int blank,
                                                                    const float* __restrict__ lse_all, const float* __restrict__ lpx,
                                                                    const float* __restrict__ alpha, const float* __restrict__ beta,
                                                                    const float* __restrict__ nll, int reduction, int zero_infinity) {
@@ -309,7 +411,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
         a[0] = f0.x; a[1] = f0.y; a[2] = f1.x; a[3] = f1.y;
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = expf(a[e] - lse) * scale;
+      for (int e = 0; e < 4; ++e) a[e] = __expf(a[e] - lse) * scale;     // arguments <= 0; 2-ulp ex2.approx is far inside the tolerance
       if constexpr (sizeof(TG) == 4) {
         reinterpret_cast<float4*>(g)[i] = make_float4(a[0], a[1], a[2], a[3]);
       } else {
@@ -331,23 +433,22 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
     if (tid == 0) blank_part[0] = part;
   }
   __syncthreads();   // also orders the softmax row writes before the fix-ups below
-  // non-blank labels: the first occurrence of each label owns the (ordered) sum over its repeats
-  for (int s = 2 * tid + 1; s < L; s += 2 * CTC_GRAD_THREADS) {
-    const int c = labels[static_cast<int64_t>(b) * smax + (s >> 1)];
-    bool first = true;
-    for (int s2 = 1; s2 < s; s2 += 2)
-      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == c) { first = false; break; }
-    if (!first || c == blank) continue;
+  // non-blank labels: the first occurrence of each label owns the sum over its repeats, taken in position order along the
+  // chain ctc_prep linked (deterministic; one writer per vocabulary column)
+  const int64_t lrow = static_cast<int64_t>(b) * smax;
+  for (int j = tid; j < S; j += CTC_GRAD_THREADS) {
+    const int c = labels[lrow + j];
+    if (!fst[lrow + j] || c == blank) continue;
     float tot = 0.0f;
-    for (int s2 = s; s2 < L; s2 += 2)
-      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == c) tot += occ[s2];
+    for (int jj = j; jj >= 0; jj = nxt[lrow + jj]) tot += occ[2 * jj + 1];
     st_grad<TG>(g, c, (expf(ld_logit<T>(x, c) - lse) - tot) * scale);
   }
   if (tid == 0) {
     // a label equal to the blank index folds into the blank column (degenerate but well defined)
     float tot = blank_part[0];
-    for (int s2 = 1; s2 < L; s2 += 2)
-      if (labels[static_cast<int64_t>(b) * smax + (s2 >> 1)] == blank) tot += occ[s2];
+    if (nblank[b] > 0)
+      for (int s2 = 1; s2 < L; s2 += 2)
+        if (labels[lrow + (s2 >> 1)] == blank) tot += occ[s2];
     st_grad<TG>(g, blank, (expf(ld_logit<T>(x, blank) - lse) - tot) * scale);
   }
 }
@@ -430,7 +531,8 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
   const int rows = p->batch * p->seq;
 
   if (p->max_label_len > 0) {
-    jl::launch(jl::ctc_prep_kernel, p->batch, 32, 0, s, p->labels, smax, p->vocab, w.labels, w.tlen);
+    jl::launch(jl::ctc_prep_kernel, p->batch, jl::CTC_PREP_THREADS, 0, s, p->labels, smax, p->vocab, p->blank, w.labels, w.nxt, w.fst, w.nblank,
+               w.tlen);
     JL_CHECK_LAUNCH("ctc_prep");
   } else {
     cudaMemsetAsync(w.tlen, 0, sizeof(int32_t) * p->batch, s);
@@ -444,21 +546,24 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
                                                                    p->vocab, p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen,
                                                                    p->blank, w.lpx);
   JL_CHECK_LAUNCH("ctc_row_stats");
-  const size_t lat_smem = static_cast<size_t>(3) * Lmax * sizeof(float);
+  const size_t lat_smem = static_cast<size_t>(3 + jl::CTC_LAT_AHEAD) * Lmax * sizeof(float);
+  const bool lat_single = Lmax <= jl::CTC_LATTICE_HALF;       // every thread owns one state of the extended label sequence
+  auto lat_kernel = lat_single ? jl::ctc_lattice_kernel<true> : jl::ctc_lattice_kernel<false>;
   if (lat_smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(jl::ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lat_smem));
+    cudaError_t e = cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lat_smem));
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "ctc: cannot reserve lattice shared memory: %s", cudaGetErrorString(e));
   }
   const int lat_half = std::min(jl::CTC_LATTICE_HALF, ((2 * smax + 1 + 31) / 32) * 32);
-  jl::launch(jl::ctc_lattice_kernel, dim3(p->batch, 2), lat_half, lat_smem, s, w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
-                                                                            w.alpha, w.beta, p->nll);
+  jl::launch(lat_kernel, dim3(p->batch, 2), lat_half, lat_smem, s, w.labels, smax, w.tlen, p->input_lengths, p->seq, p->blank, w.lpx,
+             w.alpha, w.beta, p->nll);
   JL_CHECK_LAUNCH("ctc_lattice");
   if (p->grad != nullptr) {
     const size_t gsm = static_cast<size_t>(Lmax + 32) * sizeof(float);
 #define JL_CTC_GRAD(TL, TGR)                                                                                                           \
   jl::launch(jl::ctc_grad_kernel<TL, TGR>, rows, jl::CTC_GRAD_THREADS, gsm, s, reinterpret_cast<const TL*>(p->logits), p->ld_logits,              \
                                                                         reinterpret_cast<TGR*>(p->grad), p->ld_grad, p->seq, p->vocab,   \
-                                                                        p->batch, p->input_lengths, w.labels, smax, w.tlen, p->blank,    \
+                                                                        p->batch, p->input_lengths, w.labels, w.nxt, w.fst, w.nblank,    \
+                                                                        smax, w.tlen, p->blank,                                          \
                                                                         w.lse, w.lpx, w.alpha, w.beta, p->nll, p->reduction,             \
                                                                         p->zero_infinity)
     if (p->logits_dtype == JL_DT_F32 && p->grad_dtype == JL_DT_F32) JL_CTC_GRAD(float, float);
