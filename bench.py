@@ -188,8 +188,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P = importlib.import_module(PKG)
-    if os.environ.get("JL_PDL") == "1":            # tuning aid: programmatic dependent launch (measured slower, off by default)
-        P._lib.load().jl_debug_set_pdl(1)
+    if os.environ.get("JL_PDL") in ("0", "1"):     # tuning aid: programmatic dependent launch off / on (default: on)
+        P._lib.load().jl_debug_set_pdl(int(os.environ["JL_PDL"]))
     cfg = P.JLConfig.base(adapter_ffn="att")
     model = P.JLForCTC(cfg).cuda()
     model.freeze_base_model()

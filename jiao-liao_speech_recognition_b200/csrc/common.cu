@@ -41,7 +41,7 @@ int check_device() {
   return JL_OK;
 }
 
-int g_use_pdl = 0;   // measured on B200 (profiles/): PDL edges made the 383-kernel step 4.8 % slower (7.89 vs 7.53 ms) — early CTAs of kernel N+1 sit on SM resources kernel N still needs — so plain stream order is the default
+int g_use_pdl = 1;   // measured on B200 (profiles/README.md): programmatic edges with the trigger at the END of a CTA's loads make the 383-kernel step 5 % faster (6.85 vs 7.22 ms); a trigger at CTA start made it 4.8 % slower
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;

@@ -38,7 +38,24 @@ int make_tma_map_2d_bf16(CUtensorMap* map, const void* ptr, int64_t inner, int64
 // Programmatic dependent launch: every kernel is launched with programmatic stream serialisation, lets its successor start
 // launching at once, and waits for its predecessor's memory before touching global data.  The launch latency and CTA ramp of
 // kernel N+1 then overlap the tail of kernel N (≈ 380 launches per fine-tune step).
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef JL_PDL_EARLY_TRIGGER
+#define JL_PDL_EARLY_TRIGGER 0   // 1: let the dependent grid launch as soon as every CTA has started (measured slower); 0: at CTA exit
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if JL_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// Late trigger: issued once a CTA has requested its last operand tile, so the dependent grid's launch overlaps the tail
+// (last MMAs + epilogue) of this one.  Compile with -DJL_PDL_LATE_TRIGGER=0 to leave the trigger to CTA exit.
+#ifndef JL_PDL_LATE_TRIGGER
+#define JL_PDL_LATE_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_trigger_late() {
+#if JL_PDL_LATE_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
   pdl_launch_dependents();

@@ -356,6 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      jl::pdl_trigger_late();      // all operand loads requested: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -559,6 +560,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      jl::pdl_trigger_late();      // all operand loads requested: the next kernel may start launching
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
