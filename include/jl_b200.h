@@ -108,13 +108,20 @@ typedef struct {
   int32_t epilogue;
   int32_t out_dtype;                 /* JL_DT_BF16 | JL_DT_F32 */
   float alpha;
-  void* workspace;                   /* optional split-K scratch (jl_gemm_workspace_bytes); NULL = no split-K */
+  void* workspace;                   /* optional K-split scratch (jl_gemm_workspace_bytes), 256-byte aligned; NULL = never split */
   int64_t workspace_bytes;
 } jl_gemm_params;
 int jl_gemm_bf16(const jl_gemm_params* p, void* stream);
-/* bytes of split-K scratch this product would use (0 when it runs unsplit): plain products (no bias / activation /
- * residual) whose output tiles cannot fill the SMs and whose K is long — the weight-gradient shapes dYᵀ·X */
+/* Bytes of scratch this product would use, 0 when it runs unsplit.  Two uses:
+ *  - split-K: plain products (no bias / activation / residual) whose output tiles cannot fill the SMs and whose K is long —
+ *    the weight-gradient shapes dYᵀ·X; partials are reduced in fixed order by a second launch;
+ *  - tail split: any product on the CTA-pair kernel whose last wave of 256-row tiles is partial — those tiles are cut into
+ *    K ranges that run on the otherwise idle pairs; the last range to arrive adds the partials in range order and applies
+ *    the epilogue inside the same launch (no CTA waits for another).  Its arrival counters live in the first
+ *    jl_gemm_workspace_zero_bytes() bytes of the workspace, which must be ZERO on entry and are left zero; a workspace must
+ *    not be shared by products that may run concurrently (one per stream). */
 int jl_gemm_workspace_bytes(const jl_gemm_params* p, size_t* out);
+int jl_gemm_workspace_zero_bytes(const jl_gemm_params* p, size_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (eps 1e-5).  Replaces nn.LayerNorm at
@@ -295,6 +302,8 @@ void jl_debug_set_attn_impl(int impl);
 void jl_debug_set_gemm_mode(int mode);
 /* test / tuning hook: force the N tile (32/64/128/256 single-CTA kernel, 128/192/256 pair kernel with mode 2); 0 = automatic */
 void jl_debug_set_gemm_bn(int bn);
+/* test / tuning hook: 0 = never split the tail wave of the pair kernel, 1 (default) = split it when a workspace is supplied */
+void jl_debug_set_gemm_tail(int on);
 
 /* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
  * sizes the CPU oracle cannot reach; never called by the product path. */

@@ -95,6 +95,8 @@ SYMBOLS = {
     "jl_debug_gemm_ref": (C.c_int, [C.POINTER(GemmParams), vp]),
     "jl_debug_set_gemm_mode": (None, [C.c_int]),
     "jl_debug_set_gemm_bn": (None, [C.c_int]),
+    "jl_debug_set_gemm_tail": (None, [C.c_int]),
+    "jl_gemm_workspace_zero_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),
     "jl_debug_set_attn_impl": (None, [C.c_int]),
     "jl_debug_set_pdl": (None, [C.c_int]),
     "jl_gemm_workspace_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),

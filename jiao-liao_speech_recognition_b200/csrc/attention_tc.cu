@@ -122,23 +122,13 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                    const jl_attn_fwd_params p) {
-  jl::pdl_prologue();   // `lengths` may be produced by the preceding kernel: wait before the first global read
+  // Everything up to griddepcontrol.wait touches no global memory, so under programmatic dependent launch it overlaps the
+  // tail of the preceding kernel: barrier init, tensor-map prefetch, TMEM allocation.
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_OUTER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
-  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
-  if (q0 >= len) {   // the whole query tile is padding
-    tc_zero_rows(o, p.ld_o, q0, p.seq);
-    if (lse && threadIdx.x < TC_OUTER && q0 + threadIdx.x < p.seq) lse[q0 + threadIdx.x] = 0.0f;
-    return;
-  }
   extern __shared__ uint8_t tc_smem_raw[];
   AttnFwdSmem& s = *reinterpret_cast<AttnFwdSmem*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
   TcBars& B = s.bars;
-  const int nkb = (len + TC_INNER - 1) / TC_INNER;
-
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tq);
     ptx::prefetch_tensormap(&tk);
@@ -156,8 +146,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     ptx::mbar_init(&B.acc_done, 1);
     ptx::fence_barrier_init();
   }
-  // 128 TMEM columns (64 scores + 64 output) and 65 KB of shared memory per CTA → three CTAs per SM: the score rows are
-  // pulled into registers with a single wait and the buffer is released at once, so S_{j+1} still overlaps softmax_j.
+  // 128 TMEM columns (64 scores + 64 output) per CTA: the score rows are pulled into registers with a single wait and the
+  // buffer is released at once, so S_{j+1} still overlaps softmax_j.
   if (warp == 2) {
     ptx::tmem_alloc(&B.tmem_slot, 128);
     ptx::tmem_relinquish();
@@ -165,12 +155,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  jl::pdl_prologue();   // `lengths`, q, k, v may be produced by the preceding kernel: wait before the first global access
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
+  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
+  const int nkb = (len + TC_INNER - 1) / TC_INNER;
+  const bool skip = q0 >= len;          // the whole query tile is padding
+  if (skip) {
+    tc_zero_rows(o, p.ld_o, q0, p.seq);
+    if (lse && threadIdx.x < TC_OUTER && q0 + threadIdx.x < p.seq) lse[q0 + threadIdx.x] = 0.0f;
+  }
   const uint32_t tmem = B.tmem_slot;
   const uint32_t t_s[2] = {tmem, tmem};
   const uint32_t t_o = tmem + 64;
   const int grow = static_cast<int>(row_base);        // row of the utterance's first frame in the [B·T, ld] matrices
 
-  if (warp == 0) {
+  if (skip) {
+    // nothing to compute
+  } else if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_expect_tx(&B.x_full, TC_T128);
       ptx::tma_load_2d(s.q, &tq, &B.x_full, h * 64, grow + q0);
@@ -321,26 +324,12 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constant__ CUtensorMap tx2, const __grid_constant__ CUtensorMap ty1,
                    const __grid_constant__ CUtensorMap ty2, const jl_attn_bwd_params p) {
-  jl::pdl_prologue();   // `lengths` may be produced by the preceding kernel: wait before the first global read
+  // As in the forward kernel, the set-up below needs no global memory and overlaps the preceding kernel's tail (PDL).
   const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * TC_OUTER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
-  const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
-  float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
-  __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(MODE == 0 ? p.dq : p.dv) + row_base * p.ld_dqkv + h * 64;
-  __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
-  if (r0 >= len) {
-    tc_zero_rows(out0, p.ld_dqkv, r0, p.seq);
-    if (MODE == 1) tc_zero_rows(out1, p.ld_dqkv, r0, p.seq);
-    if (MODE == 0 && threadIdx.x < TC_OUTER && r0 + threadIdx.x < p.seq) delta[r0 + threadIdx.x] = 0.0f;
-    return;
-  }
   extern __shared__ uint8_t tc_smem_raw[];
   AttnBwdSmem<MODE>& s = *reinterpret_cast<AttnBwdSmem<MODE>*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
   TcBars& B = s.bars;
-  const int nib = (len + TC_INNER - 1) / TC_INNER;
-
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tx1);
     ptx::prefetch_tensormap(&tx2);
@@ -366,11 +355,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  jl::pdl_prologue();   // `lengths` and every operand may be produced by the preceding kernel: wait before the first global access
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(MODE == 0 ? p.dq : p.dv) + row_base * p.ld_dqkv + h * 64;
+  __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
+  const int nib = (len + TC_INNER - 1) / TC_INNER;
+  const bool skip = r0 >= len;          // the whole outer tile is padding
+  if (skip) {
+    tc_zero_rows(out0, p.ld_dqkv, r0, p.seq);
+    if (MODE == 1) tc_zero_rows(out1, p.ld_dqkv, r0, p.seq);
+    if (MODE == 0 && threadIdx.x < TC_OUTER && r0 + threadIdx.x < p.seq) delta[r0 + threadIdx.x] = 0.0f;
+  }
   const uint32_t tmem = B.tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_acc0 = tmem + 128, t_acc1 = tmem + 192;
   const int grow = static_cast<int>(row_base);
 
-  if (warp == 0) {
+  if (skip) {
+    // nothing to compute
+  } else if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_expect_tx(&B.x_full, 2 * TC_T128);
       ptx::tma_load_2d(s.x1, &tx1, &B.x_full, h * 64, grow + r0);

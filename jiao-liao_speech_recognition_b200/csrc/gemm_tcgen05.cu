@@ -53,7 +53,37 @@ struct GemmDev {
   int32_t split_k, kb_per_split;
   float* ws;
   int64_t ldw;
+  // tail split (pair kernel): tiles [tail_first, num_tiles) are the partial last wave; each is cut into tail_split K ranges that
+  // run on otherwise idle CTA pairs, raw partial accumulators go to tail_ws and the LAST range to arrive (per epilogue warp,
+  // counted in tail_cnt) adds them in range order and applies the epilogue — no CTA ever waits for another one.
+  int32_t tail_first, tail_split, tail_kb_per;
+  int64_t tail_stride;     // floats per K range in tail_ws = tail tiles · 256 · BN
+  float* tail_ws;
+  int32_t* tail_cnt;
 };
+
+// One schedulable piece of the pair kernel: a whole output tile, or one K range of a tail tile.
+struct PairUnit {
+  int tile, kb0, kb1, sidx;
+  bool split;
+};
+__device__ __forceinline__ int pair_num_units(const GemmDev& g, int num_tiles) {
+  return g.tail_first + (num_tiles - g.tail_first) * g.tail_split;
+}
+__device__ __forceinline__ PairUnit pair_unit(const GemmDev& g, int u, int num_kb) {
+  PairUnit r;
+  if (u < g.tail_first) {
+    r.tile = u; r.kb0 = 0; r.kb1 = num_kb; r.sidx = 0; r.split = false;
+  } else {
+    const int v = u - g.tail_first;
+    r.tile = g.tail_first + v / g.tail_split;
+    r.sidx = v - (r.tile - g.tail_first) * g.tail_split;
+    r.kb0 = r.sidx * g.tail_kb_per;
+    r.kb1 = min(num_kb, r.kb0 + g.tail_kb_per);
+    r.split = g.tail_split > 1;
+  }
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue for one row × 32 consecutive accumulator columns (shared by the tcgen05 kernel and the
@@ -448,6 +478,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // against 85 for the single-CTA 128 × 256 tile — which is what lifts the L2 → SM operand traffic (≈ 6.3 kB/clk chip-wide)
 // out of the way of the tensor pipe.
 // ------------------------------------------------------------------------------------------------
+// K range of a tail tile (pair kernel): publish the raw fp32 partial, count the arrival, and — in the warp that arrives last for
+// its slice — add the partials in range order and apply the epilogue.  Only compiled into the TAIL instantiation of the pair
+// kernel so that its registers stay out of the default one (nvcc 12.9 crashes on a __noinline__ function holding tcgen05.ld).
+template <int BN>
+__device__ __forceinline__ void pair_tail_unit(const GemmDev& g, const PairUnit& un, uint32_t tmem_base, int as, int quad, int half, int lane, int warp,
+                                            int rank, uint32_t leader_tempty, int row, int n0) {
+  const int tile = un.tile;
+  // ---- K range of a tail tile: publish the raw partial, then the last range to arrive (per warp slice) finishes the tile
+  const int tidx = tile - g.tail_first;
+  const int64_t slice_rows = (static_cast<int64_t>(tidx) * 2 + rank) * GEMM_BM + quad * 32 + lane;       // row slot of this thread
+  const int64_t range_stride = g.tail_stride;                                                            // floats per K range
+  float* mine = g.tail_ws + static_cast<int64_t>(un.sidx) * range_stride + slice_rows * BN;
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32), v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = v[8 * i + j];
+      st_global_v8(mine + c * 32 + 8 * i, w);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty + static_cast<uint32_t>(as * 8));   // accumulator stage free
+  __threadfence();                                                                            // partial visible before it is counted
+  __syncwarp();
+  int32_t* cnt = g.tail_cnt + (tidx * 2 + rank) * GEMM_EPI_WARPS + (warp - 4);
+  int arrived = 0;
+  if (lane == 0) arrived = atomicAdd(cnt, 1);
+  arrived = __shfl_sync(0xffffffffu, arrived, 0);
+  if (arrived == g.tail_split - 1) {
+    __threadfence();
+    const float* base = g.tail_ws + slice_rows * BN;
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
+      EpiPrefetch pf;
+      epi_prefetch(g, row, n0 + c * 32, pf);
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+      for (int sp = 0; sp < g.tail_split; ++sp) {            // fixed order → bit-reproducible
+        const float4* src = reinterpret_cast<const float4*>(base + static_cast<int64_t>(sp) * range_stride + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = __ldcg(src + i);                  // L2: written by other SMs during this launch
+          acc[4 * i + 0] += q.x; acc[4 * i + 1] += q.y; acc[4 * i + 2] += q.z; acc[4 * i + 3] += q.w;
+        }
+      }
+      gemm_epilogue_row32(g, row, n0 + c * 32, acc, pf);
+    }
+    __syncwarp();
+    if (lane == 0) *cnt = 0;                                 // leave the counters zero for the next launch
+  }
+}
+
 template <int BN, int STAGES>
 struct GemmSmem2 {
   static constexpr int BNH = BN / 2;
@@ -460,7 +549,7 @@ struct GemmSmem2 {
 // PAIRS = 2: a cluster of four CTAs = two MMA pairs that share the same N tile (rows m0 … m0+511).  Each CTA fetches only a
 // quarter of the B tile and TMA-multicasts it to the CTA at the same position of the other pair, so a k-block moves
 // 4·16 KB of A + BN·128 B of B for 512 × BN × 64 MACs (175 FLOP/B at BN = 256 instead of 128).
-template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS, bool TAIL = false>
 __global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
   jl::pdl_launch_dependents();
@@ -494,6 +583,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int num_pairs = gridDim.x / (2 * PAIRS);
   const int num_tiles = g.num_m_tiles * g.num_n_tiles;          // (256·PAIRS) × BN tiles
   const int num_kb = (g.k + GEMM_BK - 1) / GEMM_BK;
+  const int num_units = pair_num_units(g, num_tiles);           // whole tiles + K ranges of the tail tiles
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
@@ -525,11 +615,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = pair; u < num_units; u += num_pairs) {
+        const PairUnit un = pair_unit(g, u, num_kb);
+        const int tile = un.tile;
         const int m0 = (tile / g.num_n_tiles) * (256 * PAIRS) + static_cast<int>(pic) * 256 + static_cast<int>(rank) * GEMM_BM;
         const int n0 = (tile % g.num_n_tiles) * BN + static_cast<int>(rank) * BNH + static_cast<int>(pic) * BQ * (PAIRS - 1);
         const uint16_t bmask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));   // same pair position in both pairs
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = un.kb0; kb < un.kb1; ++kb) {
           ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
           if (leader) ptx::mbar_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);
           const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(full_bar + stage), leader_rank);
@@ -569,13 +661,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int u = pair; u < num_units; u += num_pairs, ++it) {
+        const PairUnit un = pair_unit(g, u, num_kb);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar + as, aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = un.kb0; kb < un.kb1; ++kb) {
           ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(s_a + stage * GEMM_A_BYTES);
@@ -584,7 +677,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = A_MN ? ptx::make_sw128_desc(a_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? ptx::make_sw128_desc(b_addr + k * 2048, 8192, 1024) : ptx::make_sw128_desc(b_addr + k * 32, 16, 1024);
-            ptx::umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_2sm(d_tmem, da, db, idesc, (kb != un.kb0 || k != 0) ? 1u : 0u);
           }
           ptx::umma_commit_2sm(empty_bar + stage, PAIRS == 1 ? 0x3 : 0xF);   // every CTA that writes into these slots
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -598,7 +691,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     const int half = (warp - 4) >> 2;
     const uint32_t leader_tempty = ptx::mapa_shared(ptx::smem_u32(tempty_bar), leader_rank);
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    for (int u = pair; u < num_units; u += num_pairs, ++it) {
+      const PairUnit un = pair_unit(g, u, num_kb);
+      const int tile = un.tile;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / g.num_n_tiles) * (256 * PAIRS) + static_cast<int>(pic) * 256 + static_cast<int>(rank) * GEMM_BM;
@@ -606,6 +701,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       ptx::mbar_wait(tfull_bar + as, aphase);
       ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
+      if (TAIL && un.split) {
+        pair_tail_unit<BN>(g, un, tmem_base, as, quad, half, lane, warp, static_cast<int>(rank), leader_tempty, row, n0);
+        continue;
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
         uint32_t v[32];
@@ -744,6 +843,7 @@ static size_t splitk_ws_bytes(const jl_gemm_params* p) {
 static GemmDev to_dev(const jl_gemm_params* p, int bn) {
   GemmDev g;
   g.split_k = 1; g.kb_per_split = ceil_div(p->k, GEMM_BK); g.ws = nullptr; g.ldw = 0;
+  g.tail_first = 0; g.tail_split = 1; g.tail_kb_per = g.kb_per_split; g.tail_stride = 0; g.tail_ws = nullptr; g.tail_cnt = nullptr;
   g.c = p->c; g.ldc = p->ldc;
   g.bias = p->bias;
   g.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual); g.ldr = p->ldr;
@@ -815,6 +915,7 @@ static int dispatch_layout(const jl_gemm_params* p, cudaStream_t s) {
 }
 
 // Pick the N tile: fewest (waves × per-tile cost) over the candidates; per-tile cost ∝ BN plus a fixed part.
+static std::atomic<int> g_gemm_tail{0};   // 1 = split the tail wave of the pair kernel when a workspace is supplied; off by default: measured slower
 static std::atomic<int> g_gemm_bn{0};     // tuning hook: 0 = automatic N tile, else the N tile forced on the kernel the mode selects
 static int pick_bn(const jl_gemm_params* p) {
   const bool bmn = p->b_layout == JL_LAYOUT_MN;
@@ -824,6 +925,7 @@ static int pick_bn(const jl_gemm_params* p) {
   if (p->n <= 64) return 64;
   if (p->k <= GEMM_BK && p->m >= 1024) return 64;      // one k-block: epilogue-bound, small tiles spread it over all SMs
   if (p->n <= 256 && p->m >= 1024) return 128;
+  if (!bmn && (p->n % 256) == 0 && p->m >= 4096) return 256;   // measured: the 128 x 256 tile is the fastest on every encoder shape
   const int sms = num_sms();
   const int mt = ceil_div(p->m, GEMM_BM);
   int best = 64;
@@ -841,15 +943,49 @@ static int pick_bn(const jl_gemm_params* p) {
 }
 
 
+// Tail split of the pair kernel: the last, partial wave of 256 × bn tiles is cut into K ranges so that it fills the idle pairs.
+constexpr size_t GEMM_TAIL_ZERO_BYTES = 8192;      // arrival counters at the head of the workspace (zero on entry, left zero)
+struct TailPlan {
+  int first = 0, split = 1, kb_per = 0, tail_tiles = 0;
+  double waves = 0.0;       // full waves + the shortened tail wave
+};
+static TailPlan plan_tail(const jl_gemm_params* p, int bn, bool allow_split) {
+  TailPlan t;
+  const int pairs = num_sms() / 2;
+  const int tiles = ceil_div(p->m, 256) * ceil_div(p->n, bn);
+  const int num_kb = ceil_div(p->k, GEMM_BK);
+  const int tail = tiles % pairs;
+  t.first = tiles; t.kb_per = num_kb;
+  t.waves = static_cast<double>(ceil_div(tiles, pairs));
+  if (!allow_split || tail == 0 || g_gemm_tail.load() == 0 || p->a_layout == JL_LAYOUT_MN) return t;
+  int want = pairs / tail;
+  if (want > 4) want = 4;
+  if (want > num_kb / 4) want = num_kb / 4;
+  if (want < 2) return t;
+  const int per = ceil_div(num_kb, want);
+  const int split = ceil_div(num_kb, per);
+  if (split < 2 || static_cast<size_t>(tail) * 2 * GEMM_EPI_WARPS * sizeof(int32_t) > GEMM_TAIL_ZERO_BYTES) return t;
+  t.first = tiles - tail; t.split = split; t.kb_per = per; t.tail_tiles = tail;
+  t.waves = static_cast<double>(tiles / pairs) + static_cast<double>(per) / num_kb + 0.08;   // + fix-up traffic
+  return t;
+}
+static size_t tail_ws_bytes(const TailPlan& t, int bn) {
+  if (t.split <= 1) return 0;
+  return GEMM_TAIL_ZERO_BYTES + static_cast<size_t>(t.split) * t.tail_tiles * 256 * bn * sizeof(float);
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, int PAIRS>
 static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
   using L = GemmSmem2<BN, STAGES>;
-  auto kern = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN, PAIRS>;
+  constexpr bool CAN_TAIL = (PAIRS == 1) && !A_MN;     // the tail-split instantiation exists for K-major A only
+  auto kern = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN, PAIRS, false>;
+  auto kern_tail = gemm_tcgen05_2cta_kernel<BN, STAGES, A_MN, B_MN, PAIRS, CAN_TAIL>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e == cudaSuccess && CAN_TAIL) e = cudaFuncSetAttribute(kern_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "gemm(2cta): cannot reserve %d B of shared memory: %s", L::TOTAL, cudaGetErrorString(e));
     configured_dev = dev;
   }
@@ -863,10 +999,22 @@ static int launch_gemm_2cta(const jl_gemm_params* p, cudaStream_t stream) {
   if (rc != JL_OK) return rc;
   GemmDev g = to_dev(p, BN);
   g.num_m_tiles = ceil_div(p->m, 256 * PAIRS);
-  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  int units = g.num_m_tiles * g.num_n_tiles;
+  g.tail_first = units;
+  if (CAN_TAIL && p->workspace != nullptr && (reinterpret_cast<uintptr_t>(p->workspace) & 255) == 0) {
+    const TailPlan t = plan_tail(p, BN, true);
+    if (t.split > 1 && static_cast<size_t>(p->workspace_bytes) >= tail_ws_bytes(t, BN)) {
+      g.tail_first = t.first; g.tail_split = t.split; g.tail_kb_per = t.kb_per;
+      g.tail_stride = static_cast<int64_t>(t.tail_tiles) * 256 * BN;
+      g.tail_cnt = reinterpret_cast<int32_t*>(p->workspace);
+      g.tail_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p->workspace) + GEMM_TAIL_ZERO_BYTES);
+      units = t.first + t.tail_tiles * t.split;
+    }
+  }
+  const int tiles = units;
   const int pairs_max = num_sms() / (2 * PAIRS);
   const int pairs = tiles < pairs_max ? tiles : pairs_max;
-  jl::launch(kern, 2 * PAIRS * pairs, GEMM_THREADS, L::TOTAL, stream, ma, mb, g);
+  jl::launch(g.tail_split > 1 ? kern_tail : kern, 2 * PAIRS * pairs, GEMM_THREADS, L::TOTAL, stream, ma, mb, g);
   JL_CHECK_LAUNCH("gemm_tcgen05_2cta");
   return JL_OK;
 }
@@ -884,8 +1032,9 @@ static int dispatch_layout_2cta(const jl_gemm_params* p, cudaStream_t s) {
 
 static std::atomic<int> g_gemm_mode{0};   // 0 = auto, 1 = single-CTA kernel only, 2 = CTA-pair kernel wherever legal, 3 = + B multicast across two pairs
 
-// N tile of the CTA-pair kernel, or 0 when the product should run on the single-CTA kernel.
-static int pick_bn_2cta(const jl_gemm_params* p) {
+// N tile of the CTA-pair kernel, or 0 when the product should run on the single-CTA kernel.  `assume_ws`: plan as if the caller
+// will supply the workspace jl_gemm_workspace_bytes asks for.
+static int pick_bn_2cta(const jl_gemm_params* p, bool assume_ws = false) {
   const int mode = g_gemm_mode.load();
   if (mode == 1) return 0;
   const int forced = g_gemm_bn.load();
@@ -896,21 +1045,24 @@ static int pick_bn_2cta(const jl_gemm_params* p) {
   // dgrad) and one-k-block products (K <= 64: the adapter output projections, pure epilogue work) run faster on the
   // single-CTA kernel, whose 128-row tiles put twice as many CTAs on the machine.
   if (mode == 0 && (p->n <= 256 || p->k <= GEMM_BK)) return 0;
+  // ... and so do the large K-major products whose N is a multiple of 256 (q|k|v, attention / FFN output projections, their
+  // dgrads): 128 x 256 single-CTA tiles need 1.28-3.8 waves of 148 CTAs where 256 x 192 pair tiles need 1.7-5.2 waves of 74
+  // pairs, and measure 2-8 % faster (profiles/r1g_gemm_tile_sweep.md).  The FFN input projection (GELU epilogue, N = 3072) is
+  // a tie and stays on the pair kernel, whose epilogue has half the columns per CTA.
+  if (mode == 0 && p->b_layout == JL_LAYOUT_K && (p->n % 256) == 0 && p->m >= 4096 && p->epilogue == JL_EPI_NONE) return 0;
   int per = 0;
-  if (p->workspace != nullptr && pick_split(p, pick_bn(p), &per) > 1) return 0;
+  const bool have_ws = assume_ws || p->workspace != nullptr;
+  if (have_ws && pick_split(p, pick_bn(p), &per) > 1) return 0;
   const bool bmn = p->b_layout == JL_LAYOUT_MN;
-  const int pairs = num_sms() / 2;
-  const int mt = ceil_div(p->m, 256);
   int best = 0;
-  long best_cost = -1;
+  double best_cost = -1.0;
   const int cands[3] = {256, 192, 128};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn == 192 && bmn) continue;
     if (bn > 128 && bn / 2 >= p->n) continue;
-    const long tiles = static_cast<long>(mt) * ceil_div(p->n, bn);
-    const long waves = (tiles + pairs - 1) / pairs;
-    const long cost = waves * (bn + 32);
+    const TailPlan t = plan_tail(p, bn, have_ws && (assume_ws || p->workspace_bytes >= static_cast<int64_t>(tail_ws_bytes(plan_tail(p, bn, true), bn))));
+    const double cost = t.waves * (bn + 32);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   // Long-K products whose N is a multiple of 256 (FFN output projection, dX of the q|k|v projection): the 256-wide tile moves
@@ -964,8 +1116,25 @@ int jl_gemm_workspace_bytes(const jl_gemm_params* p, size_t* out) {
   int rc = jl::validate(p);
   if (rc != JL_OK) return rc;
   *out = jl::splitk_ws_bytes(p);
+  if (*out == 0) {
+    const int bn2 = jl::pick_bn_2cta(p, true);
+    if (bn2 != 0 && !jl::use_multicast(p, bn2)) *out = jl::tail_ws_bytes(jl::plan_tail(p, bn2, true), bn2);
+  }
   return JL_OK;
 }
+
+int jl_gemm_workspace_zero_bytes(const jl_gemm_params* p, size_t* out) {
+  JL_REQUIRE(out != nullptr, JL_EINVAL, "gemm_workspace_zero_bytes: null out");
+  int rc = jl::validate(p);
+  if (rc != JL_OK) return rc;
+  *out = 0;
+  if (jl::splitk_ws_bytes(p) != 0) return JL_OK;
+  const int bn2 = jl::pick_bn_2cta(p, true);
+  if (bn2 != 0 && !jl::use_multicast(p, bn2) && jl::plan_tail(p, bn2, true).split > 1) *out = jl::GEMM_TAIL_ZERO_BYTES;
+  return JL_OK;
+}
+
+void jl_debug_set_gemm_tail(int on) { jl::g_gemm_tail.store(on ? 1 : 0); }
 
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {
   int rc = jl::validate(p);

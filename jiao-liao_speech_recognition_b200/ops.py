@@ -70,6 +70,21 @@ def mel_cmvn(wave: torch.Tensor, num_samples: torch.Tensor, tables: dict, max_fr
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+_TAIL_WS: dict = {}
+
+
+def _tail_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Scratch for the pair kernel's tail split: its leading arrival counters must be zero on entry (the kernel leaves them
+    zero), and products that may run concurrently must not share it — one zero-initialised buffer per (device, stream),
+    grown on demand."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _TAIL_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros((max(nbytes, 24 << 20),), dtype=torch.uint8, device=device)
+        _TAIL_WS[key] = ws
+    return ws
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, epilogue: int = L.JL_EPI_NONE,
          residual: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
          row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0, out: Optional[torch.Tensor] = None,
@@ -110,11 +125,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         raise TypeError("gemm: out must be bf16 or fp32")
     lib = L.load()
     ws = None
-    if not reference and epilogue == L.JL_EPI_NONE and bias is None and residual is None and row_lengths is None:
-        nbytes = C.c_size_t(0)
+    if not reference:
+        nbytes, zbytes = C.c_size_t(0), C.c_size_t(0)
         L.check(lib.jl_gemm_workspace_bytes(C.byref(p), C.byref(nbytes)))
         if nbytes.value:
-            ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=a.device)
+            L.check(lib.jl_gemm_workspace_zero_bytes(C.byref(p), C.byref(zbytes)))
+            if zbytes.value:
+                ws = _tail_workspace(a.device, nbytes.value)       # persistent, zero counters, one per stream
+            else:
+                ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=a.device)
             p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes.value
     fn = lib.jl_debug_gemm_ref if reference else lib.jl_gemm_bf16
     L.check(fn(C.byref(p), _stream()))

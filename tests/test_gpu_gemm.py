@@ -184,3 +184,65 @@ def test_gemm_cta_pair_kernel_epilogues(pair_mode):
     valid = t < lens[torch.arange(m, device="cuda") // 275]
     assert rel_err(out, acc * valid[:, None]) < 2e-3
     torch.cuda.synchronize()
+
+
+def _tail_bytes(ops_mod, L, a, b, **kw):
+    """Workspace the library asks for when the pair kernel would split its tail wave (0 = no split planned)."""
+    import ctypes as C
+    m, k = a.shape
+    n = b.shape[0] if kw.get("b_layout", 0) == 0 else b.shape[1]
+    out = torch.empty((m, n), dtype=BF16, device="cuda")
+    bias, res = kw.get("bias"), kw.get("residual")
+    p = L.GemmParams(a=a.data_ptr(), lda=a.stride(0), b=b.data_ptr(), ldb=b.stride(0), a_layout=0, b_layout=kw.get("b_layout", 0),
+                     c=out.data_ptr(), ldc=n, bias=None if bias is None else bias.data_ptr(),
+                     residual=None if res is None else res.data_ptr(), ldr=0 if res is None else res.stride(0),
+                     m=m, n=n, k=k, epilogue=kw.get("epilogue", 0), out_dtype=L.JL_DT_BF16, alpha=1.0)
+    nb, zb = C.c_size_t(0), C.c_size_t(0)
+    L.check(L.load().jl_gemm_workspace_bytes(C.byref(p), C.byref(nb)))
+    L.check(L.load().jl_gemm_workspace_zero_bytes(C.byref(p), C.byref(zb)))
+    return nb.value, zb.value
+
+
+@pytest.mark.parametrize("m,n,k,epi", [(8000, 768, 768, "bias_res"), (8000, 768, 3072, "bias_res"), (8000, 768, 2304, "plain"),
+                                       (8000, 768, 768, "gelu"), (5000, 1024, 1024, "relu"), (2000, 768, 4096, "plain")])
+def test_gemm_tail_split_matches_unsplit_and_reference(m, n, k, epi):
+    """The partial last wave of the pair kernel is cut into K ranges (in-kernel fix-up by the last range to arrive): same
+    result as the unsplit kernel up to fp32 summation order, equal to the fp32 reference within the usual tolerance,
+    bit-identical from run to run, and the arrival counters are left zero."""
+    ops, L = _ops()
+    lib = L.load()
+    a, b, _, _ = _mk(m, n, k, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    kw = {}
+    if epi in ("bias_res", "gelu", "relu"):
+        kw["bias"] = torch.randn(n, device="cuda", generator=g)
+    if epi == "bias_res":
+        kw["residual"] = torch.randn(m, n, device="cuda", generator=g).to(BF16)
+    if epi == "gelu":
+        kw["epilogue"] = L.JL_EPI_GELU
+    if epi == "relu":
+        kw["epilogue"] = L.JL_EPI_RELU
+    lib.jl_debug_set_gemm_mode(2)          # pair kernel wherever legal (the automatic choice prefers 128 x 256 single-CTA tiles here)
+    lib.jl_debug_set_gemm_tail(1)          # the tail split is off by default (measured slower, DESIGN §3)
+    try:
+        nbytes, zbytes = _tail_bytes(ops, L, a, b, **kw)
+        assert nbytes > 0 and zbytes > 0, "this shape is expected to plan a tail split"
+        out1 = ops.gemm(a, b, **kw).clone()
+        out2 = ops.gemm(a, b, **kw).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(out1, out2), "tail split must be bit-reproducible"
+        ws = ops._TAIL_WS[(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)]
+        assert int(ws[:zbytes].to(torch.int32).abs().sum()) == 0, "arrival counters must be left zero"
+        lib.jl_debug_set_gemm_tail(0)
+        assert _tail_bytes(ops, L, a, b, **kw)[0] == 0
+        unsplit = ops.gemm(a, b, **kw)
+    finally:
+        lib.jl_debug_set_gemm_tail(0)
+        lib.jl_debug_set_gemm_mode(0)
+    ref = ops.gemm(a, b, reference=True, **kw)
+    torch.cuda.synchronize()
+    assert rel_err(out1.float(), ref.float()) < 1e-2
+    assert rel_err(out1.float(), unsplit.float()) < 4e-3
+    z = a.float() @ b.float().t()
+    if epi == "plain":
+        assert rel_err(out1.float(), z) < 1e-2
