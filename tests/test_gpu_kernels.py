@@ -131,6 +131,32 @@ def test_ctc_loss_and_grad_match_oracle(b, t, v, smax, reduction):
     assert float((grad16.float().cpu() - g2).abs().max()) < 5e-3
 
 
+@pytest.mark.parametrize("b,t,v,smax", [(2, 640, 50, 300), (3, 120, 3, 40)])
+def test_ctc_long_label_sequences_and_heavy_label_repeats(b, t, v, smax):
+    """2S+1 > 512 extended states (several states per lattice thread: the generic kernel path) and a 2-symbol alphabet (every
+    label repeats many times: the linked duplicate chains of the gradient kernel)."""
+    from oracle import ctc as oc
+    ops = pkg().ops
+    g = torch.Generator().manual_seed(b * 7 + t)
+    logits = torch.randn(b, t, v, generator=g) * 2.0
+    ilens = torch.full((b,), t, dtype=torch.int64)
+    ilens[-1] = t - 7
+    labels = torch.full((b, smax), -100, dtype=torch.int64)
+    for i in range(b):
+        s = smax if i == 0 else smax // 2
+        lab = torch.randint(1, v, (s,), generator=g)
+        if v > 3:
+            lab[1::2] = torch.where(lab[1::2] == lab[0::2][: lab[1::2].numel()], (lab[1::2] % (v - 1)) + 1, lab[1::2])   # keep it feasible
+        labels[i, :s] = lab
+    oloss, onll, ograd = oc.ctc_loss_and_grad(logits, labels, ilens, 0, "sum", True)
+    loss, nll, grad = ops.ctc_loss(logits.cuda(), labels.to(I32).cuda(), ilens.to(I32).cuda(), 0, "sum", True, want_grad=True, grad_dtype=F32)
+    torch.cuda.synchronize()
+    assert math.isfinite(oloss)
+    assert abs(float(loss) - oloss) <= 1e-4 * max(1.0, abs(oloss))
+    assert rel_err(nll, onll) < 1e-5
+    assert float((grad.cpu() - ograd).abs().max()) < 1e-3 * max(1.0, float(ograd.abs().max()))
+
+
 def test_ctc_golden_cases_infeasible_and_zero_infinity():
     ops = pkg().ops
     gold = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))

@@ -1,5 +1,7 @@
 """End-to-end GPU parity: waveform → features → encoder (+ adapters) → logits → CTC loss → adapter-only gradients,
 product modules (through the C ABI) vs the fp32 CPU oracle on bf16-rounded weights."""
+import math
+
 import pytest
 import torch
 
@@ -278,3 +280,40 @@ def test_per_utterance_dialect_ids_select_wfadapter_factor_sets():
     for name, p in model._get_adapters().items():
         got = tr.flat.out(p)
         assert rel_err(got, ref_grads[name]) < 1e-2 or float((got - ref_grads[name]).abs().max()) < 1e-5, name
+
+
+def test_batch_composition_invariance_and_zero_frame_utterance():
+    """An utterance's logits, its loss term and the adapter gradients do not depend on what else is in the batch: adding an
+    utterance that is too short to yield a single frame (< 400 samples → T' = 0, no labels) changes nothing, every output stays
+    finite, and the valid rows of the other utterances are bit-identical (each output row's summation order is fixed)."""
+    P = pkg()
+    cfg = _small_cfg(P, adapter_attn="att", adapter_ffn="wf", ctc_zero_infinity=True)
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    fe = P.JLFeatureExtractor(device="cuda")
+    wa, wb, wc = synth_wave(24000, 21), synth_wave(9000, 22), synth_wave(300, 23)
+
+    def run(waves, labels):
+        for p_ in model.parameters():
+            p_.grad = None
+        feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+        lens = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+        loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        return lens, float(loss), logits.detach().clone(), {n: p_.grad.detach().clone() for n, p_ in model._get_adapters().items()}
+
+    lab2 = _labels([37, 14], cfg.vocab_size, 8, seed=9)
+    lab3 = torch.cat([lab2, torch.full((1, 8), -100, dtype=torch.int64)], 0)
+    lens2, loss2, logits2, grads2 = run([wa, wb], lab2)
+    lens3, loss3, logits3, grads3 = run([wa, wb, wc], lab3)
+    assert lens3[:2] == lens2 and lens3[2] == 0
+    assert torch.isfinite(logits3).all() and math.isfinite(loss3)
+    for i, t in enumerate(lens2):
+        assert torch.equal(logits3[i, :t], logits2[i, :t]), f"utterance {i}: logits depend on batch composition"
+    assert abs(loss3 - loss2) <= 1e-6 * abs(loss2)
+    for n in grads2:
+        assert torch.isfinite(grads3[n]).all(), n
+        assert rel_err(grads3[n], grads2[n]) < 1e-3 or float((grads3[n] - grads2[n]).abs().max()) < 1e-6, n
