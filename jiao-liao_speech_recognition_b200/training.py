@@ -208,6 +208,9 @@ class AdapterTrainer:
         self.lr, self.weight_decay = lr, weight_decay
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, dict] = {}
+        self._stage: Dict[tuple, dict] = {}
+        self._staged = None
+        self._copy_stream = None
         self.launches_per_step = 0
 
     def _body(self, wave, nsamp, lengths, labels, max_frames, dialect=0):
@@ -239,20 +242,69 @@ class AdapterTrainer:
         self._graphs[key] = ent
         return ent
 
-    def step(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor, dialect=0) -> torch.Tensor:
-        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad),
-        ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent).
-        Returns the loss as a 1-element device tensor (call ``.item()`` for the D2H read)."""
+    @staticmethod
+    def _token_lengths(num_samples: torch.Tensor) -> torch.Tensor:
+        ns = num_samples.to(torch.int64)
+        frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
+        return subsampled_length(frames).to(I32)
+
+    def submit(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor, dialect=0) -> None:
+        """Stage the NEXT batch while the current step is still running: the host → device copies (pinned host memory) go to
+        device staging buffers on a dedicated copy stream, so a following ``step()`` without arguments only pays a
+        device-to-device copy into the graph's static inputs.  What a prefetching data loader does for the reference's
+        trainer; the copy of batch i+1 overlaps the kernels of batch i."""
         b, n = wave.shape
         s = labels.shape[1]
-        dialect = _dialect_key(dialect)
-        ent = self._static(b, n, s, dialect)
-        ent["wave"].copy_(wave, non_blocking=True)
-        ent["nsamp"].copy_(num_samples, non_blocking=True)
-        frames = torch.clamp((num_samples.to(torch.int64) - 400) // 160 + 1, min=0)
-        frames = torch.where(num_samples.to(torch.int64) < 400, torch.zeros_like(frames), frames)
-        ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
-        ent["labels"].copy_(labels, non_blocking=True)
+        dev = self.flat.param.device
+        key = (b, n, s)
+        st = self._stage.get(key)
+        if st is None:
+            st = {"wave": torch.empty((b, n), dtype=F32, device=dev), "nsamp": torch.empty((b,), dtype=I32, device=dev),
+                  "lengths": torch.empty((b,), dtype=I32, device=dev), "labels": torch.empty((b, s), dtype=I32, device=dev),
+                  "free": None}
+            self._stage[key] = st
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        if st["free"] is not None:
+            cs.wait_event(st["free"])            # the previous step may still be reading the staging buffers
+        lengths = self._token_lengths(num_samples)
+        with torch.cuda.stream(cs):
+            st["wave"].copy_(wave, non_blocking=True)
+            st["nsamp"].copy_(num_samples, non_blocking=True)
+            st["lengths"].copy_(lengths, non_blocking=True)
+            st["labels"].copy_(labels, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        self._staged = (st, ready, b, n, s, _dialect_key(dialect))
+
+    def step(self, wave: Optional[torch.Tensor] = None, num_samples: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+             dialect=0) -> torch.Tensor:
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad),
+        ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent).
+        Without arguments the batch staged by ``submit()`` is consumed.
+        Returns the loss as a 1-element device tensor (call ``.item()`` for the D2H read)."""
+        if wave is None:
+            if self._staged is None:
+                raise RuntimeError("step() without arguments needs a batch staged by submit()")
+            st, ready, b, n, s, dialect = self._staged
+            self._staged = None
+            ent = self._static(b, n, s, dialect)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready)
+            for k in ("wave", "nsamp", "lengths", "labels"):
+                ent[k].copy_(st[k], non_blocking=True)
+            st["free"] = torch.cuda.Event()
+            st["free"].record(cur)
+        else:
+            b, n = wave.shape
+            s = labels.shape[1]
+            dialect = _dialect_key(dialect)
+            ent = self._static(b, n, s, dialect)
+            ent["wave"].copy_(wave, non_blocking=True)
+            ent["nsamp"].copy_(num_samples, non_blocking=True)
+            ent["lengths"].copy_(self._token_lengths(num_samples), non_blocking=True)
+            ent["labels"].copy_(labels, non_blocking=True)
         args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
         if not self.use_cuda_graph:
             L.launch_count_reset()

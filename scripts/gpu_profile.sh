@@ -3,7 +3,7 @@
 # Raw pages are exported to CSV on the box; only the GEMM report (with source) is kept as .ncu-rep (gpurun_out <= 64 MiB).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --eager --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --eager --no-cpu-baseline --no-inference"
 timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
