@@ -134,6 +134,8 @@ typedef struct {
   float* mean; float* rstd;       /* [rows] fp32 out (NULL in inference) */
   int32_t rows, d;
   float eps;
+  int32_t act;                    /* JL_EPI_NONE, or JL_EPI_GELU applied to the normalised row: the Conv1d → LayerNorm → GELU layers
+                                     of the wav2vec2 feature encoder (modeling_wav2vec2.py:291-299) */
 } jl_layernorm_fwd_params;
 int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream);
 
@@ -252,6 +254,20 @@ int jl_im2col_k5s2(const void* x, void* out, int32_t batch, int32_t t_in, int32_
  * (modeling_speech_to_text.py:542,568-579; pos_table is the host-built [seq + 2, d] fp32 sinusoid table, :123-139) */
 int jl_embed_positions(void* h, float scale, const float* pos_table, const int32_t* lengths, int32_t batch, int32_t seq,
                        int32_t d, void* stream);
+/* Raw-waveform (wav2vec2 / XLS-R) front end — the second front end beside mel.  The convolutions run on
+ * jl_gemm_bf16; these entry points build its operands.
+ *  jl_wave_stats   stats[b] = (mean, 1/sqrt(var + 1e-7)) over the valid samples of utterance b — zero_mean_unit_var_norm,
+ *                  SP/transformers/models/wav2vec2/feature_extraction_wav2vec2.py:78-97
+ *  jl_wave_im2col  feature-encoder layer 0, Conv1d(1 → C, kernel <= 16, stride) (modeling_wav2vec2.py:275-299): normalises on
+ *                  the fly and writes the bf16 im2col matrix [batch · t_out, 16] (unused taps and samples past the utterance = 0)
+ *  jl_im2col_1d    x [batch, t_in, channels] bf16 → [batch · t_out, kernel · cg] (tap-major) for Conv1d(kernel, stride, pad)
+ *                  over channels [c0, c0 + cg): encoder layers 1-6 and the grouped positional convolution (:326-368) */
+int jl_wave_stats(const float* wave, int64_t wave_stride, const int32_t* num_samples, int32_t batch, int32_t max_samples, float* stats,
+                  void* stream);
+int jl_wave_im2col(const float* wave, int64_t wave_stride, const int32_t* num_samples, int32_t batch, int32_t max_samples, const float* stats,
+                   void* out, int32_t t_out, int32_t kernel, int32_t stride, void* stream);
+int jl_im2col_1d(const void* x, void* out, int32_t batch, int32_t t_in, int32_t channels, int32_t t_out, int32_t kernel, int32_t stride,
+                 int32_t pad, int32_t c0, int32_t cg, void* stream);
 int jl_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols, void* stream);
 /* out[n] (+)= sum_m x[m, n]  (bias gradients) */
 int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t cols, float* partial, void* stream);

@@ -2,6 +2,7 @@
 transfer.  Public surface (HF-style, drop-in for the reference's pinned stack on this path):
 
     JLFeatureExtractor   80-bin Kaldi log-mel + utterance CMVN (fused CUDA kernels)
+    JLWaveformFeatureExtractor   padded raw waveforms for the wav2vec2 / XLS-R front end (JLConfig.front_end = "wav2vec2")
     JLConfig             configuration (HF Wav2Vec2Config / Speech2TextConfig field names)
     JLEncoder            conv subsampler + pre-LN transformer with WFAdapter / AttAdapter slots
     WFAdapter, AttAdapter
@@ -17,7 +18,7 @@ or through the ``jl_b200`` alias module at the repository root.
 from . import _lib, hf_compat, ops, scoring  # noqa: F401
 from .comm import JLComm  # noqa: F401
 from .configuration import JLConfig  # noqa: F401
-from .feature_extraction import JLFeatureExtractor  # noqa: F401
+from .feature_extraction import JLFeatureExtractor, JLWaveformFeatureExtractor  # noqa: F401
 from .modeling import AttAdapter, GradSink, JLEncoder, JLEngine, JLForCTC, WFAdapter  # noqa: F401
 from .training import AdapterTrainer, BucketLayout, FlatAdapterParams, Transcriber, ordered_trainables, shard_utterances  # noqa: F401
 

@@ -39,7 +39,7 @@ class GemmParams(C.Structure):
 
 class LayerNormFwdParams(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("gamma", vp), ("beta", vp), ("y", vp), ("ldy", i64), ("mean", vp),
-                ("rstd", vp), ("rows", i32), ("d", i32), ("eps", f32)]
+                ("rstd", vp), ("rows", i32), ("d", i32), ("eps", f32), ("act", i32)]
 
 
 class LayerNormBwdParams(C.Structure):
@@ -113,6 +113,9 @@ SYMBOLS = {
     "jl_im2col_k5s2": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "jl_embed_positions": (C.c_int, [vp, f32, vp, vp, i32, i32, i32, vp]),
     "jl_transpose_bf16": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),
+    "jl_wave_stats": (C.c_int, [vp, i64, vp, i32, i32, vp, vp]),
+    "jl_wave_im2col": (C.c_int, [vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
+    "jl_im2col_1d": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "jl_colsum_bf16": (C.c_int, [vp, i64, vp, i32, i32, vp, vp]),
     "jl_colsum_workspace_bytes": (C.c_int, [i32, i32, C.POINTER(C.c_size_t)]),
     "jl_cast_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),

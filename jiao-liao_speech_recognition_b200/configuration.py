@@ -28,6 +28,15 @@ class JLConfig:
     att_dim: int = 64
     num_dialects: int = 1
     logits_dtype: str = "float32"           # "float32" | "bfloat16"
+    # front end: "mel" = 80-bin log-mel + Conv1d(k5, s2)+GLU x2 (Speech2Text); "wav2vec2" = raw-waveform conv stack with layer
+    # norm, feature projection and grouped positional convolution (XLS-R / MMS / wav2vec2-large, configuration_wav2vec2.py:
+    # 182-190, feat_extract_norm = "layer", conv_bias = True, do_stable_layer_norm = True)
+    front_end: str = "mel"
+    conv_dim: int = 512
+    conv_kernel: tuple = (10, 3, 3, 3, 3, 2, 2)
+    conv_stride: tuple = (5, 2, 2, 2, 2, 2, 2)
+    num_conv_pos_embeddings: int = 128
+    num_conv_pos_embedding_groups: int = 16
 
     def __post_init__(self):
         if self.hidden_size % 64 or self.hidden_size // self.num_attention_heads != 64:
@@ -43,6 +52,17 @@ class JLConfig:
             raise ValueError("ctc_loss_reduction must be 'sum' or 'mean'")
         if self.logits_dtype not in ("float32", "bfloat16"):
             raise ValueError("logits_dtype must be 'float32' or 'bfloat16'")
+        if self.front_end not in ("mel", "wav2vec2"):
+            raise ValueError("front_end must be 'mel' or 'wav2vec2'")
+        self.conv_kernel, self.conv_stride = tuple(self.conv_kernel), tuple(self.conv_stride)
+        if self.front_end == "wav2vec2":
+            if len(self.conv_kernel) != len(self.conv_stride) or not self.conv_kernel:
+                raise ValueError("conv_kernel and conv_stride must have the same, non-zero length")
+            if self.conv_kernel[0] > 16 or self.conv_dim % 8:
+                raise ValueError("wav2vec2 front end: first conv kernel must be <= 16 and conv_dim a multiple of 8")
+            g = self.num_conv_pos_embedding_groups
+            if self.hidden_size % g or (self.hidden_size // g) % 8:
+                raise ValueError("hidden_size / num_conv_pos_embedding_groups must be a multiple of 8")
 
     def to_dict(self):
         return asdict(self)
@@ -51,6 +71,13 @@ class JLConfig:
     def base(cls, **kw):
         """12-layer d=768 encoder (BASELINE.json configs 1, 2)."""
         return cls(**kw)
+
+    @classmethod
+    def xlsr(cls, **kw):
+        """XLS-R-300M / MMS-style model: the large transformer stack behind the raw-waveform front end."""
+        d = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096, front_end="wav2vec2")
+        d.update(kw)
+        return cls(**d)
 
     @classmethod
     def large(cls, **kw):

@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_laye
         ln_load8_f32(p.beta + ch * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, g[j], b[j]);
+        if (p.act == JL_EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
+        }
         ln_store8_bf16(yr + ch * 8, o);
       }
     }
@@ -311,6 +315,7 @@ int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
   JL_REQUIRE(p->rows > 0 && p->d > 0, JL_EINVAL, "layernorm_fwd: rows and d must be positive");
   JL_REQUIRE((p->d & 7) == 0 && p->d <= 2048, JL_EUNSUPPORTED_SHAPE, "layernorm_fwd: d must be a multiple of 8 and <= 2048 (got %d)", p->d);
   JL_REQUIRE((p->ldx & 7) == 0 && (p->ldy & 7) == 0, JL_EINVAL, "layernorm_fwd: row strides must be multiples of 8");
+  JL_REQUIRE(p->act == JL_EPI_NONE || p->act == JL_EPI_GELU, JL_EINVAL, "layernorm_fwd: act must be JL_EPI_NONE or JL_EPI_GELU (got %d)", p->act);
   JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->y) | reinterpret_cast<uintptr_t>(p->gamma) |
                reinterpret_cast<uintptr_t>(p->beta)) & 15) == 0, JL_EINVAL, "layernorm_fwd: pointers must be 16-byte aligned");
   int rc = jl::check_device();

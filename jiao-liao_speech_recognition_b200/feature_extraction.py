@@ -152,3 +152,53 @@ class JLFeatureExtractor:
                 out.append(a)
             return out
         raise ValueError("raw_speech must be a numpy array, a torch tensor or a list of them")
+
+
+class JLWaveformFeatureExtractor:
+    """Input side of the raw-waveform front end (``JLConfig.front_end = "wav2vec2"``), HF ``Wav2Vec2FeatureExtractor`` call
+    signature (SP/transformers/models/wav2vec2/feature_extraction_wav2vec2.py:102-240): pads a list of mono 16 kHz waveforms
+    to the longest, moves them to the GPU through pinned memory and returns ``{"input_values": [B, N] fp32 CUDA,
+    "attention_mask": [B, N] int32 CUDA, "num_samples": [B] int32 CUDA}``.
+
+    ``do_normalize`` (zero mean / unit variance per utterance, :78-97) is applied by the model's first kernels
+    (``jl_wave_stats`` + ``jl_wave_im2col``), not here: ``input_values`` are the padded raw samples.  The normalisation is
+    idempotent, so already-normalised input (HF's own extractor output) gives the same logits."""
+
+    model_input_names = ["input_values", "attention_mask"]
+
+    def __init__(self, feature_size: int = 1, sampling_rate: int = SAMPLE_RATE, padding_value: float = 0.0, do_normalize: bool = True,
+                 return_attention_mask: bool = True, device: Union[str, torch.device] = "cuda"):
+        if feature_size != 1:
+            raise ValueError("JLWaveformFeatureExtractor takes mono audio (feature_size = 1)")
+        if not do_normalize:
+            raise ValueError("the reference path (XLS-R / MMS / wav2vec2-large) normalises every utterance: do_normalize must be True")
+        self.feature_size, self.sampling_rate, self.padding_value = feature_size, sampling_rate, padding_value
+        self.do_normalize, self.return_attention_mask = do_normalize, return_attention_mask
+        self.device = torch.device(device)
+        L.load()   # fail loudly at construction if the CUDA library is missing
+
+    def __call__(self, raw_speech, sampling_rate: Optional[int] = None, padding: Union[bool, str] = True,
+                 return_tensors: Optional[str] = "pt", return_attention_mask: Optional[bool] = None, **kwargs) -> dict:
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            raise ValueError(
+                f"The model corresponding to this feature extractor was trained using a sampling rate of {self.sampling_rate}. "
+                f"Please make sure that the provided `raw_speech` input was sampled with {self.sampling_rate} and not {sampling_rate}.")
+        if return_tensors not in (None, "pt"):
+            raise ValueError("JLWaveformFeatureExtractor returns CUDA torch tensors (return_tensors='pt')")
+        if padding not in (True, "longest"):
+            raise ValueError("only padding=True / 'longest' is on the reference path")
+        waves = JLFeatureExtractor._as_list(raw_speech)
+        lens = [int(w.shape[0]) for w in waves]
+        nmax = (max(lens) + 3) // 4 * 4
+        host = torch.full((len(waves), nmax), float(self.padding_value), dtype=torch.float32).pin_memory()
+        for i, w in enumerate(waves):
+            host[i, : lens[i]] = torch.as_tensor(w, dtype=torch.float32)
+        out = {"input_values": host.to(self.device, non_blocking=True),
+               "num_samples": torch.tensor(lens, dtype=torch.int32).to(self.device, non_blocking=True)}
+        want_mask = self.return_attention_mask if return_attention_mask is None else return_attention_mask
+        if want_mask:
+            mask = torch.zeros((len(waves), nmax), dtype=torch.int32)
+            for i, n in enumerate(lens):
+                mask[i, :n] = 1
+            out["attention_mask"] = mask.to(self.device, non_blocking=True)
+        return out

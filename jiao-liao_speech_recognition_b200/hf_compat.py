@@ -16,8 +16,10 @@ tensors between dictionaries on the host and touches no kernel:
   modeling_speech_to_text.py:68-100, :561-608): ``conv.conv_layers.N`` → ``encoder.conv.N``, ``self_attn`` →
   ``attention``, ``self_attn_layer_norm`` → ``layer_norm``, ``fc1`` / ``fc2`` → ``feed_forward.{intermediate,output}_dense``.
 
-The raw-waveform front end of true wav2vec2 (``feature_extractor``, ``feature_projection``, ``pos_conv_embed``,
-``masked_spec_embed``) has no counterpart on this path and is reported back as skipped.
+The raw-waveform front end of true wav2vec2 (``feature_extractor``, ``feature_projection``, ``pos_conv_embed``) maps onto a
+model built with ``front_end="wav2vec2"`` (``encoder.w2v.*``, SURVEY §8 f3: "layer" feature-extractor norm with conv bias);
+a mel model reports those keys back as skipped.  ``masked_spec_embed`` (SpecAugment, training-time augmentation) is always
+skipped.
 """
 from __future__ import annotations
 
@@ -50,7 +52,19 @@ def _strip_prefix(k: str) -> str:
     return k
 
 
-def convert_hf_state_dict(sd: Dict[str, torch.Tensor], num_dialects: int = 1, dialect: int = 0) -> Tuple[Dict[str, torch.Tensor], List[str]]:
+_W2V_FRONT = [
+    (re.compile(r"^feature_extractor\.conv_layers\.(\d+)\.conv\.(weight|bias)$"), r"encoder.w2v.conv.\1.\2"),
+    (re.compile(r"^feature_extractor\.conv_layers\.(\d+)\.layer_norm\.(weight|bias)$"), r"encoder.w2v.conv_norm.\1.\2"),
+    (re.compile(r"^feature_projection\.layer_norm\.(weight|bias)$"), r"encoder.w2v.proj_norm.\1"),
+    (re.compile(r"^feature_projection\.projection\.(weight|bias)$"), r"encoder.w2v.proj.\1"),
+    (re.compile(r"^encoder\.pos_conv_embed\.conv\.(?:parametrizations\.weight\.original0|weight_g)$"), r"encoder.w2v.pos_conv.weight_g"),
+    (re.compile(r"^encoder\.pos_conv_embed\.conv\.(?:parametrizations\.weight\.original1|weight_v)$"), r"encoder.w2v.pos_conv.weight_v"),
+    (re.compile(r"^encoder\.pos_conv_embed\.conv\.bias$"), r"encoder.w2v.pos_conv.bias"),
+]
+
+
+def convert_hf_state_dict(sd: Dict[str, torch.Tensor], num_dialects: int = 1, dialect: int = 0,
+                          with_front_end: bool = False) -> Tuple[Dict[str, torch.Tensor], List[str]]:
     """HF-named tensors → (``JLForCTC``-named tensors, list of skipped HF keys).  HF bottleneck-adapter weights become the
     factor set ``dialect`` of a WFAdapter in the ``adapter_ffn`` slot; with ``num_dialects`` > 1 the returned factor
     tensors hold only that set (shape [1, …]) under the key suffix ``@<dialect>`` for ``load_hf_state_dict`` to place."""
@@ -58,6 +72,15 @@ def convert_hf_state_dict(sd: Dict[str, torch.Tensor], num_dialects: int = 1, di
     skipped: List[str] = []
     for key, val in sd.items():
         k = _strip_prefix(key)
+        if with_front_end:          # raw-waveform front end of a model built with front_end = "wav2vec2" 
+            mapped = None
+            for pat, rep in _W2V_FRONT:
+                if pat.match(k):
+                    mapped = pat.sub(rep, k)
+                    break
+            if mapped is not None:
+                out[mapped] = val.detach()
+                continue
         if any(k.startswith(p) for p in _FRONT_END):
             skipped.append(key)
             continue
@@ -95,7 +118,8 @@ def load_hf_state_dict(model, sd: Dict[str, torch.Tensor], strict: bool = False,
     """Copy an HF-named state dict into ``model`` (a ``JLForCTC``).  Returns (missing model keys, skipped HF keys);
     ``strict`` raises if a model parameter outside the adapters stays unset or a shape differs."""
     k_dialects = getattr(model.config, "num_dialects", 1)
-    conv, skipped = convert_hf_state_dict(sd, num_dialects=k_dialects, dialect=dialect)
+    conv, skipped = convert_hf_state_dict(sd, num_dialects=k_dialects, dialect=dialect,
+                                          with_front_end=getattr(model.config, "front_end", "mel") == "wav2vec2")
     own = model.state_dict()
     loaded = set()
     with torch.no_grad():

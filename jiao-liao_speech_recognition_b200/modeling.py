@@ -145,17 +145,64 @@ class JLEncoderLayer(nn.Module):
         self.adapter_ffn = _make_adapter(cfg.adapter_ffn, cfg)
 
 
+class JLWav2Vec2FrontEnd(nn.Module):
+    """Parameters of the raw-waveform front end (XLS-R / MMS / wav2vec2-large: "layer" feature-extractor norm, conv bias):
+    7 × [Conv1d → LayerNorm → GELU] (modeling_wav2vec2.py:275-299, 382-420), feature projection LayerNorm → Linear
+    (:422-434), weight-normed grouped positional Conv1d (:326-368).  Frozen on this path."""
+
+    def __init__(self, cfg: JLConfig):
+        super().__init__()
+        c, d = cfg.conv_dim, cfg.hidden_size
+        self.conv = nn.ModuleList([nn.Conv1d(1 if i == 0 else c, c, k, stride=s) for i, (k, s) in enumerate(zip(cfg.conv_kernel, cfg.conv_stride))])
+        self.conv_norm = nn.ModuleList([nn.LayerNorm(c, eps=1e-5) for _ in cfg.conv_kernel])
+        self.proj_norm = nn.LayerNorm(c, eps=cfg.layer_norm_eps)
+        self.proj = nn.Linear(c, d)
+        self.pos_conv = nn.Module()
+        kp, gp = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        self.pos_conv.weight_v = nn.Parameter(torch.empty(d, d // gp, kp))
+        self.pos_conv.weight_g = nn.Parameter(torch.empty(1, 1, kp))
+        self.pos_conv.bias = nn.Parameter(torch.zeros(d))
+
+    def reset_pos_conv(self, generator: Optional[torch.Generator] = None) -> None:
+        """modeling_wav2vec2.py:966-973: N(0, 2·sqrt(1 / (k · in_channels))) weight, zero bias; weight_norm g = ‖v‖ per tap."""
+        v = self.pos_conv.weight_v
+        with torch.no_grad():
+            v.copy_(torch.randn(v.shape, generator=generator) * (2.0 * math.sqrt(1.0 / (v.shape[2] * v.shape[0]))))
+            self.pos_conv.weight_g.copy_(v.norm(dim=(0, 1), keepdim=True))
+            self.pos_conv.bias.zero_()
+
+
+def _sample_lengths(attention_mask, frame_lengths):
+    """Valid length per utterance as the callers give it: explicit lengths win, else the mask's row sums, else None (= full)."""
+    if frame_lengths is not None:
+        return frame_lengths
+    return attention_mask.sum(-1) if attention_mask is not None else None
+
+
+def wav2vec2_lengths(num_samples, kernels, strides):
+    """floor((L - k) / s) + 1 per conv layer (modeling_wav2vec2.py:1005-1020); works on ints and integer tensors."""
+    n = num_samples
+    for k, s in zip(kernels, strides):
+        n = (n - k) // s + 1
+    return n
+
+
 class JLEncoder(nn.Module):
-    """Conv1d(k5,s2)+GLU ×2 → ×√d + sinusoid positions → N pre-LN layers with adapter slots → final LayerNorm."""
+    """Front end (mel: Conv1d(k5,s2)+GLU ×2 → ×√d + sinusoid positions; wav2vec2: raw-waveform conv stack → projection →
+    positional conv) → N pre-LN layers with adapter slots → final LayerNorm."""
 
     def __init__(self, cfg: JLConfig):
         super().__init__()
         self.config = cfg
         d = cfg.hidden_size
-        self.conv = nn.ModuleList([
-            nn.Conv1d(cfg.input_feat_per_channel, cfg.conv_channels, 5, stride=2, padding=2),
-            nn.Conv1d(cfg.conv_channels // 2, 2 * d, 5, stride=2, padding=2),
-        ])
+        if cfg.front_end == "wav2vec2":
+            self.w2v = JLWav2Vec2FrontEnd(cfg)
+            self.conv = nn.ModuleList()
+        else:
+            self.conv = nn.ModuleList([
+                nn.Conv1d(cfg.input_feat_per_channel, cfg.conv_channels, 5, stride=2, padding=2),
+                nn.Conv1d(cfg.conv_channels // 2, 2 * d, 5, stride=2, padding=2),
+            ])
         self.layers = nn.ModuleList([JLEncoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
         self.layer_norm = nn.LayerNorm(d, eps=cfg.layer_norm_eps)
         self._engine: Optional["JLEngine"] = None
@@ -173,7 +220,8 @@ class JLEncoder(nn.Module):
         final LayerNorm, as the reference).  Also returns nothing else: use ``output_lengths`` for T' lengths."""
         eng = self.engine()
         lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
-        st = eng.forward(input_features, lengths, training=False, dialect=dialect, want_logits=False)
+        st = eng.forward(input_features, lengths, training=False, dialect=dialect, want_logits=False,
+                         sample_lengths=_sample_lengths(attention_mask, frame_lengths))
         b = input_features.shape[0]
         return st.h_final.view(b, st.t, self.config.hidden_size)
 
@@ -245,6 +293,25 @@ class JLEngine:
                 w = conv.weight.permute(0, 2, 1).reshape(cout, k * cin)[idx]
                 fz[f"conv{i}.w"] = w.to(BF16).contiguous()
                 fz[f"conv{i}.b"] = conv.bias[idx].to(F32).contiguous()
+            if self.cfg.front_end == "wav2vec2":
+                fe = self.enc.w2v
+                for i, conv in enumerate(fe.conv):
+                    cout, cin, k = conv.weight.shape
+                    w = conv.weight.permute(0, 2, 1).reshape(cout, k * cin)               # tap-major columns
+                    if i == 0:                                                              # K padded to 16 (taps k..15 are zero)
+                        w = torch.cat([w, torch.zeros((cout, 16 - k), device=w.device, dtype=w.dtype)], 1)
+                    fz[f"w2v.conv{i}.w"] = w.to(BF16).contiguous()
+                    fz[f"w2v.conv{i}.b"] = conv.bias.to(F32).contiguous()
+                fz["w2v.proj.w"] = fe.proj.weight.to(BF16).contiguous()
+                fz["w2v.proj.b"] = fe.proj.bias.to(F32).contiguous()
+                v, g = fe.pos_conv.weight_v.float(), fe.pos_conv.weight_g.float()
+                wn = g * v / v.norm(dim=(0, 1), keepdim=True)                             # weight_norm(dim = 2)
+                groups = self.cfg.num_conv_pos_embedding_groups
+                cg = wn.shape[0] // groups
+                for gi in range(groups):                                                    # per group: [cg_out, k · cg_in] tap-major
+                    wg = wn[gi * cg:(gi + 1) * cg].permute(0, 2, 1).reshape(cg, -1)
+                    fz[f"w2v.pos{gi}.w"] = wg.to(BF16).contiguous()
+                fz["w2v.pos.b"] = fe.pos_conv.bias.to(F32).contiguous()
             for i, layer in enumerate(self.enc.layers):
                 a = layer.attention
                 fz[f"{i}.wqkv"] = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).to(BF16).contiguous()
@@ -346,7 +413,16 @@ class JLEngine:
 
     # ------------------------------------------------------------------ lengths
     def output_lengths(self, input_features, attention_mask=None, frame_lengths=None) -> torch.Tensor:
-        """T' lengths (int32, device) after the two stride-2 convs."""
+        """T' lengths (int32, device) after the two stride-2 convs (mel) / the conv stack (wav2vec2: ``input_features`` is the
+        waveform batch [B, N], ``attention_mask`` its sample mask, ``frame_lengths`` the valid sample counts)."""
+        if self.cfg.front_end == "wav2vec2":
+            if frame_lengths is None:
+                if attention_mask is None:
+                    frame_lengths = torch.full((input_features.shape[0],), input_features.shape[1], dtype=I32, device=input_features.device)
+                else:
+                    frame_lengths = attention_mask.sum(-1)
+            n = wav2vec2_lengths(frame_lengths.to(torch.int64), self.cfg.conv_kernel, self.cfg.conv_stride)
+            return n.clamp_min(0).to(I32)
         if frame_lengths is None:
             if attention_mask is None:
                 frame_lengths = torch.full((input_features.shape[0],), input_features.shape[1], dtype=I32, device=input_features.device)
@@ -479,28 +555,75 @@ class JLEngine:
         return dh
 
     # ------------------------------------------------------------------ forward
+    def _wav2vec2_front_end(self, wave: torch.Tensor, sample_lengths: Optional[torch.Tensor], lengths: torch.Tensor, fz: dict):
+        """Raw waveform [B, N] fp32 (un-normalised; padded with anything) + valid sample counts → hidden states entering layer 0
+        [B·T, d] bf16 (padded rows zero) and T.  Utterance normalisation is folded into the layer-0 im2col; every convolution is
+        an im2col + tcgen05 GEMM (bias epilogue) followed by the LayerNorm+GELU kernel; the grouped positional convolution is
+        one im2col + GEMM (bias + GELU + residual epilogue) per group."""
+        cfg = self.cfg
+        if wave.dim() != 2 or wave.dtype != F32:
+            raise ValueError("wav2vec2 front end expects the waveform batch [B, N] in fp32")
+        wave = wave.contiguous()
+        b, n = wave.shape
+        if sample_lengths is None:
+            sample_lengths = torch.full((b,), n, dtype=I32, device=wave.device)
+        sample_lengths = sample_lengths.to(device=wave.device, dtype=I32)
+        ks, ss = cfg.conv_kernel, cfg.conv_stride
+        fe = self.enc.w2v
+        stats = ops.wave_stats(wave, sample_lengths)
+        t = (n - ks[0]) // ss[0] + 1
+        if t <= 0:
+            raise ValueError(f"waveform batch of {n} samples is shorter than the front end's receptive field")
+        a = ops.wave_im2col(wave, sample_lengths, stats, t, ks[0], ss[0])
+        h = None
+        for i in range(len(ks)):
+            if i > 0:
+                t_out = (t - ks[i]) // ss[i] + 1
+                if t_out <= 0:
+                    raise ValueError(f"waveform batch of {n} samples is shorter than the front end's receptive field")
+                a = ops.im2col_1d(h.view(b, t, cfg.conv_dim), t_out, ks[i], ss[i])
+                t = t_out
+            y = ops.gemm(a, fz[f"w2v.conv{i}.w"], bias=fz[f"w2v.conv{i}.b"])
+            h, _, _ = ops.layernorm_fwd(y, fe.conv_norm[i].weight.detach(), fe.conv_norm[i].bias.detach(), fe.conv_norm[i].eps, gelu=True, out=y)
+        z, _, _ = ops.layernorm_fwd(h, fe.proj_norm.weight.detach(), fe.proj_norm.bias.detach(), fe.proj_norm.eps, out=h)
+        hp = ops.gemm(z, fz["w2v.proj.w"], bias=fz["w2v.proj.b"], row_lengths=lengths, rows_per_seq=t)      # padded frames := 0
+        d, groups, kp = cfg.hidden_size, cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings
+        cg = d // groups
+        out = torch.empty_like(hp)
+        col = torch.empty((b * t, kp * cg), dtype=BF16, device=hp.device)
+        hp3 = hp.view(b, t, d)
+        for gi in range(groups):
+            ops.im2col_1d(hp3, t, kp, 1, pad=kp // 2, c0=gi * cg, cg=cg, out=col)
+            ops.gemm(col, fz[f"w2v.pos{gi}.w"], bias=fz["w2v.pos.b"][gi * cg:(gi + 1) * cg], epilogue=L.JL_EPI_GELU,
+                     residual=hp[:, gi * cg:(gi + 1) * cg], out=out[:, gi * cg:(gi + 1) * cg], row_lengths=lengths, rows_per_seq=t)
+        return out, t
+
     def forward(self, input_features: torch.Tensor, lengths: torch.Tensor, training: bool = False, dialect: int = 0,
-                want_logits: bool = True) -> _State:
+                want_logits: bool = True, sample_lengths: Optional[torch.Tensor] = None) -> _State:
         cfg = self.cfg
         d, heads = cfg.hidden_size, cfg.num_attention_heads
         fz = self._frozen_pack()
         if not input_features.is_cuda:
             raise RuntimeError("JLEngine.forward: input_features must be a CUDA tensor (no CPU fallback)")
-        b, f, nmel = input_features.shape
-        if nmel != cfg.input_feat_per_channel:
-            raise ValueError(f"expected {cfg.input_feat_per_channel} mel bins, got {nmel}")
-        x16 = input_features if input_features.dtype == BF16 else ops.cast_bf16(input_features.contiguous())
-        x16 = x16.contiguous()
         st = _State()
-        st.b, st.training, st.dialect = b, training, dialect
+        st.training, st.dialect = training, dialect
         st.lengths = lengths
-        # conv subsampler as two im2col GEMMs with fused bias + GLU
-        a1, t1 = ops.im2col_k5s2(x16)
-        c1 = ops.gemm(a1, fz["conv0.w"], bias=fz["conv0.b"], epilogue=L.JL_EPI_GLU)
-        a2, t = ops.im2col_k5s2(c1.view(b, t1, cfg.conv_channels // 2))
-        h = ops.gemm(a2, fz["conv1.w"], bias=fz["conv1.b"], epilogue=L.JL_EPI_GLU)
-        st.t = t
-        ops.embed_positions_(h, math.sqrt(d), self.pos_table(h.device, t + 2), lengths, b, t)
+        if cfg.front_end == "wav2vec2":
+            b = input_features.shape[0]
+            h, t = self._wav2vec2_front_end(input_features, sample_lengths, lengths, fz)
+        else:
+            b, f, nmel = input_features.shape
+            if nmel != cfg.input_feat_per_channel:
+                raise ValueError(f"expected {cfg.input_feat_per_channel} mel bins, got {nmel}")
+            x16 = input_features if input_features.dtype == BF16 else ops.cast_bf16(input_features.contiguous())
+            x16 = x16.contiguous()
+            # conv subsampler as two im2col GEMMs with fused bias + GLU
+            a1, t1 = ops.im2col_k5s2(x16)
+            c1 = ops.gemm(a1, fz["conv0.w"], bias=fz["conv0.b"], epilogue=L.JL_EPI_GLU)
+            a2, t = ops.im2col_k5s2(c1.view(b, t1, cfg.conv_channels // 2))
+            h = ops.gemm(a2, fz["conv1.w"], bias=fz["conv1.b"], epilogue=L.JL_EPI_GLU)
+            ops.embed_positions_(h, math.sqrt(d), self.pos_table(h.device, t + 2), lengths, b, t)
+        st.b, st.t = b, t
         scale = 1.0 / 8.0   # head_dim 64
         st.layers = []
         for i, layer in enumerate(self.enc.layers):
@@ -684,6 +807,8 @@ class JLForCTC(nn.Module):
                     m.bias.copy_((torch.rand(m.bias.shape, generator=gen) * 2 - 1) * bound)
                 elif isinstance(m, (WFAdapter, AttAdapter)):
                     m.reset_parameters(std, gen)
+                elif isinstance(m, JLWav2Vec2FrontEnd):
+                    m.reset_pos_conv(gen)
 
     # ---- adapter management
     def freeze_base_model(self) -> None:
@@ -755,14 +880,23 @@ class JLForCTC(nn.Module):
         return hf_compat.load_hf_state_dict(self, sd, strict=strict, dialect=dialect)
 
     # ---- forward
-    def forward(self, input_features: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                labels: Optional[torch.Tensor] = None, frame_lengths: Optional[torch.Tensor] = None, dialect: int = 0):
-        """→ (loss | None, logits [B, T', V]).  ``labels`` [B, S] padded with -100 (any negative value)."""
+    def forward(self, input_features: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, frame_lengths: Optional[torch.Tensor] = None, dialect=0,
+                input_values: Optional[torch.Tensor] = None):
+        """→ (loss | None, logits [B, T', V]).  ``labels`` [B, S] padded with -100 (any negative value).  ``dialect``: the
+        WFAdapter factor set — one id, or one id per utterance (utterances of one dialect adjacent).  With
+        ``front_end="wav2vec2"`` the input is the waveform batch [B, N] fp32 (``input_values``, HF's name; raw or already
+        normalised — the utterance normalisation is idempotent), ``attention_mask`` its sample mask."""
         cfg = self.config
+        if input_features is None:
+            input_features = input_values
+        if input_features is None:
+            raise ValueError("forward needs input_features (mel features) or input_values (waveforms)")
         eng = self.encoder.engine(self.lm_head)
         lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
         train = labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self._get_adapters().values())
-        st = eng.forward(input_features, lengths, training=train, dialect=dialect, want_logits=True)
+        st = eng.forward(input_features, lengths, training=train, dialect=dialect, want_logits=True,
+                         sample_lengths=_sample_lengths(attention_mask, frame_lengths))
         b, t = st.b, st.t
         logits = st.logits.view(b, t, cfg.vocab_size)
         if labels is None:

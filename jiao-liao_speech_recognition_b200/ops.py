@@ -152,7 +152,7 @@ def replay_gemm_trace(trace) -> None:
 
 # ----------------------------------------------------------------------------------------------- LayerNorm
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, save_stats: bool = False,
-                  out: Optional[torch.Tensor] = None):
+                  out: Optional[torch.Tensor] = None, gelu: bool = False):
     _need(x, BF16, "x")
     _rows2d(x, "x")
     _need(gamma, F32, "gamma", 1)
@@ -162,7 +162,8 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     mean = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
     rstd = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
     p = L.LayerNormFwdParams(x=x.data_ptr(), ldx=x.stride(0), gamma=gamma.data_ptr(), beta=beta.data_ptr(), y=y.data_ptr(),
-                             ldy=y.stride(0), mean=_ptr(mean), rstd=_ptr(rstd), rows=rows, d=d, eps=eps)
+                             ldy=y.stride(0), mean=_ptr(mean), rstd=_ptr(rstd), rows=rows, d=d, eps=eps,
+                             act=L.JL_EPI_GELU if gelu else L.JL_EPI_NONE)
     L.check(L.load().jl_layernorm_fwd(C.byref(p), _stream()))
     return y, mean, rstd
 
@@ -334,6 +335,43 @@ def im2col_k5s2(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
     out = torch.empty((b * t_out, 5 * c), dtype=BF16, device=x.device)
     L.check(L.load().jl_im2col_k5s2(x.data_ptr(), out.data_ptr(), b, t, c, t_out, _stream()))
     return out, t_out
+
+
+def wave_stats(wave: torch.Tensor, num_samples: torch.Tensor) -> torch.Tensor:
+    """wave [B, N] fp32, num_samples [B] int32 → stats [B, 2] fp32 = (mean, 1 / sqrt(var + 1e-7)) over the valid samples."""
+    _need(wave, F32, "wave", 2)
+    _need(num_samples, I32, "num_samples", 1)
+    stats = torch.empty((wave.shape[0], 2), dtype=F32, device=wave.device)
+    L.check(L.load().jl_wave_stats(wave.data_ptr(), wave.stride(0), num_samples.data_ptr(), wave.shape[0], wave.shape[1], stats.data_ptr(),
+                                   _stream()))
+    return stats
+
+
+def wave_im2col(wave: torch.Tensor, num_samples: torch.Tensor, stats: torch.Tensor, t_out: int, kernel: int, stride: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Normalised waveform windows for Conv1d(1 → C, kernel, stride): → bf16 [B · t_out, 16]."""
+    _need(wave, F32, "wave", 2)
+    _need(stats, F32, "stats", 2)
+    b = wave.shape[0]
+    if out is None:
+        out = torch.empty((b * t_out, 16), dtype=BF16, device=wave.device)
+    L.check(L.load().jl_wave_im2col(wave.data_ptr(), wave.stride(0), num_samples.data_ptr(), b, wave.shape[1], stats.data_ptr(),
+                                    out.data_ptr(), t_out, kernel, stride, _stream()))
+    return out
+
+
+def im2col_1d(x: torch.Tensor, t_out: int, kernel: int, stride: int, pad: int = 0, c0: int = 0, cg: Optional[int] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B, T_in, C] bf16 → [B · t_out, kernel · cg] bf16 (tap-major) for Conv1d(kernel, stride, pad) over channels [c0, c0 + cg)."""
+    _need(x, BF16, "x", 3)
+    if not x.is_contiguous():
+        raise ValueError("im2col_1d: x must be contiguous")
+    b, t_in, c = x.shape
+    cg = c if cg is None else cg
+    if out is None:
+        out = torch.empty((b * t_out, kernel * cg), dtype=BF16, device=x.device)
+    L.check(L.load().jl_im2col_1d(x.data_ptr(), out.data_ptr(), b, t_in, c, t_out, kernel, stride, pad, c0, cg, _stream()))
+    return out
 
 
 def embed_positions_(h: torch.Tensor, scale: float, pos_table: torch.Tensor, lengths: torch.Tensor, batch: int, seq: int) -> torch.Tensor:

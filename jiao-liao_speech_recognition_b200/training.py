@@ -18,7 +18,7 @@ from . import _lib as L
 from . import ops
 from .comm import JLComm
 from .feature_extraction import JLFeatureExtractor, device_tables, num_frames
-from .modeling import AttAdapter, GradSink, JLForCTC, subsampled_length
+from .modeling import AttAdapter, GradSink, JLForCTC, subsampled_length, wav2vec2_lengths
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 _ALIGN = 64   # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 buffer
@@ -166,6 +166,15 @@ class FlatAdapterParams(GradSink):
                    grad_scale=1.0 / world, param_bf16=self.bf16)
 
 
+def token_lengths(cfg, num_samples: torch.Tensor) -> torch.Tensor:
+    """Encoder frames T' per utterance from its sample count (host tensor), for either front end."""
+    ns = num_samples.to(torch.int64)
+    if cfg.front_end == "wav2vec2":
+        return wav2vec2_lengths(ns, cfg.conv_kernel, cfg.conv_stride).clamp_min(0).to(I32)
+    frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
+    return subsampled_length(frames).to(I32)
+
+
 def _dialect_key(dialect):
     """Hashable form of a dialect argument: an int, or a tuple of per-utterance ids."""
     if isinstance(dialect, int):
@@ -214,8 +223,11 @@ class AdapterTrainer:
         self.launches_per_step = 0
 
     def _body(self, wave, nsamp, lengths, labels, max_frames, dialect=0):
-        feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-        st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, dialect=dialect, want_logits=True)
+        if self.cfg.front_end == "wav2vec2":
+            st = self.eng.forward(wave, lengths, training=True, dialect=dialect, want_logits=True, sample_lengths=nsamp)
+        else:
+            feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
+            st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, dialect=dialect, want_logits=True)
         b, t = st.b, st.t
         logits = st.logits.view(b, t, self.cfg.vocab_size)
         loss, nll, grad = ops.ctc_loss(logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
@@ -242,11 +254,8 @@ class AdapterTrainer:
         self._graphs[key] = ent
         return ent
 
-    @staticmethod
-    def _token_lengths(num_samples: torch.Tensor) -> torch.Tensor:
-        ns = num_samples.to(torch.int64)
-        frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
-        return subsampled_length(frames).to(I32)
+    def _token_lengths(self, num_samples: torch.Tensor) -> torch.Tensor:
+        return token_lengths(self.cfg, num_samples)
 
     def submit(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor, dialect=0) -> None:
         """Stage the NEXT batch while the current step is still running: the host → device copies (pinned host memory) go to
@@ -372,8 +381,11 @@ class Transcriber:
         self.launches_per_step = 0
 
     def _body(self, wave, nsamp, lengths, max_frames, dialect=0):
-        feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-        st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True)
+        if self.cfg.front_end == "wav2vec2":
+            st = self.eng.forward(wave, lengths, training=False, dialect=dialect, want_logits=True, sample_lengths=nsamp)
+        else:
+            feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
+            st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True)
         logits = st.logits.view(st.b, st.t, self.cfg.vocab_size)
         ids, n, _ = ops.ctc_greedy(logits, lengths, blank=self.cfg.pad_token_id)
         return ids, n
@@ -392,9 +404,7 @@ class Transcriber:
             self._graphs[key] = ent
         ent["wave"].copy_(wave, non_blocking=True)
         ent["nsamp"].copy_(num_samples, non_blocking=True)
-        ns = num_samples.to(torch.int64)
-        frames = torch.where(ns < 400, torch.zeros_like(ns), (ns - 400) // 160 + 1)
-        ent["lengths"].copy_(subsampled_length(frames).to(I32), non_blocking=True)
+        ent["lengths"].copy_(token_lengths(self.cfg, num_samples), non_blocking=True)
         args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"])
         if not self.use_cuda_graph:
             L.launch_count_reset()

@@ -159,9 +159,14 @@ def encoder_layer(w: W, i: int, h: torch.Tensor, lengths: torch.Tensor, heads: i
 
 def encode(w: W, cfg, feats: torch.Tensor, frame_lengths: torch.Tensor, dialect=0):
     """[B, F, 80] CMVN features + valid frame counts → (last_hidden_state [B, T', d], T' lengths)."""
-    h = conv_subsample(w, feats)
-    lengths = subsampled_length(frame_lengths)
-    h = embed(h, lengths)
+    if getattr(cfg, "front_end", "mel") == "wav2vec2":
+        # raw-waveform front end (SURVEY §8 f3): feats = normalised waveforms [B, N], frame_lengths = valid sample counts
+        from . import w2v_frontend
+        h, lengths = w2v_frontend.front_end(w, cfg, feats, frame_lengths)
+    else:
+        h = conv_subsample(w, feats)
+        lengths = subsampled_length(frame_lengths)
+        h = embed(h, lengths)
     h = zero_padded_rows(h, lengths)
     for i in range(cfg.num_hidden_layers):
         h = encoder_layer(w, i, h, lengths, cfg.num_attention_heads, cfg.adapter_attn, cfg.adapter_ffn, dialect)

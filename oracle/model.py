@@ -43,6 +43,12 @@ class OracleConfig:
     att_dim: int = 64
     num_dialects: int = 1
     initializer_range: float = 0.02
+    front_end: str = "mel"                  # "mel" (Speech2Text conv subsampler) | "wav2vec2" (raw-waveform conv stack, §8 f3)
+    conv_dim: int = 512
+    conv_kernel: tuple = (10, 3, 3, 3, 3, 2, 2)
+    conv_stride: tuple = (5, 2, 2, 2, 2, 2, 2)
+    num_conv_pos_embeddings: int = 128
+    num_conv_pos_embedding_groups: int = 16
 
 
 def init_weights(cfg: OracleConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
@@ -86,8 +92,22 @@ def init_weights(cfg: OracleConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
         else:
             raise ValueError(kind)
 
-    conv("conv.0", cfg.conv_channels, cfg.input_feat_per_channel, 5)
-    conv("conv.1", 2 * d, cfg.conv_channels // 2, 5)
+    if cfg.front_end == "wav2vec2":
+        c = cfg.conv_dim
+        for i, k in enumerate(cfg.conv_kernel):
+            conv(f"w2v.conv.{i}", c, 1 if i == 0 else c, k)
+            w[f"w2v.conv_norm.{i}.weight"], w[f"w2v.conv_norm.{i}.bias"] = torch.ones(c), torch.zeros(c)
+        w["w2v.proj_norm.weight"], w["w2v.proj_norm.bias"] = torch.ones(c), torch.zeros(c)
+        linear("w2v.proj", d, c)
+        kp, gp = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        # modeling_wav2vec2.py:966-973: N(0, 2·sqrt(1 / (k · in_channels))) weight, zero bias; weight_norm: g = ‖v‖ per tap
+        v = torch.randn(d, d // gp, kp, generator=g) * (2.0 * math.sqrt(1.0 / (kp * d)))
+        w["w2v.pos_conv.weight_v"] = v
+        w["w2v.pos_conv.weight_g"] = v.norm(dim=(0, 1), keepdim=True)
+        w["w2v.pos_conv.bias"] = torch.zeros(d)
+    else:
+        conv("conv.0", cfg.conv_channels, cfg.input_feat_per_channel, 5)
+        conv("conv.1", 2 * d, cfg.conv_channels // 2, 5)
     for i in range(cfg.num_hidden_layers):
         p = f"layers.{i}"
         ln(p + ".layer_norm")
@@ -148,6 +168,10 @@ def forward_from_features(w, cfg: OracleConfig, feats: torch.Tensor, frame_lengt
 
 def forward_from_waveforms(w, cfg: OracleConfig, waveforms: Sequence[torch.Tensor],
                            labels: Optional[torch.Tensor] = None, dialect=0):
+    if cfg.front_end == "wav2vec2":
+        from . import w2v_frontend
+        x, ns = w2v_frontend.normalize(waveforms)
+        return forward_from_features(w, cfg, x, torch.tensor(ns), labels, dialect)
     feats, mask, flens = ofeat.extract(waveforms)
     return forward_from_features(w, cfg, feats, torch.tensor(flens), labels, dialect)
 
