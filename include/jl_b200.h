@@ -94,7 +94,9 @@ enum {
   JL_LAYOUT_MN = 1      /* operand stored with M (or N) contiguous:  A as [K, M] / B as [K, N]  */
 };
 typedef struct {
-  const void* a; int64_t lda;        /* bf16, row stride lda elements (multiple of 8); [M, K] or [K, M] per a_layout */
+  const void* a; int64_t lda;        /* bf16, row stride lda elements (multiple of 8); [M, K] or [K, M] per a_layout.  A K-major A may
+                                        have lda < K: rows then overlap in memory (sliding windows of k frames over a [T, C]
+                                        activation, lda = stride·C, K = k·C — a Conv1d without an im2col copy) */
   const void* b; int64_t ldb;        /* bf16, [N, K] or [K, N] per b_layout */
   int32_t a_layout, b_layout;        /* JL_LAYOUT_K | JL_LAYOUT_MN — MN lets dgrad (dY·W) and wgrad (dYᵀ·X) run without transposed copies */
   void* c; int64_t ldc;              /* [M, N] (N/2 columns for GLU), dtype out_dtype */

@@ -798,7 +798,8 @@ static int validate(const jl_gemm_params* p) {
              (long long)p->lda, (long long)p->ldb);
   JL_REQUIRE(p->a_layout == JL_LAYOUT_K || p->a_layout == JL_LAYOUT_MN, JL_EINVAL, "gemm: bad a_layout");
   JL_REQUIRE(p->b_layout == JL_LAYOUT_K || p->b_layout == JL_LAYOUT_MN, JL_EINVAL, "gemm: bad b_layout");
-  JL_REQUIRE(p->lda >= (p->a_layout == JL_LAYOUT_K ? p->k : p->m), JL_EINVAL, "gemm: lda too small");
+  // K-major A may have lda < K: rows that overlap in memory (sliding windows over a [T, C] activation — a Conv1d without im2col)
+  JL_REQUIRE(p->lda >= (p->a_layout == JL_LAYOUT_K ? 8 : p->m), JL_EINVAL, "gemm: lda too small");
   JL_REQUIRE(p->ldb >= (p->b_layout == JL_LAYOUT_K ? p->k : p->n), JL_EINVAL, "gemm: ldb too small");
   JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_GLU, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
   JL_REQUIRE(p->out_dtype == JL_DT_BF16 || p->out_dtype == JL_DT_F32, JL_EINVAL, "gemm: unknown out_dtype %d", p->out_dtype);

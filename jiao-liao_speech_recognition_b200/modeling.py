@@ -570,20 +570,27 @@ class JLEngine:
         sample_lengths = sample_lengths.to(device=wave.device, dtype=I32)
         ks, ss = cfg.conv_kernel, cfg.conv_stride
         fe = self.enc.w2v
+        c = cfg.conv_dim
         stats = ops.wave_stats(wave, sample_lengths)
-        t = (n - ks[0]) // ss[0] + 1
-        if t <= 0:
+        t_valid = (n - ks[0]) // ss[0] + 1
+        if wav2vec2_lengths(n, ks, ss) <= 0:
             raise ValueError(f"waveform batch of {n} samples is shorter than the front end's receptive field")
+        # No im2col for layers 1..: k consecutive frames of a [T, C] activation are contiguous, so the GEMM's A operand is a view
+        # with row stride s·C and row length k·C (rows overlap in memory).  Every utterance gets the same number of rows per
+        # layer; that needs T_0 to be a multiple of the product of the later strides (the extra windows compute don't-care rows).
+        prod = 1
+        for s_ in ss[1:]:
+            prod *= s_
+        t = (t_valid + prod - 1) // prod * prod
         a = ops.wave_im2col(wave, sample_lengths, stats, t, ks[0], ss[0])
         h = None
         for i in range(len(ks)):
             if i > 0:
-                t_out = (t - ks[i]) // ss[i] + 1
-                if t_out <= 0:
-                    raise ValueError(f"waveform batch of {n} samples is shorter than the front end's receptive field")
-                a = ops.im2col_1d(h.view(b, t, cfg.conv_dim), t_out, ks[i], ss[i])
-                t = t_out
-            y = ops.gemm(a, fz[f"w2v.conv{i}.w"], bias=fz[f"w2v.conv{i}.b"])
+                t = t // ss[i]
+                a = torch.as_strided(h, (b * t, ks[i] * c), (ss[i] * c, 1))
+            buf = torch.empty((b * t + 8, c), dtype=BF16, device=wave.device)     # slack rows: the last windows of the next layer
+            buf[b * t:].zero_()
+            y = ops.gemm(a, fz[f"w2v.conv{i}.w"], bias=fz[f"w2v.conv{i}.b"], out=buf[: b * t])
             h, _, _ = ops.layernorm_fwd(y, fe.conv_norm[i].weight.detach(), fe.conv_norm[i].bias.detach(), fe.conv_norm[i].eps, gelu=True, out=y)
         z, _, _ = ops.layernorm_fwd(h, fe.proj_norm.weight.detach(), fe.proj_norm.bias.detach(), fe.proj_norm.eps, out=h)
         hp = ops.gemm(z, fz["w2v.proj.w"], bias=fz["w2v.proj.b"], row_lengths=lengths, rows_per_seq=t)      # padded frames := 0

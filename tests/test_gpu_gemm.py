@@ -246,3 +246,21 @@ def test_gemm_tail_split_matches_unsplit_and_reference(m, n, k, epi):
     z = a.float() @ b.float().t()
     if epi == "plain":
         assert rel_err(out1.float(), z) < 1e-2
+
+
+@pytest.mark.parametrize("k,s,c,t", [(3, 2, 64, 400), (2, 2, 512, 1000), (3, 2, 512, 3001)])
+def test_gemm_overlapping_a_rows_is_a_conv1d_without_im2col(k, s, c, t):
+    """K-major A with lda < K: row r is the window of k consecutive frames starting at frame s·r of a [T, C] activation
+    (rows overlap in memory) — the GEMM then equals Conv1d(C → N, k, stride s) over the frames."""
+    ops, L = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.randn(t + 8, c, device="cuda", generator=g) * 0.5).to(BF16)
+    w = (torch.randn(96, k * c, device="cuda", generator=g) * 0.1).to(BF16)
+    rows = (t - k) // s + 1
+    a = torch.as_strided(x, (rows, k * c), (s * c, 1))
+    out = ops.gemm(a, w, out_dtype=F32)
+    ref = a.float() @ w.float().t()                      # as_strided materialises the windows on the torch side
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-3
+    conv = torch.nn.functional.conv1d(x[:t].float().t()[None], w.float().view(96, k, c).permute(0, 2, 1), stride=s)[0].t()
+    assert rel_err(out, conv) < 2e-3
