@@ -416,6 +416,7 @@ static int attn_check(const void* q, const void* k, const void* v, int64_t ld_qk
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream);   // attention_tc.cu
 int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream);
 extern int g_attn_fwd_ctas;
+extern int g_attn_short;
 static std::atomic<int> g_attn_impl{0};   // 0 = tcgen05 kernels, 1 = mma.sync kernels
 
 }  // namespace jl
@@ -423,8 +424,10 @@ static std::atomic<int> g_attn_impl{0};   // 0 = tcgen05 kernels, 1 = mma.sync k
 extern "C" {
 
 void jl_debug_set_attn_impl(int impl) {
-  // 0 = tcgen05 kernels (forward compiled for 2 CTAs/SM), 1 = mma.sync kernels, 2 = tcgen05 with the 3-CTAs/SM forward build
+  // 0 = tcgen05 kernels (short-sequence forward for <= 256 frames, else the key-block forward compiled for 2 CTAs/SM),
+  // 1 = mma.sync kernels, 2 = tcgen05 with the 3-CTAs/SM key-block forward, 3 = tcgen05 with the key-block forward at every length
   jl::g_attn_fwd_ctas = (impl == 2) ? 3 : 2;
+  jl::g_attn_short = (impl == 0) ? 1 : 0;
   jl::g_attn_impl.store(impl == 1 ? 1 : 0);
 }
 

@@ -304,6 +304,190 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
 }
 
+// ================================================================================================ forward, seq <= 256
+// Utterances of at most 256 frames (10.2 s at 40 ms): one CTA per (utterance, head, 128-query tile) computes the whole score
+// tile S = Q · Kᵀ (M 128 × N 256) with one group of MMAs.  The softmax sees whole rows, so it is the plain two-pass form (max,
+// then exp / sum while writing P) — no online rescale, no key-block loop and none of its hand-offs; O = P · V runs as up to 16
+// MMAs (K = 256 keys) into TMEM columns S no longer needs, and P overwrites the Q / K staging area once the score MMAs have
+// completed.  The dependency chain of a CTA is load → S → softmax → PV → store, once, instead of once per key block; 256 TMEM
+// columns and 98 KB of shared memory keep two CTAs per SM so that one CTA's chain overlaps the other's.
+constexpr uint32_t TS_IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);   // M128 N256, A,B K-major
+
+struct __align__(1024) AttnFwdShortSmem {
+  uint8_t q[TC_T128];              // ┐
+  uint8_t k[4][TC_T64];            // │ 64 KB: Q, K (one [256 × 64] K-major B operand) — later P (4 key tiles of [128 × 64])
+  uint8_t p_tail[TC_T128];         // ┘
+  uint8_t v[4][TC_T64];            // V, 64-key tiles, read as MN-major B operands
+  float red_max[2][TC_OUTER];      // [column half][row]
+  float red_sum[2][TC_OUTER];
+  uint64_t qk_full, v_full, s_full, p_full, o_full;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                      const jl_attn_fwd_params p) {
+  const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ uint8_t tc_smem_raw[];
+  AttnFwdShortSmem& s = *reinterpret_cast<AttnFwdShortSmem*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tq);
+    ptx::prefetch_tensormap(&tk);
+    ptx::prefetch_tensormap(&tv);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(&s.qk_full, 1);
+    ptx::mbar_init(&s.v_full, 1);
+    ptx::mbar_init(&s.s_full, 1);
+    ptx::mbar_init(&s.p_full, 8);
+    ptx::mbar_init(&s.o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&s.tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  jl::pdl_prologue();     // everything above overlaps the preceding kernel; `lengths` and q / k / v may come from it
+  const uint32_t tmem = s.tmem_slot;
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const int grow = static_cast<int>(row_base);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
+  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
+  const bool active = g * TC_OUTER < len;                     // the query tile has at least one valid row
+  const int nkt = (len + TC_INNER - 1) / TC_INNER;            // 64-key tiles with at least one valid key: 0..4
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      ptx::mbar_expect_tx(&s.qk_full, TC_T128 + nkt * TC_T64);
+      ptx::tma_load_2d(s.q, &tq, &s.qk_full, h * 64, grow + g * TC_OUTER);
+      for (int j = 0; j < nkt; ++j) ptx::tma_load_2d(s.k[j], &tk, &s.qk_full, h * 64, grow + j * TC_INNER);
+      ptx::mbar_expect_tx(&s.v_full, nkt * TC_T64);
+      for (int j = 0; j < nkt; ++j) ptx::tma_load_2d(s.v[j], &tv, &s.v_full, h * 64, grow + j * TC_INNER);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      ptx::mbar_wait(&s.qk_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t q_addr = ptx::smem_u32(s.q), k_addr = ptx::smem_u32(s.k[0]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        ptx::umma_bf16(tmem, ptx::make_sw128_desc(q_addr + kk * 32, 16, 1024), ptx::make_sw128_desc(k_addr + kk * 32, 16, 1024), TS_IDESC_S,
+                       kk > 0 ? 1u : 0u);
+      ptx::umma_commit(&s.s_full);
+      ptx::mbar_wait(&s.v_full, 0);
+      ptx::mbar_wait(&s.p_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t p_base = ptx::smem_u32(s.q);
+      for (int kt = 0; kt < nkt; ++kt) tc_mma_64(tmem, p_base + kt * TC_T128, ptx::smem_u32(s.v[kt]), true, kt > 0);      // O += P[:, kt] · V_kt
+      ptx::umma_commit(&s.o_full);
+    }
+  } else if (warp >= 4) {
+    const int half = (warp - 4) >> 2;                         // which 128 of the 256 key columns
+    const int r = (warp & 3) * 32 + lane;                     // TMEM lane = query row of the tile
+    const int row = g * TC_OUTER + r;                         // row of the utterance
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    if (!active) {
+      // the whole query tile is padding (or the utterance is empty): zero rows, nothing to compute
+      if (row < p.seq) {
+        uint4* dst = reinterpret_cast<uint4*>(o + static_cast<int64_t>(row) * p.ld_o + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (lse && half == 0) lse[row] = 0.0f;
+      }
+    } else {
+      const uint32_t t_s = tmem + lane_off + 128u * half;
+      const float sl2 = p.scale * TC_LOG2E;
+      const int kbase = half * 128;
+      ptx::mbar_wait(&s.s_full, 0);
+      ptx::tc_fence_after();
+      // ---- pass 1: row maximum over this thread's 128 columns (two TMEM loads in flight)
+      float mloc = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t sa[32], sb[32];
+        ptx::tmem_ld_32x32(t_s + 32u * c, sa);
+        ptx::tmem_ld_32x32(t_s + 32u * (c + 1), sb);
+        ptx::tmem_ld_wait();
+        const int k0 = kbase + 32 * c;
+        if (k0 + 64 <= len) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sb[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (k0 + i < len) mloc = fmaxf(mloc, __uint_as_float(sa[i]));
+            if (k0 + 32 + i < len) mloc = fmaxf(mloc, __uint_as_float(sb[i]));
+          }
+        }
+      }
+      s.red_max[half][r] = mloc;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mx = fmaxf(mloc, s.red_max[half ^ 1][r]);         // finite: len >= 1 valid key
+      const float mxs = mx * sl2;
+      // ---- pass 2: exp, row sum, P as the K-major 128B-swizzled A operand of the PV MMAs (over the Q / K staging area: the
+      //      score MMAs, whose completion s_full signalled, were its last readers)
+      float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        ptx::tmem_ld_32x32(t_s + 32u * c, sv);
+        ptx::tmem_ld_wait();
+        const int k0 = kbase + 32 * c;
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = tc_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -mxs));
+          float e = tc_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -mxs));
+          if (k0 + 2 * i >= len) a = 0.0f;
+          if (k0 + 2 * i + 1 >= len) e = 0.0f;
+          sum0 += a;
+          sum1 += e;
+          packed[i] = pack_bf16x2(a, e);
+        }
+        uint8_t* tile = s.q + ((k0 >> 6) * TC_T128);                // key tile of 64 columns
+        const int chunk0 = ((k0 & 63) >> 3);                        // first 16-byte chunk inside the tile row: 0 or 4
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t t0[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t0[i] = packed[8 * c2 + i];
+          tc_store_cols16(tile, r, chunk0 + 2 * c2, t0);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s.p_full);
+      s.red_sum[half][r] = sum0 + sum1;
+      // ---- epilogue: O / l  (O occupies the first 64 of the score columns)
+      ptx::mbar_wait(&s.o_full, 0);
+      ptx::tc_fence_after();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float l_tot = (sum0 + sum1) + s.red_sum[half ^ 1][r];
+      const float inv = (row < len) ? 1.0f / l_tot : 0.0f;
+      uint32_t ov[32];
+      ptx::tmem_ld_32x32(tmem + lane_off + 32u * half, ov);
+      ptx::tmem_ld_wait();
+      float of[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
+      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
+      if (lse && half == 0 && row < p.seq) lse[row] = (row < len) ? mx * p.scale + logf(l_tot) : 0.0f;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
 // ================================================================================================ backward
 // MODE 0: dQ   (outer rows = queries; X1 = Q, X2 = dO; inner: Y1 = K_j, Y2 = V_j;  acc0 = dQ += dS · K_j)
 // MODE 1: dKV  (outer rows = keys;    X1 = K, X2 = V;  inner: Y1 = Q_i, Y2 = dO_i; acc0 = dV += Pᵀ · dO_i, acc1 = dK += dSᵀ · Q_i)
@@ -531,6 +715,7 @@ static int tc_set_smem(K kern, size_t bytes, const char* name) {
 }
 
 int g_attn_fwd_ctas = 2;   // resident CTAs per SM the forward kernel is compiled for
+int g_attn_short = 1;      // 1: utterances of <= 256 frames take the one-CTA-per-(utterance, head) forward kernel
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
@@ -540,6 +725,20 @@ int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   if (rc == JL_OK) rc = make_tma_map_2d_bf16(&tk, p->k, inner, rows, p->ld_qkv, TC_INNER);
   if (rc == JL_OK) rc = make_tma_map_2d_bf16(&tv, p->v, inner, rows, p->ld_qkv, TC_INNER);
   if (rc != JL_OK) return rc;
+  if (g_attn_short && p->seq <= 2 * TC_OUTER) {
+    const size_t smem_s = sizeof(AttnFwdShortSmem) + 1024;
+    static thread_local int configured_short = -1;
+    int dev_s = 0;
+    cudaGetDevice(&dev_s);
+    if (configured_short != dev_s) {
+      rc = tc_set_smem(attn_fwd_short_kernel, smem_s, "attn_fwd_short");
+      if (rc != JL_OK) return rc;
+      configured_short = dev_s;
+    }
+    jl::launch(attn_fwd_short_kernel, dim3(ceil_div(p->seq, TC_OUTER), p->heads, p->batch), TC_THREADS, smem_s, stream, tq, tk, tv, *p);
+    JL_CHECK_LAUNCH("attn_fwd_short");
+    return JL_OK;
+  }
   const size_t smem = sizeof(AttnFwdSmem) + 1024;
   static thread_local int configured_dev = -1;
   int dev = 0;

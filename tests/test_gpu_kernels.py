@@ -59,7 +59,7 @@ def _attn_ref(q, k, v, lengths, b, t, h, scale):
     return o * valid.reshape(b * t, 1)
 
 
-@pytest.fixture(params=[0, 1], ids=["tcgen05", "mma_sync"])
+@pytest.fixture(params=[0, 1, 3], ids=["tcgen05", "mma_sync", "tcgen05_keyblock_fwd"])
 def attn_impl(request):
     lib = pkg()._lib.load()
     lib.jl_debug_set_attn_impl(request.param)
@@ -68,7 +68,7 @@ def attn_impl(request):
 
 
 @pytest.mark.parametrize("b,t,h,lens", [(3, 250, 12, [250, 131, 64]), (2, 70, 1, [70, 1]), (2, 750, 2, [750, 300]), (1, 33, 3, [20]),
-                                        (4, 128, 2, [128, 65, 64, 0])])
+                                        (4, 128, 2, [128, 65, 64, 0]), (4, 256, 3, [256, 129, 128, 193]), (2, 257, 1, [257, 200])])
 def test_attention_fwd_bwd(attn_impl, b, t, h, lens):
     ops = pkg().ops
     g = _g(2)
