@@ -321,8 +321,11 @@ void jl_debug_set_attn_impl(int impl);
 void jl_debug_set_gemm_mode(int mode);
 /* test / tuning hook: force the N tile (32/64/128/256 single-CTA kernel, 128/192/256 pair kernel with mode 2); 0 = automatic */
 void jl_debug_set_gemm_bn(int bn);
-/* test / tuning hook: 0 = never split the tail wave of the pair kernel, 1 (default) = split it when a workspace is supplied */
-void jl_debug_set_gemm_tail(int on);
+/* test / tuning hook — what happens to the last, partial wave of output tiles (bit mask, default 2):
+ *   bit 1 (2): single-CTA kernel: the tail tiles are cut into 2 or 4 column slices (independent, shorter work units);
+ *   bit 0 (1): CTA-pair kernel: the tail tiles are cut into K ranges with an in-kernel fix-up (needs the workspace;
+ *              validated, measured slower, off by default) */
+void jl_debug_set_gemm_tail(int mode);
 
 /* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
  * sizes the CPU oracle cannot reach; never called by the product path. */

@@ -56,6 +56,10 @@ struct GemmDev {
   // tail split (pair kernel): tiles [tail_first, num_tiles) are the partial last wave; each is cut into tail_split K ranges that
   // run on otherwise idle CTA pairs, raw partial accumulators go to tail_ws and the LAST range to arrive (per epilogue warp,
   // counted in tail_cnt) adds them in range order and applies the epilogue — no CTA ever waits for another one.
+  // N split of the tail wave (single-CTA kernel): tiles [nsplit_first, tiles) — the partial last wave — are cut into nsplit
+  // column slices of BN / nsplit, each an independent (shorter) work unit: the tail wave then takes 1 / nsplit of a tile time
+  // and needs no partial sums.
+  int32_t nsplit_first, nsplit;
   int32_t tail_first, tail_split, tail_kb_per;
   int64_t tail_stride;     // floats per K range in tail_ws = tail tiles · 256 · BN
   float* tail_ws;
@@ -305,9 +309,37 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
 };
 
+// One schedulable piece of the single-CTA kernel: (output tile, K split) or (tail tile, column slice).
+struct CtaUnit {
+  int tile, split, n0, bn;
+};
+template <int BN>
+__device__ __forceinline__ CtaUnit cta_unit(const GemmDev& g, int u) {
+  CtaUnit r;
+  int sub = 0;
+  r.bn = BN;
+  if (g.nsplit > 1) {
+    r.split = 0;
+    if (u < g.nsplit_first) {
+      r.tile = u;
+    } else {
+      const int v = u - g.nsplit_first;
+      r.tile = g.nsplit_first + v / g.nsplit;
+      sub = v - (r.tile - g.nsplit_first) * g.nsplit;
+      r.bn = BN / g.nsplit;
+    }
+  } else {
+    r.tile = u / g.split_k;
+    r.split = u - r.tile * g.split_k;
+  }
+  r.n0 = (r.tile % g.num_n_tiles) * BN + sub * r.bn;
+  return r;
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev g) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b_sub,
+                    const GemmDev g) {
   jl::pdl_launch_dependents();
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -326,12 +358,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = g.num_m_tiles * g.num_n_tiles * g.split_k;      // work units: (output tile, K split)
+  const int out_tiles = g.num_m_tiles * g.num_n_tiles;
+  // work units: (output tile, K split), or whole tiles followed by the column slices of the tail tiles
+  const int num_tiles = (g.nsplit > 1) ? g.nsplit_first + (out_tiles - g.nsplit_first) * g.nsplit : out_tiles * g.split_k;
   const int num_kb_total = (g.k + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
+    if (g.nsplit > 1) ptx::prefetch_tensormap(&tma_b_sub);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -360,14 +395,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x) {
-        const int tile = unit / g.split_k, split = unit - tile * g.split_k;
+        const CtaUnit un = cta_unit<BN>(g, unit);
+        const int tile = un.tile, split = un.split;
         const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
-        const int n0 = (tile % g.num_n_tiles) * BN;
+        const int n0 = un.n0;
+        const bool sliced = un.bn != BN;                       // column slice of a tail tile (K-major B only)
         const int kb_begin = split * g.kb_per_split;
         const int kb_end = min(num_kb_total, kb_begin + g.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(empty_bar + stage, phase ^ 1u);
-          ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
+          ptx::mbar_expect_tx(full_bar + stage, sliced ? GEMM_A_BYTES + un.bn * GEMM_BK * 2 : L::STAGE_BYTES);
           uint8_t* a_dst = s_a + stage * GEMM_A_BYTES;
           uint8_t* b_dst = s_b + stage * L::B_BYTES;
           const int k0 = kb * GEMM_BK;
@@ -381,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) ptx::tma_load_2d(b_dst + i * 8192, &tma_b, full_bar + stage, n0 + 64 * i, k0);
           } else {
-            ptx::tma_load_2d(b_dst, &tma_b, full_bar + stage, k0, n0);
+            ptx::tma_load_2d(b_dst, sliced ? &tma_b_sub : &tma_b, full_bar + stage, k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -391,14 +428,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      constexpr uint32_t idesc_full = ptx::make_idesc_bf16_f32(GEMM_BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int split = unit % g.split_k;
+        const CtaUnit un = cta_unit<BN>(g, unit);
+        const int split = un.split;
+        // the N field (bits 17-22, N >> 3) of the instruction descriptor is the only thing a column slice changes
+        const uint32_t idesc = (un.bn == BN) ? idesc_full : ((idesc_full & ~(0x3Fu << 17)) | (static_cast<uint32_t>(un.bn >> 3) << 17));
         const int num_kb = min(num_kb_total, (split + 1) * g.kb_per_split) - split * g.kb_per_split;
         ptx::mbar_wait(tempty_bar + as, aphase ^ 1u);
         ptx::tc_fence_after();
@@ -430,21 +470,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int unit = blockIdx.x; unit < num_tiles; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int tile = unit / g.split_k, split = unit - tile * g.split_k;
+      const CtaUnit un = cta_unit<BN>(g, unit);
+      const int tile = un.tile, split = un.split;
       const int m0 = (tile / g.num_n_tiles) * GEMM_BM;
-      const int n0 = (tile % g.num_n_tiles) * BN;
+      const int n0 = un.n0;
+      const int nchunks = un.bn / 32;
       ptx::mbar_wait(tfull_bar + as, aphase);
       ptx::tc_fence_after();
       const int row = m0 + quad * 32 + lane;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += GEMM_EPI_WARPS / 4) {
+      for (int c = half; c < nchunks; c += GEMM_EPI_WARPS / 4) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32);
         ptx::tmem_ld_32x32(taddr, v);
         EpiPrefetch pf;
         if (g.split_k == 1) epi_prefetch(g, row, n0 + c * 32, pf);
         ptx::tmem_ld_wait();
-        if (c + GEMM_EPI_WARPS / 4 >= BN / 32) {
+        if (c + GEMM_EPI_WARPS / 4 >= nchunks) {
           // this warp's last chunk is in registers: hand the accumulator stage back BEFORE the epilogue math and stores (the
           // release semantics of the arrive would otherwise wait for this tile's global stores to be acknowledged)
           ptx::tc_fence_before();
@@ -462,7 +504,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           gemm_epilogue_row32(g, row, n0 + c * 32, acc, pf);
         }
       }
-      if (half >= BN / 32) {          // a warp without a chunk of this tile still owes its arrival
+      if (half >= nchunks) {          // a warp without a chunk of this tile still owes its arrival
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty_bar + as);
@@ -860,9 +902,11 @@ static size_t splitk_ws_bytes(const jl_gemm_params* p) {
   return static_cast<size_t>(s) * p->m * ldw * sizeof(float);
 }
 
+static std::atomic<int> g_gemm_tail{2};   // bit 0: K-range split of the pair kernel's tail wave (needs a workspace; measured slower, off); bit 1: column slices of the single-CTA kernel's tail wave (on)
 static GemmDev to_dev(const jl_gemm_params* p, int bn) {
   GemmDev g;
   g.split_k = 1; g.kb_per_split = ceil_div(p->k, GEMM_BK); g.ws = nullptr; g.ldw = 0;
+  g.nsplit_first = 0; g.nsplit = 1;
   g.tail_first = 0; g.tail_split = 1; g.tail_kb_per = g.kb_per_split; g.tail_stride = 0; g.tail_ws = nullptr; g.tail_cnt = nullptr;
   g.c = p->c; g.ldc = p->ldc;
   g.bias = p->bias;
@@ -909,9 +953,23 @@ static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
       g.ldw = (static_cast<int64_t>(p->n) + 3) & ~static_cast<int64_t>(3);
     }
   }
-  const int units = g.num_m_tiles * g.num_n_tiles * g.split_k;
+  int units = g.num_m_tiles * g.num_n_tiles * g.split_k;
+  CUtensorMap mbs = mb;
+  if (!B_MN && BN >= 128 && g.split_k == 1 && (g_gemm_tail.load() & 2)) {
+    // the last, partial wave of tiles as column slices: [tail · nsplit <= SMs] → it takes 1 / nsplit of a tile time
+    const int sms = num_sms();
+    const int first = (units / sms) * sms, tail = units - first;
+    const int ns = (tail == 0) ? 1 : (BN >= 256 && tail * 4 <= sms) ? 4 : (tail * 2 <= sms ? 2 : 1);
+    if (ns > 1) {
+      rc = make_map(&mbs, p->b, p->k, p->n, p->ldb, BN / ns);
+      if (rc != JL_OK) return rc;
+      g.nsplit_first = first;
+      g.nsplit = ns;
+      units = first + tail * ns;
+    }
+  }
   const int grid = units < num_sms() ? units : num_sms();
-  jl::launch(kern, grid, GEMM_THREADS, L::TOTAL, stream, ma, mb, g);
+  jl::launch(kern, grid, GEMM_THREADS, L::TOTAL, stream, ma, mb, mbs, g);
   JL_CHECK_LAUNCH("gemm_tcgen05");
   if (g.split_k > 1) {
     const int64_t total = static_cast<int64_t>(p->m) * p->n;
@@ -935,7 +993,6 @@ static int dispatch_layout(const jl_gemm_params* p, cudaStream_t s) {
 }
 
 // Pick the N tile: fewest (waves × per-tile cost) over the candidates; per-tile cost ∝ BN plus a fixed part.
-static std::atomic<int> g_gemm_tail{0};   // 1 = split the tail wave of the pair kernel when a workspace is supplied; off by default: measured slower
 static std::atomic<int> g_gemm_bn{0};     // tuning hook: 0 = automatic N tile, else the N tile forced on the kernel the mode selects
 static int pick_bn(const jl_gemm_params* p) {
   const bool bmn = p->b_layout == JL_LAYOUT_MN;
@@ -977,7 +1034,7 @@ static TailPlan plan_tail(const jl_gemm_params* p, int bn, bool allow_split) {
   const int tail = tiles % pairs;
   t.first = tiles; t.kb_per = num_kb;
   t.waves = static_cast<double>(ceil_div(tiles, pairs));
-  if (!allow_split || tail == 0 || g_gemm_tail.load() == 0 || p->a_layout == JL_LAYOUT_MN) return t;
+  if (!allow_split || tail == 0 || (g_gemm_tail.load() & 1) == 0 || p->a_layout == JL_LAYOUT_MN) return t;
   int want = pairs / tail;
   if (want > 4) want = 4;
   if (want > num_kb / 4) want = num_kb / 4;
@@ -1154,7 +1211,7 @@ int jl_gemm_workspace_zero_bytes(const jl_gemm_params* p, size_t* out) {
   return JL_OK;
 }
 
-void jl_debug_set_gemm_tail(int on) { jl::g_gemm_tail.store(on ? 1 : 0); }
+void jl_debug_set_gemm_tail(int mode) { jl::g_gemm_tail.store(mode & 3); }
 
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {
   int rc = jl::validate(p);

@@ -237,7 +237,7 @@ def test_gemm_tail_split_matches_unsplit_and_reference(m, n, k, epi):
         assert _tail_bytes(ops, L, a, b, **kw)[0] == 0
         unsplit = ops.gemm(a, b, **kw)
     finally:
-        lib.jl_debug_set_gemm_tail(0)
+        lib.jl_debug_set_gemm_tail(2)          # default: column slices in the single-CTA kernel only
         lib.jl_debug_set_gemm_mode(0)
     ref = ops.gemm(a, b, reference=True, **kw)
     torch.cuda.synchronize()
@@ -264,3 +264,39 @@ def test_gemm_overlapping_a_rows_is_a_conv1d_without_im2col(k, s, c, t):
     assert rel_err(out, ref) < 2e-3
     conv = torch.nn.functional.conv1d(x[:t].float().t()[None], w.float().view(96, k, c).permute(0, 2, 1), stride=s)[0].t()
     assert rel_err(out, conv) < 2e-3
+
+
+@pytest.mark.parametrize("m,n,k,epi", [(8000, 768, 768, "bias_res"), (8000, 768, 3072, "plain"), (8000, 256, 512, "gelu"), (5000, 512, 1024, "relu"),
+                                       (8000, 1000, 768, "plain")])
+def test_gemm_tail_wave_as_column_slices(m, n, k, epi):
+    """Single-CTA kernel: the partial last wave of 128 x BN tiles runs as 2 or 4 column slices per tile (independent work
+    units, no partial sums): bit-identical to the unsliced schedule — every output element has the same K summation order."""
+    ops, L = _ops()
+    lib = L.load()
+    a, b, _, _ = _mk(m, n, k, seed=4)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    kw = {}
+    if epi in ("bias_res", "gelu", "relu"):
+        kw["bias"] = torch.randn(n, device="cuda", generator=g)
+    if epi == "bias_res":
+        kw["residual"] = torch.randn(m, n, device="cuda", generator=g).to(BF16)
+    if epi == "gelu":
+        kw["epilogue"] = L.JL_EPI_GELU
+    if epi == "relu":
+        kw["epilogue"] = L.JL_EPI_RELU
+    lib.jl_debug_set_gemm_mode(1)              # single-CTA kernel
+    try:
+        for bn in (256, 128):
+            lib.jl_debug_set_gemm_bn(bn)
+            lib.jl_debug_set_gemm_tail(2)
+            sliced = ops.gemm(a, b, **kw).clone()
+            lib.jl_debug_set_gemm_tail(0)
+            whole = ops.gemm(a, b, **kw).clone()
+            torch.cuda.synchronize()
+            assert torch.equal(sliced, whole), (bn, float((sliced.float() - whole.float()).abs().max()))
+        ref = ops.gemm(a, b, reference=True, **kw)
+        assert rel_err(sliced.float(), ref.float()) < 1e-2
+    finally:
+        lib.jl_debug_set_gemm_tail(2)
+        lib.jl_debug_set_gemm_bn(0)
+        lib.jl_debug_set_gemm_mode(0)
