@@ -87,7 +87,10 @@ enum {
   JL_EPI_RELU = 2,
   JL_EPI_GELU_BWD = 3,  /* C = acc * gelu'(aux)          (aux = saved pre-activation, bf16) */
   JL_EPI_RELU_BWD = 4,  /* C = acc * (aux > 0)           (aux = saved post-activation, bf16) */
-  JL_EPI_GLU = 5        /* C[:, j] = v[2j] * sigmoid(v[2j+1]); C has N/2 columns (interleaved weight rows) */
+  JL_EPI_GLU = 5,       /* C[:, j] = v[2j] * sigmoid(v[2j+1]); C has N/2 columns (interleaved weight rows) */
+  JL_EPI_GELU_DGELU = 6,/* erf GELU to C and its derivative gelu'(pre-activation) to aux_out (bf16, required): the training
+                         * forward of the FFN input projection — erf is evaluated once per element, not again in backward */
+  JL_EPI_MUL_AUX = 7    /* C = acc * aux                   (aux = saved activation derivative, bf16) */
 };
 enum {
   JL_LAYOUT_K = 0,      /* operand stored with K contiguous:  A[M, K] / B[N, K]  (nn.Linear layout) */

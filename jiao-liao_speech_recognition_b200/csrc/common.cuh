@@ -111,19 +111,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // erf-form GELU (SP/transformers/activations.py "gelu") and its derivative.  erf via Abramowitz & Stegun 7.1.26
-// (|error| <= 1.5e-7 — far below the bf16 rounding of the stored result): one MUFU.RCP, one MUFU.EX2 and six FMAs, so the
-// GEMM epilogue stays under the ≈ 24 issue slots per output element that a K = 768 mainloop leaves it.
-//   q(v) = 0.5 · (1 − erf(|v|/√2)) = 0.5 · poly(t) · exp(−v²/2),  t = 1 / (1 + p·|v|/√2)
+// (|error| <= 1.5e-7 — far below the bf16 rounding of the stored result).  With s = |v|·√(log2(e)/2):
+//   q(v) = 0.5 · (1 − erf(|v|/√2)) = 0.5 · poly(t) · 2^(−s²),  t = 1 / (1 + (p/√log2(e))·s)
 //   Φ(v) = v >= 0 ? 1 − q : q;   gelu(v) = v · Φ(v);   gelu'(v) = Φ(v) + v · exp(−v²/2) / √(2π)
+// The two MUFU operations are the raw rcp.approx / ex2.approx (their arguments are >= 1 and <= 0: none of the denormal
+// guards of __fdividef / exp2f is needed), which leaves 12 issue slots per element — the GEMM epilogue has to stay under
+// the ≈ 40 slots per output element a K = 768 mainloop gives it (profiles/r1m_gemm_epilogues.md).
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_parts(float v, float& cdf, float& e) {
-  const float ax = fabsf(v) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float s = fabsf(v) * 0.8493218002880191f;
+  const float t = mufu_rcp(fmaf(0.2727374808792225f, s, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  e = exp2f(-ax * ax * 1.4426950408889634f);       // exp(−v²/2)
+  e = mufu_ex2(-s * s);                            // exp(−v²/2)
   const float q = 0.5f * poly * e;
   cdf = (v >= 0.0f) ? 1.0f - q : q;
 }
@@ -136,6 +148,17 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   float cdf, e;
   gelu_parts(x, cdf, e);
   return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+// value and derivative from one evaluation (the forward FFN epilogue that saves gelu' for the backward pass)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228040143268f, e, cdf);
+}
+// logistic function with one MUFU.EX2 and one MUFU.RCP (GLU gate)
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * x));      // x → −∞: ex2 = +inf, rcp(+inf) = 0
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -183,7 +183,7 @@ __device__ __forceinline__ bool epi_res_vec(const GemmDev& g, int row, int col0)
   return g.residual != nullptr && row < g.m && col0 + 32 <= g.n && (g.ldr & 7) == 0 && g.epilogue != JL_EPI_GLU;
 }
 __device__ __forceinline__ bool epi_aux_vec(const GemmDev& g, int row, int col0) {
-  return (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) && row < g.m && col0 + 32 <= g.n && (g.ldaux & 7) == 0;
+  return (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD || g.epilogue == JL_EPI_MUL_AUX) && row < g.m && col0 + 32 <= g.n && (g.ldaux & 7) == 0;
 }
 __device__ __forceinline__ void epi_prefetch(const GemmDev& g, int row, int col0, EpiPrefetch& pf) {
   if (epi_res_vec(g, row, col0)) epi_load_row(g.residual + static_cast<int64_t>(row) * g.ldr + col0, pf.res);
@@ -237,7 +237,7 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, i
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float val = acc[2 * j], gate = acc[2 * j + 1];
-      o[j] = zero_row ? 0.0f : val / (1.0f + expf(-gate));
+      o[j] = zero_row ? 0.0f : val * sigmoid_fast(gate);
     }
     const int ocol = col0 >> 1;
     const int on = g.n >> 1;
@@ -261,16 +261,26 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, i
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+  } else if (g.epilogue == JL_EPI_GELU_DGELU) {
+    // value to C, derivative to aux_out: the backward GEMM then only multiplies (JL_EPI_MUL_AUX) — the erf is evaluated once
+    float d[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) gelu_erf_both(acc[j], acc[j], d[j]);
+    __nv_bfloat16* ap = g.aux_out + static_cast<int64_t>(row) * g.ldaux_out + col0;
+    store_bf16_row<32>(ap, full && ((g.ldaux_out & 7) == 0), nvalid, d);
   } else if (g.epilogue == JL_EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.0f);
-  } else if (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD) {
+  } else if (g.epilogue == JL_EPI_GELU_BWD || g.epilogue == JL_EPI_RELU_BWD || g.epilogue == JL_EPI_MUL_AUX) {
     float a[32];
     if (epi_aux_vec(g, row, col0)) unpack_row32(pf.aux, a);
     else load_bf16_row32(g.aux + static_cast<int64_t>(row) * g.ldaux + col0, false, nvalid, a);
     if (g.epilogue == JL_EPI_GELU_BWD) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(a[j]);
+    } else if (g.epilogue == JL_EPI_MUL_AUX) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] *= a[j];
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = (a[j] > 0.0f) ? acc[j] : 0.0f;
@@ -862,12 +872,13 @@ static int validate(const jl_gemm_params* p) {
   // K-major A may have lda < K: rows that overlap in memory (sliding windows over a [T, C] activation — a Conv1d without im2col)
   JL_REQUIRE(p->lda >= (p->a_layout == JL_LAYOUT_K ? 8 : p->m), JL_EINVAL, "gemm: lda too small");
   JL_REQUIRE(p->ldb >= (p->b_layout == JL_LAYOUT_K ? p->k : p->n), JL_EINVAL, "gemm: ldb too small");
-  JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_GLU, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
+  JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_MUL_AUX, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
   JL_REQUIRE(p->out_dtype == JL_DT_BF16 || p->out_dtype == JL_DT_F32, JL_EINVAL, "gemm: unknown out_dtype %d", p->out_dtype);
   JL_REQUIRE((reinterpret_cast<uintptr_t>(p->c) & 15) == 0, JL_EINVAL, "gemm: C must be 16-byte aligned");
   if (p->epilogue == JL_EPI_GLU) JL_REQUIRE((p->n & 1) == 0, JL_EINVAL, "gemm: GLU needs an even N");
-  if (p->epilogue == JL_EPI_GELU_BWD || p->epilogue == JL_EPI_RELU_BWD)
+  if (p->epilogue == JL_EPI_GELU_BWD || p->epilogue == JL_EPI_RELU_BWD || p->epilogue == JL_EPI_MUL_AUX)
     JL_REQUIRE(p->aux != nullptr, JL_EINVAL, "gemm: activation-gradient epilogue needs aux");
+  if (p->epilogue == JL_EPI_GELU_DGELU) JL_REQUIRE(p->aux_out != nullptr, JL_EINVAL, "gemm: JL_EPI_GELU_DGELU needs aux_out");
   if (p->bias) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->bias) & 15) == 0, JL_EINVAL, "gemm: bias must be 16-byte aligned");
   if (p->residual) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0, JL_EINVAL, "gemm: residual must be 16-byte aligned");
   if (p->aux) JL_REQUIRE((reinterpret_cast<uintptr_t>(p->aux) & 15) == 0, JL_EINVAL, "gemm: aux must be 16-byte aligned");

@@ -649,8 +649,9 @@ class JLEngine:
             x2, sv.mean2, sv.rstd2 = ops.layernorm_fwd(h1, layer.final_layer_norm.weight.detach(), layer.final_layer_norm.bias.detach(),
                                                        layer.final_layer_norm.eps, save_stats=training)
             pre = torch.empty((b * t, cfg.intermediate_size), dtype=BF16, device=h.device) if training else None
-            act = ops.gemm(x2, fz[f"{i}.w1"], bias=fz[f"{i}.b1"], epilogue=L.JL_EPI_GELU, aux_out=pre)
-            sv.pre = pre
+            # training: the epilogue leaves gelu'(pre-activation) for the backward GEMM (erf evaluated once per element)
+            act = ops.gemm(x2, fz[f"{i}.w1"], bias=fz[f"{i}.b1"], epilogue=L.JL_EPI_GELU_DGELU if training else L.JL_EPI_GELU, aux_out=pre)
+            sv.dgelu = pre
             last_is_ffn = layer.adapter_ffn is None
             rl = dict(row_lengths=lengths, rows_per_seq=t) if last_is_ffn else {}
             h2 = ops.gemm(act, fz[f"{i}.w2"], bias=fz[f"{i}.b2"], residual=h1, **rl)
@@ -712,7 +713,7 @@ class JLEngine:
                 if i == l0 and layer.adapter_attn is None:
                     break
             # FFN: h2 = h1 + W2 · gelu(W1 · LN2(h1) + b1) + b2
-            dpre = ops.gemm(dh, ft[f"{i}.w2"], epilogue=L.JL_EPI_GELU_BWD, aux=sv.pre)        # dh · W2   (B = W2ᵀ stored [4d, d])
+            dpre = ops.gemm(dh, ft[f"{i}.w2"], epilogue=L.JL_EPI_MUL_AUX, aux=sv.dgelu)         # (dh · W2) ∘ gelu'   (B = W2ᵀ stored [4d, d])
             dx2 = ops.gemm(dpre, ft[f"{i}.w1"])                                                 # dpre · W1 (B = W1ᵀ stored [d, 4d])
             fl = layer.final_layer_norm
             dh1, _, _ = ops.layernorm_bwd(dx2, sv.h1, fl.weight.detach(), sv.mean2, sv.rstd2, dres=dh)

@@ -104,6 +104,18 @@ def test_gemm_epilogues():
     gp = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
     out = ops.gemm(a, b, epilogue=L.JL_EPI_GELU_BWD, aux=aux, out_dtype=F32)
     assert rel_err(out, acc * gp) < 2e-3
+    # training forward of the FFN input projection: GELU to C, gelu'(pre-activation) to aux_out; backward multiplies by it
+    dact = torch.empty(m, n, dtype=BF16, device="cuda")
+    out = ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU_DGELU, aux_out=dact, out_dtype=F32)
+    xb = acc + bias
+    assert rel_err(out, torch.nn.functional.gelu(xb)) < 2e-3
+    gpb = 0.5 * (1 + torch.erf(xb / math.sqrt(2))) + xb * torch.exp(-0.5 * xb * xb) / math.sqrt(2 * math.pi)
+    assert rel_err(dact.float(), gpb) < 5e-3
+    assert float((dact.float() - gpb).abs().max()) < 1e-2          # bf16 rounding of a value in [-0.13, 1.13]
+    out = ops.gemm(a, b, epilogue=L.JL_EPI_MUL_AUX, aux=aux, out_dtype=F32)
+    assert rel_err(out, acc * x) < 2e-3
+    with pytest.raises(L.JLError):
+        ops.gemm(a, b, bias=bias, epilogue=L.JL_EPI_GELU_DGELU)
     # ReLU backward
     out = ops.gemm(a, b, epilogue=L.JL_EPI_RELU_BWD, aux=aux, out_dtype=F32)
     assert rel_err(out, acc * (x > 0)) < 2e-3
