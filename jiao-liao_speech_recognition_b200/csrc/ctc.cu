@@ -151,7 +151,52 @@ __global__ void __launch_bounds__(256) ctc_row_stats_kernel(const T* __restrict_
   if (vec_ok) {
     const int nvec = vocab / VEC;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
-    for (int i = lane; i < nvec; i += 32) {
+    // Four 16-byte loads per lane in flight; per group of 4·VEC values: one running-max update (a rescale of the sum only
+    // when the maximum moves — a handful of times per row), then one FADD + FMUL + MUFU.EX2 + FADD per value.  The argmax
+    // is searched element by element only in the groups that raise it.
+    constexpr int U = 4;
+    int i = lane;
+    for (; i + 32 * (U - 1) < nvec; i += 32 * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = __ldg(xv + i + 32 * u);
+      float val[U][VEC];
+      float cm = -CUDART_INF_F;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if constexpr (sizeof(T) == 4) {
+          val[u][0] = __uint_as_float(raw[u].x); val[u][1] = __uint_as_float(raw[u].y);
+          val[u][2] = __uint_as_float(raw[u].z); val[u][3] = __uint_as_float(raw[u].w);
+        } else {
+          const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_bf16x2(w[q]);
+            val[u][2 * q] = f.x; val[u][2 * q + 1] = f.y;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) cm = fmaxf(cm, val[u][q]);
+      }
+      if (cm > best) {                       // indices grow with u and q: strict > keeps the first maximum
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q)
+            if (val[u][q] > best) { best = val[u][q]; besti = (i + 32 * u) * VEC + q; }
+      }
+      if (cm > m) {                          // cm is finite here; m = -inf on the first group gives ex2(-inf) = 0
+        s *= mufu_ex2((m - cm) * TC_LOG2E_F);
+        m = cm;
+      }
+      if (m != -CUDART_INF_F) {              // a group of -inf only (fully masked logits) adds nothing
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) s += mufu_ex2((val[u][q] - m) * TC_LOG2E_F);
+      }
+    }
+    for (; i < nvec; i += 32) {
       const uint4 v = __ldg(xv + i);
       if constexpr (sizeof(T) == 4) {
         online_update(__uint_as_float(v.x), i * 4 + 0, m, s, best, besti);

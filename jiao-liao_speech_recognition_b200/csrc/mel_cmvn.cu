@@ -7,10 +7,16 @@
 // attention mask at :142-163, :275-303.
 //
 // Kernel 1 (mel_fbank_kernel): one CTA = 32 consecutive frames of one utterance.  The 5360 samples the frames
-//   share are staged once in shared memory with coalesced loads (each sample is read from HBM exactly once);
-//   each warp then owns a frame at a time: frame mean by warp shuffle, pre-emphasis + window written as 256
-//   complex points, a 256-point radix-4 Stockham FFT in a per-warp shared ping-pong buffer, the real-FFT
-//   untangling pass to 257 power bins, and the sparse triangular mel projection (≤ 32 taps per bin) + log.
+//   share are staged once in shared memory with coalesced loads (each sample is read from HBM exactly once).
+//   The 512-point real FFT of a frame is a 256-point complex FFT held in REGISTERS by a half-warp: lane l owns
+//   z[l + 16 j], j = 0..15 (z[n] = y[2n] + i·y[2n+1]); radix-16 butterflies in registers → lane twiddles
+//   W256^(l·k) (registers) → ONE 16 × 16 transpose through shared memory → radix-16 again → the lane holds
+//   Z[l + 16 j].  The real-FFT untangling needs Z[256 − k], which lives in lane 16 − l: one shuffle per bin.
+//   A warp carries two frames (f, f + 16) at a time; the 257 power bins of every frame go to shared memory and
+//   the mel projection then runs with lane = frame: the filter weight is a warp-uniform load and the power bins
+//   are read conflict-free (row stride 257), i.e. 2 shared-memory wavefronts per tap for 32 frames.
+//   Shared-memory wavefronts per frame: ≈ 115 (the shared-memory Stockham version this replaces: ≈ 500, and the
+//   LSU was its limiter — profiles/README.md §5).
 //   The CTA writes its [32, 80] tile coalesced and leaves per-bin (mean, M2) partials for the CMVN statistics.
 // Kernel 2 (cmvn_kernel): merges the utterance's partials in fixed order (Chan's parallel variance update —
 //   deterministic, no atomics), normalises the tile, zeroes padded frames, optionally emits a bf16 copy.
@@ -27,58 +33,68 @@ constexpr int MEL_WARPS = 8;
 constexpr int MEL_THREADS = MEL_WARPS * 32;
 constexpr float MEL_PREEMPH = 0.97f;
 constexpr float MEL_FLT_EPS = 1.1920928955078125e-07f;
-
-// Shared-memory layouts are chosen for the LSU, which bounds this kernel (ncu: 73 % of peak shared wavefronts, half of
-// them bank conflicts in the first version): the FFT buffers are padded (one float2 after every four), the per-pass
-// twiddles are stored contiguously in the butterfly index, and the mel weights are transposed so that the 32 lanes of a
-// tap load hit 32 different banks.
-constexpr int MEL_FFT_PAD = 256 + 64;
-__device__ __forceinline__ int fft_phys(int idx) { return idx + (idx >> 2); }
+constexpr int MEL_TROW = 17;                    // float2 per row of the 16 x 16 transpose tile (17: conflict-free both ways)
+constexpr int MEL_PSTRIDE = 257;                // floats per frame of power bins (odd: lane = frame reads hit 32 banks)
+constexpr int MEL_OSTRIDE = JL_MEL_BINS + 1;    // floats per frame of log-mel outputs
+static_assert(MEL_FPC == 32, "mel_fbank_kernel maps one lane to one frame in the mel projection");
 
 struct MelSmem {
   float wave[MEL_SAMPLES_PER_CTA];
-  float2 fft[MEL_WARPS][2][MEL_FFT_PAD];
   float window[MEL_FRAME_LEN];
-  float2 tw512[257];                              // exp(-2πi k / 512), k = 0..256 (real-FFT untangling)
-  float2 tw_pass[3 * (4 + 16 + 64)];              // per radix-4 pass p ∈ {4, 16, 64}: [r-1][k] = exp(-2πi k r / (4p))
-  float mel_wt[JL_MEL_MAXW][JL_MEL_BINS + 1];     // transposed: [tap][bin]
-  int mel_lo[JL_MEL_BINS];
-  int mel_cnt[JL_MEL_BINS];
-  float out[MEL_FPC][JL_MEL_BINS];
+  float2 tbuf[MEL_WARPS][2][16 * MEL_TROW];     // per warp, per frame of the pair: transpose tile
+  float pw[MEL_FPC][MEL_PSTRIDE];               // power spectrum of every frame of the tile
+  float out[MEL_FPC][MEL_OSTRIDE];
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 __device__ __forceinline__ int utt_frames(int n) { return n < MEL_FRAME_LEN ? 0 : 1 + (n - MEL_FRAME_LEN) / MEL_FRAME_SHIFT; }
 
-// One radix-4 Stockham pass over 256 complex points held in shared memory; a warp does the 64 butterflies.
-// p = size of the sub-transforms already computed (1, 4, 16, 64); tw = this pass's twiddles [3][p].
-__device__ __forceinline__ void fft256_pass(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw, int p,
-                                            int lane) {
+// 4-point DFT (forward, e^{-2 pi i nk/4}): no multiplications
+__device__ __forceinline__ void bfly4(float2 a0, float2 a1, float2 a2, float2 a3, float2& y0, float2& y1, float2& y2, float2& y3) {
+  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+  y0 = cadd(s02, s13);
+  y1 = make_float2(d02.x + d13.y, d02.y - d13.x);     // d02 - i d13
+  y2 = csub(s02, s13);
+  y3 = make_float2(d02.x - d13.y, d02.y + d13.x);     // d02 + i d13
+}
+// a · W16^E, W16 = e^{-2 pi i / 16}
+template <int E>
+__device__ __forceinline__ float2 mul_w16(float2 a) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
+  if constexpr (E == 0) return a;
+  else if constexpr (E == 1) return make_float2(a.x * C1 + a.y * S1, a.y * C1 - a.x * S1);
+  else if constexpr (E == 2) return make_float2((a.x + a.y) * R, (a.y - a.x) * R);
+  else if constexpr (E == 3) return make_float2(a.x * S1 + a.y * C1, a.y * S1 - a.x * C1);
+  else if constexpr (E == 4) return make_float2(a.y, -a.x);
+  else if constexpr (E == 6) return make_float2((a.y - a.x) * R, -(a.x + a.y) * R);
+  else { static_assert(E == 9, "unused twiddle"); return make_float2(-(a.x * C1 + a.y * S1), a.x * S1 - a.y * C1); }   // W16^9 = (-C1, +S1)
+}
+// 16-point DFT in registers, natural order in and out: n = n0 + 4 n1, k = k1 + 4 k0
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  float2 b[4][4];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int i = lane + 32 * h;
-    const int k = i & (p - 1);
-    const int j = ((i - k) << 2) + k;
-    float2 u0 = src[fft_phys(i)], u1 = src[fft_phys(i + 64)], u2 = src[fft_phys(i + 128)], u3 = src[fft_phys(i + 192)];
-    if (p > 1) {
-      u1 = cmul(u1, tw[k]);
-      u2 = cmul(u2, tw[p + k]);
-      u3 = cmul(u3, tw[2 * p + k]);
-    }
-    const float2 a = make_float2(u0.x + u2.x, u0.y + u2.y);
-    const float2 b = make_float2(u0.x - u2.x, u0.y - u2.y);
-    const float2 c = make_float2(u1.x + u3.x, u1.y + u3.y);
-    const float2 d = make_float2(u1.x - u3.x, u1.y - u3.y);   // (u1 - u3); multiplied by -i → (d.y, -d.x)
-    dst[fft_phys(j)] = make_float2(a.x + c.x, a.y + c.y);
-    dst[fft_phys(j + p)] = make_float2(b.x + d.y, b.y - d.x);
-    dst[fft_phys(j + 2 * p)] = make_float2(a.x - c.x, a.y - c.y);
-    dst[fft_phys(j + 3 * p)] = make_float2(b.x - d.y, b.y + d.x);
-  }
-  __syncwarp();
+  for (int n0 = 0; n0 < 4; ++n0) bfly4(v[n0], v[n0 + 4], v[n0 + 8], v[n0 + 12], b[n0][0], b[n0][1], b[n0][2], b[n0][3]);
+  bfly4(b[0][0], b[1][0], b[2][0], b[3][0], v[0], v[4], v[8], v[12]);
+  bfly4(b[0][1], mul_w16<1>(b[1][1]), mul_w16<2>(b[2][1]), mul_w16<3>(b[3][1]), v[1], v[5], v[9], v[13]);
+  bfly4(b[0][2], mul_w16<2>(b[1][2]), mul_w16<4>(b[2][2]), mul_w16<6>(b[3][2]), v[2], v[6], v[10], v[14]);
+  bfly4(b[0][3], mul_w16<3>(b[1][3]), mul_w16<6>(b[2][3]), mul_w16<9>(b[3][3]), v[3], v[7], v[11], v[15]);
 }
 
-__global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmvn_params p, float* __restrict__ partials, int nblk) {
+// W32^k = e^{-2 pi i k / 32}, k = 0..15 (compile-time indices only)
+__device__ __forceinline__ float2 w32(int k) {
+  constexpr float c[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                           0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f, -0.38268343236508977f,
+                           -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+  constexpr float s[16] = {0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f, 0.83146961230254524f,
+                           0.92387953251128674f, 0.98078528040323043f, 1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                           0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+  return make_float2(c[k], -s[k]);
+}
+
+__global__ void __launch_bounds__(MEL_THREADS, 2) mel_fbank_kernel(const jl_mel_cmvn_params p, float* __restrict__ partials, int nblk) {
   jl::pdl_prologue();
   extern __shared__ __align__(16) uint8_t mel_smem_raw[];
   MelSmem& s = *reinterpret_cast<MelSmem*>(mel_smem_raw);
@@ -97,94 +113,115 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
     p.attention_mask[static_cast<int64_t>(b) * p.max_frames + f0 + tid] = (tid < nv) ? 1 : 0;
 
   if (nv > 0) {
-    // ---- stage constants and the shared span of samples
+    // ---- stage the window and the shared span of samples
     for (int i = tid; i < MEL_FRAME_LEN; i += MEL_THREADS) s.window[i] = __ldg(p.window + i);
-    for (int i = tid; i < 257; i += MEL_THREADS) s.tw512[i] = __ldg(reinterpret_cast<const float2*>(p.twiddle) + i);
-    for (int i = tid; i < 3 * (4 + 16 + 64); i += MEL_THREADS) {
-      // pass tables: offsets 0 (p = 4), 12 (p = 16), 60 (p = 64); entry [r-1][k] = W256^(k r 64/p) = tw512[2 k r 64/p]
-      const int pp = (i < 12) ? 4 : (i < 60 ? 16 : 64);
-      const int base = (i < 12) ? 0 : (i < 60 ? 12 : 60);
-      const int rr = (i - base) / pp + 1, kk = (i - base) % pp;
-      s.tw_pass[i] = __ldg(reinterpret_cast<const float2*>(p.twiddle) + ((2 * kk * rr * (64 / pp)) & 511));
-    }
-    for (int i = tid; i < JL_MEL_BINS * JL_MEL_MAXW; i += MEL_THREADS) s.mel_wt[i % JL_MEL_MAXW][i / JL_MEL_MAXW] = __ldg(p.mel_w + i);
-    if (tid < JL_MEL_BINS) {
-      s.mel_lo[tid] = __ldg(p.mel_lo + tid);
-      s.mel_cnt[tid] = __ldg(p.mel_cnt + tid);
-    }
     const float* wave = p.wave + static_cast<int64_t>(b) * p.wave_stride;
     const int s0 = f0 * MEL_FRAME_SHIFT;
     const int span = (nv - 1) * MEL_FRAME_SHIFT + MEL_FRAME_LEN;     // all < n by construction
     if ((p.wave_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.wave) & 15) == 0) {
       const float4* w4 = reinterpret_cast<const float4*>(wave + s0);  // s0 is a multiple of 160 → 16 B aligned
+      float4* d4 = reinterpret_cast<float4*>(s.wave);
       for (int i = tid; i < span / 4; i += MEL_THREADS) {
-        float4 v = __ldg(w4 + i);
-        s.wave[4 * i + 0] = v.x * 32768.0f;
-        s.wave[4 * i + 1] = v.y * 32768.0f;
-        s.wave[4 * i + 2] = v.z * 32768.0f;
-        s.wave[4 * i + 3] = v.w * 32768.0f;
+        const float4 v = __ldg(w4 + i);
+        d4[i] = make_float4(v.x * 32768.0f, v.y * 32768.0f, v.z * 32768.0f, v.w * 32768.0f);
       }
     } else {
       for (int i = tid; i < span; i += MEL_THREADS) s.wave[i] = __ldg(wave + s0 + i) * 32768.0f;
     }
+    // lane constants: hl = position in the half-warp = residue of the lane's FFT points
+    const int hl = lane & 15, fr = lane >> 4;
+    const float2* tw512 = reinterpret_cast<const float2*>(p.twiddle);   // e^{-2 pi i k / 512}
+    float2 twl[16];                                                      // W256^(hl·k1)
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) twl[k1] = __ldg(tw512 + ((2 * hl * k1) & 511));
+    const float2 wl = __ldg(tw512 + hl);                                 // W512^hl
     __syncthreads();
 
-    float2* bufA = s.fft[warp][0];
-    float2* bufB = s.fft[warp][1];
-    float* bufA_f = reinterpret_cast<float*>(bufA);
-    float* pw = reinterpret_cast<float*>(bufB);                       // 257 power bins, after the last pass
-    for (int fl = warp; fl < nv; fl += MEL_WARPS) {
-      const float* x = s.wave + fl * MEL_FRAME_SHIFT;
-      // frame mean (kaldi.py:183-186)
+    float2* tb = s.tbuf[warp][fr];
+    const int src_lane = (16 - hl) & 15;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int fa = warp + 8 * it;                  // the warp's frames: fa (lanes 0-15) and fa + 16 (lanes 16-31)
+      if (fa >= nv) break;                           // warp-uniform
+      const int fl = fa + 16 * fr;
+      const bool valid = fl < nv;
+      const float* x = s.wave + (valid ? fl : fa) * MEL_FRAME_SHIFT;
+      // ---- samples 2n, 2n+1 and 2n-1 of the lane's points n = hl + 16 j; frame mean (kaldi.py:183-186)
+      float2 raw[13];
+      float prev[13];
       float sum = 0.0f;
-      for (int i = lane; i < MEL_FRAME_LEN; i += 32) sum += x[i];
-      const float mean = warp_sum(sum) * (1.0f / MEL_FRAME_LEN);
-      // pre-emphasis with replicated first sample, povey window, zero-pad to 512
-      for (int i = lane; i < MEL_NFFT; i += 32) {
-        float y = 0.0f;
-        if (i < MEL_FRAME_LEN) {
-          const float cur = x[i] - mean;
-          const float prev = x[i > 0 ? i - 1 : 0] - mean;
-          y = (cur - MEL_PREEMPH * prev) * s.window[i];
-        }
-        bufA_f[2 * fft_phys(i >> 1) + (i & 1)] = y;                   // z[j] = (y[2j], y[2j+1])
-      }
-      __syncwarp();
-      fft256_pass(bufA, bufB, s.tw_pass, 1, lane);
-      fft256_pass(bufB, bufA, s.tw_pass, 4, lane);
-      fft256_pass(bufA, bufB, s.tw_pass + 12, 16, lane);
-      fft256_pass(bufB, bufA, s.tw_pass + 60, 64, lane);
-      // untangle the real transform: X[k] = E[k] + W512^k O[k], k = 0..256; power = |X|²
-      float pk[9];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int k = lane + 32 * j;
-        pk[j] = 0.0f;
-        if (k <= 256) {
-          const float2 zk = bufA[fft_phys(k & 255)];
-          const float2 zn = bufA[fft_phys((256 - k) & 255)];
-          const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-          const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
-          const float2 wo = cmul(s.tw512[k], o);
-          const float re = e.x + wo.x, im = e.y + wo.y;
-          pk[j] = re * re + im * im;
+      for (int j = 0; j < 13; ++j) {
+        const int nn = hl + 16 * j;
+        if (j < 12 || hl < 8) {
+          raw[j] = *reinterpret_cast<const float2*>(x + 2 * nn);
+          prev[j] = x[max(2 * nn - 1, 0)];
+          sum += raw[j].x + raw[j].y;
+        } else {
+          raw[j] = make_float2(0.0f, 0.0f);
+          prev[j] = 0.0f;
         }
       }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / MEL_FRAME_LEN);
+      // ---- pre-emphasis with replicated first sample (kaldi.py:193-198), povey window, zero-pad to 512
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) {
+        const int nn = hl + 16 * j;
+        if (j < 12 || hl < 8) {
+          const float2 w = *reinterpret_cast<const float2*>(s.window + 2 * nn);
+          const float c0 = raw[j].x - mean, c1 = raw[j].y - mean, pm = prev[j] - mean;
+          v[j] = make_float2((c0 - MEL_PREEMPH * pm) * w.x, (c1 - MEL_PREEMPH * c0) * w.y);
+        } else {
+          v[j] = make_float2(0.0f, 0.0f);
+        }
+      }
+#pragma unroll
+      for (int j = 13; j < 16; ++j) v[j] = make_float2(0.0f, 0.0f);
+      // ---- 256-point complex FFT: radix-16 over j, lane twiddles, transpose, radix-16 over the lanes' index
+      fft16(v);
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], twl[k1]);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) tb[k1 * MEL_TROW + hl] = v[k1];
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int k = lane + 32 * j;
-        if (k <= 256) pw[k] = pk[j];
-      }
+      for (int n1 = 0; n1 < 16; ++n1) v[n1] = tb[hl * MEL_TROW + n1];
       __syncwarp();
-      // sparse mel projection + log (kaldi.py:630-633)
-      for (int m = lane; m < JL_MEL_BINS; m += 32) {
-        const int lo = s.mel_lo[m], cnt = s.mel_cnt[m];
+      fft16(v);                                       // v[k2] = Z[hl + 16 k2]
+      // ---- untangle the real transform: X[k] = E[k] + W512^k O[k]; power = |X|² (kaldi.py:616-618)
+      float* pwf = s.pw[valid ? fl : fa];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        float2 zp;
+        zp.x = __shfl_sync(0xffffffffu, v[15 - k2].x, src_lane, 16);
+        zp.y = __shfl_sync(0xffffffffu, v[15 - k2].y, src_lane, 16);
+        if (hl == 0) zp = v[(16 - k2) & 15];          // lane 0 is its own partner: Z[256 - 16 k2]
+        const float2 zk = v[k2];
+        const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+        const float2 o = make_float2(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));   // (zk - conj(zp)) / (2i)
+        const float2 wo = cmul(cmul(wl, w32(k2)), o);                                  // W512^(hl + 16 k2)
+        const float re = e.x + wo.x, im = e.y + wo.y;
+        if (valid) pwf[hl + 16 * k2] = re * re + im * im;
+      }
+      if (valid && hl == 0) {
+        const float d = v[0].x - v[0].y;              // X[256] = Re Z[0] - Im Z[0]
+        pwf[256] = d * d;
+      }
+    }
+    __syncthreads();
+    // ---- mel projection + log (kaldi.py:630-633): lane = frame, the warp walks its bins; the weight load is warp-uniform
+    {
+      const float* pwl = s.pw[lane];
+      for (int m = warp; m < JL_MEL_BINS; m += MEL_WARPS) {
+        const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
+        const float* wrow = p.mel_w + m * JL_MEL_MAXW;
         float acc = 0.0f;
-        for (int j = 0; j < cnt; ++j) acc = fmaf(s.mel_wt[j][m], pw[lo + j], acc);
-        s.out[fl][m] = logf(fmaxf(acc, MEL_FLT_EPS));
+        for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(wrow + j), pwl[lo + j], acc);
+        s.out[lane][m] = logf(fmaxf(acc, MEL_FLT_EPS));
       }
-      __syncwarp();
     }
   }
   __syncthreads();
@@ -218,19 +255,26 @@ __global__ void __launch_bounds__(MEL_THREADS) mel_fbank_kernel(const jl_mel_cmv
 
 __global__ void __launch_bounds__(MEL_THREADS) cmvn_kernel(const jl_mel_cmvn_params p, const float* __restrict__ partials, int nblk) {
   jl::pdl_prologue();
-  __shared__ float s_mean[JL_MEL_BINS];
-  __shared__ float s_std[JL_MEL_BINS];
+  extern __shared__ __align__(16) float cmvn_part[];          // [used tiles][2 · 80] partials of this utterance
+  __shared__ __align__(16) float s_mean[JL_MEL_BINS];
+  __shared__ __align__(16) float s_std[JL_MEL_BINS];
   const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
   const int frames_b = min(utt_frames(p.num_samples[b]), p.max_frames);
   const int f0 = blk * MEL_FPC;
   const int nv = max(0, min(MEL_FPC, frames_b - f0));
+  const int used = (frames_b + MEL_FPC - 1) / MEL_FPC;
+  // all partials of the utterance with coalesced, independent loads (the merge below is a serial chain: it must not wait on
+  // one global load per step)
+  {
+    const float* src = partials + static_cast<int64_t>(b) * nblk * 2 * JL_MEL_BINS;
+    for (int i = tid; i < used * 2 * JL_MEL_BINS; i += MEL_THREADS) cmvn_part[i] = src[i];
+  }
+  __syncthreads();
   if (tid < JL_MEL_BINS) {
     float n = 0.0f, mean = 0.0f, m2 = 0.0f;
-    const int used = (frames_b + MEL_FPC - 1) / MEL_FPC;
     for (int c = 0; c < used; ++c) {
       const float nc = static_cast<float>(min(MEL_FPC, frames_b - c * MEL_FPC));
-      const float* src = partials + (static_cast<int64_t>(b) * nblk + c) * 2 * JL_MEL_BINS;
-      const float mc = src[tid], m2c = src[JL_MEL_BINS + tid];
+      const float mc = cmvn_part[c * 2 * JL_MEL_BINS + tid], m2c = cmvn_part[c * 2 * JL_MEL_BINS + JL_MEL_BINS + tid];
       const float tot = n + nc;
       const float delta = mc - mean;
       mean += delta * (nc / tot);
@@ -242,16 +286,42 @@ __global__ void __launch_bounds__(MEL_THREADS) cmvn_kernel(const jl_mel_cmvn_par
     s_std[tid] = (n > 0.0f) ? fmaxf(sqrtf(m2 / n), 1e-10f) : 1.0f;
   }
   __syncthreads();
-  const int64_t base = (static_cast<int64_t>(b) * p.max_frames + f0) * JL_MEL_BINS;
+  const int64_t base = (static_cast<int64_t>(b) * p.max_frames + f0) * JL_MEL_BINS;      // multiple of 2560 elements: 16-byte aligned
   const int rows = min(MEL_FPC, p.max_frames - f0);
   __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(p.feats_bf16);
-  for (int i = tid; i < rows * JL_MEL_BINS; i += MEL_THREADS) {
-    const int fl = i / JL_MEL_BINS;
-    const int m = i - fl * JL_MEL_BINS;
-    float v = 0.0f;
-    if (fl < nv) v = (p.feats[base + i] - s_mean[m]) / s_std[m];
-    p.feats[base + i] = v;
-    if (out16 != nullptr) out16[base + i] = __float2bfloat16_rn(v);
+  float4* f4 = reinterpret_cast<float4*>(p.feats + base);
+  const bool vec16 = out16 != nullptr && (reinterpret_cast<uintptr_t>(out16) & 7) == 0;
+  if ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0) {
+    for (int i = tid; i < rows * (JL_MEL_BINS / 4); i += MEL_THREADS) {
+      const int fl = i / (JL_MEL_BINS / 4);
+      const int m = (i - fl * (JL_MEL_BINS / 4)) * 4;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (fl < nv) {
+        const float4 x = f4[i];
+        const float4 mu = *reinterpret_cast<const float4*>(s_mean + m);
+        const float4 sd = *reinterpret_cast<const float4*>(s_std + m);
+        v = make_float4((x.x - mu.x) / sd.x, (x.y - mu.y) / sd.y, (x.z - mu.z) / sd.z, (x.w - mu.w) / sd.w);
+      }
+      f4[i] = v;
+      if (vec16) {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(out16 + base + 4 * i) = o;
+      } else if (out16 != nullptr) {
+        out16[base + 4 * i + 0] = __float2bfloat16_rn(v.x); out16[base + 4 * i + 1] = __float2bfloat16_rn(v.y);
+        out16[base + 4 * i + 2] = __float2bfloat16_rn(v.z); out16[base + 4 * i + 3] = __float2bfloat16_rn(v.w);
+      }
+    }
+  } else {
+    for (int i = tid; i < rows * JL_MEL_BINS; i += MEL_THREADS) {
+      const int fl = i / JL_MEL_BINS;
+      const int m = i - fl * JL_MEL_BINS;
+      float v = 0.0f;
+      if (fl < nv) v = (p.feats[base + i] - s_mean[m]) / s_std[m];
+      p.feats[base + i] = v;
+      if (out16 != nullptr) out16[base + i] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -296,7 +366,14 @@ int jl_mel_cmvn_fwd(const jl_mel_cmvn_params* p, void* workspace, void* stream) 
   jl::launch(jl::mel_fbank_kernel, grid, jl::MEL_THREADS, sizeof(jl::MelSmem), s, *p, p->apply_cmvn ? reinterpret_cast<float*>(workspace) : nullptr, nblk);
   JL_CHECK_LAUNCH("mel_fbank");
   if (p->apply_cmvn) {
-    jl::launch(jl::cmvn_kernel, grid, jl::MEL_THREADS, 0, s, *p, reinterpret_cast<const float*>(workspace), nblk);
+    const size_t part_bytes = static_cast<size_t>(nblk) * 2 * JL_MEL_BINS * sizeof(float);
+    JL_REQUIRE(part_bytes <= 200 * 1024, JL_EUNSUPPORTED_SHAPE, "mel_cmvn: max_frames %d exceeds the %d frames one utterance may have", p->max_frames,
+               (200 * 1024 / (2 * JL_MEL_BINS * 4)) * jl::MEL_FPC);
+    if (part_bytes > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(jl::cmvn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(part_bytes));
+      JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "mel_cmvn: cannot reserve shared memory: %s", cudaGetErrorString(e));
+    }
+    jl::launch(jl::cmvn_kernel, grid, jl::MEL_THREADS, part_bytes, s, *p, reinterpret_cast<const float*>(workspace), nblk);
     JL_CHECK_LAUNCH("cmvn");
   }
   return JL_OK;
