@@ -491,6 +491,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 // ================================================================================================ backward
 // MODE 0: dQ   (outer rows = queries; X1 = Q, X2 = dO; inner: Y1 = K_j, Y2 = V_j;  acc0 = dQ += dS · K_j)
 // MODE 1: dKV  (outer rows = keys;    X1 = K, X2 = V;  inner: Y1 = Q_i, Y2 = dO_i; acc0 = dV += Pᵀ · dO_i, acc1 = dK += dSᵀ · Q_i)
+constexpr int TC_BWD_PREFETCH_SEQ = 1024;
 template <int MODE>
 struct __align__(1024) AttnBwdSmem {
   uint8_t x1[TC_T128];
@@ -501,6 +502,7 @@ struct __align__(1024) AttnBwdSmem {
   uint8_t op1[MODE == 1 ? TC_T128 : 16];      // dSᵀ (MODE 1)
   float col_lse[2][TC_INNER];                 // MODE 1: per-query log-sum-exp (×log2e) and delta of the inner tile
   float col_delta[2][TC_INNER];
+  float col_all[MODE == 1 ? 2 * TC_BWD_PREFETCH_SEQ : 4];   // MODE 1, seq <= TC_BWD_PREFETCH_SEQ: lse·log2e and delta of every query, loaded once
   TcBars bars;
 };
 
@@ -631,10 +633,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
       }
       if (hh == 0 && row < p.seq) delta[row] = row_delta;
     }
+    // MODE 1 needs lse and delta of the inner tile's queries (the score columns).  For utterances of up to 1024 frames they
+    // are all fetched here, once; otherwise per inner tile — a global-load latency plus a barrier in front of every tile.
+    const bool pre = (MODE == 1) && p.seq <= TC_BWD_PREFETCH_SEQ;
+    if (pre) {
+      for (int q = tid; q < nib * TC_INNER; q += 256) {
+        s.col_all[q] = (q < len) ? lse[q] * TC_LOG2E : 0.0f;
+        s.col_all[TC_BWD_PREFETCH_SEQ + q] = (q < len) ? delta[q] : 0.0f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (int j = 0; j < nib; ++j) {
       const int st = j & 1;
       const int cbase = j * TC_INNER;                        // first key (MODE 0) / query (MODE 1) of the inner tile
-      if (MODE == 1) {
+      const float* cl = pre ? s.col_all + cbase : s.col_lse[st];
+      const float* cd = pre ? s.col_all + TC_BWD_PREFETCH_SEQ + cbase : s.col_delta[st];
+      if (MODE == 1 && !pre) {
         if (tid < TC_INNER) {
           const int q = cbase + tid;
           s.col_lse[st][tid] = (q < len) ? lse[q] * TC_LOG2E : 0.0f;
@@ -661,8 +675,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
           for (int e = 0; e < 2; ++e) {
             const int c = hh * 32 + 2 * i + e;
             const bool ok = row_ok && (cbase + c < len);
-            const float lse_c = (MODE == 0) ? row_lse : s.col_lse[st][c];
-            const float dl_c = (MODE == 0) ? row_delta : s.col_delta[st][c];
+            const float lse_c = (MODE == 0) ? row_lse : cl[c];
+            const float dl_c = (MODE == 0) ? row_delta : cd[c];
             const float pe = ok ? tc_exp2(fmaf(__uint_as_float(sv[2 * i + e]), sl2, -lse_c)) : 0.0f;
             pr[e] = pe;
             ds[e] = pe * (__uint_as_float(dv[2 * i + e]) - dl_c) * p.scale;

@@ -4,6 +4,7 @@
 //   zeroing (:542,568-579,123-139); bf16 transpose; column sums for bias gradients; casts; fused AdamW over the
 //   flat adapter bucket (torch.optim.AdamW update order).
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace jl {
 
@@ -68,54 +69,78 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
   }
 }
 
-// Column sums (bias gradients) in ONE launch: a CTA owns 8 adjacent columns, its 256 threads walk the rows with 16-byte
-// loads (thread t takes rows t, t + 256, …), then the 256 partials are combined by a fixed-order shared-memory tree —
-// deterministic, no atomics, no second kernel.
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
+// Column sums (bias gradients) in ONE launch.  A cluster of 8 CTAs owns 32 adjacent columns: four threads cover the 64
+// contiguous bytes a row has in those columns (full 32-byte sectors, where the previous 8-column CTAs used half of every
+// sector they fetched), 64 rows per CTA pass, the row groups dealt round-robin to the CTAs of the cluster, four passes in
+// flight per thread.  Each CTA combines its 64 row-threads by a fixed-order shared-memory tree; CTA 0 then adds the eight
+// partials in rank order through distributed shared memory — deterministic, no atomics, no second kernel, and 8× as many
+// CTAs as column blocks (192 for d = 768, where the 8-column version had 96).
+constexpr int CS_CLUSTER = 8;
+constexpr int CS_COLS = 32;
+__global__ void __cluster_dims__(CS_CLUSTER, 1, 1) __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ out) {
   jl::pdl_prologue();
-  __shared__ float s_acc[256][9];
-  const int col = blockIdx.x * 8;
+  __shared__ float s_acc[4][64][9];
+  __shared__ float s_part[CS_COLS];
   const int tid = threadIdx.x;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const int grp = tid & 3, rix = tid >> 2;
+  const int col = (blockIdx.x / CS_CLUSTER) * CS_COLS + grp * 8;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-  const bool vec = (col + 8 <= cols) && ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const bool vec = ((cols & 7) == 0) && ((ldx & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (vec) {
-    int r = tid;
-    for (; r + 768 < rows; r += 1024) {            // four independent 16-byte loads in flight per thread
-      uint4 v[4];
+    if (col < cols) {
+      int r = rank * 64 + rix;
+      constexpr int STEP = CS_CLUSTER * 64;
+      for (; r + 3 * STEP < rows; r += 4 * STEP) {
+        uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r + 256 * u) * ldx + col));
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r + STEP * u) * ldx + col));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
+        for (int u = 0; u < 4; ++u) {
+          const float2 f0 = unpack_bf16x2(v[u].x), f1 = unpack_bf16x2(v[u].y), f2 = unpack_bf16x2(v[u].z), f3 = unpack_bf16x2(v[u].w);
+          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+          acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+        }
+      }
+      for (; r < rows; r += STEP) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
+        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
         acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
         acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
       }
     }
-    for (; r < rows; r += 256) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
-      const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
-      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
-      acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
-    }
   } else {
-    for (int r = tid; r < rows; r += 256)
+    for (int r = rank * 64 + rix; r < rows; r += CS_CLUSTER * 64)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (col + j < cols) acc[j] += __bfloat162float(x[static_cast<int64_t>(r) * ldx + col + j]);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s_acc[tid][j] = acc[j];
+  for (int j = 0; j < 8; ++j) s_acc[grp][rix][j] = acc[j];
   __syncthreads();
-  for (int stride = 128; stride >= 1; stride >>= 1) {
-    if (tid < stride) {
+  for (int stride = 32; stride >= 1; stride >>= 1) {
+    if (rix < stride) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_acc[tid][j] += s_acc[tid + stride][j];
+      for (int j = 0; j < 8; ++j) s_acc[grp][rix][j] += s_acc[grp][rix + stride][j];
     }
     __syncthreads();
   }
-  if (tid < 8 && col + tid < cols) out[col + tid] = s_acc[0][tid];
+  if (tid < CS_COLS) s_part[tid] = s_acc[tid >> 3][0][tid & 7];
+  ptx::cluster_sync_all();
+  if (rank == 0 && tid < CS_COLS) {
+    const int c = (blockIdx.x / CS_CLUSTER) * CS_COLS + tid;
+    if (c < cols) {
+      const uint32_t local = ptx::smem_u32(&s_part[tid]);
+      float tot = 0.0f;
+#pragma unroll
+      for (int q = 0; q < CS_CLUSTER; ++q) tot += ptx::ld_shared_cluster_f32(ptx::mapa_shared(local, static_cast<uint32_t>(q)));
+      out[c] = tot;
+    }
+  }
+  ptx::cluster_sync_all();      // the partials of every CTA stay mapped until CTA 0 has read them
 }
 
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
@@ -248,7 +273,7 @@ int jl_colsum_bf16(const void* x, int64_t ldx, float* out, int32_t rows, int32_t
   JL_REQUIRE(rows > 0 && cols > 0 && ldx >= cols, JL_EINVAL, "colsum: bad dims");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::launch(jl::colsum_kernel, jl::ceil_div(cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows,
+  jl::launch(jl::colsum_kernel, jl::ceil_div(cols, jl::CS_COLS) * jl::CS_CLUSTER, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows,
                                                                                              cols, out);
   JL_CHECK_LAUNCH("colsum");
   return JL_OK;

@@ -8,6 +8,7 @@
 // the rows a CTA owns, reduces them through shared memory and leaves one partial row per CTA; a second small
 // kernel sums the partials in fixed order (deterministic, no atomics).
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace jl {
 
@@ -246,57 +247,85 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(const float* 
   }
 }
 
-// dγ = Σ_rows dy ∘ x̂, dβ = Σ_rows dy in ONE launch (CTA = 8 adjacent columns, 256 threads walk the rows with 16-byte loads,
-// fixed-order shared-memory tree): lets the dX part of an adapter norm's backward use the lean kernel on the critical path
-// while this runs on the weight-gradient branch.
-__global__ void __launch_bounds__(256) layernorm_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x,
-                                                              int64_t ldx, const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
-                                                              int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+// dγ = Σ_rows dy ∘ x̂, dβ = Σ_rows dy in ONE launch, laid out like colsum_kernel (elementwise.cu): a cluster of 8 CTAs owns 32
+// adjacent columns, four threads cover a row's 64 contiguous bytes, the row groups of 64 are dealt round-robin to the CTAs,
+// fixed-order shared-memory tree per CTA, CTA 0 adds the eight partials in rank order through distributed shared memory.
+// Lets the dX part of an adapter norm's backward use the lean kernel on the critical path while this runs on the
+// weight-gradient branch.
+constexpr int LNW_CLUSTER = 8;
+constexpr int LNW_COLS = 32;
+__global__ void __cluster_dims__(LNW_CLUSTER, 1, 1) __launch_bounds__(256)
+layernorm_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, int rows, int d, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
   jl::pdl_prologue();
-  __shared__ float s_g[256][9], s_b[256][9];
-  const int col = blockIdx.x * 8, tid = threadIdx.x;
+  __shared__ float s_g[4][64][9], s_b[4][64][9];
+  __shared__ float s_part[2][LNW_COLS];
+  const int tid = threadIdx.x;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const int grp = tid & 3, rix = tid >> 2;
+  const int col = (blockIdx.x / LNW_CLUSTER) * LNW_COLS + grp * 8;
   float g[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { g[j] = 0.0f; b[j] = 0.0f; }
-  for (int r0 = tid; r0 < rows; r0 += 1024) {
-    uint4 vy[4], vx[4];
-    float mu[4], rs[4];
+  constexpr int STEP = LNW_CLUSTER * 64;
+  if (col < d) {
+    for (int r0 = rank * 64 + rix; r0 < rows; r0 += 4 * STEP) {
+      uint4 vy[4], vx[4];
+      float mu[4], rs[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {                 // four independent rows in flight per thread
-      const int r = min(r0 + 256 * u, rows - 1);
-      vy[u] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + col));
-      vx[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
-      mu[u] = __ldg(mean + r);
-      rs[u] = __ldg(rstd + r);
-    }
+      for (int u = 0; u < 4; ++u) {                 // four independent rows in flight per thread
+        const int r = min(r0 + STEP * u, rows - 1);
+        vy[u] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + col));
+        vx[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col));
+        mu[u] = __ldg(mean + r);
+        rs[u] = __ldg(rstd + r);
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (r0 + 256 * u >= rows) break;
-      const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w}, wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + STEP * u >= rows) break;
+        const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w}, wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
-        g[2 * q] = fmaf(fy.x, (fx.x - mu[u]) * rs[u], g[2 * q]);
-        g[2 * q + 1] = fmaf(fy.y, (fx.y - mu[u]) * rs[u], g[2 * q + 1]);
-        b[2 * q] += fy.x;
-        b[2 * q + 1] += fy.y;
+        for (int q = 0; q < 4; ++q) {
+          const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
+          g[2 * q] = fmaf(fy.x, (fx.x - mu[u]) * rs[u], g[2 * q]);
+          g[2 * q + 1] = fmaf(fy.y, (fx.y - mu[u]) * rs[u], g[2 * q + 1]);
+          b[2 * q] += fy.x;
+          b[2 * q + 1] += fy.y;
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s_g[tid][j] = g[j]; s_b[tid][j] = b[j]; }
+  for (int j = 0; j < 8; ++j) { s_g[grp][rix][j] = g[j]; s_b[grp][rix][j] = b[j]; }
   __syncthreads();
-  for (int stride = 128; stride >= 1; stride >>= 1) {
-    if (tid < stride) {
+  for (int stride = 32; stride >= 1; stride >>= 1) {
+    if (rix < stride) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s_g[tid][j] += s_g[tid + stride][j]; s_b[tid][j] += s_b[tid + stride][j]; }
+      for (int j = 0; j < 8; ++j) { s_g[grp][rix][j] += s_g[grp][rix + stride][j]; s_b[grp][rix][j] += s_b[grp][rix + stride][j]; }
     }
     __syncthreads();
   }
-  if (tid < 8 && col + tid < d) {
-    dgamma[col + tid] = s_g[0][tid];
-    if (dbeta != nullptr) dbeta[col + tid] = s_b[0][tid];
+  if (tid < LNW_COLS) {
+    s_part[0][tid] = s_g[tid >> 3][0][tid & 7];
+    s_part[1][tid] = s_b[tid >> 3][0][tid & 7];
   }
+  ptx::cluster_sync_all();
+  if (rank == 0 && tid < LNW_COLS) {
+    const int c = (blockIdx.x / LNW_CLUSTER) * LNW_COLS + tid;
+    if (c < d) {
+      const uint32_t lg = ptx::smem_u32(&s_part[0][tid]), lb = ptx::smem_u32(&s_part[1][tid]);
+      float tg = 0.0f, tb = 0.0f;
+#pragma unroll
+      for (int q = 0; q < LNW_CLUSTER; ++q) {
+        tg += ptx::ld_shared_cluster_f32(ptx::mapa_shared(lg, static_cast<uint32_t>(q)));
+        tb += ptx::ld_shared_cluster_f32(ptx::mapa_shared(lb, static_cast<uint32_t>(q)));
+      }
+      dgamma[c] = tg;
+      if (dbeta != nullptr) dbeta[c] = tb;
+    }
+  }
+  ptx::cluster_sync_all();      // the partials of every CTA stay mapped until CTA 0 has read them
 }
 
 static int ln_bwd_blocks(int rows) {
@@ -338,7 +367,7 @@ int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream) {
   JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->dy)) & 15) == 0, JL_EINVAL, "layernorm_wgrad: pointers must be 16-byte aligned");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::launch(jl::layernorm_wgrad_kernel, p->d / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(p->dy),
+  jl::launch(jl::layernorm_wgrad_kernel, jl::ceil_div(p->d, jl::LNW_COLS) * jl::LNW_CLUSTER, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(p->dy),
              p->lddy, reinterpret_cast<const __nv_bfloat16*>(p->x), p->ldx, p->mean, p->rstd, p->rows, p->d, p->dgamma, p->dbeta);
   JL_CHECK_LAUNCH("layernorm_wgrad");
   return JL_OK;
