@@ -720,6 +720,284 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
   }
 }
 
+// ================================================================================================ backward, utterances of <= 256 frames
+// One CTA per (utterance, head) computes dQ, dK and dV from ONE evaluation of the scores: the 256 × 256 score matrix is
+// walked in four 128 × 128 blocks (key half j outer, query half i inner),
+//     S = Q_i·K_jᵀ, dP = dO_i·V_jᵀ  →  P = exp2(S·scale·log2e − lse), dS = P ∘ (dP − delta) · scale   (thread = query row)
+//     dQ_i += dS·K_j,   dV_j += Pᵀ·dO_i,   dK_j += dSᵀ·Q_i
+// where the two-kernel path (dQ, then dKV on transposed scores) evaluates S, dP and the exponentials twice and loads every
+// operand twice.  P and dS are written once, as K-major [128 q × 64 k] tiles; the tensor core reads the same bytes K-major
+// (A = dS for dQ) and MN-major (A = Pᵀ, dSᵀ for dV, dK) — the major bit of the instruction descriptor and the descriptor
+// strides are all that changes, as for the MN-major B operands of the other kernels.
+// TMEM (512 columns): S 0-127, dP 128-255, dQ_0 256-319, dQ_1 320-383, dK_j 384-447, dV_j 448-511.
+// Shared memory: Q, K, V, dO [256 × 64] (128 KB, one TMA box of 128 rows each half) + P, dS (64 KB): one CTA per SM.
+constexpr uint32_t TC_IDESC_S128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // M128 N128, A,B K-major
+constexpr uint32_t TC_IDESC_DQ = TC_IDESC_KMN;                                    // M128 N64, A K-major, B MN-major
+constexpr uint32_t TC_IDESC_DKV = TC_IDESC_KK | (1u << 15) | (1u << 16);          // M128 N64, A MN-major, B MN-major
+
+struct FusedBwdBars {
+  uint64_t x_full;         // Q, K, V, dO landed
+  uint64_t s_full;         // score MMAs (S, dP) of the current block complete
+  uint64_t s_empty;        // S / dP of the current block are in registers (8 warps)
+  uint64_t p_full;         // P, dS of the current block are in shared memory (8 warps)
+  uint64_t acc_done;       // accumulate MMAs of the current block complete: P / dS may be overwritten, dK_j / dV_j read after i = last
+  uint64_t dkv_empty;      // dK_j / dV_j accumulators read out by the 8 warps
+  uint32_t tmem_slot;
+};
+struct __align__(1024) AttnBwdFusedSmem {
+  uint8_t q[2][TC_T128];
+  uint8_t k[2][TC_T128];
+  uint8_t v[2][TC_T128];
+  uint8_t d_o[2][TC_T128];
+  uint8_t p[2][TC_T128];       // [key-column tile of 64][128 q rows × 128 B]
+  uint8_t ds[2][TC_T128];
+  FusedBwdBars bars;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                      const __grid_constant__ CUtensorMap tdo, const jl_attn_bwd_params p) {
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ uint8_t tc_smem_raw[];
+  AttnBwdFusedSmem& s = *reinterpret_cast<AttnBwdFusedSmem*>(tc_smem_raw + ((1024u - (ptx::smem_u32(tc_smem_raw) & 1023u)) & 1023u));
+  FusedBwdBars& B = s.bars;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tq);
+    ptx::prefetch_tensormap(&tk);
+    ptx::prefetch_tensormap(&tv);
+    ptx::prefetch_tensormap(&tdo);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(&B.x_full, 1);
+    ptx::mbar_init(&B.s_full, 1);
+    ptx::mbar_init(&B.s_empty, 8);
+    ptx::mbar_init(&B.p_full, 8);
+    ptx::mbar_init(&B.acc_done, 1);
+    ptx::mbar_init(&B.dkv_empty, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&B.tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  jl::pdl_prologue();
+  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const int grow = static_cast<int>(row_base);
+  const int nh = (len + TC_OUTER - 1) / TC_OUTER;          // 128-row halves that hold valid frames (0, 1 or 2)
+  const int nblocks = nh * nh;                            // block n: key half j = n / nh, query half i = n % nh
+  const uint32_t tmem = B.tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 256, t_dk = tmem + 384, t_dv = tmem + 448;
+
+  if (warp == 0) {
+    if (lane == 0 && nh > 0) {
+      ptx::mbar_expect_tx(&B.x_full, static_cast<uint32_t>(nh) * 4 * TC_T128);
+      for (int i = 0; i < nh; ++i) {
+        ptx::tma_load_2d(s.q[i], &tq, &B.x_full, h * 64, grow + i * TC_OUTER);
+        ptx::tma_load_2d(s.k[i], &tk, &B.x_full, h * 64, grow + i * TC_OUTER);
+        ptx::tma_load_2d(s.v[i], &tv, &B.x_full, h * 64, grow + i * TC_OUTER);
+        ptx::tma_load_2d(s.d_o[i], &tdo, &B.x_full, h * 64, grow + i * TC_OUTER);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nh > 0) {
+      const uint32_t aq = ptx::smem_u32(s.q[0]), ak = ptx::smem_u32(s.k[0]), av = ptx::smem_u32(s.v[0]), ado = ptx::smem_u32(s.d_o[0]);
+      const uint32_t ap = ptx::smem_u32(s.p[0]), ads = ptx::smem_u32(s.ds[0]);
+      ptx::mbar_wait(&B.x_full, 0);
+      auto issue_scores = [&](int n) {
+        const int j = n / nh, i = n - j * nh;
+        if (n > 0) ptx::mbar_wait(&B.s_empty, (n - 1) & 1);               // S / dP of block n-1 are in registers
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                      // S = Q_i · K_jᵀ   (M 128, N 128, K 64)
+          const uint64_t da = ptx::make_sw128_desc(aq + i * TC_T128 + k * 32, 16, 1024);
+          const uint64_t db = ptx::make_sw128_desc(ak + j * TC_T128 + k * 32, 16, 1024);
+          ptx::umma_bf16(t_s, da, db, TC_IDESC_S128, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                      // dP = dO_i · V_jᵀ
+          const uint64_t da = ptx::make_sw128_desc(ado + i * TC_T128 + k * 32, 16, 1024);
+          const uint64_t db = ptx::make_sw128_desc(av + j * TC_T128 + k * 32, 16, 1024);
+          ptx::umma_bf16(t_dp, da, db, TC_IDESC_S128, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&B.s_full);
+      };
+      issue_scores(0);
+      for (int n = 0; n < nblocks; ++n) {
+        const int j = n / nh, i = n - j * nh;
+        if (n + 1 < nblocks) issue_scores(n + 1);
+        ptx::mbar_wait(&B.p_full, n & 1);
+        if (i == 0 && j > 0) ptx::mbar_wait(&B.dkv_empty, (j - 1) & 1);    // dK / dV of the previous key half have been read out
+        ptx::tc_fence_after();
+        // dQ_i += dS · K_j : A = dS K-major (two 64-key tiles × 4 k-steps), B = K_j rows as K (MN-major, N = 64 dims)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = ptx::make_sw128_desc(ads + (kk >> 2) * TC_T128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = ptx::make_sw128_desc(ak + j * TC_T128 + kk * 2048, 8192, 1024);
+          ptx::umma_bf16(t_dq + i * 64, da, db, TC_IDESC_DQ, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        // dV_j += Pᵀ · dO_i, dK_j += dSᵀ · Q_i : A MN-major (M = 128 keys = two 64-wide tiles 16 KB apart, K = 128 queries)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = ptx::make_sw128_desc(ap + kk * 2048, TC_T128, 1024);
+          const uint64_t db = ptx::make_sw128_desc(ado + i * TC_T128 + kk * 2048, 8192, 1024);
+          ptx::umma_bf16(t_dv, da, db, TC_IDESC_DKV, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = ptx::make_sw128_desc(ads + kk * 2048, TC_T128, 1024);
+          const uint64_t db = ptx::make_sw128_desc(aq + i * TC_T128 + kk * 2048, 8192, 1024);
+          ptx::umma_bf16(t_dk, da, db, TC_IDESC_DKV, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&B.acc_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int r = (warp & 3) * 32 + lane;                    // TMEM lane = row of the 128-row half
+    const int hh = (warp - 4) >> 2;                          // which 64 of the block's 128 key columns this thread owns
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const float sl2 = p.scale * TC_LOG2E;
+    const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+    __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(p.dq) + row_base * p.ld_dqkv + h * 64;
+    __nv_bfloat16* dk = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
+    __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + row_base * p.ld_dqkv + h * 64;
+    // per query row of both halves: lse·log2e and delta = Σ_d dO·O
+    float row_lse[2] = {0.0f, 0.0f}, row_delta[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = i * TC_OUTER + r;
+      if (row < len) {
+        const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o) + (row_base + row) * p.ld_o + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (row_base + row) * p.ld_o + h * 64);
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fa = unpack_bf16x2(aw[q]), fd = unpack_bf16x2(dw[q]);
+            acc = fmaf(fa.x, fd.x, acc);
+            acc = fmaf(fa.y, fd.y, acc);
+          }
+        }
+        row_delta[i] = acc;
+        row_lse[i] = lse[row] * TC_LOG2E;
+      }
+    }
+    if (hh == 0 && p.delta != nullptr) {
+      float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+      if (r < p.seq) delta[r] = row_delta[0];
+      if (TC_OUTER + r < p.seq) delta[TC_OUTER + r] = row_delta[1];
+    }
+    for (int n = 0; n < nblocks; ++n) {
+      const int j = n / nh, i = n - j * nh;
+      const int qrow = i * TC_OUTER + r;
+      const bool row_ok = qrow < len;
+      const float lse_r = i ? row_lse[1] : row_lse[0], dl_r = i ? row_delta[1] : row_delta[0];
+      const int kbase = j * TC_OUTER + hh * 64;              // first key of this thread's 64 columns
+      ptx::mbar_wait(&B.s_full, n & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {                          // two chunks of 32 key columns
+        uint32_t sv[32], dvv[32], pkp[16], pkd[16];
+        ptx::tmem_ld_32x32(t_s + lane_off + hh * 64 + c * 32, sv);
+        ptx::tmem_ld_32x32(t_dp + lane_off + hh * 64 + c * 32, dvv);
+        ptx::tmem_ld_wait();
+        if (c == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&B.s_empty);     // this warp's share of S / dP is in registers
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float pr[2], dsv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c * 32 + 2 * e + u;
+            const bool ok = row_ok && (kbase + col < len);
+            const float pe = ok ? tc_exp2(fmaf(__uint_as_float(sv[2 * e + u]), sl2, -lse_r)) : 0.0f;
+            pr[u] = pe;
+            dsv[u] = pe * (__uint_as_float(dvv[2 * e + u]) - dl_r) * p.scale;
+          }
+          pkp[e] = pack_bf16x2(pr[0], pr[1]);
+          pkd[e] = pack_bf16x2(dsv[0], dsv[1]);
+        }
+        if (c == 0 && n > 0) ptx::mbar_wait(&B.acc_done, (n - 1) & 1);   // the accumulate MMAs of block n-1 have read P / dS
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t t0[8], t1[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { t0[q] = pkp[8 * c2 + q]; t1[q] = pkd[8 * c2 + q]; }
+          tc_store_cols16(s.p[hh], r, 4 * c + 2 * c2, t0);
+          tc_store_cols16(s.ds[hh], r, 4 * c + 2 * c2, t1);
+        }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&B.p_full);
+      if (i == nh - 1) {
+        // dK_j, dV_j are complete once this block's accumulate MMAs are: read them out (row = key), free the accumulators
+        ptx::mbar_wait(&B.acc_done, n & 1);
+        ptx::tc_fence_after();
+        const int krow = j * TC_OUTER + r;
+        uint32_t ov[32];
+        float of[32];
+        ptx::tmem_ld_32x32(t_dk + lane_off + hh * 32, ov);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
+        if (krow < p.seq) tc_store_global_row32(dk + static_cast<int64_t>(krow) * p.ld_dqkv + hh * 32, of, 1.0f);
+        ptx::tmem_ld_32x32(t_dv + lane_off + hh * 32, ov);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&B.dkv_empty);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
+        if (krow < p.seq) tc_store_global_row32(dv + static_cast<int64_t>(krow) * p.ld_dqkv + hh * 32, of, 1.0f);
+      }
+    }
+    // dQ of both halves (complete after the last block); rows of halves without valid frames are zero
+    if (nblocks > 0) {
+      ptx::mbar_wait(&B.acc_done, (nblocks - 1) & 1);
+      ptx::tc_fence_after();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int qrow = i * TC_OUTER + r;
+      float of[32];
+      if (i < nh) {
+        uint32_t ov[32];
+        ptx::tmem_ld_32x32(t_dq + i * 64 + lane_off + hh * 32, ov);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) of[e] = 0.0f;
+      }
+      if (qrow < p.seq) {
+        tc_store_global_row32(dq + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
+        if (i >= nh) {                                       // key rows of an all-padding half: dK = dV = 0
+          tc_store_global_row32(dk + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
+          tc_store_global_row32(dv + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 template <typename K>
 static int tc_set_smem(K kern, size_t bytes, const char* name) {
@@ -783,6 +1061,21 @@ int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream) {
   if (rc == JL_OK) rc = make_tma_map_2d_bf16(&q64, p->q, inner, rows, p->ld_qkv, TC_INNER);
   if (rc == JL_OK) rc = make_tma_map_2d_bf16(&do64, p->d_o, inner, rows, p->ld_o, TC_INNER);
   if (rc != JL_OK) return rc;
+  if (g_attn_short && p->seq <= 2 * TC_OUTER) {
+    // whole utterance in one CTA: scores, exponentials and operand loads once for dQ, dK and dV
+    const size_t smem_f = sizeof(AttnBwdFusedSmem) + 1024;
+    static thread_local int configured_dev_f = -1;
+    int devf = 0;
+    cudaGetDevice(&devf);
+    if (configured_dev_f != devf) {
+      rc = tc_set_smem(attn_bwd_fused_kernel, smem_f, "attn_bwd_fused");
+      if (rc != JL_OK) return rc;
+      configured_dev_f = devf;
+    }
+    jl::launch(attn_bwd_fused_kernel, dim3(p->heads, p->batch), TC_THREADS, smem_f, stream, q128, k128, v128, do128, *p);
+    JL_CHECK_LAUNCH("attn_bwd_fused");
+    return JL_OK;
+  }
   const size_t smem0 = sizeof(AttnBwdSmem<0>) + 1024, smem1 = sizeof(AttnBwdSmem<1>) + 1024;
   static thread_local int configured_dev = -1;
   int dev = 0;

@@ -58,6 +58,12 @@ L.load().jl_debug_set_attn_impl(0)
 o12, lse12 = ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125, want_lse=True)
 do12 = torch.randn_like(o12)
 timeit("attn_bwd 12 heads (tc)", lambda: ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], o12, do12, lse12, lens, 32, 250, 12, 0.125))
+o1, lse1 = ops.attn_fwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], lens, 32, 250, 1, 0.125, want_lse=True)
+do1 = torch.randn_like(o1)
+timeit("attn_bwd 1 head (tc)", lambda: ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], o1, do1, lse1, lens, 32, 250, 1, 0.125))
+L.load().jl_debug_set_attn_impl(3)
+timeit("attn_bwd 12 heads (tc, dQ + dKV kernels)", lambda: ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], o12, do12, lse12, lens, 32, 250, 12, 0.125))
+timeit("attn_bwd 1 head (tc, dQ + dKV kernels)", lambda: ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], o1, do1, lse1, lens, 32, 250, 1, 0.125))
 L.load().jl_debug_set_attn_impl(1)
 timeit("attn_bwd 12 heads (mma.sync)", lambda: ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], o12, do12, lse12, lens, 32, 250, 12, 0.125))
 timeit("attn_fwd 12 heads (mma.sync)", lambda: ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2*d], qkv[:, 2*d:], lens, 32, 250, 12, 0.125))
