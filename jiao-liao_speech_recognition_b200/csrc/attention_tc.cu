@@ -735,13 +735,16 @@ constexpr uint32_t TC_IDESC_S128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >
 constexpr uint32_t TC_IDESC_DQ = TC_IDESC_KMN;                                    // M128 N64, A K-major, B MN-major
 constexpr uint32_t TC_IDESC_DKV = TC_IDESC_KK | (1u << 15) | (1u << 16);          // M128 N64, A MN-major, B MN-major
 
+constexpr int FB_SOFTMAX_WARPS = 16;                       // 4 per TMEM lane quadrant: thread = (query row, quarter of the 128 key columns)
+constexpr int FB_THREADS = 128 + FB_SOFTMAX_WARPS * 32;     // + TMA, MMA, TMEM-allocator and one spare warp
+
 struct FusedBwdBars {
   uint64_t x_full;         // Q, K, V, dO landed
   uint64_t s_full;         // score MMAs (S, dP) of the current block complete
-  uint64_t s_empty;        // S / dP of the current block are in registers (8 warps)
-  uint64_t p_full;         // P, dS of the current block are in shared memory (8 warps)
+  uint64_t s_empty;        // S / dP of the current block are in registers (16 warps)
+  uint64_t p_full;         // P, dS of the current block are in shared memory (16 warps)
   uint64_t acc_done;       // accumulate MMAs of the current block complete: P / dS may be overwritten, dK_j / dV_j read after i = last
-  uint64_t dkv_empty;      // dK_j / dV_j accumulators read out by the 8 warps
+  uint64_t dkv_empty;      // dK_j / dV_j accumulators read out (16 warps)
   uint32_t tmem_slot;
 };
 struct __align__(1024) AttnBwdFusedSmem {
@@ -751,10 +754,25 @@ struct __align__(1024) AttnBwdFusedSmem {
   uint8_t d_o[2][TC_T128];
   uint8_t p[2][TC_T128];       // [key-column tile of 64][128 q rows × 128 B]
   uint8_t ds[2][TC_T128];
+  float row_lse[2 * TC_OUTER];   // lse · log2e per query
+  float row_delta[2 * TC_OUTER]; // Σ_d dO · O per query
   FusedBwdBars bars;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 16 fp32 → 16 bf16 (32 bytes) to global memory
+__device__ __forceinline__ void tc_store_global_row16(__nv_bfloat16* dst, const uint32_t (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    st_global_v8(dst, w);
+  } else {
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                       const __grid_constant__ CUtensorMap tdo, const jl_attn_bwd_params p) {
   const int b = blockIdx.y, h = blockIdx.x;
@@ -771,10 +789,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(&B.x_full, 1);
     ptx::mbar_init(&B.s_full, 1);
-    ptx::mbar_init(&B.s_empty, 8);
-    ptx::mbar_init(&B.p_full, 8);
+    ptx::mbar_init(&B.s_empty, FB_SOFTMAX_WARPS);
+    ptx::mbar_init(&B.p_full, FB_SOFTMAX_WARPS);
     ptx::mbar_init(&B.acc_done, 1);
-    ptx::mbar_init(&B.dkv_empty, 8);
+    ptx::mbar_init(&B.dkv_empty, FB_SOFTMAX_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -833,13 +851,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
         ptx::mbar_wait(&B.p_full, n & 1);
         if (i == 0 && j > 0) ptx::mbar_wait(&B.dkv_empty, (j - 1) & 1);    // dK / dV of the previous key half have been read out
         ptx::tc_fence_after();
-        // dQ_i += dS · K_j : A = dS K-major (two 64-key tiles × 4 k-steps), B = K_j rows as K (MN-major, N = 64 dims)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = ptx::make_sw128_desc(ads + (kk >> 2) * TC_T128 + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = ptx::make_sw128_desc(ak + j * TC_T128 + kk * 2048, 8192, 1024);
-          ptx::umma_bf16(t_dq + i * 64, da, db, TC_IDESC_DQ, (j > 0 || kk > 0) ? 1u : 0u);
-        }
         // dV_j += Pᵀ · dO_i, dK_j += dSᵀ · Q_i : A MN-major (M = 128 keys = two 64-wide tiles 16 KB apart, K = 128 queries)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -853,31 +864,39 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
           const uint64_t db = ptx::make_sw128_desc(aq + i * TC_T128 + kk * 2048, 8192, 1024);
           ptx::umma_bf16(t_dk, da, db, TC_IDESC_DKV, (i > 0 || kk > 0) ? 1u : 0u);
         }
+        // dQ_i += dS · K_j : A = dS K-major (two 64-key tiles × 4 k-steps), B = K_j rows as K (MN-major, N = 64 dims)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = ptx::make_sw128_desc(ads + (kk >> 2) * TC_T128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = ptx::make_sw128_desc(ak + j * TC_T128 + kk * 2048, 8192, 1024);
+          ptx::umma_bf16(t_dq + i * 64, da, db, TC_IDESC_DQ, (j > 0 || kk > 0) ? 1u : 0u);
+        }
         ptx::umma_commit(&B.acc_done);
       }
     }
   } else if (warp >= 4) {
+    const int st = threadIdx.x - 128;                        // 0..511
     const int r = (warp & 3) * 32 + lane;                    // TMEM lane = row of the 128-row half
-    const int hh = (warp - 4) >> 2;                          // which 64 of the block's 128 key columns this thread owns
+    const int qq = (warp - 4) >> 2;                          // which 32 of the block's 128 key columns this thread owns
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = p.scale * TC_LOG2E;
     const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
     __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(p.dq) + row_base * p.ld_dqkv + h * 64;
     __nv_bfloat16* dk = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
     __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + row_base * p.ld_dqkv + h * 64;
-    // per query row of both halves: lse·log2e and delta = Σ_d dO·O
-    float row_lse[2] = {0.0f, 0.0f}, row_delta[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int row = i * TC_OUTER + r;
+    // per query row: lse·log2e and delta = Σ_d dO·O.  Two threads share a row (64 contiguous bytes of O and dO each).
+    {
+      const int row = st >> 1, half = st & 1;
+      float acc = 0.0f;
       if (row < len) {
-        const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o) + (row_base + row) * p.ld_o + h * 64);
-        const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (row_base + row) * p.ld_o + h * 64);
-        float acc = 0.0f;
+        const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.o) + (row_base + row) * p.ld_o + h * 64) + half * 4;
+        const uint4* pd = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (row_base + row) * p.ld_o + h * 64) + half * 4;
+        uint4 a[4], d[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a = __ldg(po + c), d = __ldg(pd + c);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+        for (int c = 0; c < 4; ++c) { a[c] = __ldg(po + c); d[c] = __ldg(pd + c); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w}, dw[4] = {d[c].x, d[c].y, d[c].z, d[c].w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float2 fa = unpack_bf16x2(aw[q]), fd = unpack_bf16x2(dw[q]);
@@ -885,28 +904,30 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
             acc = fmaf(fa.y, fd.y, acc);
           }
         }
-        row_delta[i] = acc;
-        row_lse[i] = lse[row] * TC_LOG2E;
       }
-    }
-    if (hh == 0 && p.delta != nullptr) {
-      float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
-      if (r < p.seq) delta[r] = row_delta[0];
-      if (TC_OUTER + r < p.seq) delta[TC_OUTER + r] = row_delta[1];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (half == 0) {
+        s.row_delta[row] = acc;
+        s.row_lse[row] = (row < len) ? lse[row] * TC_LOG2E : 0.0f;
+        if (p.delta != nullptr && row < p.seq) p.delta[(static_cast<int64_t>(b) * p.heads + h) * p.seq + row] = acc;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(FB_SOFTMAX_WARPS * 32) : "memory");
     }
     for (int n = 0; n < nblocks; ++n) {
       const int j = n / nh, i = n - j * nh;
       const int qrow = i * TC_OUTER + r;
       const bool row_ok = qrow < len;
-      const float lse_r = i ? row_lse[1] : row_lse[0], dl_r = i ? row_delta[1] : row_delta[0];
-      const int kbase = j * TC_OUTER + hh * 64;              // first key of this thread's 64 columns
+      const float lse_r = s.row_lse[qrow], dl_r = s.row_delta[qrow];
+      const int kbase = j * TC_OUTER + qq * 32;              // first key of this thread's 32 columns
+      uint8_t* ptile = s.p[qq >> 1];
+      uint8_t* dstile = s.ds[qq >> 1];
       ptx::mbar_wait(&B.s_full, n & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {                          // two chunks of 32 key columns
-        uint32_t sv[32], dvv[32], pkp[16], pkd[16];
-        ptx::tmem_ld_32x32(t_s + lane_off + hh * 64 + c * 32, sv);
-        ptx::tmem_ld_32x32(t_dp + lane_off + hh * 64 + c * 32, dvv);
+      for (int c = 0; c < 2; ++c) {                          // two chunks of 16 key columns
+        uint32_t sv[16], dvv[16], pkp[8], pkd[8];
+        ptx::tmem_ld_32x16(t_s + lane_off + qq * 32 + c * 16, sv);
+        ptx::tmem_ld_32x16(t_dp + lane_off + qq * 32 + c * 16, dvv);
         ptx::tmem_ld_wait();
         if (c == 1) {
           ptx::tc_fence_before();
@@ -914,11 +935,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
           if (lane == 0) ptx::mbar_arrive(&B.s_empty);     // this warp's share of S / dP is in registers
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 8; ++e) {
           float pr[2], dsv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int col = c * 32 + 2 * e + u;
+            const int col = c * 16 + 2 * e + u;
             const bool ok = row_ok && (kbase + col < len);
             const float pe = ok ? tc_exp2(fmaf(__uint_as_float(sv[2 * e + u]), sl2, -lse_r)) : 0.0f;
             pr[u] = pe;
@@ -928,14 +949,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
           pkd[e] = pack_bf16x2(dsv[0], dsv[1]);
         }
         if (c == 0 && n > 0) ptx::mbar_wait(&B.acc_done, (n - 1) & 1);   // the accumulate MMAs of block n-1 have read P / dS
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t t0[8], t1[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { t0[q] = pkp[8 * c2 + q]; t1[q] = pkd[8 * c2 + q]; }
-          tc_store_cols16(s.p[hh], r, 4 * c + 2 * c2, t0);
-          tc_store_cols16(s.ds[hh], r, 4 * c + 2 * c2, t1);
-        }
+        tc_store_cols16(ptile, r, (qq & 1) * 4 + c * 2, pkp);
+        tc_store_cols16(dstile, r, (qq & 1) * 4 + c * 2, pkd);
       }
       ptx::fence_proxy_async();
       __syncwarp();
@@ -945,21 +960,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
         ptx::mbar_wait(&B.acc_done, n & 1);
         ptx::tc_fence_after();
         const int krow = j * TC_OUTER + r;
-        uint32_t ov[32];
-        float of[32];
-        ptx::tmem_ld_32x32(t_dk + lane_off + hh * 32, ov);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
-        if (krow < p.seq) tc_store_global_row32(dk + static_cast<int64_t>(krow) * p.ld_dqkv + hh * 32, of, 1.0f);
-        ptx::tmem_ld_32x32(t_dv + lane_off + hh * 32, ov);
+        uint32_t ok_[16], ov_[16];
+        ptx::tmem_ld_32x16(t_dk + lane_off + qq * 16, ok_);
+        ptx::tmem_ld_32x16(t_dv + lane_off + qq * 16, ov_);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&B.dkv_empty);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
-        if (krow < p.seq) tc_store_global_row32(dv + static_cast<int64_t>(krow) * p.ld_dqkv + hh * 32, of, 1.0f);
+        if (krow < p.seq) {
+          tc_store_global_row16(dk + static_cast<int64_t>(krow) * p.ld_dqkv + qq * 16, ok_);
+          tc_store_global_row16(dv + static_cast<int64_t>(krow) * p.ld_dqkv + qq * 16, ov_);
+        }
       }
     }
     // dQ of both halves (complete after the last block); rows of halves without valid frames are zero
@@ -970,22 +981,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int qrow = i * TC_OUTER + r;
-      float of[32];
+      uint32_t ov[16];
       if (i < nh) {
-        uint32_t ov[32];
-        ptx::tmem_ld_32x32(t_dq + i * 64 + lane_off + hh * 32, ov);
+        ptx::tmem_ld_32x16(t_dq + i * 64 + lane_off + qq * 16, ov);
         ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(ov[e]);
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) of[e] = 0.0f;
+        for (int e = 0; e < 16; ++e) ov[e] = 0u;
       }
       if (qrow < p.seq) {
-        tc_store_global_row32(dq + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
+        tc_store_global_row16(dq + static_cast<int64_t>(qrow) * p.ld_dqkv + qq * 16, ov);
         if (i >= nh) {                                       // key rows of an all-padding half: dK = dV = 0
-          tc_store_global_row32(dk + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
-          tc_store_global_row32(dv + static_cast<int64_t>(qrow) * p.ld_dqkv + hh * 32, of, 1.0f);
+          tc_store_global_row16(dk + static_cast<int64_t>(qrow) * p.ld_dqkv + qq * 16, ov);
+          tc_store_global_row16(dv + static_cast<int64_t>(qrow) * p.ld_dqkv + qq * 16, ov);
         }
       }
     }
@@ -1072,7 +1080,7 @@ int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream) {
       if (rc != JL_OK) return rc;
       configured_dev_f = devf;
     }
-    jl::launch(attn_bwd_fused_kernel, dim3(p->heads, p->batch), TC_THREADS, smem_f, stream, q128, k128, v128, do128, *p);
+    jl::launch(attn_bwd_fused_kernel, dim3(p->heads, p->batch), FB_THREADS, smem_f, stream, q128, k128, v128, do128, *p);
     JL_CHECK_LAUNCH("attn_bwd_fused");
     return JL_OK;
   }

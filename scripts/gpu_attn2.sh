@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider --timeout 300 -x -k attention > gpurun_out/pytest_attn.log 2>&1; echo "pytest attn exit $?"
+tail -n 4 gpurun_out/pytest_attn.log
 timeout 300 python scripts/microbench.py 2>&1 | grep attn | tee gpurun_out/microbench_attn.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_fused -s 2 -c 1 -f -o gpurun_out/prof_attn_fused \
-   python scripts/attn_only.py > gpurun_out/ncu_attn_fused.log 2>&1
-echo "ncu exit $?"; tail -2 gpurun_out/ncu_attn_fused.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; echo "bench exit $?"
+cut -c 1-330 gpurun_out/bench_iter.json
