@@ -314,8 +314,9 @@ int jl_comm_destroy(jl_comm* comm);
 void jl_debug_set_pdl(int on);
 
 /* test / tuning hook: attention implementation — 0 = tcgen05 kernels (TMEM scores, TMA operands; utterances of <= 256 frames
- * take the one-CTA-per-(utterance, head) forward kernel), 1 = mma.sync flash kernels, 2 / 3 = tcgen05 with the key-block
- * forward kernel at every length (2: its 3-CTAs/SM build).  All are the product's own kernels. */
+ * take the whole-row forward kernel and the fused dQ/dK/dV backward kernel), 1 = mma.sync flash kernels, 2 / 3 = tcgen05
+ * with the key-block forward kernel and the two-kernel (dQ, dKV) backward at every length (2: the forward's 3-CTAs/SM
+ * build).  All are the product's own kernels. */
 void jl_debug_set_attn_impl(int impl);
 
 /* test / tuning hook: 0 = automatic kernel choice (default), 1 = single-CTA tcgen05 kernel only, 2 = CTA-pair

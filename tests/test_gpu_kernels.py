@@ -92,6 +92,37 @@ def test_attention_fwd_bwd(attn_impl, b, t, h, lens):
         assert rel_err(dqkv[:, sl].float(), gref[:, sl]) < 2e-2, name
 
 
+@pytest.mark.parametrize("b,t,h", [(32, 250, 12), (32, 250, 1), (5, 256, 2), (3, 97, 4)])
+def test_attention_bwd_fused_matches_two_kernel_path(b, t, h):
+    """<= 256 frames: the one-CTA-per-(utterance, head) backward (scores evaluated once; P / dS read K- and MN-major) against
+    the dQ + dKV kernels on the same inputs, full bench size included, ragged lengths with an empty and a one-frame utterance."""
+    P = pkg()
+    ops, lib = P.ops, P._lib.load()
+    g = _g(5)
+    d = h * 64
+    qkv = torch.randn(b * t, 3 * d, device="cuda", generator=g).to(BF16)
+    lens = torch.randint(1, t + 1, (b,), generator=torch.Generator().manual_seed(3)).tolist()
+    lens[0], lens[1], lens[-1] = t, 0, 1
+    if b > 3:
+        lens[2], lens[3] = 128, 129
+    lengths = torch.tensor(lens, dtype=I32, device="cuda")
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    o, lse = ops.attn_fwd(q, k, v, lengths, b, t, h, 0.125, want_lse=True)
+    valid = (torch.arange(t, device="cuda")[None, :] < lengths[:, None]).reshape(b * t, 1)
+    d_o = (torch.randn(b * t, d, device="cuda", generator=g) * valid).to(BF16)
+    fused = ops.attn_bwd(q, k, v, o, d_o, lse, lengths, b, t, h, 0.125).clone()
+    lib.jl_debug_set_attn_impl(3)
+    try:
+        two = ops.attn_bwd(q, k, v, o, d_o, lse, lengths, b, t, h, 0.125).clone()
+    finally:
+        lib.jl_debug_set_attn_impl(P._lib.DEFAULT_ATTN_IMPL)
+    torch.cuda.synchronize()
+    assert torch.isfinite(fused.float()).all()
+    assert float((fused.float() * (~valid)).abs().max()) == 0.0            # padded rows carry no gradient
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        assert rel_err(fused[:, sl].float(), two[:, sl].float()) < 6e-3, name   # both round P / dS to bf16, in different orders
+
+
 # --------------------------------------------------------------------------------------------- CTC
 def _ctc_case(b, t, v, smax, seed, feasible=True):
     g = torch.Generator().manual_seed(seed)
