@@ -77,24 +77,41 @@ __global__ void __launch_bounds__(CTC_PREP_THREADS) ctc_prep_kernel(const int32_
                                                                     int32_t* __restrict__ fst, int32_t* __restrict__ nblank,
                                                                     int32_t* __restrict__ tlen) {
   jl::pdl_prologue();
-  __shared__ int s_n;
+  __shared__ int s_n, s_nb;
+  __shared__ int s_warp_cnt[CTC_PREP_THREADS / 32];
   const int b = blockIdx.x;
   int32_t* lab = out_labels + static_cast<int64_t>(b) * smax;
-  if (threadIdx.x == 0) {
-    int n = 0, nb = 0;
-    for (int j = 0; j < smax; ++j) {
-      const int v = labels[static_cast<int64_t>(b) * smax + j];
-      if (v >= 0) {
-        const int c = min(v, vocab - 1);   // range is validated on the host
-        lab[n++] = c;
-        nb += (c == blank);
-      }
+  // order-preserving compaction of the non-negative labels: coalesced loads, ballot prefix inside a warp, running offset
+  // across the rounds of 128 labels (one dependent global load per label made this kernel a 14 us latency chain)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int base = 0, nb_local = 0;
+  for (int j0 = 0; j0 < smax; j0 += CTC_PREP_THREADS) {
+    const int j = j0 + threadIdx.x;
+    const int v = (j < smax) ? labels[static_cast<int64_t>(b) * smax + j] : -1;
+    const bool keep = v >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < wid; ++w) off += s_warp_cnt[w];
+    int total = 0;
+    for (int w = 0; w < CTC_PREP_THREADS / 32; ++w) total += s_warp_cnt[w];
+    if (keep) {
+      const int c = min(v, vocab - 1);     // range is validated on the host
+      lab[off + __popc(m & ((1u << lane) - 1u))] = c;
+      nb_local += (c == blank);
     }
-    tlen[b] = n;
-    nblank[b] = nb;
-    s_n = n;
+    base += total;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) { s_n = base; s_nb = 0; }
   __syncthreads();
+  if (nb_local) atomicAdd(&s_nb, nb_local);      // integer count: order-independent
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tlen[b] = s_n;
+    nblank[b] = s_nb;
+  }
   const int n = s_n;
   for (int j = threadIdx.x; j < n; j += CTC_PREP_THREADS) {
     const int c = lab[j];

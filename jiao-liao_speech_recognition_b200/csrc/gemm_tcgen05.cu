@@ -1135,9 +1135,10 @@ static int pick_bn_2cta(const jl_gemm_params* p, bool assume_ws = false) {
   if (mode == 0 && (p->n <= 256 || p->k <= GEMM_BK)) return 0;
   // ... and so do the large K-major products whose N is a multiple of 256 (q|k|v, attention / FFN output projections, their
   // dgrads): 128 x 256 single-CTA tiles need 1.28-3.8 waves of 148 CTAs where 256 x 192 pair tiles need 1.7-5.2 waves of 74
-  // pairs, and measure 2-8 % faster (profiles/r1g_gemm_tile_sweep.md).  The FFN input projection (GELU epilogue, N = 3072) is
-  // a tie and stays on the pair kernel, whose epilogue has half the columns per CTA.
-  if (mode == 0 && p->b_layout == JL_LAYOUT_K && (p->n % 256) == 0 && p->m >= 4096 && p->epilogue == JL_EPI_NONE) return 0;
+  // pairs, and measure 2-8 % faster (profiles/r1g_gemm_tile_sweep.md).  With the activation epilogues of the FFN input
+  // projection and its dgrad (N = 3072) the single-CTA tile is equal or up to 6 % faster as well
+  // (profiles/r1m_gemm_epilogues.md: 52.1 vs 55.4 us with the GELU + gelu' epilogue); the GLU convolutions stay on the pair kernel.
+  if (mode == 0 && p->b_layout == JL_LAYOUT_K && (p->n % 256) == 0 && p->m >= 4096 && p->epilogue != JL_EPI_GLU) return 0;
   int per = 0;
   const bool have_ws = assume_ws || p->workspace != nullptr;
   if (have_ws && pick_split(p, pick_bn(p), &per) > 1) return 0;
