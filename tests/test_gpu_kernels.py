@@ -47,6 +47,38 @@ def test_layernorm_fwd_bwd(rows, d):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("rows,cols", [(8000, 768), (8000, 192), (8000, 5000), (1, 64), (63, 8), (513, 40), (700, 333), (4097, 1000)])
+def test_column_reductions_on_clusters(rows, cols):
+    """colsum_kernel / layernorm_wgrad_kernel: clusters of 8 CTAs per 32 columns, DSMEM combine in rank order — odd row counts
+    (fewer row groups than CTAs in the cluster), column counts that are not multiples of 32 or of 8 (scalar path), strided
+    views, and bit-identical results from run to run."""
+    ops = pkg().ops
+    g = _g(7)
+    x = torch.randn(rows, cols, device="cuda", generator=g).to(BF16)
+    ref = x.float().sum(0)
+    out1, out2 = ops.colsum(x), ops.colsum(x)
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2)
+    assert float((out1 - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())) + 2e-5 * rows ** 0.5
+    if cols % 8 == 0 and cols >= 16:
+        view = x[:, 8:cols]                                      # column window of a wider matrix (row stride > columns)
+        assert float((ops.colsum(view) - ref[8:]).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())) + 2e-5 * rows ** 0.5
+    if cols % 8 == 0:
+        dy = torch.randn(rows, cols, device="cuda", generator=g).to(BF16)
+        mean = x.float().mean(-1).contiguous()
+        rstd = (1.0 / torch.sqrt(x.float().var(-1, unbiased=False) + 1e-5)).contiguous()
+        dg, db = torch.empty(cols, device="cuda"), torch.empty(cols, device="cuda")
+        dg2, db2 = torch.empty_like(dg), torch.empty_like(db)
+        ops.layernorm_wgrad(dy, x, mean, rstd, dg, db)
+        ops.layernorm_wgrad(dy, x, mean, rstd, dg2, db2)
+        torch.cuda.synchronize()
+        assert torch.equal(dg, dg2) and torch.equal(db, db2)
+        xh = (x.float() - mean[:, None]) * rstd[:, None]
+        gref, bref = (dy.float() * xh).sum(0), dy.float().sum(0)
+        assert rel_err(dg, gref) < 1e-3 or float((dg - gref).abs().max()) < 1e-2
+        assert rel_err(db, bref) < 1e-3 or float((db - bref).abs().max()) < 1e-2
+
+
 # --------------------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, lengths, b, t, h, scale):
     q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in (q, k, v))
