@@ -20,7 +20,9 @@ def _extract(waves, cmvn=True):
 
 def test_raw_fbank_matches_oracle_1e4():
     from oracle import features as of
-    waves = [synth_wave(160000, 1234), synth_wave(52345, 7), synth_wave(400, 9), synth_wave(16000 * 3 + 77, 11)]
+    # frame counts whose last 32-frame tile is 6, 5, 1, 10, 20, 16 and 17 frames long: a warp carries frames f and f + 16
+    waves = [synth_wave(160000, 1234), synth_wave(52345, 7), synth_wave(400, 9), synth_wave(16000 * 3 + 77, 11),
+             synth_wave(400 + 160 * 51, 13), synth_wave(400 + 160 * 47 + 159, 14), synth_wave(400 + 160 * 48, 15)]
     out = _extract(waves, cmvn=False)
     feats = out["input_features"].cpu()
     for i, w in enumerate(waves):
