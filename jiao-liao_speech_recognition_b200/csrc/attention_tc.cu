@@ -1015,7 +1015,7 @@ static int tc_set_smem(K kern, size_t bytes, const char* name) {
 }
 
 int g_attn_fwd_ctas = 2;   // resident CTAs per SM the forward kernel is compiled for
-int g_attn_short = 1;      // 1: utterances of <= 256 frames take the one-CTA-per-(utterance, head) forward kernel
+int g_attn_short = 1;      // 1: utterances of <= 256 frames take the whole-row forward kernel and the fused dQ/dK/dV backward kernel
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
   const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;

@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = p.d >> 3;
   const float inv_d = 1.0f / static_cast<float>(p.d);
-  constexpr bool want_wgrad = WGRAD;
   constexpr int NW = WGRAD ? NCH : 1;
   float dg[NW][8], db[NW][8];
 #pragma unroll

@@ -26,7 +26,6 @@ namespace jl {
 
 constexpr int MEL_FRAME_LEN = 400;
 constexpr int MEL_FRAME_SHIFT = 160;
-constexpr int MEL_NFFT = 512;
 constexpr int MEL_FPC = JL_MEL_FRAMES_PER_CTA;                              // frames per CTA
 constexpr int MEL_SAMPLES_PER_CTA = (MEL_FPC - 1) * MEL_FRAME_SHIFT + MEL_FRAME_LEN;   // 5360
 constexpr int MEL_WARPS = 8;
