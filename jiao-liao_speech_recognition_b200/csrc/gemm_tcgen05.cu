@@ -1133,6 +1133,9 @@ static int pick_bn_2cta(const jl_gemm_params* p, bool assume_ws = false) {
   // dgrad) and one-k-block products (K <= 64: the adapter output projections, pure epilogue work) run faster on the
   // single-CTA kernel, whose 128-row tiles put twice as many CTAs on the machine.
   if (mode == 0 && (p->n <= 256 || p->k <= GEMM_BK)) return 0;
+  // ... and so does a short-K product with an MN-major B (the AttAdapter's dz = dqkv · W_qkv, K = 192): 8.6 us on the single-CTA
+  // kernel against 10.7 us on 256 x 128 pair tiles (profiles/r1g_gemm_tile_sweep.md, row "att dz").
+  if (mode == 0 && p->b_layout == JL_LAYOUT_MN && p->k <= 256) return 0;
   // ... and so do the large K-major products whose N is a multiple of 256 (q|k|v, attention / FFN output projections, their
   // dgrads): 128 x 256 single-CTA tiles need 1.28-3.8 waves of 148 CTAs where 256 x 192 pair tiles need 1.7-5.2 waves of 74
   // pairs, and measure 2-8 % faster (profiles/r1g_gemm_tile_sweep.md).  With the activation epilogues of the FFN input
