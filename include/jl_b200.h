@@ -199,6 +199,11 @@ typedef struct {
   const int32_t* lengths;         /* [B] valid frames (keys >= length masked; query rows >= length output 0) */
   int32_t batch, seq, heads;
   float scale;
+  /* Packed ("varlen") layout — SURVEY.md §5: utterance b occupies rows [cu_seqlens[b], cu_seqlens[b+1]) of [total_rows, ld]
+   * matrices, there are no padding rows; `seq` is then only the upper bound on an utterance's length (grid sizing), `lengths` is
+   * ignored, and lse is laid out [heads, total_rows].  NULL = padded [B*seq] layout. */
+  const int32_t* cu_seqlens;      /* [B + 1] int32 device, or NULL */
+  int32_t total_rows;
 } jl_attn_fwd_params;
 int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream);
 
@@ -207,10 +212,12 @@ typedef struct {
   const void* o; const void* d_o; int64_t ld_o;
   const float* lse;
   void* dq; void* dk; void* dv; int64_t ld_dqkv;   /* bf16 */
-  float* delta;                   /* workspace [B, heads, seq] fp32 */
+  float* delta;                   /* workspace [B, heads, seq] fp32 ([heads, total_rows] in the packed layout) */
   const int32_t* lengths;
   int32_t batch, seq, heads;
   float scale;
+  const int32_t* cu_seqlens;      /* packed layout, see jl_attn_fwd_params; NULL = padded */
+  int32_t total_rows;
 } jl_attn_bwd_params;
 int jl_attn_bwd(const jl_attn_bwd_params* p, void* stream);
 
@@ -231,6 +238,8 @@ typedef struct {
   float* loss;                            /* [1] fp32 out: reduced loss */
   void* grad; int64_t ld_grad;            /* optional [B*seq, V] d loss / d logits, dtype grad_dtype */
   int32_t grad_dtype;
+  const int32_t* cu_seqlens;              /* optional [B + 1]: packed layout — frame t of utterance b is row cu_seqlens[b] + t of
+                                             logits and grad (no padding rows; `seq` = upper bound on the lengths); NULL = row b*seq + t */
 } jl_ctc_params;
 int jl_ctc_workspace_bytes(const jl_ctc_params* p, size_t* out);
 int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream);
@@ -247,6 +256,7 @@ typedef struct {
   int32_t* frame_ids;     /* workspace/out [B, seq] per-frame argmax */
   int32_t* out_ids;       /* [B, seq] compacted ids (tail = -1) */
   int32_t* out_lengths;   /* [B] */
+  const int32_t* cu_seqlens; /* optional [B + 1]: packed logits rows (see jl_ctc_params); frame_ids / out_ids stay [B, seq] */
 } jl_ctc_greedy_params;
 int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream);
 
@@ -259,6 +269,11 @@ int jl_im2col_k5s2(const void* x, void* out, int32_t batch, int32_t t_in, int32_
  * (modeling_speech_to_text.py:542,568-579; pos_table is the host-built [seq + 2, d] fp32 sinusoid table, :123-139) */
 int jl_embed_positions(void* h, float scale, const float* pos_table, const int32_t* lengths, int32_t batch, int32_t seq,
                        int32_t d, void* stream);
+/* The same embedding that also PACKS the rows: out[cu_seqlens[b] + t, :] = h[b, t, :] * scale + pos[t + 2, :] for t < len_b
+ * (len_b = cu_seqlens[b+1] - cu_seqlens[b]); padded frames of h are dropped.  h: [batch, seq, d] bf16, out: [total, d] bf16.
+ * Entry into the packed (varlen) layout of the encoder: no padding rows in any GEMM / LayerNorm / attention after it. */
+int jl_embed_positions_packed(const void* h, void* out, float scale, const float* pos_table, const int32_t* cu_seqlens,
+                              int32_t batch, int32_t seq, int32_t d, void* stream);
 /* Raw-waveform (wav2vec2 / XLS-R) front end — the second front end beside mel.  The convolutions run on
  * jl_gemm_bf16; these entry points build its operands.
  *  jl_wave_stats   stats[b] = (mean, 1/sqrt(var + 1e-7)) over the valid samples of utterance b — zero_mean_unit_var_norm,
@@ -281,14 +296,23 @@ int jl_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 int jl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
 /* Fused AdamW over one flat fp32 bucket (adapter + lm_head parameters); also refreshes the bf16
- * shadow copy the kernels read.  grad is multiplied by grad_scale first (1/world after allreduce). */
+ * shadow copy the kernels read.  grad is multiplied by grad_scale first (1/world after allreduce).
+ * hyper_dev (optional): DEVICE pointer to 3 floats {lr, 1 - beta1^step, sqrt(1 - beta2^step)} read by the kernel instead of
+ * lr / step — the launch then carries no step-dependent scalar and can live inside a captured CUDA graph (the host refreshes
+ * the 12 bytes before each replay). */
 typedef struct {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq; void* param_bf16;
   int64_t n;
   float lr, beta1, beta2, eps, weight_decay, grad_scale;
   int32_t step;
+  const float* hyper_dev;
 } jl_adamw_params;
 int jl_adamw_bucket(const jl_adamw_params* p, void* stream);
+/* Advance the device-side optimizer clock that `hyper_dev` launches read: hyper = {lr, bc1, bc2_sqrt, step, beta1, beta2}
+ * (6 fp32 in device memory; the host writes lr / beta1 / beta2 and step = 0 once).  One thread: step += 1,
+ * bc1 = 1 - beta1^step, bc2_sqrt = sqrt(1 - beta2^step).  Enqueued once per training step, before the AdamW launches, it makes
+ * the whole step (forward, backward, all-reduce, AdamW) one replayable CUDA graph with no host-computed scalar in it. */
+int jl_adamw_advance(float* hyper_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11: the one collective of the fine-tune step — sum of the flat fp32 adapter + lm_head gradient

@@ -56,31 +56,32 @@ class WFAdapterFwdParams(C.Structure):
 
 class AttnFwdParams(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("ld_qkv", i64), ("o", vp), ("ld_o", i64), ("lse", vp),
-                ("lengths", vp), ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32)]
+                ("lengths", vp), ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32), ("cu_seqlens", vp), ("total_rows", i32)]
 
 
 class AttnBwdParams(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("ld_qkv", i64), ("o", vp), ("d_o", vp), ("ld_o", i64), ("lse", vp),
                 ("dq", vp), ("dk", vp), ("dv", vp), ("ld_dqkv", i64), ("delta", vp), ("lengths", vp),
-                ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32)]
+                ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32), ("cu_seqlens", vp), ("total_rows", i32)]
 
 
 class CtcParams(C.Structure):
     _fields_ = [("logits", vp), ("ld_logits", i64), ("logits_dtype", i32), ("labels", vp), ("max_label_len", i32),
                 ("input_lengths", vp), ("batch", i32), ("seq", i32), ("vocab", i32), ("blank", i32),
                 ("reduction", i32), ("zero_infinity", i32), ("nll", vp), ("loss", vp), ("grad", vp), ("ld_grad", i64),
-                ("grad_dtype", i32)]
+                ("grad_dtype", i32), ("cu_seqlens", vp)]
 
 
 class CtcGreedyParams(C.Structure):
     _fields_ = [("logits", vp), ("ld_logits", i64), ("logits_dtype", i32), ("input_lengths", vp), ("batch", i32),
-                ("seq", i32), ("vocab", i32), ("blank", i32), ("frame_ids", vp), ("out_ids", vp), ("out_lengths", vp)]
+                ("seq", i32), ("vocab", i32), ("blank", i32), ("frame_ids", vp), ("out_ids", vp), ("out_lengths", vp),
+                ("cu_seqlens", vp)]
 
 
 class AdamWParams(C.Structure):
     _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("param_bf16", vp), ("n", i64),
                 ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("grad_scale", f32),
-                ("step", i32)]
+                ("step", i32), ("hyper_dev", vp)]
 
 
 # name -> (restype, argtypes); every symbol include/jl_b200.h declares
@@ -112,6 +113,7 @@ SYMBOLS = {
     "jl_ctc_greedy": (C.c_int, [C.POINTER(CtcGreedyParams), vp]),
     "jl_im2col_k5s2": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "jl_embed_positions": (C.c_int, [vp, f32, vp, vp, i32, i32, i32, vp]),
+    "jl_embed_positions_packed": (C.c_int, [vp, vp, f32, vp, vp, i32, i32, i32, vp]),
     "jl_transpose_bf16": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),
     "jl_wave_stats": (C.c_int, [vp, i64, vp, i32, i32, vp, vp]),
     "jl_wave_im2col": (C.c_int, [vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, vp]),
@@ -121,6 +123,7 @@ SYMBOLS = {
     "jl_cast_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "jl_add_bf16": (C.c_int, [vp, vp, vp, i64, vp]),
     "jl_adamw_bucket": (C.c_int, [C.POINTER(AdamWParams), vp]),
+    "jl_adamw_advance": (C.c_int, [vp, vp]),
     "jl_comm_unique_id": (C.c_int, [vp]),
     "jl_comm_init": (C.c_int, [vp, i32, i32, C.POINTER(vp)]),
     "jl_comm_allreduce": (C.c_int, [vp, vp, C.c_size_t, vp]),

@@ -438,7 +438,9 @@ int jl_attn_fwd(const jl_attn_fwd_params* p, void* stream) {
   JL_REQUIRE(p->o && (p->ld_o & 7) == 0 && (reinterpret_cast<uintptr_t>(p->o) & 15) == 0, JL_EINVAL, "attn_fwd: bad output pointer / stride");
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
+  if (p->cu_seqlens != nullptr) JL_REQUIRE(p->total_rows > 0, JL_EINVAL, "attn_fwd: packed layout needs total_rows > 0");
   if (jl::g_attn_impl.load() == 0) return jl::attn_fwd_tc(p, reinterpret_cast<cudaStream_t>(stream));
+  JL_REQUIRE(p->cu_seqlens == nullptr, JL_EUNSUPPORTED_SHAPE, "attn_fwd: the packed (cu_seqlens) layout is implemented by the tcgen05 kernels only");
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
   jl::launch(jl::attn_fwd_kernel, grid, jl::ATT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream), *p);
   JL_CHECK_LAUNCH("attn_fwd");
@@ -457,7 +459,9 @@ int jl_attn_bwd(const jl_attn_bwd_params* p, void* stream) {
   rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->cu_seqlens != nullptr) JL_REQUIRE(p->total_rows > 0, JL_EINVAL, "attn_bwd: packed layout needs total_rows > 0");
   if (jl::g_attn_impl.load() == 0) return jl::attn_bwd_tc(p, s);
+  JL_REQUIRE(p->cu_seqlens == nullptr, JL_EUNSUPPORTED_SHAPE, "attn_bwd: the packed (cu_seqlens) layout is implemented by the tcgen05 kernels only");
   dim3 grid(jl::ceil_div(p->seq, jl::ATT_B), p->heads, p->batch);
   jl::launch(jl::attn_bwd_dq_kernel, grid, jl::ATT_THREADS, 0, s, *p);
   JL_CHECK_LAUNCH("attn_bwd_dq");

@@ -96,6 +96,34 @@ __device__ __forceinline__ void tc_zero_rows(__nv_bfloat16* base, int64_t ld, in
   }
 }
 
+// Where an utterance lives.  Padded layout: rows [b·seq, (b+1)·seq) of the [B·seq, ld] matrices, `lengths[b]` of them valid, the
+// others kept zero (they are written).  Packed layout (cu_seqlens != NULL, SURVEY §5 "varlen packing"): rows [cu[b], cu[b+1]) of
+// the [total_rows, ld] matrices, no padding rows at all — nothing past the utterance's last row may be written (it is the next
+// utterance's first row); per-row statistics (lse, delta) are laid out [heads, total_rows].
+struct TcSeq {
+  int64_t row_base;     // first row of the utterance in the q|k|v / o matrices
+  int64_t stat_base;    // first element of the utterance's (lse, delta) run for this head
+  int len;              // valid frames
+  int lim;              // rows this utterance owns in the matrices (padded: seq, packed: len)
+};
+template <typename P>
+__device__ __forceinline__ TcSeq tc_seq(const P& p, int b, int h) {
+  TcSeq q;
+  if (p.cu_seqlens != nullptr) {
+    const int r0 = p.cu_seqlens[b];
+    q.row_base = r0;
+    q.len = min(p.cu_seqlens[b + 1] - r0, p.seq);
+    q.lim = q.len;
+    q.stat_base = static_cast<int64_t>(h) * p.total_rows + r0;
+  } else {
+    q.row_base = static_cast<int64_t>(b) * p.seq;
+    q.len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
+    q.lim = p.seq;
+    q.stat_base = (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  }
+  return q;
+}
+
 struct TcBars {
   uint64_t x_full;         // outer tile(s) landed
   uint64_t y_full[2];      // inner tile stage landed
@@ -156,15 +184,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   jl::pdl_prologue();   // `lengths`, q, k, v may be produced by the preceding kernel: wait before the first global access
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const TcSeq sq = tc_seq(p, b, h);
+  const int len = sq.len, lim = sq.lim;
+  const int64_t row_base = sq.row_base;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
-  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
+  float* lse = p.lse ? p.lse + sq.stat_base : nullptr;
   const int nkb = (len + TC_INNER - 1) / TC_INNER;
   const bool skip = q0 >= len;          // the whole query tile is padding
   if (skip) {
-    tc_zero_rows(o, p.ld_o, q0, p.seq);
-    if (lse && threadIdx.x < TC_OUTER && q0 + threadIdx.x < p.seq) lse[q0 + threadIdx.x] = 0.0f;
+    tc_zero_rows(o, p.ld_o, q0, lim);
+    if (lse && threadIdx.x < TC_OUTER && q0 + threadIdx.x < lim) lse[q0 + threadIdx.x] = 0.0f;
   }
   const uint32_t tmem = B.tmem_slot;
   const uint32_t t_s[2] = {tmem, tmem};
@@ -292,9 +321,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       float of[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
-      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
+      if (row < lim) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
     }
-    if (lse && half == 0 && row < p.seq) lse[row] = (row < len) ? m * p.scale + logf(l_tot) : 0.0f;
+    if (lse && half == 0 && row < lim) lse[row] = (row < len) ? m * p.scale + logf(l_tot) : 0.0f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -353,11 +382,12 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   ptx::tc_fence_after();
   jl::pdl_prologue();     // everything above overlaps the preceding kernel; `lengths` and q / k / v may come from it
   const uint32_t tmem = s.tmem_slot;
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const TcSeq sq = tc_seq(p, b, h);
+  const int len = sq.len, lim = sq.lim;
+  const int64_t row_base = sq.row_base;
   const int grow = static_cast<int>(row_base);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.o) + row_base * p.ld_o + h * 64;
-  float* lse = p.lse ? p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq : nullptr;
+  float* lse = p.lse ? p.lse + sq.stat_base : nullptr;
   const bool active = g * TC_OUTER < len;                     // the query tile has at least one valid row
   const int nkt = (len + TC_INNER - 1) / TC_INNER;            // 64-key tiles with at least one valid key: 0..4
 
@@ -393,7 +423,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     if (!active) {
       // the whole query tile is padding (or the utterance is empty): zero rows, nothing to compute
-      if (row < p.seq) {
+      if (row < lim) {
         uint4* dst = reinterpret_cast<uint4*>(o + static_cast<int64_t>(row) * p.ld_o + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -476,8 +506,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       float of[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
-      if (row < p.seq) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
-      if (lse && half == 0 && row < p.seq) lse[row] = (row < len) ? mx * p.scale + logf(l_tot) : 0.0f;
+      if (row < lim) tc_store_global_row32(o + static_cast<int64_t>(row) * p.ld_o + half * 32, of, inv);
+      if (lse && half == 0 && row < lim) lse[row] = (row < len) ? mx * p.scale + logf(l_tot) : 0.0f;
     }
   }
   ptx::tc_fence_before();
@@ -542,18 +572,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   jl::pdl_prologue();   // `lengths` and every operand may be produced by the preceding kernel: wait before the first global access
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
-  const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
-  float* delta = p.delta + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+  const TcSeq sq = tc_seq(p, b, h);
+  const int len = sq.len, lim = sq.lim;
+  const int64_t row_base = sq.row_base;
+  const float* lse = p.lse + sq.stat_base;
+  float* delta = p.delta + sq.stat_base;
   __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(MODE == 0 ? p.dq : p.dv) + row_base * p.ld_dqkv + h * 64;
   __nv_bfloat16* out1 = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
   const int nib = (len + TC_INNER - 1) / TC_INNER;
   const bool skip = r0 >= len;          // the whole outer tile is padding
   if (skip) {
-    tc_zero_rows(out0, p.ld_dqkv, r0, p.seq);
-    if (MODE == 1) tc_zero_rows(out1, p.ld_dqkv, r0, p.seq);
-    if (MODE == 0 && threadIdx.x < TC_OUTER && r0 + threadIdx.x < p.seq) delta[r0 + threadIdx.x] = 0.0f;
+    tc_zero_rows(out0, p.ld_dqkv, r0, lim);
+    if (MODE == 1) tc_zero_rows(out1, p.ld_dqkv, r0, lim);
+    if (MODE == 0 && threadIdx.x < TC_OUTER && r0 + threadIdx.x < lim) delta[r0 + threadIdx.x] = 0.0f;
   }
   const uint32_t tmem = B.tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_acc0 = tmem + 128, t_acc1 = tmem + 192;
@@ -631,7 +662,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
         }
         row_lse = lse[row] * TC_LOG2E;
       }
-      if (hh == 0 && row < p.seq) delta[row] = row_delta;
+      if (hh == 0 && row < lim) delta[row] = row_delta;
     }
     // MODE 1 needs lse and delta of the inner tile's queries (the score columns).  For utterances of up to 1024 frames they
     // are all fetched here, once; otherwise per inner tile — a global-load latency plus a barrier in front of every tile.
@@ -709,7 +740,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tx1, const __grid_constan
       float of[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) of[i] = __uint_as_float(ov[i]);
-      if (row < p.seq) tc_store_global_row32(dst + static_cast<int64_t>(row) * p.ld_dqkv + hh * 32, of, 1.0f);
+      if (row < lim) tc_store_global_row32(dst + static_cast<int64_t>(row) * p.ld_dqkv + hh * 32, of, 1.0f);
     }
   }
   ptx::tc_fence_before();
@@ -803,8 +834,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   jl::pdl_prologue();
-  const int len = min(p.lengths ? p.lengths[b] : p.seq, p.seq);
-  const int64_t row_base = static_cast<int64_t>(b) * p.seq;
+  const TcSeq sq = tc_seq(p, b, h);
+  const int len = sq.len, lim = sq.lim;
+  const int64_t row_base = sq.row_base;
   const int grow = static_cast<int>(row_base);
   const int nh = (len + TC_OUTER - 1) / TC_OUTER;          // 128-row halves that hold valid frames (0, 1 or 2)
   const int nblocks = nh * nh;                            // block n: key half j = n / nh, query half i = n % nh
@@ -880,7 +912,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     const int qq = (warp - 4) >> 2;                          // which 32 of the block's 128 key columns this thread owns
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float sl2 = p.scale * TC_LOG2E;
-    const float* lse = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.seq;
+    const float* lse = p.lse + sq.stat_base;
     __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(p.dq) + row_base * p.ld_dqkv + h * 64;
     __nv_bfloat16* dk = reinterpret_cast<__nv_bfloat16*>(p.dk) + row_base * p.ld_dqkv + h * 64;
     __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(p.dv) + row_base * p.ld_dqkv + h * 64;
@@ -909,7 +941,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       if (half == 0) {
         s.row_delta[row] = acc;
         s.row_lse[row] = (row < len) ? lse[row] * TC_LOG2E : 0.0f;
-        if (p.delta != nullptr && row < p.seq) p.delta[(static_cast<int64_t>(b) * p.heads + h) * p.seq + row] = acc;
+        if (p.delta != nullptr && row < lim) p.delta[sq.stat_base + row] = acc;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(FB_SOFTMAX_WARPS * 32) : "memory");
     }
@@ -967,7 +999,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&B.dkv_empty);
-        if (krow < p.seq) {
+        if (krow < lim) {
           tc_store_global_row16(dk + static_cast<int64_t>(krow) * p.ld_dqkv + qq * 16, ok_);
           tc_store_global_row16(dv + static_cast<int64_t>(krow) * p.ld_dqkv + qq * 16, ov_);
         }
@@ -989,7 +1021,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 #pragma unroll
         for (int e = 0; e < 16; ++e) ov[e] = 0u;
       }
-      if (qrow < p.seq) {
+      if (qrow < lim) {
         tc_store_global_row16(dq + static_cast<int64_t>(qrow) * p.ld_dqkv + qq * 16, ov);
         if (i >= nh) {                                       // key rows of an all-padding half: dK = dV = 0
           tc_store_global_row16(dk + static_cast<int64_t>(qrow) * p.ld_dqkv + qq * 16, ov);
@@ -1018,7 +1050,7 @@ int g_attn_fwd_ctas = 2;   // resident CTAs per SM the forward kernel is compile
 int g_attn_short = 1;      // 1: utterances of <= 256 frames take the whole-row forward kernel and the fused dQ/dK/dV backward kernel
 
 int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
-  const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
+  const int64_t rows = p->cu_seqlens ? static_cast<int64_t>(p->total_rows) : static_cast<int64_t>(p->batch) * p->seq;
   const int64_t inner = static_cast<int64_t>(p->heads) * 64;
   CUtensorMap tq, tk, tv;
   int rc = make_tma_map_2d_bf16(&tq, p->q, inner, rows, p->ld_qkv, TC_OUTER);
@@ -1057,7 +1089,7 @@ int attn_fwd_tc(const jl_attn_fwd_params* p, cudaStream_t stream) {
 }
 
 int attn_bwd_tc(const jl_attn_bwd_params* p, cudaStream_t stream) {
-  const int64_t rows = static_cast<int64_t>(p->batch) * p->seq;
+  const int64_t rows = p->cu_seqlens ? static_cast<int64_t>(p->total_rows) : static_cast<int64_t>(p->batch) * p->seq;
   const int64_t inner = static_cast<int64_t>(p->heads) * 64;
   CUtensorMap q128, do128, k64, v64, k128, v128, q64, do64;
   int rc = make_tma_map_2d_bf16(&q128, p->q, inner, rows, p->ld_qkv, TC_OUTER);

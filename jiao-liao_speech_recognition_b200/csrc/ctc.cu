@@ -147,10 +147,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) ctc_row_stats_kernel(const T* __restrict__ logits, int64_t ld, int rows, int seq, int vocab,
                                                             const int32_t* __restrict__ lengths, float* __restrict__ lse_out,
                                                             int32_t* __restrict__ frame_ids, const int32_t* __restrict__ labels, int smax,
-                                                            const int32_t* __restrict__ tlen, int blank, float* __restrict__ lpx) {
+                                                            const int32_t* __restrict__ tlen, int blank, float* __restrict__ lpx,
+                                                            const int32_t* __restrict__ cu) {
   jl::pdl_prologue();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);       // (b, t) in the padded index space: lse / frame_ids / lpx are [B, seq]
   if (row >= rows) return;
   const int b = row / seq, t = row - b * seq;
   if (t >= lengths[b]) {
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(256) ctc_row_stats_kernel(const T* __restrict_
     }
     return;
   }
-  const T* x = logits + static_cast<int64_t>(row) * ld;
+  // packed layout: the frame's logits are row cu[b] + t (no padding rows in the logits matrix)
+  const T* x = logits + (cu != nullptr ? static_cast<int64_t>(cu[b]) + t : static_cast<int64_t>(row)) * ld;
   // The 2S+1 label logits of the row are gathered BEFORE the streaming pass (raw, lse subtracted at the end): the sectors
   // they touch are then re-read by the stream within microseconds, from L2.  Gathered after the pass, a fifth of them had
   // already been evicted by the other rows in flight (ncu: 192 MB of DRAM reads for 160 MB of logits).
@@ -435,13 +437,16 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
                                                                    int smax, const int32_t* __restrict__ tlen, int blank,
                                                                    const float* __restrict__ lse_all, const float* __restrict__ lpx,
                                                                    const float* __restrict__ alpha, const float* __restrict__ beta,
-                                                                   const float* __restrict__ nll, int reduction, int zero_infinity) {
+                                                                   const float* __restrict__ nll, int reduction, int zero_infinity,
+                                                                   const int32_t* __restrict__ cu) {
   jl::pdl_prologue();
   extern __shared__ float grad_smem[];
   const int row = blockIdx.x;
   const int b = row / seq, t = row - b * seq;
   const int tid = threadIdx.x;
-  TG* g = grad + static_cast<int64_t>(row) * ldg;
+  if (cu != nullptr && t >= lengths[b]) return;               // packed layout: a padded (b, t) has no row at all
+  const int64_t mrow = (cu != nullptr) ? static_cast<int64_t>(cu[b]) + t : static_cast<int64_t>(row);   // row in logits / grad
+  TG* g = grad + mrow * ldg;
   const float nll_b = nll[b];
   const bool infeasible = isinf(nll_b);
   if (t >= lengths[b] || (infeasible && zero_infinity)) {
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(const T* __r
     occ[s] = (isfinite(o)) ? o : 0.0f;
   }
   __syncthreads();
-  const T* x = logits + static_cast<int64_t>(row) * ld;
+  const T* x = logits + mrow * ld;
   const float lse = lse_all[row];
   // softmax part, written once (4 elements per thread per step when the rows are 16-byte aligned)
   if ((ld & 3) == 0 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0) {
@@ -610,11 +615,11 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
   const int sblocks = jl::ceil_div(rows, 8);
   if (p->logits_dtype == JL_DT_F32)
     jl::launch(jl::ctc_row_stats_kernel<float>, sblocks, 256, 0, s, reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
-                                                           p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen, p->blank, w.lpx);
+                                                           p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen, p->blank, w.lpx, p->cu_seqlens);
   else
     jl::launch(jl::ctc_row_stats_kernel<__nv_bfloat16>, sblocks, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
                                                                    p->vocab, p->input_lengths, w.lse, nullptr, w.labels, smax, w.tlen,
-                                                                   p->blank, w.lpx);
+                                                                   p->blank, w.lpx, p->cu_seqlens);
   JL_CHECK_LAUNCH("ctc_row_stats");
   const size_t lat_smem = static_cast<size_t>(3 + jl::CTC_LAT_AHEAD) * Lmax * sizeof(float);
   const bool lat_single = Lmax <= jl::CTC_LATTICE_HALF;       // every thread owns one state of the extended label sequence
@@ -635,7 +640,7 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
                                                                         p->batch, p->input_lengths, w.labels, w.nxt, w.fst, w.nblank,    \
                                                                         smax, w.tlen, p->blank,                                          \
                                                                         w.lse, w.lpx, w.alpha, w.beta, p->nll, p->reduction,             \
-                                                                        p->zero_infinity)
+                                                                        p->zero_infinity, p->cu_seqlens)
     if (p->logits_dtype == JL_DT_F32 && p->grad_dtype == JL_DT_F32) JL_CTC_GRAD(float, float);
     else if (p->logits_dtype == JL_DT_F32) JL_CTC_GRAD(float, __nv_bfloat16);
     else if (p->grad_dtype == JL_DT_F32) JL_CTC_GRAD(__nv_bfloat16, float);
@@ -660,11 +665,11 @@ int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream) {
   const int sblocks = jl::ceil_div(rows, 8);
   if (p->logits_dtype == JL_DT_F32)
     jl::launch(jl::ctc_row_stats_kernel<float>, sblocks, 256, 0, s, reinterpret_cast<const float*>(p->logits), p->ld_logits, rows, p->seq, p->vocab,
-                                                           p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr, p->blank, nullptr);
+                                                           p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr, p->blank, nullptr, p->cu_seqlens);
   else
     jl::launch(jl::ctc_row_stats_kernel<__nv_bfloat16>, sblocks, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(p->logits), p->ld_logits, rows, p->seq,
                                                                    p->vocab, p->input_lengths, nullptr, p->frame_ids, nullptr, 1, nullptr,
-                                                                   p->blank, nullptr);
+                                                                   p->blank, nullptr, p->cu_seqlens);
   JL_CHECK_LAUNCH("ctc_argmax");
   jl::launch(jl::ctc_collapse_kernel, p->batch, 32, 0, s, p->frame_ids, p->input_lengths, p->seq, p->blank, p->out_ids, p->out_lengths);
   JL_CHECK_LAUNCH("ctc_collapse");

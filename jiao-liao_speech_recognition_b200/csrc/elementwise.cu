@@ -53,6 +53,32 @@ __global__ void embed_positions_kernel(__nv_bfloat16* __restrict__ h, float scal
   }
 }
 
+// out[cu[b] + t, :] = h[b, t, :] * scale + pos[t + 2, :] for t < cu[b+1] - cu[b]: the embedding and the entry into the packed layout
+__global__ void embed_positions_packed_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, float scale,
+                                              const float* __restrict__ pos, const int32_t* __restrict__ cu, int batch, int seq, int d) {
+  jl::pdl_prologue();
+  const int d8 = d >> 3;
+  const int64_t total = static_cast<int64_t>(batch) * seq * d8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % d8);
+    const int64_t row = i / d8;
+    const int t = static_cast<int>(row % seq);
+    const int b = static_cast<int>(row / seq);
+    const int r0 = cu[b];
+    if (t >= cu[b + 1] - r0) continue;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(h) + i);
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<int64_t>(t + 2) * d + ch * 8));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<int64_t>(t + 2) * d + ch * 8) + 1);
+    const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+    uint4 o;
+    o.x = pack_bf16x2(fmaf(f0.x, scale, p0.x), fmaf(f0.y, scale, p0.y));
+    o.y = pack_bf16x2(fmaf(f1.x, scale, p0.z), fmaf(f1.y, scale, p0.w));
+    o.z = pack_bf16x2(fmaf(f2.x, scale, p1.x), fmaf(f2.y, scale, p1.y));
+    o.w = pack_bf16x2(fmaf(f3.x, scale, p1.z), fmaf(f3.y, scale, p1.w));
+    reinterpret_cast<uint4*>(out)[(static_cast<int64_t>(r0) + t) * d8 + ch] = o;
+  }
+}
+
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out, int64_t ld_out,
                                       int rows, int cols) {
   jl::pdl_prologue();
@@ -191,11 +217,17 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 __global__ void adamw_kernel(const jl_adamw_params p, float bc1, float bc2_sqrt) {
   jl::pdl_prologue();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const float step_size = p.lr / bc1;
+  float lr = p.lr;
+  if (p.hyper_dev != nullptr) {      // graph-captured launch: the step-dependent scalars come from device memory
+    lr = __ldg(p.hyper_dev);
+    bc1 = __ldg(p.hyper_dev + 1);
+    bc2_sqrt = __ldg(p.hyper_dev + 2);
+  }
+  const float step_size = lr / bc1;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
     const float g = p.grad[i] * p.grad_scale;
     float w = p.param[i];
-    w *= (1.0f - p.lr * p.weight_decay);
+    w *= (1.0f - lr * p.weight_decay);
     const float m = p.exp_avg[i] + (g - p.exp_avg[i]) * (1.0f - p.beta1);
     const float v = p.exp_avg_sq[i] * p.beta2 + (1.0f - p.beta2) * g * g;
     const float denom = sqrtf(v) / bc2_sqrt + p.eps;
@@ -204,6 +236,17 @@ __global__ void adamw_kernel(const jl_adamw_params p, float bc1, float bc2_sqrt)
     p.exp_avg[i] = m;
     p.exp_avg_sq[i] = v;
     if (p.param_bf16 != nullptr) reinterpret_cast<__nv_bfloat16*>(p.param_bf16)[i] = __float2bfloat16_rn(w);
+  }
+}
+
+// the optimizer clock of graph-captured steps (see jl_adamw_advance)
+__global__ void adamw_advance_kernel(float* __restrict__ hyper) {
+  jl::pdl_prologue();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float step = hyper[3] + 1.0f;
+    hyper[3] = step;
+    hyper[1] = 1.0f - powf(hyper[4], step);
+    hyper[2] = sqrtf(1.0f - powf(hyper[5], step));
   }
 }
 
@@ -246,6 +289,21 @@ int jl_embed_positions(void* h, float scale, const float* pos_table, const int32
   jl::launch(jl::embed_positions_kernel, jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<__nv_bfloat16*>(h), scale, pos_table, lengths, batch, seq, d);
   JL_CHECK_LAUNCH("embed_positions");
+  return JL_OK;
+}
+
+int jl_embed_positions_packed(const void* h, void* out, float scale, const float* pos_table, const int32_t* cu_seqlens, int32_t batch,
+                              int32_t seq, int32_t d, void* stream) {
+  JL_REQUIRE(h && out && pos_table && cu_seqlens, JL_EINVAL, "embed_positions_packed: null pointer");
+  JL_REQUIRE(batch > 0 && seq > 0 && d > 0 && (d & 7) == 0, JL_EINVAL, "embed_positions_packed: bad dims (d must be a multiple of 8)");
+  JL_REQUIRE(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pos_table)) & 15) == 0, JL_EINVAL,
+             "embed_positions_packed: pointers must be 16-byte aligned");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  const int64_t total = static_cast<int64_t>(batch) * seq * (d / 8);
+  jl::launch(jl::embed_positions_packed_kernel, jl::grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<__nv_bfloat16*>(out), scale, pos_table, cu_seqlens, batch, seq, d);
+  JL_CHECK_LAUNCH("embed_positions_packed");
   return JL_OK;
 }
 
@@ -299,13 +357,23 @@ int jl_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream
   return JL_OK;
 }
 
-int jl_adamw_bucket(const jl_adamw_params* p, void* stream) {
-  JL_REQUIRE(p && p->param && p->grad && p->exp_avg && p->exp_avg_sq, JL_EINVAL, "adamw: null pointer");
-  JL_REQUIRE(p->n > 0 && p->step >= 1, JL_EINVAL, "adamw: n must be positive and step >= 1");
+int jl_adamw_advance(float* hyper_dev, void* stream) {
+  JL_REQUIRE(hyper_dev != nullptr && (reinterpret_cast<uintptr_t>(hyper_dev) & 3) == 0, JL_EINVAL, "adamw_advance: null / misaligned pointer");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  const float bc1 = 1.0f - powf(p->beta1, static_cast<float>(p->step));
-  const float bc2_sqrt = sqrtf(1.0f - powf(p->beta2, static_cast<float>(p->step)));
+  jl::launch(jl::adamw_advance_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream), hyper_dev);
+  JL_CHECK_LAUNCH("adamw_advance");
+  return JL_OK;
+}
+
+int jl_adamw_bucket(const jl_adamw_params* p, void* stream) {
+  JL_REQUIRE(p && p->param && p->grad && p->exp_avg && p->exp_avg_sq, JL_EINVAL, "adamw: null pointer");
+  JL_REQUIRE(p->n > 0 && (p->step >= 1 || p->hyper_dev != nullptr), JL_EINVAL, "adamw: n must be positive and step >= 1 (or hyper_dev given)");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  const float stepf = static_cast<float>(p->step >= 1 ? p->step : 1);
+  const float bc1 = 1.0f - powf(p->beta1, stepf);
+  const float bc2_sqrt = sqrtf(1.0f - powf(p->beta2, stepf));
   jl::launch(jl::adamw_kernel, jl::grid_for(p->n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), *p, bc1, bc2_sqrt);
   JL_CHECK_LAUNCH("adamw_bucket");
   return JL_OK;

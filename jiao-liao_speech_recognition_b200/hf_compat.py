@@ -114,9 +114,32 @@ def convert_hf_state_dict(sd: Dict[str, torch.Tensor], num_dialects: int = 1, di
     return out, skipped
 
 
-def load_hf_state_dict(model, sd: Dict[str, torch.Tensor], strict: bool = False, dialect: int = 0) -> Tuple[List[str], List[str]]:
+def check_hf_architecture(sd: Dict[str, torch.Tensor], hf_config=None) -> None:
+    """``JLEncoderLayer`` is the *stable-layer-norm* (pre-LN) layer of XLS-R / MMS / wav2vec2-large-lv60
+    (``Wav2Vec2EncoderLayerStableLayerNorm``, modeling_wav2vec2.py:612-655) and the raw-waveform front end is the "layer"-norm
+    feature extractor with conv bias.  Post-LN wav2vec2-base checkpoints (``do_stable_layer_norm=False``,
+    ``feat_extract_norm="group"``, no conv bias) carry the same transformer leaf names and would load silently into the wrong
+    arithmetic — refuse them.  Detection: the HF config when given, else the feature-extractor keys (a multi-layer "group"
+    extractor has a norm on conv layer 0 only and no conv biases — the layout every post-LN wav2vec2-base checkpoint has)."""
+    if hf_config is not None:
+        get = (lambda k, d=None: hf_config.get(k, d)) if isinstance(hf_config, dict) else (lambda k, d=None: getattr(hf_config, k, d))
+        if get("do_stable_layer_norm", True) is False:
+            raise ValueError("checkpoint has do_stable_layer_norm=False (post-LN wav2vec2-base layers): only the stable-layer-norm "
+                             "(pre-LN) architecture of XLS-R / MMS / wav2vec2-large is implemented")
+        if get("feat_extract_norm", "layer") == "group":
+            raise ValueError("checkpoint has feat_extract_norm='group': only the 'layer'-norm feature extractor (with conv bias) is implemented")
+    keys = {_strip_prefix(k) for k in sd}
+    if "feature_extractor.conv_layers.1.conv.weight" in keys:          # a real multi-layer feature extractor
+        if "feature_extractor.conv_layers.1.layer_norm.weight" not in keys and "feature_extractor.conv_layers.1.conv.bias" not in keys:
+            raise ValueError("checkpoint has a 'group'-norm feature extractor without conv bias (wav2vec2-base, do_stable_layer_norm=False): "
+                             "its post-LN transformer layers share these parameter names but not this model's arithmetic — not supported")
+
+
+def load_hf_state_dict(model, sd: Dict[str, torch.Tensor], strict: bool = False, dialect: int = 0, hf_config=None) -> Tuple[List[str], List[str]]:
     """Copy an HF-named state dict into ``model`` (a ``JLForCTC``).  Returns (missing model keys, skipped HF keys);
-    ``strict`` raises if a model parameter outside the adapters stays unset or a shape differs."""
+    ``strict`` raises if a model parameter outside the adapters stays unset or a shape differs.  Raises for post-LN /
+    group-norm wav2vec2-base checkpoints (``check_hf_architecture``; pass the HF config as ``hf_config`` when there is one)."""
+    check_hf_architecture(sd, hf_config)
     k_dialects = getattr(model.config, "num_dialects", 1)
     conv, skipped = convert_hf_state_dict(sd, num_dialects=k_dialects, dialect=dialect,
                                           with_front_end=getattr(model.config, "front_end", "mel") == "wav2vec2")

@@ -227,6 +227,33 @@ class JLEncoder(nn.Module):
 
 
 # =============================================================================================== engine
+class PackedLayout:
+    """Row layout of a packed ("varlen") batch: the T'_b valid frames of utterance b are rows [cu[b], cu[b+1]) of every
+    [total, C] activation matrix — no padding rows, so the GEMMs, LayerNorms, adapters and the CTC head do no work on padding.
+    ``cu`` is the device copy the attention / CTC kernels read; ``cu_host`` drives host-side slicing (dialect runs);
+    ``seq_bound`` (a multiple of 128 >= the longest utterance) sizes the attention grid and the CTC workspace."""
+
+    def __init__(self, lengths_host, device, cu: Optional[torch.Tensor] = None):
+        self.lens = [int(x) for x in lengths_host]
+        self.cu_host = [0]
+        for n in self.lens:
+            if n < 0:
+                raise ValueError("negative utterance length")
+            self.cu_host.append(self.cu_host[-1] + n)
+        self.total = self.cu_host[-1]
+        self.batch = len(self.lens)
+        self.seq_bound = max(128, (max(self.lens + [1]) + 127) // 128 * 128)
+        if cu is None:
+            cu = torch.tensor(self.cu_host, dtype=I32, device=device)
+        elif cu.numel() != self.batch + 1 or cu.dtype != I32:
+            raise ValueError("cu must be an int32 tensor of batch + 1 entries")
+        self.cu = cu
+
+    def key(self):
+        """What a captured CUDA graph bakes in (shapes and grids); the contents of ``cu`` may change between replays."""
+        return (self.batch, self.total, self.seq_bound)
+
+
 class _State:
     """Activations kept between forward and backward of one step."""
     pass
@@ -237,9 +264,9 @@ class _SideBranch:
     the captured CUDA graph they become parallel branches that fill the SMs the (latency-bound) main chain leaves idle.
     Tensors a branch reads are kept alive until ``join`` so the caching allocator cannot recycle them early."""
 
-    def __init__(self, enabled: bool = True):
+    def __init__(self, enabled: bool = True, stream: Optional["torch.cuda.Stream"] = None):
         self.enabled = enabled
-        self.side = torch.cuda.Stream() if enabled else None
+        self.side = (stream if stream is not None else torch.cuda.Stream()) if enabled else None
         self.keep = []
 
     def run(self, fn, *tensors) -> None:
@@ -272,9 +299,33 @@ class JLEngine:
         self._pos: Dict[Tuple[str, int], torch.Tensor] = {}
         self.flat = None   # set by training.FlatAdapterParams
         self.side_branch = True   # issue weight-gradient products on a second stream (parallel graph branches)
+        self._side_streams: Dict[int, "torch.cuda.Stream"] = {}   # one side stream per device, created once
         self.fused_wf = True      # inference: WFAdapter as one kernel (jl_wfadapter_fwd)
 
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        st = self._side_streams.get(idx)
+        if st is None:
+            st = torch.cuda.Stream(device=idx)
+            self._side_streams[idx] = st
+        return st
+
     # ------------------------------------------------------------------ weights
+    def weights_version(self, include_optimizer_steps: bool = True) -> int:
+        """Changes whenever a parameter of the model (backbone, adapters, lm_head) is modified through torch (``copy_``,
+        optimizer step, ``load_state_dict``, ``load_adapter``, ``init_adapter_layers`` …) or re-allocated.  Captured CUDA graphs
+        bake in the pointers of the bf16 shadows / packed weights derived from the parameters, so ``AdapterTrainer`` and
+        ``Transcriber`` compare this number before every replay and rebuild what is stale.  The fused AdamW kernel updates the flat
+        bucket behind torch's back; it is counted through ``flat.generation`` (left out for the trainer's own check: its graph
+        reads the bucket's bf16 shadow, which that kernel refreshes in place)."""
+        v = self.flat.generation if (include_optimizer_steps and self.flat is not None) else 0
+        ps = list(self.enc.parameters())
+        if self.lm_head is not None:
+            ps += list(self.lm_head.parameters())
+        for p in ps:
+            v = (v * 1000003 + p._version * 31 + (p.data_ptr() >> 4)) & 0xFFFFFFFFFFFF
+        return v
+
     def _backbone_params(self):
         for n, p in self.enc.named_parameters():
             if ".adapter_attn." not in n and ".adapter_ffn." not in n:
@@ -384,7 +435,7 @@ class JLEngine:
         """Factors of dialect ``k`` in the layouts the fused kernel reads: B_d ⊙ γ (LayerNorm folded into the first
         projection) with its row sums s and the β term t, rank dimension of A_d / A_u zero-padded to 64."""
         ps = [ad.norm.weight, ad.norm.bias, ad.down_B, ad.down_A, ad.down_bias, ad.up_B, ad.up_A, ad.up_bias]
-        ver = tuple((q.data_ptr(), q._version) for q in ps) + (k,)
+        ver = tuple((q.data_ptr(), q._version) for q in ps) + (k, self.flat.generation if self.flat is not None else 0)
         key = ("wf", id(ad), k)
         ent = self._shadow.get(key)
         if ent is not None and ent[0] == ver:
@@ -456,16 +507,27 @@ class JLEngine:
             raise ValueError("utterances of one dialect must be adjacent in the batch (sort the batch by dialect id)")
         return [tuple(x) for x in segs]
 
-    def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect, zero_rows: bool):
-        """Returns (out, saved).  out = h + adapter(h); padded rows zeroed when ``zero_rows`` (end of a layer)."""
+    @staticmethod
+    def _seg_rows(b0: int, b1: int, t: int, pk: Optional[PackedLayout]) -> slice:
+        """Rows of the utterances [b0, b1) in the [rows, C] activation matrices."""
+        return slice(b0 * t, b1 * t) if pk is None else slice(pk.cu_host[b0], pk.cu_host[b1])
+
+    def _adapter_fwd(self, ad: nn.Module, h: torch.Tensor, lengths, b: int, t: int, training: bool, dialect, zero_rows: bool,
+                     pk: Optional[PackedLayout] = None):
+        """Returns (out, saved).  out = h + adapter(h); padded rows zeroed when ``zero_rows`` (end of a layer; the packed layout
+        ``pk`` has no padded rows)."""
         eps = ad.norm.eps
+        zero_rows = zero_rows and pk is None
+        cu = None if pk is None else pk.cu
         segs = self.dialect_segments(dialect, b, ad.num_dialects) if ad.kind == "wf" else None
         if ad.kind == "wf" and not training and self.fused_wf and self._wf_fusable(ad):
             # inference: the whole adapter is one kernel per dialect run (LN folded into the first projection); training
             # keeps the composed path because the backward needs every intermediate
             out = torch.empty_like(h)
             for k, b0, b1 in segs:
-                rows = slice(b0 * t, b1 * t)
+                rows = self._seg_rows(b0, b1, t, pk)
+                if rows.stop == rows.start:
+                    continue
                 ops.wfadapter_fwd(h[rows], self._wf_pack(ad, k), eps, row_lengths=lengths[b0:b1] if zero_rows else None,
                                   rows_per_seq=t if zero_rows else 0, out=out[rows])
             return out, None
@@ -478,7 +540,9 @@ class JLEngine:
             t2 = torch.empty((m, ad.rank), dtype=BF16, device=dev)
             out = torch.empty_like(h)
             for k, b0, b1 in segs:
-                rows = slice(b0 * t, b1 * t)
+                rows = self._seg_rows(b0, b1, t, pk)
+                if rows.stop == rows.start:
+                    continue
                 rls = dict(row_lengths=lengths[b0:b1], rows_per_seq=t) if zero_rows else {}
                 ops.gemm(z[rows], self._bf16(ad.down_B)[k], out=t1[rows])
                 ops.gemm(t1[rows], self._bf16(ad.down_A)[k], bias=ad.down_bias.detach()[k], epilogue=L.JL_EPI_RELU, out=u[rows])
@@ -489,7 +553,8 @@ class JLEngine:
             wqkv = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
             bqkv = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
             qkv = ops.gemm(z, wqkv, bias=bqkv)
-            a, lse = ops.attn_fwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], lengths, b, t, 1, 1.0 / 8.0, want_lse=training)
+            a, lse = ops.attn_fwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], lengths, b, t, 1, 1.0 / 8.0, want_lse=training,
+                                  cu_seqlens=cu)
             out = ops.gemm(a, self._bf16(ad.o_proj.weight), bias=ad.o_proj.bias.detach(), residual=h, **rl)
             saved = (h, mean, rstd, z, qkv, a, lse) if training else None
         return out, saved
@@ -516,16 +581,22 @@ class JLEngine:
         sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
         ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                                # dt1 · B_d
 
-    def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink", sb: "_SideBranch") -> torch.Tensor:
+    def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink", sb: "_SideBranch",
+                     pk: Optional[PackedLayout] = None) -> torch.Tensor:
         """dy = grad of the adapter output → returns grad of the adapter input; weight grads go to ``g`` (issued on the
         side branch ``sb``)."""
         MN = L.JL_LAYOUT_MN
+        cu = None if pk is None else pk.cu
         if ad.kind == "wf":
             h, mean, rstd, z, t1, u, t2, segs = saved
             dz = torch.empty_like(h)
+            present = set()
             for k, b0, b1 in segs:
-                self._wf_bwd_rows(ad, k, slice(b0 * t, b1 * t), dy, z, t1, u, t2, dz, g, sb)
-            present = {k for k, _, _ in segs}
+                rows = self._seg_rows(b0, b1, t, pk)
+                if rows.stop == rows.start:
+                    continue
+                present.add(k)
+                self._wf_bwd_rows(ad, k, rows, dy, z, t1, u, t2, dz, g, sb)
             for k in range(ad.num_dialects):           # factor sets without utterances in this batch: zero gradient
                 if k not in present:
                     for prm in (ad.up_A, ad.up_bias, ad.up_B, ad.down_A, ad.down_bias, ad.down_B):
@@ -538,7 +609,7 @@ class JLEngine:
                 ops.colsum(dy, out=g.out(ad.o_proj.bias))
             sb.run(w_o, dy, a)
             da = ops.gemm(dy, self._bf16(ad.o_proj.weight), b_layout=MN)                                      # dy · W_o
-            dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0)
+            dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0, cu_seqlens=cu)
             ws = [ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight]
             bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
 
@@ -606,7 +677,10 @@ class JLEngine:
         return out, t
 
     def forward(self, input_features: torch.Tensor, lengths: torch.Tensor, training: bool = False, dialect: int = 0,
-                want_logits: bool = True, sample_lengths: Optional[torch.Tensor] = None) -> _State:
+                want_logits: bool = True, sample_lengths: Optional[torch.Tensor] = None, packed: Optional[PackedLayout] = None) -> _State:
+        """``packed``: run the encoder in the packed row layout (mel front end only): the conv subsampler still sees the padded
+        [B, F, 80] features, its output is packed by the position-embedding kernel, and from there on every matrix is
+        [total valid frames, C].  ``st.logits`` / ``st.h_final`` are then packed too."""
         cfg = self.cfg
         d, heads = cfg.hidden_size, cfg.num_attention_heads
         fz = self._frozen_pack()
@@ -615,6 +689,10 @@ class JLEngine:
         st = _State()
         st.training, st.dialect = training, dialect
         st.lengths = lengths
+        st.packed = pk = packed
+        cu = None if pk is None else pk.cu
+        if pk is not None and cfg.front_end == "wav2vec2":
+            raise NotImplementedError("the packed layout is implemented for the mel front end")
         if cfg.front_end == "wav2vec2":
             b = input_features.shape[0]
             h, t = self._wav2vec2_front_end(input_features, sample_lengths, lengths, fz)
@@ -629,7 +707,13 @@ class JLEngine:
             c1 = ops.gemm(a1, fz["conv0.w"], bias=fz["conv0.b"], epilogue=L.JL_EPI_GLU)
             a2, t = ops.im2col_k5s2(c1.view(b, t1, cfg.conv_channels // 2))
             h = ops.gemm(a2, fz["conv1.w"], bias=fz["conv1.b"], epilogue=L.JL_EPI_GLU)
-            ops.embed_positions_(h, math.sqrt(d), self.pos_table(h.device, t + 2), lengths, b, t)
+            if pk is None:
+                ops.embed_positions_(h, math.sqrt(d), self.pos_table(h.device, t + 2), lengths, b, t)
+            else:
+                if pk.batch != b or max(pk.lens + [0]) > t:
+                    raise ValueError("packed layout does not match the feature batch")
+                h = ops.embed_positions_packed(h, math.sqrt(d), self.pos_table(h.device, t + 2), cu, b, t, pk.total)
+                t = pk.seq_bound                      # from here on: upper bound on an utterance's length (attention grid)
         st.b, st.t = b, t
         scale = 1.0 / 8.0   # head_dim 64
         st.layers = []
@@ -639,25 +723,26 @@ class JLEngine:
             x1, sv.mean1, sv.rstd1 = ops.layernorm_fwd(h, layer.layer_norm.weight.detach(), layer.layer_norm.bias.detach(),
                                                        layer.layer_norm.eps, save_stats=training)
             qkv = ops.gemm(x1, fz[f"{i}.wqkv"], bias=fz[f"{i}.bqkv"])
-            o, lse = ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], lengths, b, t, heads, scale, want_lse=training)
+            o, lse = ops.attn_fwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], lengths, b, t, heads, scale, want_lse=training,
+                                  cu_seqlens=cu)
             h1 = ops.gemm(o, fz[f"{i}.wo"], bias=fz[f"{i}.bo"], residual=h)
             sv.qkv, sv.o, sv.lse = qkv, o, lse
             sv.ad_attn = None
             if layer.adapter_attn is not None:
-                h1, sv.ad_attn = self._adapter_fwd(layer.adapter_attn, h1, lengths, b, t, training, dialect, zero_rows=False)
+                h1, sv.ad_attn = self._adapter_fwd(layer.adapter_attn, h1, lengths, b, t, training, dialect, zero_rows=False, pk=pk)
             sv.h1 = h1
             x2, sv.mean2, sv.rstd2 = ops.layernorm_fwd(h1, layer.final_layer_norm.weight.detach(), layer.final_layer_norm.bias.detach(),
                                                        layer.final_layer_norm.eps, save_stats=training)
-            pre = torch.empty((b * t, cfg.intermediate_size), dtype=BF16, device=h.device) if training else None
+            pre = torch.empty((h.shape[0], cfg.intermediate_size), dtype=BF16, device=h.device) if training else None
             # training: the epilogue leaves gelu'(pre-activation) for the backward GEMM (erf evaluated once per element)
             act = ops.gemm(x2, fz[f"{i}.w1"], bias=fz[f"{i}.b1"], epilogue=L.JL_EPI_GELU_DGELU if training else L.JL_EPI_GELU, aux_out=pre)
             sv.dgelu = pre
             last_is_ffn = layer.adapter_ffn is None
-            rl = dict(row_lengths=lengths, rows_per_seq=t) if last_is_ffn else {}
+            rl = dict(row_lengths=lengths, rows_per_seq=t) if (last_is_ffn and pk is None) else {}
             h2 = ops.gemm(act, fz[f"{i}.w2"], bias=fz[f"{i}.b2"], residual=h1, **rl)
             sv.ad_ffn = None
             if layer.adapter_ffn is not None:
-                h2, sv.ad_ffn = self._adapter_fwd(layer.adapter_ffn, h2, lengths, b, t, training, dialect, zero_rows=True)
+                h2, sv.ad_ffn = self._adapter_fwd(layer.adapter_ffn, h2, lengths, b, t, training, dialect, zero_rows=True, pk=pk)
             h = h2
             if training:
                 st.layers.append(sv)
@@ -679,8 +764,11 @@ class JLEngine:
                 return i
         return len(self.enc.layers)
 
-    def backward(self, st: _State, dlogits: torch.Tensor, g: "GradSink") -> None:
-        """dlogits [B*T', V] bf16 (d loss / d logits, zero on padded rows) → adapter + lm_head gradients into ``g``."""
+    def backward(self, st: _State, dlogits: torch.Tensor, g: "GradSink", on_progress=None) -> None:
+        """dlogits [B*T', V] bf16 (d loss / d logits, zero on padded rows) → adapter + lm_head gradients into ``g``.
+        ``on_progress(i, side_stream)`` is called when every weight gradient of lm_head and of the layers above ``i`` has been
+        issued (layers are visited top-down), so a trainer can start exchanging that part of the bucket while the backward of the
+        lower layers is still running."""
         for n, p in self._backbone_params():
             if p.requires_grad:
                 raise NotImplementedError(
@@ -692,7 +780,10 @@ class JLEngine:
         b, t = st.b, st.t
         ft = self._frozen_pack_t()
         lengths = st.lengths
-        sb = _SideBranch(enabled=self.side_branch)
+        pk = getattr(st, "packed", None)
+        cu = None if pk is None else pk.cu
+        sb = _SideBranch(enabled=self.side_branch, stream=self._side_stream(dlogits.device) if self.side_branch else None)
+        g.prepare(self)      # sinks that allocate do so here, on the main stream (the side branch only writes into them)
 
         # head: logits = h_final · Wᵀ + b
         def w_head():
@@ -708,8 +799,10 @@ class JLEngine:
         dh, _, _ = ops.layernorm_bwd(dhf, st.h_last, ln.weight.detach(), st.mean_f, st.rstd_f)
         for i in range(len(self.enc.layers) - 1, l0 - 1, -1):
             layer, sv = self.enc.layers[i], st.layers[i]
+            if on_progress is not None:
+                on_progress(i, sb.side)
             if layer.adapter_ffn is not None:
-                dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g, sb)
+                dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g, sb, pk=pk)
                 if i == l0 and layer.adapter_attn is None:
                     break
             # FFN: h2 = h1 + W2 · gelu(W1 · LN2(h1) + b1) + b2
@@ -718,13 +811,14 @@ class JLEngine:
             fl = layer.final_layer_norm
             dh1, _, _ = ops.layernorm_bwd(dx2, sv.h1, fl.weight.detach(), sv.mean2, sv.rstd2, dres=dh)
             if layer.adapter_attn is not None:
-                dh1 = self._adapter_bwd(layer.adapter_attn, sv.ad_attn, dh1, lengths, b, t, g, sb)
+                dh1 = self._adapter_bwd(layer.adapter_attn, sv.ad_attn, dh1, lengths, b, t, g, sb, pk=pk)
                 if i == l0:
                     break
             # attention: h1 = h + Wo · attn(LN1(h) Wqkvᵀ) + bo
             d_o = ops.gemm(dh1, ft[f"{i}.wo"])
             qkv = sv.qkv
-            dqkv = ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], sv.o, d_o, sv.lse, lengths, b, t, heads, 1.0 / 8.0)
+            dqkv = ops.attn_bwd(qkv[:, 0:d], qkv[:, d:2 * d], qkv[:, 2 * d:3 * d], sv.o, d_o, sv.lse, lengths, b, t, heads, 1.0 / 8.0,
+                                cu_seqlens=cu)
             dx1 = ops.gemm(dqkv, ft[f"{i}.wqkv"])
             l1 = layer.layer_norm
             dh, _, _ = ops.layernorm_bwd(dx1, sv.h_in, l1.weight.detach(), sv.mean1, sv.rstd1, dres=dh1)
@@ -738,6 +832,16 @@ class GradSink:
     def __init__(self):
         self.grads: Dict[int, torch.Tensor] = {}
         self.params: Dict[int, torch.Tensor] = {}
+
+    def prepare(self, engine: "JLEngine") -> None:
+        """Allocate (zeroed) gradient tensors for every trainable parameter on the CURRENT stream, before the backward pass
+        starts issuing weight-gradient products on its side stream: the caching allocator then never sees a block that was
+        allocated on one stream and freed on another."""
+        ps = [p for p in engine.enc.parameters() if p.requires_grad]
+        if engine.lm_head is not None:
+            ps += [p for p in engine.lm_head.parameters() if p.requires_grad]
+        for p in ps:
+            self._full(p)
 
     def _full(self, p: torch.Tensor) -> torch.Tensor:
         gt = self.grads.get(id(p))
@@ -778,7 +882,7 @@ class _CTCStep(torch.autograd.Function):
         sink = GradSink()
         eng = ctx.model.encoder.engine(ctx.model.lm_head)
         b, t = ctx.st.b, ctx.st.t
-        eng.backward(ctx.st, ctx.dlogits.view(b * t, -1), sink)
+        eng.backward(ctx.st, ctx.dlogits.view(-1, ctx.dlogits.shape[-1]), sink)
         grads = []
         for p in ctx.params:
             gt = sink.grads.get(id(p))
@@ -864,6 +968,12 @@ class JLForCTC(nn.Module):
         hf_named = any(".adapter_layer." in k for k in sd)
         new_vocab = sd["lm_head.weight"].shape[0] if "lm_head.weight" in sd else self.config.vocab_size
         if new_vocab != self.config.vocab_size:
+            eng = self.encoder._engine
+            if eng is not None and eng.flat is not None:
+                raise RuntimeError(
+                    f"load_adapter: the file's vocabulary ({new_vocab}) differs from the model's ({self.config.vocab_size}) and an "
+                    "AdapterTrainer is attached: its flat parameter bucket was laid out for the current lm_head.  Load the adapter "
+                    "before building the trainer (or build a new trainer afterwards).")
             dev = self.lm_head.weight.device
             self.lm_head = nn.Linear(self.config.hidden_size, new_vocab).to(dev)
             self.config.vocab_size = new_vocab
@@ -882,19 +992,22 @@ class JLForCTC(nn.Module):
                 if n in mine:
                     mine[n].copy_(v.to(mine[n].device, mine[n].dtype))
 
-    def load_hf_state_dict(self, sd, strict: bool = False, dialect: int = 0):
+    def load_hf_state_dict(self, sd, strict: bool = False, dialect: int = 0, hf_config=None):
         """Load a ``Wav2Vec2ForCTC`` / ``Speech2Text`` encoder state dict by its HF names (see ``hf_compat``).
-        Returns (missing model keys, skipped checkpoint keys)."""
-        return hf_compat.load_hf_state_dict(self, sd, strict=strict, dialect=dialect)
+        Returns (missing model keys, skipped checkpoint keys).  Post-LN / group-norm wav2vec2-base checkpoints are refused."""
+        return hf_compat.load_hf_state_dict(self, sd, strict=strict, dialect=dialect, hf_config=hf_config)
 
     # ---- forward
     def forward(self, input_features: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
                 labels: Optional[torch.Tensor] = None, frame_lengths: Optional[torch.Tensor] = None, dialect=0,
-                input_values: Optional[torch.Tensor] = None):
+                input_values: Optional[torch.Tensor] = None, packed: bool = False):
         """→ (loss | None, logits [B, T', V]).  ``labels`` [B, S] padded with -100 (any negative value).  ``dialect``: the
         WFAdapter factor set — one id, or one id per utterance (utterances of one dialect adjacent).  With
         ``front_end="wav2vec2"`` the input is the waveform batch [B, N] fp32 (``input_values``, HF's name; raw or already
-        normalised — the utterance normalisation is idempotent), ``attention_mask`` its sample mask."""
+        normalised — the utterance normalisation is idempotent), ``attention_mask`` its sample mask.
+        ``packed=True`` (mel front end): the encoder runs on the packed row layout (no work on padded frames — mixed-length
+        batches); the returned logits are then [total valid frames, V] with utterance b at rows ``self.last_packed.cu_host[b]:
+        cu_host[b+1]`` (``unpack_logits`` restores [B, T', V]).  The lengths are read back to the host once to lay the rows out."""
         cfg = self.config
         if input_features is None:
             input_features = input_values
@@ -903,17 +1016,20 @@ class JLForCTC(nn.Module):
         eng = self.encoder.engine(self.lm_head)
         lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
         train = labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self._get_adapters().values())
+        pk = PackedLayout(lengths.tolist(), lengths.device) if packed else None
+        self.last_packed = pk
         st = eng.forward(input_features, lengths, training=train, dialect=dialect, want_logits=True,
-                         sample_lengths=_sample_lengths(attention_mask, frame_lengths))
+                         sample_lengths=_sample_lengths(attention_mask, frame_lengths), packed=pk)
         b, t = st.b, st.t
-        logits = st.logits.view(b, t, cfg.vocab_size)
+        logits = st.logits if pk is not None else st.logits.view(b, t, cfg.vocab_size)
         if labels is None:
             return None, logits
         if int(labels.max()) >= cfg.vocab_size:
             raise ValueError(f"Label values must be <= vocab_size: {cfg.vocab_size}")
         lab = labels.to(device=logits.device, dtype=I32)
         loss, nll, grad = ops.ctc_loss(logits, lab, lengths, blank=cfg.pad_token_id, reduction=cfg.ctc_loss_reduction,
-                                       zero_infinity=cfg.ctc_zero_infinity, want_grad=train, grad_dtype=BF16)
+                                       zero_infinity=cfg.ctc_zero_infinity, want_grad=train, grad_dtype=BF16,
+                                       cu_seqlens=None if pk is None else pk.cu, max_len=0 if pk is None else pk.seq_bound)
         loss = loss.view(())
         if train:
             params = [p for p in self._get_adapters().values() if p.requires_grad]
@@ -923,10 +1039,23 @@ class JLForCTC(nn.Module):
     def output_lengths(self, input_features, attention_mask=None, frame_lengths=None) -> torch.Tensor:
         return self.encoder.engine(self.lm_head).output_lengths(input_features, attention_mask, frame_lengths)
 
+    @staticmethod
+    def unpack_logits(logits: torch.Tensor, pk: PackedLayout) -> torch.Tensor:
+        """[total, V] packed logits → [B, max T', V] (padded frames zero): a row gather, no arithmetic."""
+        tmax = max(pk.lens + [1])
+        out = logits.new_zeros((pk.batch, tmax, logits.shape[-1]))
+        for b, n in enumerate(pk.lens):
+            out[b, :n] = logits[pk.cu_host[b]: pk.cu_host[b + 1]]
+        return out
+
     @torch.no_grad()
-    def greedy_decode(self, logits: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+    def greedy_decode(self, logits: torch.Tensor, lengths: torch.Tensor, packed: Optional[PackedLayout] = None) -> List[List[int]]:
         """argmax → collapse repeats → strip blank (tokenization_wav2vec2.py:310-317) on the GPU; only the compacted
-        ids cross to the host."""
+        ids cross to the host.  ``packed``: the layout of [total, V] logits produced with ``forward(packed=True)``."""
+        if packed is not None:
+            ids, n, _ = ops.ctc_greedy(logits, lengths.to(I32), blank=self.config.pad_token_id, cu_seqlens=packed.cu, max_len=packed.seq_bound)
+            ids, n = ids.cpu(), n.cpu()
+            return [ids[i, : int(n[i])].tolist() for i in range(ids.shape[0])]
         ids, n, _ = ops.ctc_greedy(logits, lengths.to(I32), blank=self.config.pad_token_id)
         ids, n = ids.cpu(), n.cpu()
         return [ids[i, : int(n[i])].tolist() for i in range(ids.shape[0])]

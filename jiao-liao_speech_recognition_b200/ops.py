@@ -235,28 +235,42 @@ def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional
 
 # ----------------------------------------------------------------------------------------------- attention
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int, heads: int,
-             scale: float, want_lse: bool = False):
-    """q/k/v: [B*seq, heads*64] views (unit inner stride, common row stride).  Returns (o [B*seq, heads*64] bf16, lse | None)."""
+             scale: float, want_lse: bool = False, cu_seqlens: Optional[torch.Tensor] = None):
+    """q/k/v: [B*seq, heads*64] views (unit inner stride, common row stride).  Returns (o [B*seq, heads*64] bf16, lse | None).
+    Packed layout (``cu_seqlens`` [B + 1] int32): q/k/v/o are [total, heads*64], utterance b = rows [cu[b], cu[b+1]), ``seq`` is the
+    upper bound on an utterance's length, lse is [heads, total]."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _need(t, BF16, nm)
         _rows2d(t, nm)
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise ValueError("attn: q, k, v must share one row stride")
-    if q.shape[0] != batch * seq or q.shape[1] != heads * 64:
-        raise ValueError(f"attn: q has shape {tuple(q.shape)}, expected {(batch * seq, heads * 64)} (head_dim is 64)")
-    o = torch.empty((batch * seq, heads * 64), dtype=BF16, device=q.device)
-    lse = torch.empty((batch, heads, seq), dtype=F32, device=q.device) if want_lse else None
+    rows = q.shape[0]
+    if cu_seqlens is None:
+        if rows != batch * seq:
+            raise ValueError(f"attn: q has {rows} rows, expected {batch * seq}")
+    else:
+        _need(cu_seqlens, I32, "cu_seqlens", 1)
+        if cu_seqlens.numel() != batch + 1:
+            raise ValueError(f"attn: cu_seqlens must have {batch + 1} entries")
+    if q.shape[1] != heads * 64:
+        raise ValueError(f"attn: q has shape {tuple(q.shape)}, expected {heads * 64} columns (head_dim is 64)")
+    o = torch.empty((rows, heads * 64), dtype=BF16, device=q.device)
+    lse = None
+    if want_lse:
+        lse = torch.empty((batch, heads, seq) if cu_seqlens is None else (heads, rows), dtype=F32, device=q.device)
     p = L.AttnFwdParams(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), ld_qkv=q.stride(0), o=o.data_ptr(), ld_o=o.stride(0),
-                        lse=_ptr(lse), lengths=_ptr(lengths), batch=batch, seq=seq, heads=heads, scale=scale)
+                        lse=_ptr(lse), lengths=_ptr(lengths), batch=batch, seq=seq, heads=heads, scale=scale,
+                        cu_seqlens=_ptr(cu_seqlens), total_rows=rows if cu_seqlens is not None else 0)
     L.check(L.load().jl_attn_fwd(C.byref(p), _stream()))
     return o, lse
 
 
-def attn_bwd(q, k, v, o, d_o, lse, lengths, batch: int, seq: int, heads: int, scale: float):
-    """Returns dqkv [B*seq, 3*heads*64] bf16 (dq | dk | dv column blocks)."""
+def attn_bwd(q, k, v, o, d_o, lse, lengths, batch: int, seq: int, heads: int, scale: float, cu_seqlens: Optional[torch.Tensor] = None):
+    """Returns dqkv [B*seq, 3*heads*64] bf16 (dq | dk | dv column blocks); [total, 3*heads*64] in the packed layout."""
     hd = heads * 64
-    dqkv = torch.empty((batch * seq, 3 * hd), dtype=BF16, device=q.device)
-    delta = torch.empty((batch, heads, seq), dtype=F32, device=q.device)
+    rows = q.shape[0]
+    dqkv = torch.empty((rows, 3 * hd), dtype=BF16, device=q.device)
+    delta = torch.empty((batch, heads, seq) if cu_seqlens is None else (heads, rows), dtype=F32, device=q.device)
     for t, nm in ((o, "o"), (d_o, "d_o")):
         _need(t, BF16, nm)
         _rows2d(t, nm)
@@ -265,36 +279,49 @@ def attn_bwd(q, k, v, o, d_o, lse, lengths, batch: int, seq: int, heads: int, sc
     p = L.AttnBwdParams(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), ld_qkv=q.stride(0), o=o.data_ptr(), d_o=d_o.data_ptr(),
                         ld_o=o.stride(0), lse=lse.data_ptr(), dq=dqkv.data_ptr(), dk=dqkv[:, hd:].data_ptr(),
                         dv=dqkv[:, 2 * hd:].data_ptr(), ld_dqkv=dqkv.stride(0), delta=delta.data_ptr(), lengths=_ptr(lengths),
-                        batch=batch, seq=seq, heads=heads, scale=scale)
+                        batch=batch, seq=seq, heads=heads, scale=scale, cu_seqlens=_ptr(cu_seqlens),
+                        total_rows=rows if cu_seqlens is not None else 0)
     L.check(L.load().jl_attn_bwd(C.byref(p), _stream()))
     return dqkv
 
 
 # ----------------------------------------------------------------------------------------------- CTC
 def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, input_lengths: torch.Tensor, blank: int = 0, reduction: str = "sum",
-             zero_infinity: bool = False, want_grad: bool = False, grad_dtype=BF16):
+             zero_infinity: bool = False, want_grad: bool = False, grad_dtype=BF16, cu_seqlens: Optional[torch.Tensor] = None,
+             max_len: int = 0):
     """logits [B, T, V] (fp32 | bf16, unit inner stride), labels [B, S] int32 (negative = pad), input_lengths [B] int32.
-    Returns (loss [1] fp32, nll [B] fp32, grad [B, T, V] | None)."""
+    Returns (loss [1] fp32, nll [B] fp32, grad [B, T, V] | None).  Packed layout: logits [total, V] with ``cu_seqlens`` [B + 1]
+    and ``max_len`` >= every length; the gradient is then [total, V] too."""
     if logits.dtype not in (F32, BF16):
         raise TypeError("ctc_loss: logits must be fp32 or bf16")
-    _need(logits, logits.dtype, "logits", 3)
     _need(labels, I32, "labels", 2)
     _need(input_lengths, I32, "input_lengths", 1)
     if reduction not in ("sum", "mean"):
         raise ValueError(f"ctc_loss: unsupported reduction {reduction!r}")
-    b, t, v = logits.shape
-    if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
-        raise ValueError("ctc_loss: logits must be row-contiguous [B*T, V]")
+    if cu_seqlens is None:
+        _need(logits, logits.dtype, "logits", 3)
+        b, t, v = logits.shape
+        if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
+            raise ValueError("ctc_loss: logits must be row-contiguous [B*T, V]")
+        ld, gshape = logits.stride(1), (b, t, v)
+    else:
+        _need(logits, logits.dtype, "logits", 2)
+        _need(cu_seqlens, I32, "cu_seqlens", 1)
+        _rows2d(logits, "logits")
+        b, t, v = input_lengths.numel(), int(max_len), logits.shape[1]
+        if t <= 0 or cu_seqlens.numel() != b + 1:
+            raise ValueError("ctc_loss: the packed layout needs max_len > 0 and cu_seqlens of B + 1 entries")
+        ld, gshape = logits.stride(0), (logits.shape[0], v)
     labels = labels.contiguous()
     dev = logits.device
     nll = torch.empty((b,), dtype=F32, device=dev)
     loss = torch.empty((1,), dtype=F32, device=dev)
-    grad = torch.empty((b, t, v), dtype=grad_dtype, device=dev) if want_grad else None
-    p = L.CtcParams(logits=logits.data_ptr(), ld_logits=logits.stride(1), logits_dtype=L.JL_DT_F32 if logits.dtype == F32 else L.JL_DT_BF16,
+    grad = torch.empty(gshape, dtype=grad_dtype, device=dev) if want_grad else None
+    p = L.CtcParams(logits=logits.data_ptr(), ld_logits=ld, logits_dtype=L.JL_DT_F32 if logits.dtype == F32 else L.JL_DT_BF16,
                     labels=labels.data_ptr(), max_label_len=labels.shape[1], input_lengths=input_lengths.data_ptr(), batch=b, seq=t,
                     vocab=v, blank=blank, reduction=L.JL_CTC_SUM if reduction == "sum" else L.JL_CTC_MEAN,
                     zero_infinity=1 if zero_infinity else 0, nll=nll.data_ptr(), loss=loss.data_ptr(), grad=_ptr(grad),
-                    ld_grad=v, grad_dtype=L.JL_DT_F32 if grad_dtype == F32 else L.JL_DT_BF16)
+                    ld_grad=v, grad_dtype=L.JL_DT_F32 if grad_dtype == F32 else L.JL_DT_BF16, cu_seqlens=_ptr(cu_seqlens))
     lib = L.load()
     nbytes = C.c_size_t(0)
     L.check(lib.jl_ctc_workspace_bytes(C.byref(p), C.byref(nbytes)))
@@ -303,23 +330,35 @@ def ctc_loss(logits: torch.Tensor, labels: torch.Tensor, input_lengths: torch.Te
     return loss, nll, grad
 
 
-def ctc_greedy(logits: torch.Tensor, input_lengths: torch.Tensor, blank: int = 0):
-    """→ (out_ids [B, T] int32 with -1 tail, out_lengths [B] int32, frame_ids [B, T] int32)."""
+def ctc_greedy(logits: torch.Tensor, input_lengths: torch.Tensor, blank: int = 0, cu_seqlens: Optional[torch.Tensor] = None,
+               max_len: int = 0):
+    """→ (out_ids [B, T] int32 with -1 tail, out_lengths [B] int32, frame_ids [B, T] int32).  Packed layout: logits [total, V] with
+    ``cu_seqlens`` [B + 1] and T = ``max_len``."""
     if logits.dtype not in (F32, BF16):
         raise TypeError("ctc_greedy: logits must be fp32 or bf16")
-    _need(logits, logits.dtype, "logits", 3)
     _need(input_lengths, I32, "input_lengths", 1)
-    b, t, v = logits.shape
-    if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
-        raise ValueError("ctc_greedy: logits must be row-contiguous [B*T, V]")
+    if cu_seqlens is None:
+        _need(logits, logits.dtype, "logits", 3)
+        b, t, v = logits.shape
+        if logits.stride(2) != 1 or logits.stride(0) != t * logits.stride(1):
+            raise ValueError("ctc_greedy: logits must be row-contiguous [B*T, V]")
+        ld = logits.stride(1)
+    else:
+        _need(logits, logits.dtype, "logits", 2)
+        _need(cu_seqlens, I32, "cu_seqlens", 1)
+        _rows2d(logits, "logits")
+        b, t, v = input_lengths.numel(), int(max_len), logits.shape[1]
+        if t <= 0 or cu_seqlens.numel() != b + 1:
+            raise ValueError("ctc_greedy: the packed layout needs max_len > 0 and cu_seqlens of B + 1 entries")
+        ld = logits.stride(0)
     dev = logits.device
     frame_ids = torch.empty((b, t), dtype=I32, device=dev)
     out_ids = torch.empty((b, t), dtype=I32, device=dev)
     out_len = torch.empty((b,), dtype=I32, device=dev)
-    p = L.CtcGreedyParams(logits=logits.data_ptr(), ld_logits=logits.stride(1),
+    p = L.CtcGreedyParams(logits=logits.data_ptr(), ld_logits=ld,
                           logits_dtype=L.JL_DT_F32 if logits.dtype == F32 else L.JL_DT_BF16, input_lengths=input_lengths.data_ptr(),
                           batch=b, seq=t, vocab=v, blank=blank, frame_ids=frame_ids.data_ptr(), out_ids=out_ids.data_ptr(),
-                          out_lengths=out_len.data_ptr())
+                          out_lengths=out_len.data_ptr(), cu_seqlens=_ptr(cu_seqlens))
     L.check(L.load().jl_ctc_greedy(C.byref(p), _stream()))
     return out_ids, out_len, frame_ids
 
@@ -384,6 +423,20 @@ def embed_positions_(h: torch.Tensor, scale: float, pos_table: torch.Tensor, len
     return h
 
 
+def embed_positions_packed(h: torch.Tensor, scale: float, pos_table: torch.Tensor, cu_seqlens: torch.Tensor, batch: int, seq: int,
+                           total: int) -> torch.Tensor:
+    """h [B·seq, d] bf16 (padded rows) → [total, d] bf16 packed rows: × scale + sinusoid row (t + 2); padded frames are dropped."""
+    _need(h, BF16, "h", 2)
+    _need(pos_table, F32, "pos_table", 2)
+    _need(cu_seqlens, I32, "cu_seqlens", 1)
+    if not h.is_contiguous() or h.shape[0] != batch * seq or pos_table.shape[0] < seq + 2 or pos_table.shape[1] != h.shape[1] or not pos_table.is_contiguous():
+        raise ValueError("embed_positions_packed: bad shapes")
+    out = torch.empty((total, h.shape[1]), dtype=BF16, device=h.device)
+    L.check(L.load().jl_embed_positions_packed(h.data_ptr(), out.data_ptr(), scale, pos_table.data_ptr(), cu_seqlens.data_ptr(), batch, seq,
+                                               h.shape[1], _stream()))
+    return out
+
+
 def transpose(x: torch.Tensor) -> torch.Tensor:
     _need(x, BF16, "x")
     _rows2d(x, "x")
@@ -425,12 +478,24 @@ def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) ->
 
 def adamw_(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, lr: float,
            beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01, grad_scale: float = 1.0,
-           param_bf16: Optional[torch.Tensor] = None) -> None:
+           param_bf16: Optional[torch.Tensor] = None, hyper_dev: Optional[torch.Tensor] = None) -> None:
+    """Fused AdamW on a flat fp32 bucket (any contiguous slice of it).  ``hyper_dev``: fp32 CUDA tensor {lr, 1 - β1^t, sqrt(1 - β2^t)}
+    read by the kernel instead of ``lr`` / ``step`` (graph-captured launches)."""
     for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _need(t, F32, nm, 1)
         if not t.is_contiguous():
             raise ValueError(f"adamw: {nm} must be contiguous")
     p = L.AdamWParams(param=param.data_ptr(), grad=grad.data_ptr(), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(),
                       param_bf16=_ptr(param_bf16), n=param.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
-                      weight_decay=weight_decay, grad_scale=grad_scale, step=step)
+                      weight_decay=weight_decay, grad_scale=grad_scale, step=step, hyper_dev=_ptr(hyper_dev))
+    if hyper_dev is not None:
+        _need(hyper_dev, F32, "hyper_dev", 1)
     L.check(L.load().jl_adamw_bucket(C.byref(p), _stream()))
+
+
+def adamw_advance_(hyper: torch.Tensor) -> None:
+    """hyper = {lr, bc1, bc2_sqrt, step, beta1, beta2} fp32 on the device: step += 1 and the bias corrections follow."""
+    _need(hyper, F32, "hyper", 1)
+    if hyper.numel() < 6 or not hyper.is_contiguous():
+        raise ValueError("adamw_advance: hyper must be a contiguous fp32 tensor of 6 elements")
+    L.check(L.load().jl_adamw_advance(hyper.data_ptr(), _stream()))

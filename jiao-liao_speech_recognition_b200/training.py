@@ -18,15 +18,32 @@ from . import _lib as L
 from . import ops
 from .comm import JLComm
 from .feature_extraction import JLFeatureExtractor, device_tables, num_frames
-from .modeling import AttAdapter, GradSink, JLForCTC, subsampled_length, wav2vec2_lengths
+from .modeling import AttAdapter, GradSink, JLForCTC, PackedLayout, subsampled_length, wav2vec2_lengths
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 _ALIGN = 64   # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 buffer
 
 
-def ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
-    """Trainable parameters, with each AttAdapter's q/k/v weights (and biases) adjacent so that the concatenated
+def _layer_adapter_params(layer) -> List[torch.nn.Parameter]:
+    """Adapter parameters of one encoder layer, an AttAdapter's q/k/v weights (and biases) adjacent so that the concatenated
     [192, d] projection the kernels use is a plain view of the bucket."""
+    out = []
+    for ad in (layer.adapter_attn, layer.adapter_ffn):
+        if ad is None:
+            continue
+        first = []
+        if isinstance(ad, AttAdapter):
+            first = [ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight, ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
+        seen = {id(p) for p in first}
+        out += first + [p for p in ad.parameters() if id(p) not in seen]
+    return out
+
+
+def ordered_trainables(model: JLForCTC, return_split: bool = False):
+    """Trainable parameters in the order the backward pass completes their gradients: lm_head first, then the adapters of
+    layer L-1, L-2, … 0.  The bucket can then be exchanged in two contiguous halves — [lm_head + layers >= L/2] while the
+    backward of the lower layers is still running, [layers < L/2] at the end.  With ``return_split`` also returns
+    the index (into the list) of the first parameter of the second half."""
     seen, out = set(), []
 
     def add(p):
@@ -34,13 +51,21 @@ def ordered_trainables(model: JLForCTC) -> List[torch.nn.Parameter]:
             seen.add(id(p))
             out.append(p)
 
-    for m in model.modules():
-        if isinstance(m, AttAdapter):
-            for p in (m.q_proj.weight, m.k_proj.weight, m.v_proj.weight, m.q_proj.bias, m.k_proj.bias, m.v_proj.bias):
-                add(p)
-    for p in model._get_adapters().values():
+    for p in model.lm_head.parameters():
         add(p)
-    return out
+    layers = list(model.encoder.layers)
+    split_layer = len(layers) // 2
+    split_idx = None
+    for i in range(len(layers) - 1, -1, -1):
+        if i == split_layer - 1 and split_idx is None:
+            split_idx = len(out)
+        for p in _layer_adapter_params(layers[i]):
+            add(p)
+    for p in model._get_adapters().values():          # anything the walk above did not reach
+        add(p)
+    if split_idx is None:
+        split_idx = len(out)
+    return (out, split_idx, split_layer) if return_split else out
 
 
 class BucketLayout:
@@ -86,7 +111,7 @@ class FlatAdapterParams(GradSink):
     def __init__(self, model: JLForCTC):
         super().__init__()
         self.model = model
-        self.plist = ordered_trainables(model)
+        self.plist, split_idx, self.split_layer = ordered_trainables(model, return_split=True)
         if not self.plist:
             raise ValueError("no trainable parameters: call model.freeze_base_model() first")
         dev = self.plist[0].device
@@ -95,6 +120,8 @@ class FlatAdapterParams(GradSink):
         self.layout = BucketLayout(self.plist)
         self.offset = self.layout.offset
         self.total, self.num_params = self.layout.total, self.layout.num_params
+        # element offset where the second half of the bucket (adapters of the layers below split_layer) starts
+        self.split = self.layout.offset[id(self.plist[split_idx])] if split_idx < len(self.plist) else self.total
         off = self.total
         self.param = torch.zeros(off, dtype=F32, device=dev)
         self.grad = torch.zeros(off, dtype=F32, device=dev)
@@ -109,8 +136,35 @@ class FlatAdapterParams(GradSink):
                 p.grad = self._view(self.grad, p)
         ops.cast_bf16(self.param, out=self.bf16)
         self.step_count = 0
-        self.comm = None          # optional JLComm (C-ABI NCCL communicator); None → torch.distributed, if initialised
+        self.generation = 0       # bumped by every fused AdamW step (the kernel writes the bucket behind torch's version counters)
+        # how gradients are exchanged: "none" = single rank (no collective, even inside an initialised process group),
+        # "jl" = jl_comm_allreduce through ``self.comm`` (a JLComm), "torch" = torch.distributed.all_reduce (any backend; the
+        # gloo path of the CPU tests)
+        self.comm_mode = "none"
+        self.comm = None
         model.encoder.engine(model.lm_head).flat = self
+
+    def set_comm(self, mode: str, comm=None) -> None:
+        if mode not in ("none", "jl", "torch"):
+            raise ValueError(f"comm mode must be 'none', 'jl' or 'torch', got {mode!r}")
+        if mode == "jl" and comm is None:
+            raise ValueError("comm mode 'jl' needs a JLComm")
+        if mode == "torch" and not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("comm mode 'torch' needs an initialised torch.distributed process group")
+        self.comm_mode, self.comm = mode, (comm if mode == "jl" else None)
+
+    def prepare(self, engine) -> None:      # GradSink interface: the bucket already exists
+        return None
+
+    def torch_version(self) -> int:
+        """Sum of the torch version counters of the trainable parameters: changes when one of them is written through torch
+        (``load_adapter``, ``init_adapter_layers``, ``load_state_dict``, a torch optimizer) — not by ``adamw_step``."""
+        return sum(p._version for p in self.plist)
+
+    def refresh_shadow(self) -> None:
+        """Re-derive the bf16 shadow the kernels read from the fp32 master bucket."""
+        ops.cast_bf16(self.param, out=self.bf16)
+        self.generation += 1
 
     def _view(self, buf: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
         return self.layout.view(buf, p)
@@ -146,22 +200,25 @@ class FlatAdapterParams(GradSink):
 
     # ---- collective + optimizer
     def world_size(self) -> int:
-        if self.comm is not None:
+        if self.comm_mode == "jl":
             return self.comm.world
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.comm_mode == "torch":
+            return dist.get_world_size()
+        return 1
 
-    def allreduce(self) -> None:
-        """Sum of the gradient bucket over ranks — the single collective of the fine-tune step (NCCL over NVLink):
-        ``jl_comm_allreduce`` when a ``JLComm`` is attached, else ``torch.distributed.all_reduce`` (also the gloo path
-        of the CPU tests)."""
-        if self.comm is not None:
-            self.comm.allreduce_(self.grad)
-        elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+    def allreduce(self, lo: int = 0, hi: Optional[int] = None) -> None:
+        """Sum of the gradient bucket (elements [lo, hi)) over ranks — the single collective of the fine-tune step (NCCL over
+        NVLink): ``jl_comm_allreduce`` in mode "jl", ``torch.distributed.all_reduce`` in mode "torch", nothing in mode "none"."""
+        buf = self.grad if (lo == 0 and hi is None) else self.grad[lo:hi]
+        if self.comm_mode == "jl":
+            self.comm.allreduce_(buf)
+        elif self.comm_mode == "torch" and dist.get_world_size() > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
 
     def adamw_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.01) -> None:
         world = self.world_size()
         self.step_count += 1
+        self.generation += 1
         ops.adamw_(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, beta1, beta2, eps, weight_decay,
                    grad_scale=1.0 / world, param_bf16=self.bf16)
 
@@ -196,47 +253,162 @@ def shard_utterances(num_frames_per_utt: Sequence[int], world: int) -> List[List
 
 
 class AdapterTrainer:
-    """One fine-tune step = H2D(waveforms, labels) → [mel+CMVN → encoder → lm_head → CTC loss+grad → adapter-only
-    backward] → all-reduce(adapter grads) → fused AdamW → D2H(loss).  The bracketed part is captured in a CUDA graph
-    per (batch, samples, label length) shape."""
+    """One fine-tune step = H2D(waveforms, labels) → [mel+CMVN → encoder → lm_head → CTC loss+grad → adapter-only backward →
+    all-reduce(adapter grads) → fused AdamW] → D2H(loss).  The bracketed part is ONE CUDA graph per input shape.
 
-    def __init__(self, model: JLForCTC, lr: float = 1e-4, weight_decay: float = 0.01, use_cuda_graph: bool = True, comm="auto"):
-        """``comm``: a ``JLComm``; ``"auto"`` (default) builds one from the initialised torch.distributed group when the
-        world has more than one rank; ``"torch"`` leaves the all-reduce to ``torch.distributed``; ``None`` = single rank."""
+    Gradient exchange: the flat bucket is ordered as the backward pass completes it (lm_head, then the adapters of
+    layers L-1 … 0), so it is reduced in two contiguous halves — [lm_head + layers >= L/2] on a communication stream while the
+    backward of the lower layers is still running, [layers < L/2] at the end — each followed by its slice of the fused AdamW.
+    The optimizer's step-dependent scalars live in device memory (``jl_adamw_advance``), so nothing in the graph depends on the
+    step number.
+
+    ``packed=True`` runs the encoder on the packed row layout (mixed-length batches: no GEMM / LayerNorm / attention / CTC work on
+    padded frames); the graph is then keyed by the batch's (total frames, longest-utterance bucket) as well."""
+
+    def __init__(self, model: JLForCTC, lr: float = 1e-4, weight_decay: float = 0.01, use_cuda_graph: bool = True, comm="auto",
+                 betas=(0.9, 0.999), eps: float = 1e-8, overlap_exchange: bool = True, packed: bool = False,
+                 exchange_in_graph: bool = True):
+        """``comm``: ``"auto"`` (default) builds a ``JLComm`` from the initialised torch.distributed group when the world has more
+        than one rank, else no collective; a ``JLComm`` uses it; ``"torch"`` leaves the all-reduce to ``torch.distributed``;
+        ``None`` / ``"none"`` = single rank: no collective and no 1/world scaling even inside an initialised process group."""
         self.model = model
         self.cfg = model.config
         self.flat = FlatAdapterParams(model)
         if comm == "auto":
             multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-            comm = JLComm.from_torch_distributed() if multi else None
+            if multi:
+                self.flat.set_comm("jl", JLComm.from_torch_distributed())
         elif comm == "torch":
-            comm = None
-        self.flat.comm = comm
+            self.flat.set_comm("torch")
+        elif isinstance(comm, JLComm):
+            self.flat.set_comm("jl", comm)
+        elif comm not in (None, "none"):
+            raise ValueError(f"comm must be 'auto', 'torch', 'none', None or a JLComm, got {comm!r}")
         self.eng = model.encoder.engine(model.lm_head)
-        self.fe = JLFeatureExtractor(device=self.flat.param.device)
-        self.lr, self.weight_decay = lr, weight_decay
+        dev = self.flat.param.device
+        self.fe = JLFeatureExtractor(device=dev)
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.use_cuda_graph = use_cuda_graph
+        self.overlap_exchange = overlap_exchange and exchange_in_graph
+        # False: the graph holds forward + backward only; all-reduce and AdamW follow it on the same stream (the round-1 scheme)
+        self.exchange_in_graph = exchange_in_graph
+        self.packed = packed
+        if packed and self.cfg.front_end != "mel":
+            raise NotImplementedError("packed=True is implemented for the mel front end")
+        self.grad_scale: Optional[float] = None      # None → 1 / world size of the gradient exchange
+        # device-side optimizer clock {lr, 1 - β1^t, sqrt(1 - β2^t), t, β1, β2}
+        self.hyper = torch.tensor([lr, 0.0, 0.0, 0.0, betas[0], betas[1]], dtype=F32, device=dev)
+        self._comm_stream = torch.cuda.Stream(device=dev)
         self._graphs: Dict[tuple, dict] = {}
         self._stage: Dict[tuple, dict] = {}
         self._staged = None
         self._copy_stream = None
+        self._seen_version = None
         self.launches_per_step = 0
+        self._warm_kernels()
 
-    def _body(self, wave, nsamp, lengths, labels, max_frames, dialect=0):
+    def _warm_kernels(self) -> None:
+        """Launch the optimizer kernels and the collective once on scratch data, outside any capture: the first launch of a
+        kernel loads its module, and the first collective sets up NCCL's channels — neither belongs inside a stream capture."""
+        dev = self.flat.param.device
+        scratch = torch.zeros(4 * 64, dtype=F32, device=dev)
+        hyper = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.9, 0.999], dtype=F32, device=dev)
+        ops.adamw_advance_(hyper)
+        ops.adamw_(scratch[0:64], scratch[64:128], scratch[128:192], scratch[192:256], 0, 0.0, hyper_dev=hyper)
+        if self.flat.comm_mode == "jl":
+            self.flat.comm.allreduce_(scratch)
+        elif self.flat.comm_mode == "torch" and dist.get_world_size() > 1:
+            dist.all_reduce(scratch)
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ weights that changed behind the graphs
+    def set_lr(self, lr: float) -> None:
+        """Change the learning rate of the following steps (one 4-byte host → device write; the graphs read it from device memory)."""
+        self.lr = lr
+        self.hyper[0:1].copy_(torch.tensor([lr], dtype=F32))
+
+    def refresh(self) -> None:
+        """Re-derive everything the captured graphs bake in from the current parameters: the bf16 shadow of the bucket, and —
+        by dropping the graphs — the packed / transposed copies of the backbone.  Called automatically by ``step()`` when a
+        parameter was written through torch since the last step (``load_adapter``, ``load_hf_state_dict``,
+        ``init_adapter_layers``, ``load_state_dict``, a torch optimizer)."""
+        self.flat.refresh_shadow()
+        for ent in self._graphs.values():
+            ent["graph"] = None
+        self._seen_version = self._version()
+
+    def _version(self):
+        return (self.eng.weights_version(include_optimizer_steps=False), id(self.model.lm_head))
+
+    def _check_weights(self) -> None:
+        v = self._version()
+        if self._seen_version is None:
+            self._seen_version = v
+        elif v != self._seen_version:
+            if id(self.model.lm_head.weight) not in self.flat.offset:
+                raise RuntimeError("lm_head was replaced (resized) under an attached AdapterTrainer: build a new trainer")
+            self.refresh()
+
+    # ------------------------------------------------------------------ the step body (what the graph captures)
+    def _exchange_and_update(self, lo: int, hi: int) -> None:
+        """All-reduce + AdamW of the bucket elements [lo, hi) on the current (communication) stream."""
+        if hi <= lo:
+            return
+        f = self.flat
+        f.allreduce(lo, hi)
+        scale = self.grad_scale if self.grad_scale is not None else 1.0 / f.world_size()
+        ops.adamw_(f.param[lo:hi], f.grad[lo:hi], f.exp_avg[lo:hi], f.exp_avg_sq[lo:hi], 0, self.lr, self.betas[0], self.betas[1], self.eps,
+                   self.weight_decay, grad_scale=scale, param_bf16=f.bf16[lo:hi], hyper_dev=self.hyper)
+
+    def _body(self, wave, nsamp, lengths, labels, max_frames, dialect=0, pk=None, update: bool = True):
+        main = torch.cuda.current_stream()
+        cs = self._comm_stream
+        f = self.flat
+        if update:
+            cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                ops.adamw_advance_(self.hyper)                 # the optimizer clock ticks while the forward pass runs
         if self.cfg.front_end == "wav2vec2":
             st = self.eng.forward(wave, lengths, training=True, dialect=dialect, want_logits=True, sample_lengths=nsamp)
         else:
             feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-            st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, dialect=dialect, want_logits=True)
+            st = self.eng.forward(feats["input_features_bf16"], lengths, training=True, dialect=dialect, want_logits=True, packed=pk)
         b, t = st.b, st.t
-        logits = st.logits.view(b, t, self.cfg.vocab_size)
-        loss, nll, grad = ops.ctc_loss(logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
-                                       zero_infinity=self.cfg.ctc_zero_infinity, want_grad=True, grad_dtype=BF16)
-        self.eng.backward(st, grad.view(b * t, -1), self.flat)
+        if pk is None:
+            logits = st.logits.view(b, t, self.cfg.vocab_size)
+            loss, nll, grad = ops.ctc_loss(logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
+                                           zero_infinity=self.cfg.ctc_zero_infinity, want_grad=True, grad_dtype=BF16)
+        else:
+            loss, nll, grad = ops.ctc_loss(st.logits, labels, lengths, blank=self.cfg.pad_token_id, reduction=self.cfg.ctc_loss_reduction,
+                                           zero_infinity=self.cfg.ctc_zero_infinity, want_grad=True, grad_dtype=BF16,
+                                           cu_seqlens=pk.cu, max_len=pk.seq_bound)
+        state = {"first_done": False}
+        split_layer, split = f.split_layer, f.split
+
+        def progress(i, side):
+            # layers above i are done: once the upper half of the stack is, its half of the bucket (lm_head + adapters of the
+            # layers >= split_layer) is complete as soon as the weight-gradient branch has drained
+            if update and self.overlap_exchange and not state["first_done"] and i == split_layer - 1 and 0 < split < f.total:
+                state["first_done"] = True
+                if side is not None:
+                    cs.wait_stream(side)
+                cs.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cs):
+                    self._exchange_and_update(0, split)
+
+        self.eng.backward(st, grad.view(-1, grad.shape[-1]), f, on_progress=progress)
+        if update:
+            cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                if state["first_done"]:
+                    self._exchange_and_update(split, f.total)
+                else:
+                    self._exchange_and_update(0, f.total)
+            main.wait_stream(cs)
         return loss
 
-    def _static(self, b: int, n: int, s: int, dialect=0) -> dict:
-        key = (b, n, s, dialect)                 # the dialect runs are host-side structure baked into the captured graph
+    def _static(self, b: int, n: int, s: int, dialect=0, pkey=None) -> dict:
+        key = (b, n, s, dialect, pkey)           # the dialect runs / packed row counts are host-side structure baked into the graph
         ent = self._graphs.get(key)
         if ent is not None:
             return ent
@@ -246,8 +418,10 @@ class AdapterTrainer:
             "nsamp": torch.full((b,), n, dtype=I32, device=dev),
             "lengths": torch.ones((b,), dtype=I32, device=dev),
             "labels": torch.full((b, s), -100, dtype=I32, device=dev),
+            "cu": torch.zeros((b + 1,), dtype=I32, device=dev),
             "max_frames": max(num_frames(n), 1),
             "dialect": dialect,
+            "pk": None,
             "graph": None,
             "loss": None,
         }
@@ -256,6 +430,16 @@ class AdapterTrainer:
 
     def _token_lengths(self, num_samples: torch.Tensor) -> torch.Tensor:
         return token_lengths(self.cfg, num_samples)
+
+    def _layout(self, lengths_host: torch.Tensor, dialect):
+        """Packed mode: (host row layout, graph-key part).  With per-utterance dialects the row ranges of the dialect runs are
+        baked into the graph, so the key then holds every length."""
+        if not self.packed:
+            return None, None
+        lens = [int(x) for x in lengths_host.tolist()]
+        total, bound = sum(lens), max(128, (max(lens + [1]) + 127) // 128 * 128)
+        pkey = (total, bound) if isinstance(dialect, int) else (total, bound, tuple(lens))
+        return lens, pkey
 
     def submit(self, wave: torch.Tensor, num_samples: torch.Tensor, labels: torch.Tensor, dialect=0) -> None:
         """Stage the NEXT batch while the current step is still running: the host → device copies (pinned host memory) go to
@@ -270,7 +454,7 @@ class AdapterTrainer:
         if st is None:
             st = {"wave": torch.empty((b, n), dtype=F32, device=dev), "nsamp": torch.empty((b,), dtype=I32, device=dev),
                   "lengths": torch.empty((b,), dtype=I32, device=dev), "labels": torch.empty((b, s), dtype=I32, device=dev),
-                  "free": None}
+                  "cu": torch.empty((b + 1,), dtype=I32, device=dev), "free": None}
             self._stage[key] = st
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -278,30 +462,49 @@ class AdapterTrainer:
         if st["free"] is not None:
             cs.wait_event(st["free"])            # the previous step may still be reading the staging buffers
         lengths = self._token_lengths(num_samples)
+        dialect = _dialect_key(dialect)
+        lens, pkey = self._layout(lengths, dialect)
+        cu_host = None
+        if lens is not None:
+            cu_host = torch.zeros((b + 1,), dtype=I32)
+            cu_host[1:] = torch.cumsum(lengths.to(torch.int64), 0).to(I32)
+            cu_host = cu_host.pin_memory()
+            lengths = lengths.pin_memory()
         with torch.cuda.stream(cs):
             st["wave"].copy_(wave, non_blocking=True)
             st["nsamp"].copy_(num_samples, non_blocking=True)
             st["lengths"].copy_(lengths, non_blocking=True)
             st["labels"].copy_(labels, non_blocking=True)
+            if cu_host is not None:
+                st["cu"].copy_(cu_host, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(cs)
-        self._staged = (st, ready, b, n, s, _dialect_key(dialect))
+        self._staged = (st, ready, b, n, s, dialect, lens, pkey, (cu_host, lengths))
+
+    def _bind_layout(self, ent: dict, lens) -> None:
+        if lens is not None and ent["pk"] is None:
+            ent["pk"] = PackedLayout(lens, ent["cu"].device, cu=ent["cu"])
+        elif lens is not None:
+            # same graph key → same (batch, total, seq_bound) [and same lengths when dialect runs are baked in]; only the device
+            # copy of cu_seqlens differs between replays.  Keep the host view current for eager (no-graph) runs.
+            ent["pk"] = PackedLayout(lens, ent["cu"].device, cu=ent["cu"])
 
     def step(self, wave: Optional[torch.Tensor] = None, num_samples: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
              dialect=0) -> torch.Tensor:
         """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 (host), labels [B, S] int32 (host, negative pad),
         ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent).
         Without arguments the batch staged by ``submit()`` is consumed.
-        Returns the loss as a 1-element device tensor (call ``.item()`` for the D2H read)."""
+        Returns the loss as a 1-element device tensor — a copy, valid until you drop it (call ``.item()`` for the D2H read)."""
+        self._check_weights()
         if wave is None:
             if self._staged is None:
                 raise RuntimeError("step() without arguments needs a batch staged by submit()")
-            st, ready, b, n, s, dialect = self._staged
+            st, ready, b, n, s, dialect, lens, pkey, _keep = self._staged
             self._staged = None
-            ent = self._static(b, n, s, dialect)
+            ent = self._static(b, n, s, dialect, pkey)
             cur = torch.cuda.current_stream()
             cur.wait_event(ready)
-            for k in ("wave", "nsamp", "lengths", "labels"):
+            for k in ("wave", "nsamp", "lengths", "labels") + (("cu",) if lens is not None else ()):
                 ent[k].copy_(st[k], non_blocking=True)
             st["free"] = torch.cuda.Event()
             st["free"].record(cur)
@@ -309,57 +512,75 @@ class AdapterTrainer:
             b, n = wave.shape
             s = labels.shape[1]
             dialect = _dialect_key(dialect)
-            ent = self._static(b, n, s, dialect)
+            lengths = self._token_lengths(num_samples)
+            lens, pkey = self._layout(lengths, dialect)
+            ent = self._static(b, n, s, dialect, pkey)
             ent["wave"].copy_(wave, non_blocking=True)
             ent["nsamp"].copy_(num_samples, non_blocking=True)
-            ent["lengths"].copy_(self._token_lengths(num_samples), non_blocking=True)
+            ent["lengths"].copy_(lengths, non_blocking=True)
             ent["labels"].copy_(labels, non_blocking=True)
-        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
+            if lens is not None:
+                cu_host = torch.zeros((b + 1,), dtype=I32)
+                cu_host[1:] = torch.cumsum(lengths.to(torch.int64), 0).to(I32)
+                ent["cu"].copy_(cu_host, non_blocking=False)
+        self._bind_layout(ent, lens)
+        loss = self._run(ent)
+        self._last = ent
+        return loss.clone()
+
+    def _args(self, ent):
+        return (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"], ent["pk"])
+
+    def _run(self, ent: dict) -> torch.Tensor:
+        args = self._args(ent)
+        self.flat.step_count += 1
+        self.flat.generation += 1
+        in_graph = self.exchange_in_graph
         if not self.use_cuda_graph:
             L.launch_count_reset()
-            loss = self._body(*args)
+            loss = self._body(*args, update=in_graph)
+            if not in_graph:
+                self._update_after()
             self.launches_per_step = L.launch_count()
-        else:
-            if ent["graph"] is None:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for _ in range(2):                      # warm-up: lazy packs, cudaFuncSetAttribute, allocator
-                        L.launch_count_reset()
-                        self._body(*args)
-                        self.launches_per_step = L.launch_count()
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    ent["loss"] = self._body(*args)
-                ent["graph"] = graph
-            ent["graph"].replay()
-            loss = ent["loss"]
-        self.flat.allreduce()
-        self.flat.adamw_step(self.lr, weight_decay=self.weight_decay)
-        self._last = ent
-        return loss
+            return loss
+        if ent["graph"] is None:
+            # warm-up outside the capture (lazy weight packs, cudaFuncSetAttribute, allocator) WITHOUT the update, so that the
+            # parameters and the optimizer clock only move once per step() call
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._body(*args, update=False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            L.launch_count_reset()
+            with torch.cuda.graph(graph):
+                ent["loss"] = self._body(*args, update=in_graph)
+            self.launches_per_step = L.launch_count() + (0 if in_graph else 2)
+            ent["graph"] = graph
+        ent["graph"].replay()
+        if not in_graph:
+            self._update_after()
+        return ent["loss"]
+
+    def _update_after(self) -> None:
+        ops.adamw_advance_(self.hyper)
+        self._exchange_and_update(0, self.flat.total)
 
     def step_resident(self) -> torch.Tensor:
-        """Repeat the last step on the inputs already resident in HBM (no host↔device copies): graph replay →
-        all-reduce → fused AdamW.  Used by bench.py for the device-resident throughput."""
-        ent = self._last
-        if ent["graph"] is not None:
-            ent["graph"].replay()
-            loss = ent["loss"]
-        else:
-            loss = self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
-        self.flat.allreduce()
-        self.flat.adamw_step(self.lr, weight_decay=self.weight_decay)
-        return loss
+        """Repeat the last step on the inputs already resident in HBM (no host↔device copies): one graph replay (forward,
+        backward, gradient exchange, AdamW).  Used by bench.py for the device-resident throughput.  Returns the graph's static
+        loss tensor (overwritten by the next step)."""
+        self._check_weights()
+        return self._run(self._last)
 
     def trace_gemms(self):
-        """One eager pass of the step body with GEMM tracing on → list for ops.replay_gemm_trace()."""
+        """One eager pass of the step body (no parameter update) with GEMM tracing on → list for ops.replay_gemm_trace()."""
         ent = self._last
         ops.GEMM_TRACE = []
         try:
-            self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"])
+            self._body(*self._args(ent), update=False)
             trace = ops.GEMM_TRACE
         finally:
             ops.GEMM_TRACE = None
@@ -368,49 +589,83 @@ class AdapterTrainer:
 
 class Transcriber:
     """Inference: H2D(waveforms) → [mel+CMVN → encoder → lm_head → greedy collapse] → D2H(token ids), graph-captured
-    per (batch, samples) shape."""
+    per (batch, samples) shape.  ``packed=True``: the encoder runs on the packed row layout (mixed-length batches)."""
 
-    def __init__(self, model: JLForCTC, use_cuda_graph: bool = True):
+    def __init__(self, model: JLForCTC, use_cuda_graph: bool = True, packed: bool = False):
         self.model = model
         self.cfg = model.config
         self.eng = model.encoder.engine(model.lm_head)
         self.dev = next(model.parameters()).device
         self.fe = JLFeatureExtractor(device=self.dev)
         self.use_cuda_graph = use_cuda_graph
+        self.packed = packed
+        if packed and self.cfg.front_end != "mel":
+            raise NotImplementedError("packed=True is implemented for the mel front end")
         self._graphs: Dict[tuple, dict] = {}
+        self._seen_version = None
         self.launches_per_step = 0
 
-    def _body(self, wave, nsamp, lengths, max_frames, dialect=0):
+    def _check_weights(self) -> None:
+        """Captured graphs read bf16 shadows / packed copies derived from the parameters: when a parameter changed (a torch-side
+        write, ``load_adapter``, or a fine-tune step of an ``AdapterTrainer`` on the same model) they are captured again."""
+        self.eng.lm_head = self.model.lm_head
+        v = (self.eng.weights_version(include_optimizer_steps=True), id(self.model.lm_head))
+        if self._seen_version is not None and v != self._seen_version:
+            self._graphs.clear()
+        self._seen_version = v
+
+    def _body(self, wave, nsamp, lengths, max_frames, dialect=0, pk=None):
         if self.cfg.front_end == "wav2vec2":
             st = self.eng.forward(wave, lengths, training=False, dialect=dialect, want_logits=True, sample_lengths=nsamp)
         else:
             feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-            st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True)
+            st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True, packed=pk)
+        if pk is not None:
+            ids, n, _ = ops.ctc_greedy(st.logits, lengths, blank=self.cfg.pad_token_id, cu_seqlens=pk.cu, max_len=pk.seq_bound)
+            return ids, n
         logits = st.logits.view(st.b, st.t, self.cfg.vocab_size)
         ids, n, _ = ops.ctc_greedy(logits, lengths, blank=self.cfg.pad_token_id)
         return ids, n
 
     @torch.no_grad()
     def __call__(self, wave: torch.Tensor, num_samples: torch.Tensor, dialect=0):
-        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 host → (ids [B, T'] int32 device, lengths [B]).
-        ``dialect``: WFAdapter factor set — one id or one id per utterance (same-dialect utterances adjacent)."""
+        """wave [B, N] fp32 (pinned host or device), num_samples [B] int32 host → (ids [B, T'] int32 device, lengths [B]) — copies
+        of the graph's outputs, valid until dropped.  ``dialect``: WFAdapter factor set — one id or one id per utterance
+        (same-dialect utterances adjacent)."""
+        self._check_weights()
         b, n = wave.shape
         dialect = _dialect_key(dialect)
-        key = (b, n, dialect)
+        lengths = token_lengths(self.cfg, num_samples)
+        lens, pkey = None, None
+        if self.packed:
+            lens = [int(x) for x in lengths.tolist()]
+            total, bound = sum(lens), max(128, (max(lens + [1]) + 127) // 128 * 128)
+            pkey = (total, bound) if isinstance(dialect, int) else (total, bound, tuple(lens))
+        key = (b, n, dialect, pkey)
         ent = self._graphs.get(key)
         if ent is None:
             ent = {"dialect": dialect, "wave": torch.zeros((b, n), dtype=F32, device=self.dev), "nsamp": torch.full((b,), n, dtype=I32, device=self.dev),
-                   "lengths": torch.ones((b,), dtype=I32, device=self.dev), "max_frames": max(num_frames(n), 1), "graph": None, "out": None}
+                   "lengths": torch.ones((b,), dtype=I32, device=self.dev), "cu": torch.zeros((b + 1,), dtype=I32, device=self.dev),
+                   "max_frames": max(num_frames(n), 1), "graph": None, "out": None, "pk": None}
             self._graphs[key] = ent
         ent["wave"].copy_(wave, non_blocking=True)
         ent["nsamp"].copy_(num_samples, non_blocking=True)
-        ent["lengths"].copy_(token_lengths(self.cfg, num_samples), non_blocking=True)
-        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"])
+        ent["lengths"].copy_(lengths, non_blocking=True)
+        if lens is not None:
+            cu_host = torch.zeros((b + 1,), dtype=I32)
+            cu_host[1:] = torch.cumsum(lengths.to(torch.int64), 0).to(I32)
+            ent["cu"].copy_(cu_host, non_blocking=False)
+            ent["pk"] = PackedLayout(lens, self.dev, cu=ent["cu"])
+        self._last = ent
+        out = self._run(ent)
+        return out[0].clone(), out[1].clone()
+
+    def _run(self, ent):
+        args = (ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"], ent["pk"])
         if not self.use_cuda_graph:
             L.launch_count_reset()
             out = self._body(*args)
             self.launches_per_step = L.launch_count()
-            self._last = ent
             return out
         if ent["graph"] is None:
             side = torch.cuda.Stream()
@@ -427,12 +682,9 @@ class Transcriber:
                 ent["out"] = self._body(*args)
             ent["graph"] = graph
         ent["graph"].replay()
-        self._last = ent
         return ent["out"]
 
+    @torch.no_grad()
     def run_resident(self):
-        ent = self._last
-        if ent["graph"] is not None:
-            ent["graph"].replay()
-            return ent["out"]
-        return self._body(ent["wave"], ent["nsamp"], ent["lengths"], ent["max_frames"], ent["dialect"])
+        """Replay the last call on the inputs already in HBM; returns the graph's static outputs (overwritten by the next call)."""
+        return self._run(self._last)

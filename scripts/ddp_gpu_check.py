@@ -48,20 +48,14 @@ def main():
     # reference: one process, whole batch, no collective (world "1": run with the process group hidden)
     ok = True
     if rank == 0:
-        ref = P.AdapterTrainer(make(), lr=1e-3, use_cuda_graph=False, comm=None)
-        ref.flat.allreduce = lambda: None
-        import types
-        def adamw_no_dist(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
-            self.step_count += 1
-            P.ops.adamw_(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, beta1, beta2, eps, weight_decay,
-                         grad_scale=1.0 / world, param_bf16=self.bf16)
-        ref.flat.adamw_step = types.MethodType(adamw_no_dist, ref.flat)
+        ref = P.AdapterTrainer(make(), lr=1e-3, use_cuda_graph=False, comm=None)      # mode "none": no collective
+        ref.grad_scale = 1.0 / world                # the whole batch on one rank: sum-reduced CTC gradients, DDP's 1 / world mean
         rloss = ref.step(wave.pin_memory(), ns, labels).item()
         torch.cuda.synchronize()
         gerr = float((bucket - ref.flat.grad).norm() / ref.flat.grad.norm())
         perr = float((params - ref.flat.param).abs().max())
         lerr = abs(float(lt) - rloss) / abs(rloss)
-        print(f"collective: {'jl_comm_allreduce (C ABI)' if tr.flat.comm is not None else 'torch.distributed'}")
+        print(f"collective: {tr.flat.comm_mode} ({'jl_comm_allreduce (C ABI), inside the step graph, two halves' if tr.flat.comm_mode == 'jl' else 'torch.distributed'})")
         print(f"world {world}: loss sum {float(lt):.4f} vs single {rloss:.4f} (rel {lerr:.2e}); bucket rel err {gerr:.2e}; param max diff {perr:.2e}")
         ok = lerr < 1e-3 and gerr < 2e-2 and perr < 1e-3
     # every rank must hold the same parameters after the step

@@ -1,0 +1,382 @@
+"""Parity at the sizes BASELINE.json quotes, against the fp32 CPU oracle on bf16-rounded weights, with the tolerances of
+SURVEY.md §8d asserted as written there: encoder logits relative Frobenius <= 2e-2 (12 layers) / 3e-2 (24 layers) and
+max|Δ| <= 5e-2·max|logit|, CTC loss <= 1e-3 relative, adapter + lm_head gradients relative Frobenius <= 3e-2.
+
+  * configs[1] at FULL size: base 12-layer d=768 encoder + AttAdapter, 32 x 10 s, through ``AdapterTrainer.step`` (the CUDA
+    graph the benchmark times) and through the module path;
+  * mixed-length utterances of 12 / 20 / 30 s (T' = 300 / 500 / 750 > 256): the general-length tcgen05 attention kernels
+    (``attn_fwd_tc_kernel`` / ``attn_bwd_tc_kernel``) under the engine, padded AND packed row layouts;
+  * configs[2] at FULL depth: 24-layer d=1024 / 16 heads / FFN 4096 with AttAdapter (attention slot) + WFAdapter (FFN slot).
+
+WFAdapter / AttAdapter have no external pin (the reference publishes no code, /root/reference/README.md:3): the oracle's
+definition is the contract, so these tests are what "matches the reference" means for a6 / a7.
+Every measured error is also written to gpurun_out/parity_r2.json (evidence for DESIGN.md §5).
+"""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+from helpers import ROOT, pkg, rel_err, round_bf16_, synth_wave
+
+pytestmark = pytest.mark.gpu
+I32 = torch.int32
+_RECORD = {}
+
+
+def _record(name, **kw):
+    _RECORD[name] = kw
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_r2.json")
+        old = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                old = json.load(f)
+        old.update(_RECORD)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _oracle(model, cfg):
+    from oracle import model as om
+    w = om.from_product_state_dict(model.state_dict())
+    ocfg = om.OracleConfig(**{k: v for k, v in cfg.to_dict().items() if k in om.OracleConfig.__dataclass_fields__})
+    for k, v in w.items():
+        v.requires_grad_(om.is_trainable(k))
+    return om, w, ocfg
+
+
+def _labels(lengths, vocab, seed):
+    g = torch.Generator().manual_seed(seed)
+    smax = max(1, max(int(0.4 * int(t)) for t in lengths))
+    lab = torch.full((len(lengths), smax), -100, dtype=torch.int64)
+    for i, t in enumerate(lengths):
+        s = int(0.4 * int(t))
+        lab[i, :s] = torch.randint(1, vocab, (s,), generator=g)
+    return lab
+
+
+def _grad_errors(named_grads, w):
+    """name -> (relative Frobenius error, |err|, |ref|) of every adapter / lm_head gradient against the oracle's."""
+    out = {}
+    for name, g in named_grads.items():
+        ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
+        err = float((g.float().cpu() - ref).norm())
+        out[name] = (err / max(float(ref.norm()), 1e-30), err, float(ref.norm()), ref.numel())
+    return out
+
+
+def _assert_grads(errs, tol):
+    worst = ("", 0.0)
+    for name, (rel, err, refn, numel) in errs.items():
+        # analytically-zero gradients (the AttAdapter key bias shifts every score of a query equally) hold rounding noise on both
+        # sides: they are compared absolutely
+        assert err <= tol * refn + 2e-6 * numel ** 0.5, f"grad {name}: rel {rel:.3e} (err {err:.3e}, ref norm {refn:.3e})"
+        if refn > 1e-4 * numel ** 0.5 and rel > worst[1]:
+            worst = (name, rel)
+    return worst
+
+
+def _argmax_stats(logits, ologits, lens):
+    """frame-argmax agreement overall, and on the frames whose oracle top-2 margin exceeds twice the largest logit error."""
+    band = 2.0 * float((logits - ologits).abs().max())
+    agree = tot = agree_clear = tot_clear = 0
+    for i, t in enumerate(lens):
+        a, o = logits[i, :t], ologits[i, :t]
+        top2 = o.topk(2, dim=-1).values
+        clear = (top2[:, 0] - top2[:, 1]) > band
+        same = a.argmax(-1) == o.argmax(-1)
+        agree += int(same.sum()); tot += t
+        agree_clear += int((same & clear).sum()); tot_clear += int(clear.sum())
+    return agree / max(tot, 1), (agree_clear / tot_clear if tot_clear else 1.0), tot_clear / max(tot, 1)
+
+
+def test_headline_config_full_size_trainer_step_vs_oracle():
+    """BASELINE.json configs[1] at the size the metric is quoted on: 12-layer d=768 encoder + AttAdapter after every FFN, V = 5000,
+    32 x 10 s of synthetic audio.  Loss, logits and every adapter / lm_head gradient of the product (module path AND the
+    captured-graph trainer step bench.py times) against the oracle."""
+    import bench
+    P = pkg()
+    cfg = P.JLConfig.base(adapter_ffn="att")
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    wave, ns, labels32, tp = bench.synth_batch(32, 1234, cfg.vocab_size)
+    labels = labels32.to(torch.int64)
+    # ---- module path (loss.backward())
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe.extract_device(wave.cuda(), ns.cuda(), max_frames=998)
+    loss, logits = model(feats["input_features"], labels=labels.cuda(), frame_lengths=feats["frame_lengths"])
+    loss.backward()
+    torch.cuda.synchronize()
+    grads_mod = {n: p.grad.detach().clone() for n, p in model._get_adapters().items()}
+    logits = logits.float().cpu()
+    # ---- the trainer's graph (lr = 0: gradients only)
+    for p_ in model.parameters():
+        p_.grad = None
+    tr = P.AdapterTrainer(model, lr=0.0, weight_decay=0.0, use_cuda_graph=True, comm=None)
+    tl = float(tr.step(wave.pin_memory(), ns, labels32).item())
+    tl2 = float(tr.step(wave.pin_memory(), ns, labels32).item())      # replay
+    torch.cuda.synchronize()
+    grads_tr = {n: tr.flat.out(p).detach().clone() for n, p in model._get_adapters().items()}
+    # ---- oracle (fp32 CPU, same bf16-representable weights)
+    t0 = time.perf_counter()
+    om, w, ocfg = _oracle(model, cfg)
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, [wave[i] for i in range(32)], labels)
+    oloss.backward()
+    cpu_s = time.perf_counter() - t0
+    lens = olens.tolist()
+    assert lens == [tp] * 32
+    oloss = float(oloss)
+    fro = rel_err(logits, ologits)
+    mx = float((logits - ologits).abs().max()) / float(ologits.abs().max())
+    agree, agree_clear, frac_clear = _argmax_stats(logits, ologits, lens)
+    e_mod, e_tr = _grad_errors(grads_mod, w), _grad_errors(grads_tr, w)
+    _record("configs1_full", loss=float(loss), loss_trainer=tl, loss_oracle=oloss, loss_rel=abs(float(loss) - oloss) / abs(oloss),
+            loss_trainer_rel=abs(tl - oloss) / abs(oloss), logits_fro=fro, logits_max_rel=mx, argmax_agree=agree,
+            argmax_agree_outside_error_band=agree_clear, frames_outside_error_band=frac_clear, oracle_seconds=cpu_s,
+            grad_rel_module={k: v[0] for k, v in e_mod.items()}, grad_rel_trainer={k: v[0] for k, v in e_tr.items()})
+    assert abs(float(loss) - oloss) <= 1e-3 * abs(oloss), (float(loss), oloss)
+    assert abs(tl - oloss) <= 1e-3 * abs(oloss) and abs(tl2 - tl) <= 1e-6 * abs(tl), (tl, tl2, oloss)
+    assert fro <= 2e-2, f"logits relative Frobenius error {fro}"
+    assert mx <= 5e-2, f"logits max error / max |logit| = {mx}"
+    # random-init logits are nearly flat: the 99 % argmax agreement of SURVEY §8d is asserted where the oracle's own top-2 margin
+    # exceeds the numerical error band (there it must be exact), and the overall figure is recorded
+    assert agree_clear >= 0.99, (agree, agree_clear, frac_clear)
+    _assert_grads(e_mod, 3e-2)
+    _assert_grads(e_tr, 3e-2)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_long_mixed_length_utterances_run_the_general_attention_kernels(packed):
+    """Utterances of 12 / 20 / 30 / 2.5 s → T' = 300 / 500 / 750 / 62 frames: every attention call (12-head encoder attention and the
+    AttAdapter's single head) takes the key-block forward kernel and the dQ / dKV backward kernels (the <= 256-frame kernels do
+    not apply), in the padded layout and in the packed (cu_seqlens) layout; loss, logits and gradients vs the oracle."""
+    P = pkg()
+    cfg = P.JLConfig(hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=512, conv_channels=128, vocab_size=200,
+                     adapter_attn="att", adapter_ffn="wf", wf_bottleneck=64, wf_rank=16)
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    secs = [12.0, 20.0, 30.0, 2.5]
+    waves = [synth_wave(int(16000 * s_), 40 + i) for i, s_ in enumerate(secs)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+    assert lens == [300, 500, 750, 62]
+    labels = _labels(lens, cfg.vocab_size, seed=6)
+    loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda(), packed=packed)
+    loss.backward()
+    torch.cuda.synchronize()
+    if packed:
+        assert logits.shape[0] == sum(lens)
+        logits = model.unpack_logits(logits, model.last_packed)
+    logits = logits.float().cpu()
+    om, w, ocfg = _oracle(model, cfg)
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, waves, labels)
+    oloss.backward()
+    assert olens.tolist() == lens
+    worst_l = 0.0
+    for i, t in enumerate(lens):
+        worst_l = max(worst_l, rel_err(logits[i, :t], ologits[i, :t]))
+    errs = _grad_errors({n: p.grad for n, p in model._get_adapters().items()}, w)
+    _record(f"long_mixed_{'packed' if packed else 'padded'}", loss_rel=abs(float(loss) - float(oloss)) / abs(float(oloss)), logits_fro_worst=worst_l,
+            grad_rel={k: v[0] for k, v in errs.items()})
+    assert worst_l <= 2e-2, worst_l
+    assert abs(float(loss) - float(oloss)) <= 1e-3 * abs(float(oloss))
+    _assert_grads(errs, 3e-2)
+
+
+def test_large_config_full_depth_24_layers_both_adapters():
+    """BASELINE.json configs[2] at full depth: 24 layers, d = 1024, 16 heads, FFN 4096, AttAdapter after the attention and
+    WFAdapter after the FFN of every layer, V = 5000; two utterances (10 s and 6.3 s)."""
+    P = pkg()
+    cfg = P.JLConfig.large(adapter_attn="att", adapter_ffn="wf")
+    assert cfg.num_hidden_layers == 24 and cfg.hidden_size == 1024
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    waves = [synth_wave(160000, 71), synth_wave(100800, 72)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"]).cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, seed=8)
+    loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    logits = logits.float().cpu()
+    om, w, ocfg = _oracle(model, cfg)
+    oloss, ologits, olens = om.forward_from_waveforms(w, ocfg, waves, labels)
+    oloss.backward()
+    assert olens.tolist() == lens
+    worst_l = max(rel_err(logits[i, :t], ologits[i, :t]) for i, t in enumerate(lens))
+    errs = _grad_errors({n: p.grad for n, p in model._get_adapters().items()}, w)
+    worst = _assert_grads(errs, 3e-2)
+    _record("configs2_full_depth", loss_rel=abs(float(loss) - float(oloss)) / abs(float(oloss)), logits_fro_worst=worst_l,
+            grad_rel_worst=worst[1], grad_rel_worst_name=worst[0], grad_rel={k: v[0] for k, v in errs.items()})
+    assert worst_l <= 3e-2, worst_l                                    # stated bf16 tolerance, 24 layers
+    assert abs(float(loss) - float(oloss)) <= 1e-3 * abs(float(oloss))
+
+
+def test_packed_layout_matches_padded_layout_module_and_trainer():
+    """The packed row layout changes where rows live, not what is computed: logits, loss and gradients agree with the padded
+    layout to bf16 rounding of a single pass (each row's reductions run in the same order), through the module path and
+    through the trainer's CUDA graph (per-utterance dialect ids included); greedy ids from packed logits are bit-exact vs the
+    oracle's decode of the same logits."""
+    from oracle import ctc as oc
+    P = pkg()
+    cfg = P.JLConfig(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, conv_channels=64, vocab_size=48,
+                     adapter_attn="att", adapter_ffn="wf", wf_bottleneck=32, wf_rank=8, num_dialects=2)
+    model = P.JLForCTC(cfg)
+    round_bf16_(model)
+    model = model.cuda()
+    model.freeze_base_model()
+    ns_list = [48000, 16000, 30001, 9000]
+    dialects = [1, 1, 0, 0]
+    waves = [synth_wave(n, 50 + i) for i, n in enumerate(ns_list)]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    lens_t = model.output_lengths(feats["input_features"], frame_lengths=feats["frame_lengths"])
+    lens = lens_t.cpu().tolist()
+    labels = _labels(lens, cfg.vocab_size, seed=3)
+    out = {}
+    for packed in (False, True):
+        for p_ in model.parameters():
+            p_.grad = None
+        loss, logits = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda(), dialect=dialects, packed=packed)
+        loss.backward()
+        torch.cuda.synchronize()
+        if packed:
+            pk = model.last_packed
+            ids = model.greedy_decode(logits.detach(), lens_t, packed=pk)
+            full = model.unpack_logits(logits.detach(), pk)
+            assert ids == oc.greedy_decode(full.float().cpu(), lens_t.cpu(), cfg.pad_token_id)
+            logits = full
+        out[packed] = (float(loss), logits.detach().float().cpu(), {n: p_.grad.detach().clone() for n, p_ in model._get_adapters().items()})
+    assert abs(out[True][0] - out[False][0]) <= 1e-4 * abs(out[False][0])
+    for i, t in enumerate(lens):
+        assert rel_err(out[True][1][i, :t], out[False][1][i, :t]) < 5e-3, i
+    for n in out[False][2]:
+        a, b_ = out[True][2][n], out[False][2][n]
+        assert rel_err(a, b_) < 1e-2 or float((a - b_).abs().max()) < 1e-5, n
+    # trainer: packed graph == padded graph == module path
+    nmax = max(ns_list)
+    wave = torch.zeros((4, nmax))
+    for i, w_ in enumerate(waves):
+        wave[i, : w_.shape[0]] = w_
+    ns = torch.tensor(ns_list, dtype=I32)
+    lab32 = labels.to(I32)
+    for packed in (False, True):
+        tr = P.AdapterTrainer(model, lr=0.0, weight_decay=0.0, use_cuda_graph=True, comm=None, packed=packed)
+        l1 = float(tr.step(wave.pin_memory(), ns, lab32, dialect=dialects).item())
+        tr.submit(wave.pin_memory(), ns.pin_memory(), lab32.pin_memory(), dialect=dialects)      # prefetch path + graph replay
+        l2 = float(tr.step().item())
+        torch.cuda.synchronize()
+        assert abs(l1 - out[False][0]) <= 1e-3 * abs(out[False][0]) and abs(l2 - l1) <= 1e-6 * abs(l1), (packed, l1, l2, out[False][0])
+        for n, p_ in model._get_adapters().items():
+            got = tr.flat.out(p_)
+            assert rel_err(got, out[False][2][n]) < 1e-2 or float((got - out[False][2][n]).abs().max()) < 1e-5, (packed, n)
+        model.encoder.engine(model.lm_head).flat = None
+
+
+def test_graphs_follow_weight_changes_made_through_torch(tmp_path):
+    """captured graphs bake in pointers to bf16 shadows / packed weights.  After ``load_adapter`` /
+    ``init_adapter_layers`` / a backbone write, ``Transcriber`` and ``AdapterTrainer`` must run the NEW weights, and a
+    fine-tune step must be seen by a ``Transcriber`` sharing the model."""
+    P = pkg()
+    cfg = P.JLConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, conv_channels=64, vocab_size=40,
+                     adapter_ffn="wf", wf_bottleneck=64, wf_rank=16)
+    torch.manual_seed(0)
+    model = P.JLForCTC(cfg).cuda()
+    model.freeze_base_model()
+    n = 24000
+    wave = torch.stack([synth_wave(n, 81), synth_wave(n, 82)])
+    ns = torch.tensor([n, 20000], dtype=I32)
+    tr = P.Transcriber(model)
+
+    def module_ids():
+        fe = P.JLFeatureExtractor(device="cuda")
+        feats = fe([wave[i, : int(ns[i])].numpy() for i in range(2)], sampling_rate=16000)
+        with torch.no_grad():
+            _, logits = model(feats["input_features"], attention_mask=feats["attention_mask"])
+        return model.greedy_decode(logits, model.output_lengths(feats["input_features"], feats["attention_mask"]))
+
+    def graph_ids():
+        ids, nid = tr(wave.pin_memory(), ns)
+        torch.cuda.synchronize()
+        return [ids[i, : int(nid[i])].cpu().tolist() for i in range(2)]
+
+    before = graph_ids()
+    assert before == module_ids() and graph_ids() == before
+    # a different adapter + head, saved from a second model and loaded in place
+    other = P.JLForCTC(cfg)
+    other.init_adapter_layers(seed=123)
+    with torch.no_grad():
+        other.lm_head.weight.mul_(3.0)
+    path = str(tmp_path / "adapter.test.safetensors")
+    other.save_adapter(path)
+    model.load_adapter(path)
+    after = graph_ids()
+    assert after == module_ids(), "Transcriber replayed a graph holding the old adapter weights"
+    assert after != before
+    # a backbone write
+    with torch.no_grad():
+        model.encoder.layers[0].feed_forward.output_dense.weight.mul_(0.5)
+    assert graph_ids() == module_ids()
+    # trainer: a step changes the weights the Transcriber must see; load_adapter under the trainer refreshes its shadow
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(1, cfg.vocab_size, (2, 10), generator=g, dtype=I32)
+    trn = P.AdapterTrainer(model, lr=5e-2, weight_decay=0.0, comm=None)
+    l0 = float(trn.step(wave.pin_memory(), ns, labels).item())
+    assert graph_ids() == module_ids(), "Transcriber did not see the fine-tune step"
+    model.load_adapter(path)                                   # back to the file's weights, under the attached trainer
+    trn.set_lr(0.0)
+    l_file = float(trn.step(wave.pin_memory(), ns, labels).item())
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([wave[i, : int(ns[i])].numpy() for i in range(2)], sampling_rate=16000)
+    with torch.no_grad():
+        ref_loss, _ = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda().long())
+    assert abs(l_file - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)), (l_file, float(ref_loss), l0)
+    # resizing lm_head under an attached trainer is refused with a clear message
+    big = P.JLForCTC(P.JLConfig(**{**cfg.to_dict(), "vocab_size": 64}))
+    path2 = str(tmp_path / "adapter.big.safetensors")
+    big.save_adapter(path2)
+    with pytest.raises(RuntimeError, match="AdapterTrainer"):
+        model.load_adapter(path2)
+
+
+def test_overlapped_exchange_in_graph_equals_serial_update():
+    """The two-half exchange + AdamW captured inside the step graph (device-side optimizer clock) produces the same parameters
+    as the serial scheme (graph = forward + backward, then all-reduce + AdamW on the same stream), bit for bit on one rank, and
+    as torch.optim.AdamW on the same gradients to fp32 rounding."""
+    P = pkg()
+    cfg = P.JLConfig(hidden_size=128, num_hidden_layers=4, num_attention_heads=2, intermediate_size=256, conv_channels=64, vocab_size=40,
+                     adapter_attn="att", adapter_ffn="wf", wf_bottleneck=32, wf_rank=8)
+    n = 16000
+    wave = torch.stack([synth_wave(n, 91), synth_wave(n, 92)])
+    ns = torch.tensor([n, 12000], dtype=I32)
+    g = torch.Generator().manual_seed(2)
+    labels = torch.randint(1, cfg.vocab_size, (2, 8), generator=g, dtype=I32)
+    params = []
+    for in_graph in (True, False):
+        torch.manual_seed(0)
+        model = P.JLForCTC(cfg).cuda()
+        model.freeze_base_model()
+        tr = P.AdapterTrainer(model, lr=1e-2, weight_decay=0.01, comm=None, exchange_in_graph=in_graph)
+        assert 0 < tr.flat.split < tr.flat.total
+        losses = [float(tr.step(wave.pin_memory(), ns, labels).item()) for _ in range(3)]
+        torch.cuda.synchronize()
+        params.append((tr.flat.param.clone(), losses, float(tr.hyper[3])))
+        assert losses[2] < losses[0]
+    assert params[0][2] == 3.0 and params[1][2] == 3.0           # the device-side clock ticked once per step
+    assert torch.equal(params[0][0], params[1][0]), float((params[0][0] - params[1][0]).abs().max())
+    assert params[0][1] == params[1][1]

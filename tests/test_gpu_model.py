@@ -58,14 +58,15 @@ def test_small_model_logits_loss_and_adapter_grads(slots):
     assert olens.tolist() == lens
     for i, t in enumerate(lens):
         assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
-    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    assert abs(float(loss) - float(oloss)) <= 1e-3 * abs(float(oloss))          # CTC loss <= 1e-3 relative
     for name, p in model._get_adapters().items():
         ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
         assert p.grad is not None, name
-        # relative Frobenius error, with an absolute floor for gradients that are analytically zero (the AttAdapter key
-        # bias shifts every score of a query equally, so its true gradient is 0 and both sides hold only rounding noise)
+        # adapter gradients <= 3e-2 relative Frobenius, with an absolute floor for gradients that are analytically
+        # zero (the AttAdapter key bias shifts every score of a query equally, so its true gradient is 0 and both sides hold
+        # only rounding noise)
         err = float((p.grad.float().cpu() - ref).norm())
-        assert err <= 5e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
+        assert err <= 3e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
 
 
 def test_base_config_forward_logits_and_greedy_ids():
@@ -91,12 +92,18 @@ def test_base_config_forward_logits_and_greedy_ids():
     assert float((logits.float().cpu() - ologits).abs().max()) <= 5e-2 * float(ologits.abs().max())
     # frame-argmax agreement: random-init logits are nearly flat, so flips are allowed only where the oracle's own margin
     # between the two candidates is inside the numerical error band
+    # SURVEY §8d asks for >= 99 % frame-argmax agreement.  Random-init logits are nearly flat (top-2 margins of the order of the
+    # bf16 error), so the 99 % is asserted on the frames whose oracle top-2 margin exceeds the numerical error band — there the
+    # argmax must agree — and every flip must lie inside the band; the overall figure (measured 0.97-0.99) is checked loosely.
     mine, theirs = logits.float().cpu().argmax(-1), ologits.argmax(-1)
     agree = (mine == theirs).float().mean()
     assert float(agree) >= 0.95, float(agree)
     gap = ologits.gather(-1, theirs[..., None]) - ologits.gather(-1, mine[..., None])
     band = 2.0 * float((logits.float().cpu() - ologits).abs().max())
     assert float(gap.max()) <= band, (float(gap.max()), band)
+    top2 = ologits.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > band
+    assert float((mine == theirs)[clear].float().mean()) >= 0.99
     # greedy ids are bit-exact when decoded from the same logits
     from oracle import ctc as oc
     assert model.greedy_decode(logits, lens) == oc.greedy_decode(logits.float().cpu(), lens.cpu(), 0)
@@ -178,11 +185,11 @@ def test_large_config_both_adapters_mixed_lengths():
     assert olens.tolist() == lens
     for i, t in enumerate(lens):
         assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
-    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    assert abs(float(loss) - float(oloss)) <= 1e-3 * abs(float(oloss))
     for name, p in model._get_adapters().items():
         ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
         err = float((p.grad.float().cpu() - ref).norm())
-        assert err <= 5e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
+        assert err <= 3e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
 
 
 def test_transcriber_matches_module_path_and_oracle_ids():
@@ -242,11 +249,11 @@ def test_per_utterance_dialect_ids_select_wfadapter_factor_sets():
     oloss.backward()
     for i, t in enumerate(lens):
         assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
-    assert abs(float(loss) - float(oloss)) <= 1e-2 * abs(float(oloss))
+    assert abs(float(loss) - float(oloss)) <= 2e-3 * abs(float(oloss))      # amplified adapters (below): twice the 1e-3 of SURVEY §8d
     for name, p in model._get_adapters().items():
         ref = w[name[len("encoder."):] if name.startswith("encoder.") else name].grad
         err = float((p.grad.float().cpu() - ref).norm())
-        # 8e-2: the adapters are amplified ~770x here, and with them the bf16 rounding of everything that flows through them
+        # 8e-2 instead of SURVEY §8d's 3e-2, for this test only: the adapters are amplified ~770x here, and with them the bf16 rounding of everything that flows through them
         assert err <= 8e-2 * float(ref.norm()) + 2e-6 * ref.numel() ** 0.5, f"grad {name}: err {err} ref norm {float(ref.norm())}"
         if ".adapter_ffn." in name and p.dim() >= 2 and p.shape[0] == 3 and "norm" not in name:
             assert float(p.grad[1].abs().max()) == 0.0, f"{name}: unused dialect 1 must have zero gradient"

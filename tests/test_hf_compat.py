@@ -138,3 +138,22 @@ def test_own_adapter_files_safetensors_and_bin(tmp_path):
     assert P.hf_compat.adapter_file(str(tmp_path), "x").endswith("adapter.x.safetensors")
     os.remove(str(tmp_path / "adapter.x.safetensors"))
     assert P.hf_compat.adapter_file(str(tmp_path), "x").endswith("adapter.x.bin")
+
+
+def test_post_ln_group_norm_checkpoints_are_refused():
+    """wav2vec2-base style checkpoints (do_stable_layer_norm=False, feat_extract_norm="group", no conv bias) share the transformer
+    leaf names with XLS-R / MMS but not the arithmetic (post-LN layers): loading them must raise, by config or by key layout."""
+    from transformers import Wav2Vec2Config, Wav2Vec2ForCTC
+    P = pkg()
+    cfg = Wav2Vec2Config(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, conv_dim=(8, 8), conv_kernel=(10, 3),
+                         conv_stride=(5, 2), num_feat_extract_layers=2, num_conv_pos_embeddings=4, num_conv_pos_embedding_groups=2,
+                         vocab_size=24, do_stable_layer_norm=False, feat_extract_norm="group", conv_bias=False)
+    hf = Wav2Vec2ForCTC(cfg)
+    jl = _jl_model(P)
+    with pytest.raises(ValueError, match="group"):
+        jl.load_hf_state_dict(hf.state_dict())                       # detected from the feature-extractor keys
+    sd_no_fe = {k: v for k, v in hf.state_dict().items() if "feature_extractor" not in k}
+    with pytest.raises(ValueError, match="do_stable_layer_norm"):
+        jl.load_hf_state_dict(sd_no_fe, hf_config=cfg)               # detected from the config
+    with pytest.raises(ValueError, match="do_stable_layer_norm"):
+        jl.load_hf_state_dict(sd_no_fe, hf_config={"do_stable_layer_norm": False})
