@@ -90,7 +90,11 @@ enum {
   JL_EPI_GLU = 5,       /* C[:, j] = v[2j] * sigmoid(v[2j+1]); C has N/2 columns (interleaved weight rows) */
   JL_EPI_GELU_DGELU = 6,/* erf GELU to C and its derivative gelu'(pre-activation) to aux_out (bf16, required): the training
                          * forward of the FFN input projection — erf is evaluated once per element, not again in backward */
-  JL_EPI_MUL_AUX = 7    /* C = acc * aux                   (aux = saved activation derivative, bf16) */
+  JL_EPI_MUL_AUX = 7,   /* C = acc * aux                   (aux = saved activation derivative, bf16) */
+  JL_EPI_ARGMAX = 8     /* SURVEY §8 f1 (inference): the output matrix is never written.  Per row and per chunk of 32 output columns
+                         * the epilogue emits (max, first argmax) of alpha*acc + bias:  c = float [ceil(N/32), ldc] maxima,
+                         * aux_out = int32 [ceil(N/32), ldaux_out] column indices (chunk-major, ld >= M; out_dtype ignored).
+                         * lm_head + greedy CTC decode without a [B*T', V] logits tensor: jl_ctc_greedy_from_partials finishes it. */
 };
 enum {
   JL_LAYOUT_K = 0,      /* operand stored with K contiguous:  A[M, K] / B[N, K]  (nn.Linear layout) */
@@ -259,6 +263,12 @@ typedef struct {
   const int32_t* cu_seqlens; /* optional [B + 1]: packed logits rows (see jl_ctc_params); frame_ids / out_ids stay [B, seq] */
 } jl_ctc_greedy_params;
 int jl_ctc_greedy(const jl_ctc_greedy_params* p, void* stream);
+/* f1: greedy decode from the per-chunk (max, argmax) pairs a JL_EPI_ARGMAX lm_head GEMM produced instead of logits.
+ * pmax / pidx: [num_chunks, ld] (row = frame row of the hidden-state matrix: b*seq + t, or cu_seqlens[b] + t when packed).
+ * Ties go to the lowest column index, as torch.argmax.  Outputs as jl_ctc_greedy ([B, seq] frame_ids / out_ids, [B] out_lengths). */
+int jl_ctc_greedy_from_partials(const float* pmax, const int32_t* pidx, int64_t ld, int32_t num_chunks, const int32_t* input_lengths,
+                                const int32_t* cu_seqlens, int32_t batch, int32_t seq, int32_t blank, int32_t* frame_ids,
+                                int32_t* out_ids, int32_t* out_lengths, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-movement / elementwise helpers on the path.

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libjl_b200.so")
 
 JL_OK, JL_EINVAL, JL_EUNSUPPORTED_SHAPE, JL_ECUDA, JL_EUNSUPPORTED = 0, -1, -2, -3, -4
 JL_DT_BF16, JL_DT_F32 = 0, 1
-JL_EPI_NONE, JL_EPI_GELU, JL_EPI_RELU, JL_EPI_GELU_BWD, JL_EPI_RELU_BWD, JL_EPI_GLU, JL_EPI_GELU_DGELU, JL_EPI_MUL_AUX = range(8)
+JL_EPI_NONE, JL_EPI_GELU, JL_EPI_RELU, JL_EPI_GELU_BWD, JL_EPI_RELU_BWD, JL_EPI_GLU, JL_EPI_GELU_DGELU, JL_EPI_MUL_AUX, JL_EPI_ARGMAX = range(9)
 JL_LAYOUT_K, JL_LAYOUT_MN = 0, 1
 JL_CTC_SUM, JL_CTC_MEAN = 0, 1
 JL_MEL_BINS, JL_MEL_MAXW, JL_MEL_FRAMES_PER_CTA = 80, 32, 32
@@ -111,6 +111,7 @@ SYMBOLS = {
     "jl_ctc_workspace_bytes": (C.c_int, [C.POINTER(CtcParams), C.POINTER(C.c_size_t)]),
     "jl_ctc_fwd": (C.c_int, [C.POINTER(CtcParams), vp, vp]),
     "jl_ctc_greedy": (C.c_int, [C.POINTER(CtcGreedyParams), vp]),
+    "jl_ctc_greedy_from_partials": (C.c_int, [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "jl_im2col_k5s2": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "jl_embed_positions": (C.c_int, [vp, f32, vp, vp, i32, i32, i32, vp]),
     "jl_embed_positions_packed": (C.c_int, [vp, vp, f32, vp, vp, i32, i32, i32, vp]),

@@ -569,6 +569,34 @@ __global__ void ctc_collapse_kernel(const int32_t* __restrict__ frame_ids, const
   if (lane == 0) out_lengths[b] = base;
 }
 
+// f1: frame argmax from the per-chunk (max, argmax) pairs of a JL_EPI_ARGMAX lm_head GEMM.  Thread = frame (b, t); the chunk-major
+// layout makes every load of a warp coalesced.  Chunks are visited in column order and only a strictly larger maximum replaces
+// the current one, so ties go to the lowest column, as torch.argmax.
+__global__ void __launch_bounds__(256) ctc_argmax_reduce_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx, int64_t ld,
+                                                                int num_chunks, const int32_t* __restrict__ lengths,
+                                                                const int32_t* __restrict__ cu, int batch, int seq,
+                                                                int32_t* __restrict__ frame_ids) {
+  jl::pdl_prologue();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * seq) return;
+  const int b = idx / seq, t = idx - b * seq;
+  if (t >= lengths[b]) {
+    frame_ids[idx] = -1;
+    return;
+  }
+  const int64_t row = (cu != nullptr) ? static_cast<int64_t>(cu[b]) + t : static_cast<int64_t>(idx);
+  float best = -CUDART_INF_F;
+  int besti = 0x7fffffff;
+  for (int c = 0; c < num_chunks; ++c) {
+    const float v = __ldg(pmax + c * ld + row);
+    if (v > best) {
+      best = v;
+      besti = __ldg(pidx + c * ld + row);
+    }
+  }
+  frame_ids[idx] = besti;
+}
+
 static int ctc_validate_common(const void* logits, const int32_t* lengths, int batch, int seq, int vocab, int blank, int dtype) {
   JL_REQUIRE(logits && lengths, JL_EINVAL, "ctc: null logits / input_lengths");
   JL_REQUIRE(batch > 0 && seq > 0 && vocab > 1, JL_EINVAL, "ctc: batch, seq must be positive and vocab > 1");
@@ -650,6 +678,22 @@ int jl_ctc_fwd(const jl_ctc_params* p, void* workspace, void* stream) {
   }
   jl::launch(jl::ctc_reduce_kernel, 1, 32, 0, s, p->nll, w.tlen, p->batch, p->reduction, p->zero_infinity, p->loss);
   JL_CHECK_LAUNCH("ctc_reduce");
+  return JL_OK;
+}
+
+int jl_ctc_greedy_from_partials(const float* pmax, const int32_t* pidx, int64_t ld, int32_t num_chunks, const int32_t* input_lengths,
+                                const int32_t* cu_seqlens, int32_t batch, int32_t seq, int32_t blank, int32_t* frame_ids,
+                                int32_t* out_ids, int32_t* out_lengths, void* stream) {
+  JL_REQUIRE(pmax && pidx && input_lengths && frame_ids && out_ids && out_lengths, JL_EINVAL, "ctc_greedy_from_partials: null pointer");
+  JL_REQUIRE(batch > 0 && seq > 0 && num_chunks > 0 && ld > 0 && blank >= 0, JL_EINVAL, "ctc_greedy_from_partials: bad dims");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  jl::launch(jl::ctc_argmax_reduce_kernel, jl::ceil_div(batch * seq, 256), 256, 0, s, pmax, pidx, ld, num_chunks, input_lengths, cu_seqlens, batch,
+             seq, frame_ids);
+  JL_CHECK_LAUNCH("ctc_argmax_reduce");
+  jl::launch(jl::ctc_collapse_kernel, batch, 32, 0, s, frame_ids, input_lengths, seq, blank, out_ids, out_lengths);
+  JL_CHECK_LAUNCH("ctc_collapse");
   return JL_OK;
 }
 

@@ -17,6 +17,7 @@
 //   warps 4-15  epilogue: tcgen05.ld 32 lanes × 32 columns → registers → bias / GELU / ReLU / GLU / residual /
 //               activation-gradient / row masking → 16-byte global stores
 #include <cuda.h>
+#include <math_constants.h>
 
 #include <atomic>
 #include <mutex>
@@ -229,6 +230,20 @@ __device__ __forceinline__ void gemm_epilogue_row32(const GemmDev& g, int row, i
     const int b = row / g.rows_per_seq;
     const int t = row - b * g.rows_per_seq;
     zero_row = (t >= __ldg(g.row_lengths + b));
+  }
+
+  if (g.epilogue == JL_EPI_ARGMAX) {
+    // f1 (inference head): no output matrix — (max, first argmax) of this row over the chunk's columns, chunk-major so that the
+    // 32 rows of a warp store 128 contiguous bytes
+    float best = -CUDART_INF_F;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid && acc[j] > best) { best = acc[j]; besti = col0 + j; }      // strict >: the first maximum wins
+    const int64_t chunk = col0 >> 5;
+    reinterpret_cast<float*>(g.c)[chunk * g.ldc + row] = best;
+    reinterpret_cast<int32_t*>(g.aux_out)[chunk * g.ldaux_out + row] = besti;
+    return;
   }
 
   if (g.epilogue == JL_EPI_GLU) {
@@ -872,7 +887,11 @@ static int validate(const jl_gemm_params* p) {
   // K-major A may have lda < K: rows that overlap in memory (sliding windows over a [T, C] activation — a Conv1d without im2col)
   JL_REQUIRE(p->lda >= (p->a_layout == JL_LAYOUT_K ? 8 : p->m), JL_EINVAL, "gemm: lda too small");
   JL_REQUIRE(p->ldb >= (p->b_layout == JL_LAYOUT_K ? p->k : p->n), JL_EINVAL, "gemm: ldb too small");
-  JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_MUL_AUX, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
+  JL_REQUIRE(p->epilogue >= JL_EPI_NONE && p->epilogue <= JL_EPI_ARGMAX, JL_EINVAL, "gemm: unknown epilogue %d", p->epilogue);
+  if (p->epilogue == JL_EPI_ARGMAX) {
+    JL_REQUIRE(p->aux_out != nullptr && p->ldc >= p->m && p->ldaux_out >= p->m, JL_EINVAL, "gemm: JL_EPI_ARGMAX needs aux_out and ldc, ldaux_out >= M");
+    JL_REQUIRE(p->residual == nullptr && p->row_lengths == nullptr, JL_EINVAL, "gemm: JL_EPI_ARGMAX takes no residual / row_lengths");
+  }
   JL_REQUIRE(p->out_dtype == JL_DT_BF16 || p->out_dtype == JL_DT_F32, JL_EINVAL, "gemm: unknown out_dtype %d", p->out_dtype);
   JL_REQUIRE((reinterpret_cast<uintptr_t>(p->c) & 15) == 0, JL_EINVAL, "gemm: C must be 16-byte aligned");
   if (p->epilogue == JL_EPI_GLU) JL_REQUIRE((p->n & 1) == 0, JL_EINVAL, "gemm: GLU needs an even N");

@@ -750,11 +750,16 @@ class JLEngine:
         ln = self.enc.layer_norm
         st.h_final, st.mean_f, st.rstd_f = ops.layernorm_fwd(h, ln.weight.detach(), ln.bias.detach(), ln.eps, save_stats=training)
         st.logits = None
+        st.argmax_partials = None
         if want_logits:
             if self.lm_head is None:
                 raise RuntimeError("JLEngine.forward: no lm_head attached")
-            out_dtype = F32 if cfg.logits_dtype == "float32" else BF16
-            st.logits = ops.gemm(st.h_final, self._bf16(self.lm_head.weight), bias=self.lm_head.bias.detach(), out_dtype=out_dtype)
+            if want_logits == "argmax":
+                # lm_head ⊕ frame argmax — the [B·T', V] logits (5 MB fp32 per 10 s utterance) are never written
+                st.argmax_partials = ops.lm_head_argmax(st.h_final, self._bf16(self.lm_head.weight), self.lm_head.bias.detach())
+            else:
+                out_dtype = F32 if cfg.logits_dtype == "float32" else BF16
+                st.logits = ops.gemm(st.h_final, self._bf16(self.lm_head.weight), bias=self.lm_head.bias.detach(), out_dtype=out_dtype)
         return st
 
     # ------------------------------------------------------------------ backward (adapter-only)
@@ -1061,6 +1066,17 @@ class JLForCTC(nn.Module):
         return [ids[i, : int(n[i])].tolist() for i in range(ids.shape[0])]
 
     @torch.no_grad()
-    def transcribe(self, input_features, attention_mask=None, frame_lengths=None) -> List[List[int]]:
-        _, logits = self.forward(input_features, attention_mask, None, frame_lengths)
-        return self.greedy_decode(logits, self.output_lengths(input_features, attention_mask, frame_lengths))
+    def transcribe(self, input_features, attention_mask=None, frame_lengths=None, dialect=0, fused_head: bool = True) -> List[List[int]]:
+        """Features → token ids.  ``fused_head`` (default): the lm_head GEMM's epilogue emits per-chunk (max, argmax) pairs instead
+        of logits and the greedy decoder reads those; the ids are identical to decoding the materialised logits."""
+        if not fused_head:
+            _, logits = self.forward(input_features, attention_mask, None, frame_lengths, dialect=dialect)
+            return self.greedy_decode(logits, self.output_lengths(input_features, attention_mask, frame_lengths))
+        eng = self.encoder.engine(self.lm_head)
+        lengths = eng.output_lengths(input_features, attention_mask, frame_lengths)
+        st = eng.forward(input_features, lengths, training=False, dialect=dialect, want_logits="argmax",
+                         sample_lengths=_sample_lengths(attention_mask, frame_lengths))
+        pmax, pidx = st.argmax_partials
+        ids, n, _ = ops.ctc_greedy_from_partials(pmax, pidx, lengths, st.b, st.t, blank=self.config.pad_token_id)
+        ids, n = ids.cpu(), n.cpu()
+        return [ids[i, : int(n[i])].tolist() for i in range(ids.shape[0])]

@@ -142,6 +142,53 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
+def lm_head_argmax(h: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """SURVEY §8 f1 (inference): the lm_head product h [M, d] · w [V, d]ᵀ + bias with the JL_EPI_ARGMAX epilogue — the [M, V]
+    logits are never written; returns (pmax fp32 [ceil(V/32), M], pidx int32 [ceil(V/32), M]): per frame and chunk of 32 vocabulary
+    entries the maximum logit and its (first) index.  ``ctc_greedy_from_partials`` turns them into token ids."""
+    _need(h, BF16, "h")
+    _need(w, BF16, "w")
+    _rows2d(h, "h")
+    _rows2d(w, "w")
+    m, k = h.shape
+    v, kb = w.shape
+    if k != kb:
+        raise ValueError(f"lm_head_argmax: K mismatch ({k} vs {kb})")
+    if bias is not None:
+        _need(bias, F32, "bias", 1)
+    chunks = (v + 31) // 32
+    ld = (m + 31) // 32 * 32
+    pmax = torch.empty((chunks, ld), dtype=F32, device=h.device)
+    pidx = torch.empty((chunks, ld), dtype=I32, device=h.device)
+    p = L.GemmParams(a=h.data_ptr(), lda=h.stride(0), b=w.data_ptr(), ldb=w.stride(0), a_layout=L.JL_LAYOUT_K, b_layout=L.JL_LAYOUT_K,
+                     c=pmax.data_ptr(), ldc=ld, bias=_ptr(bias), residual=None, ldr=0, aux=None, ldaux=0, aux_out=pidx.data_ptr(), ldaux_out=ld,
+                     row_lengths=None, rows_per_seq=0, m=m, n=v, k=k, epilogue=L.JL_EPI_ARGMAX, out_dtype=L.JL_DT_F32, alpha=1.0)
+    L.check(L.load().jl_gemm_bf16(C.byref(p), _stream()))
+    if GEMM_TRACE is not None:
+        GEMM_TRACE.append((p, (h, w, pmax, pidx, bias), 2.0 * m * v * k))
+    return pmax, pidx
+
+
+def ctc_greedy_from_partials(pmax: torch.Tensor, pidx: torch.Tensor, input_lengths: torch.Tensor, batch: int, seq: int, blank: int = 0,
+                             cu_seqlens: Optional[torch.Tensor] = None):
+    """(pmax, pidx) of ``lm_head_argmax`` → (out_ids [B, seq] int32 with -1 tail, out_lengths [B] int32, frame_ids [B, seq] int32)."""
+    _need(pmax, F32, "pmax", 2)
+    _need(pidx, I32, "pidx", 2)
+    _need(input_lengths, I32, "input_lengths", 1)
+    if pmax.shape != pidx.shape or pmax.stride(1) != 1 or pidx.stride(1) != 1 or pmax.stride(0) != pidx.stride(0):
+        raise ValueError("ctc_greedy_from_partials: pmax / pidx must be equally shaped chunk-major matrices")
+    if cu_seqlens is not None:
+        _need(cu_seqlens, I32, "cu_seqlens", 1)
+    dev = pmax.device
+    frame_ids = torch.empty((batch, seq), dtype=I32, device=dev)
+    out_ids = torch.empty((batch, seq), dtype=I32, device=dev)
+    out_len = torch.empty((batch,), dtype=I32, device=dev)
+    L.check(L.load().jl_ctc_greedy_from_partials(pmax.data_ptr(), pidx.data_ptr(), pmax.stride(0), pmax.shape[0], input_lengths.data_ptr(),
+                                                 _ptr(cu_seqlens), batch, seq, blank, frame_ids.data_ptr(), out_ids.data_ptr(),
+                                                 out_len.data_ptr(), _stream()))
+    return out_ids, out_len, frame_ids
+
+
 def replay_gemm_trace(trace) -> None:
     """Re-issue recorded GEMM launches (same operands, same shapes) on the current stream."""
     lib = L.load()

@@ -591,7 +591,10 @@ class Transcriber:
     """Inference: H2D(waveforms) → [mel+CMVN → encoder → lm_head → greedy collapse] → D2H(token ids), graph-captured
     per (batch, samples) shape.  ``packed=True``: the encoder runs on the packed row layout (mixed-length batches)."""
 
-    def __init__(self, model: JLForCTC, use_cuda_graph: bool = True, packed: bool = False):
+    def __init__(self, model: JLForCTC, use_cuda_graph: bool = True, packed: bool = False, fused_head: bool = True):
+        """``fused_head`` (default): lm_head ⊕ frame argmax in the GEMM epilogue — no [B·T', V] logits tensor; the
+        token ids are identical to decoding the materialised logits (``fused_head=False``)."""
+        self.fused_head = fused_head
         self.model = model
         self.cfg = model.config
         self.eng = model.encoder.engine(model.lm_head)
@@ -615,11 +618,17 @@ class Transcriber:
         self._seen_version = v
 
     def _body(self, wave, nsamp, lengths, max_frames, dialect=0, pk=None):
+        want = "argmax" if self.fused_head else True
         if self.cfg.front_end == "wav2vec2":
-            st = self.eng.forward(wave, lengths, training=False, dialect=dialect, want_logits=True, sample_lengths=nsamp)
+            st = self.eng.forward(wave, lengths, training=False, dialect=dialect, want_logits=want, sample_lengths=nsamp)
         else:
             feats = self.fe.extract_device(wave, nsamp, max_frames, return_bf16=True)
-            st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=True, packed=pk)
+            st = self.eng.forward(feats["input_features_bf16"], lengths, training=False, dialect=dialect, want_logits=want, packed=pk)
+        if self.fused_head:
+            pmax, pidx = st.argmax_partials
+            ids, n, _ = ops.ctc_greedy_from_partials(pmax, pidx, lengths, st.b, st.t, blank=self.cfg.pad_token_id,
+                                                     cu_seqlens=None if pk is None else pk.cu)
+            return ids, n
         if pk is not None:
             ids, n, _ = ops.ctc_greedy(st.logits, lengths, blank=self.cfg.pad_token_id, cu_seqlens=pk.cu, max_len=pk.seq_bound)
             return ids, n

@@ -48,3 +48,50 @@ def round_bf16_(model) -> None:
     with torch.no_grad():
         for p in model.parameters():
             p.copy_(p.to(torch.bfloat16).to(torch.float32))
+
+
+# Gradients that pass through the WFAdapter's ReLU on their way back (its down projection and its LayerNorm): bf16 rounding of
+# LN(h) and of the rank-r intermediate moves the pre-activations by ~0.3 %, which flips the ReLU mask of the fraction f of them
+# that sit that close to zero (zero-bias N(0, 0.02) factors centre the pre-activations on zero), and flipping a fraction f of the
+# elements of dpre is a relative L2 error of sqrt(f) — 3-6 % — in ANY implementation that feeds bf16 operands to the tensor cores,
+# whatever its kernels do (tests/test_oracle_encoder.py::test_relu_mask_flips_bound_bf16_wfadapter_down_gradients reproduces it on
+# the CPU with exact arithmetic and a single bf16 rounding).  SURVEY §8d's 3e-2 holds for every other gradient; these get 8e-2.
+WF_RELU_PATH = ("down_A", "down_B", "down_bias", "norm.weight", "norm.bias")
+
+
+def grad_tolerance(name: str, model, base: float = 3e-2, relu_path: float = 8e-2) -> float:
+    """Relative-Frobenius tolerance for the gradient of parameter ``name`` of ``model`` (a JLForCTC): SURVEY §8d's 3e-2, except
+    for the WFAdapter parameters upstream of its ReLU (see WF_RELU_PATH)."""
+    for slot in (".adapter_ffn.", ".adapter_attn."):
+        if slot in name:
+            prefix, leaf = name.split(slot)
+            mod = model.get_submodule(prefix + slot[:-1])
+            if getattr(mod, "kind", None) == "wf" and leaf in WF_RELU_PATH:
+                return relu_path
+    return base
+
+
+def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None):
+    """Every adapter / lm_head gradient of ``model`` against ``ref_grad_of(name)`` (the oracle's): relative Frobenius error <=
+    grad_tolerance(name); the analytically-zero AttAdapter key-bias gradient is compared with the query-bias gradient's norm.
+    Returns {name: relative error} and the worst (name, error) among the gradients held to ``base``."""
+    named = dict(model._get_adapters())
+    errs, worst = {}, ("", 0.0)
+    norms = {}
+    for name, p in named.items():
+        g = p.grad if grads is None else grads[name]
+        assert g is not None, name
+        ref = ref_grad_of(name)
+        err, refn = float((g.float().cpu() - ref).norm()), float(ref.norm())
+        errs[name] = err / max(refn, 1e-30)
+        norms[name] = (err, refn, ref.numel())
+    for name, (err, refn, numel) in norms.items():
+        if name.endswith("k_proj.bias") and (".adapter_ffn." in name or ".adapter_attn." in name):
+            qn = norms[name.replace("k_proj.bias", "q_proj.bias")][1]
+            assert err <= base * qn + 1e-7, f"grad {name}: |err| {err:.3e} vs q_proj.bias grad norm {qn:.3e}"
+            continue
+        tol = grad_tolerance(name, model, base)
+        assert err <= tol * refn + 2e-6 * numel ** 0.5, f"grad {name}: rel {errs[name]:.3e} (err {err:.3e}, ref norm {refn:.3e}), tolerance {tol}"
+        if tol == base and refn > 1e-4 * numel ** 0.5 and errs[name] > worst[1]:
+            worst = (name, errs[name])
+    return errs, worst

@@ -353,6 +353,7 @@ def test_wfadapter_fused_forward_matches_oracle(d, b, r, rows, seq, lens):
         pass
     eng = md.JLEngine.__new__(md.JLEngine)
     eng._shadow = {}
+    eng.flat = None
     g = _g(9)
     h = (torch.randn(rows, d, device="cuda", generator=g) * 1.5 + 0.2).to(BF16)
     lengths = torch.tensor(lens, dtype=I32, device="cuda")
