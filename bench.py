@@ -307,17 +307,27 @@ def inference_rate(P, steps: int, batch: int = 4):
 
 def _time_rotating(fn_list, reps: int = 3) -> float:
     """Average seconds per call of the launches in `fn_list` (each on its own buffers: together > L2, so every launch streams its
-    operands from HBM), CUDA events on the launching stream, after a warm-up round."""
-    for fn in fn_list:
-        fn()
+    operands from HBM).  The sequence is captured into a CUDA graph — as the product runs its kernels — so the figure is device
+    time, not Python call overhead; CUDA events on the replaying stream, after a warm-up replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for fn in fn_list:
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = [fn() for fn in fn_list]
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for fn in fn_list:
-            fn()
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
+    del keep
     return e0.elapsed_time(e1) / 1e3 / (reps * len(fn_list))
 
 

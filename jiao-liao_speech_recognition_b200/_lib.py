@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjl_b200.so")
+# JL_B200_LIB: tuning aid — an alternative build of the same sources (scripts/build_variant.sh) for A/B runs; default = the in-tree library
+LIB_PATH = os.environ.get("JL_B200_LIB") or os.path.join(_HERE, "libjl_b200.so")
 
 JL_OK, JL_EINVAL, JL_EUNSUPPORTED_SHAPE, JL_ECUDA, JL_EUNSUPPORTED = 0, -1, -2, -3, -4
 JL_DT_BF16, JL_DT_F32 = 0, 1

@@ -29,7 +29,10 @@ namespace jl {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 12;
+#ifndef JL_GEMM_EPI_WARPS
+#define JL_GEMM_EPI_WARPS 12
+#endif
+constexpr int GEMM_EPI_WARPS = JL_GEMM_EPI_WARPS;   // a multiple of 4 (one warp per TMEM lane quadrant and column group)
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 

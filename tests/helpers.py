@@ -71,10 +71,11 @@ def grad_tolerance(name: str, model, base: float = 3e-2, relu_path: float = 8e-2
     return base
 
 
-def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None):
+def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None, record=None):
     """Every adapter / lm_head gradient of ``model`` against ``ref_grad_of(name)`` (the oracle's): relative Frobenius error <=
     grad_tolerance(name); the analytically-zero AttAdapter key-bias gradient is compared with the query-bias gradient's norm.
-    Returns {name: relative error} and the worst (name, error) among the gradients held to ``base``."""
+    Returns {name: relative error} and the worst (name, error) among the gradients held to ``base``.  ``record(errs)`` is called
+    with every measured error before anything is asserted."""
     named = dict(model._get_adapters())
     errs, worst = {}, ("", 0.0)
     norms = {}
@@ -85,6 +86,8 @@ def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None):
         err, refn = float((g.float().cpu() - ref).norm()), float(ref.norm())
         errs[name] = err / max(refn, 1e-30)
         norms[name] = (err, refn, ref.numel())
+    if record is not None:
+        record({k: v for k, v in errs.items() if not k.endswith("k_proj.bias")})
     for name, (err, refn, numel) in norms.items():
         if name.endswith("k_proj.bias") and (".adapter_ffn." in name or ".adapter_attn." in name):
             qn = norms[name.replace("k_proj.bias", "q_proj.bias")][1]
