@@ -191,6 +191,32 @@ typedef struct {
 int jl_wfadapter_fwd(const jl_wfadapter_fwd_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;
+ * /root/reference/README.md:1 "multi-dialect knowledge transfer" + "adapter with attention").  Per frame:
+ *   alpha = softmax_k(q . key_k * scale),   out = h + sum_k alpha_k y_k
+ * y_k = update of the k-th dialect's WFAdapter, q / key_k = projections of LN(h) / y_k (all produced by jl_gemm_bf16).  These
+ * entry points are the part that is not a GEMM: the K dot products, the softmax over K and the weighted sum (forward); and
+ * d alpha, the softmax backward, dq, dkey_k and dy_k = alpha_k dout (backward; the caller adds dkey_k W_k to dy_k with a GEMM).
+ * One struct serves both directions; a tensor of K matrices is addressed as base + k * stride (elements).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* h; int64_t ldh;                          /* fwd: bf16 [rows, d] */
+  const void* y; int64_t ldy; int64_t y_stride;        /* bf16 K x [rows, d] */
+  const void* q; int64_t ldq;                          /* bf16 [rows, b] */
+  const void* key; int64_t ldkey; int64_t key_stride;  /* bf16 K x [rows, b] */
+  void* out; int64_t ldo;                              /* fwd: bf16 [rows, d] */
+  float* alpha;                                        /* fp32 [rows, K]: written by fwd, read by bwd */
+  const void* dout; int64_t lddout;                    /* bwd: bf16 [rows, d] */
+  void* dy; int64_t lddy; int64_t dy_stride;           /* bwd out: bf16 K x [rows, d] = alpha_k * dout */
+  void* dq; int64_t lddq;                              /* bwd out: bf16 [rows, b] */
+  void* dkey; int64_t lddkey; int64_t dkey_stride;     /* bwd out: bf16 K x [rows, b] */
+  int32_t rows, d, b, num_adapters;                    /* d, b multiples of 8; b <= 256; num_adapters <= 8 */
+  float scale;                                         /* 1 / sqrt(b) */
+} jl_fusion_params;
+int jl_fusion_combine_fwd(const jl_fusion_params* p, void* stream);
+int jl_fusion_combine_bwd(const jl_fusion_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-attention softmax(Q K^T * scale + keymask) V per (utterance, head), head_dim 64.
  * Replaces the eager math at SP/transformers/models/wav2vec2/modeling_wav2vec2.py:438-463
  * (never materialises the [B,H,T,T] scores); also the AttAdapter attention (heads = 1).

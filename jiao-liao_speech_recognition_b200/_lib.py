@@ -55,6 +55,13 @@ class WFAdapterFwdParams(C.Structure):
                 ("mean", vp), ("rstd", vp), ("rows", i32), ("d", i32), ("r", i32), ("b", i32), ("eps", f32)]
 
 
+class FusionParams(C.Structure):
+    _fields_ = [("h", vp), ("ldh", i64), ("y", vp), ("ldy", i64), ("y_stride", i64), ("q", vp), ("ldq", i64), ("key", vp), ("ldkey", i64),
+                ("key_stride", i64), ("out", vp), ("ldo", i64), ("alpha", vp), ("dout", vp), ("lddout", i64), ("dy", vp), ("lddy", i64),
+                ("dy_stride", i64), ("dq", vp), ("lddq", i64), ("dkey", vp), ("lddkey", i64), ("dkey_stride", i64),
+                ("rows", i32), ("d", i32), ("b", i32), ("num_adapters", i32), ("scale", f32)]
+
+
 class AttnFwdParams(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("ld_qkv", i64), ("o", vp), ("ld_o", i64), ("lse", vp),
                 ("lengths", vp), ("batch", i32), ("seq", i32), ("heads", i32), ("scale", f32), ("cu_seqlens", vp), ("total_rows", i32)]
@@ -107,6 +114,8 @@ SYMBOLS = {
     "jl_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_layernorm_wgrad": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_wfadapter_fwd": (C.c_int, [C.POINTER(WFAdapterFwdParams), vp]),
+    "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
+    "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),
     "jl_attn_bwd": (C.c_int, [C.POINTER(AttnBwdParams), vp]),
     "jl_ctc_workspace_bytes": (C.c_int, [C.POINTER(CtcParams), C.POINTER(C.c_size_t)]),

@@ -131,6 +131,32 @@ def att_adapter(w: W, p: str, h: torch.Tensor, lengths: torch.Tensor) -> torch.T
     return h + F.linear(a, w[p + ".o_proj.weight"], w[p + ".o_proj.bias"])
 
 
+def fusion_adapter(w: W, p: str, h: torch.Tensor) -> torch.Tensor:
+    """AdapterFusion-style AttAdapter over the K source-dialect adapters of the slot (SURVEY §8c ambiguity (ii), §8f f4;
+    /root/reference/README.md:1 "multi-dialect knowledge transfer" + "adapter with attention"; Pfeiffer et al.'s AdapterFusion
+    with the value projection fixed to the identity).  The K factor sets of ``<p>.source`` (a WFAdapter, one set per source
+    dialect) are all applied to every frame; the frame then attends over their K outputs:
+        y_k   = WFAdapter_k(h) - h                         (the k-th dialect adapter's update, k = 0..K-1)
+        q     = LN_f(h) W_qᵀ + b_q            ∈ R^b
+        key_k = y_k W_kᵀ + b_k                ∈ R^b
+        α     = softmax_k(q · key_k / √b)                  (over the K dialects, per frame — no attention over time)
+        out   = h + Σ_k α_k y_k
+    No dialect id is needed: the fusion weights α pick the mixture of source dialects per frame."""
+    src = p + ".source"
+    kd = w[src + ".down_B"].shape[0]
+    z = layer_norm(h, w, src + ".norm")
+    ys = []
+    for k in range(kd):
+        u = torch.relu(F.linear(F.linear(z, w[src + ".down_B"][k]), w[src + ".down_A"][k], w[src + ".down_bias"][k]))
+        ys.append(F.linear(F.linear(u, w[src + ".up_B"][k]), w[src + ".up_A"][k], w[src + ".up_bias"][k]))
+    y = torch.stack(ys, 0)                                                    # [K, B, T, d]
+    q = F.linear(layer_norm(h, w, p + ".norm"), w[p + ".q_proj.weight"], w[p + ".q_proj.bias"])      # [B, T, b]
+    key = F.linear(y, w[p + ".k_proj.weight"], w[p + ".k_proj.bias"])        # [K, B, T, b]
+    s = (q.unsqueeze(0) * key).sum(-1) * (q.shape[-1] ** -0.5)               # [K, B, T]
+    alpha = torch.softmax(s, dim=0)
+    return h + (alpha.unsqueeze(-1) * y).sum(0)
+
+
 def apply_adapter(w: W, p: str, kind: Optional[str], h: torch.Tensor, lengths: torch.Tensor, dialect=0) -> torch.Tensor:
     if kind is None:
         return h
@@ -138,6 +164,8 @@ def apply_adapter(w: W, p: str, kind: Optional[str], h: torch.Tensor, lengths: t
         return wf_adapter(w, p, h, dialect)
     if kind == "att":
         return att_adapter(w, p, h, lengths)
+    if kind == "fuse":
+        return fusion_adapter(w, p, h)
     raise ValueError(kind)
 
 

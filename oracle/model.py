@@ -36,7 +36,7 @@ class OracleConfig:
     pad_token_id: int = 0
     ctc_loss_reduction: str = "sum"
     ctc_zero_infinity: bool = False
-    adapter_attn: Optional[str] = None      # None | "wf" | "att"
+    adapter_attn: Optional[str] = None      # None | "wf" | "att" | "fuse"
     adapter_ffn: Optional[str] = None
     wf_bottleneck: int = 256
     wf_rank: int = 32
@@ -89,6 +89,14 @@ def init_weights(cfg: OracleConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
             for n in ("q_proj", "k_proj", "v_proj"):
                 linear(f"{p}.{n}", cfg.att_dim, d)
             linear(p + ".o_proj", d, cfg.att_dim)
+        elif kind == "fuse":
+            # parameter order = the product module's (FusionAdapter: source WFAdapter, then norm / q_proj / k_proj) — ``ln`` above
+            # has already created <p>.norm; move it behind the source adapter's tensors to keep one naming scheme
+            nw, nb = w.pop(p + ".norm.weight"), w.pop(p + ".norm.bias")
+            adapter(p + ".source", "wf")
+            w[p + ".norm.weight"], w[p + ".norm.bias"] = nw, nb
+            linear(p + ".q_proj", cfg.att_dim, d)
+            linear(p + ".k_proj", cfg.att_dim, d)
         else:
             raise ValueError(kind)
 

@@ -36,6 +36,7 @@ STRUCTS = {
     "jl_ctc_params": "CtcParams",
     "jl_ctc_greedy_params": "CtcGreedyParams",
     "jl_adamw_params": "AdamWParams",
+    "jl_fusion_params": "FusionParams",
 }
 
 
