@@ -412,6 +412,8 @@ def run_ours(args):
     P = importlib.import_module(PKG)
     if os.environ.get("JL_PDL") in ("0", "1"):     # tuning aid: programmatic dependent launch off / on (default: on)
         P._lib.load().jl_debug_set_pdl(int(os.environ["JL_PDL"]))
+    if os.environ.get("JL_GEMM_TAIL"):             # tuning aid: tail-wave policy of the GEMM (jl_debug_set_gemm_tail bit mask)
+        P._lib.load().jl_debug_set_gemm_tail(int(os.environ["JL_GEMM_TAIL"]))
     wl = WORKLOADS[args.config]
     cfg = (P.JLConfig.large if wl["size"] == "large" else P.JLConfig.base)(**wl["model"])
     model = P.JLForCTC(cfg).cuda()

@@ -212,6 +212,7 @@ typedef struct {
   void* dkey; int64_t lddkey; int64_t dkey_stride;     /* bwd out: bf16 K x [rows, b] */
   int32_t rows, d, b, num_adapters;                    /* d, b multiples of 8; b <= 256; num_adapters <= 8 */
   float scale;                                         /* 1 / sqrt(b) */
+  const int32_t* row_lengths; int32_t rows_per_seq;    /* fwd, optional (padded layout): rows t >= length of their utterance := 0 */
 } jl_fusion_params;
 int jl_fusion_combine_fwd(const jl_fusion_params* p, void* stream);
 int jl_fusion_combine_bwd(const jl_fusion_params* p, void* stream);
@@ -386,7 +387,8 @@ void jl_debug_set_gemm_mode(int mode);
 /* test / tuning hook: force the N tile (32/64/128/256 single-CTA kernel, 128/192/256 pair kernel with mode 2); 0 = automatic */
 void jl_debug_set_gemm_bn(int bn);
 /* test / tuning hook — what happens to the last, partial wave of output tiles (bit mask, default 2):
- *   bit 1 (2): single-CTA kernel: the tail tiles are cut into 2 or 4 column slices (independent, shorter work units);
+ *   bit 1 (2): single-CTA kernel: the tail tiles are cut into 2, 3 (96 + 96 + 64 columns of a 256-wide tile) or 4 column slices
+ *              (independent, shorter work units);  bit 2 (4): never use the three-way cut;
  *   bit 0 (1): CTA-pair kernel: the tail tiles are cut into K ranges with an in-kernel fix-up (needs the workspace;
  *              validated, measured slower, off by default) */
 void jl_debug_set_gemm_tail(int mode);

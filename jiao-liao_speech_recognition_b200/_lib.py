@@ -59,7 +59,7 @@ class FusionParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("y", vp), ("ldy", i64), ("y_stride", i64), ("q", vp), ("ldq", i64), ("key", vp), ("ldkey", i64),
                 ("key_stride", i64), ("out", vp), ("ldo", i64), ("alpha", vp), ("dout", vp), ("lddout", i64), ("dy", vp), ("lddy", i64),
                 ("dy_stride", i64), ("dq", vp), ("lddq", i64), ("dkey", vp), ("lddkey", i64), ("dkey_stride", i64),
-                ("rows", i32), ("d", i32), ("b", i32), ("num_adapters", i32), ("scale", f32)]
+                ("rows", i32), ("d", i32), ("b", i32), ("num_adapters", i32), ("scale", f32), ("row_lengths", vp), ("rows_per_seq", i32)]
 
 
 class AttnFwdParams(C.Structure):

@@ -21,8 +21,10 @@ class JLConfig:
     ctc_zero_infinity: bool = False         # :204
     layer_norm_eps: float = 1e-5            # :179
     initializer_range: float = 0.02
-    adapter_attn: Optional[str] = None      # None | "wf" | "att"  — slot after the self-attention residual
-    adapter_ffn: Optional[str] = None       # None | "wf" | "att"  — slot after the FFN residual (HF's adapter_layer site)
+    # adapter kinds: "wf" = WFAdapter (factor set chosen by dialect id), "att" = AttAdapter (attention over the utterance's frames),
+    # "fuse" = FusionAdapter (AdapterFusion-style attention over the outputs of the num_dialects source-dialect WFAdapter sets)
+    adapter_attn: Optional[str] = None      # None | "wf" | "att" | "fuse"  — slot after the self-attention residual
+    adapter_ffn: Optional[str] = None       # None | "wf" | "att" | "fuse"  — slot after the FFN residual (HF's adapter_layer site)
     wf_bottleneck: int = 256
     wf_rank: int = 32
     att_dim: int = 64
@@ -42,8 +44,10 @@ class JLConfig:
         if self.hidden_size % 64 or self.hidden_size // self.num_attention_heads != 64:
             raise ValueError("hidden_size / num_attention_heads must be 64 (the attention kernel's head_dim)")
         for slot in (self.adapter_attn, self.adapter_ffn):
-            if slot not in (None, "wf", "att"):
+            if slot not in (None, "wf", "att", "fuse"):
                 raise ValueError(f"unknown adapter kind {slot!r}")
+            if slot == "fuse" and not 1 <= self.num_dialects <= 8:
+                raise ValueError("the fusion adapter attends over 1..8 source-dialect adapters (num_dialects)")
         if self.att_dim != 64:
             raise ValueError("att_dim must be 64 (one attention head of head_dim 64)")
         if self.wf_rank % 8 or self.wf_bottleneck % 8:

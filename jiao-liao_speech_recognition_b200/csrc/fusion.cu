@@ -71,6 +71,13 @@ __global__ void __launch_bounds__(256) fusion_combine_fwd_kernel(const jl_fusion
   const uint4* hrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.h) + static_cast<int64_t>(row) * p.ldh);
   uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo);
   const int nv = p.d >> 3;
+  if (p.row_lengths != nullptr) {                  // padded layout: rows past the utterance's last frame stay exactly zero
+    const int bi = row / p.rows_per_seq;
+    if (row - bi * p.rows_per_seq >= __ldg(p.row_lengths + bi)) {
+      for (int c = lane; c < nv; c += 32) orow[c] = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+  }
   for (int c = lane; c < nv; c += 32) {
     float acc[8];
     fuse_unpack8(__ldg(hrow + c), acc);
@@ -166,6 +173,7 @@ static int fusion_validate(const jl_fusion_params* p, bool bwd) {
   JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->y) | reinterpret_cast<uintptr_t>(p->q) | reinterpret_cast<uintptr_t>(p->key)) & 15) == 0, JL_EINVAL,
              "fusion: pointers must be 16-byte aligned");
   if (!bwd) {
+    JL_REQUIRE(p->row_lengths == nullptr || p->rows_per_seq > 0, JL_EINVAL, "fusion_fwd: row_lengths needs rows_per_seq > 0");
     JL_REQUIRE(p->h && p->out && ((p->ldh | p->ldo) & 7) == 0, JL_EINVAL, "fusion_fwd: null h / out or bad stride");
     JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->h) | reinterpret_cast<uintptr_t>(p->out)) & 15) == 0, JL_EINVAL, "fusion_fwd: pointers must be 16-byte aligned");
   } else {

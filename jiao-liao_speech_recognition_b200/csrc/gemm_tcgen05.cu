@@ -354,6 +354,11 @@ __device__ __forceinline__ CtaUnit cta_unit(const GemmDev& g, int u) {
       const int v = u - g.nsplit_first;
       r.tile = g.nsplit_first + v / g.nsplit;
       sub = v - (r.tile - g.nsplit_first) * g.nsplit;
+      if (g.nsplit == 3) {                 // 256 columns as 96 + 96 + 64 (UMMA N is a multiple of 16, the epilogue works in chunks of 32)
+        r.bn = (sub < 2) ? 96 : 64;
+        r.n0 = (r.tile % g.num_n_tiles) * BN + sub * 96;
+        return r;
+      }
       r.bn = BN / g.nsplit;
     }
   } else {
@@ -367,7 +372,7 @@ __device__ __forceinline__ CtaUnit cta_unit(const GemmDev& g, int u) {
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b_sub,
-                    const GemmDev g) {
+                    const __grid_constant__ CUtensorMap tma_b_sub2, const GemmDev g) {
   jl::pdl_launch_dependents();
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -395,6 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
     if (g.nsplit > 1) ptx::prefetch_tensormap(&tma_b_sub);
+    if (g.nsplit == 3) ptx::prefetch_tensormap(&tma_b_sub2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -446,7 +452,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) ptx::tma_load_2d(b_dst + i * 8192, &tma_b, full_bar + stage, n0 + 64 * i, k0);
           } else {
-            ptx::tma_load_2d(b_dst, sliced ? &tma_b_sub : &tma_b, full_bar + stage, k0, n0);
+            ptx::tma_load_2d(b_dst, !sliced ? &tma_b : ((g.nsplit == 3 && un.bn == 64) ? &tma_b_sub2 : &tma_b_sub), full_bar + stage, k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -987,14 +993,17 @@ static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
     }
   }
   int units = g.num_m_tiles * g.num_n_tiles * g.split_k;
-  CUtensorMap mbs = mb;
+  CUtensorMap mbs = mb, mbs2 = mb;
   if (!B_MN && BN >= 128 && g.split_k == 1 && (g_gemm_tail.load() & 2)) {
-    // the last, partial wave of tiles as column slices: [tail · nsplit <= SMs] → it takes 1 / nsplit of a tile time
+    // the last, partial wave of tiles as column slices: [tail · nsplit <= SMs] → it takes 1 / nsplit of a tile time (3 slices of a
+    // 256-wide tile: 96 + 96 + 64 columns → 0.375; bit 2 of the tail mode switches the three-way split off)
     const int sms = num_sms();
     const int first = (units / sms) * sms, tail = units - first;
-    const int ns = (tail == 0) ? 1 : (BN >= 256 && tail * 4 <= sms) ? 4 : (tail * 2 <= sms ? 2 : 1);
+    const bool three = BN == 256 && (g_gemm_tail.load() & 4) == 0;
+    const int ns = (tail == 0) ? 1 : (BN >= 256 && tail * 4 <= sms) ? 4 : (three && tail * 3 <= sms) ? 3 : (tail * 2 <= sms ? 2 : 1);
     if (ns > 1) {
-      rc = make_map(&mbs, p->b, p->k, p->n, p->ldb, BN / ns);
+      rc = make_map(&mbs, p->b, p->k, p->n, p->ldb, ns == 3 ? 96 : BN / ns);
+      if (rc == JL_OK && ns == 3) rc = make_map(&mbs2, p->b, p->k, p->n, p->ldb, 64);
       if (rc != JL_OK) return rc;
       g.nsplit_first = first;
       g.nsplit = ns;
@@ -1002,7 +1011,7 @@ static int launch_gemm(const jl_gemm_params* p, cudaStream_t stream) {
     }
   }
   const int grid = units < num_sms() ? units : num_sms();
-  jl::launch(kern, grid, GEMM_THREADS, L::TOTAL, stream, ma, mb, mbs, g);
+  jl::launch(kern, grid, GEMM_THREADS, L::TOTAL, stream, ma, mb, mbs, mbs2, g);
   JL_CHECK_LAUNCH("gemm_tcgen05");
   if (g.split_k > 1) {
     const int64_t total = static_cast<int64_t>(p->m) * p->n;
@@ -1248,7 +1257,7 @@ int jl_gemm_workspace_zero_bytes(const jl_gemm_params* p, size_t* out) {
   return JL_OK;
 }
 
-void jl_debug_set_gemm_tail(int mode) { jl::g_gemm_tail.store(mode & 3); }
+void jl_debug_set_gemm_tail(int mode) { jl::g_gemm_tail.store(mode & 7); }
 
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream) {
   int rc = jl::validate(p);

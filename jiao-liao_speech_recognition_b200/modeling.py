@@ -29,6 +29,10 @@ from . import hf_compat, ops
 from .configuration import JLConfig
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+_DEBUG_SKIP_SIDE = os.environ.get("JL_DEBUG_SKIP_SIDE") == "1"
+# where the dγ / dβ of a trainable adapter LayerNorm are computed: "side" = a kernel of its own on the weight-gradient branch
+# (re-reads dz and h), "main" = inside the LayerNorm backward kernel of the main chain (per-CTA partials + fixed-order reduce)
+_LN_WGRAD = os.environ.get("JL_LN_WGRAD", "side")
 
 
 def subsampled_length(n, num_convs: int = 2):
@@ -110,9 +114,43 @@ class AttAdapter(nn.Module):
             self.norm.bias.zero_()
 
 
+class FusionAdapter(nn.Module):
+    """AdapterFusion-style AttAdapter over the K source-dialect adapters of the slot (SURVEY §8c ambiguity (ii), §8f f4): every
+    frame runs all K factor sets of ``source`` (a WFAdapter, one set per source dialect), then attends over their K updates:
+    y_k = WFAdapter_k(h) − h;  q = LN_f(h) W_qᵀ + b_q;  key_k = y_k W_kᵀ + b_k;  α = softmax_k(q·key_k / √b);  out = h + Σ_k α_k y_k.
+    No dialect id is needed.  For knowledge transfer, train the source sets on the neighbouring dialects (kind "wf"), load them
+    here, freeze ``source`` (``requires_grad_(False)``) and fine-tune norm / q_proj / k_proj on the target dialect."""
+
+    kind = "fuse"
+
+    def __init__(self, hidden_size: int, att_dim: int = 64, bottleneck: int = 256, rank: int = 32, num_dialects: int = 2, eps: float = 1e-5):
+        super().__init__()
+        if not 1 <= num_dialects <= 8:
+            raise ValueError("FusionAdapter: 1 <= num_dialects <= 8")
+        if att_dim % 8 or att_dim > 256:
+            raise ValueError("FusionAdapter: att_dim must be a multiple of 8, <= 256")
+        self.hidden_size, self.att_dim, self.num_dialects = hidden_size, att_dim, num_dialects
+        self.source = WFAdapter(hidden_size, bottleneck, rank, num_dialects, eps)
+        self.norm = nn.LayerNorm(hidden_size, eps=eps)
+        self.q_proj = nn.Linear(hidden_size, att_dim)
+        self.k_proj = nn.Linear(hidden_size, att_dim)
+        self.reset_parameters()
+
+    def reset_parameters(self, std: float = 0.02, generator: Optional[torch.Generator] = None):
+        self.source.reset_parameters(std, generator)
+        with torch.no_grad():
+            for lin in (self.q_proj, self.k_proj):
+                lin.weight.copy_(torch.randn(lin.weight.shape, generator=generator) * std)
+                lin.bias.zero_()
+            self.norm.weight.fill_(1.0)
+            self.norm.bias.zero_()
+
+
 def _make_adapter(kind: Optional[str], cfg: JLConfig) -> Optional[nn.Module]:
     if kind is None:
         return None
+    if kind == "fuse":
+        return FusionAdapter(cfg.hidden_size, cfg.att_dim, cfg.wf_bottleneck, cfg.wf_rank, cfg.num_dialects, cfg.layer_norm_eps)
     if kind == "wf":
         return WFAdapter(cfg.hidden_size, cfg.wf_bottleneck, cfg.wf_rank, cfg.num_dialects, cfg.layer_norm_eps)
     if kind == "att":
@@ -270,6 +308,8 @@ class _SideBranch:
         self.keep = []
 
     def run(self, fn, *tensors) -> None:
+        if _DEBUG_SKIP_SIDE:          # timing experiment only (wrong gradients): what the weight-gradient branch costs the step
+            return
         if not self.enabled:
             fn()
             return
@@ -519,6 +559,8 @@ class JLEngine:
         eps = ad.norm.eps
         zero_rows = zero_rows and pk is None
         cu = None if pk is None else pk.cu
+        if ad.kind == "fuse":
+            return self._fusion_fwd(ad, h, lengths, t, training, zero_rows)
         segs = self.dialect_segments(dialect, b, ad.num_dialects) if ad.kind == "wf" else None
         if ad.kind == "wf" and not training and self.fused_wf and self._wf_fusable(ad):
             # inference: the whole adapter is one kernel per dialect run (LN folded into the first projection); training
@@ -559,6 +601,83 @@ class JLEngine:
             saved = (h, mean, rstd, z, qkv, a, lse) if training else None
         return out, saved
 
+    # ------------------------------------------------------------------ f4: AdapterFusion-style adapter
+    def _fusion_fwd(self, ad: "FusionAdapter", h: torch.Tensor, lengths, t: int, training: bool, zero_rows: bool):
+        """All K source-dialect factor sets on every row (the first projection of all sets is ONE GEMM with N = K·r, the key
+        projection ONE GEMM over the K·M rows of y), then the fusion combine kernel.  Returns (out, saved)."""
+        src = ad.source
+        kk, r, bt, d, m = src.num_dialects, src.rank, src.bottleneck, src.hidden_size, h.shape[0]
+        dev = h.device
+        zs, mean_s, rstd_s = ops.layernorm_fwd(h, src.norm.weight.detach(), src.norm.bias.detach(), src.norm.eps, save_stats=training)
+        t1 = ops.gemm(zs, self._bf16(src.down_B).view(kk * r, d))                                  # [m, K·r]
+        u = torch.empty((kk, m, bt), dtype=BF16, device=dev)
+        t2 = torch.empty((m, kk * r), dtype=BF16, device=dev)
+        y = torch.empty((kk, m, d), dtype=BF16, device=dev)
+        for k in range(kk):
+            cs = slice(k * r, (k + 1) * r)
+            ops.gemm(t1[:, cs], self._bf16(src.down_A)[k], bias=src.down_bias.detach()[k], epilogue=L.JL_EPI_RELU, out=u[k])
+            ops.gemm(u[k], self._bf16(src.up_B)[k], out=t2[:, cs])
+            ops.gemm(t2[:, cs], self._bf16(src.up_A)[k], bias=src.up_bias.detach()[k], out=y[k])      # the update only: no residual
+        zf, mean_f, rstd_f = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, save_stats=training)
+        q = ops.gemm(zf, self._bf16(ad.q_proj.weight), bias=ad.q_proj.bias.detach())
+        key = ops.gemm(y.view(kk * m, d), self._bf16(ad.k_proj.weight), bias=ad.k_proj.bias.detach()).view(kk, m, ad.att_dim)
+        scale = 1.0 / math.sqrt(ad.att_dim)
+        out, alpha = ops.fusion_combine_fwd(h, y, q, key, scale, row_lengths=lengths if zero_rows else None, rows_per_seq=t if zero_rows else 0)
+        saved = (h, zs, mean_s, rstd_s, t1, u, t2, y, zf, mean_f, rstd_f, q, key, alpha, scale) if training else None
+        return out, saved
+
+    def _fusion_bwd(self, ad: "FusionAdapter", saved, dout: torch.Tensor, g: "GradSink", sb: "_SideBranch") -> torch.Tensor:
+        MN = L.JL_LAYOUT_MN
+        h, zs, mean_s, rstd_s, t1, u, t2, y, zf, mean_f, rstd_f, q, key, alpha, scale = saved
+        src = ad.source
+        kk, r, d, m, b = src.num_dialects, src.rank, src.hidden_size, h.shape[0], ad.att_dim
+        dy, dq, dkey = ops.fusion_combine_bwd(dout, y, q, key, alpha, scale)
+        dkey2, y2, dy2 = dkey.view(kk * m, b), y.view(kk * m, d), dy.view(kk * m, d)
+        # knowledge transfer freezes the source-dialect adapters and trains the fusion only: their weight gradients are then skipped
+        # (the gradient still flows THROUGH them to the layers below)
+        train_src = src.down_B.requires_grad
+
+        def w_fuse():
+            ops.gemm(dkey2, y2, a_layout=MN, b_layout=MN, out=g.out(ad.k_proj.weight), out_dtype=F32)      # dkeyᵀ · y
+            ops.colsum(dkey2, out=g.out(ad.k_proj.bias))
+            ops.gemm(dq, zf, a_layout=MN, b_layout=MN, out=g.out(ad.q_proj.weight), out_dtype=F32)         # dqᵀ · LN_f(h)
+            ops.colsum(dq, out=g.out(ad.q_proj.bias))
+        sb.run(w_fuse, dkey2, y2, dq, zf)
+        # the keys are projections of y: dy_k += dkey_k · W_k
+        dyt = ops.gemm(dkey2, self._bf16(ad.k_proj.weight), b_layout=MN, residual=dy2)
+        dzf = ops.gemm(dq, self._bf16(ad.q_proj.weight), b_layout=MN)
+        sb.run(lambda: ops.layernorm_wgrad(dzf, h, mean_f, rstd_f, g.out(ad.norm.weight), g.out(ad.norm.bias)), dzf, h, mean_f, rstd_f)
+        dh, _, _ = ops.layernorm_bwd(dzf, h, ad.norm.weight.detach(), mean_f, rstd_f, dres=dout)
+        # the K source adapters, each on every row
+        dt1 = torch.empty_like(t1)
+        for k in range(kk):
+            cs = slice(k * r, (k + 1) * r)
+            dyk, t1k, t2k, uk = dyt[k * m:(k + 1) * m], t1[:, cs], t2[:, cs], u[k]
+
+            def w_up(dyk=dyk, t2k=t2k, k=k):
+                ops.gemm(dyk, t2k, a_layout=MN, b_layout=MN, out=g.out(src.up_A, k), out_dtype=F32)
+                ops.colsum(dyk, out=g.out(src.up_bias, k))
+            if train_src:
+                sb.run(w_up, dyk, t2k)
+            dt2 = ops.gemm(dyk, self._bf16(src.up_A)[k], b_layout=MN)
+            if train_src:
+                sb.run(lambda dt2=dt2, uk=uk, k=k: ops.gemm(dt2, uk, a_layout=MN, b_layout=MN, out=g.out(src.up_B, k), out_dtype=F32), dt2, uk)
+            dpre = ops.gemm(dt2, self._bf16(src.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=uk)
+
+            def w_down(dpre=dpre, t1k=t1k, k=k):
+                ops.colsum(dpre, out=g.out(src.down_bias, k))
+                ops.gemm(dpre, t1k, a_layout=MN, b_layout=MN, out=g.out(src.down_A, k), out_dtype=F32)
+            if train_src:
+                sb.run(w_down, dpre, t1k)
+            ops.gemm(dpre, self._bf16(src.down_A)[k], b_layout=MN, out=dt1[:, cs])
+            if train_src:
+                sb.run(lambda k=k, cs=cs: ops.gemm(dt1[:, cs], zs, a_layout=MN, b_layout=MN, out=g.out(src.down_B, k), out_dtype=F32), dt1, zs)
+        dzs = ops.gemm(dt1, self._bf16(src.down_B).view(kk * r, d), b_layout=MN)                  # Σ_k dt1_k · B_d[k]: one GEMM, K = K·r
+        if train_src:
+            sb.run(lambda: ops.layernorm_wgrad(dzs, h, mean_s, rstd_s, g.out(src.norm.weight), g.out(src.norm.bias)), dzs, h, mean_s, rstd_s)
+        dh, _, _ = ops.layernorm_bwd(dzs, h, src.norm.weight.detach(), mean_s, rstd_s, dres=dh)
+        return dh
+
     def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch") -> None:
         """Backward of the WFAdapter projections for the utterances of dialect ``k`` (a row slice): weight gradients of
         factor set k on the side branch, dz[rows] = gradient at the adapter's LayerNorm output."""
@@ -587,6 +706,8 @@ class JLEngine:
         side branch ``sb``)."""
         MN = L.JL_LAYOUT_MN
         cu = None if pk is None else pk.cu
+        if ad.kind == "fuse":
+            return self._fusion_bwd(ad, saved, dy, g, sb)
         if ad.kind == "wf":
             h, mean, rstd, z, t1, u, t2, segs = saved
             dz = torch.empty_like(h)
@@ -621,6 +742,10 @@ class JLEngine:
                 g.scatter_cat(bs, gb)
             sb.run(w_qkv, dqkv, z)
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
+        if _LN_WGRAD == "main":
+            dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True, dgamma=g.out(ad.norm.weight),
+                                         dbeta=g.out(ad.norm.bias))
+            return dh
         sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
         dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy)
         return dh
@@ -949,7 +1074,7 @@ class JLForCTC(nn.Module):
         std = self.config.initializer_range
         with torch.no_grad():
             for m in self.modules():
-                if isinstance(m, (WFAdapter, AttAdapter)):
+                if isinstance(m, (WFAdapter, AttAdapter, FusionAdapter)):
                     m.reset_parameters(std, gen)
             self.lm_head.weight.copy_((torch.randn(self.lm_head.weight.shape, generator=gen) * std).to(self.lm_head.weight.device))
             self.lm_head.bias.zero_()

@@ -280,6 +280,59 @@ def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional
     return out, mean, rstd
 
 
+# ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)
+def _fusion_params(y, q, key, alpha, scale):
+    kk, rows, d = y.shape
+    b = q.shape[1]
+    for t, nm in ((y, "y"), (key, "key")):
+        _need(t, BF16, nm, 3)
+        if not t.is_contiguous():
+            raise ValueError(f"fusion: {nm} must be contiguous [K, rows, C]")
+    _need(q, BF16, "q", 2)
+    _rows2d(q, "q")
+    _need(alpha, F32, "alpha", 2)
+    if key.shape != (kk, rows, b) or q.shape[0] != rows or alpha.shape != (rows, kk) or not alpha.is_contiguous():
+        raise ValueError("fusion: shape mismatch between y / q / key / alpha")
+    return L.FusionParams(y=y.data_ptr(), ldy=d, y_stride=rows * d, q=q.data_ptr(), ldq=q.stride(0), key=key.data_ptr(), ldkey=b,
+                          key_stride=rows * b, alpha=alpha.data_ptr(), rows=rows, d=d, b=b, num_adapters=kk, scale=scale)
+
+
+def fusion_combine_fwd(h: torch.Tensor, y: torch.Tensor, q: torch.Tensor, key: torch.Tensor, scale: float,
+                       row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0):
+    """out = h + Σ_k softmax_k(q · key_k · scale) y_k per row.  h [rows, d], y [K, rows, d], q [rows, b], key [K, rows, b] (bf16) →
+    (out [rows, d] bf16, alpha [rows, K] fp32)."""
+    _need(h, BF16, "h", 2)
+    _rows2d(h, "h")
+    rows, d = h.shape
+    alpha = torch.empty((rows, y.shape[0]), dtype=F32, device=h.device)
+    out = torch.empty((rows, d), dtype=BF16, device=h.device)
+    p = _fusion_params(y, q, key, alpha, scale)
+    if y.shape[1] != rows or y.shape[2] != d:
+        raise ValueError("fusion: y must be [K, rows, d]")
+    p.h, p.ldh, p.out, p.ldo = h.data_ptr(), h.stride(0), out.data_ptr(), out.stride(0)
+    p.row_lengths, p.rows_per_seq = _ptr(row_lengths), rows_per_seq
+    L.check(L.load().jl_fusion_combine_fwd(C.byref(p), _stream()))
+    return out, alpha
+
+
+def fusion_combine_bwd(dout: torch.Tensor, y: torch.Tensor, q: torch.Tensor, key: torch.Tensor, alpha: torch.Tensor, scale: float):
+    """→ (dy [K, rows, d] = α_k · dout, dq [rows, b], dkey [K, rows, b]), all bf16; the caller adds dkey_k · W_k to dy_k."""
+    _need(dout, BF16, "dout", 2)
+    _rows2d(dout, "dout")
+    kk, rows, d = y.shape
+    b = q.shape[1]
+    dy = torch.empty((kk, rows, d), dtype=BF16, device=y.device)
+    dq = torch.empty((rows, b), dtype=BF16, device=y.device)
+    dkey = torch.empty((kk, rows, b), dtype=BF16, device=y.device)
+    p = _fusion_params(y, q, key, alpha, scale)
+    p.dout, p.lddout = dout.data_ptr(), dout.stride(0)
+    p.dy, p.lddy, p.dy_stride = dy.data_ptr(), d, rows * d
+    p.dq, p.lddq = dq.data_ptr(), b
+    p.dkey, p.lddkey, p.dkey_stride = dkey.data_ptr(), b, rows * b
+    L.check(L.load().jl_fusion_combine_bwd(C.byref(p), _stream()))
+    return dy, dq, dkey
+
+
 # ----------------------------------------------------------------------------------------------- attention
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int, heads: int,
              scale: float, want_lse: bool = False, cu_seqlens: Optional[torch.Tensor] = None):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list of `bench.py --eager`: per-kernel time share of
-ONE fine-tune step (the launches between two consecutive fused-AdamW kernels).  Usage:
+ONE fine-tune step (the launches between two consecutive optimizer-clock kernels).  Usage:
     python scripts/summarize_launches.py gpurun_out/launches.csv [step_index] > profiles/<name>.md"""
 import collections
 import csv
@@ -19,9 +19,10 @@ def main():
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
     rows = list(csv.DictReader(lines))
-    idx = [i for i, r in enumerate(rows) if "adamw" in r["Kernel Name"]]
+    # a step starts with the optimizer-clock kernel (jl_adamw_advance, first launch of the step body)
+    idx = [i for i, r in enumerate(rows) if "adamw_advance" in r["Kernel Name"]]
     a, b = idx[which], idx[which + 1]
-    step = rows[a + 1: b + 1]
+    step = rows[a: b]
     tot = sum(float(r["Metric Value"]) for r in step)
     agg = collections.OrderedDict()
     for r in step:

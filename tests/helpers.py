@@ -66,6 +66,8 @@ def grad_tolerance(name: str, model, base: float = 3e-2, relu_path: float = 8e-2
         if slot in name:
             prefix, leaf = name.split(slot)
             mod = model.get_submodule(prefix + slot[:-1])
+            if leaf.startswith("source."):             # the source-dialect WFAdapter sets of a FusionAdapter
+                mod, leaf = mod.source, leaf[len("source."):]
             if getattr(mod, "kind", None) == "wf" and leaf in WF_RELU_PATH:
                 return relu_path
     return base
