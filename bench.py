@@ -598,7 +598,9 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps * 3, "gpu_launches_per_step": launches_per_step,
         "rtf": (t_res / args.steps) / audio_s_per_step, "loss": loss_val, "cuda_graph": not args.eager,
         "exchange": {"in_graph": trainer.exchange_in_graph, "overlapped_halves": trainer.overlap_exchange, "mode": trainer.flat.comm_mode,
-                     "bucket_bytes": trainer.flat.total * 4, "first_half_bytes": trainer.flat.split * 4},
+                     "bucket_bytes": trainer.flat.total * 4,
+                     "first_part_bytes": (trainer.flat.split_head if trainer.eng.defer_wgrads else trainer.flat.split) * 4,
+                     "adapter_wgrads": "deferred to the end of the backward pass (unsplit, concurrent)" if trainer.eng.defer_wgrads else "beside the main chain"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "inference": inference,
     }
     emit(line)

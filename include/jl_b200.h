@@ -165,6 +165,21 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream);
  * the dx part (jl_layernorm_bwd with dgamma = NULL) on the critical path and the weight gradients on a side stream */
 int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream);
 
+/* Several column reductions in one launch — what the weight-gradient branch of an adapter's backward pass needs: the bias
+ * gradients sum_r dy[r, :] of its projections (autograd's sum over rows of nn.Linear's grad_output) and the d gamma / d beta of its
+ * LayerNorm.  Per job: out_sum[c] = sum_r dy[r, c] and, when x != NULL, out_dot[c] = sum_r dy[r, c] * (x[r, c] - mean[r]) * rstd[r].
+ * Deterministic (fixed-order trees, no atomics).  cols, lddy, ldx multiples of 8. */
+#define JL_COLREDUCE_MAX_JOBS 4
+typedef struct {
+  const void* dy; int64_t lddy;       /* bf16 [rows, cols] */
+  const void* x; int64_t ldx;         /* bf16 [rows, cols] or NULL (plain column sum) */
+  const float* mean; const float* rstd;   /* [rows] fp32 (with x) */
+  int32_t rows, cols;
+  float* out_sum;                     /* [cols] fp32 or NULL */
+  float* out_dot;                     /* [cols] fp32 or NULL */
+} jl_colreduce_job;
+int jl_colreduce_multi(const jl_colreduce_job* jobs, int32_t num_jobs, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a6: WFAdapter forward in one kernel — LayerNorm + factorised down / up projections + bias / ReLU + residual.
  *   out = h + (relu((LN(h) B_d^T) A_d^T + c_d) B_u^T) A_u^T + c_u            (/root/reference/README.md:1;
@@ -386,7 +401,7 @@ void jl_debug_set_attn_impl(int impl);
 void jl_debug_set_gemm_mode(int mode);
 /* test / tuning hook: force the N tile (32/64/128/256 single-CTA kernel, 128/192/256 pair kernel with mode 2); 0 = automatic */
 void jl_debug_set_gemm_bn(int bn);
-/* test / tuning hook — what happens to the last, partial wave of output tiles (bit mask, default 2):
+/* test / tuning hook — what happens to the last, partial wave of output tiles (bit mask, default 2 | 4):
  *   bit 1 (2): single-CTA kernel: the tail tiles are cut into 2, 3 (96 + 96 + 64 columns of a 256-wide tile) or 4 column slices
  *              (independent, shorter work units);  bit 2 (4): never use the three-way cut;
  *   bit 0 (1): CTA-pair kernel: the tail tiles are cut into K ranges with an in-kernel fix-up (needs the workspace;

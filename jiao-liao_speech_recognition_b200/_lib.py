@@ -49,6 +49,11 @@ class LayerNormBwdParams(C.Structure):
                 ("partial", vp), ("rows", i32), ("d", i32)]
 
 
+class ColReduceJob(C.Structure):
+    _fields_ = [("dy", vp), ("lddy", i64), ("x", vp), ("ldx", i64), ("mean", vp), ("rstd", vp), ("rows", i32), ("cols", i32),
+                ("out_sum", vp), ("out_dot", vp)]
+
+
 class WFAdapterFwdParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("out", vp), ("ldo", i64), ("bd_scaled", vp), ("s", vp), ("t", vp), ("ad_pad", vp),
                 ("c_d", vp), ("bu", vp), ("au_pad", vp), ("c_u", vp), ("row_lengths", vp), ("rows_per_seq", i32),
@@ -113,6 +118,7 @@ SYMBOLS = {
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_layernorm_wgrad": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
+    "jl_colreduce_multi": (C.c_int, [C.POINTER(ColReduceJob), i32, vp]),
     "jl_wfadapter_fwd": (C.c_int, [C.POINTER(WFAdapterFwdParams), vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),

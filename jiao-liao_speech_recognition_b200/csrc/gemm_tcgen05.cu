@@ -941,7 +941,12 @@ static size_t splitk_ws_bytes(const jl_gemm_params* p) {
   return static_cast<size_t>(s) * p->m * ldw * sizeof(float);
 }
 
-static std::atomic<int> g_gemm_tail{2};   // bit 0: K-range split of the pair kernel's tail wave (needs a workspace; measured slower, off); bit 1: column slices of the single-CTA kernel's tail wave (on)
+// bit 0: K-range split of the pair kernel's tail wave (needs a workspace; measured slower, off); bit 1: column slices of the
+// single-CTA kernel's tail wave (on); bit 2: never cut a 256-wide tail tile three ways (96 + 96 + 64) — on: the three-way cut is
+// 1-2 % faster per GEMM timed alone (8000x768x3072: 37.0 → 36.8 us, 8000x768x768: 16.0 → 15.1) but 1.1 % SLOWER for the whole step
+// (6.36 vs 6.29 ms, three A/B jobs): with 123 instead of 82 CTAs busy in the tail wave the weight-gradient branch finds fewer
+// idle SMs and finishes later (without that branch the three-way cut wins: 6.04 vs 6.09 ms)
+static std::atomic<int> g_gemm_tail{2 | 4};
 static GemmDev to_dev(const jl_gemm_params* p, int bn) {
   GemmDev g;
   g.split_k = 1; g.kb_per_split = ceil_div(p->k, GEMM_BK); g.ws = nullptr; g.ldw = 0;

@@ -327,6 +327,105 @@ layernorm_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const
   ptx::cluster_sync_all();      // the partials of every CTA stay mapped until CTA 0 has read them
 }
 
+// Several column reductions in ONE launch (the weight-gradient branch of an adapter's backward pass needs three: the bias gradients
+// Σ_r dy[r, :] of its two projections and the dγ / dβ of its LayerNorm).  A job is Σ_r dy[r, c] (out_sum) and, when x is given,
+// Σ_r dy[r, c] · (x[r, c] − mean[r]) · rstd[r] (out_dot).  Same scheme as layernorm_wgrad_kernel — a cluster of 8 CTAs per 32
+// columns, fixed-order trees, the 8 partials added in rank order through distributed shared memory — but the clusters of all jobs
+// share one grid: 54 clusters instead of three launches of 6-24, and one launch latency instead of three.
+struct ColReduceDev {
+  jl_colreduce_job job[JL_COLREDUCE_MAX_JOBS];
+  int32_t first_cluster[JL_COLREDUCE_MAX_JOBS + 1];     // prefix sums of the jobs' cluster counts
+  int32_t num_jobs;
+};
+__global__ void __cluster_dims__(LNW_CLUSTER, 1, 1) __launch_bounds__(256) colreduce_multi_kernel(const ColReduceDev p) {
+  jl::pdl_prologue();
+  __shared__ float s_g[4][64][9], s_b[4][64][9];
+  __shared__ float s_part[2][LNW_COLS];
+  const int tid = threadIdx.x;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const int cluster = blockIdx.x / LNW_CLUSTER;
+  int ji = 0;
+  while (ji + 1 < p.num_jobs && cluster >= p.first_cluster[ji + 1]) ++ji;
+  const jl_colreduce_job& jb = p.job[ji];
+  const int grp = tid & 3, rix = tid >> 2;
+  const int col0 = (cluster - p.first_cluster[ji]) * LNW_COLS;
+  const int col = col0 + grp * 8;
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(jb.dy);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(jb.x);
+  const bool dot = x != nullptr;
+  const int rows = jb.rows;
+  float g[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { g[j] = 0.0f; b[j] = 0.0f; }
+  constexpr int STEP = LNW_CLUSTER * 64;
+  if (col < jb.cols) {
+    for (int r0 = rank * 64 + rix; r0 < rows; r0 += 4 * STEP) {
+      uint4 vy[4], vx[4];
+      float mu[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                 // four independent rows in flight per thread
+        const int r = min(r0 + STEP * u, rows - 1);
+        vy[u] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * jb.lddy + col));
+        if (dot) {
+          vx[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * jb.ldx + col));
+          mu[u] = __ldg(jb.mean + r);
+          rs[u] = __ldg(jb.rstd + r);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + STEP * u >= rows) break;
+        const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fy = unpack_bf16x2(wy[q]);
+          b[2 * q] += fy.x;
+          b[2 * q + 1] += fy.y;
+        }
+        if (dot) {
+          const uint32_t wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fy = unpack_bf16x2(wy[q]), fx = unpack_bf16x2(wx[q]);
+            g[2 * q] = fmaf(fy.x, (fx.x - mu[u]) * rs[u], g[2 * q]);
+            g[2 * q + 1] = fmaf(fy.y, (fx.y - mu[u]) * rs[u], g[2 * q + 1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_g[grp][rix][j] = g[j]; s_b[grp][rix][j] = b[j]; }
+  __syncthreads();
+  for (int stride = 32; stride >= 1; stride >>= 1) {
+    if (rix < stride) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s_g[grp][rix][j] += s_g[grp][rix + stride][j]; s_b[grp][rix][j] += s_b[grp][rix + stride][j]; }
+    }
+    __syncthreads();
+  }
+  if (tid < LNW_COLS) {
+    s_part[0][tid] = s_g[tid >> 3][0][tid & 7];
+    s_part[1][tid] = s_b[tid >> 3][0][tid & 7];
+  }
+  ptx::cluster_sync_all();
+  if (rank == 0 && tid < LNW_COLS) {
+    const int c = col0 + tid;
+    if (c < jb.cols) {
+      const uint32_t lg = ptx::smem_u32(&s_part[0][tid]), lb = ptx::smem_u32(&s_part[1][tid]);
+      float tg = 0.0f, tb = 0.0f;
+#pragma unroll
+      for (int q = 0; q < LNW_CLUSTER; ++q) {
+        tg += ptx::ld_shared_cluster_f32(ptx::mapa_shared(lg, static_cast<uint32_t>(q)));
+        tb += ptx::ld_shared_cluster_f32(ptx::mapa_shared(lb, static_cast<uint32_t>(q)));
+      }
+      if (jb.out_sum != nullptr) jb.out_sum[c] = tb;
+      if (dot && jb.out_dot != nullptr) jb.out_dot[c] = tg;
+    }
+  }
+  ptx::cluster_sync_all();      // the partials of every CTA stay mapped until CTA 0 has read them
+}
+
 static int ln_bwd_blocks(int rows) {
   int blocks = ceil_div(rows, LN_WARPS);
   return blocks < 296 ? blocks : 296;   // 2 CTAs per SM on 148 SMs
@@ -369,6 +468,32 @@ int jl_layernorm_wgrad(const jl_layernorm_bwd_params* p, void* stream) {
   jl::launch(jl::layernorm_wgrad_kernel, jl::ceil_div(p->d, jl::LNW_COLS) * jl::LNW_CLUSTER, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(p->dy),
              p->lddy, reinterpret_cast<const __nv_bfloat16*>(p->x), p->ldx, p->mean, p->rstd, p->rows, p->d, p->dgamma, p->dbeta);
   JL_CHECK_LAUNCH("layernorm_wgrad");
+  return JL_OK;
+}
+
+int jl_colreduce_multi(const jl_colreduce_job* jobs, int32_t num_jobs, void* stream) {
+  JL_REQUIRE(jobs != nullptr && num_jobs >= 1 && num_jobs <= JL_COLREDUCE_MAX_JOBS, JL_EINVAL, "colreduce_multi: 1..%d jobs", JL_COLREDUCE_MAX_JOBS);
+  jl::ColReduceDev d;
+  d.num_jobs = num_jobs;
+  int clusters = 0;
+  for (int i = 0; i < num_jobs; ++i) {
+    const jl_colreduce_job& j = jobs[i];
+    JL_REQUIRE(j.dy != nullptr && j.rows > 0 && j.cols > 0, JL_EINVAL, "colreduce_multi: job %d: null dy or empty shape", i);
+    JL_REQUIRE((j.cols & 7) == 0 && (j.lddy & 7) == 0 && (reinterpret_cast<uintptr_t>(j.dy) & 15) == 0, JL_EINVAL,
+               "colreduce_multi: job %d: cols / lddy must be multiples of 8 and dy 16-byte aligned", i);
+    if (j.x != nullptr)
+      JL_REQUIRE(j.mean && j.rstd && (j.ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(j.x) & 15) == 0, JL_EINVAL,
+                 "colreduce_multi: job %d: x needs mean, rstd, ldx %% 8 == 0 and 16-byte alignment", i);
+    JL_REQUIRE(j.out_sum != nullptr || (j.x != nullptr && j.out_dot != nullptr), JL_EINVAL, "colreduce_multi: job %d has no output", i);
+    d.job[i] = j;
+    d.first_cluster[i] = clusters;
+    clusters += jl::ceil_div(j.cols, jl::LNW_COLS);
+  }
+  for (int i = num_jobs; i <= JL_COLREDUCE_MAX_JOBS; ++i) d.first_cluster[i] = clusters;
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::colreduce_multi_kernel, clusters * jl::LNW_CLUSTER, 256, 0, reinterpret_cast<cudaStream_t>(stream), d);
+  JL_CHECK_LAUNCH("colreduce_multi");
   return JL_OK;
 }
 

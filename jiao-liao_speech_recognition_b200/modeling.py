@@ -33,6 +33,13 @@ _DEBUG_SKIP_SIDE = os.environ.get("JL_DEBUG_SKIP_SIDE") == "1"
 # where the dγ / dβ of a trainable adapter LayerNorm are computed: "side" = a kernel of its own on the weight-gradient branch
 # (re-reads dz and h), "main" = inside the LayerNorm backward kernel of the main chain (per-CTA partials + fixed-order reduce)
 _LN_WGRAD = os.environ.get("JL_LN_WGRAD", "side")
+# CUDA stream priority of the weight-gradient branch (0 = default, -1 = high: its kernel nodes outrank the main chain's when an SM frees up)
+_SIDE_PRIORITY = int(os.environ.get("JL_SIDE_PRIORITY", "0"))
+# the column reductions of an adapter's backward pass (bias gradients, LayerNorm dγ / dβ) as ONE launch (jl_colreduce_multi) instead
+# of one kernel each.  Measured on B200: 24 fewer launches per step but SLOWER (6.38 vs 6.29 ms; 20.0 vs 19.8 ms on the 24-layer
+# config) — the merged launch can only start when its last operand (dz) exists and then competes with the main chain as one large
+# grid, where the three small kernels slip into the gaps as their operands appear.  Off by default.
+_MERGED_REDUCE = os.environ.get("JL_MERGED_REDUCE", "0") == "1"
 
 
 def subsampled_length(n, num_convs: int = 2):
@@ -298,29 +305,62 @@ class _State:
 
 
 class _SideBranch:
-    """Weight-gradient products do not feed the dX chain, so the backward pass issues them on a second stream: inside
-    the captured CUDA graph they become parallel branches that fill the SMs the (latency-bound) main chain leaves idle.
-    Tensors a branch reads are kept alive until ``join`` so the caching allocator cannot recycle them early."""
+    """Weight-gradient products do not feed the dX chain.  Two ways to keep them off the critical path:
 
-    def __init__(self, enabled: bool = True, stream: Optional["torch.cuda.Stream"] = None):
+    * ``defer=False`` — issue each on a second stream as soon as its operands exist: inside the captured CUDA graph they become
+      parallel branches beside the main chain.  Measured cost on B200: the main chain's persistent GEMMs occupy every SM (128
+      registers x 512 threads), so a branch kernel only ever runs in the gaps, and the ~86 small launches of a step (split-K
+      products + their reduce kernels, column sums, LayerNorm dγ/dβ) cost the step 3-5 % (profiles/README.md, round 2).
+    * ``defer=True`` — collect them and issue them all after the main chain's last kernel, round-robin over a pool of
+      streams: every product then runs UNSPLIT on its few CTAs (K = all B·T' rows) with the products of all layers in flight at the
+      same time — no split-K partials, no reduce kernels — at the price of an exposed tail.  Measured SLOWER (6.42 vs 6.33 ms on
+      the headline config, 20.3 vs 19.8 ms on the 24-layer config): the unsplit K = 8000 products take ~40 µs each on their few
+      CTAs and the tail is longer than what the overlap costs.  Kept as an option (``engine.defer_wgrads``), off by default.
+
+    ``now=True`` issues immediately in both modes (the lm_head gradient, which the first half of the gradient exchange waits
+    for).  Tensors a branch reads are kept alive until ``join`` so the caching allocator cannot recycle them early."""
+
+    def __init__(self, enabled: bool = True, stream: Optional["torch.cuda.Stream"] = None, defer: bool = False, pool=None):
         self.enabled = enabled
         self.side = (stream if stream is not None else torch.cuda.Stream()) if enabled else None
+        self.defer_mode = defer and enabled
+        self.pool = pool or []
+        self.deferred = []
         self.keep = []
 
-    def run(self, fn, *tensors) -> None:
+    def run(self, fn, *tensors, now: bool = False) -> None:
         if _DEBUG_SKIP_SIDE:          # timing experiment only (wrong gradients): what the weight-gradient branch costs the step
             return
         if not self.enabled:
             fn()
             return
         self.keep.extend(tensors)
+        if self.defer_mode and not now:
+            self.deferred.append(fn)
+            return
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             fn()
 
     def join(self) -> None:
-        if self.enabled:
-            torch.cuda.current_stream().wait_stream(self.side)
+        if self.enabled and not _DEBUG_SKIP_SIDE:
+            main = torch.cuda.current_stream()
+            if self.deferred:
+                streams = self.pool if self.pool else [self.side]
+                used = streams[: min(len(streams), len(self.deferred))]
+                for st in used:
+                    st.wait_stream(main)
+                ops.GEMM_NO_SPLIT = True          # each product keeps its whole K on its own few CTAs: all layers run side by side
+                try:
+                    for i, fn in enumerate(self.deferred):
+                        with torch.cuda.stream(used[i % len(used)]):
+                            fn()
+                finally:
+                    ops.GEMM_NO_SPLIT = False
+                for st in used:
+                    main.wait_stream(st)
+                self.deferred = []
+            main.wait_stream(self.side)
         self.keep.clear()
 
 
@@ -339,6 +379,10 @@ class JLEngine:
         self._pos: Dict[Tuple[str, int], torch.Tensor] = {}
         self.flat = None   # set by training.FlatAdapterParams
         self.side_branch = True   # issue weight-gradient products on a second stream (parallel graph branches)
+        # adapter weight gradients: all at the end of the backward pass, unsplit and concurrent (True), or each as soon as its
+        # operands exist, beside the main chain (False) — see _SideBranch
+        self.defer_wgrads = os.environ.get("JL_DEFER_WGRADS", "0") == "1"     # measured slower on B200 (profiles/README.md): off
+        self._side_pools: Dict[int, list] = {}
         self._side_streams: Dict[int, "torch.cuda.Stream"] = {}   # one side stream per device, created once
         self.fused_wf = True      # inference: WFAdapter as one kernel (jl_wfadapter_fwd)
 
@@ -346,9 +390,17 @@ class JLEngine:
         idx = device.index if device.index is not None else torch.cuda.current_device()
         st = self._side_streams.get(idx)
         if st is None:
-            st = torch.cuda.Stream(device=idx)
+            st = torch.cuda.Stream(device=idx, priority=_SIDE_PRIORITY)
             self._side_streams[idx] = st
         return st
+
+    def _side_pool(self, device, n: int = 8) -> list:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        pool = self._side_pools.get(idx)
+        if pool is None:
+            pool = [torch.cuda.Stream(device=idx) for _ in range(n)]
+            self._side_pools[idx] = pool
+        return pool
 
     # ------------------------------------------------------------------ weights
     def weights_version(self, include_optimizer_steps: bool = True) -> int:
@@ -678,24 +730,31 @@ class JLEngine:
         dh, _, _ = ops.layernorm_bwd(dzs, h, src.norm.weight.detach(), mean_s, rstd_s, dres=dh)
         return dh
 
-    def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch") -> None:
+    def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch", jobs: Optional[list] = None) -> None:
         """Backward of the WFAdapter projections for the utterances of dialect ``k`` (a row slice): weight gradients of
-        factor set k on the side branch, dz[rows] = gradient at the adapter's LayerNorm output."""
+        factor set k on the side branch, dz[rows] = gradient at the adapter's LayerNorm output.  With ``jobs`` the bias-gradient
+        column sums are appended to it (for one merged launch by the caller) instead of being launched here."""
         MN = L.JL_LAYOUT_MN
         dy, z, t1, u, t2 = dy[rows], z[rows], t1[rows], u[rows], t2[rows]
 
         def w_up():
             ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)             # dyᵀ · t2
-            ops.colsum(dy, out=g.out(ad.up_bias, k))
+            if jobs is None:
+                ops.colsum(dy, out=g.out(ad.up_bias, k))
         sb.run(w_up, dy, t2)
+        if jobs is not None:
+            jobs.append(dict(dy=dy, out_sum=g.out(ad.up_bias, k)))
         dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
         sb.run(lambda: ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32), dt2, u)   # dt2ᵀ · u
         dpre = ops.gemm(dt2, self._bf16(ad.up_B)[k], b_layout=MN, epilogue=L.JL_EPI_RELU_BWD, aux=u)      # (dt2 · B_u) ∘ relu'
 
         def w_down():
-            ops.colsum(dpre, out=g.out(ad.down_bias, k))
+            if jobs is None:
+                ops.colsum(dpre, out=g.out(ad.down_bias, k))
             ops.gemm(dpre, t1, a_layout=MN, b_layout=MN, out=g.out(ad.down_A, k), out_dtype=F32)          # dpreᵀ · t1
         sb.run(w_down, dpre, t1)
+        if jobs is not None:
+            jobs.append(dict(dy=dpre, out_sum=g.out(ad.down_bias, k)))
         dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
         sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
         ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                                # dt1 · B_d
@@ -712,12 +771,13 @@ class JLEngine:
             h, mean, rstd, z, t1, u, t2, segs = saved
             dz = torch.empty_like(h)
             present = set()
+            jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
             for k, b0, b1 in segs:
                 rows = self._seg_rows(b0, b1, t, pk)
                 if rows.stop == rows.start:
                     continue
                 present.add(k)
-                self._wf_bwd_rows(ad, k, rows, dy, z, t1, u, t2, dz, g, sb)
+                self._wf_bwd_rows(ad, k, rows, dy, z, t1, u, t2, dz, g, sb, jobs)
             for k in range(ad.num_dialects):           # factor sets without utterances in this batch: zero gradient
                 if k not in present:
                     for prm in (ad.up_A, ad.up_bias, ad.up_B, ad.down_A, ad.down_bias, ad.down_B):
@@ -725,28 +785,50 @@ class JLEngine:
         else:
             h, mean, rstd, z, qkv, a, lse = saved
 
+            jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
+
             def w_o():
                 ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)         # dyᵀ · a
-                ops.colsum(dy, out=g.out(ad.o_proj.bias))
+                if jobs is None:
+                    ops.colsum(dy, out=g.out(ad.o_proj.bias))
             sb.run(w_o, dy, a)
+            if jobs is not None:
+                jobs.append(dict(dy=dy, out_sum=g.out(ad.o_proj.bias)))
             da = ops.gemm(dy, self._bf16(ad.o_proj.weight), b_layout=MN)                                      # dy · W_o
             dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0, cu_seqlens=cu)
             ws = [ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight]
             bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
 
+            gb_cat = g.out_cat(bs)
+
             def w_qkv():
-                gw, gb = g.out_cat(ws), g.out_cat(bs)
+                gw = g.out_cat(ws)
                 ops.gemm(dqkv, z, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                            # dqkvᵀ · z
-                ops.colsum(dqkv, out=gb)
                 g.scatter_cat(ws, gw)
-                g.scatter_cat(bs, gb)
+                if jobs is None:
+                    ops.colsum(dqkv, out=gb_cat)
+                    g.scatter_cat(bs, gb_cat)
             sb.run(w_qkv, dqkv, z)
+            if jobs is not None:
+                jobs.append(dict(dy=dqkv, out_sum=gb_cat, scatter=(bs, gb_cat)))
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
         if _LN_WGRAD == "main":
             dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True, dgamma=g.out(ad.norm.weight),
                                          dbeta=g.out(ad.norm.bias))
             return dh
-        sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
+        if jobs is not None:
+            # one launch for every column reduction of this adapter: its bias gradients and the dγ / dβ of its LayerNorm
+            jobs.append(dict(dy=dz, x=h, mean=mean, rstd=rstd, out_sum=g.out(ad.norm.bias), out_dot=g.out(ad.norm.weight)))
+
+            def reduce_all(jobs=jobs):
+                for i in range(0, len(jobs), 4):
+                    ops.colreduce_multi(jobs[i:i + 4])
+                for j in jobs:
+                    if "scatter" in j:
+                        g.scatter_cat(*j["scatter"])
+            sb.run(reduce_all, dz, h, mean, rstd, *[j["dy"] for j in jobs])
+        else:
+            sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
         dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy)
         return dh
 
@@ -912,14 +994,15 @@ class JLEngine:
         lengths = st.lengths
         pk = getattr(st, "packed", None)
         cu = None if pk is None else pk.cu
-        sb = _SideBranch(enabled=self.side_branch, stream=self._side_stream(dlogits.device) if self.side_branch else None)
+        sb = _SideBranch(enabled=self.side_branch, stream=self._side_stream(dlogits.device) if self.side_branch else None,
+                         defer=self.defer_wgrads, pool=self._side_pool(dlogits.device) if (self.side_branch and self.defer_wgrads) else None)
         g.prepare(self)      # sinks that allocate do so here, on the main stream (the side branch only writes into them)
 
         # head: logits = h_final · Wᵀ + b
         def w_head():
             ops.gemm(dlogits, st.h_final, a_layout=MN, b_layout=MN, out=g.out(self.lm_head.weight), out_dtype=F32)   # dlogitsᵀ · h_final
             ops.colsum(dlogits, out=g.out(self.lm_head.bias))
-        sb.run(w_head, dlogits, st.h_final)
+        sb.run(w_head, dlogits, st.h_final, now=True)
         l0 = self.lowest_adapter_layer()
         if l0 >= len(self.enc.layers):
             sb.join()
@@ -930,7 +1013,7 @@ class JLEngine:
         for i in range(len(self.enc.layers) - 1, l0 - 1, -1):
             layer, sv = self.enc.layers[i], st.layers[i]
             if on_progress is not None:
-                on_progress(i, sb.side)
+                on_progress(i, None if _DEBUG_SKIP_SIDE else sb.side)
             if layer.adapter_ffn is not None:
                 dh = self._adapter_bwd(layer.adapter_ffn, sv.ad_ffn, dh, lengths, b, t, g, sb, pk=pk)
                 if i == l0 and layer.adapter_attn is None:

@@ -18,6 +18,9 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 # When set to a list, every gemm() call appends (params, kept-alive tensors, 2·M·N·K): bench.py replays the list to
 # time the step's tensor-core launches on their own (roofline of the dominant kernel).
 GEMM_TRACE = None
+# True while the deferred weight-gradient products of a backward pass are being issued (modeling._SideBranch.join): split-K is off,
+# every product keeps its whole K range on its own CTAs and the products of all layers run concurrently on a pool of streams.
+GEMM_NO_SPLIT = False
 
 
 def _stream() -> int:
@@ -125,7 +128,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         raise TypeError("gemm: out must be bf16 or fp32")
     lib = L.load()
     ws = None
-    if not reference:
+    if not reference and not GEMM_NO_SPLIT:
         nbytes, zbytes = C.c_size_t(0), C.c_size_t(0)
         L.check(lib.jl_gemm_workspace_bytes(C.byref(p), C.byref(nbytes)))
         if nbytes.value:
@@ -253,6 +256,34 @@ def layernorm_wgrad(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd:
                              rstd=rstd.data_ptr(), dres=None, lddres=0, dx=None, lddx=0, dgamma=dgamma.data_ptr(), dbeta=_ptr(dbeta),
                              partial=None, rows=rows, d=d)
     L.check(L.load().jl_layernorm_wgrad(C.byref(p), _stream()))
+
+
+def colreduce_multi(jobs) -> None:
+    """Up to 4 column reductions in one launch.  Each job is a dict: ``dy`` [rows, cols] bf16, ``out_sum`` [cols] fp32 (Σ_r dy) and /
+    or — with ``x`` [rows, cols] bf16, ``mean``, ``rstd`` [rows] fp32 — ``out_dot`` [cols] fp32 (Σ_r dy · (x − mean) · rstd)."""
+    if not 1 <= len(jobs) <= 4:
+        raise ValueError("colreduce_multi: 1..4 jobs")
+    arr = (L.ColReduceJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        dy = j["dy"]
+        _need(dy, BF16, "dy")
+        _rows2d(dy, "dy")
+        x = j.get("x")
+        if x is not None:
+            _need(x, BF16, "x")
+            _rows2d(x, "x")
+            if x.shape != dy.shape:
+                raise ValueError("colreduce_multi: x and dy must have the same shape")
+        for nm in ("out_sum", "out_dot"):
+            o = j.get(nm)
+            if o is not None:
+                _need(o, F32, nm, 1)
+                if o.numel() != dy.shape[1] or not o.is_contiguous():
+                    raise ValueError(f"colreduce_multi: {nm} must be a contiguous fp32 vector of {dy.shape[1]} elements")
+        arr[i] = L.ColReduceJob(dy=dy.data_ptr(), lddy=dy.stride(0), x=_ptr(x), ldx=0 if x is None else x.stride(0), mean=_ptr(j.get("mean")),
+                                rstd=_ptr(j.get("rstd")), rows=dy.shape[0], cols=dy.shape[1], out_sum=_ptr(j.get("out_sum")),
+                                out_dot=_ptr(j.get("out_dot")))
+    L.check(L.load().jl_colreduce_multi(arr, len(jobs), _stream()))
 
 
 # ----------------------------------------------------------------------------------------------- fused WFAdapter

@@ -53,6 +53,7 @@ def ordered_trainables(model: JLForCTC, return_split: bool = False):
 
     for p in model.lm_head.parameters():
         add(p)
+    head_idx = len(out)
     layers = list(model.encoder.layers)
     split_layer = len(layers) // 2
     split_idx = None
@@ -65,7 +66,7 @@ def ordered_trainables(model: JLForCTC, return_split: bool = False):
         add(p)
     if split_idx is None:
         split_idx = len(out)
-    return (out, split_idx, split_layer) if return_split else out
+    return (out, split_idx, split_layer, head_idx) if return_split else out
 
 
 class BucketLayout:
@@ -111,7 +112,7 @@ class FlatAdapterParams(GradSink):
     def __init__(self, model: JLForCTC):
         super().__init__()
         self.model = model
-        self.plist, split_idx, self.split_layer = ordered_trainables(model, return_split=True)
+        self.plist, split_idx, self.split_layer, head_idx = ordered_trainables(model, return_split=True)
         if not self.plist:
             raise ValueError("no trainable parameters: call model.freeze_base_model() first")
         dev = self.plist[0].device
@@ -122,6 +123,9 @@ class FlatAdapterParams(GradSink):
         self.total, self.num_params = self.layout.total, self.layout.num_params
         # element offset where the second half of the bucket (adapters of the layers below split_layer) starts
         self.split = self.layout.offset[id(self.plist[split_idx])] if split_idx < len(self.plist) else self.total
+        # ... and where the adapters start (lm_head comes first): the split used when the adapter weight gradients are deferred to
+        # the end of the backward pass — lm_head's gradient (the bulk of the bucket) is exchanged under the whole backward pass
+        self.split_head = self.layout.offset[id(self.plist[head_idx])] if head_idx < len(self.plist) else self.total
         off = self.total
         self.param = torch.zeros(off, dtype=F32, device=dev)
         self.grad = torch.zeros(off, dtype=F32, device=dev)
@@ -383,11 +387,16 @@ class AdapterTrainer:
                                            zero_infinity=self.cfg.ctc_zero_infinity, want_grad=True, grad_dtype=BF16,
                                            cu_seqlens=pk.cu, max_len=pk.seq_bound)
         state = {"first_done": False}
-        split_layer, split = f.split_layer, f.split
+        if self.eng.defer_wgrads and self.eng.side_branch:
+            # adapter weight gradients are issued after the main chain: the first part of the exchange is lm_head's gradient
+            # (complete right after the head's products at the top of the backward pass), the second part every adapter's
+            split_layer, split = len(self.model.encoder.layers), f.split_head
+        else:
+            split_layer, split = f.split_layer, f.split
 
         def progress(i, side):
-            # layers above i are done: once the upper half of the stack is, its half of the bucket (lm_head + adapters of the
-            # layers >= split_layer) is complete as soon as the weight-gradient branch has drained
+            # layers above i are done: once the upper part of the stack is, its part of the bucket (lm_head [+ adapters of the
+            # layers >= split_layer]) is complete as soon as the weight-gradient branch has drained
             if update and self.overlap_exchange and not state["first_done"] and i == split_layer - 1 and 0 < split < f.total:
                 state["first_done"] = True
                 if side is not None:

@@ -73,7 +73,7 @@ def grad_tolerance(name: str, model, base: float = 3e-2, relu_path: float = 8e-2
     return base
 
 
-def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None, record=None):
+def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None, record=None, relu_path: float = 8e-2):
     """Every adapter / lm_head gradient of ``model`` against ``ref_grad_of(name)`` (the oracle's): relative Frobenius error <=
     grad_tolerance(name); the analytically-zero AttAdapter key-bias gradient is compared with the query-bias gradient's norm.
     Returns {name: relative error} and the worst (name, error) among the gradients held to ``base``.  ``record(errs)`` is called
@@ -95,7 +95,7 @@ def assert_grads_match(model, ref_grad_of, base: float = 3e-2, grads=None, recor
             qn = norms[name.replace("k_proj.bias", "q_proj.bias")][1]
             assert err <= base * qn + 1e-7, f"grad {name}: |err| {err:.3e} vs q_proj.bias grad norm {qn:.3e}"
             continue
-        tol = grad_tolerance(name, model, base)
+        tol = grad_tolerance(name, model, base, relu_path)
         assert err <= tol * refn + 2e-6 * numel ** 0.5, f"grad {name}: rel {errs[name]:.3e} (err {err:.3e}, ref norm {refn:.3e}), tolerance {tol}"
         if tol == base and refn > 1e-4 * numel ** 0.5 and errs[name] > worst[1]:
             worst = (name, errs[name])

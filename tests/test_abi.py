@@ -37,6 +37,7 @@ STRUCTS = {
     "jl_ctc_greedy_params": "CtcGreedyParams",
     "jl_adamw_params": "AdamWParams",
     "jl_fusion_params": "FusionParams",
+    "jl_colreduce_job": "ColReduceJob",
 }
 
 

