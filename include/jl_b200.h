@@ -202,8 +202,23 @@ typedef struct {
   float* mean; float* rstd;         /* optional fp32 [rows] LayerNorm statistics out */
   int32_t rows, d, r, b;
   float eps;
+  /* training: the intermediates the backward pass needs, written by the same launch (all optional, bf16, contiguous rows):
+   * t1 = LN(h) B_d^T [rows, r], u = relu(t1 A_d^T + c_d) [rows, b], t2 = u B_u^T [rows, r] */
+  void* t1_out; void* u_out; void* t2_out;
 } jl_wfadapter_fwd_params;
 int jl_wfadapter_fwd(const jl_wfadapter_fwd_params* p, void* stream);
+/* The operands jl_wfadapter_fwd reads, derived from the adapter's parameters ON THE DEVICE (so that a captured training step
+ * re-derives them from the freshly updated factors at every replay): for each of the `sets` dialect factor sets
+ *   bd_scaled = bf16(B_d * gamma) [r, d],  s[j] = sum_k bd_scaled[j, k],  t[j] = sum_k B_d[j, k] * beta[k],
+ *   ad_pad = A_d zero-padded to [b, 64],  au_pad = A_u zero-padded to [d, 64].
+ * down_B [sets, r, d], down_A [sets, b, r], up_A [sets, d, r]: bf16 (the shadow copies the GEMMs read); gamma, beta: fp32 [d]. */
+typedef struct {
+  const void* down_B; const void* down_A; const void* up_A;
+  const float* gamma; const float* beta;
+  void* bd_scaled; float* s; float* t; void* ad_pad; void* au_pad;     /* outputs, [sets, ...] */
+  int32_t sets, d, r, b;
+} jl_wfadapter_pack_params;
+int jl_wfadapter_pack(const jl_wfadapter_pack_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;

@@ -57,7 +57,13 @@ class ColReduceJob(C.Structure):
 class WFAdapterFwdParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("out", vp), ("ldo", i64), ("bd_scaled", vp), ("s", vp), ("t", vp), ("ad_pad", vp),
                 ("c_d", vp), ("bu", vp), ("au_pad", vp), ("c_u", vp), ("row_lengths", vp), ("rows_per_seq", i32),
-                ("mean", vp), ("rstd", vp), ("rows", i32), ("d", i32), ("r", i32), ("b", i32), ("eps", f32)]
+                ("mean", vp), ("rstd", vp), ("rows", i32), ("d", i32), ("r", i32), ("b", i32), ("eps", f32),
+                ("t1_out", vp), ("u_out", vp), ("t2_out", vp)]
+
+
+class WFAdapterPackParams(C.Structure):
+    _fields_ = [("down_B", vp), ("down_A", vp), ("up_A", vp), ("gamma", vp), ("beta", vp), ("bd_scaled", vp), ("s", vp), ("t", vp),
+                ("ad_pad", vp), ("au_pad", vp), ("sets", i32), ("d", i32), ("r", i32), ("b", i32)]
 
 
 class FusionParams(C.Structure):
@@ -120,6 +126,7 @@ SYMBOLS = {
     "jl_layernorm_wgrad": (C.c_int, [C.POINTER(LayerNormBwdParams), vp]),
     "jl_colreduce_multi": (C.c_int, [C.POINTER(ColReduceJob), i32, vp]),
     "jl_wfadapter_fwd": (C.c_int, [C.POINTER(WFAdapterFwdParams), vp]),
+    "jl_wfadapter_pack": (C.c_int, [C.POINTER(WFAdapterPackParams), vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),

@@ -61,6 +61,14 @@ __device__ __forceinline__ void wf_store_chunk(uint8_t* tile, int r, int c, cons
   *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
+// training: 32 columns (first column col0) of an intermediate's row → global memory, 8 columns per 16-byte store; `width` = r or b
+__device__ __forceinline__ void wf_save_cols32(void* base, int64_t row, int width, int col0, const uint32_t (&pk)[16]) {
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base) + row * width + col0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (col0 + c * 8 < width) reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
 __global__ void __launch_bounds__(WF_THREADS, 1)
 wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_constant__ CUtensorMap t_bd, const __grid_constant__ CUtensorMap t_ad,
                      const __grid_constant__ CUtensorMap t_bu, const __grid_constant__ CUtensorMap t_au, const jl_wfadapter_fwd_params p) {
@@ -234,6 +242,7 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
         const uint32_t q4[4] = {pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]};
         wf_store_chunk(s.t, r, hh * 4 + c, q4);
       }
+      if (p.t1_out != nullptr && row < p.rows && hh * 32 < p.r) wf_save_cols32(p.t1_out, row, p.r, hh * 32, pk);
     }
     ptx::tc_fence_before();
     ptx::fence_proxy_async();
@@ -259,6 +268,7 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
         const uint32_t q4[4] = {pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]};
         wf_store_chunk(s.hs[cc >> 1], r, (cc & 1) * 4 + c, q4);
       }
+      if (p.u_out != nullptr && row < p.rows) wf_save_cols32(p.u_out, row, p.b, cc * 32, pk);
     }
     ptx::tc_fence_before();
     ptx::fence_proxy_async();
@@ -288,6 +298,7 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
         const uint32_t q4[4] = {pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]};
         wf_store_chunk(s.t, r, hh * 4 + c, q4);
       }
+      if (p.t2_out != nullptr && row < p.rows && hh * 32 < p.r) wf_save_cols32(p.t2_out, row, p.r, hh * 32, pk);
     }
     ptx::tc_fence_before();
     ptx::fence_proxy_async();
@@ -353,9 +364,58 @@ wfadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_const
   }
 }
 
+// Operand packing on the device (see jl_wfadapter_pack): one CTA per (factor-set, rank row j) for B_d' = B_d ⊙ γ with its row sums
+// s, t; the zero-padded copies of A_d / A_u by a grid-stride loop of the same grid.
+__global__ void __launch_bounds__(256) wfadapter_pack_kernel(const jl_wfadapter_pack_params p) {
+  jl::pdl_prologue();
+  __shared__ float red_s[8], red_t[8];
+  const int k = blockIdx.y, j = blockIdx.x;            // j < r
+  const __nv_bfloat16* bd = reinterpret_cast<const __nv_bfloat16*>(p.down_B) + (static_cast<int64_t>(k) * p.r + j) * p.d;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.bd_scaled) + (static_cast<int64_t>(k) * p.r + j) * p.d;
+  float ss = 0.0f, tt = 0.0f;
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    const float w = __bfloat162float(bd[c]);
+    const __nv_bfloat16 ws = __float2bfloat16_rn(w * __ldg(p.gamma + c));
+    out[c] = ws;
+    ss += __bfloat162float(ws);                          // the sum of what the tensor core will actually multiply by
+    tt = fmaf(w, __ldg(p.beta + c), tt);
+  }
+  ss = warp_sum(ss);
+  tt = warp_sum(tt);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = ss; red_t[threadIdx.x >> 5] = tt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, b = 0.0f;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += red_s[w]; b += red_t[w]; }     // fixed order
+    p.s[k * p.r + j] = a;
+    p.t[k * p.r + j] = b;
+  }
+  // zero-padded [rows, 64] copies of A_d [b, r] and A_u [d, r] of factor set k
+  const int tid = j * blockDim.x + threadIdx.x, nthr = p.r * blockDim.x;
+  const __nv_bfloat16* ad = reinterpret_cast<const __nv_bfloat16*>(p.down_A) + static_cast<int64_t>(k) * p.b * p.r;
+  const __nv_bfloat16* au = reinterpret_cast<const __nv_bfloat16*>(p.up_A) + static_cast<int64_t>(k) * p.d * p.r;
+  __nv_bfloat16* adp = reinterpret_cast<__nv_bfloat16*>(p.ad_pad) + static_cast<int64_t>(k) * p.b * 64;
+  __nv_bfloat16* aup = reinterpret_cast<__nv_bfloat16*>(p.au_pad) + static_cast<int64_t>(k) * p.d * 64;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.0f);
+  for (int i = tid; i < p.b * 64; i += nthr) adp[i] = ((i & 63) < p.r) ? ad[(i >> 6) * p.r + (i & 63)] : zero;
+  for (int i = tid; i < p.d * 64; i += nthr) aup[i] = ((i & 63) < p.r) ? au[(i >> 6) * p.r + (i & 63)] : zero;
+}
+
 }  // namespace jl
 
 extern "C" {
+
+int jl_wfadapter_pack(const jl_wfadapter_pack_params* p, void* stream) {
+  JL_REQUIRE(p != nullptr, JL_EINVAL, "wfadapter_pack: null params");
+  JL_REQUIRE(p->down_B && p->down_A && p->up_A && p->gamma && p->beta && p->bd_scaled && p->s && p->t && p->ad_pad && p->au_pad, JL_EINVAL,
+             "wfadapter_pack: null pointer");
+  JL_REQUIRE(p->sets >= 1 && p->d > 0 && p->r >= 1 && p->r <= 64 && p->b >= 1, JL_EINVAL, "wfadapter_pack: bad dims (1 <= r <= 64)");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::wfadapter_pack_kernel, dim3(p->r, p->sets), 256, 0, reinterpret_cast<cudaStream_t>(stream), *p);
+  JL_CHECK_LAUNCH("wfadapter_pack");
+  return JL_OK;
+}
 
 int jl_wfadapter_fwd(const jl_wfadapter_fwd_params* p, void* stream) {
   JL_REQUIRE(p != nullptr, JL_EINVAL, "wfadapter_fwd: null params");

@@ -385,6 +385,12 @@ class JLEngine:
         self._side_pools: Dict[int, list] = {}
         self._side_streams: Dict[int, "torch.cuda.Stream"] = {}   # one side stream per device, created once
         self.fused_wf = True      # inference: WFAdapter as one kernel (jl_wfadapter_fwd)
+        # training: the same kernel, which then also writes the intermediates the backward pass needs (t1, u, t2, LayerNorm
+        # statistics); its LayerNorm-folded operands are re-derived on the device at every step (jl_wfadapter_pack).  Parity-tested,
+        # but measured no faster than LN + 4 GEMMs on B200 (24-layer config 19.96 vs 20.02 ms; mixed-length config with four dialect
+        # runs per layer 15.49 vs 15.15 ms: one CTA per SM and a four-stage dependency chain per 128 rows) — off by default.
+        self.fused_wf_train = os.environ.get("JL_FUSED_WF_TRAIN", "0") == "1"
+        self._wf_bufs: Dict[int, dict] = {}
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -546,6 +552,14 @@ class JLEngine:
         self._shadow[key] = (ver, None, pack)
         return pack
 
+    def _wf_pack_dev(self, ad) -> dict:
+        """Kernel-layout operands of every factor set of ``ad``, derived ON THE DEVICE from the bf16 shadows by one launch into
+        buffers that keep their addresses — inside a captured training step they follow the optimizer's updates at every replay."""
+        bufs = ops.wfadapter_pack(self._bf16(ad.down_B), self._bf16(ad.down_A), self._bf16(ad.up_A), ad.norm.weight.detach(),
+                                  ad.norm.bias.detach(), self._wf_bufs.get(id(ad)))
+        self._wf_bufs[id(ad)] = bufs
+        return bufs
+
     def pos_table(self, device, rows: int) -> torch.Tensor:
         key = (str(device), self.cfg.hidden_size)
         tab = self._pos.get(key)
@@ -625,6 +639,27 @@ class JLEngine:
                 ops.wfadapter_fwd(h[rows], self._wf_pack(ad, k), eps, row_lengths=lengths[b0:b1] if zero_rows else None,
                                   rows_per_seq=t if zero_rows else 0, out=out[rows])
             return out, None
+        if ad.kind == "wf" and training and self.fused_wf_train and self._wf_fusable(ad):
+            # training: one kernel per dialect run as well; it also writes t1, u, t2 and the LayerNorm statistics.  LN(h) itself is
+            # only needed by one weight-gradient product and is recomputed on the weight-gradient branch (``_adapter_bwd``).
+            m, dev = h.shape[0], h.device
+            bufs = self._wf_pack_dev(ad)
+            bu16 = self._bf16(ad.up_B)
+            mean = torch.empty((m,), dtype=F32, device=dev)
+            rstd = torch.empty((m,), dtype=F32, device=dev)
+            t1 = torch.empty((m, ad.rank), dtype=BF16, device=dev)
+            u = torch.empty((m, ad.bottleneck), dtype=BF16, device=dev)
+            t2 = torch.empty((m, ad.rank), dtype=BF16, device=dev)
+            out = torch.empty_like(h)
+            for k, b0, b1 in segs:
+                rows = self._seg_rows(b0, b1, t, pk)
+                if rows.stop == rows.start:
+                    continue
+                pack = {"bd": bufs["bd"][k], "s": bufs["s"][k], "t": bufs["t"][k], "ad": bufs["ad"][k], "au": bufs["au"][k], "bu": bu16[k],
+                        "c_d": ad.down_bias.detach()[k], "c_u": ad.up_bias.detach()[k], "r": ad.rank, "b": ad.bottleneck}
+                ops.wfadapter_fwd(h[rows], pack, eps, row_lengths=lengths[b0:b1] if zero_rows else None, rows_per_seq=t if zero_rows else 0,
+                                  out=out[rows], mean=mean[rows], rstd=rstd[rows], t1=t1[rows], u=u[rows], t2=t2[rows])
+            return out, (h, mean, rstd, None, t1, u, t2, segs)
         z, mean, rstd = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), eps, save_stats=training)
         rl = dict(row_lengths=lengths, rows_per_seq=t) if zero_rows else {}
         if ad.kind == "wf":
@@ -769,6 +804,11 @@ class JLEngine:
             return self._fusion_bwd(ad, saved, dy, g, sb)
         if ad.kind == "wf":
             h, mean, rstd, z, t1, u, t2, segs = saved
+            if z is None:
+                # the fused forward kernel never wrote LN(h); only dB_d = dt1ᵀ · LN(h) needs it: recompute it on the weight-gradient
+                # branch (the buffer is allocated here, on the main stream; the branch only writes into it)
+                z = torch.empty_like(h)
+                sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
             dz = torch.empty_like(h)
             present = set()
             jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None

@@ -288,8 +288,12 @@ def colreduce_multi(jobs) -> None:
 
 # ----------------------------------------------------------------------------------------------- fused WFAdapter
 def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional[torch.Tensor] = None, rows_per_seq: int = 0,
-                  save_stats: bool = False, out: Optional[torch.Tensor] = None):
-    """out = h + WFAdapter(h) in one kernel.  ``pack`` holds the kernel-layout factors (see modeling.JLEngine._wf_pack)."""
+                  save_stats: bool = False, out: Optional[torch.Tensor] = None, mean: Optional[torch.Tensor] = None,
+                  rstd: Optional[torch.Tensor] = None, t1: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None,
+                  t2: Optional[torch.Tensor] = None):
+    """out = h + WFAdapter(h) in one kernel.  ``pack`` holds the kernel-layout factors (``wfadapter_pack`` /
+    modeling.JLEngine._wf_pack).  Training: ``mean`` / ``rstd`` [rows] fp32 and ``t1`` [rows, r], ``u`` [rows, b], ``t2`` [rows, r]
+    bf16 (contiguous) receive the LayerNorm statistics and the intermediates the backward pass needs."""
     _need(h, BF16, "h")
     _rows2d(h, "h")
     rows, d = h.shape
@@ -300,15 +304,47 @@ def wfadapter_fwd(h: torch.Tensor, pack: dict, eps: float, row_lengths: Optional
         _rows2d(out, "out")
         if tuple(out.shape) != (rows, d):
             raise ValueError(f"wfadapter_fwd: out has shape {tuple(out.shape)}, expected {(rows, d)}")
-    mean = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
-    rstd = torch.empty((rows,), dtype=F32, device=h.device) if save_stats else None
+    if save_stats and mean is None:
+        mean = torch.empty((rows,), dtype=F32, device=h.device)
+        rstd = torch.empty((rows,), dtype=F32, device=h.device)
+    r, b = pack["r"], pack["b"]
+    for t, nm, w in ((t1, "t1", r), (u, "u", b), (t2, "t2", r)):
+        if t is not None:
+            _need(t, BF16, nm, 2)
+            if tuple(t.shape) != (rows, w) or not t.is_contiguous():
+                raise ValueError(f"wfadapter_fwd: {nm} must be a contiguous [{rows}, {w}] bf16 tensor")
     p = L.WFAdapterFwdParams(h=h.data_ptr(), ldh=h.stride(0), out=out.data_ptr(), ldo=out.stride(0), bd_scaled=pack["bd"].data_ptr(),
                              s=pack["s"].data_ptr(), t=pack["t"].data_ptr(), ad_pad=pack["ad"].data_ptr(), c_d=pack["c_d"].data_ptr(),
                              bu=pack["bu"].data_ptr(), au_pad=pack["au"].data_ptr(), c_u=pack["c_u"].data_ptr(),
                              row_lengths=_ptr(row_lengths), rows_per_seq=rows_per_seq, mean=_ptr(mean), rstd=_ptr(rstd), rows=rows, d=d,
-                             r=pack["r"], b=pack["b"], eps=eps)
+                             r=r, b=b, eps=eps, t1_out=_ptr(t1), u_out=_ptr(u), t2_out=_ptr(t2))
     L.check(L.load().jl_wfadapter_fwd(C.byref(p), _stream()))
     return out, mean, rstd
+
+
+def wfadapter_pack(down_B: torch.Tensor, down_A: torch.Tensor, up_A: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bufs: Optional[dict] = None) -> dict:
+    """Kernel-layout operands of ``wfadapter_fwd`` for every factor set, derived on the device (one launch): ``down_B`` [K, r, d],
+    ``down_A`` [K, b, r], ``up_A`` [K, d, r] bf16; ``gamma`` / ``beta`` fp32 [d].  → {"bd" [K, r, d] bf16, "s" / "t" [K, r] fp32,
+    "ad" [K, b, 64], "au" [K, d, 64] bf16}; ``bufs`` (a previous result) is overwritten in place — the buffers a captured graph
+    holds stay valid."""
+    for t_, nm in ((down_B, "down_B"), (down_A, "down_A"), (up_A, "up_A")):
+        _need(t_, BF16, nm, 3)
+        if not t_.is_contiguous():
+            raise ValueError(f"wfadapter_pack: {nm} must be contiguous")
+    _need(gamma, F32, "gamma", 1)
+    _need(beta, F32, "beta", 1)
+    k, r, d = down_B.shape
+    b = down_A.shape[1]
+    dev = down_B.device
+    if bufs is None:
+        bufs = {"bd": torch.empty((k, r, d), dtype=BF16, device=dev), "s": torch.empty((k, r), dtype=F32, device=dev),
+                "t": torch.empty((k, r), dtype=F32, device=dev), "ad": torch.empty((k, b, 64), dtype=BF16, device=dev),
+                "au": torch.empty((k, d, 64), dtype=BF16, device=dev)}
+    p = L.WFAdapterPackParams(down_B=down_B.data_ptr(), down_A=down_A.data_ptr(), up_A=up_A.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                              bd_scaled=bufs["bd"].data_ptr(), s=bufs["s"].data_ptr(), t=bufs["t"].data_ptr(), ad_pad=bufs["ad"].data_ptr(),
+                              au_pad=bufs["au"].data_ptr(), sets=k, d=d, r=r, b=b)
+    L.check(L.load().jl_wfadapter_pack(C.byref(p), _stream()))
+    return bufs
 
 
 # ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)

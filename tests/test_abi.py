@@ -38,6 +38,7 @@ STRUCTS = {
     "jl_adamw_params": "AdamWParams",
     "jl_fusion_params": "FusionParams",
     "jl_colreduce_job": "ColReduceJob",
+    "jl_wfadapter_pack_params": "WFAdapterPackParams",
 }
 
 

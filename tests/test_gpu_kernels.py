@@ -416,3 +416,49 @@ def test_colreduce_multi_matches_torch(rows):
     xhat = (h.double() - mean.double()[:, None]) * rstd.double()[:, None]
     for got, ref in ((o1, dy.double().sum(0)), (o2, dq.double().sum(0)), (o3, dz.double().sum(0)), (o4, (dz.double() * xhat).sum(0))):
         assert float((got.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-5
+
+
+@pytest.mark.parametrize("d,b,r,rows,kk", [(768, 256, 32, 1000, 2), (1024, 256, 32, 300, 1), (128, 64, 16, 77, 3)])
+def test_wfadapter_training_forward_saves_intermediates_and_device_pack_matches_host_pack(d, b, r, rows, kk):
+    """Training mode of the fused WFAdapter kernel: the same launch writes t1 = LN(h) B_dᵀ, u = relu(t1 A_dᵀ + c_d), t2 = u B_uᵀ and
+    the LayerNorm statistics; the LayerNorm-folded operands come from ``jl_wfadapter_pack`` (device) and equal the host pack."""
+    P = pkg()
+    ops, md = P.ops, P.modeling
+    from oracle import encoder as oe
+    torch.manual_seed(5)
+    ad = P.WFAdapter(d, b, r, num_dialects=kk)
+    with torch.no_grad():
+        ad.norm.weight.copy_(1.0 + 0.2 * torch.randn(d))
+        ad.norm.bias.copy_(0.1 * torch.randn(d))
+        ad.down_bias.copy_(0.05 * torch.randn(kk, b))
+        ad.up_bias.copy_(0.05 * torch.randn(kk, d))
+        for q in (ad.down_B, ad.down_A, ad.up_B, ad.up_A):
+            q.mul_(3.0)
+        for q in ad.parameters():
+            q.copy_(q.to(BF16).float())
+    ad = ad.cuda()
+    eng = md.JLEngine.__new__(md.JLEngine)
+    eng._shadow, eng.flat, eng._wf_bufs = {}, None, {}
+    g = _g(3)
+    h = (torch.randn(rows, d, device="cuda", generator=g) * 1.5 + 0.2).to(BF16)
+    bufs = eng._wf_pack_dev(ad)
+    for k in range(kk):
+        host = eng._wf_pack(ad, k)
+        assert torch.equal(bufs["bd"][k], host["bd"]) and torch.equal(bufs["ad"][k], host["ad"]) and torch.equal(bufs["au"][k], host["au"])
+        assert rel_err(bufs["s"][k], host["s"]) < 1e-5 and rel_err(bufs["t"][k], host["t"]) < 1e-4
+        pack = {"bd": bufs["bd"][k], "s": bufs["s"][k], "t": bufs["t"][k], "ad": bufs["ad"][k], "au": bufs["au"][k], "bu": eng._bf16(ad.up_B)[k],
+                "c_d": ad.down_bias.detach()[k], "c_u": ad.up_bias.detach()[k], "r": r, "b": b}
+        t1 = torch.empty((rows, r), dtype=BF16, device="cuda")
+        u = torch.empty((rows, b), dtype=BF16, device="cuda")
+        t2 = torch.empty((rows, r), dtype=BF16, device="cuda")
+        out, mean, rstd = ops.wfadapter_fwd(h, pack, ad.norm.eps, save_stats=True, t1=t1, u=u, t2=t2)
+        out2, _, _ = ops.wfadapter_fwd(h, host, ad.norm.eps)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2)                              # saving the intermediates does not change the result
+        hf = h.float().cpu()
+        z = F.layer_norm(hf, (d,), ad.norm.weight.detach().cpu(), ad.norm.bias.detach().cpu(), ad.norm.eps)
+        rt1 = z @ ad.down_B.detach().cpu()[k].t()
+        ru = torch.relu(rt1 @ ad.down_A.detach().cpu()[k].t() + ad.down_bias.detach().cpu()[k])
+        rt2 = ru @ ad.up_B.detach().cpu()[k].t()
+        assert rel_err(t1.float(), rt1) < 1e-2 and rel_err(u.float(), ru) < 2e-2 and rel_err(t2.float(), rt2) < 2e-2
+        assert rel_err(mean, hf.mean(-1)) < 1e-3 and rel_err(rstd, 1.0 / torch.sqrt(hf.var(-1, unbiased=False) + ad.norm.eps)) < 1e-3

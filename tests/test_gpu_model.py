@@ -154,8 +154,11 @@ def test_trainer_step_matches_autograd_path_and_updates_adapters():
     assert tr.launches_per_step > 50
 
 
-def test_large_config_both_adapters_mixed_lengths():
-    """BASELINE.json configs 3 + 4 in miniature: d=1024 / 16 heads / 4096 FFN transformer stack (4 of the 24 layers to keep
+@pytest.mark.parametrize("fused_wf_train", [False, True])
+def test_large_config_both_adapters_mixed_lengths(fused_wf_train):
+    """``fused_wf_train``: the WFAdapter forward of the training pass as LN + 4 GEMMs (default) or as the one fused kernel that also
+    writes the intermediates (``JLEngine.fused_wf_train``).
+    BASELINE.json configs 3 + 4 in miniature: d=1024 / 16 heads / 4096 FFN transformer stack (4 of the 24 layers to keep
     the CPU oracle quick) with AttAdapter after attention and WFAdapter after the FFN, mixed-length utterances (padded and
     masked), CTC 'mean' reduction: logits, loss and adapter gradients vs the oracle."""
     P = pkg()
@@ -164,6 +167,7 @@ def test_large_config_both_adapters_mixed_lengths():
     round_bf16_(model)
     model = model.cuda()
     model.freeze_base_model()
+    model.encoder.engine(model.lm_head).fused_wf_train = fused_wf_train
     waves = [synth_wave(16000 * 3 + 123, 21), synth_wave(16000 * 2, 22), synth_wave(9000, 23), synth_wave(16000 * 3 + 123, 24)]
     fe = P.JLFeatureExtractor(device="cuda")
     feats = fe([w.numpy() for w in waves], sampling_rate=16000)
