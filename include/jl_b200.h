@@ -221,6 +221,40 @@ typedef struct {
 int jl_wfadapter_pack(const jl_wfadapter_pack_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a7: the AttAdapter forward in one kernel, for utterances of at most 256 frames —
+ *   out = h + softmax(q k^T * scale + keymask) v W_o^T + b_o,   q|k|v = LN(h) W_qkv^T + b_qkv  (one head of 64)
+ * (/root/reference/README.md:1 "adapter with attention").  Replaces LayerNorm → GEMM → jl_attn_fwd → GEMM.
+ * The LayerNorm is folded into the q|k|v projection, so the caller passes the operands jl_lnfold_pack derives on the device:
+ * wqkv_scaled = bf16(W_qkv * gamma) [192, d], s[j] = sum_k wqkv_scaled[j, k], tb[j] = sum_k W_qkv[j, k] beta[k] + b_qkv[j].
+ * Rows: padded layout b*seq + t with `lengths`, or packed layout cu_seqlens[b] + t (see jl_attn_fwd_params).
+ * Training: qkv_out [rows, 192], a_out [rows, 64] (bf16), mean / rstd [rows], lse ([B, seq] padded, [total_rows] packed) receive
+ * what the backward pass (jl_attn_bwd + GEMMs) needs.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* h; int64_t ldh;          /* bf16 [rows, d] */
+  void* out; int64_t ldo;              /* bf16 [rows, d] */
+  const void* wqkv_scaled;             /* bf16 [192, d] */
+  const float* s; const float* tb;     /* fp32 [192] */
+  const void* wo; const float* bo;     /* bf16 [d, 64], fp32 [d] */
+  const int32_t* lengths;              /* [B] valid frames (padded layout) or NULL */
+  const int32_t* cu_seqlens; int32_t total_rows;   /* packed layout or NULL */
+  int32_t batch, seq, d;               /* seq <= 256; d a multiple of 64 */
+  float scale, eps;
+  int32_t zero_padded_rows;            /* padded layout: rows t >= length are written as 0 (else b_o + h, as the composed path) */
+  void* qkv_out; void* a_out; float* mean; float* rstd; float* lse;      /* optional (training) */
+} jl_attadapter_fwd_params;
+int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream);
+/* LayerNorm folding of a projection that follows a LayerNorm: LN(h) W^T + bias = rstd (h W'^T - mean s) + tb with
+ * W' = bf16(W * gamma) [n, d], s[j] = sum_k W'[j, k], tb[j] = sum_k W[j, k] beta[k] + bias[j] (bias may be NULL).  Derived on the
+ * device so that a captured training step follows the optimizer. */
+typedef struct {
+  const void* w; const float* bias; const float* gamma; const float* beta;
+  void* w_scaled; float* s; float* tb;
+  int32_t n, d;
+} jl_lnfold_pack_params;
+int jl_lnfold_pack(const jl_lnfold_pack_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;
  * /root/reference/README.md:1 "multi-dialect knowledge transfer" + "adapter with attention").  Per frame:
  *   alpha = softmax_k(q . key_k * scale),   out = h + sum_k alpha_k y_k

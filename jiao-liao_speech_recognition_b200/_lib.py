@@ -66,6 +66,16 @@ class WFAdapterPackParams(C.Structure):
                 ("ad_pad", vp), ("au_pad", vp), ("sets", i32), ("d", i32), ("r", i32), ("b", i32)]
 
 
+class AttAdapterFwdParams(C.Structure):
+    _fields_ = [("h", vp), ("ldh", i64), ("out", vp), ("ldo", i64), ("wqkv_scaled", vp), ("s", vp), ("tb", vp), ("wo", vp), ("bo", vp),
+                ("lengths", vp), ("cu_seqlens", vp), ("total_rows", i32), ("batch", i32), ("seq", i32), ("d", i32), ("scale", f32), ("eps", f32),
+                ("zero_padded_rows", i32), ("qkv_out", vp), ("a_out", vp), ("mean", vp), ("rstd", vp), ("lse", vp)]
+
+
+class LnFoldPackParams(C.Structure):
+    _fields_ = [("w", vp), ("bias", vp), ("gamma", vp), ("beta", vp), ("w_scaled", vp), ("s", vp), ("tb", vp), ("n", i32), ("d", i32)]
+
+
 class FusionParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("y", vp), ("ldy", i64), ("y_stride", i64), ("q", vp), ("ldq", i64), ("key", vp), ("ldkey", i64),
                 ("key_stride", i64), ("out", vp), ("ldo", i64), ("alpha", vp), ("dout", vp), ("lddout", i64), ("dy", vp), ("lddy", i64),
@@ -127,6 +137,8 @@ SYMBOLS = {
     "jl_colreduce_multi": (C.c_int, [C.POINTER(ColReduceJob), i32, vp]),
     "jl_wfadapter_fwd": (C.c_int, [C.POINTER(WFAdapterFwdParams), vp]),
     "jl_wfadapter_pack": (C.c_int, [C.POINTER(WFAdapterPackParams), vp]),
+    "jl_attadapter_fwd": (C.c_int, [C.POINTER(AttAdapterFwdParams), vp]),
+    "jl_lnfold_pack": (C.c_int, [C.POINTER(LnFoldPackParams), vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),

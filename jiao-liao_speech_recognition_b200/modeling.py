@@ -390,6 +390,10 @@ class JLEngine:
         # but measured no faster than LN + 4 GEMMs on B200 (24-layer config 19.96 vs 20.02 ms; mixed-length config with four dialect
         # runs per layer 15.49 vs 15.15 ms: one CTA per SM and a four-stage dependency chain per 128 rows) — off by default.
         self.fused_wf_train = os.environ.get("JL_FUSED_WF_TRAIN", "0") == "1"
+        # AttAdapter forward as one kernel (jl_attadapter_fwd) for utterances of <= 256 frames, inference and training
+        self.fused_att = os.environ.get("JL_FUSED_ATT", "0") == "1"
+        self._att_bufs: Dict[int, dict] = {}
+        self._vparams = None
         self._wf_bufs: Dict[int, dict] = {}
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
@@ -417,12 +421,15 @@ class JLEngine:
         bucket behind torch's back; it is counted through ``flat.generation`` (left out for the trainer's own check: its graph
         reads the bucket's bf16 shadow, which that kernel refreshes in place)."""
         v = self.flat.generation if (include_optimizer_steps and self.flat is not None) else 0
-        ps = list(self.enc.parameters())
-        if self.lm_head is not None:
-            ps += list(self.lm_head.parameters())
-        for p in ps:
-            v = (v * 1000003 + p._version * 31 + (p.data_ptr() >> 4)) & 0xFFFFFFFFFFFF
-        return v
+        # the module walk (≈ 0.8 ms for 320 parameters) is done once; the per-call cost is one pass over the cached Parameter
+        # objects.  Parameter objects are replaced only when a module is (lm_head on a vocabulary change: tracked by identity).
+        key = id(self.lm_head)
+        if self._vparams is None or self._vparams[0] != key:
+            ps = list(self.enc.parameters())
+            if self.lm_head is not None:
+                ps += list(self.lm_head.parameters())
+            self._vparams = (key, ps)
+        return hash((v, tuple([(p._version, p.data_ptr()) for p in self._vparams[1]])))
 
     def _backbone_params(self):
         for n, p in self.enc.named_parameters():
@@ -560,6 +567,21 @@ class JLEngine:
         self._wf_bufs[id(ad)] = bufs
         return bufs
 
+    def _att_pack_dev(self, ad, training: bool) -> dict:
+        """LayerNorm-folded q|k|v projection of an AttAdapter (jl_lnfold_pack), derived on the device into buffers that keep their
+        addresses.  Training: re-derived at every call (inside the captured step it follows the optimizer); inference: only when
+        a parameter changed."""
+        ps = [ad.norm.weight, ad.norm.bias, ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight, ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
+        ver = tuple((q.data_ptr(), q._version) for q in ps) + (self.flat.generation if self.flat is not None else 0,)
+        ent = self._att_bufs.get(id(ad))
+        if ent is not None and not training and ent[0] == ver:
+            return ent[1]
+        w = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
+        bq = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
+        bufs = ops.lnfold_pack(w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), None if ent is None else ent[1])
+        self._att_bufs[id(ad)] = (ver, bufs)
+        return bufs
+
     def pos_table(self, device, rows: int) -> torch.Tensor:
         key = (str(device), self.cfg.hidden_size)
         tab = self._pos.get(key)
@@ -660,6 +682,14 @@ class JLEngine:
                 ops.wfadapter_fwd(h[rows], pack, eps, row_lengths=lengths[b0:b1] if zero_rows else None, rows_per_seq=t if zero_rows else 0,
                                   out=out[rows], mean=mean[rows], rstd=rstd[rows], t1=t1[rows], u=u[rows], t2=t2[rows])
             return out, (h, mean, rstd, None, t1, u, t2, segs)
+        if ad.kind == "att" and self.fused_att and t <= 256 and ad.hidden_size % 64 == 0:
+            # the whole adapter in one kernel (LayerNorm folded into the q|k|v projection, attention, output projection, residual)
+            out, sv = ops.attadapter_fwd(h, self._att_pack_dev(ad, training), self._bf16(ad.o_proj.weight), ad.o_proj.bias.detach(), lengths, b, t,
+                                         eps, zero_padded_rows=zero_rows, training=training, cu_seqlens=cu)
+            if not training:
+                return out, None
+            mean, rstd, qkv, a, lse = sv
+            return out, (h, mean, rstd, None, qkv, a, lse)
         z, mean, rstd = ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), eps, save_stats=training)
         rl = dict(row_lengths=lengths, rows_per_seq=t) if zero_rows else {}
         if ad.kind == "wf":
@@ -824,7 +854,11 @@ class JLEngine:
                         g.out(prm, k).zero_()
         else:
             h, mean, rstd, z, qkv, a, lse = saved
-
+            if z is None:
+                # the fused forward kernel never wrote LN(h); only dW_qkv = dqkvᵀ · LN(h) needs it: recomputed on the weight-gradient
+                # branch into a buffer allocated here, on the main stream
+                z = torch.empty_like(h)
+                sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
             jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
 
             def w_o():

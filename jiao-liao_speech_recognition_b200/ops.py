@@ -347,6 +347,61 @@ def wfadapter_pack(down_B: torch.Tensor, down_A: torch.Tensor, up_A: torch.Tenso
     return bufs
 
 
+# ----------------------------------------------------------------------------------------------- fused AttAdapter forward
+def lnfold_pack(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, bufs: Optional[dict] = None) -> dict:
+    """LayerNorm folding of the projection ``w`` [n, d] bf16 (+ ``bias`` [n] fp32) that follows LayerNorm(γ, β): → {"w" bf16 [n, d] =
+    W ⊙ γ, "s" fp32 [n] its row sums, "tb" fp32 [n] = W β + bias}, one launch; ``bufs`` (a previous result) is overwritten in place."""
+    _need(w, BF16, "w", 2)
+    if not w.is_contiguous():
+        raise ValueError("lnfold_pack: w must be contiguous")
+    _need(gamma, F32, "gamma", 1)
+    _need(beta, F32, "beta", 1)
+    if bias is not None:
+        _need(bias, F32, "bias", 1)
+    n, d = w.shape
+    if bufs is None:
+        bufs = {"w": torch.empty((n, d), dtype=BF16, device=w.device), "s": torch.empty((n,), dtype=F32, device=w.device),
+                "tb": torch.empty((n,), dtype=F32, device=w.device)}
+    p = L.LnFoldPackParams(w=w.data_ptr(), bias=_ptr(bias), gamma=gamma.data_ptr(), beta=beta.data_ptr(), w_scaled=bufs["w"].data_ptr(),
+                           s=bufs["s"].data_ptr(), tb=bufs["tb"].data_ptr(), n=n, d=d)
+    L.check(L.load().jl_lnfold_pack(C.byref(p), _stream()))
+    return bufs
+
+
+def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int,
+                   eps: float, zero_padded_rows: bool = False, training: bool = False, cu_seqlens: Optional[torch.Tensor] = None):
+    """out = h + AttAdapter(h) in one kernel (utterances of <= 256 frames).  ``pack`` = ``lnfold_pack`` of the concatenated q|k|v
+    projection ([192, d]); ``wo`` [d, 64] bf16, ``bo`` [d] fp32.  Returns (out, saved) with saved = (mean, rstd, qkv [rows, 192],
+    a [rows, 64], lse) when ``training`` else None."""
+    _need(h, BF16, "h", 2)
+    _rows2d(h, "h")
+    _need(wo, BF16, "wo", 2)
+    _need(bo, F32, "bo", 1)
+    rows, d = h.shape
+    if wo.shape != (d, 64) or not wo.is_contiguous() or pack["w"].shape != (192, d):
+        raise ValueError("attadapter_fwd: wo must be [d, 64] and the packed q|k|v projection [192, d]")
+    if cu_seqlens is None and rows != batch * seq:
+        raise ValueError(f"attadapter_fwd: h has {rows} rows, expected {batch * seq}")
+    dev = h.device
+    out = torch.empty((rows, d), dtype=BF16, device=dev)
+    saved = None
+    mean = rstd = qkv = a = lse = None
+    if training:
+        mean = torch.empty((rows,), dtype=F32, device=dev)
+        rstd = torch.empty((rows,), dtype=F32, device=dev)
+        qkv = torch.empty((rows, 192), dtype=BF16, device=dev)
+        a = torch.empty((rows, 64), dtype=BF16, device=dev)
+        lse = torch.empty((batch, 1, seq) if cu_seqlens is None else (1, rows), dtype=F32, device=dev)
+        saved = (mean, rstd, qkv, a, lse)
+    p = L.AttAdapterFwdParams(h=h.data_ptr(), ldh=h.stride(0), out=out.data_ptr(), ldo=out.stride(0), wqkv_scaled=pack["w"].data_ptr(),
+                              s=pack["s"].data_ptr(), tb=pack["tb"].data_ptr(), wo=wo.data_ptr(), bo=bo.data_ptr(), lengths=_ptr(lengths),
+                              cu_seqlens=_ptr(cu_seqlens), total_rows=rows if cu_seqlens is not None else 0, batch=batch, seq=seq, d=d,
+                              scale=0.125, eps=eps, zero_padded_rows=1 if zero_padded_rows else 0, qkv_out=_ptr(qkv), a_out=_ptr(a),
+                              mean=_ptr(mean), rstd=_ptr(rstd), lse=_ptr(lse))
+    L.check(L.load().jl_attadapter_fwd(C.byref(p), _stream()))
+    return out, saved
+
+
 # ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)
 def _fusion_params(y, q, key, alpha, scale):
     kk, rows, d = y.shape

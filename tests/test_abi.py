@@ -39,6 +39,8 @@ STRUCTS = {
     "jl_fusion_params": "FusionParams",
     "jl_colreduce_job": "ColReduceJob",
     "jl_wfadapter_pack_params": "WFAdapterPackParams",
+    "jl_attadapter_fwd_params": "AttAdapterFwdParams",
+    "jl_lnfold_pack_params": "LnFoldPackParams",
 }
 
 

@@ -462,3 +462,117 @@ def test_wfadapter_training_forward_saves_intermediates_and_device_pack_matches_
         rt2 = ru @ ad.up_B.detach().cpu()[k].t()
         assert rel_err(t1.float(), rt1) < 1e-2 and rel_err(u.float(), ru) < 2e-2 and rel_err(t2.float(), rt2) < 2e-2
         assert rel_err(mean, hf.mean(-1)) < 1e-3 and rel_err(rstd, 1.0 / torch.sqrt(hf.var(-1, unbiased=False) + ad.norm.eps)) < 1e-3
+
+
+# --------------------------------------------------------------------------------------------- fused AttAdapter
+@pytest.mark.parametrize("d,seq,lens,packed", [(768, 250, [250, 100, 250, 7, 129, 128], False), (1024, 256, [256, 1, 200], False),
+                                                (128, 77, [50, 77], False), (768, 136, [136, 0, 64], False),
+                                                (768, 250, [250, 100, 37, 129, 250], True), (256, 200, [64, 65, 200, 128], True)])
+def test_attadapter_fused_forward_matches_oracle(d, seq, lens, packed):
+    """One-kernel AttAdapter (LN folded into the q|k|v projection, whole-row softmax, output projection + residual) vs the oracle's
+    att_adapter on the same bf16 weights, padded ([B·seq] rows) and packed (cu_seqlens) row layouts, plus the tensors it saves for
+    the backward pass.  a7 is definitional: nothing external pins it; the oracle is the definition."""
+    from oracle import encoder as oe
+    P = pkg()
+    ops, md = P.ops, P.modeling
+    torch.manual_seed(1)
+    ad = md.AttAdapter(d)
+    with torch.no_grad():
+        ad.norm.weight.copy_(1.0 + 0.1 * torch.randn(d))
+        ad.norm.bias.copy_(0.1 * torch.randn(d))
+        for lin in (ad.q_proj, ad.k_proj, ad.v_proj, ad.o_proj):
+            lin.weight.copy_(torch.randn(lin.weight.shape) * (0.08 if lin is not ad.o_proj else 0.05))
+            lin.bias.copy_(0.05 * torch.randn(lin.bias.shape))
+        for q in ad.parameters():
+            q.copy_(q.to(BF16).float())
+    w = {"a." + k: v.detach().clone() for k, v in ad.state_dict().items()}
+    ad = ad.cuda()
+    b = len(lens)
+    g = _g(11)
+    hp = (torch.randn(b, seq, d, device="cuda", generator=g) * 1.5 + 0.2).to(BF16)
+    lt = torch.tensor(lens)
+    valid = torch.arange(seq)[None, :] < lt[:, None]                           # [B, seq]
+    hp = hp * valid[:, :, None].cuda()                                         # padded rows are zero, as the engine keeps them
+    ref = oe.att_adapter(w, "a", hp.float().cpu(), lt)                         # [B, seq, d]
+    wqkv = torch.cat([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight]).detach().to(BF16).contiguous()
+    bqkv = torch.cat([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]).detach().float().contiguous()
+    pack = ops.lnfold_pack(wqkv, bqkv, ad.norm.weight.detach(), ad.norm.bias.detach())
+    # the fold itself
+    ws = (wqkv.float() * ad.norm.weight.detach()[None, :]).to(BF16)
+    assert torch.equal(pack["w"], ws)
+    assert rel_err(pack["s"], ws.float().sum(-1)) < 1e-5
+    assert rel_err(pack["tb"], wqkv.float() @ ad.norm.bias.detach() + bqkv) < 1e-5
+    wo = ad.o_proj.weight.detach().to(BF16).contiguous()
+    bo = ad.o_proj.bias.detach().float()
+    lengths = lt.to(I32).cuda()
+    if packed:
+        cu = torch.zeros(b + 1, dtype=I32)
+        cu[1:] = torch.cumsum(lt, 0)
+        rows = int(cu[-1])
+        h = hp[valid.cuda()].contiguous()
+        ref2 = ref[valid]
+        out, sv = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps, training=True, cu_seqlens=cu.cuda())
+        vrow = torch.ones(rows, dtype=torch.bool)
+    else:
+        h = hp.reshape(b * seq, d)
+        ref2 = ref.reshape(b * seq, d)
+        vrow = valid.reshape(-1)
+        out, sv = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps, zero_padded_rows=True, training=True)
+        ref2 = torch.where(vrow[:, None], ref2, torch.zeros(()))      # (an empty utterance is all-NaN in the oracle's softmax)
+    torch.cuda.synchronize()
+    mean, rstd, qkv, a, lse = sv
+    assert rel_err(out.float(), ref2) < 1e-2, rel_err(out.float(), ref2)
+    if (~vrow).any():
+        assert float(out.float().cpu()[~vrow].abs().max()) == 0.0
+    # the adapter's own contribution (out − h), which the residual would otherwise mask
+    dlt, dref = (out.float().cpu() - h.float().cpu())[vrow], (ref2 - h.float().cpu())[vrow]
+    assert rel_err(dlt, dref) < 4e-2, rel_err(dlt, dref)
+    # saved tensors
+    hv = h.float().cpu()[vrow]
+    assert rel_err(mean.cpu()[vrow], hv.mean(-1)) < 1e-3
+    assert rel_err(rstd.cpu()[vrow], 1.0 / torch.sqrt(hv.var(-1, unbiased=False) + ad.norm.eps)) < 1e-3
+    z = F.layer_norm(hv, (d,), w["a.norm.weight"], w["a.norm.bias"], ad.norm.eps)
+    qkv_ref = z @ wqkv.float().cpu().T + bqkv.cpu()
+    assert rel_err(qkv.float().cpu()[vrow], qkv_ref) < 1e-2
+    # without the saved tensors and without zeroing: padded rows get h + b_o (what the composed path writes)
+    if not packed:
+        out2, sv2 = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps)
+        assert sv2 is None
+        torch.cuda.synchronize()
+        assert torch.equal(out2[vrow.cuda()], out[vrow.cuda()])
+        if (~vrow).any():
+            exp = (h.float() + bo[None, :]).to(BF16)
+            assert torch.equal(out2[~vrow.cuda()], exp[~vrow.cuda()])
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_attadapter_fused_matches_composed_path_through_the_engine(packed):
+    """Model-level: loss and adapter gradients with the fused AttAdapter forward == the composed LN → GEMM → attention → GEMM path
+    on the same weights and batch; bf16 rounding points differ (LN(h) is never rounded in the fused kernel), hence tolerances."""
+    from helpers import synth_wave
+    P = pkg()
+    cfg = P.JLConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512, conv_channels=64, vocab_size=48,
+                     adapter_attn="att", adapter_ffn="att")
+    torch.manual_seed(3)
+    model = P.JLForCTC(cfg).cuda()
+    model.freeze_base_model()
+    waves = [synth_wave(n, i) for i, n in enumerate([32000, 16000, 24000, 8000])]
+    fe = P.JLFeatureExtractor(device="cuda")
+    feats = fe([w.numpy() for w in waves], sampling_rate=16000)
+    labels = torch.full((4, 8), -100, dtype=torch.int64)
+    for i, k in enumerate((7, 3, 5, 2)):
+        labels[i, :k] = torch.randint(1, 48, (k,))
+    res = {}
+    for fused in (True, False):
+        model.zero_grad(set_to_none=True)
+        model.encoder.engine(model.lm_head).fused_att = fused
+        loss, _ = model(feats["input_features"], attention_mask=feats["attention_mask"], labels=labels.cuda(), packed=packed)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[fused] = (float(loss), {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert abs(res[True][0] - res[False][0]) <= 2e-3 * abs(res[False][0]), (res[True][0], res[False][0])
+    assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) > 0
+    for n, gr in res[False][1].items():
+        if float(gr.norm()) == 0.0 or n.endswith("k_proj.bias"):      # the key bias has an analytically zero gradient
+            continue
+        assert rel_err(res[True][1][n], gr) < 3e-2, (n, rel_err(res[True][1][n], gr))
