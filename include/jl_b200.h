@@ -238,7 +238,7 @@ typedef struct {
   const void* wo; const float* bo;     /* bf16 [d, 64], fp32 [d] */
   const int32_t* lengths;              /* [B] valid frames (padded layout) or NULL */
   const int32_t* cu_seqlens; int32_t total_rows;   /* packed layout or NULL */
-  int32_t batch, seq, d;               /* seq <= 256; d a multiple of 64 */
+  int32_t batch, seq, d;               /* seq <= 256; d a multiple of 128, at most 1024 */
   float scale, eps;
   int32_t zero_padded_rows;            /* padded layout: rows t >= length are written as 0 (else b_o + h, as the composed path) */
   void* qkv_out; void* a_out; float* mean; float* rstd; float* lse;      /* optional (training) */

@@ -7,21 +7,25 @@
 // GEMM → jl_attn_fwd → GEMM).  It replaces four launches (and their three HBM round trips of z, q|k|v and a) by one:
 // h is read once for the projections and once more (L2) for the residual, out is written once.
 //
-// One CTA per (utterance, 128-query tile), 384 threads:
-//   warp 0   TMA producer: 64-wide k-chunks of h and of W' = W_qkv ⊙ γ through a 3-stage ring, W_o in 256-row chunks
+// One CLUSTER of two CTAs per utterance, one CTA per 128-frame half, 384 threads:
+//   warp 0   TMA producer: 64-wide k-chunks of h (own 128 rows) and of W' = W_qkv ⊙ γ through a 3-stage ring — each CTA of an
+//            active pair fetches HALF of every W' chunk and multicasts it to both — and all of W_o (128-row chunks)
 //   warp 1   tcgen05.mma issuer, accumulators in TMEM (512 columns)
 //   warp 2   TMEM allocator
 //   warps 4-11  row statistics (4 warps), then every epilogue: LayerNorm fold + bias → bf16 operand tiles, softmax, a, output
 // Phases:
-//   A  acc_own[128, 192] = h_own · W'ᵀ  (q, k, v of the CTA's own 128 frames);  when the utterance has frames in the OTHER
-//      128-row half, acc_oth[128, 128] = h_oth · W'_kvᵀ (their k, v: the attention needs every key; recomputing them here
-//      costs one more pass over 196 KB of L2-resident h and avoids a cluster exchange).  The LayerNorm is folded into the
-//      projection, (LN(h) Wᵀ)[i, j] = rstd_i (h W'ᵀ[i, j] − μ_i s_j) + t_j, so the tensor cores consume the raw h tiles
-//      while the row threads accumulate Σx, Σx² from the same shared-memory tiles (as in wfadapter_tc.cu).
-//   B  fold + bias → q, k, v as K-major 128B-swizzled bf16 operand tiles in shared memory (+ q|k|v, statistics to HBM when training)
+//   A  acc[128, 192] = h_own · W'ᵀ (q, k, v of the CTA's own frames).  The LayerNorm is folded into the projection,
+//      (LN(h) Wᵀ)[i, j] = rstd_i (h W'ᵀ[i, j] − μ_i s_j) + t_j, so the tensor cores consume the raw h tiles while the row threads
+//      accumulate Σx, Σx² from the same shared-memory tiles (as in wfadapter_tc.cu).
+//   B  fold + bias → q, k, v as K-major 128B-swizzled bf16 operand tiles in shared memory; the k and v tiles are ALSO written into
+//      the peer CTA's shared memory (st.shared::cluster), so each CTA ends up with the keys and values of all 256 frames without
+//      recomputing the other half's projections (the first version did: 883 KB of operand traffic per CTA, now 344 KB).
 //   C  S[128, 256] = q · kᵀ;  two-pass softmax over whole rows (8 warps);  P → shared memory;  O[128, 64] = P · v
-//   D  a = O / l → bf16 operand tile (+ a, lse to HBM when training);  out[128, d] = a · W_oᵀ + b_o + h in chunks of 256 columns,
-//      accumulators double-buffered in TMEM against the store
+//   D  a = O / l → bf16 operand tile;  out[128, d] = a · W_oᵀ + b_o + h in chunks of 128 columns: the residual tile arrives by TMA
+//      in a staging buffer, each thread adds its row of the accumulator in place, and the tile leaves with coalesced 16-byte
+//      stores (a warp writes four 128-byte row segments per instruction; the first version's row-per-thread 32-byte accesses
+//      cost 27 k of its 61 k cycles).
+// Training also writes q|k|v, a (from the operand tiles, coalesced), the LayerNorm statistics and the row logsumexp.
 #include <cuda.h>
 #include <math_constants.h>
 
@@ -31,23 +35,32 @@
 namespace jl {
 
 constexpr int AA_THREADS = 384;
-constexpr int AA_STAGES = 3;                        // 3 x 40 KB ring + 64 KB of W_o chunks + the barriers fit the 227 KB of a CTA
+constexpr int AA_STAGES = 4;                        // 4 x 40 KB ring (the TMA round trip is ≈ 1400 cycles, a stage is consumed in ≈ 150)
 constexpr uint32_t AA_T128 = 128 * 128;             // bytes of a [128 x 64] bf16 tile
 constexpr uint32_t AA_WQKV = 192 * 128;             // bytes of a [192 x 64] bf16 tile
 constexpr uint32_t AA_STAGE = AA_T128 + AA_WQKV;    // 40 KB
+constexpr int AA_WO_BUFS = 3;                       // W_o chunks of 128 output columns (16 KB), cycled
+constexpr int AA_OUT_BUFS = 4;                      // TMEM accumulators of 128 columns for the output projection
+constexpr int AA_STG = 3;                           // 32 KB staging buffers (residual in, result out) over the dead operand tiles
+constexpr int AA_MAX_D = 1024;
 constexpr float AA_LOG2E = 1.4426950408889634f;
 
 struct __align__(1024) AaSmem {
-  uint8_t ring[AA_STAGES * AA_STAGE];   // phase A ring; afterwards: q | k[2] | (P tail) | v[2] | a operand tiles (see offsets below)
-  uint8_t wo[2][256 * 128];             // W_o chunks [256 rows x 64]
-  float mu[2][128], rs[2][128];         // LayerNorm statistics: [0] own rows, [1] rows of the other half
+  uint8_t ring[AA_STAGES * AA_STAGE];   // phase A ring; afterwards the operand tiles / staging buffers (offsets below)
+  uint8_t wo[AA_WO_BUFS][128 * 128];    // W_o chunks [128 output columns x 64]
+  float bo[AA_MAX_D];
+  float fs[192], ftb[192];              // LayerNorm-fold vectors s, t (see jl_lnfold_pack)
+  float mu[128], rs[128];               // LayerNorm statistics of the CTA's rows
   float red_max[2][128], red_sum[2][128];
   uint64_t full[AA_STAGES], empty[AA_STAGES];
   uint64_t acc_full;                    // phase A accumulators complete
-  uint64_t kv_ready;                    // q, k, v operand tiles written (8 warps)
+  uint64_t kv_ready;                    // q, k, v operand tiles written (8 warps, + the peer's 8 when the pair is active)
   uint64_t s_full, p_full, o_full, a_ready;
-  uint64_t wo_full[2], wo_empty[2], out_full[2], out_empty[2];
+  uint64_t wo_full[AA_WO_BUFS], wo_empty[AA_WO_BUFS], out_full[AA_OUT_BUFS], out_empty[AA_OUT_BUFS], res_full[AA_STG], res_empty[AA_STG];
   uint32_t tmem_slot;
+#ifdef JL_AA_TIMING
+  long long ts_prod[16], ts_mma[16], ts_stat[16], ts_out[8][5];
+#endif
 };
 // operand tiles inside `ring` once phase A is over
 constexpr uint32_t AA_OFF_Q = 0;                    // [128 x 64]            later P tile 0
@@ -55,14 +68,17 @@ constexpr uint32_t AA_OFF_K = AA_T128;              // [256 x 64] (2 tiles)  lat
 constexpr uint32_t AA_OFF_PT = 3 * AA_T128;         //                       P tile 3
 constexpr uint32_t AA_OFF_V = 4 * AA_T128;          // [256 x 64] = four 64-key tiles, read as MN-major B operands
 constexpr uint32_t AA_OFF_A = 6 * AA_T128;          // [128 x 64]
+// staging buffer i = ring + i * 32 KB (i < 3): over q / k / P / v, which are dead once O = P · v is complete
+static_assert(AA_STG * 2 * AA_T128 <= AA_OFF_A, "staging buffers must not reach the `a` operand tile");
 
 __device__ __forceinline__ float aa_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t aa_chunk_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
 __device__ __forceinline__ void aa_store_chunk(uint8_t* tile, int r, int c, const uint32_t* pk) {      // 8 bf16 = 16 B, chunk c of row r
-  *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(tile + aa_chunk_off(r, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 // D[128 x n] (+)= A[128 x 64] · B[n x 64]ᵀ, both K-major 128B-swizzled; 4 MMAs of K = 16
 __device__ __forceinline__ void aa_mma_kk(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int n, bool accumulate) {
@@ -80,6 +96,29 @@ __device__ __forceinline__ void aa_mma_pv(uint32_t d_tmem, uint32_t p_addr, uint
     ptx::umma_bf16(d_tmem, ptx::make_sw128_desc(p_addr + k * 32, 16, 1024), ptx::make_sw128_desc(v_addr + k * 2048, 8192, 1024), idesc,
                    (accumulate || k > 0) ? 1u : 0u);
 }
+// Coalesced copy of NT [128 x 64] bf16 operand tiles (shared-memory addresses tile[i]) to global rows: tile i → columns
+// [i * 64, i * 64 + 64) of the row.  256 threads; thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 j: a warp writes four
+// 128-byte row segments per instruction, and the swizzled chunk offset is the same for all of a thread's rows.
+__device__ __forceinline__ uint4 aa_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+template <int NT>
+__device__ __forceinline__ void aa_tiles_to_global(const uint32_t (&tile)[NT], __nv_bfloat16* dst, int64_t ld, int rows_valid, int t) {
+  const int ch = t & 7, r0 = t >> 3;
+  const uint32_t off = static_cast<uint32_t>(r0 * 128 + ((ch ^ (r0 & 7)) << 4));
+  __nv_bfloat16* d0 = dst + static_cast<int64_t>(r0) * ld + ch * 8;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = aa_lds128(tile[i] + off + j * 4096);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r0 + 32 * j < rows_valid) *reinterpret_cast<uint4*>(d0 + static_cast<int64_t>(32 * j) * ld + i * 64) = v[j];
+  }
+}
 
 #ifdef JL_AA_TIMING
 #define AA_T(i) do { if (threadIdx.x == 128 && blockIdx.x == 0 && blockIdx.y == 0) aa_ts[i] = clock64(); } while (0)
@@ -87,55 +126,32 @@ __device__ __forceinline__ void aa_mma_pv(uint32_t d_tmem, uint32_t p_addr, uint
 #define AA_T(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(AA_THREADS, 1)
-attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_constant__ CUtensorMap t_w, const __grid_constant__ CUtensorMap t_wkv,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AA_THREADS, 1)
+attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_constant__ CUtensorMap t_w, const __grid_constant__ CUtensorMap t_w96,
                       const __grid_constant__ CUtensorMap t_wo, const jl_attadapter_fwd_params p) {
   extern __shared__ uint8_t aa_smem_raw[];
   AaSmem& s = *reinterpret_cast<AaSmem*>(aa_smem_raw + ((1024u - (ptx::smem_u32(aa_smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x, b = blockIdx.y;         // query half, utterance
+  const int g = blockIdx.x, b = blockIdx.y;         // frame half (= rank in the cluster), utterance
+  const uint32_t peer = static_cast<uint32_t>(g ^ 1);
   const int nk = p.d / 64;                          // k-chunks of the projections
-  const int nc = (p.d + 255) / 256;                 // 256-column chunks of the output projection
+  const int nc = p.d / 128;                         // 128-column chunks of the output projection
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&t_h);
     ptx::prefetch_tensormap(&t_w);
-    ptx::prefetch_tensormap(&t_wkv);
+    ptx::prefetch_tensormap(&t_w96);
     ptx::prefetch_tensormap(&t_wo);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < AA_STAGES; ++i) {
-      ptx::mbar_init(&s.full[i], 1);
-      ptx::mbar_init(&s.empty[i], 5);         // MMA commit + the 4 statistics warps
-    }
-    ptx::mbar_init(&s.acc_full, 1);
-    ptx::mbar_init(&s.kv_ready, 8);
-    ptx::mbar_init(&s.s_full, 1);
-    ptx::mbar_init(&s.p_full, 8);
-    ptx::mbar_init(&s.o_full, 1);
-    ptx::mbar_init(&s.a_ready, 8);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&s.wo_full[i], 1);
-      ptx::mbar_init(&s.wo_empty[i], 1);
-      ptx::mbar_init(&s.out_full[i], 1);
-      ptx::mbar_init(&s.out_empty[i], 8);
-    }
-    ptx::fence_barrier_init();
   }
   if (warp == 2) {
     ptx::tmem_alloc(&s.tmem_slot, 512);
     ptx::tmem_relinquish();
   }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = s.tmem_slot;
   jl::pdl_prologue();           // h, lengths and the packed weights may come from the preceding kernels
 #ifdef JL_AA_TIMING
   long long aa_ts[12];
   for (int i = 0; i < 12; ++i) aa_ts[i] = 0;
 #endif
-  AA_T(0);
 
   // where the utterance lives (padded rows b·seq + t, or packed rows cu[b] + t)
   int64_t row_base;
@@ -151,100 +167,139 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
     lim = p.seq;
   }
   const int grow = static_cast<int>(row_base);
-  const bool active = g * 128 < len;                   // the CTA's query tile holds at least one valid frame
-  const bool other = active && len > 128;              // the other 128-row half holds keys
-  const int og = g ^ 1;
-  const int npass = other ? 2 : 1;
+  const bool active = g * 128 < len;                   // the CTA's frame half holds at least one valid frame
+  const bool pair = len > 128;                         // both CTAs of the cluster are active: they share W' and exchange k, v
   const int nkt = (len + 63) / 64;                     // 64-key tiles with valid keys
-  const uint32_t t_acc_own = tmem, t_acc_oth = tmem + 192;
-  const uint32_t t_s = tmem, t_o = tmem + 256;
-  const uint32_t t_out[2] = {tmem, tmem + 256};
+  const uint32_t t_acc = 0, t_s = 0, t_o = 256;        // TMEM column offsets
   uint8_t* R = s.ring;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < AA_STAGES; ++i) {
+      ptx::mbar_init(&s.full[i], 1);
+      ptx::mbar_init(&s.empty[i], pair ? 18 : 9);     // MMA commit + the 8 statistics warps, of every CTA the stage's W' half goes to
+    }
+    ptx::mbar_init(&s.acc_full, 1);
+    ptx::mbar_init(&s.kv_ready, pair ? 16 : 8);
+    ptx::mbar_init(&s.s_full, 1);
+    ptx::mbar_init(&s.p_full, 8);
+    ptx::mbar_init(&s.o_full, 1);
+    ptx::mbar_init(&s.a_ready, 8);
+    for (int i = 0; i < AA_WO_BUFS; ++i) {
+      ptx::mbar_init(&s.wo_full[i], 1);
+      ptx::mbar_init(&s.wo_empty[i], 1);
+    }
+    for (int i = 0; i < AA_OUT_BUFS; ++i) {
+      ptx::mbar_init(&s.out_full[i], 1);
+      ptx::mbar_init(&s.out_empty[i], 8);
+    }
+    for (int i = 0; i < AA_STG; ++i) {
+      ptx::mbar_init(&s.res_full[i], 1);
+      ptx::mbar_init(&s.res_empty[i], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s.tmem_slot;
+  ptx::cluster_sync_all();      // the peer's barriers exist before anything is multicast to it or arrives on them
+  // Second cluster barrier phase = "phase A is over in both CTAs" (their rings may be overwritten with operand tiles): the
+  // epilogue warps of an active CTA arrive once their accumulators are complete and their statistics are done; everybody else
+  // has nothing to protect and arrives at once.  All waits pair up below.
+  if (!active || warp < 4) ptx::cluster_arrive();
+  AA_T(0);
 
   if (warp == 0) {
     if (lane == 0 && active) {
-      // W_o chunks 0, 1 right away (their buffers are not shared with anything)
-      for (int c = 0; c < min(nc, 2); ++c) {
-        ptx::mbar_expect_tx(&s.wo_full[c], 256 * 128);
-        ptx::tma_load_2d(s.wo[c], &t_wo, &s.wo_full[c], 0, c * 256);
+      // all of W_o (or its first chunks) right away: dedicated buffers
+      for (int c = 0; c < min(nc, AA_WO_BUFS); ++c) {
+        ptx::mbar_expect_tx(&s.wo_full[c], AA_T128);
+        ptx::tma_load_2d(s.wo[c], &t_wo, &s.wo_full[c], 0, c * 128);
       }
-      int it = 0;
-      for (int pass = 0; pass < npass; ++pass) {
-        const int r0 = grow + (pass == 0 ? g : og) * 128;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int st = it % AA_STAGES;
-          ptx::mbar_wait(&s.empty[st], ((it / AA_STAGES) & 1) ^ 1u);
-          uint8_t* base = R + st * AA_STAGE;
-          if (pass == 0) {
-            ptx::mbar_expect_tx(&s.full[st], AA_STAGE);
-            ptx::tma_load_2d(base, &t_h, &s.full[st], kc * 64, r0);
-            ptx::tma_load_2d(base + AA_T128, &t_w, &s.full[st], kc * 64, 0);
-          } else {
-            ptx::mbar_expect_tx(&s.full[st], 2 * AA_T128);
-            ptx::tma_load_2d(base, &t_h, &s.full[st], kc * 64, r0);
-            ptx::tma_load_2d(base + AA_T128, &t_wkv, &s.full[st], kc * 64, 0);
-          }
+      for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc % AA_STAGES;
+        ptx::mbar_wait(&s.empty[st], ((kc / AA_STAGES) & 1) ^ 1u);
+#ifdef JL_AA_TIMING
+        if (kc < 16) s.ts_prod[kc] = clock64();
+#endif
+        uint8_t* base = R + st * AA_STAGE;
+        ptx::mbar_expect_tx(&s.full[st], AA_STAGE);
+        ptx::tma_load_2d(base, &t_h, &s.full[st], kc * 64, grow + g * 128);
+        if (pair) ptx::tma_load_2d_mcast(base + AA_T128 + g * (96 * 128), &t_w96, &s.full[st], kc * 64, g * 96, static_cast<uint16_t>(3));
+        else ptx::tma_load_2d(base + AA_T128, &t_w, &s.full[st], kc * 64, 0);
+      }
+      jl::pdl_trigger_late();
+      // phase D: the residual tile of output chunk c lands in staging buffer c % 3 (over q / k / P / v: dead once O = P · v is
+      // complete; afterwards a buffer is free when the epilogue has stored the chunk it held), and the remaining W_o chunks
+      ptx::mbar_wait(&s.o_full, 0);
+      for (int c = 0; c < nc; ++c) {
+        const int sb = c % AA_STG;
+        if (c >= AA_STG) ptx::mbar_wait(&s.res_empty[sb], ((c / AA_STG) - 1) & 1);
+        uint8_t* stg = R + sb * (2 * AA_T128);
+        ptx::mbar_expect_tx(&s.res_full[sb], 2 * AA_T128);
+        ptx::tma_load_2d(stg, &t_h, &s.res_full[sb], c * 128, grow + g * 128);
+        ptx::tma_load_2d(stg + AA_T128, &t_h, &s.res_full[sb], c * 128 + 64, grow + g * 128);
+        if (c >= AA_WO_BUFS) {
+          const int wb = c % AA_WO_BUFS;
+          ptx::mbar_wait(&s.wo_empty[wb], ((c / AA_WO_BUFS) - 1) & 1);
+          ptx::mbar_expect_tx(&s.wo_full[wb], AA_T128);
+          ptx::tma_load_2d(s.wo[wb], &t_wo, &s.wo_full[wb], 0, c * 128);
         }
-      }
-      for (int c = 2; c < nc; ++c) {
-        const int st = c & 1;
-        ptx::mbar_wait(&s.wo_empty[st], ((c >> 1) & 1) ^ 1u);
-        ptx::mbar_expect_tx(&s.wo_full[st], 256 * 128);
-        ptx::tma_load_2d(s.wo[st], &t_wo, &s.wo_full[st], 0, c * 256);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && active) {
       // ---- phase A
-      int it = 0;
-      for (int pass = 0; pass < npass; ++pass) {
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int st = it % AA_STAGES;
-          ptx::mbar_wait(&s.full[st], (it / AA_STAGES) & 1);
-          ptx::tc_fence_after();
-          const uint32_t base = ptx::smem_u32(R + st * AA_STAGE);
-          if (pass == 0) aa_mma_kk(t_acc_own, base, base + AA_T128, 192, kc > 0);
-          else aa_mma_kk(t_acc_oth, base, base + AA_T128, 128, kc > 0);
-          ptx::umma_commit(&s.empty[st]);
-        }
+      for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc % AA_STAGES;
+        ptx::mbar_wait(&s.full[st], (kc / AA_STAGES) & 1);
+        ptx::tc_fence_after();
+#ifdef JL_AA_TIMING
+        if (kc < 16) s.ts_mma[kc] = clock64();
+#endif
+        const uint32_t base = ptx::smem_u32(R + st * AA_STAGE);
+        aa_mma_kk(tmem + t_acc, base, base + AA_T128, 192, kc > 0);
+        if (pair) ptx::umma_commit_mcast(&s.empty[st], static_cast<uint16_t>(3));
+        else ptx::umma_commit(&s.empty[st]);
       }
       ptx::umma_commit(&s.acc_full);
       // ---- phase C: S = q · kᵀ (N = 256 keys), then O = P · v over the key tiles that hold frames
-      ptx::mbar_wait(&s.kv_ready, 0);
+      ptx::mbar_wait_cluster(&s.kv_ready, 0);
       ptx::tc_fence_after();
       const uint32_t rb = ptx::smem_u32(R);
-      aa_mma_kk(t_s, rb + AA_OFF_Q, rb + AA_OFF_K, 256, false);
+      aa_mma_kk(tmem + t_s, rb + AA_OFF_Q, rb + AA_OFF_K, 256, false);
       ptx::umma_commit(&s.s_full);
       ptx::mbar_wait(&s.p_full, 0);
       ptx::tc_fence_after();
-      for (int kt = 0; kt < nkt; ++kt) aa_mma_pv(t_o, rb + kt * AA_T128, rb + AA_OFF_V + kt * (64 * 128), kt > 0);
+      for (int kt = 0; kt < nkt; ++kt) aa_mma_pv(tmem + t_o, rb + kt * AA_T128, rb + AA_OFF_V + kt * (64 * 128), kt > 0);
       ptx::umma_commit(&s.o_full);
       // ---- phase D: out chunk c = a · W_o[c]ᵀ
       ptx::mbar_wait(&s.a_ready, 0);
       ptx::tc_fence_after();
       for (int c = 0; c < nc; ++c) {
-        const int st = c & 1;
-        const int ncols = min(256, p.d - c * 256);
-        ptx::mbar_wait(&s.wo_full[st], (c >> 1) & 1);
-        ptx::mbar_wait(&s.out_empty[st], ((c >> 1) & 1) ^ 1u);
+        const int wb = c % AA_WO_BUFS, ob = c % AA_OUT_BUFS;
+        ptx::mbar_wait(&s.wo_full[wb], (c / AA_WO_BUFS) & 1);
+        ptx::mbar_wait(&s.out_empty[ob], ((c / AA_OUT_BUFS) & 1) ^ 1u);
         ptx::tc_fence_after();
-        aa_mma_kk(t_out[st], rb + AA_OFF_A, ptx::smem_u32(s.wo[st]), ncols, false);
-        ptx::umma_commit(&s.wo_empty[st]);
-        ptx::umma_commit(&s.out_full[st]);
+        aa_mma_kk(tmem + ob * 128, rb + AA_OFF_A, ptx::smem_u32(s.wo[wb]), 128, false);
+        ptx::umma_commit(&s.wo_empty[wb]);
+        ptx::umma_commit(&s.out_full[ob]);
       }
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
     const int grp = (warp - 4) >> 2;                     // 0: warps 4-7, 1: warps 8-11
     const int r = quad * 32 + lane;                      // TMEM lane = row of the 128-row tile
+    const int et = threadIdx.x - 128;                    // 0..255 among the epilogue threads
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int qrow = g * 128 + r;                        // frame index inside the utterance
-    __nv_bfloat16* out_row = reinterpret_cast<__nv_bfloat16*>(p.out) + (row_base + qrow) * p.ldo;
-    const __nv_bfloat16* h_row = reinterpret_cast<const __nv_bfloat16*>(p.h) + (row_base + qrow) * p.ldh;
+    const int rows_owned = min(128, lim - g * 128);      // rows of this tile the layout gives to this utterance (may be <= 0)
     if (!active) {
-      // no valid frame in this tile: the rows the layout still owns get what the composed path gives them — a = 0, so
+      // no valid frame in this half: the rows the layout still owns get what the composed path gives them — a = 0, so
       // out = b_o + h (or 0 when the caller wants padded rows zeroed); saved tensors are zero there
       if (qrow < lim) {
+        __nv_bfloat16* out_row = reinterpret_cast<__nv_bfloat16*>(p.out) + (row_base + qrow) * p.ldo;
+        const __nv_bfloat16* h_row = reinterpret_cast<const __nv_bfloat16*>(p.h) + (row_base + qrow) * p.ldh;
         for (int c = grp * (p.d / 16); c < (grp + 1) * (p.d / 16); ++c) {          // 8 columns per step, half the row per warp group
           float o[8];
           if (p.zero_padded_rows) {
@@ -273,90 +328,117 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         }
       }
     } else {
-      // ---- phase A (warps 4-7): LayerNorm statistics of the staged h tiles, own rows then the other half's
-      if (grp == 0) {
-        int it = 0;
-        for (int pass = 0; pass < npass; ++pass) {
-          float sx = 0.0f, sxx = 0.0f;
-          for (int kc = 0; kc < nk; ++kc, ++it) {
-            const int st = it % AA_STAGES;
-            ptx::mbar_wait(&s.full[st], (it / AA_STAGES) & 1);
-            const uint8_t* tile = R + st * AA_STAGE;
+      for (int i = et; i < p.d; i += 256) s.bo[i] = __ldg(p.bo + i);
+      if (et < 192) { s.fs[et] = __ldg(p.s + et); s.ftb[et] = __ldg(p.tb + et); }
+      // ---- phase A (all 8 warps): LayerNorm statistics of the staged h tiles — warp group 0 sums the first 32 columns of every
+      //      64-column chunk, group 1 the other 32; four independent accumulator chains per thread
+      {
+        float sx[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int kc = 0; kc < nk; ++kc) {
+          const int st = kc % AA_STAGES;
+          ptx::mbar_wait(&s.full[st], (kc / AA_STAGES) & 1);
+          const uint8_t* tile = R + st * AA_STAGE;
+          uint4 v[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
-              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const uint4*>(tile + aa_chunk_off(r, grp * 4 + c));
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = unpack_bf16x2(w[q]);
-                sx += f.x + f.y;
-                sxx = fmaf(f.x, f.x, fmaf(f.y, f.y, sxx));
-              }
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = unpack_bf16x2(w[q]);
+              sx[q] += f.x;
+              sq[q] = fmaf(f.x, f.x, sq[q]);
+              sx[q] += f.y;
+              sq[q] = fmaf(f.y, f.y, sq[q]);
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s.empty[st]);
           }
+          __syncwarp();
+#ifdef JL_AA_TIMING
+          if (threadIdx.x == 128 && kc < 16) s.ts_stat[kc] = clock64();
+#endif
+          if (lane == 0) {
+            ptx::mbar_arrive(&s.empty[st]);
+            if (pair) ptx::mbar_arrive_remote(ptx::mapa_shared(ptx::smem_u32(&s.empty[st]), peer));
+          }
+        }
+        s.red_sum[grp][r] = (sx[0] + sx[1]) + (sx[2] + sx[3]);
+        s.red_max[grp][r] = (sq[0] + sq[1]) + (sq[2] + sq[3]);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (grp == 0) {
+          const float tx = s.red_sum[0][r] + s.red_sum[1][r], txx = s.red_max[0][r] + s.red_max[1][r];
           const float inv_d = 1.0f / static_cast<float>(p.d);
-          const float mu = sx * inv_d;
-          const float var = fmaxf(sxx * inv_d - mu * mu, 0.0f);
+          const float mu = tx * inv_d;
+          const float var = fmaxf(txx * inv_d - mu * mu, 0.0f);
           const float rstd = 1.0f / sqrtf(var + p.eps);
-          s.mu[pass][r] = mu;
-          s.rs[pass][r] = rstd;
-          if (pass == 0 && p.mean != nullptr && qrow < lim) {
+          s.mu[r] = mu;
+          s.rs[r] = rstd;
+          if (p.mean != nullptr && qrow < lim) {
             p.mean[row_base + qrow] = mu;
             p.rstd[row_base + qrow] = rstd;
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // statistics visible to all 8 warps
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // statistics (and b_o) visible to all 8 warps
       AA_T(1);
-      // ---- phase B: fold + bias → q, k, v operand tiles (and q|k|v to HBM).  Own rows: 6 chunks of 32 columns (q0 q1 k0 k1 v0 v1),
-      //      other rows: 4 chunks (k0 k1 v0 v1); warp group 0 takes own 0-2 + other 0-1, group 1 own 3-5 + other 2-3.
       ptx::mbar_wait(&s.acc_full, 0);
       ptx::tc_fence_after();
       AA_T(2);
-      __nv_bfloat16* qkv_row = (p.qkv_out != nullptr && qrow < lim) ? reinterpret_cast<__nv_bfloat16*>(p.qkv_out) + (row_base + qrow) * 192 : nullptr;
+      ptx::cluster_arrive();                               // this CTA's ring is free …
+      ptx::cluster_wait();                                 // … and so is the peer's
+      // ---- phase B: fold + bias → q, k, v operand tiles: 6 chunks of 32 columns (q0 q1 k0 | k1 v0 v1), three per warp group;
+      //      the k and v chunks also go to the same place in the peer's shared memory
+      const float mu = s.mu[r], rstd = s.rs[r];
 #pragma unroll 1
-      for (int item = 0; item < 5; ++item) {
-        const bool own = item < 3;
-        if (!own && !other) break;
-        const int ch = own ? grp * 3 + item : grp * 2 + (item - 3);          // chunk index inside the accumulator
-        const int col0 = own ? ch * 32 : 64 + ch * 32;                       // column of W_qkv (q 0-63, k 64-127, v 128-191)
-        const float mu = s.mu[own ? 0 : 1][r], rstd = s.rs[own ? 0 : 1][r];
+      for (int item = 0; item < 3; ++item) {
+        const int ch = grp * 3 + item;
+        const int col0 = ch * 32;                                            // column of W_qkv (q 0-63, k 64-127, v 128-191)
         uint32_t v[32];
-        ptx::tmem_ld_32x32((own ? t_acc_own : t_acc_oth) + lane_off + ch * 32, v);
+        ptx::tmem_ld_32x32(tmem + t_acc + lane_off + ch * 32, v);
         ptx::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int j = col0 + 2 * i;
-          const float x0 = fmaf(rstd, __uint_as_float(v[2 * i]) - mu * __ldg(p.s + j), __ldg(p.tb + j));
-          const float x1 = fmaf(rstd, __uint_as_float(v[2 * i + 1]) - mu * __ldg(p.s + j + 1), __ldg(p.tb + j + 1));
+          const float2 fs = *reinterpret_cast<const float2*>(s.fs + j), ft = *reinterpret_cast<const float2*>(s.ftb + j);
+          const float x0 = fmaf(rstd, __uint_as_float(v[2 * i]) - mu * fs.x, ft.x);
+          const float x1 = fmaf(rstd, __uint_as_float(v[2 * i + 1]) - mu * fs.y, ft.y);
           pk[i] = pack_bf16x2(x0, x1);
         }
-        // destination tile: q; k / v of the half the rows belong to (utterance order: half 0 = frames 0-127)
-        const int hidx = own ? g : og;
+        // destination tile: q; k / v of this CTA's frame half (utterance order: half 0 = frames 0-127)
         uint8_t* tile;
         if (col0 < 64) tile = R + AA_OFF_Q;
-        else if (col0 < 128) tile = R + AA_OFF_K + hidx * AA_T128;
-        else tile = R + AA_OFF_V + hidx * AA_T128;
+        else if (col0 < 128) tile = R + AA_OFF_K + g * AA_T128;
+        else tile = R + AA_OFF_V + g * AA_T128;
         const int c0 = ((col0 & 63) >> 3);                                   // first 16-byte chunk inside the 64-wide tile row: 0 or 4
 #pragma unroll
         for (int c = 0; c < 4; ++c) aa_store_chunk(tile, r, c0 + c, pk + 4 * c);
-        if (own && qkv_row != nullptr) {
+        if (pair && col0 >= 64) {
+          const uint32_t remote = ptx::mapa_shared(ptx::smem_u32(tile), peer);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(qkv_row + col0)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          for (int c = 0; c < 4; ++c)
+            ptx::st_shared_cluster_v4(remote + aa_chunk_off(r, c0 + c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
       }
       ptx::tc_fence_before();
-      ptx::fence_proxy_async();
+      ptx::fence_proxy_async_all();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s.kv_ready);
+      if (lane == 0) {
+        ptx::mbar_arrive(&s.kv_ready);
+        if (pair) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s.kv_ready), peer));
+      }
       AA_T(3);
+      if (p.qkv_out != nullptr) {
+        // q | k | v of the CTA's rows, from the operand tiles (they stay until the softmax overwrites them with P)
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const uint32_t rb = ptx::smem_u32(R);
+        const uint32_t tiles[3] = {rb + AA_OFF_Q, rb + AA_OFF_K + g * AA_T128, rb + AA_OFF_V + g * AA_T128};
+        aa_tiles_to_global<3>(tiles, reinterpret_cast<__nv_bfloat16*>(p.qkv_out) + (row_base + g * 128) * 192, 192, rows_owned, et);
+      }
       // ---- phase C: softmax over the whole row of 256 scores (this thread: 128 of them), P → operand tiles over q / k
       const float sl2 = p.scale * AA_LOG2E;
       const int kbase = grp * 128;
-      const uint32_t t_srow = t_s + lane_off + 128u * grp;
+      const uint32_t t_srow = tmem + t_s + lane_off + 128u * grp;
       ptx::mbar_wait(&s.s_full, 0);
       ptx::tc_fence_after();
       AA_T(4);
@@ -406,7 +488,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
       if (lane == 0) ptx::mbar_arrive(&s.p_full);
       AA_T(5);
       s.red_sum[grp][r] = sum;
-      // ---- phase D: a = O / l (this thread: 32 of the 64 dims) → operand tile, HBM; lse
+      // ---- phase D: a = O / l (this thread: 32 of the 64 dims) → operand tile; lse
       ptx::mbar_wait(&s.o_full, 0);
       ptx::tc_fence_after();
       AA_T(6);
@@ -416,18 +498,13 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
       const float inv = valid ? 1.0f / l_tot : 0.0f;
       {
         uint32_t ov[32];
-        ptx::tmem_ld_32x32(t_o + lane_off + 32u * grp, ov);
+        ptx::tmem_ld_32x32(tmem + t_o + lane_off + 32u * grp, ov);
         ptx::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
 #pragma unroll
         for (int c = 0; c < 4; ++c) aa_store_chunk(R + AA_OFF_A, r, grp * 4 + c, pk + 4 * c);
-        if (p.a_out != nullptr && qrow < lim) {
-          uint4* ad = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.a_out) + (row_base + qrow) * 64 + grp * 32);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ad[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        }
         if (p.lse != nullptr && grp == 0 && qrow < lim)
           p.lse[(p.cu_seqlens ? row_base : static_cast<int64_t>(b) * p.seq) + qrow] = valid ? mx * p.scale + logf(l_tot) : 0.0f;
       }
@@ -436,48 +513,68 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s.a_ready);
       AA_T(7);
-      // ---- output projection epilogue: out = acc + b_o + h, 32 columns per step; this warp group takes column groups grp, grp + 2, …
-      const bool write = qrow < lim;
+      if (p.a_out != nullptr) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const uint32_t tiles[1] = {ptx::smem_u32(R) + AA_OFF_A};
+        aa_tiles_to_global<1>(tiles, reinterpret_cast<__nv_bfloat16*>(p.a_out) + (row_base + g * 128) * 64, 64, rows_owned, et);
+      }
+      // ---- output projection epilogue, 128 columns per chunk: this thread adds its row's 64 accumulator columns (+ b_o) to the
+      //      residual tile in place, then the 256 threads store the tile with coalesced 16-byte accesses
       const bool zero = p.zero_padded_rows && !valid;
+      __nv_bfloat16* out_tile = reinterpret_cast<__nv_bfloat16*>(p.out) + (row_base + g * 128) * p.ldo;
       for (int c = 0; c < nc; ++c) {
-        const int st = c & 1;
-        const int ngrp = min(256, p.d - c * 256) / 32;
-        ptx::mbar_wait(&s.out_full[st], (c >> 1) & 1);
+        const int sb = c % AA_STG, ob = c % AA_OUT_BUFS;
+        uint8_t* stg = R + sb * (2 * AA_T128);
+        ptx::mbar_wait(&s.res_full[sb], (c / AA_STG) & 1);
+        ptx::mbar_wait(&s.out_full[ob], (c / AA_OUT_BUFS) & 1);
         ptx::tc_fence_after();
         if (c == 0) AA_T(8);
-#pragma unroll 1
-        for (int q = grp; q < ngrp; q += 2) {
-          const int col = c * 256 + q * 32;
-          uint32_t hres[2][8];
-          if (write && !zero) {
-            ld_global_nc_v8(h_row + col, hres[0]);
-            ld_global_nc_v8(h_row + col + 16, hres[1]);
-          }
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(t_out[st] + lane_off + q * 32, v);
-          ptx::tmem_ld_wait();
-          if (write) {
+#ifdef JL_AA_TIMING
+#define AA_TO(i) do { if (threadIdx.x == 128 && c < 8) s.ts_out[c][i] = clock64(); } while (0)
+#else
+#define AA_TO(i) do { } while (0)
+#endif
+        AA_TO(0);
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32(tmem + ob * 128 + lane_off + grp * 64, va);
+        ptx::tmem_ld_32x32(tmem + ob * 128 + lane_off + grp * 64 + 32, vb);
+        ptx::tmem_ld_wait();
+        uint8_t* mytile = stg + grp * AA_T128;
+        const float* bias = s.bo + c * 128 + grp * 64;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t w[8];
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4* cell = reinterpret_cast<uint4*>(mytile + aa_chunk_off(r, ch));
+          const uint4 hv = *cell;
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + ch * 8), b1 = *reinterpret_cast<const float4*>(bias + ch * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t w[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = hh * 16 + 2 * i;
-                float o0 = 0.0f, o1 = 0.0f;
-                if (!zero) {
-                  const float2 hr = unpack_bf16x2(hres[hh][i]);
-                  o0 = __uint_as_float(v[j]) + __ldg(p.bo + col + j) + hr.x;
-                  o1 = __uint_as_float(v[j + 1]) + __ldg(p.bo + col + j + 1) + hr.y;
-                }
-                w[i] = pack_bf16x2(o0, o1);
-              }
-              st_global_v8(out_row + col + hh * 16, w);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int j = (ch & 3) * 8 + 2 * i;
+            const float a0 = __uint_as_float(ch < 4 ? va[j] : vb[j]), a1 = __uint_as_float(ch < 4 ? va[j + 1] : vb[j + 1]);
+            const float2 hr = unpack_bf16x2(hw[i]);
+            w[i] = zero ? 0u : pack_bf16x2(a0 + bb[2 * i] + hr.x, a1 + bb[2 * i + 1] + hr.y);
           }
+          *cell = make_uint4(w[0], w[1], w[2], w[3]);
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&s.out_empty[st]);
+        if (lane == 0) ptx::mbar_arrive(&s.out_empty[ob]);
+        AA_TO(1);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        AA_TO(2);
+        {
+          const uint32_t tiles[2] = {ptx::smem_u32(stg), ptx::smem_u32(stg) + AA_T128};
+          aa_tiles_to_global<2>(tiles, out_tile + c * 128, p.ldo, rows_owned, et);
+        }
+        AA_TO(3);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        AA_TO(4);
+        if (et == 0) {
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&s.res_empty[sb]);
+        }
       }
       AA_T(9);
 #ifdef JL_AA_TIMING
@@ -485,8 +582,19 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         printf("aa phases (cycles): stats %lld  acc_wait %lld  fold %lld  s_wait %lld  softmax %lld  o_wait %lld  a %lld  out_wait %lld  out %lld  total %lld\n",
                aa_ts[1] - aa_ts[0], aa_ts[2] - aa_ts[1], aa_ts[3] - aa_ts[2], aa_ts[4] - aa_ts[3], aa_ts[5] - aa_ts[4], aa_ts[6] - aa_ts[5],
                aa_ts[7] - aa_ts[6], aa_ts[8] - aa_ts[7], aa_ts[9] - aa_ts[8], aa_ts[9] - aa_ts[0]);
+      if (threadIdx.x == 128 && blockIdx.x == 0 && blockIdx.y == 0)
+        for (int kc = 0; kc < min(nk, 16); ++kc)
+          printf("  kc %2d  producer-issue %6lld  mma-sees-full %6lld  stats-done %6lld\n", kc, s.ts_prod[kc] - aa_ts[0], s.ts_mma[kc] - aa_ts[0], s.ts_stat[kc] - aa_ts[0]);
+      if (threadIdx.x == 128 && blockIdx.x == 0 && blockIdx.y == 0)
+        for (int c = 0; c < min(nc, 8); ++c)
+          printf("  out chunk %d  start %6lld  compute %5lld  bar %5lld  store %5lld  bar %5lld\n", c, s.ts_out[c][0] - aa_ts[8], s.ts_out[c][1] - s.ts_out[c][0],
+                 s.ts_out[c][2] - s.ts_out[c][1], s.ts_out[c][3] - s.ts_out[c][2], s.ts_out[c][4] - s.ts_out[c][3]);
 #endif
     }
+  }
+  if (!active || warp < 4) {
+    __syncwarp();
+    ptx::cluster_wait();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -542,7 +650,8 @@ int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream) {
   JL_REQUIRE(p->h && p->out && p->wqkv_scaled && p->s && p->tb && p->wo && p->bo, JL_EINVAL, "attadapter_fwd: null pointer");
   JL_REQUIRE(p->batch > 0 && p->seq > 0, JL_EINVAL, "attadapter_fwd: batch and seq must be positive");
   JL_REQUIRE(p->seq <= 256, JL_EUNSUPPORTED_SHAPE, "attadapter_fwd: utterances of at most 256 frames (got seq %d): use the composed path", p->seq);
-  JL_REQUIRE(p->d >= 64 && (p->d % 64) == 0, JL_EUNSUPPORTED_SHAPE, "attadapter_fwd: d must be a multiple of 64 (got %d)", p->d);
+  JL_REQUIRE(p->d >= 128 && (p->d % 128) == 0 && p->d <= jl::AA_MAX_D, JL_EUNSUPPORTED_SHAPE,
+             "attadapter_fwd: d must be a multiple of 128, at most %d (got %d): use the composed path", jl::AA_MAX_D, p->d);
   JL_REQUIRE((p->ldh % 16) == 0 && (p->ldo % 16) == 0, JL_EINVAL, "attadapter_fwd: row strides must be multiples of 16 elements");
   JL_REQUIRE(((reinterpret_cast<uintptr_t>(p->h) | reinterpret_cast<uintptr_t>(p->out)) & 31) == 0, JL_EINVAL, "attadapter_fwd: h / out must be 32-byte aligned");
   JL_REQUIRE(p->cu_seqlens == nullptr || p->total_rows > 0, JL_EINVAL, "attadapter_fwd: packed layout needs total_rows > 0");
@@ -552,12 +661,11 @@ int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream) {
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   const int64_t rows = p->cu_seqlens ? static_cast<int64_t>(p->total_rows) : static_cast<int64_t>(p->batch) * p->seq;
-  CUtensorMap t_h, t_w, t_wkv, t_wo;
+  CUtensorMap t_h, t_w, t_w96, t_wo;
   rc = jl::make_tma_map_2d_bf16(&t_h, p->h, p->d, rows, p->ldh, 128);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->wqkv_scaled, p->d, 192, p->d, 192);
-  if (rc == JL_OK)
-    rc = jl::make_tma_map_2d_bf16(&t_wkv, reinterpret_cast<const __nv_bfloat16*>(p->wqkv_scaled) + static_cast<int64_t>(64) * p->d, p->d, 128, p->d, 128);
-  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_wo, p->wo, 64, p->d, 64, 256);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w96, p->wqkv_scaled, p->d, 192, p->d, 96);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_wo, p->wo, 64, p->d, 64, 128);
   if (rc != JL_OK) return rc;
   const size_t smem = sizeof(jl::AaSmem) + 1024;
   static thread_local int configured_dev = -1;
@@ -568,8 +676,7 @@ int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream) {
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "attadapter_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     configured_dev = dev;
   }
-  jl::launch(jl::attadapter_fwd_kernel, dim3(jl::ceil_div(p->seq, 128), p->batch), jl::AA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_h, t_w,
-             t_wkv, t_wo, *p);
+  jl::launch(jl::attadapter_fwd_kernel, dim3(2, p->batch), jl::AA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_h, t_w, t_w96, t_wo, *p);
   JL_CHECK_LAUNCH("attadapter_fwd");
   return JL_OK;
 }

@@ -391,7 +391,7 @@ class JLEngine:
         # runs per layer 15.49 vs 15.15 ms: one CTA per SM and a four-stage dependency chain per 128 rows) — off by default.
         self.fused_wf_train = os.environ.get("JL_FUSED_WF_TRAIN", "0") == "1"
         # AttAdapter forward as one kernel (jl_attadapter_fwd) for utterances of <= 256 frames, inference and training
-        self.fused_att = os.environ.get("JL_FUSED_ATT", "0") == "1"
+        self.fused_att = os.environ.get("JL_FUSED_ATT", "1") != "0"
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._wf_bufs: Dict[int, dict] = {}
@@ -682,7 +682,7 @@ class JLEngine:
                 ops.wfadapter_fwd(h[rows], pack, eps, row_lengths=lengths[b0:b1] if zero_rows else None, rows_per_seq=t if zero_rows else 0,
                                   out=out[rows], mean=mean[rows], rstd=rstd[rows], t1=t1[rows], u=u[rows], t2=t2[rows])
             return out, (h, mean, rstd, None, t1, u, t2, segs)
-        if ad.kind == "att" and self.fused_att and t <= 256 and ad.hidden_size % 64 == 0:
+        if ad.kind == "att" and self.fused_att and t <= 256 and ad.hidden_size % 128 == 0 and ad.hidden_size <= 1024:
             # the whole adapter in one kernel (LayerNorm folded into the q|k|v projection, attention, output projection, residual)
             out, sv = ops.attadapter_fwd(h, self._att_pack_dev(ad, training), self._bf16(ad.o_proj.weight), ad.o_proj.bias.detach(), lengths, b, t,
                                          eps, zero_padded_rows=zero_rows, training=training, cu_seqlens=cu)

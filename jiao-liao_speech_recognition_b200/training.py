@@ -256,6 +256,19 @@ def shard_utterances(num_frames_per_utt: Sequence[int], world: int) -> List[List
     return shards
 
 
+class LossHandle:
+    """The loss of one ``AdapterTrainer.step_async`` call: ``item()`` waits for that step's device → host copy (4 bytes into pinned
+    memory) and returns the value.  Valid until four more ``step_async`` calls have been made (the pinned slots are a ring)."""
+    __slots__ = ("_host", "_event")
+
+    def __init__(self, host: torch.Tensor, event: "torch.cuda.Event"):
+        self._host, self._event = host, event
+
+    def item(self) -> float:
+        self._event.synchronize()
+        return float(self._host[0])
+
+
 class AdapterTrainer:
     """One fine-tune step = H2D(waveforms, labels) → [mel+CMVN → encoder → lm_head → CTC loss+grad → adapter-only backward →
     all-reduce(adapter grads) → fused AdamW] → D2H(loss).  The bracketed part is ONE CUDA graph per input shape.
@@ -307,6 +320,7 @@ class AdapterTrainer:
         self._stage: Dict[tuple, dict] = {}
         self._staged = None
         self._copy_stream = None
+        self._loss_ring = None
         self._seen_version = None
         self.launches_per_step = 0
         self._warm_kernels()
@@ -536,6 +550,22 @@ class AdapterTrainer:
         loss = self._run(ent)
         self._last = ent
         return loss.clone()
+
+    def step_async(self, wave: Optional[torch.Tensor] = None, num_samples: Optional[torch.Tensor] = None,
+                   labels: Optional[torch.Tensor] = None, dialect=0) -> "LossHandle":
+        """``step()`` whose loss comes back through pinned host memory: the device → host copy of the loss is enqueued behind the
+        step and the returned handle's ``item()`` waits for THAT copy only.  A loop that calls ``item()`` on step i's handle after
+        launching step i+1 (what a trainer that logs the loss does) keeps one step queued on the device, so the host work between
+        two steps (batch staging, the launch itself, a scheduler hiccup) is not exposed."""
+        loss = self.step(wave, num_samples, labels, dialect=dialect)
+        if self._loss_ring is None:
+            self._loss_ring = [(torch.empty((1,), dtype=F32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_slot = 0
+        host, ev = self._loss_ring[self._loss_slot]
+        self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+        host.copy_(loss.view(1), non_blocking=True)
+        ev.record(torch.cuda.current_stream())
+        return LossHandle(host, ev)
 
     def _args(self, ent):
         return (ent["wave"], ent["nsamp"], ent["lengths"], ent["labels"], ent["max_frames"], ent["dialect"], ent["pk"])

@@ -7,6 +7,7 @@ cfg = P.JLConfig(hidden_size=d, num_hidden_layers=1, num_attention_heads=d // 64
 model = P.JLForCTC(cfg).cuda().eval()
 eng = model.encoder.engine(model.lm_head)
 ad = model.encoder.layers[0].adapter_ffn
+eng.fused_att = True
 h = torch.randn(B * T, d, device="cuda").to(torch.bfloat16)
 lengths = torch.full((B,), T, dtype=torch.int32, device="cuda")
 for training in (False, True, False, True):
