@@ -14,6 +14,18 @@ namespace jl {
 
 constexpr int LN_WARPS = 8;
 constexpr int LN_THREADS = LN_WARPS * 32;
+// CTA sizes of the two streaming kernels that run 72 times per step (forward; backward of the frozen norms): small CTAs spread
+// the 8000 rows evenly over the 148 SMs (250 CTAs of 32 rows leave 46 SMs with half the work of the others): 9.8 -> 9.3 us and 10.6 -> 10.0 us at 8000 x 768
+// with 2 warps per CTA (profiles/README.md).
+#ifndef JL_LN_FWD_WARPS
+#define JL_LN_FWD_WARPS 2
+#endif
+#ifndef JL_LN_FWD_HOIST
+#define JL_LN_FWD_HOIST 0
+#endif
+#ifndef JL_LN_BWD_WARPS
+#define JL_LN_BWD_WARPS 2
+#endif
 
 template <int NCH>
 __device__ __forceinline__ void ln_load_row(const __nv_bfloat16* row, int nchunks, int lane, float (&x)[NCH][8]) {
@@ -56,7 +68,7 @@ template <int NCH>
 __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_layernorm_fwd_params p) {
   jl::pdl_prologue();
   const int lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_ROWS;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LN_ROWS;
   if (row0 >= p.rows) return;
   const int nchunks = p.d >> 3;
   const float inv_d = 1.0f / static_cast<float>(p.d);
@@ -70,6 +82,16 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_laye
       raw[r][c] = (ch < nchunks) ? __ldg(reinterpret_cast<const uint4*>(xr) + ch) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
+#if JL_LN_FWD_HOIST
+  // γ, β of this lane's chunks once per warp (4 rows), not once per row: a quarter of the L1 traffic of the stream
+  float gq[NCH][8], bq[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = min(c * 32 + lane, nchunks - 1);
+    ln_load8_f32(p.gamma + ch * 8, gq[c]);
+    ln_load8_f32(p.beta + ch * 8, bq[c]);
+  }
+#endif
 #pragma unroll
   for (int r = 0; r < LN_ROWS; ++r) {
     const int row = row0 + r;
@@ -104,11 +126,17 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_fwd_kernel(const jl_laye
     for (int c = 0; c < NCH; ++c) {
       const int ch = c * 32 + lane;
       if (ch < nchunks) {
-        float g[8], b[8], o[8];
+        float o[8];
+#if JL_LN_FWD_HOIST
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, gq[c][j], bq[c][j]);
+#else
+        float g[8], b[8];
         ln_load8_f32(p.gamma + ch * 8, g);
         ln_load8_f32(p.beta + ch * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((x[c][j] - mean) * rstd, g[j], b[j]);
+#endif
         if (p.act == JL_EPI_GELU) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
@@ -136,7 +164,8 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const jl_laye
     for (int j = 0; j < 8; ++j) { dg[c][j] = 0.0f; db[c][j] = 0.0f; }
 
   constexpr int RB = WGRAD ? 1 : 2;       // rows per warp-iteration (the lean dx-only variant keeps two rows in flight)
-  for (int row0 = (blockIdx.x * LN_WARPS + warp) * RB; row0 < p.rows; row0 += gridDim.x * LN_WARPS * RB) {
+  const int nwarps = blockDim.x >> 5;
+  for (int row0 = (blockIdx.x * nwarps + warp) * RB; row0 < p.rows; row0 += gridDim.x * nwarps * RB) {
     uint4 rx[RB][NCH], rdy[RB][NCH], rdr[RB][NCH];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
@@ -448,11 +477,11 @@ int jl_layernorm_fwd(const jl_layernorm_fwd_params* p, void* stream) {
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int blocks = jl::ceil_div(p->rows, jl::LN_WARPS * jl::LN_ROWS);
+  const int blocks = jl::ceil_div(p->rows, JL_LN_FWD_WARPS * jl::LN_ROWS);
   switch (jl::ln_pick(p->d)) {
-    case 3: jl::launch(jl::layernorm_fwd_kernel<3>, blocks, jl::LN_THREADS, 0, s, *p); break;
-    case 4: jl::launch(jl::layernorm_fwd_kernel<4>, blocks, jl::LN_THREADS, 0, s, *p); break;
-    default: jl::launch(jl::layernorm_fwd_kernel<8>, blocks, jl::LN_THREADS, 0, s, *p); break;
+    case 3: jl::launch(jl::layernorm_fwd_kernel<3>, blocks, JL_LN_FWD_WARPS * 32, 0, s, *p); break;
+    case 4: jl::launch(jl::layernorm_fwd_kernel<4>, blocks, JL_LN_FWD_WARPS * 32, 0, s, *p); break;
+    default: jl::launch(jl::layernorm_fwd_kernel<8>, blocks, JL_LN_FWD_WARPS * 32, 0, s, *p); break;
   }
   JL_CHECK_LAUNCH("layernorm_fwd");
   return JL_OK;
@@ -513,20 +542,20 @@ int jl_layernorm_bwd(const jl_layernorm_bwd_params* p, void* stream) {
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, jl::LN_WARPS * 2);
+  const int blocks = (p->dgamma != nullptr) ? jl::ln_bwd_blocks(p->rows) : jl::ceil_div(p->rows, JL_LN_BWD_WARPS * 2);
   const bool wg = p->dgamma != nullptr;
   switch (jl::ln_pick(p->d)) {
     case 3:
       if (wg) jl::launch(jl::layernorm_bwd_kernel<3, true>, blocks, jl::LN_THREADS, 0, s, *p);
-      else jl::launch(jl::layernorm_bwd_kernel<3, false>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<3, false>, blocks, JL_LN_BWD_WARPS * 32, 0, s, *p);
       break;
     case 4:
       if (wg) jl::launch(jl::layernorm_bwd_kernel<4, true>, blocks, jl::LN_THREADS, 0, s, *p);
-      else jl::launch(jl::layernorm_bwd_kernel<4, false>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<4, false>, blocks, JL_LN_BWD_WARPS * 32, 0, s, *p);
       break;
     default:
       if (wg) jl::launch(jl::layernorm_bwd_kernel<8, true>, blocks, jl::LN_THREADS, 0, s, *p);
-      else jl::launch(jl::layernorm_bwd_kernel<8, false>, blocks, jl::LN_THREADS, 0, s, *p);
+      else jl::launch(jl::layernorm_bwd_kernel<8, false>, blocks, JL_LN_BWD_WARPS * 32, 0, s, *p);
       break;
   }
   JL_CHECK_LAUNCH("layernorm_bwd");
