@@ -255,6 +255,29 @@ typedef struct {
 int jl_lnfold_pack(const jl_lnfold_pack_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a7 (backward): backward through "LayerNorm → narrow projection" in one kernel — the tail of the AttAdapter backward:
+ *   forward  y = LN(h) W^T + b   (W [n, d], n = 64 / 128 / 192: the q|k|v projection)
+ *   dz = dy W;   dx = LayerNorm'(dz; h, mean, rstd, gamma) + dres
+ * Replaces jl_gemm_bf16 (dy · W) + jl_layernorm_bwd (SP/transformers/models/wav2vec2/modeling_wav2vec2.py:941 analogue under
+ * autograd).  s / tb are the LayerNorm-fold vectors of jl_lnfold_pack for this projection; y is the projection output saved by
+ * the forward pass.  dz (optional) receives dy W in bf16 for the LayerNorm weight gradients (jl_layernorm_wgrad).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* dy; int64_t lddy;        /* bf16 [rows, n] */
+  const void* y; int64_t ldy;          /* bf16 [rows, n] saved forward output (bias included) */
+  const void* w;                       /* bf16 [n, d] contiguous (unscaled projection weight) */
+  const float* s; const float* tb;     /* fp32 [n] */
+  const float* gamma;                  /* fp32 [d] */
+  const void* h; int64_t ldh;          /* bf16 [rows, d] LayerNorm input */
+  const float* mean; const float* rstd;/* fp32 [rows] */
+  const void* dres; int64_t lddres;    /* bf16 [rows, d] gradient of the residual branch (added) */
+  void* dx; int64_t lddx;              /* bf16 [rows, d] out */
+  void* dz; int64_t lddz;              /* optional bf16 [rows, d] out */
+  int32_t rows, n, d;                  /* d a multiple of 64, at most 1024 */
+} jl_lnproj_bwd_params;
+int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;
  * /root/reference/README.md:1 "multi-dialect knowledge transfer" + "adapter with attention").  Per frame:
  *   alpha = softmax_k(q . key_k * scale),   out = h + sum_k alpha_k y_k

@@ -76,6 +76,12 @@ class LnFoldPackParams(C.Structure):
     _fields_ = [("w", vp), ("bias", vp), ("gamma", vp), ("beta", vp), ("w_scaled", vp), ("s", vp), ("tb", vp), ("n", i32), ("d", i32)]
 
 
+class LnProjBwdParams(C.Structure):
+    _fields_ = [("dy", vp), ("lddy", i64), ("y", vp), ("ldy", i64), ("w", vp), ("s", vp), ("tb", vp), ("gamma", vp), ("h", vp), ("ldh", i64),
+                ("mean", vp), ("rstd", vp), ("dres", vp), ("lddres", i64), ("dx", vp), ("lddx", i64), ("dz", vp), ("lddz", i64),
+                ("rows", i32), ("n", i32), ("d", i32)]
+
+
 class FusionParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("y", vp), ("ldy", i64), ("y_stride", i64), ("q", vp), ("ldq", i64), ("key", vp), ("ldkey", i64),
                 ("key_stride", i64), ("out", vp), ("ldo", i64), ("alpha", vp), ("dout", vp), ("lddout", i64), ("dy", vp), ("lddy", i64),
@@ -139,6 +145,7 @@ SYMBOLS = {
     "jl_wfadapter_pack": (C.c_int, [C.POINTER(WFAdapterPackParams), vp]),
     "jl_attadapter_fwd": (C.c_int, [C.POINTER(AttAdapterFwdParams), vp]),
     "jl_lnfold_pack": (C.c_int, [C.POINTER(LnFoldPackParams), vp]),
+    "jl_lnproj_bwd": (C.c_int, [C.POINTER(LnProjBwdParams), vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),

@@ -1,0 +1,312 @@
+// Backward through "LayerNorm → narrow projection" in ONE kernel (the tail of the AttAdapter backward, a7):
+//
+//   forward:   y = LN(h) Wᵀ + b          W [n, d], n <= 192 (the AttAdapter's q | k | v projection: n = 192)
+//   backward:  dz = dy · W               [rows, d]    (gradient of the LayerNorm output)
+//              dh = LN'(dz) + dres       dh_ij = rstd_i (dz_ij γ_j − c1_i − x̂_ij c2_i) + dres_ij,  x̂ = (h − μ) rstd
+//              c1_i = mean_j(dz_ij γ_j),  c2_i = mean_j(dz_ij γ_j x̂_ij)
+//
+// It replaces jl_gemm_bf16 (dy · W, 10 µs at 8000 × 768 × 192) + jl_layernorm_bwd (10.6 µs), and the HBM round trip of dz between
+// them.  The two row means do NOT need the full dz row: with the LayerNorm-fold vectors of the forward kernel (jl_lnfold_pack:
+// W' = bf16(W ⊙ γ), s_k = Σ_j W'_kj, t_k = Σ_j W_kj β_j + b_k)
+//   c1_i = (1/d) Σ_k dy_ik s_k                       because Σ_j dz_ij γ_j = Σ_k dy_ik Σ_j W_kj γ_j
+//   c2_i = (1/d) Σ_k dy_ik (y_ik − t_k)              because Σ_j W'_kj x̂_ij = y_ik − t_k  (the forward projection itself)
+// are dot products over the n <= 192 columns of dy and the SAVED y — a prologue — so the product runs once, chunk by chunk, and
+// every chunk's epilogue emits final dh.
+//
+// CTA = 128 rows, 384 threads: warp 0 TMA producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator, warps 4-11 epilogue.
+//   A = dy tile [128 x n] resident (K-major, n / 64 swizzled tiles); B = W[:, 64-column chunk] as it lies in memory ([n, 64] box,
+//   read MN-major); per chunk the h and dres tiles arrive by TMA in staging buffers (3 deep), each thread folds its row of the
+//   accumulator into the dres tile in place (and dz into the h tile when the caller wants it for dγ / dβ), and the tiles leave
+//   with coalesced 16-byte stores.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace jl {
+
+constexpr int LP_THREADS = 384;
+constexpr int LP_BUFS = 3;                          // B chunk / staging buffers
+constexpr int LP_ACC = 8;                           // TMEM accumulators of 64 columns
+constexpr uint32_t LP_T128 = 128 * 128;             // bytes of a [128 x 64] bf16 tile
+constexpr uint32_t LP_BCH = 192 * 128;              // bytes of a [192 x 64] bf16 box
+constexpr int LP_MAX_D = 1024;
+
+struct __align__(1024) LpSmem {
+  uint8_t a[3][LP_T128];                // dy tiles (k = 64-column groups of dy)
+  uint8_t b[LP_BUFS][LP_BCH];           // W[0:n, chunk]: n rows of 64 contiguous columns
+  uint8_t hs[LP_BUFS][LP_T128];         // h tile of the chunk (first: the saved y tiles for the prologue); dz in place
+  uint8_t rs[LP_BUFS][LP_T128];         // dres tile of the chunk; dh in place
+  float gamma[LP_MAX_D];
+  float fs[192], ftb[192];
+  float red1[2][128], red2[2][128];
+  uint64_t a_full, y_full, y_done;
+  uint64_t b_full[LP_BUFS], b_empty[LP_BUFS], h_full[LP_BUFS], r_full[LP_BUFS], stg_empty[LP_BUFS];
+  uint64_t acc_full[LP_ACC], acc_empty[LP_ACC];
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t lp_chunk_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint4 lp_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// coalesced copy of one [128 x 64] bf16 tile to global rows (256 threads; thread t: 16-byte chunk t & 7 of rows (t >> 3) + 32 j)
+__device__ __forceinline__ void lp_tile_to_global(uint32_t tile, __nv_bfloat16* dst, int64_t ld, int rows_valid, int t) {
+  const int ch = t & 7, r0 = t >> 3;
+  const uint32_t off = static_cast<uint32_t>(r0 * 128 + ((ch ^ (r0 & 7)) << 4));
+  uint4 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = lp_lds128(tile + off + j * 4096);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (r0 + 32 * j < rows_valid) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r0 + 32 * j) * ld + ch * 8) = v[j];
+}
+
+__global__ void __launch_bounds__(LP_THREADS, 1)
+lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constant__ CUtensorMap t_y, const __grid_constant__ CUtensorMap t_w,
+                  const __grid_constant__ CUtensorMap t_h, const __grid_constant__ CUtensorMap t_r, const jl_lnproj_bwd_params p) {
+  extern __shared__ uint8_t lp_smem_raw[];
+  LpSmem& s = *reinterpret_cast<LpSmem*>(lp_smem_raw + ((1024u - (ptx::smem_u32(lp_smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128;
+  const int nkt = p.n / 64;                         // 64-wide k tiles (columns of dy)
+  // the 64-column output chunks of the row tile may be split between gridDim.y CTAs (each repeats the small prologue): an SM takes
+  // in ≈ 57 B/clk and stores ≈ 28 B/clk (see the host function for when)
+  const int nc_all = p.d / 64;
+  const int c_begin = static_cast<int>((static_cast<int64_t>(nc_all) * blockIdx.y) / gridDim.y);
+  const int c_end = static_cast<int>((static_cast<int64_t>(nc_all) * (blockIdx.y + 1)) / gridDim.y);
+  const int nc = c_end - c_begin;                   // chunks of this CTA: global chunk index c_begin + c
+  const int rows_valid = min(128, p.rows - row0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&t_dy);
+    ptx::prefetch_tensormap(&t_y);
+    ptx::prefetch_tensormap(&t_w);
+    ptx::prefetch_tensormap(&t_h);
+    ptx::prefetch_tensormap(&t_r);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(&s.a_full, 1);
+    ptx::mbar_init(&s.y_full, 1);
+    ptx::mbar_init(&s.y_done, 8);
+    for (int i = 0; i < LP_BUFS; ++i) {
+      ptx::mbar_init(&s.b_full[i], 1);
+      ptx::mbar_init(&s.b_empty[i], 1);
+      ptx::mbar_init(&s.h_full[i], 1);
+      ptx::mbar_init(&s.r_full[i], 1);
+      ptx::mbar_init(&s.stg_empty[i], 1);
+    }
+    for (int i = 0; i < LP_ACC; ++i) {
+      ptx::mbar_init(&s.acc_full[i], 1);
+      ptx::mbar_init(&s.acc_empty[i], 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&s.tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s.tmem_slot;
+  jl::pdl_prologue();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&s.a_full, nkt * LP_T128);
+      for (int kt = 0; kt < nkt; ++kt) ptx::tma_load_2d(s.a[kt], &t_dy, &s.a_full, kt * 64, row0);
+      ptx::mbar_expect_tx(&s.y_full, nkt * LP_T128);
+      for (int kt = 0; kt < nkt; ++kt) ptx::tma_load_2d(s.hs[kt], &t_y, &s.y_full, kt * 64, row0);
+      for (int c = 0; c < min(nc, LP_BUFS); ++c) {
+        ptx::mbar_expect_tx(&s.b_full[c], p.n * 128);
+        ptx::tma_load_2d(s.b[c], &t_w, &s.b_full[c], (c_begin + c) * 64, 0);
+        ptx::mbar_expect_tx(&s.r_full[c], LP_T128);
+        ptx::tma_load_2d(s.rs[c], &t_r, &s.r_full[c], (c_begin + c) * 64, row0);
+      }
+      ptx::mbar_wait(&s.y_done, 0);                 // the prologue has read the saved y tiles: their buffers take h tiles now
+      for (int c = 0; c < min(nc, LP_BUFS); ++c) {
+        ptx::mbar_expect_tx(&s.h_full[c], LP_T128);
+        ptx::tma_load_2d(s.hs[c], &t_h, &s.h_full[c], (c_begin + c) * 64, row0);
+      }
+      for (int c = LP_BUFS; c < nc; ++c) {
+        const int bi = c % LP_BUFS;
+        const uint32_t par = ((c / LP_BUFS) - 1) & 1;
+        ptx::mbar_wait(&s.b_empty[bi], par);
+        ptx::mbar_expect_tx(&s.b_full[bi], p.n * 128);
+        ptx::tma_load_2d(s.b[bi], &t_w, &s.b_full[bi], (c_begin + c) * 64, 0);
+        ptx::mbar_wait(&s.stg_empty[bi], par);
+        ptx::mbar_expect_tx(&s.h_full[bi], LP_T128);
+        ptx::tma_load_2d(s.hs[bi], &t_h, &s.h_full[bi], (c_begin + c) * 64, row0);
+        ptx::mbar_expect_tx(&s.r_full[bi], LP_T128);
+        ptx::tma_load_2d(s.rs[bi], &t_r, &s.r_full[bi], (c_begin + c) * 64, row0);
+        if (c == nc - 1) jl::pdl_trigger_late();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(&s.a_full, 0);
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64) | (1u << 16);      // B operand MN-major
+      for (int c = 0; c < nc; ++c) {
+        const int bi = c % LP_BUFS, ai = c % LP_ACC;
+        ptx::mbar_wait(&s.b_full[bi], (c / LP_BUFS) & 1);
+        ptx::mbar_wait(&s.acc_empty[ai], ((c / LP_ACC) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t bb = ptx::smem_u32(s.b[bi]);
+        for (int kt = 0; kt < nkt; ++kt) {
+          const uint32_t ab = ptx::smem_u32(s.a[kt]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem + ai * 64, ptx::make_sw128_desc(ab + k * 32, 16, 1024), ptx::make_sw128_desc(bb + kt * 8192 + k * 2048, 8192, 1024), idesc,
+                           (kt > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&s.b_empty[bi]);
+        ptx::umma_commit(&s.acc_full[ai]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = quad * 32 + lane;                      // TMEM lane = row of the tile
+    const int et = threadIdx.x - 128;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int row = row0 + r;
+    for (int i = et; i < p.d; i += 256) s.gamma[i] = __ldg(p.gamma + i);
+    if (et < p.n) { s.fs[et] = __ldg(p.s + et); s.ftb[et] = __ldg(p.tb + et); }
+    const float mu = row < p.rows ? __ldg(p.mean + row) : 0.0f;
+    const float rstd = row < p.rows ? __ldg(p.rstd + row) : 0.0f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- prologue: c1, c2 from dy and the saved y (this thread: every other 16-byte chunk group of its row)
+    ptx::mbar_wait(&s.a_full, 0);
+    ptx::mbar_wait(&s.y_full, 0);
+    float p1 = 0.0f, p2 = 0.0f;
+    for (int kt = 0; kt < nkt; ++kt) {
+      const uint32_t at = ptx::smem_u32(s.a[kt]), yt = ptx::smem_u32(s.hs[kt]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = grp * 4 + j;
+        const uint4 dv = lp_lds128(at + lp_chunk_off(r, ch)), yv = lp_lds128(yt + lp_chunk_off(r, ch));
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        const float* fs = s.fs + kt * 64 + ch * 8;
+        const float* ft = s.ftb + kt * 64 + ch * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 d2 = unpack_bf16x2(dw[q]), y2 = unpack_bf16x2(yw[q]);
+          p1 = fmaf(d2.x, fs[2 * q], p1);
+          p1 = fmaf(d2.y, fs[2 * q + 1], p1);
+          p2 = fmaf(d2.x, y2.x - ft[2 * q], p2);
+          p2 = fmaf(d2.y, y2.y - ft[2 * q + 1], p2);
+        }
+      }
+    }
+    s.red1[grp][r] = p1;
+    s.red2[grp][r] = p2;
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&s.y_done);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv_d = 1.0f / static_cast<float>(p.d);
+    const float c1 = (s.red1[0][r] + s.red1[1][r]) * inv_d;
+    const float c2 = (s.red2[0][r] + s.red2[1][r]) * inv_d;
+    const float nmr = -mu * rstd;
+    __nv_bfloat16* dx_tile = reinterpret_cast<__nv_bfloat16*>(p.dx) + static_cast<int64_t>(row0) * p.lddx;
+    __nv_bfloat16* dz_tile = p.dz ? reinterpret_cast<__nv_bfloat16*>(p.dz) + static_cast<int64_t>(row0) * p.lddz : nullptr;
+    // ---- chunks of 64 output columns: this thread = row r, columns grp * 32 … + 32
+    for (int c = 0; c < nc; ++c) {
+      const int bi = c % LP_BUFS, ai = c % LP_ACC;
+      ptx::mbar_wait(&s.acc_full[ai], (c / LP_ACC) & 1);
+      ptx::mbar_wait(&s.h_full[bi], (c / LP_BUFS) & 1);
+      ptx::mbar_wait(&s.r_full[bi], (c / LP_BUFS) & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem + ai * 64 + lane_off + grp * 32, v);
+      ptx::tmem_ld_wait();
+      const uint32_t ht = ptx::smem_u32(s.hs[bi]), rt = ptx::smem_u32(s.rs[bi]);
+      const float* gam = s.gamma + (c_begin + c) * 64 + grp * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = lp_chunk_off(r, grp * 4 + j);
+        const uint4 hv = lp_lds128(ht + off), rv = lp_lds128(rt + off);
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        const float4 g0 = *reinterpret_cast<const float4*>(gam + j * 8), g1 = *reinterpret_cast<const float4*>(gam + j * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        uint32_t ox[4], oz[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 h2 = unpack_bf16x2(hw[q]), r2 = unpack_bf16x2(rw[q]);
+          const float z0 = __uint_as_float(v[j * 8 + 2 * q]), z1 = __uint_as_float(v[j * 8 + 2 * q + 1]);
+          const float x0 = fmaf(h2.x, rstd, nmr), x1 = fmaf(h2.y, rstd, nmr);
+          const float t0 = fmaf(-x0, c2, fmaf(z0, gg[2 * q], -c1)), t1 = fmaf(-x1, c2, fmaf(z1, gg[2 * q + 1], -c1));
+          ox[q] = pack_bf16x2(fmaf(rstd, t0, r2.x), fmaf(rstd, t1, r2.y));
+          oz[q] = pack_bf16x2(z0, z1);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rt + off), "r"(ox[0]), "r"(ox[1]), "r"(ox[2]), "r"(ox[3]) : "memory");
+        if (dz_tile != nullptr)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ht + off), "r"(oz[0]), "r"(oz[1]), "r"(oz[2]), "r"(oz[3]) : "memory");
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s.acc_empty[ai]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      lp_tile_to_global(rt, dx_tile + (c_begin + c) * 64, p.lddx, rows_valid, et);
+      if (dz_tile != nullptr) lp_tile_to_global(ht, dz_tile + (c_begin + c) * 64, p.lddz, rows_valid, et);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&s.stg_empty[bi]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace jl
+
+extern "C" {
+
+int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
+  JL_REQUIRE(p != nullptr, JL_EINVAL, "lnproj_bwd: null params");
+  JL_REQUIRE(p->dy && p->y && p->w && p->s && p->tb && p->gamma && p->h && p->mean && p->rstd && p->dres && p->dx, JL_EINVAL, "lnproj_bwd: null pointer");
+  JL_REQUIRE(p->rows > 0, JL_EINVAL, "lnproj_bwd: rows must be positive");
+  JL_REQUIRE(p->n >= 64 && p->n <= 192 && (p->n % 64) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: n must be 64, 128 or 192 (got %d)", p->n);
+  JL_REQUIRE(p->d >= 64 && (p->d % 64) == 0 && p->d <= jl::LP_MAX_D, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: d must be a multiple of 64, at most %d (got %d)",
+             jl::LP_MAX_D, p->d);
+  JL_REQUIRE((p->lddy % 8) == 0 && (p->ldy % 8) == 0 && (p->ldh % 8) == 0 && (p->lddres % 8) == 0 && (p->lddx % 8) == 0 && (p->dz == nullptr || (p->lddz % 8) == 0),
+             JL_EINVAL, "lnproj_bwd: row strides must be multiples of 8 elements");
+  for (const void* q : {p->dy, p->y, p->w, p->h, p->dres, static_cast<const void*>(p->dx), static_cast<const void*>(p->dz)})
+    JL_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, JL_EINVAL, "lnproj_bwd: pointers must be 16-byte aligned");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  CUtensorMap t_dy, t_y, t_w, t_h, t_r;
+  rc = jl::make_tma_map_2d_bf16(&t_dy, p->dy, p->n, p->rows, p->lddy, 128);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_y, p->y, p->n, p->rows, p->ldy, 128);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->w, p->d, p->n, p->d, p->n);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_h, p->h, p->d, p->rows, p->ldh, 128);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_r, p->dres, p->d, p->rows, p->lddres, 128);
+  if (rc != JL_OK) return rc;
+  const size_t smem = sizeof(jl::LpSmem) + 1024;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(jl::lnproj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "lnproj_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured_dev = dev;
+  }
+  const int row_tiles = jl::ceil_div(p->rows, 128);
+  // Two CTAs per row tile (column halves) make the kernel itself faster (8000 x 768: 12.7 vs 19.9 µs with dz) but the fine-tune step
+  // slower (6.20 vs 6.17 ms): there the weight-gradient branch fills the SMs this kernel leaves idle, and the split repeats the
+  // prologue.  So: split only when the row tiles alone would leave most of the machine idle AND nothing else is likely to run.
+  const int split = (row_tiles * 8 <= jl::num_sms() && p->d >= 128) ? 2 : 1;
+  jl::launch(jl::lnproj_bwd_kernel, dim3(row_tiles, split), jl::LP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_dy, t_y, t_w, t_h, t_r, *p);
+  JL_CHECK_LAUNCH("lnproj_bwd");
+  return JL_OK;
+}
+
+}  // extern "C"

@@ -392,6 +392,8 @@ class JLEngine:
         self.fused_wf_train = os.environ.get("JL_FUSED_WF_TRAIN", "0") == "1"
         # AttAdapter forward as one kernel (jl_attadapter_fwd) for utterances of <= 256 frames, inference and training
         self.fused_att = os.environ.get("JL_FUSED_ATT", "1") != "0"
+        # tail of the AttAdapter backward (dqkv · W_qkv + LayerNorm backward) as one kernel (jl_lnproj_bwd)
+        self.fused_att_bwd = os.environ.get("JL_FUSED_ATT_BWD", "1") != "0"
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._wf_bufs: Dict[int, dict] = {}
@@ -567,15 +569,15 @@ class JLEngine:
         self._wf_bufs[id(ad)] = bufs
         return bufs
 
-    def _att_pack_dev(self, ad, training: bool) -> dict:
+    def _att_pack_dev(self, ad, training: bool, reuse: bool = False) -> dict:
         """LayerNorm-folded q|k|v projection of an AttAdapter (jl_lnfold_pack), derived on the device into buffers that keep their
         addresses.  Training: re-derived at every call (inside the captured step it follows the optimizer); inference: only when
         a parameter changed."""
         ps = [ad.norm.weight, ad.norm.bias, ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight, ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
         ver = tuple((q.data_ptr(), q._version) for q in ps) + (self.flat.generation if self.flat is not None else 0,)
         ent = self._att_bufs.get(id(ad))
-        if ent is not None and not training and ent[0] == ver:
-            return ent[1]
+        if ent is not None and (reuse or (not training and ent[0] == ver)):
+            return ent[1]          # reuse: the backward pass of the step whose forward pass derived the pack
         w = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
         bq = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
         bufs = ops.lnfold_pack(w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), None if ent is None else ent[1])
@@ -854,6 +856,7 @@ class JLEngine:
                         g.out(prm, k).zero_()
         else:
             h, mean, rstd, z, qkv, a, lse = saved
+            fused_fwd = z is None
             if z is None:
                 # the fused forward kernel never wrote LN(h); only dW_qkv = dqkvᵀ · LN(h) needs it: recomputed on the weight-gradient
                 # branch into a buffer allocated here, on the main stream
@@ -885,6 +888,24 @@ class JLEngine:
             sb.run(w_qkv, dqkv, z)
             if jobs is not None:
                 jobs.append(dict(dy=dqkv, out_sum=gb_cat, scatter=(bs, gb_cat)))
+            if self.fused_att_bwd and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024:
+                # dqkv · W_qkv and the LayerNorm backward in one kernel (its row means come from dqkv and the saved q|k|v); dz is
+                # still written, for the LayerNorm weight gradients on the side branch
+                dh, dz = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd),
+                                        ad.norm.weight.detach(), h, mean, rstd, dy, want_dz=True)
+                if jobs is not None:
+                    jobs.append(dict(dy=dz, x=h, mean=mean, rstd=rstd, out_sum=g.out(ad.norm.bias), out_dot=g.out(ad.norm.weight)))
+
+                    def reduce_all(jobs=jobs):
+                        for i in range(0, len(jobs), 4):
+                            ops.colreduce_multi(jobs[i:i + 4])
+                        for j in jobs:
+                            if "scatter" in j:
+                                g.scatter_cat(*j["scatter"])
+                    sb.run(reduce_all, dz, h, mean, rstd, *[j["dy"] for j in jobs])
+                else:
+                    sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
+                return dh
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
         if _LN_WGRAD == "main":
             dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True, dgamma=g.out(ad.norm.weight),

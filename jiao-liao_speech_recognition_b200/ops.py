@@ -402,6 +402,32 @@ def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tens
     return out, saved
 
 
+def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
+               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False):
+    """Backward through LayerNorm → projection (W [n, d], n in {64, 128, 192}) in one kernel: dx = LayerNorm'(dy · W) + dres.
+    ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
+    dz = dy · W (bf16) only when ``want_dz`` (the LayerNorm weight gradients need it)."""
+    _need(dy, BF16, "dy", 2)
+    _need(y, BF16, "y", 2)
+    _need(w, BF16, "w", 2)
+    _need(h, BF16, "h", 2)
+    _need(dres, BF16, "dres", 2)
+    for t_, nm in ((dy, "dy"), (y, "y"), (h, "h"), (dres, "dres")):
+        _rows2d(t_, nm)
+    rows, n = dy.shape
+    d = h.shape[1]
+    if y.shape != (rows, n) or w.shape != (n, d) or not w.is_contiguous() or h.shape[0] != rows or dres.shape != (rows, d):
+        raise ValueError("lnproj_bwd: shapes do not match")
+    dx = torch.empty((rows, d), dtype=BF16, device=h.device)
+    dz = torch.empty((rows, d), dtype=BF16, device=h.device) if want_dz else None
+    p = L.LnProjBwdParams(dy=dy.data_ptr(), lddy=dy.stride(0), y=y.data_ptr(), ldy=y.stride(0), w=w.data_ptr(), s=pack["s"].data_ptr(),
+                          tb=pack["tb"].data_ptr(), gamma=gamma.data_ptr(), h=h.data_ptr(), ldh=h.stride(0), mean=mean.data_ptr(),
+                          rstd=rstd.data_ptr(), dres=dres.data_ptr(), lddres=dres.stride(0), dx=dx.data_ptr(), lddx=dx.stride(0),
+                          dz=_ptr(dz), lddz=dz.stride(0) if dz is not None else 0, rows=rows, n=n, d=d)
+    L.check(L.load().jl_lnproj_bwd(C.byref(p), _stream()))
+    return dx, dz
+
+
 # ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)
 def _fusion_params(y, q, key, alpha, scale):
     kk, rows, d = y.shape

@@ -7,7 +7,7 @@ name=$1; shift
 PKG=jiao-liao_speech_recognition_b200
 OBJ=build/obj_$name
 mkdir -p $OBJ
-SRCS="common gemm_tcgen05 mel_cmvn layernorm ctc elementwise attention attention_tc wfadapter_tc comm w2v_frontend fusion attadapter_tc"
+SRCS="common gemm_tcgen05 mel_cmvn layernorm ctc elementwise attention attention_tc wfadapter_tc comm w2v_frontend fusion attadapter_tc lnproj_bwd_tc"
 for s in $SRCS; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -c $PKG/csrc/$s.cu -o $OBJ/$s.o &
 done

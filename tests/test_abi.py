@@ -41,6 +41,7 @@ STRUCTS = {
     "jl_wfadapter_pack_params": "WFAdapterPackParams",
     "jl_attadapter_fwd_params": "AttAdapterFwdParams",
     "jl_lnfold_pack_params": "LnFoldPackParams",
+    "jl_lnproj_bwd_params": "LnProjBwdParams",
 }
 
 

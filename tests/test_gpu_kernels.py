@@ -618,3 +618,43 @@ def test_attadapter_fused_is_bit_reproducible_and_matches_the_composed_path_on_r
     dl, dr = (out0.float() - h.float())[valid], (ref.float() - h.float())[valid]
     assert rel_err(dl, dr) < 3e-2, rel_err(dl, dr)
     assert rel_err(out0[valid].float(), ref[valid].float()) < 1.5e-2      # two bf16 roundings of h + a (amplified) adapter update
+
+
+@pytest.mark.parametrize("rows,n,d", [(8000, 192, 768), (1000, 192, 1024), (333, 64, 128), (129, 128, 256), (5, 192, 768)])
+def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d):
+    """jl_lnproj_bwd (dy · W + LayerNorm backward in one kernel, row means from dy and the saved projection output) vs (a) plain
+    fp32 autograd through LayerNorm → Linear and (b) the two-kernel path it replaces (jl_gemm_bf16 + jl_layernorm_bwd)."""
+    P = pkg()
+    ops = P.ops
+    g = _g(31)
+    h = (torch.randn(rows, d, device="cuda", generator=g) * 1.4 + 0.3).to(BF16)
+    w = (torch.randn(n, d, device="cuda", generator=g) * 0.06).to(BF16)
+    bias = torch.randn(n, device="cuda", generator=g) * 0.1
+    gamma = 1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    dy = (torch.randn(rows, n, device="cuda", generator=g) * 0.5).to(BF16)
+    dres = (torch.randn(rows, d, device="cuda", generator=g) * 0.3).to(BF16)
+    eps = 1e-5
+    # fp32 reference
+    hf = h.float().requires_grad_(True)
+    z = F.layer_norm(hf, (d,), gamma, beta, eps)
+    yref = z @ w.float().T + bias
+    (yref * dy.float()).sum().backward()
+    dx_ref = hf.grad + dres.float()
+    dz_ref = dy.float() @ w.float()
+    # product path: forward pieces the kernel consumes
+    zb, mean, rstd = ops.layernorm_fwd(h, gamma, beta, eps, save_stats=True)
+    pack = ops.lnfold_pack(w, bias, gamma, beta)
+    y = yref.detach().to(BF16)                                   # what the forward pass saved (bf16)
+    dx, dz = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_dz=True)
+    dx2, none = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres)
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(dx, dx2)
+    assert rel_err(dz.float(), dz_ref) < 6e-3, rel_err(dz.float(), dz_ref)
+    assert rel_err(dx.float() - dres.float(), dx_ref - dres.float()) < 1.5e-2, rel_err(dx.float() - dres.float(), dx_ref - dres.float())
+    # the two-kernel path
+    dz2 = ops.gemm(dy, w, b_layout=P._lib.JL_LAYOUT_MN) if hasattr(P._lib, "JL_LAYOUT_MN") else ops.gemm(dy, w, b_layout=1)
+    dxc, _, _ = ops.layernorm_bwd(dz2, h, gamma, mean, rstd, dres=dres)
+    torch.cuda.synchronize()
+    e_fused, e_two = rel_err(dx.float() - dres.float(), dx_ref - dres.float()), rel_err(dxc.float() - dres.float(), dx_ref - dres.float())
+    assert e_fused <= max(1.5 * e_two, 8e-3), (e_fused, e_two)     # no less accurate than what it replaces (dz is not rounded to bf16 here)
