@@ -274,8 +274,13 @@ typedef struct {
   void* dx; int64_t lddx;              /* bf16 [rows, d] out */
   void* dz; int64_t lddz;              /* optional bf16 [rows, d] out */
   int32_t rows, n, d;                  /* d a multiple of 64, at most 1024 */
+  float* col_partial;                  /* optional fp32 [3][ceil(rows / 128)][d]: per-row-tile column sums of dz (→ dbeta), dz * xhat
+                                          (→ dgamma) and dres (→ the bias gradient of the layer whose output gradient dres is), to be
+                                          summed by jl_lnproj_bwd_reduce — the LayerNorm weight gradients without a dz tensor */
 } jl_lnproj_bwd_params;
 int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
+/* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial */
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;

@@ -19,6 +19,7 @@
 //   accumulator into the dres tile in place (and dz into the h tile when the caller wants it for dγ / dβ), and the tiles leave
 //   with coalesced 16-byte stores.
 #include <cuda.h>
+#include <cstddef>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -46,6 +47,8 @@ struct __align__(1024) LpSmem {
   uint32_t tmem_slot;
 };
 
+static_assert(offsetof(LpSmem, ftb) == offsetof(LpSmem, fs) + 192 * 4 && offsetof(LpSmem, red1) == offsetof(LpSmem, ftb) + 192 * 4 &&
+              offsetof(LpSmem, red2) == offsetof(LpSmem, red1) + 2 * 128 * 4, "the column-partial scratch aliases fs | ftb | red1 | red2");
 __device__ __forceinline__ uint32_t lp_chunk_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
 __device__ __forceinline__ uint4 lp_lds128(uint32_t addr) {
   uint4 v;
@@ -62,6 +65,22 @@ __device__ __forceinline__ void lp_tile_to_global(uint32_t tile, __nv_bfloat16* 
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (r0 + 32 * j < rows_valid) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r0 + 32 * j) * ld + ch * 8) = v[j];
+}
+
+// Column sums over the 32 rows a warp holds: in: a[j] = this lane's (row's) value in column j; out (return value): the sum over the
+// warp's 32 rows of column `lane`.  Recursive halving — 31 shuffles instead of the 160 of 32 butterfly reductions; fixed order.
+__device__ __forceinline__ float lp_warp_colsum(float (&a)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? a[i] : a[i + off];
+      const float keep = upper ? a[i + off] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return a[0];
 }
 
 __global__ void __launch_bounds__(LP_THREADS, 1)
@@ -210,6 +229,8 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
     const float c1 = (s.red1[0][r] + s.red1[1][r]) * inv_d;
     const float c2 = (s.red2[0][r] + s.red2[1][r]) * inv_d;
     const float nmr = -mu * rstd;
+    const bool want_cols = p.col_partial != nullptr;
+    float* colp = s.fs;                 // [3][4][64] floats over fs | ftb | red1 | red2 (3584 B): all dead after the prologue
     __nv_bfloat16* dx_tile = reinterpret_cast<__nv_bfloat16*>(p.dx) + static_cast<int64_t>(row0) * p.lddx;
     __nv_bfloat16* dz_tile = p.dz ? reinterpret_cast<__nv_bfloat16*>(p.dz) + static_cast<int64_t>(row0) * p.lddz : nullptr;
     // ---- chunks of 64 output columns: this thread = row r, columns grp * 32 … + 32
@@ -220,6 +241,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
       ptx::mbar_wait(&s.r_full[bi], (c / LP_BUFS) & 1);
       ptx::tc_fence_after();
       uint32_t v[32];
+      float zx[32], ro[32];
       ptx::tmem_ld_32x32(tmem + ai * 64 + lane_off + grp * 32, v);
       ptx::tmem_ld_wait();
       const uint32_t ht = ptx::smem_u32(s.hs[bi]), rt = ptx::smem_u32(s.rs[bi]);
@@ -237,6 +259,12 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
           const float2 h2 = unpack_bf16x2(hw[q]), r2 = unpack_bf16x2(rw[q]);
           const float z0 = __uint_as_float(v[j * 8 + 2 * q]), z1 = __uint_as_float(v[j * 8 + 2 * q + 1]);
           const float x0 = fmaf(h2.x, rstd, nmr), x1 = fmaf(h2.y, rstd, nmr);
+          if (want_cols) {
+            zx[j * 8 + 2 * q] = z0 * x0;
+            zx[j * 8 + 2 * q + 1] = z1 * x1;
+            ro[j * 8 + 2 * q] = r2.x;
+            ro[j * 8 + 2 * q + 1] = r2.y;
+          }
           const float t0 = fmaf(-x0, c2, fmaf(z0, gg[2 * q], -c1)), t1 = fmaf(-x1, c2, fmaf(z1, gg[2 * q + 1], -c1));
           ox[q] = pack_bf16x2(fmaf(rstd, t0, r2.x), fmaf(rstd, t1, r2.y));
           oz[q] = pack_bf16x2(z0, z1);
@@ -248,7 +276,23 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s.acc_empty[ai]);
+      if (want_cols) {
+        // column sums of this warp's 32 rows: Σ dz (→ dβ), Σ dz x̂ (→ dγ), Σ dres (→ the bias gradient of the layer that produced dres)
+        float zz[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zz[i] = __uint_as_float(v[i]);
+        const float sb = lp_warp_colsum(zz, lane), sg = lp_warp_colsum(zx, lane), so = lp_warp_colsum(ro, lane);
+        colp[(0 * 4 + quad) * 64 + grp * 32 + lane] = sb;
+        colp[(1 * 4 + quad) * 64 + grp * 32 + lane] = sg;
+        colp[(2 * 4 + quad) * 64 + grp * 32 + lane] = so;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (want_cols && et < 192) {
+        const int qn = et >> 6, col = et & 63;
+        const float* cp = colp + qn * 256 + col;
+        const float tot = ((cp[0] + cp[64]) + cp[128]) + cp[192];          // the four 32-row groups, fixed order
+        p.col_partial[(static_cast<int64_t>(qn) * gridDim.x + blockIdx.x) * p.d + (c_begin + c) * 64 + col] = tot;
+      }
       lp_tile_to_global(rt, dx_tile + (c_begin + c) * 64, p.lddx, rows_valid, et);
       if (dz_tile != nullptr) lp_tile_to_global(ht, dz_tile + (c_begin + c) * 64, p.lddz, rows_valid, et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -266,9 +310,48 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
   }
 }
 
+// col_partial [3][nblk][d] → dbeta = Σ_blk q0, dgamma = Σ_blk q1, dbias = Σ_blk q2 (any output may be NULL); fixed order.
+// CTA = 32 columns × 8 row groups (each sums a strided subset of the partial rows, coalesced 128 B reads).
+__global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, float* __restrict__ dbias) {
+  jl::pdl_prologue();
+  __shared__ float sm[3][8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  if (i < d) {
+    for (int k = grp; k < nblk; k += 8) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[q] += partial[(static_cast<int64_t>(q) * nblk + k) * d + i];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) sm[q][grp][lane] = acc[q];
+  __syncthreads();
+  if (grp == 0 && i < d) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float t = acc[q];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += sm[q][w][lane];
+      float* out = q == 0 ? dbeta : (q == 1 ? dgamma : dbias);
+      if (out != nullptr) out[i] = t;
+    }
+  }
+}
+
 }  // namespace jl
 
 extern "C" {
+
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  JL_REQUIRE(col_partial != nullptr && row_tiles > 0 && d > 0, JL_EINVAL, "lnproj_bwd_reduce: bad arguments");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::lnproj_bwd_reduce_kernel, jl::ceil_div(d, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream), col_partial, row_tiles, d, dgamma, dbeta, dbias);
+  JL_CHECK_LAUNCH("lnproj_bwd_reduce");
+  return JL_OK;
+}
 
 int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   JL_REQUIRE(p != nullptr, JL_EINVAL, "lnproj_bwd: null params");
@@ -303,7 +386,7 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   // Two CTAs per row tile (column halves) make the kernel itself faster (8000 x 768: 12.7 vs 19.9 µs with dz) but the fine-tune step
   // slower (6.20 vs 6.17 ms): there the weight-gradient branch fills the SMs this kernel leaves idle, and the split repeats the
   // prologue.  So: split only when the row tiles alone would leave most of the machine idle AND nothing else is likely to run.
-  const int split = (row_tiles * 8 <= jl::num_sms() && p->d >= 128) ? 2 : 1;
+  const int split = (row_tiles * 8 <= jl::num_sms() && p->d >= 128) ? 2 : 1;      // (col_partial rows are indexed by the row tile only: any split works)
   jl::launch(jl::lnproj_bwd_kernel, dim3(row_tiles, split), jl::LP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_dy, t_y, t_w, t_h, t_r, *p);
   JL_CHECK_LAUNCH("lnproj_bwd");
   return JL_OK;

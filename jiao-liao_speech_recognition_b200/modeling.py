@@ -863,13 +863,15 @@ class JLEngine:
                 z = torch.empty_like(h)
                 sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
             jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
+            # tail of the backward as one kernel (jl_lnproj_bwd): it also leaves the column sums behind dγ, dβ and db_o
+            use_lp = self.fused_att_bwd and _LN_WGRAD != "main" and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024
 
             def w_o():
                 ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)         # dyᵀ · a
-                if jobs is None:
+                if jobs is None and not use_lp:
                     ops.colsum(dy, out=g.out(ad.o_proj.bias))
             sb.run(w_o, dy, a)
-            if jobs is not None:
+            if jobs is not None and not use_lp:
                 jobs.append(dict(dy=dy, out_sum=g.out(ad.o_proj.bias)))
             da = ops.gemm(dy, self._bf16(ad.o_proj.weight), b_layout=MN)                                      # dy · W_o
             dqkv = ops.attn_bwd(qkv[:, 0:64], qkv[:, 64:128], qkv[:, 128:192], a, da, lse, lengths, b, t, 1, 1.0 / 8.0, cu_seqlens=cu)
@@ -888,23 +890,21 @@ class JLEngine:
             sb.run(w_qkv, dqkv, z)
             if jobs is not None:
                 jobs.append(dict(dy=dqkv, out_sum=gb_cat, scatter=(bs, gb_cat)))
-            if self.fused_att_bwd and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024:
-                # dqkv · W_qkv and the LayerNorm backward in one kernel (its row means come from dqkv and the saved q|k|v); dz is
-                # still written, for the LayerNorm weight gradients on the side branch
-                dh, dz = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd),
-                                        ad.norm.weight.detach(), h, mean, rstd, dy, want_dz=True)
-                if jobs is not None:
-                    jobs.append(dict(dy=dz, x=h, mean=mean, rstd=rstd, out_sum=g.out(ad.norm.bias), out_dot=g.out(ad.norm.weight)))
-
+            if use_lp:
+                # dqkv · W_qkv and the LayerNorm backward in one kernel (its row means come from dqkv and the saved q|k|v); no dz tensor:
+                # the kernel leaves per-row-tile column sums, finished on the weight-gradient branch → dγ, dβ of the adapter's
+                # LayerNorm and the output projection's bias gradient (Σ_rows dy)
+                dh, _, cols = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd), ad.norm.weight.detach(),
+                                             h, mean, rstd, dy, want_cols=True)
+                sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
+                if jobs:
                     def reduce_all(jobs=jobs):
                         for i in range(0, len(jobs), 4):
                             ops.colreduce_multi(jobs[i:i + 4])
                         for j in jobs:
                             if "scatter" in j:
                                 g.scatter_cat(*j["scatter"])
-                    sb.run(reduce_all, dz, h, mean, rstd, *[j["dy"] for j in jobs])
-                else:
-                    sb.run(lambda: ops.layernorm_wgrad(dz, h, mean, rstd, g.out(ad.norm.weight), g.out(ad.norm.bias)), dz, h, mean, rstd)
+                    sb.run(reduce_all, *[j["dy"] for j in jobs])
                 return dh
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
         if _LN_WGRAD == "main":

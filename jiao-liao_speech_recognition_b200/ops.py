@@ -402,11 +402,27 @@ def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tens
     return out, saved
 
 
+def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor]) -> None:
+    """Finish the column sums ``lnproj_bwd(..., want_cols=True)`` left per row tile: dgamma = Σ dz·x̂, dbeta = Σ dz, dbias = Σ dres
+    (fp32 [d] outputs, any may be None), summed in fixed order."""
+    _need(col_partial, F32, "col_partial", 3)
+    three, tiles, d = col_partial.shape
+    if three != 3 or not col_partial.is_contiguous():
+        raise ValueError("lnproj_bwd_reduce: col_partial must be a contiguous [3, row_tiles, d] tensor")
+    for t_, nm in ((dgamma, "dgamma"), (dbeta, "dbeta"), (dbias, "dbias")):
+        if t_ is not None:
+            _need(t_, F32, nm, 1)
+            if t_.numel() != d or not t_.is_contiguous():
+                raise ValueError(f"lnproj_bwd_reduce: {nm} must be a contiguous [d] tensor")
+    L.check(L.load().jl_lnproj_bwd_reduce(col_partial.data_ptr(), tiles, d, _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()))
+
+
 def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
-               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False):
+               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False):
     """Backward through LayerNorm → projection (W [n, d], n in {64, 128, 192}) in one kernel: dx = LayerNorm'(dy · W) + dres.
     ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
-    dz = dy · W (bf16) only when ``want_dz`` (the LayerNorm weight gradients need it)."""
+    dz = dy · W (bf16) only when ``want_dz``.  ``want_cols``: → (dx, dz | None, col_partial [3, ⌈rows/128⌉, d] fp32) — per-row-tile column
+    sums for ``lnproj_bwd_reduce`` (the LayerNorm weight gradients and the bias gradient behind ``dres`` without reading dz again)."""
     _need(dy, BF16, "dy", 2)
     _need(y, BF16, "y", 2)
     _need(w, BF16, "w", 2)
@@ -424,8 +440,10 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
                           tb=pack["tb"].data_ptr(), gamma=gamma.data_ptr(), h=h.data_ptr(), ldh=h.stride(0), mean=mean.data_ptr(),
                           rstd=rstd.data_ptr(), dres=dres.data_ptr(), lddres=dres.stride(0), dx=dx.data_ptr(), lddx=dx.stride(0),
                           dz=_ptr(dz), lddz=dz.stride(0) if dz is not None else 0, rows=rows, n=n, d=d)
+    cols = torch.empty((3, (rows + 127) // 128, d), dtype=F32, device=h.device) if want_cols else None
+    p.col_partial = _ptr(cols)
     L.check(L.load().jl_lnproj_bwd(C.byref(p), _stream()))
-    return dx, dz
+    return (dx, dz, cols) if want_cols else (dx, dz)
 
 
 # ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)

@@ -10,9 +10,9 @@ if grep -q "failed\|rror" gpurun_out/t_lp.log; then exit 1; fi
 run t_model 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider --timeout 300 -x
 tail -n 4 gpurun_out/t_model.log | tee -a $S
 L="--steps 20 --warmup 5 --no-inference --no-cpu-baseline --no-kernel-rooflines"
-JL_FUSED_ATT_BWD=1 run ab_lp_on 600 python bench.py $L
+run ab_lp_on 600 python bench.py $L
 JL_FUSED_ATT_BWD=0 run ab_lp_off 600 python bench.py $L
-JL_FUSED_ATT_BWD=1 run ab_lp_on2 600 python bench.py $L
+run ab_lp_on2 600 python bench.py $L
 JL_FUSED_ATT_BWD=0 run ab_lp_off2 600 python bench.py $L
 for f in ab_lp_on ab_lp_off ab_lp_on2 ab_lp_off2; do python -c "
 import json

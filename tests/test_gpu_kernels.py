@@ -630,8 +630,8 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     h = (torch.randn(rows, d, device="cuda", generator=g) * 1.4 + 0.3).to(BF16)
     w = (torch.randn(n, d, device="cuda", generator=g) * 0.06).to(BF16)
     bias = torch.randn(n, device="cuda", generator=g) * 0.1
-    gamma = 1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)
-    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    gamma = (1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device="cuda", generator=g)).requires_grad_(True)
     dy = (torch.randn(rows, n, device="cuda", generator=g) * 0.5).to(BF16)
     dres = (torch.randn(rows, d, device="cuda", generator=g) * 0.3).to(BF16)
     eps = 1e-5
@@ -642,6 +642,8 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     (yref * dy.float()).sum().backward()
     dx_ref = hf.grad + dres.float()
     dz_ref = dy.float() @ w.float()
+    dgamma_ref, dbeta_ref = gamma.grad.clone(), beta.grad.clone()
+    gamma, beta = gamma.detach(), beta.detach()
     # product path: forward pieces the kernel consumes
     zb, mean, rstd = ops.layernorm_fwd(h, gamma, beta, eps, save_stats=True)
     pack = ops.lnfold_pack(w, bias, gamma, beta)
@@ -650,6 +652,15 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     dx2, none = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres)
     torch.cuda.synchronize()
     assert none is None and torch.equal(dx, dx2)
+    # column sums left for the LayerNorm weight gradients and the bias gradient behind dres
+    dx3, none3, cols = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_cols=True)
+    dg, db, do = (torch.empty(d, device="cuda") for _ in range(3))
+    ops.lnproj_bwd_reduce(cols, dg, db, do)
+    ops.lnproj_bwd_reduce(cols, None, None, None)
+    torch.cuda.synchronize()
+    assert none3 is None and torch.equal(dx3, dx) and cols.shape == (3, (rows + 127) // 128, d)
+    assert rel_err(db, dbeta_ref) < 5e-3 and rel_err(dg, dgamma_ref) < 5e-3, (rel_err(db, dbeta_ref), rel_err(dg, dgamma_ref))
+    assert rel_err(do, dres.float().sum(0)) < 1e-5
     assert rel_err(dz.float(), dz_ref) < 6e-3, rel_err(dz.float(), dz_ref)
     assert rel_err(dx.float() - dres.float(), dx_ref - dres.float()) < 1.5e-2, rel_err(dx.float() - dres.float(), dx_ref - dres.float())
     # the two-kernel path
