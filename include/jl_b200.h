@@ -277,8 +277,15 @@ typedef struct {
   float* col_partial;                  /* optional fp32 [3][ceil(rows / 128)][d]: per-row-tile column sums of dz (→ dbeta), dz * xhat
                                           (→ dgamma) and dres (→ the bias gradient of the layer whose output gradient dres is), to be
                                           summed by jl_lnproj_bwd_reduce — the LayerNorm weight gradients without a dz tensor */
+  void* dy_scaled; int64_t lddys;      /* optional bf16 [rows, n] out: dy * rstd (row-scaled), the A operand of the projection's weight gradient */
+  float* wgrad_partial;                /* with dy_scaled: fp32 [2][4 * ceil(rows / 128)][n] column sums of dy and of dy_scaled * mean per 32 rows */
 } jl_lnproj_bwd_params;
 int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
+/* The projection's weight / bias gradient WITHOUT LN(h):  m0 = dy_scaled^T h  (a jl_gemm_bf16 with MN-major operands, fp32 [n, d]) is
+ * finished in place:  dW = (m0 - v 1^T) * gamma + cs beta^T,  dbias = cs,  with cs / v = the column sums in wgrad_partial
+ * (partial_rows = 4 * ceil(rows / 128)).  Replaces the LayerNorm recomputation + jl_colsum_bf16 of the two-kernel path. */
+int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t partial_rows, int32_t n, int32_t d, const float* gamma, const float* beta,
+                    float* dbias, void* stream);
 /* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial */
 int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream);
 

@@ -79,7 +79,8 @@ class LnFoldPackParams(C.Structure):
 class LnProjBwdParams(C.Structure):
     _fields_ = [("dy", vp), ("lddy", i64), ("y", vp), ("ldy", i64), ("w", vp), ("s", vp), ("tb", vp), ("gamma", vp), ("h", vp), ("ldh", i64),
                 ("mean", vp), ("rstd", vp), ("dres", vp), ("lddres", i64), ("dx", vp), ("lddx", i64), ("dz", vp), ("lddz", i64),
-                ("rows", i32), ("n", i32), ("d", i32), ("col_partial", vp)]
+                ("rows", i32), ("n", i32), ("d", i32), ("col_partial", vp),
+                ("dy_scaled", vp), ("lddys", i64), ("wgrad_partial", vp)]
 
 
 class FusionParams(C.Structure):
@@ -147,6 +148,7 @@ SYMBOLS = {
     "jl_lnfold_pack": (C.c_int, [C.POINTER(LnFoldPackParams), vp]),
     "jl_lnproj_bwd": (C.c_int, [C.POINTER(LnProjBwdParams), vp]),
     "jl_lnproj_bwd_reduce": (C.c_int, [vp, i32, i32, vp, vp, vp, vp]),
+    "jl_lnproj_wgrad": (C.c_int, [vp, i64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),

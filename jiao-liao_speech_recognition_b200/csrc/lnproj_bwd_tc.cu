@@ -220,6 +220,42 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
         }
       }
     }
+    if (p.dy_scaled != nullptr) {
+      // operands of the projection's weight gradient without LN(h):  dW = ((dy ⊙ rstd)ᵀ h − v 1ᵀ) ⊙ γ + cs βᵀ  with  v = (dy ⊙ rstd)ᵀ μ,
+      // cs = Σ_rows dy.  Here: dy ⊙ rstd (bf16) to HBM and the column sums v, cs of this warp's 32 rows (finished by jl_lnproj_wgrad).
+      for (int kt = 0; kt < nkt; ++kt) {
+        const uint32_t at = ptx::smem_u32(s.a[kt]);
+        float dv[32], dm[32];
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 v4 = lp_lds128(at + lp_chunk_off(r, grp * 4 + j));
+          const uint32_t w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 d2 = unpack_bf16x2(w4[q]);
+            dv[j * 8 + 2 * q] = d2.x;
+            dv[j * 8 + 2 * q + 1] = d2.y;
+            pk[j * 4 + q] = pack_bf16x2(d2.x * rstd, d2.y * rstd);
+            const float2 s2 = unpack_bf16x2(pk[j * 4 + q]);          // the rounded operand the GEMM will see
+            dm[j * 8 + 2 * q] = s2.x * mu;
+            dm[j * 8 + 2 * q + 1] = s2.y * mu;
+          }
+        }
+        if (row < p.rows) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dy_scaled) + static_cast<int64_t>(row) * p.lddys + kt * 64 + grp * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        const float cs = lp_warp_colsum(dv, lane), vm = lp_warp_colsum(dm, lane);
+        const int64_t prow = static_cast<int64_t>(blockIdx.x) * 4 + quad;
+        const int64_t nrows = static_cast<int64_t>(gridDim.x) * 4;
+        if (blockIdx.y == 0) {
+          p.wgrad_partial[prow * p.n + kt * 64 + grp * 32 + lane] = cs;
+          p.wgrad_partial[(nrows + prow) * p.n + kt * 64 + grp * 32 + lane] = vm;
+        }
+      }
+    }
     s.red1[grp][r] = p1;
     s.red2[grp][r] = p2;
     __syncwarp();
@@ -340,9 +376,48 @@ __global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __r
   }
 }
 
+// dW[k, :] = (M0[k, :] − v_k) ⊙ γ + cs_k β,  db_k = cs_k, with cs = Σ partial[0], v = Σ partial[1] over the `prow` partial rows
+// (fixed order).  One CTA per projection row k; M0 is overwritten in place.
+__global__ void __launch_bounds__(256) lnproj_wgrad_kernel(float* __restrict__ m0, int64_t ldm, const float* __restrict__ partial, int prow, int n, int d,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dbias) {
+  jl::pdl_prologue();
+  __shared__ float red[2][256];
+  const int k = blockIdx.x, t = threadIdx.x;
+  float cs = 0.0f, vm = 0.0f;
+  for (int i = t; i < prow; i += 256) {
+    cs += partial[static_cast<int64_t>(i) * n + k];
+    vm += partial[(static_cast<int64_t>(prow) + i) * n + k];
+  }
+  red[0][t] = cs;
+  red[1][t] = vm;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (t < off) {
+      red[0][t] += red[0][t + off];
+      red[1][t] += red[1][t + off];
+    }
+    __syncthreads();
+  }
+  cs = red[0][0];
+  vm = red[1][0];
+  float* row = m0 + static_cast<int64_t>(k) * ldm;
+  for (int j = t; j < d; j += 256) row[j] = fmaf(row[j] - vm, __ldg(gamma + j), cs * __ldg(beta + j));
+  if (t == 0 && dbias != nullptr) dbias[k] = cs;
+}
+
 }  // namespace jl
 
 extern "C" {
+
+int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t partial_rows, int32_t n, int32_t d, const float* gamma, const float* beta,
+                    float* dbias, void* stream) {
+  JL_REQUIRE(m0 && wgrad_partial && gamma && beta && partial_rows > 0 && n > 0 && d > 0 && ldm >= d, JL_EINVAL, "lnproj_wgrad: bad arguments");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::lnproj_wgrad_kernel, n, 256, 0, reinterpret_cast<cudaStream_t>(stream), m0, ldm, wgrad_partial, partial_rows, n, d, gamma, beta, dbias);
+  JL_CHECK_LAUNCH("lnproj_wgrad");
+  return JL_OK;
+}
 
 int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream) {
   JL_REQUIRE(col_partial != nullptr && row_tiles > 0 && d > 0, JL_EINVAL, "lnproj_bwd_reduce: bad arguments");
@@ -357,6 +432,9 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   JL_REQUIRE(p != nullptr, JL_EINVAL, "lnproj_bwd: null params");
   JL_REQUIRE(p->dy && p->y && p->w && p->s && p->tb && p->gamma && p->h && p->mean && p->rstd && p->dres && p->dx, JL_EINVAL, "lnproj_bwd: null pointer");
   JL_REQUIRE(p->rows > 0, JL_EINVAL, "lnproj_bwd: rows must be positive");
+  JL_REQUIRE((p->dy_scaled == nullptr) == (p->wgrad_partial == nullptr), JL_EINVAL, "lnproj_bwd: dy_scaled and wgrad_partial go together");
+  JL_REQUIRE(p->dy_scaled == nullptr || ((p->lddys % 8) == 0 && (reinterpret_cast<uintptr_t>(p->dy_scaled) & 15) == 0), JL_EINVAL,
+             "lnproj_bwd: dy_scaled must be 16-byte aligned with a row stride that is a multiple of 8");
   JL_REQUIRE(p->n >= 64 && p->n <= 192 && (p->n % 64) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: n must be 64, 128 or 192 (got %d)", p->n);
   JL_REQUIRE(p->d >= 64 && (p->d % 64) == 0 && p->d <= jl::LP_MAX_D, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: d must be a multiple of 64, at most %d (got %d)",
              jl::LP_MAX_D, p->d);

@@ -394,6 +394,7 @@ class JLEngine:
         self.fused_att = os.environ.get("JL_FUSED_ATT", "1") != "0"
         # tail of the AttAdapter backward (dqkv · W_qkv + LayerNorm backward) as one kernel (jl_lnproj_bwd)
         self.fused_att_bwd = os.environ.get("JL_FUSED_ATT_BWD", "1") != "0"
+        self.lp_wgrad = os.environ.get("JL_LP_WGRAD", "0") == "1"      # dW_qkv without LN(h) (jl_lnproj_wgrad): measured slower in the step (6.07 vs 6.03 ms), off
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._wf_bufs: Dict[int, dict] = {}
@@ -857,14 +858,15 @@ class JLEngine:
         else:
             h, mean, rstd, z, qkv, a, lse = saved
             fused_fwd = z is None
-            if z is None:
+            # tail of the backward as one kernel (jl_lnproj_bwd): it also leaves what the weight-gradient branch needs for dγ, dβ, db_o
+            # and (without LN(h)) for dW_qkv, db_qkv
+            use_lp = self.fused_att_bwd and _LN_WGRAD != "main" and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024
+            if z is None and not use_lp:
                 # the fused forward kernel never wrote LN(h); only dW_qkv = dqkvᵀ · LN(h) needs it: recomputed on the weight-gradient
                 # branch into a buffer allocated here, on the main stream
                 z = torch.empty_like(h)
                 sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
             jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
-            # tail of the backward as one kernel (jl_lnproj_bwd): it also leaves the column sums behind dγ, dβ and db_o
-            use_lp = self.fused_att_bwd and _LN_WGRAD != "main" and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024
 
             def w_o():
                 ops.gemm(dy, a, a_layout=MN, b_layout=MN, out=g.out(ad.o_proj.weight), out_dtype=F32)         # dyᵀ · a
@@ -879,6 +881,47 @@ class JLEngine:
             bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
 
             gb_cat = g.out_cat(bs)
+            if use_lp and not self.lp_wgrad:
+                # (variant kept for A/B: dW_qkv from LN(h) recomputed on the weight-gradient branch, as the two-kernel path does)
+                if z is None:
+                    z = torch.empty_like(h)
+                    sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
+                dh, _, cols = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd), ad.norm.weight.detach(),
+                                             h, mean, rstd, dy, want_cols=True)
+                sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
+
+                def w_qkv_z():
+                    gw = g.out_cat(ws)
+                    ops.gemm(dqkv, z, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                        # dqkvᵀ · z
+                    g.scatter_cat(ws, gw)
+                    ops.colsum(dqkv, out=gb_cat)
+                    g.scatter_cat(bs, gb_cat)
+                sb.run(w_qkv_z, dqkv, z)
+                return dh
+            if use_lp:
+                # dqkv · W_qkv and the LayerNorm backward in one kernel (its row means come from dqkv and the saved q|k|v); no dz, no
+                # LN(h): the kernel leaves per-row-tile column sums and dqkv ⊙ rstd, from which the weight-gradient branch gets dγ, dβ,
+                # db_o (jl_lnproj_bwd_reduce) and dW_qkv = ((dqkv ⊙ rstd)ᵀ h − v 1ᵀ) ⊙ γ + cs βᵀ, db_qkv = cs (GEMM + jl_lnproj_wgrad)
+                dh, _, cols, dys, wpart = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd),
+                                                         ad.norm.weight.detach(), h, mean, rstd, dy, want_cols=True, want_wgrad_operands=True)
+                sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
+
+                def w_qkv_lp():
+                    gw = g.out_cat(ws)
+                    ops.gemm(dys, h, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                         # (dqkv ⊙ rstd)ᵀ · h
+                    ops.lnproj_wgrad(gw, wpart, ad.norm.weight.detach(), ad.norm.bias.detach(), gb_cat)
+                    g.scatter_cat(ws, gw)
+                    g.scatter_cat(bs, gb_cat)
+                sb.run(w_qkv_lp, dys, h, wpart)
+                if jobs:
+                    def reduce_all(jobs=jobs):
+                        for i in range(0, len(jobs), 4):
+                            ops.colreduce_multi(jobs[i:i + 4])
+                        for j in jobs:
+                            if "scatter" in j:
+                                g.scatter_cat(*j["scatter"])
+                    sb.run(reduce_all, *[j["dy"] for j in jobs])
+                return dh
 
             def w_qkv():
                 gw = g.out_cat(ws)
@@ -890,22 +933,6 @@ class JLEngine:
             sb.run(w_qkv, dqkv, z)
             if jobs is not None:
                 jobs.append(dict(dy=dqkv, out_sum=gb_cat, scatter=(bs, gb_cat)))
-            if use_lp:
-                # dqkv · W_qkv and the LayerNorm backward in one kernel (its row means come from dqkv and the saved q|k|v); no dz tensor:
-                # the kernel leaves per-row-tile column sums, finished on the weight-gradient branch → dγ, dβ of the adapter's
-                # LayerNorm and the output projection's bias gradient (Σ_rows dy)
-                dh, _, cols = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd), ad.norm.weight.detach(),
-                                             h, mean, rstd, dy, want_cols=True)
-                sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
-                if jobs:
-                    def reduce_all(jobs=jobs):
-                        for i in range(0, len(jobs), 4):
-                            ops.colreduce_multi(jobs[i:i + 4])
-                        for j in jobs:
-                            if "scatter" in j:
-                                g.scatter_cat(*j["scatter"])
-                    sb.run(reduce_all, *[j["dy"] for j in jobs])
-                return dh
             dz = ops.gemm(dqkv, self._cat_bf16(ws), b_layout=MN)                                              # dqkv · W_qkv
         if _LN_WGRAD == "main":
             dh, _, _ = ops.layernorm_bwd(dz, h, ad.norm.weight.detach(), mean, rstd, dres=dy, want_wgrad=True, dgamma=g.out(ad.norm.weight),

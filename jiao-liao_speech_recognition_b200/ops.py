@@ -418,7 +418,7 @@ def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor],
 
 
 def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
-               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False):
+               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False, want_wgrad_operands: bool = False):
     """Backward through LayerNorm → projection (W [n, d], n in {64, 128, 192}) in one kernel: dx = LayerNorm'(dy · W) + dres.
     ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
     dz = dy · W (bf16) only when ``want_dz``.  ``want_cols``: → (dx, dz | None, col_partial [3, ⌈rows/128⌉, d] fp32) — per-row-tile column
@@ -442,8 +442,31 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
                           dz=_ptr(dz), lddz=dz.stride(0) if dz is not None else 0, rows=rows, n=n, d=d)
     cols = torch.empty((3, (rows + 127) // 128, d), dtype=F32, device=h.device) if want_cols else None
     p.col_partial = _ptr(cols)
+    dys = wpart = None
+    if want_wgrad_operands:
+        # ``dys`` = dy ⊙ rstd (bf16), ``wpart`` [2, 4·⌈rows/128⌉, n]: operands of ``lnproj_wgrad`` (the projection's weight / bias gradient)
+        dys = torch.empty((rows, n), dtype=BF16, device=h.device)
+        wpart = torch.empty((2, 4 * ((rows + 127) // 128), n), dtype=F32, device=h.device)
+        p.dy_scaled, p.lddys, p.wgrad_partial = dys.data_ptr(), dys.stride(0), wpart.data_ptr()
     L.check(L.load().jl_lnproj_bwd(C.byref(p), _stream()))
-    return (dx, dz, cols) if want_cols else (dx, dz)
+    out = (dx, dz, cols) if want_cols else (dx, dz)
+    return out + (dys, wpart) if want_wgrad_operands else out
+
+
+def lnproj_wgrad(m0: torch.Tensor, wpart: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
+    """Finish the weight gradient of a projection that follows a LayerNorm, in place: ``m0`` [n, d] fp32 = (dy ⊙ rstd)ᵀ · h (from
+    ``gemm`` with MN-major operands) → dW = (m0 − v 1ᵀ) ⊙ γ + cs βᵀ; ``dbias`` [n] ← cs.  ``wpart`` from ``lnproj_bwd``."""
+    _need(m0, F32, "m0", 2)
+    _need(wpart, F32, "wpart", 3)
+    n, d = m0.shape
+    if wpart.shape[0] != 2 or wpart.shape[2] != n or not wpart.is_contiguous() or m0.stride(1) != 1:
+        raise ValueError("lnproj_wgrad: shapes do not match")
+    if dbias is not None:
+        _need(dbias, F32, "dbias", 1)
+        if dbias.numel() != n or not dbias.is_contiguous():
+            raise ValueError("lnproj_wgrad: dbias must be a contiguous [n] tensor")
+    L.check(L.load().jl_lnproj_wgrad(m0.data_ptr(), m0.stride(0), wpart.data_ptr(), wpart.shape[1], n, d, gamma.data_ptr(), beta.data_ptr(),
+                                     _ptr(dbias), _stream()))
 
 
 # ----------------------------------------------------------------------------------------------- AdapterFusion combine (f4)

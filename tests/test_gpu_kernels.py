@@ -661,6 +661,18 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     assert none3 is None and torch.equal(dx3, dx) and cols.shape == (3, (rows + 127) // 128, d)
     assert rel_err(db, dbeta_ref) < 5e-3 and rel_err(dg, dgamma_ref) < 5e-3, (rel_err(db, dbeta_ref), rel_err(dg, dgamma_ref))
     assert rel_err(do, dres.float().sum(0)) < 1e-5
+    # the projection's own weight / bias gradient without LN(h): (dy ⊙ rstd)ᵀ h finished by lnproj_wgrad
+    dx4, none4, dys, wpart = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_wgrad_operands=True)
+    m0 = torch.empty((n, d), dtype=F32, device="cuda")
+    ops.gemm(dys, h, a_layout=1, b_layout=1, out=m0, out_dtype=F32)
+    dbq = torch.empty(n, device="cuda")
+    ops.lnproj_wgrad(m0, wpart, gamma, beta, dbq)
+    torch.cuda.synchronize()
+    assert torch.equal(dx4, dx) and none4 is None
+    assert rel_err(dys.float(), dy.float() * rstd[:, None]) < 4e-3
+    dw_ref = dy.float().T @ z.detach()
+    assert rel_err(m0, dw_ref) < 1e-2, rel_err(m0, dw_ref)
+    assert rel_err(dbq, dy.float().sum(0)) < 1e-4
     assert rel_err(dz.float(), dz_ref) < 6e-3, rel_err(dz.float(), dz_ref)
     assert rel_err(dx.float() - dres.float(), dx_ref - dres.float()) < 1.5e-2, rel_err(dx.float() - dres.float(), dx_ref - dres.float())
     # the two-kernel path
