@@ -253,6 +253,9 @@ typedef struct {
   int32_t n, d;
 } jl_lnfold_pack_params;
 int jl_lnfold_pack(const jl_lnfold_pack_params* p, void* stream);
+/* the same for up to JL_LNFOLD_MAX_JOBS projections in one launch (every AttAdapter of a model at the start of a training step) */
+#define JL_LNFOLD_MAX_JOBS 48
+int jl_lnfold_pack_multi(const jl_lnfold_pack_params* jobs, int32_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a7 (backward): backward through "LayerNorm → narrow projection" in one kernel — the tail of the AttAdapter backward:

@@ -631,9 +631,59 @@ __global__ void __launch_bounds__(256) lnfold_pack_kernel(const jl_lnfold_pack_p
   }
 }
 
+// Several projections in one launch (all the AttAdapters of a model at the start of a training step): blockIdx.y = job.
+struct LnFoldJobs {
+  jl_lnfold_pack_params job[JL_LNFOLD_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) lnfold_pack_multi_kernel(const __grid_constant__ LnFoldJobs jobs) {
+  jl::pdl_prologue();
+  const jl_lnfold_pack_params& p = jobs.job[blockIdx.y];
+  if (static_cast<int>(blockIdx.x) >= p.n) return;
+  __shared__ float red_s[8], red_t[8];
+  const int j = blockIdx.x;
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(p.w) + static_cast<int64_t>(j) * p.d;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.w_scaled) + static_cast<int64_t>(j) * p.d;
+  float ss = 0.0f, tt = 0.0f;
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
+    const float x = __bfloat162float(w[c]);
+    const __nv_bfloat16 xs = __float2bfloat16_rn(x * __ldg(p.gamma + c));
+    out[c] = xs;
+    ss += __bfloat162float(xs);
+    tt = fmaf(x, __ldg(p.beta + c), tt);
+  }
+  ss = warp_sum(ss);
+  tt = warp_sum(tt);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = ss; red_t[threadIdx.x >> 5] = tt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, b = 0.0f;
+    for (int q = 0; q < static_cast<int>(blockDim.x >> 5); ++q) { a += red_s[q]; b += red_t[q]; }
+    p.s[j] = a;
+    p.tb[j] = b + (p.bias != nullptr ? __ldg(p.bias + j) : 0.0f);
+  }
+}
+
 }  // namespace jl
 
 extern "C" {
+
+int jl_lnfold_pack_multi(const jl_lnfold_pack_params* jobs, int32_t count, void* stream) {
+  JL_REQUIRE(jobs != nullptr && count >= 1 && count <= JL_LNFOLD_MAX_JOBS, JL_EINVAL, "lnfold_pack_multi: 1..%d jobs", JL_LNFOLD_MAX_JOBS);
+  jl::LnFoldJobs js;
+  int nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    const jl_lnfold_pack_params& p = jobs[i];
+    JL_REQUIRE(p.w && p.gamma && p.beta && p.w_scaled && p.s && p.tb && p.n > 0 && p.d > 0, JL_EINVAL, "lnfold_pack_multi: job %d: null pointer or bad dims", i);
+    js.job[i] = p;
+    nmax = p.n > nmax ? p.n : nmax;
+  }
+  for (int i = count; i < JL_LNFOLD_MAX_JOBS; ++i) js.job[i] = jobs[0];
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::lnfold_pack_multi_kernel, dim3(nmax, count), 256, 0, reinterpret_cast<cudaStream_t>(stream), js);
+  JL_CHECK_LAUNCH("lnfold_pack_multi");
+  return JL_OK;
+}
 
 int jl_lnfold_pack(const jl_lnfold_pack_params* p, void* stream) {
   JL_REQUIRE(p != nullptr && p->w && p->gamma && p->beta && p->w_scaled && p->s && p->tb, JL_EINVAL, "lnfold_pack: null pointer");

@@ -397,6 +397,7 @@ class JLEngine:
         self.lp_wgrad = os.environ.get("JL_LP_WGRAD", "0") == "1"      # dW_qkv without LN(h) (jl_lnproj_wgrad): measured slower in the step (6.07 vs 6.03 ms), off
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
+        self._att_packed_step = False
         self._wf_bufs: Dict[int, dict] = {}
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
@@ -577,6 +578,8 @@ class JLEngine:
         ps = [ad.norm.weight, ad.norm.bias, ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight, ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
         ver = tuple((q.data_ptr(), q._version) for q in ps) + (self.flat.generation if self.flat is not None else 0,)
         ent = self._att_bufs.get(id(ad))
+        if ent is not None and training and self._att_packed_step:
+            return ent[1]          # packed by _att_pack_all at the start of this step's forward pass
         if ent is not None and (reuse or (not training and ent[0] == ver)):
             return ent[1]          # reuse: the backward pass of the step whose forward pass derived the pack
         w = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
@@ -584,6 +587,26 @@ class JLEngine:
         bufs = ops.lnfold_pack(w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), None if ent is None else ent[1])
         self._att_bufs[id(ad)] = (ver, bufs)
         return bufs
+
+    def _att_pack_all(self) -> None:
+        """Training step: the LayerNorm-folded q|k|v projections of EVERY AttAdapter in one launch at the start of the forward pass
+        (they depend on the weights only; one launch per adapter cost 12 x 4.6 µs on the main chain).  The per-adapter calls of this
+        step then reuse the buffers."""
+        jobs = []
+        for layer in self.enc.layers:
+            for ad in (layer.adapter_attn, layer.adapter_ffn):
+                if ad is None or ad.kind != "att":
+                    continue
+                ent = self._att_bufs.get(id(ad))
+                if ent is None:
+                    self._att_pack_dev(ad, True)             # first use: allocates the buffers (and packs)
+                    continue
+                w = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
+                bq = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
+                jobs.append((w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[1]))
+        if jobs:
+            ops.lnfold_pack_multi(jobs)
+        self._att_packed_step = True
 
     def pos_table(self, device, rows: int) -> torch.Tensor:
         key = (str(device), self.cfg.hidden_size)
@@ -1046,6 +1069,9 @@ class JLEngine:
         st.b, st.t = b, t
         scale = 1.0 / 8.0   # head_dim 64
         st.layers = []
+        self._att_packed_step = False
+        if training and self.fused_att and t <= 256:
+            self._att_pack_all()
         for i, layer in enumerate(self.enc.layers):
             sv = _State()
             sv.h_in = h

@@ -368,6 +368,24 @@ def lnfold_pack(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tens
     return bufs
 
 
+LNFOLD_MAX_JOBS = 48
+
+
+def lnfold_pack_multi(jobs: list) -> None:
+    """``lnfold_pack`` for several projections in one launch per 48: ``jobs`` = [(w, bias | None, gamma, beta, bufs)], ``bufs`` the
+    existing result dicts, overwritten in place."""
+    for i0 in range(0, len(jobs), LNFOLD_MAX_JOBS):
+        part = jobs[i0:i0 + LNFOLD_MAX_JOBS]
+        arr = (L.LnFoldPackParams * len(part))()
+        for i, (w, bias, gamma, beta, bufs) in enumerate(part):
+            _need(w, BF16, "w", 2)
+            if not w.is_contiguous() or bufs["w"].shape != w.shape:
+                raise ValueError("lnfold_pack_multi: w must be contiguous and match its buffers")
+            arr[i] = L.LnFoldPackParams(w=w.data_ptr(), bias=_ptr(bias), gamma=gamma.data_ptr(), beta=beta.data_ptr(), w_scaled=bufs["w"].data_ptr(),
+                                        s=bufs["s"].data_ptr(), tb=bufs["tb"].data_ptr(), n=w.shape[0], d=w.shape[1])
+        L.check(L.load().jl_lnfold_pack_multi(arr, len(part), _stream()))
+
+
 def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int,
                    eps: float, zero_padded_rows: bool = False, training: bool = False, cu_seqlens: Optional[torch.Tensor] = None):
     """out = h + AttAdapter(h) in one kernel (utterances of <= 256 frames).  ``pack`` = ``lnfold_pack`` of the concatenated q|k|v
