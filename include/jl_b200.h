@@ -259,7 +259,8 @@ int jl_lnfold_pack_multi(const jl_lnfold_pack_params* jobs, int32_t count, void*
 
 /* ------------------------------------------------------------------------------------------
  * a7 (backward): backward through "LayerNorm → narrow projection" in one kernel — the tail of the AttAdapter backward:
- *   forward  y = LN(h) W^T + b   (W [n, d], n = 64 / 128 / 192: the q|k|v projection)
+ *   forward  y = LN(h) W^T + b   (W [n, d], n a multiple of 8, at most 192: the AttAdapter's q|k|v projection, n = 192; the WFAdapter's
+ *   first low-rank projection, n = rank)
  *   dz = dy W;   dx = LayerNorm'(dz; h, mean, rstd, gamma) + dres
  * Replaces jl_gemm_bf16 (dy · W) + jl_layernorm_bwd (SP/transformers/models/wav2vec2/modeling_wav2vec2.py:941 analogue under
  * autograd).  s / tb are the LayerNorm-fold vectors of jl_lnfold_pack for this projection; y is the projection output saved by
@@ -289,8 +290,9 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
  * (partial_rows = 4 * ceil(rows / 128)).  Replaces the LayerNorm recomputation + jl_colsum_bf16 of the two-kernel path. */
 int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t partial_rows, int32_t n, int32_t d, const float* gamma, const float* beta,
                     float* dbias, void* stream);
-/* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial */
-int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream);
+/* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial; accumulate != 0: dgamma and dbeta
+ * are added to (row ranges of one LayerNorm handled by several calls — the dialect runs of a WFAdapter), dbias is always overwritten */
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;

@@ -90,7 +90,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
   LpSmem& s = *reinterpret_cast<LpSmem*>(lp_smem_raw + ((1024u - (ptx::smem_u32(lp_smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128;
-  const int nkt = p.n / 64;                         // 64-wide k tiles (columns of dy)
+  const int nkt = (p.n + 63) / 64;                  // 64-wide k tiles (columns of dy; a partial last tile is zero-filled by TMA)
   // the 64-column output chunks of the row tile may be split between gridDim.y CTAs (each repeats the small prologue): an SM takes
   // in ≈ 57 B/clk and stores ≈ 28 B/clk (see the host function for when)
   const int nc_all = p.d / 64;
@@ -140,7 +140,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
       ptx::mbar_expect_tx(&s.y_full, nkt * LP_T128);
       for (int kt = 0; kt < nkt; ++kt) ptx::tma_load_2d(s.hs[kt], &t_y, &s.y_full, kt * 64, row0);
       for (int c = 0; c < min(nc, LP_BUFS); ++c) {
-        ptx::mbar_expect_tx(&s.b_full[c], p.n * 128);
+        ptx::mbar_expect_tx(&s.b_full[c], nkt * 64 * 128);
         ptx::tma_load_2d(s.b[c], &t_w, &s.b_full[c], (c_begin + c) * 64, 0);
         ptx::mbar_expect_tx(&s.r_full[c], LP_T128);
         ptx::tma_load_2d(s.rs[c], &t_r, &s.r_full[c], (c_begin + c) * 64, row0);
@@ -154,7 +154,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
         const int bi = c % LP_BUFS;
         const uint32_t par = ((c / LP_BUFS) - 1) & 1;
         ptx::mbar_wait(&s.b_empty[bi], par);
-        ptx::mbar_expect_tx(&s.b_full[bi], p.n * 128);
+        ptx::mbar_expect_tx(&s.b_full[bi], nkt * 64 * 128);
         ptx::tma_load_2d(s.b[bi], &t_w, &s.b_full[bi], (c_begin + c) * 64, 0);
         ptx::mbar_wait(&s.stg_empty[bi], par);
         ptx::mbar_expect_tx(&s.h_full[bi], LP_T128);
@@ -193,7 +193,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int row = row0 + r;
     for (int i = et; i < p.d; i += 256) s.gamma[i] = __ldg(p.gamma + i);
-    if (et < p.n) { s.fs[et] = __ldg(p.s + et); s.ftb[et] = __ldg(p.tb + et); }
+    if (et < 192) { s.fs[et] = et < p.n ? __ldg(p.s + et) : 0.0f; s.ftb[et] = et < p.n ? __ldg(p.tb + et) : 0.0f; }
     const float mu = row < p.rows ? __ldg(p.mean + row) : 0.0f;
     const float rstd = row < p.rows ? __ldg(p.rstd + row) : 0.0f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -349,7 +349,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
 // col_partial [3][nblk][d] → dbeta = Σ_blk q0, dgamma = Σ_blk q1, dbias = Σ_blk q2 (any output may be NULL); fixed order.
 // CTA = 32 columns × 8 row groups (each sums a strided subset of the partial rows, coalesced 128 B reads).
 __global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta, float* __restrict__ dbias) {
+                                                                float* __restrict__ dbeta, float* __restrict__ dbias, int accumulate) {
   jl::pdl_prologue();
   __shared__ float sm[3][8][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __r
 #pragma unroll
       for (int w = 1; w < 8; ++w) t += sm[q][w][lane];
       float* out = q == 0 ? dbeta : (q == 1 ? dgamma : dbias);
-      if (out != nullptr) out[i] = t;
+      if (out != nullptr) out[i] = (accumulate && q < 2) ? out[i] + t : t;      // dgamma / dbeta may collect several row ranges
     }
   }
 }
@@ -419,11 +419,12 @@ int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t 
   return JL_OK;
 }
 
-int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, void* stream) {
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate, void* stream) {
   JL_REQUIRE(col_partial != nullptr && row_tiles > 0 && d > 0, JL_EINVAL, "lnproj_bwd_reduce: bad arguments");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
-  jl::launch(jl::lnproj_bwd_reduce_kernel, jl::ceil_div(d, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream), col_partial, row_tiles, d, dgamma, dbeta, dbias);
+  jl::launch(jl::lnproj_bwd_reduce_kernel, jl::ceil_div(d, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream), col_partial, row_tiles, d, dgamma, dbeta, dbias,
+             static_cast<int>(accumulate));
   JL_CHECK_LAUNCH("lnproj_bwd_reduce");
   return JL_OK;
 }
@@ -435,7 +436,8 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   JL_REQUIRE((p->dy_scaled == nullptr) == (p->wgrad_partial == nullptr), JL_EINVAL, "lnproj_bwd: dy_scaled and wgrad_partial go together");
   JL_REQUIRE(p->dy_scaled == nullptr || ((p->lddys % 8) == 0 && (reinterpret_cast<uintptr_t>(p->dy_scaled) & 15) == 0), JL_EINVAL,
              "lnproj_bwd: dy_scaled must be 16-byte aligned with a row stride that is a multiple of 8");
-  JL_REQUIRE(p->n >= 64 && p->n <= 192 && (p->n % 64) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: n must be 64, 128 or 192 (got %d)", p->n);
+  JL_REQUIRE(p->n >= 8 && p->n <= 192 && (p->n % 8) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: n must be a multiple of 8, at most 192 (got %d)", p->n);
+  JL_REQUIRE(p->dy_scaled == nullptr || (p->n % 64) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: dy_scaled needs n to be a multiple of 64 (got %d)", p->n);
   JL_REQUIRE(p->d >= 64 && (p->d % 64) == 0 && p->d <= jl::LP_MAX_D, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: d must be a multiple of 64, at most %d (got %d)",
              jl::LP_MAX_D, p->d);
   JL_REQUIRE((p->lddy % 8) == 0 && (p->ldy % 8) == 0 && (p->ldh % 8) == 0 && (p->lddres % 8) == 0 && (p->lddx % 8) == 0 && (p->dz == nullptr || (p->lddz % 8) == 0),
@@ -447,7 +449,7 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   CUtensorMap t_dy, t_y, t_w, t_h, t_r;
   rc = jl::make_tma_map_2d_bf16(&t_dy, p->dy, p->n, p->rows, p->lddy, 128);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_y, p->y, p->n, p->rows, p->ldy, 128);
-  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->w, p->d, p->n, p->d, p->n);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->w, p->d, p->n, p->d, (p->n + 63) / 64 * 64);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_h, p->h, p->d, p->rows, p->ldh, 128);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_r, p->dres, p->d, p->rows, p->lddres, 128);
   if (rc != JL_OK) return rc;

@@ -398,6 +398,9 @@ class JLEngine:
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._att_packed_step = False
+        self._wf_fold: Dict[int, list] = {}
+        # tail of the WFAdapter backward (dt1 · B_d + LayerNorm backward + column sums) through jl_lnproj_bwd
+        self.fused_wf_bwd = os.environ.get("JL_FUSED_WF_BWD", "1") != "0"
         self._wf_bufs: Dict[int, dict] = {}
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
@@ -587,6 +590,25 @@ class JLEngine:
         bufs = ops.lnfold_pack(w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), None if ent is None else ent[1])
         self._att_bufs[id(ad)] = (ver, bufs)
         return bufs
+
+    def _wf_fold_packs(self, ad) -> list:
+        """LayerNorm-fold vectors (s, tb) of the first low-rank projection of every factor set of a WFAdapter (B_d[k] [r, d], no bias),
+        for jl_lnproj_bwd; derived on the device into buffers that keep their addresses (inside a captured step they follow the
+        optimizer)."""
+        w = self._bf16(ad.down_B)
+        ent = self._wf_fold.get(id(ad))
+        if ent is None:
+            ent = [None] * ad.num_dialects
+            self._wf_fold[id(ad)] = ent
+        jobs = []
+        for k in range(ad.num_dialects):
+            if ent[k] is None:
+                ent[k] = ops.lnfold_pack(w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach())
+            else:
+                jobs.append((w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[k]))
+        if jobs:
+            ops.lnfold_pack_multi(jobs)
+        return ent
 
     def _att_pack_all(self) -> None:
         """Training step: the LayerNorm-folded q|k|v projections of EVERY AttAdapter in one launch at the start of the forward pass
@@ -821,7 +843,8 @@ class JLEngine:
         dh, _, _ = ops.layernorm_bwd(dzs, h, src.norm.weight.detach(), mean_s, rstd_s, dres=dh)
         return dh
 
-    def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch", jobs: Optional[list] = None) -> None:
+    def _wf_bwd_rows(self, ad, k: int, rows: slice, dy, z, t1, u, t2, dz, g: "GradSink", sb: "_SideBranch", jobs: Optional[list] = None,
+                     lp: Optional[dict] = None) -> None:
         """Backward of the WFAdapter projections for the utterances of dialect ``k`` (a row slice): weight gradients of
         factor set k on the side branch, dz[rows] = gradient at the adapter's LayerNorm output.  With ``jobs`` the bias-gradient
         column sums are appended to it (for one merged launch by the caller) instead of being launched here."""
@@ -830,10 +853,10 @@ class JLEngine:
 
         def w_up():
             ops.gemm(dy, t2, a_layout=MN, b_layout=MN, out=g.out(ad.up_A, k), out_dtype=F32)             # dyᵀ · t2
-            if jobs is None:
+            if jobs is None and lp is None:
                 ops.colsum(dy, out=g.out(ad.up_bias, k))
         sb.run(w_up, dy, t2)
-        if jobs is not None:
+        if jobs is not None and lp is None:
             jobs.append(dict(dy=dy, out_sum=g.out(ad.up_bias, k)))
         dt2 = ops.gemm(dy, self._bf16(ad.up_A)[k], b_layout=MN)                                           # dy · A_u
         sb.run(lambda: ops.gemm(dt2, u, a_layout=MN, b_layout=MN, out=g.out(ad.up_B, k), out_dtype=F32), dt2, u)   # dt2ᵀ · u
@@ -848,7 +871,16 @@ class JLEngine:
             jobs.append(dict(dy=dpre, out_sum=g.out(ad.down_bias, k)))
         dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
         sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
-        ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                                # dt1 · B_d
+        if lp is None:
+            ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                            # dt1 · B_d
+            return
+        # dt1 · B_d and the LayerNorm backward of these rows in one kernel (jl_lnproj_bwd); its column sums give this factor set's
+        # up-projection bias gradient (Σ dy) and this row range's share of the adapter LayerNorm's dγ / dβ
+        _, _, cols = ops.lnproj_bwd(dt1, t1, self._bf16(ad.down_B)[k], lp["packs"][k], ad.norm.weight.detach(), lp["h"][rows], lp["mean"][rows],
+                                    lp["rstd"][rows], dy, want_cols=True, out=lp["dh"][rows])
+        acc = lp["seen"] > 0
+        lp["seen"] += 1
+        sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.up_bias, k), accumulate=acc), cols)
 
     def _adapter_bwd(self, ad: nn.Module, saved, dy: torch.Tensor, lengths, b: int, t: int, g: "GradSink", sb: "_SideBranch",
                      pk: Optional[PackedLayout] = None) -> torch.Tensor:
@@ -865,19 +897,41 @@ class JLEngine:
                 # branch (the buffer is allocated here, on the main stream; the branch only writes into it)
                 z = torch.empty_like(h)
                 sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
-            dz = torch.empty_like(h)
             present = set()
             jobs = [] if (_MERGED_REDUCE and _LN_WGRAD != "main") else None
+            lp = None
+            if self.fused_wf_bwd and _LN_WGRAD != "main" and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024 and ad.rank % 8 == 0 and ad.rank <= 192:
+                lp = dict(h=h, mean=mean, rstd=rstd, seen=0)
+                spans = [self._seg_rows(b0, b1, t, pk) for _, b0, b1 in segs]
+                spans = [r_ for r_ in spans if r_.stop > r_.start]
+                # one kernel per dialect run: with several runs per layer (the mixed-dialect batch: 4) the extra launches on the main chain
+                # cost more than the side branch saves (14.81 vs 14.73 ms), with one run it pays (24-layer config 18.62 vs 18.96 ms)
+                if len(spans) != 1 or spans[0].stop - spans[0].start != h.shape[0]:
+                    lp = None
+            if lp is not None:
+                lp["packs"], lp["dh"] = self._wf_fold_packs(ad), torch.empty_like(h)
+            dz = torch.empty_like(h) if lp is None else None
             for k, b0, b1 in segs:
                 rows = self._seg_rows(b0, b1, t, pk)
                 if rows.stop == rows.start:
                     continue
                 present.add(k)
-                self._wf_bwd_rows(ad, k, rows, dy, z, t1, u, t2, dz, g, sb, jobs)
+                self._wf_bwd_rows(ad, k, rows, dy, z, t1, u, t2, dz, g, sb, jobs, lp)
             for k in range(ad.num_dialects):           # factor sets without utterances in this batch: zero gradient
                 if k not in present:
                     for prm in (ad.up_A, ad.up_bias, ad.up_B, ad.down_A, ad.down_bias, ad.down_B):
                         g.out(prm, k).zero_()
+            if lp is not None:
+                if lp["seen"] == 0:                # no utterance at all: the LayerNorm gradients are zero too
+                    g.out(ad.norm.weight).zero_()
+                    g.out(ad.norm.bias).zero_()
+                    lp["dh"].copy_(dy)
+                if jobs:
+                    def reduce_wf(jobs=jobs):
+                        for i in range(0, len(jobs), 4):
+                            ops.colreduce_multi(jobs[i:i + 4])
+                    sb.run(reduce_wf, *[j["dy"] for j in jobs])
+                return lp["dh"]
         else:
             h, mean, rstd, z, qkv, a, lse = saved
             fused_fwd = z is None

@@ -420,9 +420,10 @@ def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tens
     return out, saved
 
 
-def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor]) -> None:
+def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
+                      accumulate: bool = False) -> None:
     """Finish the column sums ``lnproj_bwd(..., want_cols=True)`` left per row tile: dgamma = Σ dz·x̂, dbeta = Σ dz, dbias = Σ dres
-    (fp32 [d] outputs, any may be None), summed in fixed order."""
+    (fp32 [d] outputs, any may be None), summed in fixed order.  ``accumulate``: add to dgamma / dbeta instead of overwriting them."""
     _need(col_partial, F32, "col_partial", 3)
     three, tiles, d = col_partial.shape
     if three != 3 or not col_partial.is_contiguous():
@@ -432,12 +433,13 @@ def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor],
             _need(t_, F32, nm, 1)
             if t_.numel() != d or not t_.is_contiguous():
                 raise ValueError(f"lnproj_bwd_reduce: {nm} must be a contiguous [d] tensor")
-    L.check(L.load().jl_lnproj_bwd_reduce(col_partial.data_ptr(), tiles, d, _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()))
+    L.check(L.load().jl_lnproj_bwd_reduce(col_partial.data_ptr(), tiles, d, _ptr(dgamma), _ptr(dbeta), _ptr(dbias), 1 if accumulate else 0, _stream()))
 
 
 def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
-               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False, want_wgrad_operands: bool = False):
-    """Backward through LayerNorm → projection (W [n, d], n in {64, 128, 192}) in one kernel: dx = LayerNorm'(dy · W) + dres.
+               rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False, want_wgrad_operands: bool = False,
+               out: Optional[torch.Tensor] = None):
+    """Backward through LayerNorm → projection (W [n, d], n a multiple of 8, at most 192) in one kernel: dx = LayerNorm'(dy · W) + dres.
     ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
     dz = dy · W (bf16) only when ``want_dz``.  ``want_cols``: → (dx, dz | None, col_partial [3, ⌈rows/128⌉, d] fp32) — per-row-tile column
     sums for ``lnproj_bwd_reduce`` (the LayerNorm weight gradients and the bias gradient behind ``dres`` without reading dz again)."""
@@ -452,7 +454,14 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
     d = h.shape[1]
     if y.shape != (rows, n) or w.shape != (n, d) or not w.is_contiguous() or h.shape[0] != rows or dres.shape != (rows, d):
         raise ValueError("lnproj_bwd: shapes do not match")
-    dx = torch.empty((rows, d), dtype=BF16, device=h.device)
+    if out is None:
+        dx = torch.empty((rows, d), dtype=BF16, device=h.device)
+    else:
+        _need(out, BF16, "out", 2)
+        _rows2d(out, "out")
+        if out.shape != (rows, d):
+            raise ValueError("lnproj_bwd: out must be [rows, d]")
+        dx = out
     dz = torch.empty((rows, d), dtype=BF16, device=h.device) if want_dz else None
     p = L.LnProjBwdParams(dy=dy.data_ptr(), lddy=dy.stride(0), y=y.data_ptr(), ldy=y.stride(0), w=w.data_ptr(), s=pack["s"].data_ptr(),
                           tb=pack["tb"].data_ptr(), gamma=gamma.data_ptr(), h=h.data_ptr(), ldh=h.stride(0), mean=mean.data_ptr(),

@@ -620,7 +620,7 @@ def test_attadapter_fused_is_bit_reproducible_and_matches_the_composed_path_on_r
     assert rel_err(out0[valid].float(), ref[valid].float()) < 1.5e-2      # two bf16 roundings of h + a (amplified) adapter update
 
 
-@pytest.mark.parametrize("rows,n,d", [(8000, 192, 768), (1000, 192, 1024), (333, 64, 128), (129, 128, 256), (5, 192, 768)])
+@pytest.mark.parametrize("rows,n,d", [(8000, 192, 768), (1000, 192, 1024), (333, 64, 128), (129, 128, 256), (5, 192, 768), (2500, 32, 1024), (700, 8, 256)])
 def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d):
     """jl_lnproj_bwd (dy · W + LayerNorm backward in one kernel, row means from dy and the saved projection output) vs (a) plain
     fp32 autograd through LayerNorm → Linear and (b) the two-kernel path it replaces (jl_gemm_bf16 + jl_layernorm_bwd)."""
@@ -661,6 +661,17 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     assert none3 is None and torch.equal(dx3, dx) and cols.shape == (3, (rows + 127) // 128, d)
     assert rel_err(db, dbeta_ref) < 5e-3 and rel_err(dg, dgamma_ref) < 5e-3, (rel_err(db, dbeta_ref), rel_err(dg, dgamma_ref))
     assert rel_err(do, dres.float().sum(0)) < 1e-5
+    # accumulate: a second call adds to dgamma / dbeta and overwrites dbias
+    ops.lnproj_bwd_reduce(cols, dg, db, do, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel_err(db, 2 * dbeta_ref) < 5e-3 and rel_err(dg, 2 * dgamma_ref) < 5e-3 and rel_err(do, dres.float().sum(0)) < 1e-5
+    # into a caller-provided row slice
+    big = torch.zeros((rows + 7, d), dtype=BF16, device="cuda")
+    ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, out=big[3:3 + rows] if (3 * d * 2) % 16 == 0 else big[8 - 8:rows])
+    torch.cuda.synchronize()
+    assert torch.equal(big[3:3 + rows] if (3 * d * 2) % 16 == 0 else big[:rows], dx)
+    if n % 64 != 0:
+        return
     # the projection's own weight / bias gradient without LN(h): (dy ⊙ rstd)ᵀ h finished by lnproj_wgrad
     dx4, none4, dys, wpart = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_wgrad_operands=True)
     m0 = torch.empty((n, d), dtype=F32, device="cuda")
