@@ -597,6 +597,8 @@ class JLEngine:
         optimizer)."""
         w = self._bf16(ad.down_B)
         ent = self._wf_fold.get(id(ad))
+        if ent is not None and self._att_packed_step and all(e is not None for e in ent):
+            return ent             # derived by _att_pack_all at the start of this step's forward pass
         if ent is None:
             ent = [None] * ad.num_dialects
             self._wf_fold[id(ad)] = ent
@@ -626,6 +628,18 @@ class JLEngine:
                 w = self._cat_bf16([ad.q_proj.weight, ad.k_proj.weight, ad.v_proj.weight])
                 bq = self._cat_f32([ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias])
                 jobs.append((w, bq, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[1]))
+        if self.fused_wf_bwd:
+            # ... and the fold vectors of the WFAdapters' first projections (jl_lnproj_bwd in their backward pass)
+            for layer in self.enc.layers:
+                for ad in (layer.adapter_attn, layer.adapter_ffn):
+                    if ad is None or ad.kind != "wf":
+                        continue
+                    ent = self._wf_fold.get(id(ad))
+                    if ent is None or any(e is None for e in ent):
+                        continue                                 # first step: allocated (and packed) where they are first needed
+                    w = self._bf16(ad.down_B)
+                    for k in range(ad.num_dialects):
+                        jobs.append((w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[k]))
         if jobs:
             ops.lnfold_pack_multi(jobs)
         self._att_packed_step = True
@@ -1124,7 +1138,7 @@ class JLEngine:
         scale = 1.0 / 8.0   # head_dim 64
         st.layers = []
         self._att_packed_step = False
-        if training and self.fused_att and t <= 256:
+        if training:
             self._att_pack_all()
         for i, layer in enumerate(self.enc.layers):
             sv = _State()

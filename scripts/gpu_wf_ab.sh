@@ -10,9 +10,9 @@ if grep -q "failed\|rror" gpurun_out/t_wf.log; then exit 1; fi
 L="--steps 10 --warmup 3 --no-inference --no-cpu-baseline --no-kernel-rooflines"
 run wf_large_on 600 python bench.py --config large $L
 JL_FUSED_WF_BWD=0 run wf_large_off 600 python bench.py --config large $L
-run wf_mixed_on 600 python bench.py --config mixed $L
-JL_FUSED_WF_BWD=0 run wf_mixed_off 600 python bench.py --config mixed $L
-for f in wf_large_on wf_large_off wf_mixed_on wf_mixed_off; do python -c "
+
+
+for f in wf_large_on wf_large_off; do python -c "
 import json
 d=json.load(open('gpurun_out/$f.log'))
 print('$f', round(d['value']), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'launches', d['gpu_launches_per_step'], 'loss', d['loss'])
