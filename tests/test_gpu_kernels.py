@@ -692,3 +692,27 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     torch.cuda.synchronize()
     e_fused, e_two = rel_err(dx.float() - dres.float(), dx_ref - dres.float()), rel_err(dxc.float() - dres.float(), dx_ref - dres.float())
     assert e_fused <= max(1.5 * e_two, 8e-3), (e_fused, e_two)     # no less accurate than what it replaces (dz is not rounded to bf16 here)
+
+
+def test_lnfold_pack_multi_equals_single_packs():
+    """One launch for many projections (every AttAdapter / WFAdapter of a model at the start of a training step) == one launch each,
+    bit for bit, including jobs of different n (192 and 32) in the same launch and more jobs than one launch holds."""
+    P = pkg()
+    ops = P.ops
+    g = _g(41)
+    d = 256
+    jobs, singles = [], []
+    for i in range(53):
+        n = 192 if i % 3 else 32
+        w = (torch.randn(n, d, device="cuda", generator=g) * 0.1).to(BF16)
+        bias = torch.randn(n, device="cuda", generator=g) if i % 2 else None
+        gamma = 1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)
+        beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+        singles.append(ops.lnfold_pack(w, bias, gamma, beta))
+        bufs = {k: torch.full_like(v, 7.0) for k, v in singles[-1].items()}
+        jobs.append((w, bias, gamma, beta, bufs))
+    ops.lnfold_pack_multi(jobs)
+    torch.cuda.synchronize()
+    for (w, bias, gamma, beta, bufs), ref in zip(jobs, singles):
+        for k in ("w", "s", "tb"):
+            assert torch.equal(bufs[k], ref[k]), k

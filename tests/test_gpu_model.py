@@ -152,6 +152,20 @@ def test_trainer_step_matches_autograd_path_and_updates_adapters():
     torch.cuda.synchronize()
     assert loss_c < loss_b
     assert tr.launches_per_step > 50
+    # prefetching path: submit() stages the next batch on a copy stream, step_async() returns a handle whose item() waits for that
+    # step's 4-byte device → host copy only; the losses read late (after the next launch) are the losses of their own steps
+    wp, lp = wave.pin_memory(), labels.to(I32).pin_memory()
+    tr.submit(wp, ns, lp)
+    handles = []
+    for i in range(3):
+        hd = tr.step_async()
+        if i < 2:
+            tr.submit(wp, ns, lp)
+        handles.append(hd)
+    lagged = [hd.item() for hd in handles]
+    assert lagged[0] < loss_c and lagged[1] < lagged[0] and lagged[2] < lagged[1], (loss_c, lagged)
+    ref = tr.step(wp, ns, lp).item()
+    assert ref < lagged[2]
 
 
 @pytest.mark.parametrize("fused_wf_train", [False, True])
