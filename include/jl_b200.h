@@ -288,6 +288,9 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
 /* The projection's weight / bias gradient WITHOUT LN(h):  m0 = dy_scaled^T h  (a jl_gemm_bf16 with MN-major operands, fp32 [n, d]) is
  * finished in place:  dW = (m0 - v 1^T) * gamma + cs beta^T,  dbias = cs,  with cs / v = the column sums in wgrad_partial
  * (partial_rows = 4 * ceil(rows / 128)).  Replaces the LayerNorm recomputation + jl_colsum_bf16 of the two-kernel path. */
+/* dy_scaled / wgrad_partial (see jl_lnproj_bwd_params) produced by a kernel of their own, for the weight-gradient branch */
+int jl_lnproj_wgrad_prep(const void* dy, int64_t lddy, const float* mean, const float* rstd, int32_t rows, int32_t n, void* dy_scaled, int64_t lddys,
+                         float* wgrad_partial, void* stream);
 int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t partial_rows, int32_t n, int32_t d, const float* gamma, const float* beta,
                     float* dbias, void* stream);
 /* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial; accumulate != 0: dgamma and dbeta

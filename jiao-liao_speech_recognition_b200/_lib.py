@@ -150,6 +150,7 @@ SYMBOLS = {
     "jl_lnproj_bwd": (C.c_int, [C.POINTER(LnProjBwdParams), vp]),
     "jl_lnproj_bwd_reduce": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp]),
     "jl_lnproj_wgrad": (C.c_int, [vp, i64, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "jl_lnproj_wgrad_prep": (C.c_int, [vp, i64, vp, vp, i32, i32, vp, i64, vp, vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_fusion_combine_bwd": (C.c_int, [C.POINTER(FusionParams), vp]),
     "jl_attn_fwd": (C.c_int, [C.POINTER(AttnFwdParams), vp]),

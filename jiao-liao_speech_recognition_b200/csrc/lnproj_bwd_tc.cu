@@ -405,9 +405,62 @@ __global__ void __launch_bounds__(256) lnproj_wgrad_kernel(float* __restrict__ m
   if (t == 0 && dbias != nullptr) dbias[k] = cs;
 }
 
+// The operands of jl_lnproj_wgrad as a kernel of their own (for the weight-gradient branch): dy ⊙ rstd (bf16) and, per 32 rows, the
+// column sums of dy and of (dy ⊙ rstd) μ.  CTA = 128 rows, 256 threads: thread = (row, half of every 64-column group).
+__global__ void __launch_bounds__(256) lnproj_wgrad_prep_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, int rows, int n, __nv_bfloat16* __restrict__ dys, int64_t lddys,
+                                                                float* __restrict__ partial) {
+  jl::pdl_prologue();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, grp = warp >> 2;
+  const int row = blockIdx.x * 128 + quad * 32 + lane;
+  const bool ok = row < rows;
+  const float mu = ok ? __ldg(mean + row) : 0.0f, rs = ok ? __ldg(rstd + row) : 0.0f;
+  const int64_t prow = static_cast<int64_t>(blockIdx.x) * 4 + quad, nrows = static_cast<int64_t>(gridDim.x) * 4;
+  for (int c0 = grp * 32; c0 < n; c0 += 64) {
+    float dv[32], dm[32];
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = ok && c0 + j * 8 < n;
+      const uint4 v4 = in ? __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(row) * lddy + c0) + j) : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 d2 = unpack_bf16x2(w4[q]);
+        dv[j * 8 + 2 * q] = d2.x;
+        dv[j * 8 + 2 * q + 1] = d2.y;
+        pk[j * 4 + q] = pack_bf16x2(d2.x * rs, d2.y * rs);
+        const float2 s2 = unpack_bf16x2(pk[j * 4 + q]);
+        dm[j * 8 + 2 * q] = s2.x * mu;
+        dm[j * 8 + 2 * q + 1] = s2.y * mu;
+      }
+      if (in) reinterpret_cast<uint4*>(dys + static_cast<int64_t>(row) * lddys + c0)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    const float cs = lp_warp_colsum(dv, lane), vm = lp_warp_colsum(dm, lane);
+    if (c0 + lane < n) {
+      partial[prow * n + c0 + lane] = cs;
+      partial[(nrows + prow) * n + c0 + lane] = vm;
+    }
+  }
+}
+
 }  // namespace jl
 
 extern "C" {
+
+int jl_lnproj_wgrad_prep(const void* dy, int64_t lddy, const float* mean, const float* rstd, int32_t rows, int32_t n, void* dy_scaled, int64_t lddys,
+                         float* wgrad_partial, void* stream) {
+  JL_REQUIRE(dy && mean && rstd && dy_scaled && wgrad_partial && rows > 0 && n > 0 && (n % 8) == 0, JL_EINVAL, "lnproj_wgrad_prep: bad arguments");
+  JL_REQUIRE((lddy % 8) == 0 && (lddys % 8) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy_scaled)) & 15) == 0, JL_EINVAL,
+             "lnproj_wgrad_prep: 16-byte aligned pointers and row strides that are multiples of 8");
+  int rc = jl::check_device();
+  if (rc != JL_OK) return rc;
+  jl::launch(jl::lnproj_wgrad_prep_kernel, jl::ceil_div(rows, 128), 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
+             mean, rstd, static_cast<int>(rows), static_cast<int>(n), reinterpret_cast<__nv_bfloat16*>(dy_scaled), lddys, wgrad_partial);
+  JL_CHECK_LAUNCH("lnproj_wgrad_prep");
+  return JL_OK;
+}
 
 int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t partial_rows, int32_t n, int32_t d, const float* gamma, const float* beta,
                     float* dbias, void* stream) {

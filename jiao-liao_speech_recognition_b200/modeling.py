@@ -394,7 +394,9 @@ class JLEngine:
         self.fused_att = os.environ.get("JL_FUSED_ATT", "1") != "0"
         # tail of the AttAdapter backward (dqkv · W_qkv + LayerNorm backward) as one kernel (jl_lnproj_bwd)
         self.fused_att_bwd = os.environ.get("JL_FUSED_ATT_BWD", "1") != "0"
-        self.lp_wgrad = os.environ.get("JL_LP_WGRAD", "0") == "1"      # dW_qkv without LN(h) (jl_lnproj_wgrad): measured slower in the step (6.07 vs 6.03 ms), off
+        # dW_qkv without LN(h) (jl_lnproj_wgrad): 0 = off (LN(h) recomputed on the weight-gradient branch), 1 = operands from the prologue of
+        # jl_lnproj_bwd (measured slower in the step: 6.07 vs 6.03 ms), 2 = operands from jl_lnproj_wgrad_prep on the weight-gradient branch
+        self.lp_wgrad = int(os.environ.get("JL_LP_WGRAD", "0"))
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._att_packed_step = False
@@ -952,7 +954,7 @@ class JLEngine:
             # tail of the backward as one kernel (jl_lnproj_bwd): it also leaves what the weight-gradient branch needs for dγ, dβ, db_o
             # and (without LN(h)) for dW_qkv, db_qkv
             use_lp = self.fused_att_bwd and _LN_WGRAD != "main" and ad.hidden_size % 64 == 0 and ad.hidden_size <= 1024
-            if z is None and not use_lp:
+            if z is None and not use_lp:       # (with use_lp the variants below recompute it only if they need it)
                 # the fused forward kernel never wrote LN(h); only dW_qkv = dqkvᵀ · LN(h) needs it: recomputed on the weight-gradient
                 # branch into a buffer allocated here, on the main stream
                 z = torch.empty_like(h)
@@ -972,6 +974,21 @@ class JLEngine:
             bs = [ad.q_proj.bias, ad.k_proj.bias, ad.v_proj.bias]
 
             gb_cat = g.out_cat(bs)
+            if use_lp and self.lp_wgrad == 2:
+                # dW_qkv without LN(h), its operands derived on the weight-gradient branch (jl_lnproj_wgrad_prep): nothing added to the main chain
+                dh, _, cols = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd), ad.norm.weight.detach(),
+                                             h, mean, rstd, dy, want_cols=True)
+                sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
+
+                def w_qkv_prep():
+                    dys, wpart = ops.lnproj_wgrad_prep(dqkv, mean, rstd)
+                    gw = g.out_cat(ws)
+                    ops.gemm(dys, h, a_layout=MN, b_layout=MN, out=gw, out_dtype=F32)                         # (dqkv ⊙ rstd)ᵀ · h
+                    ops.lnproj_wgrad(gw, wpart, ad.norm.weight.detach(), ad.norm.bias.detach(), gb_cat)
+                    g.scatter_cat(ws, gw)
+                    g.scatter_cat(bs, gb_cat)
+                sb.run(w_qkv_prep, dqkv, h, mean, rstd)
+                return dh
             if use_lp and not self.lp_wgrad:
                 # (variant kept for A/B: dW_qkv from LN(h) recomputed on the weight-gradient branch, as the two-kernel path does)
                 if z is None:

@@ -480,6 +480,18 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
     return out + (dys, wpart) if want_wgrad_operands else out
 
 
+def lnproj_wgrad_prep(dy: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
+    """→ (dy ⊙ rstd bf16 [rows, n], wpart fp32 [2, 4·⌈rows/128⌉, n]): the operands of ``lnproj_wgrad`` from a kernel of their own."""
+    _need(dy, BF16, "dy", 2)
+    _rows2d(dy, "dy")
+    rows, n = dy.shape
+    dys = torch.empty((rows, n), dtype=BF16, device=dy.device)
+    wpart = torch.empty((2, 4 * ((rows + 127) // 128), n), dtype=F32, device=dy.device)
+    L.check(L.load().jl_lnproj_wgrad_prep(dy.data_ptr(), dy.stride(0), mean.data_ptr(), rstd.data_ptr(), rows, n, dys.data_ptr(), dys.stride(0),
+                                          wpart.data_ptr(), _stream()))
+    return dys, wpart
+
+
 def lnproj_wgrad(m0: torch.Tensor, wpart: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
     """Finish the weight gradient of a projection that follows a LayerNorm, in place: ``m0`` [n, d] fp32 = (dy ⊙ rstd)ᵀ · h (from
     ``gemm`` with MN-major operands) → dW = (m0 − v 1ᵀ) ⊙ γ + cs βᵀ; ``dbias`` [n] ← cs.  ``wpart`` from ``lnproj_bwd``."""

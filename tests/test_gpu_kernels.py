@@ -684,6 +684,10 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     dw_ref = dy.float().T @ z.detach()
     assert rel_err(m0, dw_ref) < 1e-2, rel_err(m0, dw_ref)
     assert rel_err(dbq, dy.float().sum(0)) < 1e-4
+    # the same operands from the stand-alone kernel (weight-gradient branch): bit-identical
+    dys2, wpart2 = ops.lnproj_wgrad_prep(dy, mean, rstd)
+    torch.cuda.synchronize()
+    assert torch.equal(dys2, dys) and torch.equal(wpart2, wpart)
     assert rel_err(dz.float(), dz_ref) < 6e-3, rel_err(dz.float(), dz_ref)
     assert rel_err(dx.float() - dres.float(), dx_ref - dres.float()) < 1.5e-2, rel_err(dx.float() - dres.float(), dx_ref - dres.float())
     # the two-kernel path
