@@ -422,6 +422,8 @@ def run_ours(args):
     P = importlib.import_module(PKG)
     if os.environ.get("JL_PDL") in ("0", "1"):     # tuning aid: programmatic dependent launch off / on (default: on)
         P._lib.load().jl_debug_set_pdl(int(os.environ["JL_PDL"]))
+    if os.environ.get("JL_LNPROJ_SPLIT"):          # tuning aid: CTAs per row tile of jl_lnproj_bwd
+        P._lib.load().jl_debug_set_lnproj_split(int(os.environ["JL_LNPROJ_SPLIT"]))
     if os.environ.get("JL_GEMM_TAIL"):             # tuning aid: tail-wave policy of the GEMM (jl_debug_set_gemm_tail bit mask)
         P._lib.load().jl_debug_set_gemm_tail(int(os.environ["JL_GEMM_TAIL"]))
     wl = WORKLOADS[args.config]

@@ -283,6 +283,7 @@ typedef struct {
                                           summed by jl_lnproj_bwd_reduce — the LayerNorm weight gradients without a dz tensor */
   void* dy_scaled; int64_t lddys;      /* optional bf16 [rows, n] out: dy * rstd (row-scaled), the A operand of the projection's weight gradient */
   float* wgrad_partial;                /* with dy_scaled: fp32 [2][4 * ceil(rows / 128)][n] column sums of dy and of dy_scaled * mean per 32 rows */
+  int32_t col_split;                   /* CTAs per 128-row tile (column ranges): 0 = automatic, 1, 2 — 2 lowers the kernel's latency, 1 its SM-time */
 } jl_lnproj_bwd_params;
 int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
 /* The projection's weight / bias gradient WITHOUT LN(h):  m0 = dy_scaled^T h  (a jl_gemm_bf16 with MN-major operands, fp32 [n, d]) is
@@ -502,6 +503,8 @@ void jl_debug_set_gemm_tail(int mode);
 
 /* test-only device reference GEMM (SIMT fp32 accumulate) used by tests/ to check jl_gemm_bf16 at
  * sizes the CPU oracle cannot reach; never called by the product path. */
+/* CTAs per row tile of jl_lnproj_bwd (column ranges): 0 = automatic, 1, 2, ... */
+void jl_debug_set_lnproj_split(int split);
 int jl_debug_gemm_ref(const jl_gemm_params* p, void* stream);
 
 #ifdef __cplusplus

@@ -80,7 +80,7 @@ class LnProjBwdParams(C.Structure):
     _fields_ = [("dy", vp), ("lddy", i64), ("y", vp), ("ldy", i64), ("w", vp), ("s", vp), ("tb", vp), ("gamma", vp), ("h", vp), ("ldh", i64),
                 ("mean", vp), ("rstd", vp), ("dres", vp), ("lddres", i64), ("dx", vp), ("lddx", i64), ("dz", vp), ("lddz", i64),
                 ("rows", i32), ("n", i32), ("d", i32), ("col_partial", vp),
-                ("dy_scaled", vp), ("lddys", i64), ("wgrad_partial", vp)]
+                ("dy_scaled", vp), ("lddys", i64), ("wgrad_partial", vp), ("col_split", i32)]
 
 
 class FusionParams(C.Structure):
@@ -136,6 +136,7 @@ SYMBOLS = {
     "jl_gemm_workspace_zero_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),
     "jl_debug_set_attn_impl": (None, [C.c_int]),
     "jl_debug_set_pdl": (None, [C.c_int]),
+    "jl_debug_set_lnproj_split": (None, [i32]),
     "jl_gemm_workspace_bytes": (C.c_int, [C.POINTER(GemmParams), C.POINTER(C.c_size_t)]),
     "jl_layernorm_fwd": (C.c_int, [C.POINTER(LayerNormFwdParams), vp]),
     "jl_layernorm_bwd_workspace_bytes": (C.c_int, [C.POINTER(LayerNormBwdParams), C.POINTER(C.c_size_t)]),

@@ -32,6 +32,7 @@ constexpr int LP_ACC = 8;                           // TMEM accumulators of 64 c
 constexpr uint32_t LP_T128 = 128 * 128;             // bytes of a [128 x 64] bf16 tile
 constexpr uint32_t LP_BCH = 192 * 128;              // bytes of a [192 x 64] bf16 box
 constexpr int LP_MAX_D = 1024;
+extern int g_lnproj_split;
 
 struct __align__(1024) LpSmem {
   uint8_t a[3][LP_T128];                // dy tiles (k = 64-column groups of dy)
@@ -445,9 +446,13 @@ __global__ void __launch_bounds__(256) lnproj_wgrad_prep_kernel(const __nv_bfloa
   }
 }
 
+int g_lnproj_split = 0;     // 0 = automatic; tuning aid (jl_debug_set_lnproj_split)
+
 }  // namespace jl
 
 extern "C" {
+
+void jl_debug_set_lnproj_split(int split) { jl::g_lnproj_split = split; }
 
 int jl_lnproj_wgrad_prep(const void* dy, int64_t lddy, const float* mean, const float* rstd, int32_t rows, int32_t n, void* dy_scaled, int64_t lddys,
                          float* wgrad_partial, void* stream) {
@@ -516,10 +521,14 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
     configured_dev = dev;
   }
   const int row_tiles = jl::ceil_div(p->rows, 128);
-  // Two CTAs per row tile (column halves) make the kernel itself faster (8000 x 768: 12.7 vs 19.9 µs with dz) but the fine-tune step
-  // slower (6.20 vs 6.17 ms): there the weight-gradient branch fills the SMs this kernel leaves idle, and the split repeats the
-  // prologue.  So: split only when the row tiles alone would leave most of the machine idle AND nothing else is likely to run.
-  const int split = (row_tiles * 8 <= jl::num_sms() && p->d >= 128) ? 2 : 1;      // (col_partial rows are indexed by the row tile only: any split works)
+  // Two CTAs per row tile (column halves) make the kernel itself faster (8000 x 768: 12.7 vs 19.9 µs with dz).  Whether the STEP gets
+  // faster depends on what runs beside it: with a busy weight-gradient branch (it fills the SMs this kernel leaves idle) the split only
+  // repeats the prologue (base config before the column partials: 6.20 vs 6.17 ms; 24-layer config with two adapters per layer: 18.48 vs
+  // 18.30 ms); with a light one it pays (base config now: 5.95 vs 5.99 ms).  The caller knows and says so with col_split; automatic =
+  // split only when the row tiles alone would leave most of the machine idle.
+  int split = (row_tiles * 8 <= jl::num_sms() && p->d >= 128) ? 2 : 1;
+  if (p->col_split > 0 && p->d >= 128 * p->col_split) split = p->col_split;
+  if (jl::g_lnproj_split > 0 && p->d >= 128 * jl::g_lnproj_split) split = jl::g_lnproj_split;      // (col_partial rows are indexed by the row tile only: any split works)
   jl::launch(jl::lnproj_bwd_kernel, dim3(row_tiles, split), jl::LP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_dy, t_y, t_w, t_h, t_r, *p);
   JL_CHECK_LAUNCH("lnproj_bwd");
   return JL_OK;

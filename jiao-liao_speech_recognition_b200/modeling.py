@@ -397,6 +397,10 @@ class JLEngine:
         # dW_qkv without LN(h) (jl_lnproj_wgrad): 0 = off (LN(h) recomputed on the weight-gradient branch), 1 = operands from the prologue of
         # jl_lnproj_bwd (measured slower in the step: 6.07 vs 6.03 ms), 2 = operands from jl_lnproj_wgrad_prep on the weight-gradient branch
         self.lp_wgrad = int(os.environ.get("JL_LP_WGRAD", "0"))
+        # CTAs per row tile of jl_lnproj_bwd in the AttAdapter backward: 2 (lower latency) when the layer's weight-gradient branch is light
+        # (one adapter per layer: base config 5.95 vs 5.99 ms), 1 (less SM-time) with two adapters per layer (24-layer config 18.30 vs 18.48 ms)
+        two = any(l.adapter_attn is not None and l.adapter_ffn is not None for l in self.enc.layers)
+        self.lp_col_split = int(os.environ.get("JL_LNPROJ_COL_SPLIT", "1" if two else "2"))
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._att_packed_step = False
@@ -995,7 +999,7 @@ class JLEngine:
                     z = torch.empty_like(h)
                     sb.run(lambda z=z: ops.layernorm_fwd(h, ad.norm.weight.detach(), ad.norm.bias.detach(), ad.norm.eps, out=z), h, z)
                 dh, _, cols = ops.lnproj_bwd(dqkv, qkv, self._cat_bf16(ws), self._att_pack_dev(ad, True, reuse=fused_fwd), ad.norm.weight.detach(),
-                                             h, mean, rstd, dy, want_cols=True)
+                                             h, mean, rstd, dy, want_cols=True, col_split=self.lp_col_split)
                 sb.run(lambda: ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), g.out(ad.o_proj.bias)), cols)
 
                 def w_qkv_z():

@@ -438,7 +438,7 @@ def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor],
 
 def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
                rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False, want_wgrad_operands: bool = False,
-               out: Optional[torch.Tensor] = None):
+               out: Optional[torch.Tensor] = None, col_split: int = 0):
     """Backward through LayerNorm → projection (W [n, d], n a multiple of 8, at most 192) in one kernel: dx = LayerNorm'(dy · W) + dres.
     ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
     dz = dy · W (bf16) only when ``want_dz``.  ``want_cols``: → (dx, dz | None, col_partial [3, ⌈rows/128⌉, d] fp32) — per-row-tile column
@@ -469,6 +469,7 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
                           dz=_ptr(dz), lddz=dz.stride(0) if dz is not None else 0, rows=rows, n=n, d=d)
     cols = torch.empty((3, (rows + 127) // 128, d), dtype=F32, device=h.device) if want_cols else None
     p.col_partial = _ptr(cols)
+    p.col_split = col_split
     dys = wpart = None
     if want_wgrad_operands:
         # ``dys`` = dy ⊙ rstd (bf16), ``wpart`` [2, 4·⌈rows/128⌉, n]: operands of ``lnproj_wgrad`` (the projection's weight / bias gradient)
