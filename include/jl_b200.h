@@ -242,6 +242,8 @@ typedef struct {
   float scale, eps;
   int32_t zero_padded_rows;            /* padded layout: rows t >= length are written as 0 (else b_o + h, as the composed path) */
   void* qkv_out; void* a_out; float* mean; float* rstd; float* lse;      /* optional (training) */
+  int32_t col_split;                   /* 2: two clusters per utterance share the output columns (each repeats the attention): lower
+                                          latency, more SM-time; 0 / 1: one */
 } jl_attadapter_fwd_params;
 int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream);
 /* LayerNorm folding of a projection that follows a LayerNorm: LN(h) W^T + bias = rstd (h W'^T - mean s) + tb with

@@ -69,7 +69,7 @@ class WFAdapterPackParams(C.Structure):
 class AttAdapterFwdParams(C.Structure):
     _fields_ = [("h", vp), ("ldh", i64), ("out", vp), ("ldo", i64), ("wqkv_scaled", vp), ("s", vp), ("tb", vp), ("wo", vp), ("bo", vp),
                 ("lengths", vp), ("cu_seqlens", vp), ("total_rows", i32), ("batch", i32), ("seq", i32), ("d", i32), ("scale", f32), ("eps", f32),
-                ("zero_padded_rows", i32), ("qkv_out", vp), ("a_out", vp), ("mean", vp), ("rstd", vp), ("lse", vp)]
+                ("zero_padded_rows", i32), ("qkv_out", vp), ("a_out", vp), ("mean", vp), ("rstd", vp), ("lse", vp), ("col_split", i32)]
 
 
 class LnFoldPackParams(C.Structure):

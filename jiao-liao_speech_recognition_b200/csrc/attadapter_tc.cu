@@ -135,7 +135,12 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
   const int g = blockIdx.x, b = blockIdx.y;         // frame half (= rank in the cluster), utterance
   const uint32_t peer = static_cast<uint32_t>(g ^ 1);
   const int nk = p.d / 64;                          // k-chunks of the projections
-  const int nc = p.d / 128;                         // 128-column chunks of the output projection
+  // 128-column chunks of the output projection; gridDim.z clusters per utterance share them (each repeats phases A-C: more SM-time,
+  // a shorter phase D — for when the kernel's latency, not the machine's occupancy, bounds the step)
+  const int nc_all = p.d / 128;
+  const int c_begin = static_cast<int>((static_cast<int64_t>(nc_all) * blockIdx.z) / gridDim.z);
+  const int nc = static_cast<int>((static_cast<int64_t>(nc_all) * (blockIdx.z + 1)) / gridDim.z) - c_begin;
+  const bool first_z = blockIdx.z == 0;             // writes the tensors saved for the backward pass
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&t_h);
@@ -214,7 +219,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
       // all of W_o (or its first chunks) right away: dedicated buffers
       for (int c = 0; c < min(nc, AA_WO_BUFS); ++c) {
         ptx::mbar_expect_tx(&s.wo_full[c], AA_T128);
-        ptx::tma_load_2d(s.wo[c], &t_wo, &s.wo_full[c], 0, c * 128);
+        ptx::tma_load_2d(s.wo[c], &t_wo, &s.wo_full[c], 0, (c_begin + c) * 128);
       }
       for (int kc = 0; kc < nk; ++kc) {
         const int st = kc % AA_STAGES;
@@ -237,13 +242,13 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         if (c >= AA_STG) ptx::mbar_wait(&s.res_empty[sb], ((c / AA_STG) - 1) & 1);
         uint8_t* stg = R + sb * (2 * AA_T128);
         ptx::mbar_expect_tx(&s.res_full[sb], 2 * AA_T128);
-        ptx::tma_load_2d(stg, &t_h, &s.res_full[sb], c * 128, grow + g * 128);
-        ptx::tma_load_2d(stg + AA_T128, &t_h, &s.res_full[sb], c * 128 + 64, grow + g * 128);
+        ptx::tma_load_2d(stg, &t_h, &s.res_full[sb], (c_begin + c) * 128, grow + g * 128);
+        ptx::tma_load_2d(stg + AA_T128, &t_h, &s.res_full[sb], (c_begin + c) * 128 + 64, grow + g * 128);
         if (c >= AA_WO_BUFS) {
           const int wb = c % AA_WO_BUFS;
           ptx::mbar_wait(&s.wo_empty[wb], ((c / AA_WO_BUFS) - 1) & 1);
           ptx::mbar_expect_tx(&s.wo_full[wb], AA_T128);
-          ptx::tma_load_2d(s.wo[wb], &t_wo, &s.wo_full[wb], 0, c * 128);
+          ptx::tma_load_2d(s.wo[wb], &t_wo, &s.wo_full[wb], 0, (c_begin + c) * 128);
         }
       }
     }
@@ -297,7 +302,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
     if (!active) {
       // no valid frame in this half: the rows the layout still owns get what the composed path gives them — a = 0, so
       // out = b_o + h (or 0 when the caller wants padded rows zeroed); saved tensors are zero there
-      if (qrow < lim) {
+      if (qrow < lim && first_z) {
         __nv_bfloat16* out_row = reinterpret_cast<__nv_bfloat16*>(p.out) + (row_base + qrow) * p.ldo;
         const __nv_bfloat16* h_row = reinterpret_cast<const __nv_bfloat16*>(p.h) + (row_base + qrow) * p.ldh;
         for (int c = grp * (p.d / 16); c < (grp + 1) * (p.d / 16); ++c) {          // 8 columns per step, half the row per warp group
@@ -373,7 +378,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
           const float rstd = 1.0f / sqrtf(var + p.eps);
           s.mu[r] = mu;
           s.rs[r] = rstd;
-          if (p.mean != nullptr && qrow < lim) {
+          if (p.mean != nullptr && qrow < lim && first_z) {
             p.mean[row_base + qrow] = mu;
             p.rstd[row_base + qrow] = rstd;
           }
@@ -428,7 +433,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         if (pair) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&s.kv_ready), peer));
       }
       AA_T(3);
-      if (p.qkv_out != nullptr) {
+      if (p.qkv_out != nullptr && first_z) {
         // q | k | v of the CTA's rows, from the operand tiles (they stay until the softmax overwrites them with P)
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const uint32_t rb = ptx::smem_u32(R);
@@ -505,7 +510,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
 #pragma unroll
         for (int c = 0; c < 4; ++c) aa_store_chunk(R + AA_OFF_A, r, grp * 4 + c, pk + 4 * c);
-        if (p.lse != nullptr && grp == 0 && qrow < lim)
+        if (p.lse != nullptr && grp == 0 && qrow < lim && first_z)
           p.lse[(p.cu_seqlens ? row_base : static_cast<int64_t>(b) * p.seq) + qrow] = valid ? mx * p.scale + logf(l_tot) : 0.0f;
       }
       ptx::tc_fence_before();
@@ -513,7 +518,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s.a_ready);
       AA_T(7);
-      if (p.a_out != nullptr) {
+      if (p.a_out != nullptr && first_z) {
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const uint32_t tiles[1] = {ptx::smem_u32(R) + AA_OFF_A};
         aa_tiles_to_global<1>(tiles, reinterpret_cast<__nv_bfloat16*>(p.a_out) + (row_base + g * 128) * 64, 64, rows_owned, et);
@@ -540,7 +545,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         ptx::tmem_ld_32x32(tmem + ob * 128 + lane_off + grp * 64 + 32, vb);
         ptx::tmem_ld_wait();
         uint8_t* mytile = stg + grp * AA_T128;
-        const float* bias = s.bo + c * 128 + grp * 64;
+        const float* bias = s.bo + (c_begin + c) * 128 + grp * 64;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           uint4* cell = reinterpret_cast<uint4*>(mytile + aa_chunk_off(r, ch));
@@ -566,7 +571,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
         AA_TO(2);
         {
           const uint32_t tiles[2] = {ptx::smem_u32(stg), ptx::smem_u32(stg) + AA_T128};
-          aa_tiles_to_global<2>(tiles, out_tile + c * 128, p.ldo, rows_owned, et);
+          aa_tiles_to_global<2>(tiles, out_tile + (c_begin + c) * 128, p.ldo, rows_owned, et);
         }
         AA_TO(3);
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -726,7 +731,8 @@ int jl_attadapter_fwd(const jl_attadapter_fwd_params* p, void* stream) {
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "attadapter_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     configured_dev = dev;
   }
-  jl::launch(jl::attadapter_fwd_kernel, dim3(2, p->batch), jl::AA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_h, t_w, t_w96, t_wo, *p);
+  const int zs = (p->col_split >= 2 && p->d >= 256) ? 2 : 1;
+  jl::launch(jl::attadapter_fwd_kernel, dim3(2, p->batch, zs), jl::AA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), t_h, t_w, t_w96, t_wo, *p);
   JL_CHECK_LAUNCH("attadapter_fwd");
   return JL_OK;
 }

@@ -401,6 +401,9 @@ class JLEngine:
         # (one adapter per layer: base config 5.95 vs 5.99 ms), 1 (less SM-time) with two adapters per layer (24-layer config 18.30 vs 18.48 ms)
         two = any(l.adapter_attn is not None and l.adapter_ffn is not None for l in self.enc.layers)
         self.lp_col_split = int(os.environ.get("JL_LNPROJ_COL_SPLIT", "1" if two else "2"))
+        # clusters per utterance of the fused AttAdapter forward (they share the output columns, each repeats the attention): 2 lowers the
+        # kernel's latency (64 -> 128 CTAs at 32 utterances): base config 5.97 -> 5.92 ms, 24-layer config 18.76 -> 18.61 ms
+        self.att_col_split = int(os.environ.get("JL_ATT_COL_SPLIT", "2"))
         self._att_bufs: Dict[int, dict] = {}
         self._vparams = None
         self._att_packed_step = False
@@ -753,7 +756,7 @@ class JLEngine:
         if ad.kind == "att" and self.fused_att and t <= 256 and ad.hidden_size % 128 == 0 and ad.hidden_size <= 1024:
             # the whole adapter in one kernel (LayerNorm folded into the q|k|v projection, attention, output projection, residual)
             out, sv = ops.attadapter_fwd(h, self._att_pack_dev(ad, training), self._bf16(ad.o_proj.weight), ad.o_proj.bias.detach(), lengths, b, t,
-                                         eps, zero_padded_rows=zero_rows, training=training, cu_seqlens=cu)
+                                         eps, zero_padded_rows=zero_rows, training=training, cu_seqlens=cu, col_split=self.att_col_split)
             if not training:
                 return out, None
             mean, rstd, qkv, a, lse = sv

@@ -387,7 +387,8 @@ def lnfold_pack_multi(jobs: list) -> None:
 
 
 def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tensor, lengths: Optional[torch.Tensor], batch: int, seq: int,
-                   eps: float, zero_padded_rows: bool = False, training: bool = False, cu_seqlens: Optional[torch.Tensor] = None):
+                   eps: float, zero_padded_rows: bool = False, training: bool = False, cu_seqlens: Optional[torch.Tensor] = None,
+                   col_split: int = 0):
     """out = h + AttAdapter(h) in one kernel (utterances of <= 256 frames).  ``pack`` = ``lnfold_pack`` of the concatenated q|k|v
     projection ([192, d]); ``wo`` [d, 64] bf16, ``bo`` [d] fp32.  Returns (out, saved) with saved = (mean, rstd, qkv [rows, 192],
     a [rows, 64], lse) when ``training`` else None."""
@@ -416,6 +417,7 @@ def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tens
                               cu_seqlens=_ptr(cu_seqlens), total_rows=rows if cu_seqlens is not None else 0, batch=batch, seq=seq, d=d,
                               scale=0.125, eps=eps, zero_padded_rows=1 if zero_padded_rows else 0, qkv_out=_ptr(qkv), a_out=_ptr(a),
                               mean=_ptr(mean), rstd=_ptr(rstd), lse=_ptr(lse))
+    p.col_split = col_split
     L.check(L.load().jl_attadapter_fwd(C.byref(p), _stream()))
     return out, saved
 

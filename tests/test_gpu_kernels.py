@@ -534,6 +534,17 @@ def test_attadapter_fused_forward_matches_oracle(d, seq, lens, packed):
     z = F.layer_norm(hv, (d,), w["a.norm.weight"], w["a.norm.bias"], ad.norm.eps)
     qkv_ref = z @ wqkv.float().cpu().T + bqkv.cpu()
     assert rel_err(qkv.float().cpu()[vrow], qkv_ref) < 1e-2
+    # two clusters per utterance sharing the output columns (col_split = 2): bit-identical outputs and saved tensors
+    if d >= 256:
+        kw = dict(training=True, col_split=2)
+        if packed:
+            out_s, sv_s = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps, cu_seqlens=cu.cuda(), **kw)
+        else:
+            out_s, sv_s = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps, zero_padded_rows=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(out_s, out)
+        for t_a, t_b in zip(sv_s, sv):
+            assert torch.equal(t_a[vrow.cuda()] if t_a.shape[0] == vrow.numel() else t_a, t_b[vrow.cuda()] if t_b.shape[0] == vrow.numel() else t_b)
     # without the saved tensors and without zeroing: padded rows get h + b_o (what the composed path writes)
     if not packed:
         out2, sv2 = ops.attadapter_fwd(h, pack, wo, bo, lengths, b, seq, ad.norm.eps)
