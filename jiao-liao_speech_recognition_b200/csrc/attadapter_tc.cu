@@ -8,11 +8,12 @@
 // h is read once for the projections and once more (L2) for the residual, out is written once.
 //
 // One CLUSTER of two CTAs per utterance, one CTA per 128-frame half, 384 threads:
-//   warp 0   TMA producer: 64-wide k-chunks of h (own 128 rows) and of W' = W_qkv ⊙ γ through a 3-stage ring — each CTA of an
-//            active pair fetches HALF of every W' chunk and multicasts it to both — and all of W_o (128-row chunks)
+//   warp 0   TMA producer: 64-wide k-chunks of h (own 128 rows) and of W' = W_qkv ⊙ γ through a 4-stage ring — each CTA of an
+//            active pair fetches HALF of every W' chunk and multicasts it to both —, W_o in 128-row chunks (3 buffers) and, in phase D,
+//            the residual tiles
 //   warp 1   tcgen05.mma issuer, accumulators in TMEM (512 columns)
 //   warp 2   TMEM allocator
-//   warps 4-11  row statistics (4 warps), then every epilogue: LayerNorm fold + bias → bf16 operand tiles, softmax, a, output
+//   warps 4-11  row statistics, then every epilogue: LayerNorm fold + bias → bf16 operand tiles, softmax, a, output
 // Phases:
 //   A  acc[128, 192] = h_own · W'ᵀ (q, k, v of the CTA's own frames).  The LayerNorm is folded into the projection,
 //      (LN(h) Wᵀ)[i, j] = rstd_i (h W'ᵀ[i, j] − μ_i s_j) + t_j, so the tensor cores consume the raw h tiles while the row threads
@@ -216,7 +217,7 @@ attadapter_fwd_kernel(const __grid_constant__ CUtensorMap t_h, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0 && active) {
-      // all of W_o (or its first chunks) right away: dedicated buffers
+      // the first W_o chunks right away: dedicated buffers
       for (int c = 0; c < min(nc, AA_WO_BUFS); ++c) {
         ptx::mbar_expect_tx(&s.wo_full[c], AA_T128);
         ptx::tma_load_2d(s.wo[c], &t_wo, &s.wo_full[c], 0, (c_begin + c) * 128);
