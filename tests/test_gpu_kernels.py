@@ -672,6 +672,12 @@ def test_lnproj_bwd_matches_gemm_plus_layernorm_bwd_and_fp32_autograd(rows, n, d
     assert none3 is None and torch.equal(dx3, dx) and cols.shape == (3, (rows + 127) // 128, d)
     assert rel_err(db, dbeta_ref) < 5e-3 and rel_err(dg, dgamma_ref) < 5e-3, (rel_err(db, dbeta_ref), rel_err(dg, dgamma_ref))
     assert rel_err(do, dres.float().sum(0)) < 1e-5
+    # two CTAs per row tile (column halves): bit-identical dx and column partials
+    if d >= 256:
+        dx5, _, cols5 = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_cols=True, col_split=2)
+        dx6, _, cols6 = ops.lnproj_bwd(dy, y, w, pack, gamma, h, mean, rstd, dres, want_cols=True, col_split=1)
+        torch.cuda.synchronize()
+        assert torch.equal(dx5, dx6) and torch.equal(dx5, dx) and torch.equal(cols5, cols6)
     # accumulate: a second call adds to dgamma / dbeta and overwrites dbias
     ops.lnproj_bwd_reduce(cols, dg, db, do, accumulate=True)
     torch.cuda.synchronize()
