@@ -286,7 +286,14 @@ typedef struct {
   void* dy_scaled; int64_t lddys;      /* optional bf16 [rows, n] out: dy * rstd (row-scaled), the A operand of the projection's weight gradient */
   float* wgrad_partial;                /* with dy_scaled: fp32 [2][4 * ceil(rows / 128)][n] column sums of dy and of dy_scaled * mean per 32 rows */
   int32_t col_split;                   /* CTAs per 128-row tile (column ranges): 0 = automatic, 1, 2 — 2 lowers the kernel's latency, 1 its SM-time */
+  /* Row runs (the dialect runs of a WFAdapter): rows [run_start[i], run_start[i+1]) use factor set run_set[i], i.e. rows set*n … of w
+   * ([w_sets * n, d]) and entries set*n … of s / tb.  Row tiles never straddle a run; col_partial then has one row per tile of every
+   * run, in run order.  num_runs = 0: one run, all rows, set 0. */
+  int32_t num_runs, w_sets;
+  int32_t run_start[9];
+  int32_t run_set[8];
 } jl_lnproj_bwd_params;
+#define JL_LNPROJ_MAX_RUNS 8
 int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream);
 /* The projection's weight / bias gradient WITHOUT LN(h):  m0 = dy_scaled^T h  (a jl_gemm_bf16 with MN-major operands, fp32 [n, d]) is
  * finished in place:  dW = (m0 - v 1^T) * gamma + cs beta^T,  dbias = cs,  with cs / v = the column sums in wgrad_partial
@@ -298,7 +305,8 @@ int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t 
                     float* dbias, void* stream);
 /* dgamma / dbeta / dbias [d] (any may be NULL) = fixed-order sums over the row tiles of col_partial; accumulate != 0: dgamma and dbeta
  * are added to (row ranges of one LayerNorm handled by several calls — the dialect runs of a WFAdapter), dbias is always overwritten */
-int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate, void* stream);
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate,
+                         int32_t tile_offset, int32_t total_tiles, void* stream);    /* sums tiles [tile_offset, tile_offset + row_tiles) of total_tiles (0 = row_tiles) */
 
 /* ------------------------------------------------------------------------------------------
  * f4: AdapterFusion-style AttAdapter over the K source-dialect adapters of a slot (SURVEY.md §8c ambiguity (ii), §8f f4;

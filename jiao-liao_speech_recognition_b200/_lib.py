@@ -80,7 +80,8 @@ class LnProjBwdParams(C.Structure):
     _fields_ = [("dy", vp), ("lddy", i64), ("y", vp), ("ldy", i64), ("w", vp), ("s", vp), ("tb", vp), ("gamma", vp), ("h", vp), ("ldh", i64),
                 ("mean", vp), ("rstd", vp), ("dres", vp), ("lddres", i64), ("dx", vp), ("lddx", i64), ("dz", vp), ("lddz", i64),
                 ("rows", i32), ("n", i32), ("d", i32), ("col_partial", vp),
-                ("dy_scaled", vp), ("lddys", i64), ("wgrad_partial", vp), ("col_split", i32)]
+                ("dy_scaled", vp), ("lddys", i64), ("wgrad_partial", vp), ("col_split", i32),
+                ("num_runs", i32), ("w_sets", i32), ("run_start", i32 * 9), ("run_set", i32 * 8)]
 
 
 class FusionParams(C.Structure):
@@ -149,7 +150,7 @@ SYMBOLS = {
     "jl_lnfold_pack": (C.c_int, [C.POINTER(LnFoldPackParams), vp]),
     "jl_lnfold_pack_multi": (C.c_int, [C.POINTER(LnFoldPackParams), i32, vp]),
     "jl_lnproj_bwd": (C.c_int, [C.POINTER(LnProjBwdParams), vp]),
-    "jl_lnproj_bwd_reduce": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, vp]),
+    "jl_lnproj_bwd_reduce": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp]),
     "jl_lnproj_wgrad": (C.c_int, [vp, i64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "jl_lnproj_wgrad_prep": (C.c_int, [vp, i64, vp, vp, i32, i32, vp, i64, vp, vp]),
     "jl_fusion_combine_fwd": (C.c_int, [C.POINTER(FusionParams), vp]),

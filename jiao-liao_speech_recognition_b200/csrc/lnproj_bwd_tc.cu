@@ -90,7 +90,20 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
   extern __shared__ uint8_t lp_smem_raw[];
   LpSmem& s = *reinterpret_cast<LpSmem*>(lp_smem_raw + ((1024u - (ptx::smem_u32(lp_smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 128;
+  // row tile → rows [row0, row_end) and the factor set of its run (several row ranges, each with its own W / s / t block: the dialect
+  // runs of a WFAdapter); without runs: tile i = rows 128 i … of the whole matrix, set 0
+  int row0 = blockIdx.x * 128, row_end = p.rows, set = 0;
+  if (p.num_runs > 0) {
+    int tile = blockIdx.x, i = 0;
+    for (; i < p.num_runs - 1; ++i) {
+      const int nt = (p.run_start[i + 1] - p.run_start[i] + 127) / 128;
+      if (tile < nt) break;
+      tile -= nt;
+    }
+    row0 = p.run_start[i] + tile * 128;
+    row_end = p.run_start[i + 1];
+    set = p.run_set[i];
+  }
   const int nkt = (p.n + 63) / 64;                  // 64-wide k tiles (columns of dy; a partial last tile is zero-filled by TMA)
   // the 64-column output chunks of the row tile may be split between gridDim.y CTAs (each repeats the small prologue): an SM takes
   // in ≈ 57 B/clk and stores ≈ 28 B/clk (see the host function for when)
@@ -98,7 +111,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
   const int c_begin = static_cast<int>((static_cast<int64_t>(nc_all) * blockIdx.y) / gridDim.y);
   const int c_end = static_cast<int>((static_cast<int64_t>(nc_all) * (blockIdx.y + 1)) / gridDim.y);
   const int nc = c_end - c_begin;                   // chunks of this CTA: global chunk index c_begin + c
-  const int rows_valid = min(128, p.rows - row0);
+  const int rows_valid = min(128, row_end - row0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&t_dy);
@@ -142,7 +155,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
       for (int kt = 0; kt < nkt; ++kt) ptx::tma_load_2d(s.hs[kt], &t_y, &s.y_full, kt * 64, row0);
       for (int c = 0; c < min(nc, LP_BUFS); ++c) {
         ptx::mbar_expect_tx(&s.b_full[c], nkt * 64 * 128);
-        ptx::tma_load_2d(s.b[c], &t_w, &s.b_full[c], (c_begin + c) * 64, 0);
+        ptx::tma_load_2d(s.b[c], &t_w, &s.b_full[c], (c_begin + c) * 64, set * p.n);
         ptx::mbar_expect_tx(&s.r_full[c], LP_T128);
         ptx::tma_load_2d(s.rs[c], &t_r, &s.r_full[c], (c_begin + c) * 64, row0);
       }
@@ -156,7 +169,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
         const uint32_t par = ((c / LP_BUFS) - 1) & 1;
         ptx::mbar_wait(&s.b_empty[bi], par);
         ptx::mbar_expect_tx(&s.b_full[bi], nkt * 64 * 128);
-        ptx::tma_load_2d(s.b[bi], &t_w, &s.b_full[bi], (c_begin + c) * 64, 0);
+        ptx::tma_load_2d(s.b[bi], &t_w, &s.b_full[bi], (c_begin + c) * 64, set * p.n);
         ptx::mbar_wait(&s.stg_empty[bi], par);
         ptx::mbar_expect_tx(&s.h_full[bi], LP_T128);
         ptx::tma_load_2d(s.hs[bi], &t_h, &s.h_full[bi], (c_begin + c) * 64, row0);
@@ -194,9 +207,9 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int row = row0 + r;
     for (int i = et; i < p.d; i += 256) s.gamma[i] = __ldg(p.gamma + i);
-    if (et < 192) { s.fs[et] = et < p.n ? __ldg(p.s + et) : 0.0f; s.ftb[et] = et < p.n ? __ldg(p.tb + et) : 0.0f; }
-    const float mu = row < p.rows ? __ldg(p.mean + row) : 0.0f;
-    const float rstd = row < p.rows ? __ldg(p.rstd + row) : 0.0f;
+    if (et < 192) { s.fs[et] = et < p.n ? __ldg(p.s + set * p.n + et) : 0.0f; s.ftb[et] = et < p.n ? __ldg(p.tb + set * p.n + et) : 0.0f; }
+    const float mu = row < row_end ? __ldg(p.mean + row) : 0.0f;
+    const float rstd = row < row_end ? __ldg(p.rstd + row) : 0.0f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- prologue: c1, c2 from dy and the saved y (this thread: every other 16-byte chunk group of its row)
     ptx::mbar_wait(&s.a_full, 0);
@@ -243,7 +256,7 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
             dm[j * 8 + 2 * q + 1] = s2.y * mu;
           }
         }
-        if (row < p.rows) {
+        if (row < row_end) {
           uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dy_scaled) + static_cast<int64_t>(row) * p.lddys + kt * 64 + grp * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -315,9 +328,15 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
       if (lane == 0) ptx::mbar_arrive(&s.acc_empty[ai]);
       if (want_cols) {
         // column sums of this warp's 32 rows: Σ dz (→ dβ), Σ dz x̂ (→ dγ), Σ dres (→ the bias gradient of the layer that produced dres)
+        // (rows past the end of a run hold the next run's data — zero-filled by TMA only past the end of the matrix)
+        const bool live = r < rows_valid;
         float zz[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) zz[i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) {
+          zz[i] = live ? __uint_as_float(v[i]) : 0.0f;
+          zx[i] = live ? zx[i] : 0.0f;
+          ro[i] = live ? ro[i] : 0.0f;
+        }
         const float sb = lp_warp_colsum(zz, lane), sg = lp_warp_colsum(zx, lane), so = lp_warp_colsum(ro, lane);
         colp[(0 * 4 + quad) * 64 + grp * 32 + lane] = sb;
         colp[(1 * 4 + quad) * 64 + grp * 32 + lane] = sg;
@@ -350,7 +369,8 @@ lnproj_bwd_kernel(const __grid_constant__ CUtensorMap t_dy, const __grid_constan
 // col_partial [3][nblk][d] → dbeta = Σ_blk q0, dgamma = Σ_blk q1, dbias = Σ_blk q2 (any output may be NULL); fixed order.
 // CTA = 32 columns × 8 row groups (each sums a strided subset of the partial rows, coalesced 128 B reads).
 __global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta, float* __restrict__ dbias, int accumulate) {
+                                                                float* __restrict__ dbeta, float* __restrict__ dbias, int accumulate, int tile_offset,
+                                                                int total_tiles) {
   jl::pdl_prologue();
   __shared__ float sm[3][8][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -359,7 +379,7 @@ __global__ void __launch_bounds__(256) lnproj_bwd_reduce_kernel(const float* __r
   if (i < d) {
     for (int k = grp; k < nblk; k += 8) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) acc[q] += partial[(static_cast<int64_t>(q) * nblk + k) * d + i];
+      for (int q = 0; q < 3; ++q) acc[q] += partial[(static_cast<int64_t>(q) * total_tiles + tile_offset + k) * d + i];
     }
   }
 #pragma unroll
@@ -477,12 +497,15 @@ int jl_lnproj_wgrad(float* m0, int64_t ldm, const float* wgrad_partial, int32_t 
   return JL_OK;
 }
 
-int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate, void* stream) {
+int jl_lnproj_bwd_reduce(const float* col_partial, int32_t row_tiles, int32_t d, float* dgamma, float* dbeta, float* dbias, int32_t accumulate,
+                         int32_t tile_offset, int32_t total_tiles, void* stream) {
   JL_REQUIRE(col_partial != nullptr && row_tiles > 0 && d > 0, JL_EINVAL, "lnproj_bwd_reduce: bad arguments");
+  if (total_tiles <= 0) total_tiles = row_tiles;
+  JL_REQUIRE(tile_offset >= 0 && tile_offset + row_tiles <= total_tiles, JL_EINVAL, "lnproj_bwd_reduce: tile range out of bounds");
   int rc = jl::check_device();
   if (rc != JL_OK) return rc;
   jl::launch(jl::lnproj_bwd_reduce_kernel, jl::ceil_div(d, 32), 256, 0, reinterpret_cast<cudaStream_t>(stream), col_partial, row_tiles, d, dgamma, dbeta, dbias,
-             static_cast<int>(accumulate));
+             static_cast<int>(accumulate), static_cast<int>(tile_offset), static_cast<int>(total_tiles));
   JL_CHECK_LAUNCH("lnproj_bwd_reduce");
   return JL_OK;
 }
@@ -496,6 +519,18 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
              "lnproj_bwd: dy_scaled must be 16-byte aligned with a row stride that is a multiple of 8");
   JL_REQUIRE(p->n >= 8 && p->n <= 192 && (p->n % 8) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: n must be a multiple of 8, at most 192 (got %d)", p->n);
   JL_REQUIRE(p->dy_scaled == nullptr || (p->n % 64) == 0, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: dy_scaled needs n to be a multiple of 64 (got %d)", p->n);
+  JL_REQUIRE(p->num_runs >= 0 && p->num_runs <= JL_LNPROJ_MAX_RUNS, JL_EINVAL, "lnproj_bwd: at most %d row runs", JL_LNPROJ_MAX_RUNS);
+  JL_REQUIRE(p->num_runs == 0 || p->dy_scaled == nullptr, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: dy_scaled is not available with row runs");
+  const int w_sets = p->w_sets > 0 ? p->w_sets : 1;
+  int row_tiles = jl::ceil_div(p->rows, 128);
+  if (p->num_runs > 0) {
+    row_tiles = 0;
+    for (int i = 0; i < p->num_runs; ++i) {
+      JL_REQUIRE(p->run_start[i] >= 0 && p->run_start[i + 1] > p->run_start[i] && p->run_start[i + 1] <= p->rows, JL_EINVAL, "lnproj_bwd: run %d is empty or out of range", i);
+      JL_REQUIRE(p->run_set[i] >= 0 && p->run_set[i] < w_sets, JL_EINVAL, "lnproj_bwd: run %d names factor set %d of %d", i, p->run_set[i], w_sets);
+      row_tiles += jl::ceil_div(p->run_start[i + 1] - p->run_start[i], 128);
+    }
+  }
   JL_REQUIRE(p->d >= 64 && (p->d % 64) == 0 && p->d <= jl::LP_MAX_D, JL_EUNSUPPORTED_SHAPE, "lnproj_bwd: d must be a multiple of 64, at most %d (got %d)",
              jl::LP_MAX_D, p->d);
   JL_REQUIRE((p->lddy % 8) == 0 && (p->ldy % 8) == 0 && (p->ldh % 8) == 0 && (p->lddres % 8) == 0 && (p->lddx % 8) == 0 && (p->dz == nullptr || (p->lddz % 8) == 0),
@@ -507,7 +542,7 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
   CUtensorMap t_dy, t_y, t_w, t_h, t_r;
   rc = jl::make_tma_map_2d_bf16(&t_dy, p->dy, p->n, p->rows, p->lddy, 128);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_y, p->y, p->n, p->rows, p->ldy, 128);
-  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->w, p->d, p->n, p->d, (p->n + 63) / 64 * 64);
+  if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_w, p->w, p->d, static_cast<int64_t>(w_sets) * p->n, p->d, (p->n + 63) / 64 * 64);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_h, p->h, p->d, p->rows, p->ldh, 128);
   if (rc == JL_OK) rc = jl::make_tma_map_2d_bf16(&t_r, p->dres, p->d, p->rows, p->lddres, 128);
   if (rc != JL_OK) return rc;
@@ -520,7 +555,6 @@ int jl_lnproj_bwd(const jl_lnproj_bwd_params* p, void* stream) {
     JL_REQUIRE(e == cudaSuccess, JL_ECUDA, "lnproj_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     configured_dev = dev;
   }
-  const int row_tiles = jl::ceil_div(p->rows, 128);
   // Two CTAs per row tile (column halves) make the kernel itself faster (8000 x 768: 12.7 vs 19.9 µs with dz).  Whether the STEP gets
   // faster depends on what runs beside it: with a busy weight-gradient branch (it fills the SMs this kernel leaves idle) the split only
   // repeats the prologue (base config before the column partials: 6.20 vs 6.17 ms; 24-layer config with two adapters per layer: 18.48 vs

@@ -410,6 +410,7 @@ class JLEngine:
         self._wf_fold: Dict[int, list] = {}
         # tail of the WFAdapter backward (dt1 · B_d + LayerNorm backward + column sums) through jl_lnproj_bwd
         self.fused_wf_bwd = os.environ.get("JL_FUSED_WF_BWD", "1") != "0"
+        self.wf_multi_run = os.environ.get("JL_WF_MULTI_RUN", "1") != "0"     # several dialect runs per batch: one jl_lnproj_bwd launch with row runs
         self._wf_bufs: Dict[int, dict] = {}
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
@@ -600,25 +601,22 @@ class JLEngine:
         self._att_bufs[id(ad)] = (ver, bufs)
         return bufs
 
-    def _wf_fold_packs(self, ad) -> list:
+    def _wf_fold_packs(self, ad) -> dict:
         """LayerNorm-fold vectors (s, tb) of the first low-rank projection of every factor set of a WFAdapter (B_d[k] [r, d], no bias),
-        for jl_lnproj_bwd; derived on the device into buffers that keep their addresses (inside a captured step they follow the
-        optimizer)."""
+        for jl_lnproj_bwd: {"k": [per-set dicts], "all": {"s", "tb"} the same vectors as contiguous [K · r] arrays (multi-run calls)}.
+        Derived on the device into buffers that keep their addresses (inside a captured step they follow the optimizer)."""
         w = self._bf16(ad.down_B)
         ent = self._wf_fold.get(id(ad))
-        if ent is not None and self._att_packed_step and all(e is not None for e in ent):
+        if ent is not None and self._att_packed_step:
             return ent             # derived by _att_pack_all at the start of this step's forward pass
         if ent is None:
-            ent = [None] * ad.num_dialects
+            kk, r, d = w.shape
+            s_all = torch.empty((kk, r), dtype=F32, device=w.device)
+            tb_all = torch.empty((kk, r), dtype=F32, device=w.device)
+            scratch = torch.empty((kk, r, d), dtype=BF16, device=w.device)
+            ent = {"all": {"s": s_all.view(-1), "tb": tb_all.view(-1)}, "k": [{"w": scratch[k], "s": s_all[k], "tb": tb_all[k]} for k in range(kk)]}
             self._wf_fold[id(ad)] = ent
-        jobs = []
-        for k in range(ad.num_dialects):
-            if ent[k] is None:
-                ent[k] = ops.lnfold_pack(w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach())
-            else:
-                jobs.append((w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[k]))
-        if jobs:
-            ops.lnfold_pack_multi(jobs)
+        ops.lnfold_pack_multi([(w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent["k"][k]) for k in range(ad.num_dialects)])
         return ent
 
     def _att_pack_all(self) -> None:
@@ -644,11 +642,11 @@ class JLEngine:
                     if ad is None or ad.kind != "wf":
                         continue
                     ent = self._wf_fold.get(id(ad))
-                    if ent is None or any(e is None for e in ent):
+                    if ent is None:
                         continue                                 # first step: allocated (and packed) where they are first needed
                     w = self._bf16(ad.down_B)
                     for k in range(ad.num_dialects):
-                        jobs.append((w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent[k]))
+                        jobs.append((w[k], None, ad.norm.weight.detach(), ad.norm.bias.detach(), ent["k"][k]))
         if jobs:
             ops.lnfold_pack_multi(jobs)
         self._att_packed_step = True
@@ -892,14 +890,20 @@ class JLEngine:
         sb.run(w_down, dpre, t1)
         if jobs is not None:
             jobs.append(dict(dy=dpre, out_sum=g.out(ad.down_bias, k)))
-        dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                       # dpre · A_d
+        if lp is not None and lp.get("dt1_all") is not None:
+            dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN, out=lp["dt1_all"][rows])           # dpre · A_d, into the shared matrix
+        else:
+            dt1 = ops.gemm(dpre, self._bf16(ad.down_A)[k], b_layout=MN)                                   # dpre · A_d
         sb.run(lambda: ops.gemm(dt1, z, a_layout=MN, b_layout=MN, out=g.out(ad.down_B, k), out_dtype=F32), dt1, z)  # dt1ᵀ · z
         if lp is None:
             ops.gemm(dt1, self._bf16(ad.down_B)[k], b_layout=MN, out=dz[rows])                            # dt1 · B_d
             return
+        if lp.get("dt1_all") is not None:
+            lp["runs"].append((rows.start, rows.stop, k))       # the tail of all runs is ONE jl_lnproj_bwd launch, issued by the caller
+            return
         # dt1 · B_d and the LayerNorm backward of these rows in one kernel (jl_lnproj_bwd); its column sums give this factor set's
         # up-projection bias gradient (Σ dy) and this row range's share of the adapter LayerNorm's dγ / dβ
-        _, _, cols = ops.lnproj_bwd(dt1, t1, self._bf16(ad.down_B)[k], lp["packs"][k], ad.norm.weight.detach(), lp["h"][rows], lp["mean"][rows],
+        _, _, cols = ops.lnproj_bwd(dt1, t1, self._bf16(ad.down_B)[k], lp["packs"]["k"][k], ad.norm.weight.detach(), lp["h"][rows], lp["mean"][rows],
                                     lp["rstd"][rows], dy, want_cols=True, out=lp["dh"][rows])
         acc = lp["seen"] > 0
         lp["seen"] += 1
@@ -929,8 +933,14 @@ class JLEngine:
                 spans = [r_ for r_ in spans if r_.stop > r_.start]
                 # one kernel per dialect run: with several runs per layer (the mixed-dialect batch: 4) the extra launches on the main chain
                 # cost more than the side branch saves (14.81 vs 14.73 ms), with one run it pays (24-layer config 18.62 vs 18.96 ms)
-                if len(spans) != 1 or spans[0].stop - spans[0].start != h.shape[0]:
+                if sum(r_.stop - r_.start for r_ in spans) != h.shape[0] or len(spans) == 0 or len(spans) > 8:
                     lp = None
+                elif len(spans) > 1:
+                    if self.wf_multi_run:
+                        # several dialect runs: their tails run as ONE launch over a shared dt1 matrix (row runs with their own factor set)
+                        lp["dt1_all"], lp["runs"] = torch.empty((h.shape[0], ad.rank), dtype=BF16, device=h.device), []
+                    else:
+                        lp = None
             if lp is not None:
                 lp["packs"], lp["dh"] = self._wf_fold_packs(ad), torch.empty_like(h)
             dz = torch.empty_like(h) if lp is None else None
@@ -944,6 +954,21 @@ class JLEngine:
                 if k not in present:
                     for prm in (ad.up_A, ad.up_bias, ad.up_B, ad.down_A, ad.down_bias, ad.down_B):
                         g.out(prm, k).zero_()
+            if lp is not None and lp.get("dt1_all") is not None:
+                w_all = self._bf16(ad.down_B).view(ad.num_dialects * ad.rank, ad.hidden_size)
+                _, _, cols = ops.lnproj_bwd(lp["dt1_all"], t1, w_all, lp["packs"]["all"], ad.norm.weight.detach(), h, mean, rstd, dy, want_cols=True,
+                                            out=lp["dh"], runs=lp["runs"])
+                runs = lp["runs"]
+
+                def reduce_runs(cols=cols, runs=runs):
+                    ops.lnproj_bwd_reduce(cols, g.out(ad.norm.weight), g.out(ad.norm.bias), None)
+                    off = 0
+                    for r0_, r1_, k_ in runs:
+                        nt = (r1_ - r0_ + 127) // 128
+                        ops.lnproj_bwd_reduce(cols, None, None, g.out(ad.up_bias, k_), tile_offset=off, num_tiles=nt)
+                        off += nt
+                sb.run(reduce_runs, cols)
+                lp["seen"] = len(runs)
             if lp is not None:
                 if lp["seen"] == 0:                # no utterance at all: the LayerNorm gradients are zero too
                     g.out(ad.norm.weight).zero_()

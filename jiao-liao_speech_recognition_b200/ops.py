@@ -423,9 +423,10 @@ def attadapter_fwd(h: torch.Tensor, pack: dict, wo: torch.Tensor, bo: torch.Tens
 
 
 def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
-                      accumulate: bool = False) -> None:
+                      accumulate: bool = False, tile_offset: int = 0, num_tiles: Optional[int] = None) -> None:
     """Finish the column sums ``lnproj_bwd(..., want_cols=True)`` left per row tile: dgamma = Σ dz·x̂, dbeta = Σ dz, dbias = Σ dres
-    (fp32 [d] outputs, any may be None), summed in fixed order.  ``accumulate``: add to dgamma / dbeta instead of overwriting them."""
+    (fp32 [d] outputs, any may be None), summed in fixed order.  ``accumulate``: add to dgamma / dbeta instead of overwriting them.
+    ``tile_offset`` / ``num_tiles``: sum only that range of row tiles (one run of a multi-run ``lnproj_bwd``)."""
     _need(col_partial, F32, "col_partial", 3)
     three, tiles, d = col_partial.shape
     if three != 3 or not col_partial.is_contiguous():
@@ -435,12 +436,14 @@ def lnproj_bwd_reduce(col_partial: torch.Tensor, dgamma: Optional[torch.Tensor],
             _need(t_, F32, nm, 1)
             if t_.numel() != d or not t_.is_contiguous():
                 raise ValueError(f"lnproj_bwd_reduce: {nm} must be a contiguous [d] tensor")
-    L.check(L.load().jl_lnproj_bwd_reduce(col_partial.data_ptr(), tiles, d, _ptr(dgamma), _ptr(dbeta), _ptr(dbias), 1 if accumulate else 0, _stream()))
+    n_t = tiles if num_tiles is None else num_tiles
+    L.check(L.load().jl_lnproj_bwd_reduce(col_partial.data_ptr(), n_t, d, _ptr(dgamma), _ptr(dbeta), _ptr(dbias), 1 if accumulate else 0, tile_offset, tiles,
+                                          _stream()))
 
 
 def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, gamma: torch.Tensor, h: torch.Tensor, mean: torch.Tensor,
                rstd: torch.Tensor, dres: torch.Tensor, want_dz: bool = False, want_cols: bool = False, want_wgrad_operands: bool = False,
-               out: Optional[torch.Tensor] = None, col_split: int = 0):
+               out: Optional[torch.Tensor] = None, col_split: int = 0, runs: Optional[list] = None):
     """Backward through LayerNorm → projection (W [n, d], n a multiple of 8, at most 192) in one kernel: dx = LayerNorm'(dy · W) + dres.
     ``y`` = the projection output saved by the forward pass, ``pack`` = ``lnfold_pack`` of this projection.  → (dx, dz | None);
     dz = dy · W (bf16) only when ``want_dz``.  ``want_cols``: → (dx, dz | None, col_partial [3, ⌈rows/128⌉, d] fp32) — per-row-tile column
@@ -454,7 +457,17 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
         _rows2d(t_, nm)
     rows, n = dy.shape
     d = h.shape[1]
-    if y.shape != (rows, n) or w.shape != (n, d) or not w.is_contiguous() or h.shape[0] != rows or dres.shape != (rows, d):
+    w_sets = 1
+    if runs is not None:
+        # ``runs`` = [(row_start, row_end, set)]: row ranges in ascending order, each with its own block of w ([sets · n, d]) and of
+        # pack["s"] / pack["tb"] ([sets · n]); row tiles never straddle a run; col_partial gets one row per tile of every run
+        if w.shape[0] % n or w.shape[1] != d or len(runs) == 0 or len(runs) > 8:
+            raise ValueError("lnproj_bwd: with runs, w must be [sets * n, d] and 1..8 runs given")
+        w_sets = w.shape[0] // n
+        w_ok = True
+    else:
+        w_ok = w.shape == (n, d)
+    if y.shape != (rows, n) or not w_ok or not w.is_contiguous() or h.shape[0] != rows or dres.shape != (rows, d):
         raise ValueError("lnproj_bwd: shapes do not match")
     if out is None:
         dx = torch.empty((rows, d), dtype=BF16, device=h.device)
@@ -469,7 +482,15 @@ def lnproj_bwd(dy: torch.Tensor, y: torch.Tensor, w: torch.Tensor, pack: dict, g
                           tb=pack["tb"].data_ptr(), gamma=gamma.data_ptr(), h=h.data_ptr(), ldh=h.stride(0), mean=mean.data_ptr(),
                           rstd=rstd.data_ptr(), dres=dres.data_ptr(), lddres=dres.stride(0), dx=dx.data_ptr(), lddx=dx.stride(0),
                           dz=_ptr(dz), lddz=dz.stride(0) if dz is not None else 0, rows=rows, n=n, d=d)
-    cols = torch.empty((3, (rows + 127) // 128, d), dtype=F32, device=h.device) if want_cols else None
+    tiles = (rows + 127) // 128
+    if runs is not None:
+        tiles = sum((e - s_ + 127) // 128 for s_, e, _ in runs)
+        p.num_runs, p.w_sets = len(runs), w_sets
+        for i, (s_, e, k_) in enumerate(runs):
+            p.run_start[i], p.run_start[i + 1], p.run_set[i] = s_, e, k_
+            if i and s_ != runs[i - 1][1]:
+                raise ValueError("lnproj_bwd: runs must be adjacent row ranges in ascending order")
+    cols = torch.empty((3, tiles, d), dtype=F32, device=h.device) if want_cols else None
     p.col_partial = _ptr(cols)
     p.col_split = col_split
     dys = wpart = None

@@ -737,3 +737,48 @@ def test_lnfold_pack_multi_equals_single_packs():
     for (w, bias, gamma, beta, bufs), ref in zip(jobs, singles):
         for k in ("w", "s", "tb"):
             assert torch.equal(bufs[k], ref[k]), k
+
+
+def test_lnproj_bwd_row_runs_equal_one_call_per_run():
+    """jl_lnproj_bwd with row runs (the dialect runs of a WFAdapter: every run its own factor set of w / s / tb, row tiles never
+    straddle a run) == one call per run on the row slices: dx bit for bit, the summed column partials to fp32 accuracy."""
+    P = pkg()
+    ops = P.ops
+    g = _g(51)
+    d, n, sets = 768, 32, 4
+    runs = [(0, 300, 2), (300, 429, 0), (429, 1500, 3)]                  # set 1 absent; lengths not multiples of 128
+    rows = runs[-1][1]
+    h = (torch.randn(rows, d, device="cuda", generator=g) * 1.2 + 0.2).to(BF16)
+    w = (torch.randn(sets, n, d, device="cuda", generator=g) * 0.07).to(BF16)
+    gamma = 1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    dy = (torch.randn(rows, n, device="cuda", generator=g) * 0.5).to(BF16)
+    y = (torch.randn(rows, n, device="cuda", generator=g)).to(BF16)
+    dres = (torch.randn(rows, d, device="cuda", generator=g) * 0.3).to(BF16)
+    _, mean, rstd = ops.layernorm_fwd(h, gamma, beta, 1e-5, save_stats=True)
+    s_all = torch.empty(sets, n, device="cuda")
+    tb_all = torch.empty(sets, n, device="cuda")
+    packs = [ops.lnfold_pack(w[k], None, gamma, beta, {"w": torch.empty_like(w[k]), "s": s_all[k], "tb": tb_all[k]}) for k in range(sets)]
+    dx, _, cols = ops.lnproj_bwd(dy, y, w.view(sets * n, d), {"s": s_all.view(-1), "tb": tb_all.view(-1)}, gamma, h, mean, rstd, dres,
+                                 want_cols=True, runs=runs)
+    dg, db = torch.empty(d, device="cuda"), torch.empty(d, device="cuda")
+    ops.lnproj_bwd_reduce(cols, dg, db, None)
+    ref_dx = torch.empty_like(dx)
+    dg_ref, db_ref = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    off = 0
+    for i, (r0, r1, k) in enumerate(runs):
+        sl = slice(r0, r1)
+        _, _, c_k = ops.lnproj_bwd(dy[sl], y[sl], w[k], packs[k], gamma, h[sl], mean[sl], rstd[sl], dres[sl], want_cols=True, out=ref_dx[sl])
+        a, b_, o_ref, o = (torch.empty(d, device="cuda") for _ in range(4))
+        ops.lnproj_bwd_reduce(c_k, a, b_, o_ref)
+        dg_ref += a
+        db_ref += b_
+        nt = (r1 - r0 + 127) // 128
+        ops.lnproj_bwd_reduce(cols, None, None, o, tile_offset=off, num_tiles=nt)
+        off += nt
+        torch.cuda.synchronize()
+        assert rel_err(o, o_ref) < 1e-6 and rel_err(o, dres[sl].float().sum(0)) < 1e-5, i
+    torch.cuda.synchronize()
+    assert cols.shape[1] == off
+    assert torch.equal(dx, ref_dx)
+    assert rel_err(dg, dg_ref) < 1e-5 and rel_err(db, db_ref) < 1e-5
